@@ -1,0 +1,136 @@
+"""ctypes binding of libgracing.so (include/gracing.h).  There is NO CPU fallback: importing
+:func:`load` without the built CUDA library raises, and every entry point needs device pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import layout as L
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgracing.so")
+
+c_f = C.c_float
+c_i = C.c_int32
+c_p = C.c_void_p
+
+
+class GrConfig(C.Structure):
+    _fields_ = [
+        ("dt", c_f), ("max_episode_length", c_i), ("gravity", c_f), ("grad_decay", c_f), ("inertia", c_f * 3),
+        ("action_scale0", c_f), ("body_rate_bound", c_f), ("thrust_lo", c_f), ("thrust_hi", c_f), ("update_threshold", c_f),
+        ("drag1", c_f), ("drag1_rand", c_f), ("drag2", c_f), ("drag2_rand", c_f), ("z_drag", c_f), ("z_drag_rand", c_f),
+        ("random_drag", c_i), ("thr_err_reset_std", c_f), ("thr_err_init_std", c_f),
+        ("default_pos", c_f * 3), ("reset_pos", c_f), ("reset_roll_pitch", c_f), ("reset_yaw", c_f), ("reset_vel", c_f),
+        ("kp", c_f * 3), ("kd", c_f * 3), ("thrust_delay", c_f), ("torque_delay", c_f * 3),
+        ("pid_scale_lo", c_f), ("pid_scale_span", c_f), ("delay_scale_lo", c_f), ("delay_scale_span", c_f),
+        ("mass", c_f), ("max_init_level", c_i),
+        ("term_oob", c_i), ("term_bad_pose", c_i), ("oob_lo", c_f), ("oob_hi", c_f),
+        ("w_reward", c_f * L.NUM_REWARD_TERMS),
+        ("add_cmd_noise", c_i), ("cmd_noise_pos", c_f), ("cmd_noise_yaw", c_f),
+        ("level_up_gates", c_i), ("level_down_gates", c_i),
+        ("noise_curriculum", c_i), ("noise_up_gates", c_i), ("noise_down_gates", c_i), ("noise_up", c_f), ("noise_down", c_f),
+        ("w_loss", c_f * 3), ("obs_vel_noise", c_f), ("obs_euler_noise", c_f),
+    ]
+
+
+class GrTrack(C.Structure):
+    _fields_ = [("rows", c_p), ("types", c_i), ("levels", c_i), ("gates", c_i)]
+
+
+class GrState(C.Structure):
+    _fields_ = [("planes", c_p), ("plane_stride", C.c_int64), ("num_envs", c_i), ("num_planes", c_i),
+                ("env_id_offset", c_i), ("max_types_per_block", c_i), ("chunk_types", c_p)]
+
+
+class GrRandom(C.Structure):
+    _fields_ = [("rnd", c_p), ("seed", C.c_uint64), ("step", C.c_uint32)]
+
+
+class GrStepIO(C.Structure):
+    _fields_ = [("action", c_p), ("obs", c_p), ("critic_obs", c_p), ("aux_obs", c_p), ("reward", c_p),
+                ("terminated", c_p), ("time_out", c_p), ("dones", c_p), ("reward_terms", c_p), ("gate_passed", c_p),
+                ("loss", c_p), ("loss_terms", c_p), ("tape", c_p), ("tape_stride", C.c_int64), ("log_accum", c_p)]
+
+
+class GrBwdIO(C.Structure):
+    _fields_ = [("tape", c_p), ("tape_stride", C.c_int64), ("t_begin", c_i), ("t_end", c_i), ("grad_loss", c_p),
+                ("grad_scale", c_f), ("adjoint", c_p), ("adj_stride", C.c_int64), ("grad_action", c_p)]
+
+
+class GrTransition(C.Structure):
+    _fields_ = [("obs", c_p), ("critic_obs", c_p), ("actions", c_p), ("rewards", c_p), ("dones", c_p), ("dones_is_int64", c_i),
+                ("values", c_p), ("log_prob", c_p), ("mu", c_p), ("sigma", c_p), ("time_outs", c_p), ("gamma", c_f)]
+
+
+class GrStorage(C.Structure):
+    _fields_ = [("obs", c_p), ("critic_obs", c_p), ("actions", c_p), ("rewards", c_p), ("dones", c_p), ("values", c_p),
+                ("log_prob", c_p), ("mu", c_p), ("sigma", c_p), ("returns", c_p), ("advantages", c_p),
+                ("T", c_i), ("N", c_i), ("obs_dim", c_i), ("critic_dim", c_i), ("act_dim", c_i)]
+
+
+class GrMiniBatch(C.Structure):
+    _fields_ = [("obs", c_p), ("critic_obs", c_p), ("actions", c_p), ("values", c_p), ("advantages", c_p), ("returns", c_p),
+                ("log_prob", c_p), ("mu", c_p), ("sigma", c_p)]
+
+
+GR_LOG_SLOTS = 16
+STATUS = {0: "GR_OK", -1: "GR_ERR_NULL", -2: "GR_ERR_SIZE", -3: "GR_ERR_ALIGN", -4: "GR_ERR_CONFIG", -5: "GR_ERR_SMEM"}
+
+# symbol -> (restype, argtypes); every symbol include/gracing.h declares
+PROTOTYPES = {
+    "gr_abi_version": (C.c_int, []),
+    "gr_env_startup": (C.c_int, [C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), c_p, c_p, c_p, C.c_uint64, c_p]),
+    "gr_env_reset": (C.c_int, [C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom), c_p, c_p, c_p, c_p, c_p]),
+    "gr_env_observe": (C.c_int, [C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom), c_p, c_p, c_p, c_p]),
+    "gr_step_fwd": (C.c_int, [C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom), C.POINTER(GrStepIO), c_p]),
+    "gr_step_bwd": (C.c_int, [C.POINTER(GrConfig), C.POINTER(GrState), C.POINTER(GrBwdIO), c_p]),
+    "gr_fill_rand": (C.c_int, [c_p, c_i, c_i, C.c_uint64, C.c_uint32, c_p]),
+    "gr_fill_startup_rand": (C.c_int, [c_p, c_i, c_i, C.c_uint64, c_p]),
+    "gr_storage_add": (C.c_int, [C.POINTER(GrStorage), C.POINTER(GrTransition), c_i, c_p]),
+    "gr_gae_scratch_bytes": (C.c_int64, [c_i]),
+    "gr_compute_returns": (C.c_int, [C.POINTER(GrStorage), c_p, c_f, c_f, c_p, c_p, c_i, c_p]),
+    "gr_advantage_normalize": (C.c_int, [C.POINTER(GrStorage), c_p, c_p]),
+    "gr_storage_gather": (C.c_int, [C.POINTER(GrStorage), c_p, c_i, C.POINTER(GrMiniBatch), c_p]),
+}
+
+
+class GracingError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    if rc < 0:
+        raise GracingError(f"{what}: {STATUS.get(rc, rc)}")
+    raise GracingError(f"{what}: CUDA error {rc} at launch")
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libgracing.so and bind every prototype.  Raises if the library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the racing hot path has no CPU fallback. Build the sm_100a library with "
+            "`python -m generalizableracing_b200.build` (or __graft_entry__.build()).")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    if lib.gr_abi_version() != 1:
+        raise ImportError("libgracing.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a torch tensor (None stays NULL)."""
+    return None if t is None else t.data_ptr()

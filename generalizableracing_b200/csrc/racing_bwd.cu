@@ -1,0 +1,199 @@
+// racing_bwd.cu -- analytic reverse sweep of the racing step over a BPTT window (one thread per env,
+// adjoints in registers across the whole horizon, tape streamed from HBM with a one-step prefetch).
+//
+// Replaces torch.autograd through DroneDynamics.step/align (QD/mdp/dynamics/droneDynamics.py:119-181),
+// CTBRController.compute (L/controllers/controller_diff.py:120-138) and the tanh action map with 1-step lag
+// (QD/mdp/diff_action.py:160-176), driven by BPTT.update (standalone/diff_rl/algorithms/bptt.py:38-44).
+// Derivation: SURVEY.md Appendix A.6; the quaternion Jacobians differentiate the *literal* Isaac Lab
+// formulas (gr_math.cuh), not rotation matrices.
+//
+// Tape per env-step, written by racing_step.cu (7 float4 planes):
+//   0: q (pre-step)          1: omega_b | A0      2: F_b | A1      3: D | A2
+//   4: v' | A3               5: omega_b' | cut    6: dloss/dP | -
+//   A0 = dF'/da_lag[0] = clampmask*thr_err*scale0*(1-tanh^2)*(1-e_f);  A_i = dtau'_i/da_lag[i]
+//   D  = dF_b/dv_b (diagonal) = -(2 k2 |v_b| + k1);  cut = env state at the start of the step was fresh from a reset
+#include "gr_common.cuh"
+
+namespace gr {
+
+struct QAdj { float w; V3 u; };
+
+// adjoint of y = quat_rotate(q, v) w.r.t. q
+__device__ __forceinline__ QAdj rot_q_adj(Q4 q, V3 v, V3 yb) {
+  const V3 u = v3(q.x, q.y, q.z);
+  const V3 uxv = cross(u, v);
+  const float wb = dot(yb, 4.0f * q.w * v + 2.0f * uxv);
+  const V3 ub = 2.0f * q.w * cross(v, yb) + 2.0f * dot(u, v) * yb + 2.0f * dot(u, yb) * v;
+  return QAdj{wb, ub};
+}
+// adjoint of y = quat_rotate_inverse(q, v) w.r.t. q
+__device__ __forceinline__ QAdj rotinv_q_adj(Q4 q, V3 v, V3 yb) {
+  const V3 u = v3(q.x, q.y, q.z);
+  const V3 uxv = cross(u, v);
+  const float wb = dot(yb, 4.0f * q.w * v - 2.0f * uxv);
+  const V3 ub = -2.0f * q.w * cross(v, yb) + 2.0f * dot(u, v) * yb + 2.0f * dot(u, yb) * v;
+  return QAdj{wb, ub};
+}
+
+constexpr int kBwdBlock = 128;
+
+__global__ void __launch_bounds__(kBwdBlock) racing_step_bwd_kernel(const GrConfig cfg, const GrState st, const GrBwdIO io) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= st.num_envs) return;
+  const float4* __restrict__ P = reinterpret_cast<const float4*>(st.planes);
+  const int64_t S = st.plane_stride;
+  const float m = __ldg(&P[(int64_t)PL_DRAG2 * S + i]).w;
+  const float ef = __ldg(&P[(int64_t)PL_DRAG1 * S + i]).w;
+  const V3 etau = xyz(__ldg(&P[(int64_t)PL_ETAU * S + i]));
+  const V3 J = v3(cfg.inertia[0], cfg.inertia[1], cfg.inertia[2]);
+  const V3 Jinv = v3(1.0f / J.x, 1.0f / J.y, 1.0f / J.z);
+  const float dt = cfg.dt, decay = cfg.grad_decay;
+  const float wv = cfg.w_loss[1] * (2.0f / 3.0f);
+
+  float4* __restrict__ A = reinterpret_cast<float4*>(io.adjoint);
+  const int64_t AS = io.adj_stride;
+  float4 a0 = A[0 * AS + i], a1 = A[1 * AS + i], a2 = A[2 * AS + i], a3 = A[3 * AS + i], a4 = A[4 * AS + i];
+  V3 lP = xyz(a0); float lF = a0.w;
+  Q4 lQ = quat(a1);
+  V3 lV = xyz(a2), lVb = xyz(a3), lWb = xyz(a4);
+  V3 lTau = v3(a2.w, a3.w, a4.w);
+
+  const float4* __restrict__ T = reinterpret_cast<const float4*>(io.tape);
+  const int64_t TS = io.tape_stride;
+  const int N = st.num_envs;
+
+  float4 nx[GR_TAPE_PLANES];
+  float ng = io.grad_scale;
+  if (io.t_end > io.t_begin) {
+    const int t = io.t_end - 1;
+#pragma unroll
+    for (int k = 0; k < GR_TAPE_PLANES; ++k) nx[k] = __ldcs(T + ((int64_t)t * GR_TAPE_PLANES + k) * TS + i);
+    if (io.grad_loss) ng = __ldg(io.grad_loss + (int64_t)t * N + i);
+  }
+
+  for (int t = io.t_end - 1; t >= io.t_begin; --t) {
+    float4 c[GR_TAPE_PLANES];
+#pragma unroll
+    for (int k = 0; k < GR_TAPE_PLANES; ++k) c[k] = nx[k];
+    const float g = ng;
+    if (t - 1 >= io.t_begin) {     // prefetch the next (earlier) step while this one is processed
+#pragma unroll
+      for (int k = 0; k < GR_TAPE_PLANES; ++k) nx[k] = __ldcs(T + ((int64_t)(t - 1) * GR_TAPE_PLANES + k) * TS + i);
+      if (io.grad_loss) ng = __ldg(io.grad_loss + (int64_t)(t - 1) * N + i);
+    }
+    const Q4 q = quat(c[0]);
+    const V3 om_b = xyz(c[1]); const float A0 = c[1].w;
+    const V3 F_b = xyz(c[2]);
+    const V3 D = xyz(c[3]);
+    const V3 v1 = xyz(c[4]);
+    const V3 Again = v3(c[2].w, c[3].w, c[4].w);
+    const V3 omb1 = xyz(c[5]); const bool cut = __float_as_uint(c[5].w) != 0u;
+    const V3 dLdP = xyz(c[6]);
+
+    // loss gradient of this step (QD/mdp/losses.py:72-80,95-101,111-117), captured before the reset detach
+    lP = lP + g * dLdP;
+    lV = lV + (g * wv) * v1;
+
+    // recompute q' and omega_w' (droneDynamics.py:129-134)
+    const Q4 dq = quat_mul(q, Q4{0.f, om_b.x, om_b.y, om_b.z});
+    const Q4 qt = Q4{q.w + 0.5f * dq.w * dt, q.x + 0.5f * dq.x * dt, q.y + 0.5f * dq.y * dt, q.z + 0.5f * dq.z * dt};
+    const float qn = sqrtf(qt.w * qt.w + qt.x * qt.x + qt.y * qt.y + qt.z * qt.z);
+    const Q4 q1 = Q4{qt.w / qn, qt.x / qn, qt.y / qn, qt.z / qn};
+    const V3 omw1 = quat_rotate(q1, omb1);
+
+    // align (droneDynamics.py:174-179): d/d nominal = decay * d/d aligned
+    const V3 p1b = decay * lP;
+    float q1b_w = decay * lQ.w; V3 q1b_u = decay * v3(lQ.x, lQ.y, lQ.z);
+    V3 v1b = decay * lV;
+    {   // aligned v_b = rotinv(q', v')
+      const V3 yb = decay * lVb;
+      v1b = v1b + quat_rotate(q1, yb);
+      const QAdj a = rotinv_q_adj(q1, v1, yb);
+      q1b_w += a.w; q1b_u = q1b_u + a.u;
+    }
+    V3 omw1b;
+    {   // aligned omega_b = rotinv(q', omega_w')
+      const V3 yb = decay * lWb;
+      omw1b = quat_rotate(q1, yb);
+      const QAdj a = rotinv_q_adj(q1, omw1, yb);
+      q1b_w += a.w; q1b_u = q1b_u + a.u;
+    }
+    // omega_w' = rot(q', omega_b')
+    const V3 omb1b = quat_rotate_inverse(q1, omw1b);
+    {
+      const QAdj a = rot_q_adj(q1, omb1, omw1b);
+      q1b_w += a.w; q1b_u = q1b_u + a.u;
+    }
+    // omega_b' = omega_b + alpha dt ; v' = v + a dt ; p' = p + v dt + 0.5 a dt^2
+    V3 ombb = omb1b;
+    const V3 alphab = dt * omb1b;
+    const V3 vb_w = v1b + dt * p1b;                     // adjoint of v (world)
+    const V3 accb = dt * v1b + (0.5f * dt * dt) * p1b;
+    const V3 pb = p1b;
+    // q' = qt / |qt|
+    const float qdot = q1.w * q1b_w + q1.x * q1b_u.x + q1.y * q1b_u.y + q1.z * q1b_u.z;
+    const float tb_w = (q1b_w - q1.w * qdot) / qn;
+    const V3 tb_u = v3((q1b_u.x - q1.x * qdot) / qn, (q1b_u.y - q1.y * qdot) / qn, (q1b_u.z - q1.z * qdot) / qn);
+    // qt = q + 0.5 dt * qmul(q, (0, omega_b))
+    float qb_w = tb_w; V3 qb_u = tb_u;
+    {
+      const float ow = 0.5f * dt * tb_w; const V3 o = (0.5f * dt) * tb_u;
+      qb_w += o.x * om_b.x + o.y * om_b.y + o.z * om_b.z;
+      qb_u.x += -ow * om_b.x - o.y * om_b.z + o.z * om_b.y;
+      qb_u.y += -ow * om_b.y + o.x * om_b.z - o.z * om_b.x;
+      qb_u.z += -ow * om_b.z - o.x * om_b.y + o.y * om_b.x;
+      ombb.x += -ow * q.x + o.x * q.w + o.y * q.z - o.z * q.y;
+      ombb.y += -ow * q.y - o.x * q.z + o.y * q.w + o.z * q.x;
+      ombb.z += -ow * q.z + o.x * q.y - o.y * q.x + o.z * q.w;
+    }
+    // a = g + rot(q, F_b)/m
+    const V3 yb = accb / m;
+    const V3 Fb = quat_rotate_inverse(q, yb);
+    {
+      const QAdj a = rot_q_adj(q, F_b, yb);
+      qb_w += a.w; qb_u = qb_u + a.u;
+    }
+    // alpha = Jinv*tau' - Jinv*(omega_b x J omega_b)
+    const V3 taub = lTau + Jinv * alphab;
+    {
+      const V3 z = -(Jinv * alphab);
+      ombb = ombb + cross(J * om_b, z) + J * cross(z, om_b);
+    }
+    // F_b = f' e_z - k2 v_b |v_b| - k1 v_b
+    const float fb = lF + Fb.z;
+    const V3 vbb = D * Fb;
+    // controller filters + action map (controller_diff.py:128-135; diff_action.py:174-176); 1-step lag -> a_{t-1}
+    if (t >= 1) {
+      reinterpret_cast<float4*>(io.grad_action)[(int64_t)(t - 1) * N + i] =
+          make_float4(A0 * fb, Again.x * taub.x, Again.y * taub.y, Again.z * taub.z);
+    }
+    if (cut) {     // state at the start of step t came from a reset: nothing flows further back
+      lP = v3(0.f, 0.f, 0.f); lQ = Q4{0.f, 0.f, 0.f, 0.f}; lV = lP; lVb = lP; lWb = lP; lF = 0.f; lTau = lP;
+    } else {
+      lP = pb; lQ = Q4{qb_w, qb_u.x, qb_u.y, qb_u.z}; lV = vb_w; lVb = vbb; lWb = ombb;
+      lF = ef * fb; lTau = etau * taub;
+    }
+  }
+  A[0 * AS + i] = pack(lP, lF);
+  A[1 * AS + i] = pack(lQ);
+  A[2 * AS + i] = pack(lV, lTau.x);
+  A[3 * AS + i] = pack(lVb, lTau.y);
+  A[4 * AS + i] = pack(lWb, lTau.z);
+}
+
+}  // namespace gr
+
+#ifndef GR_CPU_EMUL
+using namespace gr;
+
+extern "C" int gr_step_bwd(const GrConfig* cfg, const GrState* st, const GrBwdIO* io, void* stream) {
+  if (!cfg || !st || !io || !st->planes || !io->tape || !io->adjoint || !io->grad_action) return GR_ERR_NULL;
+  if (st->num_envs <= 0 || st->plane_stride < st->num_envs || io->tape_stride < st->num_envs || io->adj_stride < st->num_envs) return GR_ERR_SIZE;
+  if (io->t_begin < 0 || io->t_end < io->t_begin) return GR_ERR_SIZE;
+  auto mis = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; };
+  if (mis(st->planes) || mis(io->tape) || mis(io->adjoint) || mis(io->grad_action)) return GR_ERR_ALIGN;
+  const int grid = (st->num_envs + kBwdBlock - 1) / kBwdBlock;
+  racing_step_bwd_kernel<<<grid, kBwdBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*cfg, *st, *io);
+  return (int)cudaGetLastError();
+}
+#endif  // GR_CPU_EMUL

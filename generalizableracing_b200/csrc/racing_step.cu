@@ -1,0 +1,673 @@
+// racing_step.cu -- one fused sm_100a kernel per env.step() of the racing task (one thread per env).
+//
+// Reference path replaced (relative to the reference root; QD = extensions/diff.lab_tasks/diff/
+// lab_tasks/tasks/quadcopter_diff, L = extensions/diff.lab/diff/lab): the ~700 eager aten launches of
+// ManagerBasedDiffRLEnv.step (L/envs/manager_based_diff_rl_env.py:160-267).  Section comments carry the
+// file:line of what each block computes.  Data layout: SoA of float4 "planes" (see gr_common.cuh);
+// every persistent column is read once and written once per step with 128-bit coalesced accesses; the
+// gate table slice of the block's terrain types is staged in shared memory.
+#include "gr_common.cuh"
+
+namespace gr {
+
+struct EnvRegs {
+  Q4 q; V3 w; float f; V3 v; int eplen; V3 om; uint32_t pk; V3 tau; V3 aacc; float4 fifo;
+  V3 k2; float m; V3 k1; float ef; V3 kp; float thr; V3 kd; V3 etau;
+  V3 dcur, dnext; float noise_hi, noise_level;
+  float aux;      // last cross_obs value (RewardManager._step_reward survives resets)
+};
+
+template <bool kNoise>
+__device__ __forceinline__ void load_env(EnvRegs& e, const float4* __restrict__ P, int64_t S, int i) {
+  const float4 a0 = ld_plane(P, S, PL_QUAT, i), a1 = ld_plane(P, S, PL_POS, i), a2 = ld_plane(P, S, PL_LINVEL, i),
+               a3 = ld_plane(P, S, PL_ANGVEL, i), a4 = ld_plane(P, S, PL_TORQUE, i), a5 = ld_plane(P, S, PL_ANGACC, i),
+               a6 = ld_plane(P, S, PL_FIFO, i);
+  const float4 c0 = ld_plane_ro(P, S, PL_DRAG2, i), c1 = ld_plane_ro(P, S, PL_DRAG1, i), c2 = ld_plane_ro(P, S, PL_KP, i),
+               c3 = ld_plane_ro(P, S, PL_KD, i), c4 = ld_plane_ro(P, S, PL_ETAU, i);
+  e.q = quat(a0); e.w = xyz(a1); e.f = a1.w; e.v = xyz(a2); e.eplen = __float_as_int(a2.w);
+  e.om = xyz(a3); e.pk = __float_as_uint(a3.w); e.tau = xyz(a4); e.aux = a4.w; e.aacc = xyz(a5); e.fifo = a6;
+  e.k2 = xyz(c0); e.m = c0.w; e.k1 = xyz(c1); e.ef = c1.w; e.kp = xyz(c2); e.thr = c2.w; e.kd = xyz(c3); e.etau = xyz(c4);
+  if (kNoise) {
+    const float4 n0 = ld_plane_ro(P, S, PL_NOISE0, i), n1 = ld_plane_ro(P, S, PL_NOISE1, i);
+    e.dcur = xyz(n0); e.dnext = v3(n0.w, n1.x, n1.y); e.noise_hi = n1.z; e.noise_level = n1.w;
+  } else {
+    e.dcur = v3(0.f, 0.f, 0.f); e.dnext = v3(0.f, 0.f, 0.f); e.noise_hi = 0.f; e.noise_level = 1.f;
+  }
+}
+
+__device__ __forceinline__ float4 tanh4(float4 a) { return make_float4(tanhf(a.x), tanhf(a.y), tanhf(a.z), tanhf(a.w)); }
+
+// F.cosine_similarity(a, b, dim=-1, eps=1e-8): sum((a/max(|a|,eps)) * (b/max(|b|,eps)))
+__device__ __forceinline__ float cosine_similarity(V3 a, V3 b) {
+  const float na = fmaxf(norm(a), 1e-8f), nb = fmaxf(norm(b), 1e-8f);
+  const V3 x = a / na, y = b / nb;
+  return x.x * y.x + x.y * y.y + x.z * y.z;
+}
+
+// noise offsets of QD/mdp/commands.py:287-289: lo + r*(hi - lo), lo = -hi
+__device__ __forceinline__ V3 gate_noise(float hi, float u0, float u1, float u2) {
+  const float lo = -hi, span = hi - lo;
+  return v3(lo + u0 * span, lo + u1 * span, lo + u2 * span);
+}
+
+// policy / critic / auxiliary observations (QD/racing_ctbr_env.py:139-174, QD/mdp/observation.py:22-104)
+template <bool kNoise>
+__device__ __forceinline__ void write_observations(const GrConfig& cfg, const EnvRegs& e, V3 origin, V3 gate_rel, V3 next_rel,
+                                                   float4 th_lag, float4 n01, float4 n23, float aux, int i,
+                                                   float* __restrict__ obs, float* __restrict__ critic, float* __restrict__ aux_out) {
+  const V3 vb = quat_rotate_inverse(e.q, e.v);
+  const V3 g_gt = gate_rel + origin, gn_gt = next_rel + origin;
+  // modified_last_action (:55-63): ctbr of the lagged raw action, thrust / mass
+  float4 ctbr = make_float4(th_lag.x * cfg.action_scale0 + cfg.action_scale0, th_lag.y * cfg.body_rate_bound + 0.0f,
+                            th_lag.z * cfg.body_rate_bound + 0.0f, th_lag.w * cfg.body_rate_bound + 0.0f);
+  ctbr.x = ctbr.x / e.m;
+  // policy: noisy lin vel (:52), noisy attitude row (:27-32), command w.r.t. the noisy gates (commands.py:208-219)
+  const V3 vn = v3(vb.x * (1.0f + n01.x * cfg.obs_vel_noise), vb.y * (1.0f + n01.y * cfg.obs_vel_noise),
+                   vb.z * (1.0f + n01.z * cfg.obs_vel_noise));
+  const Q4 qn = quat_from_euler_xyz(n01.w * cfg.obs_euler_noise, n23.x * cfg.obs_euler_noise, n23.y * cfg.obs_euler_noise);
+  const V3 rn = rotmat_row2(quat_mul(e.q, qn));
+  V3 g_pol = g_gt, gn_pol = gn_gt;
+  if (kNoise) { g_pol = g_gt + e.dcur; gn_pol = gn_gt + e.dnext; }
+  const V3 c0 = quat_rotate_inverse(e.q, g_pol - e.w), c1 = quat_rotate_inverse(e.q, gn_pol - g_pol);
+  float4* o = reinterpret_cast<float4*>(obs) + (int64_t)i * 4;
+  __stcs(o + 0, make_float4(vn.x, vn.y, vn.z, rn.x));
+  __stcs(o + 1, make_float4(rn.y, rn.z, c0.x, c0.y));
+  __stcs(o + 2, make_float4(c0.z, c1.x, c1.y, c1.z));
+  __stcs(o + 3, ctbr);
+  if (critic) {
+    const V3 r = rotmat_row2(e.q);
+    const V3 d0 = quat_rotate_inverse(e.q, g_gt - e.w), d1 = quat_rotate_inverse(e.q, gn_gt - g_gt);
+    float4* c = reinterpret_cast<float4*>(critic) + (int64_t)i * 4;
+    __stcs(c + 0, make_float4(vb.x, vb.y, vb.z, r.x));
+    __stcs(c + 1, make_float4(r.y, r.z, d0.x, d0.y));
+    __stcs(c + 2, make_float4(d0.z, d1.x, d1.y, d1.z));
+    __stcs(c + 3, ctbr);
+  }
+  if (aux_out) aux_out[i] = aux;
+}
+
+// _reset_idx for one env (L/envs/manager_based_diff_rl_env.py:362-410): curricula, root-state sampler,
+// controller/dynamics/command reset.  Mutates e; returns the new origin.
+template <bool kNoise, bool kPhilox>
+__device__ __forceinline__ V3 reset_env(const GrConfig& cfg, const TrackSmem& tr, EnvRegs& e, const RandSrc<kPhilox>& rs, float thr_normal) {
+  const int type = (int)pk_type(e.pk);
+  int level = (int)pk_level(e.pk);
+  const int acc = (int)pk_acc(e.pk);
+  const float4 u_pose0 = rs.get4(2), u_pose1 = rs.get4(3), u_vel = rs.get4(4), u_d0 = rs.get4(5), u_d1 = rs.get4(6);
+  // -- terrain curriculum (QD/mdp/curriculums.py:25-38 + TerrainImporter.update_env_origins)
+  {
+    const int lv = level + (acc >= cfg.level_up_gates ? 1 : 0) - (acc < cfg.level_down_gates ? 1 : 0);
+    int rand_lv = (int)floorf(u_d1.w * (float)tr.levels);          // slot 27
+    if (rand_lv > tr.levels - 1) rand_lv = tr.levels - 1;
+    level = (lv >= tr.levels) ? rand_lv : (lv < 0 ? 0 : lv);
+  }
+  // -- command-noise curriculum (QD/mdp/curriculums.py:40-54, QD/mdp/commands.py:385-402)
+  if (kNoise && cfg.noise_curriculum) {
+    const float up = acc >= cfg.noise_up_gates ? cfg.noise_up : 1.0f;
+    const float down = acc < cfg.noise_down_gates ? cfg.noise_down : 1.0f;
+    e.noise_level *= up; e.noise_level *= down;
+    e.noise_hi *= up; e.noise_hi *= down;
+  }
+  const float4 orow = tr.origin_row(type, level);
+  const V3 origin = xyz(orow);
+  const int start_gate = __float_as_int(orow.w);
+  // -- reset_root_state_racing (QD/mdp/events.py:139-177): slots 8..13 pose, 14..19 velocity
+  const float sp = cfg.reset_pos - (-cfg.reset_pos), srp = cfg.reset_roll_pitch - (-cfg.reset_roll_pitch),
+              sy = cfg.reset_yaw - (-cfg.reset_yaw), sv = cfg.reset_vel - (-cfg.reset_vel);
+  const V3 dpos = v3(u_pose0.x * sp + (-cfg.reset_pos), u_pose0.y * sp + (-cfg.reset_pos), u_pose0.z * sp + (-cfg.reset_pos));
+  const float roll = u_pose0.w * srp + (-cfg.reset_roll_pitch), pitch = u_pose1.x * srp + (-cfg.reset_roll_pitch);
+  const float dyaw = u_pose1.y * sy + (-cfg.reset_yaw);
+  const V3 pos = v3(cfg.default_pos[0], cfg.default_pos[1], cfg.default_pos[2]) + origin + dpos;
+  const V3 towards = (tr.gate(type, level, start_gate) + origin) - pos;
+  const float yaw = wrap_to_pi(atan2f(towards.y, towards.x)) + dyaw;
+  e.q = quat_mul(Q4{1.f, 0.f, 0.f, 0.f}, quat_from_euler_xyz(roll, pitch, yaw));
+  e.w = pos;
+  e.v = v3(u_pose1.z * sv + (-cfg.reset_vel), u_pose1.w * sv + (-cfg.reset_vel), u_vel.x * sv + (-cfg.reset_vel));
+  e.om = v3(u_vel.y * sv + (-cfg.reset_vel), u_vel.z * sv + (-cfg.reset_vel), u_vel.w * sv + (-cfg.reset_vel));
+  e.aacc = v3(0.f, 0.f, 0.f);                      // closure A.1
+  // -- CTBRController.reset_idx (L/controllers/controller_diff.py:146-160)
+  e.f = 0.f; e.tau = v3(0.f, 0.f, 0.f);
+  // -- DroneDynamics.reset_idx (QD/mdp/dynamics/droneDynamics.py:50-57): slots 20 z, 21..23 drag2, 24..26 drag1
+  if (cfg.random_drag) {
+    const float z = 1.0f * cfg.z_drag + u_d0.x * cfg.z_drag_rand;
+    const float b2 = cfg.drag2 * e.m, b1 = cfg.drag1 * e.m;
+    e.k2 = v3(b2 + u_d0.y * cfg.drag2_rand, b2 + u_d0.z * cfg.drag2_rand, (b2 + u_d0.w * cfg.drag2_rand) * z);
+    e.k1 = v3(b1 + u_d1.x * cfg.drag1_rand, b1 + u_d1.y * cfg.drag1_rand, (b1 + u_d1.z * cfg.drag1_rand) * z);
+  }
+  // -- DiffActions.reset_idx (QD/mdp/diff_action.py:233)
+  e.thr = 1.0f + thr_normal * cfg.thr_err_reset_std;
+  // -- RacingCommand._resample_command (QD/mdp/commands.py:262-306): slots 28..33 gate, 34..39 next gate
+  if (kNoise) {
+    const float4 u_g0 = rs.get4(7), u_g1 = rs.get4(8);
+    e.dcur = gate_noise(e.noise_hi, u_g0.x, u_g0.y, u_g0.z);
+    e.dnext = gate_noise(e.noise_hi, u_g1.z, u_g1.w, rs.get4(9).x);
+  }
+  e.pk = pk_make((uint32_t)start_gate, 0u, (uint32_t)level, (uint32_t)type, 1u);
+  e.eplen = 0;
+  return origin;
+}
+
+template <bool kNoise, bool kStats>
+__device__ __forceinline__ void store_env(const EnvRegs& e, float4* __restrict__ P, int64_t S, int i, bool cold_dirty, bool noise_dirty) {
+  st_plane(P, S, PL_QUAT, i, pack(e.q));
+  st_plane(P, S, PL_POS, i, pack(e.w, e.f));
+  st_plane(P, S, PL_LINVEL, i, pack(e.v, __int_as_float(e.eplen)));
+  st_plane(P, S, PL_ANGVEL, i, pack(e.om, __uint_as_float(e.pk)));
+  st_plane(P, S, PL_TORQUE, i, pack(e.tau, e.aux));
+  st_plane(P, S, PL_ANGACC, i, pack(e.aacc, 0.f));
+  if (cold_dirty) {
+    P[(int64_t)PL_DRAG2 * S + i] = pack(e.k2, e.m);
+    P[(int64_t)PL_DRAG1 * S + i] = pack(e.k1, e.ef);
+    P[(int64_t)PL_KP * S + i] = pack(e.kp, e.thr);
+  }
+  if (kNoise && noise_dirty) {
+    P[(int64_t)PL_NOISE0 * S + i] = make_float4(e.dcur.x, e.dcur.y, e.dcur.z, e.dnext.x);
+    P[(int64_t)PL_NOISE1 * S + i] = make_float4(e.dnext.y, e.dnext.z, e.noise_hi, e.noise_level);
+  }
+}
+
+// =============================================================================================
+// the step kernel
+// =============================================================================================
+template <bool kNoise, bool kDiff, bool kPhilox, bool kStats>
+__global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg, const GrTrack track, const GrState st,
+                                                              const GrRandom rng, const GrStepIO io) {
+  GR_DYN_SMEM(float4, smem_rows);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i < st.num_envs;
+  const int li = active ? i : st.num_envs - 1;        // inactive threads shadow the last env (loads only)
+  float4* __restrict__ P = reinterpret_cast<float4*>(st.planes);
+  const int64_t S = st.plane_stride;
+
+  EnvRegs e;
+  load_env<kNoise>(e, P, S, li);
+  const float4 a_t = __ldcs(reinterpret_cast<const float4*>(io.action) + li);
+  float4 eps0 = make_float4(0.f, 0.f, 0.f, 0.f), eps1 = eps0;
+  if (kStats) { eps0 = ld_plane(P, S, PL_EPSUM0, li); eps1 = ld_plane(P, S, PL_EPSUM1, li); }
+  const RandSrc<kPhilox> rs(rng, li, st.env_id_offset + li);
+  const float4 n01 = rs.get4(0), n23 = rs.get4(1);   // obs normals (slots 0..5), thr_est_error normal (slot 6)
+
+  const TrackSmem tr = stage_track(track, reinterpret_cast<const int2*>(st.chunk_types), st.num_envs, smem_rows);
+  if (!active) return;
+
+  const int type = (int)pk_type(e.pk);
+  int level = (int)pk_level(e.pk);
+  int gate_id = (int)pk_gate(e.pk);
+  const uint32_t fresh = pk_fresh(e.pk);
+  V3 origin = xyz(tr.origin_row(type, level));
+  const float dt = cfg.dt;
+  const V3 J = v3(cfg.inertia[0], cfg.inertia[1], cfg.inertia[2]);
+  const V3 Jinv = v3(1.0f / J.x, 1.0f / J.y, 1.0f / J.z);
+
+  // ---- 1. process_action (L/managers/action_manager.py:44-45; QD/mdp/diff_action.py:160-176) ----
+  // FIFO (lag 1): the applied action is a_{t-1}; prev_action is a_{t-1} unless the latches were zeroed by a reset
+  const float4 th_lag = tanh4(e.fifo);
+  const float4 th_a = tanh4(a_t);
+  const float4 th_prev = fresh ? make_float4(0.f, 0.f, 0.f, 0.f) : th_lag;
+  // get_state_from_sim (QD/mdp/diff_action.py:126-154)
+  const V3 p = e.w - origin;
+  const V3 om_b = quat_rotate_inverse(e.q, e.om);
+  const V3 v_b = quat_rotate_inverse(e.q, e.v);
+  const V3 aacc_b = quat_rotate_inverse(e.q, e.aacc);
+  float cmd0 = th_lag.x * cfg.action_scale0 + cfg.action_scale0;
+  cmd0 *= e.thr;
+  const V3 cmd_rate = v3(th_lag.y * cfg.body_rate_bound + 0.0f, th_lag.z * cfg.body_rate_bound + 0.0f, th_lag.w * cfg.body_rate_bound + 0.0f);
+
+  // ---- CTBRController.compute (L/controllers/controller_diff.py:120-138) ----
+  const float thrust_des = fminf(fmaxf(cmd0, cfg.thrust_lo), cfg.thrust_hi);
+  const float f_new = (1.0f - e.ef) * thrust_des + e.ef * e.f;
+  const V3 rate_c = v3(fminf(fmaxf(cmd_rate.x, -cfg.body_rate_bound), cfg.body_rate_bound),
+                       fminf(fmaxf(cmd_rate.y, -cfg.body_rate_bound), cfg.body_rate_bound),
+                       fminf(fmaxf(cmd_rate.z, -cfg.body_rate_bound), cfg.body_rate_bound));
+  const V3 gyro = cross(om_b, J * om_b);
+  const V3 torque_des = J * (e.kp * (rate_c - om_b)) + gyro - e.kd * aacc_b;
+  const V3 one_m_etau = v3(1.0f - e.etau.x, 1.0f - e.etau.y, 1.0f - e.etau.z);
+  const V3 tau_new = one_m_etau * torque_des + e.etau * e.tau;
+
+  // ---- DroneDynamics.step (QD/mdp/dynamics/droneDynamics.py:119-135) ----
+  const V3 F_b = v3(0.f, 0.f, f_new) - e.k2 * v_b * vabs(v_b) - e.k1 * v_b;
+  const V3 acc = v3(0.f, 0.f, -cfg.gravity) + quat_rotate(e.q, F_b) / e.m;
+  const V3 alpha = Jinv * tau_new - Jinv * gyro;
+  const V3 p1 = p + e.v * dt + 0.5f * acc * dt * dt;
+  const Q4 dq = quat_mul(e.q, Q4{0.f, om_b.x, om_b.y, om_b.z});
+  Q4 qt = Q4{e.q.w + 0.5f * dq.w * dt, e.q.x + 0.5f * dq.x * dt, e.q.y + 0.5f * dq.y * dt, e.q.z + 0.5f * dq.z * dt};
+  const float qn = sqrtf(qt.w * qt.w + qt.x * qt.x + qt.y * qt.y + qt.z * qt.z);
+  const Q4 q1 = Q4{qt.w / qn, qt.x / qn, qt.y / qn, qt.z / qn};
+  const V3 v1 = e.v + acc * dt;
+  const V3 omb1 = om_b + alpha * dt;
+  const V3 omw1 = quat_rotate(q1, omb1);
+
+  // ---- BPTT tape planes 0..5 of this step (consumer: racing_bwd.cu; SURVEY.md A.6/A.7, derived form) ----
+  if (kDiff && io.tape) {
+    float4* __restrict__ T = reinterpret_cast<float4*>(io.tape);
+    const int64_t TS = io.tape_stride;
+    const float b = cfg.body_rate_bound;
+    const float m0 = (cmd0 >= cfg.thrust_lo && cmd0 <= cfg.thrust_hi) ? 1.0f : 0.0f;
+    const float A0 = m0 * e.thr * cfg.action_scale0 * (1.0f - th_lag.x * th_lag.x) * (1.0f - e.ef);
+    const V3 mk = v3((cmd_rate.x >= -b && cmd_rate.x <= b) ? b : 0.0f, (cmd_rate.y >= -b && cmd_rate.y <= b) ? b : 0.0f,
+                     (cmd_rate.z >= -b && cmd_rate.z <= b) ? b : 0.0f);
+    const V3 A = mk * v3(1.0f - th_lag.y * th_lag.y, 1.0f - th_lag.z * th_lag.z, 1.0f - th_lag.w * th_lag.w) * one_m_etau * J * e.kp;
+    const V3 D = -(2.0f * (e.k2 * vabs(v_b)) + e.k1);
+    __stcs(T + 0 * TS + i, pack(e.q));
+    __stcs(T + 1 * TS + i, pack(om_b, A0));
+    __stcs(T + 2 * TS + i, pack(F_b, A.x));
+    __stcs(T + 3 * TS + i, pack(D, A.y));
+    __stcs(T + 4 * TS + i, pack(v1, A.z));
+    __stcs(T + 5 * TS + i, pack(omb1, __uint_as_float(fresh)));
+  }
+
+  // ---- 2. "physics": closure A.1, truth := nominal; world pose, last angular acceleration ----
+  e.w = p1 + origin; e.q = q1; e.v = v1; e.om = omw1; e.aacc = quat_rotate(q1, alpha);
+  e.f = f_new; e.tau = tau_new;
+  // ---- 3. align (droneDynamics.py:156-181): value = sim-derived state; aligned local position for the loss ----
+  const V3 p_al = e.w - origin;
+  const V3 v_al = v1;
+
+  // ---- 4./5. counters + terminations (QD/mdp/termination.py:15-33; Isaac Lab mdp.time_out) ----
+  e.eplen += 1;
+  const bool time_out = e.eplen >= cfg.max_episode_length;
+  bool terminated = false;
+  if (cfg.term_oob) terminated = terminated || (e.w.z < cfg.oob_lo) || (e.w.z > cfg.oob_hi);
+  bool bad = false;
+  if (cfg.term_bad_pose || cfg.w_reward[5] != 0.0f) bad = bad_pose(q1);
+  if (cfg.term_bad_pose) terminated = terminated || bad;
+
+  // ---- 6. rewards (QD/mdp/rewards.py:154-253; RewardManager.compute: sum_i term_i * w_i * dt) ----
+  float terms[GR_NUM_REWARD_TERMS];
+  float reward = 0.0f;
+  {
+    const V3 g_gt = tr.gate(type, level, gate_id) + origin;
+    const V3 vec = g_gt - e.w;
+    const V3 vb1 = quat_rotate_inverse(q1, v1);
+    const V3 cmd_gt0 = quat_rotate_inverse(q1, vec);
+    terms[0] = cosine_similarity(vb1, cmd_gt0);                                                   // :154-161
+    const V3 br = v3(th_a.y * cfg.body_rate_bound, th_a.z * cfg.body_rate_bound, th_a.w * cfg.body_rate_bound);
+    terms[1] = norm(br);                                                                          // :188-194
+    {
+      const float s0 = cfg.action_scale0, sb = cfg.body_rate_bound;                                // :196-206
+      const float d0 = (th_a.x * s0 + s0) - (th_prev.x * s0 + s0), d1 = (th_a.y * sb + 0.0f) - (th_prev.y * sb + 0.0f),
+                  d2 = (th_a.z * sb + 0.0f) - (th_prev.z * sb + 0.0f), d3 = (th_a.w * sb + 0.0f) - (th_prev.w * sb + 0.0f);
+      terms[2] = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+    {
+      const float n = fmaxf(norm(cmd_gt0), 1e-12f);                                                // :171-179
+      terms[3] = cosine_similarity(cmd_gt0 / n, v3(1.0f, 0.0f, 0.0f));
+    }
+    const float d = norm(vec);                                                                     // :215-224
+    terms[4] = (d < cfg.update_threshold ? 1.0f : 0.0f) * (1.0f / (d * d + 1.0f));
+    terms[5] = bad ? 1.0f : 0.0f;                                                                  // :244-253
+#pragma unroll
+    for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k) {
+      if (cfg.w_reward[k] != 0.0f) {
+        const float value = terms[k] * cfg.w_reward[k] * dt;
+        reward = reward + value;
+        terms[k] = value / dt;
+        if (kStats) { if (k < 4) (&eps0.x)[k] += value; else (&eps1.x)[k - 4] += value; }
+      } else {
+        terms[k] = 0.0f;
+      }
+    }
+  }
+  e.aux = terms[4] > 0.0f ? 1.0f : 0.0f;                 // cross_obs (QD/mdp/observation.py:97-104)
+
+  // ---- 7. reset (L/envs/manager_based_diff_rl_env.py:232-247,362-410) ----
+  const bool reset = terminated || time_out;
+  bool noise_dirty = false;
+  if (reset) {
+    if (io.log_accum) {
+      atomicAdd(io.log_accum + GR_LOG_NUM_RESET, 1.0f);
+      atomicAdd(io.log_accum + GR_LOG_SUM_GATES, (float)pk_acc(e.pk));
+      if (time_out) atomicAdd(io.log_accum + GR_LOG_NUM_TIMEOUT, 1.0f);
+      if (terminated) atomicAdd(io.log_accum + GR_LOG_NUM_TERMINATED, 1.0f);
+      if (kStats) {
+#pragma unroll
+        for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k)
+          atomicAdd(io.log_accum + GR_LOG_SUM_EPSUM + k, k < 4 ? (&eps0.x)[k] : (&eps1.x)[k - 4]);
+      }
+    }
+    if (kStats) { eps0 = make_float4(0.f, 0.f, 0.f, 0.f); eps1 = eps0; }
+    origin = reset_env<kNoise, kPhilox>(cfg, tr, e, rs, n23.z);
+    level = (int)pk_level(e.pk);
+    gate_id = (int)pk_gate(e.pk);
+    noise_dirty = true;
+  } else {
+    e.pk &= 0x7FFFFFFFu;      // latches hold a_t again
+  }
+
+  // ---- 8. command update (QD/mdp/commands.py:247-260 then :308-350), on the post-reset state ----
+  V3 gate_rel = tr.gate(type, level, gate_id);
+  bool passed;
+  {
+    const V3 diff = (gate_rel + origin) - e.w;
+    passed = norm(diff) < cfg.update_threshold;
+    if (passed) {
+      uint32_t acc_g = pk_acc(e.pk) + 1u;
+      gate_id = (gate_id + 1) % tr.gates;
+      e.pk = pk_make((uint32_t)gate_id, acc_g, (uint32_t)level, (uint32_t)type, pk_fresh(e.pk));
+      gate_rel = tr.gate(type, level, gate_id);
+      if (kNoise) {
+        const float4 u0 = rs.get4(10), u1 = rs.get4(11);     // slots 40..45 gate, 46..51 next
+        e.dcur = gate_noise(e.noise_hi, u0.x, u0.y, u0.z);
+        e.dnext = gate_noise(e.noise_hi, u1.z, u1.w, rs.get4(12).x);
+        noise_dirty = true;
+      }
+    }
+  }
+  const V3 next_rel = tr.gate(type, level, (gate_id + 1) % tr.gates);
+
+  // ---- 9. BPTT losses (QD/mdp/losses.py:72-80,95-101,111-117) + tape of this step ----
+  if (kDiff) {
+    const V3 desired = (gate_rel + origin) - origin;
+    const V3 dvec = desired - p_al;
+    const float dist = norm(dvec);
+    const float l_target = dist * cfg.w_loss[0];
+    const float l_vel = ((v_al.x * v_al.x + v_al.y * v_al.y + v_al.z * v_al.z) / 3.0f) * cfg.w_loss[1];
+    const float z = p_al.z;
+    const float den = 1.0f + 1.0f * z + 10.0f * (z * z);
+    const float l_fall = (1.0f / den) * cfg.w_loss[2];
+    if (io.loss) io.loss[i] = ((0.0f + l_target) + l_vel) + l_fall;
+    if (io.loss_terms) { io.loss_terms[i * 3 + 0] = l_target; io.loss_terms[i * 3 + 1] = l_vel; io.loss_terms[i * 3 + 2] = l_fall; }
+    if (io.tape) {
+      // plane 6: d loss / d aligned position (target + falling terms); d loss / d velocity is rebuilt from v1
+      const float inv = dist > 0.0f ? cfg.w_loss[0] / dist : 0.0f;
+      const float dfall = -cfg.w_loss[2] * (1.0f + 20.0f * z) / (den * den);
+      __stcs(reinterpret_cast<float4*>(io.tape) + 6 * io.tape_stride + i,
+             make_float4(-dvec.x * inv, -dvec.y * inv, -dvec.z * inv + dfall, 0.0f));
+    }
+  }
+
+  // ---- 11. observations on the post-reset state (QD/mdp/observation.py) ----
+  write_observations<kNoise>(cfg, e, origin, gate_rel, next_rel, th_lag, n01, n23, e.aux, i, io.obs, io.critic_obs, io.aux_obs);
+
+  // ---- 12. outputs + state write-back ----
+  e.fifo = a_t;
+  store_env<kNoise, kStats>(e, P, S, i, reset, noise_dirty);
+  st_plane(P, S, PL_FIFO, i, e.fifo);
+  if (kStats) { st_plane(P, S, PL_EPSUM0, i, eps0); st_plane(P, S, PL_EPSUM1, i, eps1); }
+  io.reward[i] = reward;
+  io.terminated[i] = terminated ? 1 : 0;
+  io.time_out[i] = time_out ? 1 : 0;
+  if (io.dones) io.dones[i] = reset ? 1 : 0;
+  if (io.gate_passed) io.gate_passed[i] = passed ? 1 : 0;
+  if (io.reward_terms) {
+#pragma unroll
+    for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k) io.reward_terms[i * GR_NUM_REWARD_TERMS + k] = terms[k];
+  }
+}
+
+
+// =============================================================================================
+// reset / observe: ManagerBasedRLEnv.reset() = _reset_idx(ids) + observation_manager.compute();
+// with an all-zero mask this is observation_manager.compute() alone (get_observations).
+// The "last action" observation uses the FIFO content (a_t) -- see DESIGN.md (get_observations caveat).
+// =============================================================================================
+template <bool kNoise, bool kPhilox, bool kStats>
+__global__ void __launch_bounds__(256) racing_reset_kernel(const GrConfig cfg, const GrTrack track, const GrState st, const GrRandom rng,
+                                                           const uint8_t* __restrict__ mask, const int mode /*0 mask,1 all,2 none*/,
+                                                           float* __restrict__ obs, float* __restrict__ critic, float* __restrict__ aux_out) {
+  GR_DYN_SMEM(float4, smem_rows);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i < st.num_envs;
+  const int li = active ? i : st.num_envs - 1;
+  float4* __restrict__ P = reinterpret_cast<float4*>(st.planes);
+  const int64_t S = st.plane_stride;
+  EnvRegs e;
+  load_env<kNoise>(e, P, S, li);
+  const RandSrc<kPhilox> rs(rng, li, st.env_id_offset + li);
+  const float4 n01 = rs.get4(0), n23 = rs.get4(1);
+  const TrackSmem tr = stage_track(track, reinterpret_cast<const int2*>(st.chunk_types), st.num_envs, smem_rows);
+  if (!active) return;
+  const bool do_reset = mode == 1 || (mode == 0 && mask[i] != 0);
+  const int type = (int)pk_type(e.pk);
+  V3 origin;
+  if (do_reset) {
+    origin = reset_env<kNoise, kPhilox>(cfg, tr, e, rs, n23.z);
+    store_env<kNoise, kStats>(e, P, S, i, true, true);
+    if (kStats) { st_plane(P, S, PL_EPSUM0, i, make_float4(0.f, 0.f, 0.f, 0.f)); st_plane(P, S, PL_EPSUM1, i, make_float4(0.f, 0.f, 0.f, 0.f)); }
+  } else {
+    origin = xyz(tr.origin_row(type, (int)pk_level(e.pk)));
+  }
+  const int level = (int)pk_level(e.pk), gate_id = (int)pk_gate(e.pk);
+  if (obs) {
+    const V3 gate_rel = tr.gate(type, level, gate_id), next_rel = tr.gate(type, level, (gate_id + 1) % tr.gates);
+    write_observations<kNoise>(cfg, e, origin, gate_rel, next_rel, tanh4(e.fifo), n01, n23, e.aux, i, obs, critic, aux_out);
+  }
+}
+
+// =============================================================================================
+// startup: construction-time state + domain randomisation (QD/mdp/events.py:105-137,
+// QD/mdp/diff_action.py:86, QD/mdp/dynamics/droneDynamics.py:23-34, TerrainImporter env-origin assignment)
+// =============================================================================================
+__device__ __forceinline__ void startup_draws(const float* __restrict__ srnd, uint64_t seed, int i, int env_id, float (&s)[GR_SRND_STRIDE]) {
+  if (srnd) {
+    const float4* row = reinterpret_cast<const float4*>(srnd) + (int64_t)i * (GR_SRND_STRIDE / 4);
+#pragma unroll
+    for (int c = 0; c < GR_SRND_STRIDE / 4; ++c) { const float4 v = __ldg(row + c); s[4 * c] = v.x; s[4 * c + 1] = v.y; s[4 * c + 2] = v.z; s[4 * c + 3] = v.w; }
+  } else {
+    const Philox ph(seed, (uint32_t)env_id, 0xFFFFFFFFu);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { const uint4 x = ph((uint32_t)c); s[4 * c] = u01(x.x); s[4 * c + 1] = u01(x.y); s[4 * c + 2] = u01(x.z); s[4 * c + 3] = u01(x.w); }
+    const uint4 x = ph(3u);
+    const float2 a = box_muller(x.x, x.y), b = box_muller(x.z, x.w);
+    s[12] = a.x; s[13] = a.y; s[14] = b.x; s[15] = b.y;
+  }
+}
+
+__global__ void racing_startup_kernel(const GrConfig cfg, const GrTrack track, const GrState st, const int32_t* __restrict__ terrain_types,
+                                      int32_t* __restrict__ chunk_types, const float* __restrict__ srnd, const uint64_t seed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= st.num_envs) return;
+  float4* __restrict__ P = reinterpret_cast<float4*>(st.planes);
+  const int64_t S = st.plane_stride;
+  float s[GR_SRND_STRIDE];
+  startup_draws(srnd, seed, i, st.env_id_offset + i, s);
+  const int type = terrain_types[i];
+  if ((i & 63) == 0) {
+    const int j = min(i + 63, st.num_envs - 1);
+    chunk_types[2 * (i >> 6)] = type;
+    chunk_types[2 * (i >> 6) + 1] = terrain_types[j];
+  }
+  int max_init = cfg.max_init_level < track.levels - 1 ? cfg.max_init_level : track.levels - 1;
+  int level = (int)floorf(s[10] * (float)(max_init + 1));
+  if (level > max_init) level = max_init;
+  const float ps = cfg.pid_scale_span, ds = cfg.delay_scale_span;
+  const V3 kp = v3(cfg.kp[0] * (s[0] * ps + cfg.pid_scale_lo), cfg.kp[1] * (s[1] * ps + cfg.pid_scale_lo), cfg.kp[2] * (s[2] * ps + cfg.pid_scale_lo));
+  const V3 kd = v3(cfg.kd[0] * (s[3] * ps + cfg.pid_scale_lo), cfg.kd[1] * (s[4] * ps + cfg.pid_scale_lo), cfg.kd[2] * (s[5] * ps + cfg.pid_scale_lo));
+  const float thrust_delay = cfg.thrust_delay * (s[6] * ds + cfg.delay_scale_lo);
+  const V3 torque_delay = v3(cfg.torque_delay[0] * (s[7] * ds + cfg.delay_scale_lo), cfg.torque_delay[1] * (s[8] * ds + cfg.delay_scale_lo),
+                             cfg.torque_delay[2] * (s[9] * ds + cfg.delay_scale_lo));
+  const float m = cfg.mass;
+  const float b2 = cfg.drag2 * m, b1 = cfg.drag1 * m;
+  const float zero = 0.0f;
+  P[(int64_t)PL_QUAT * S + i] = make_float4(1.f, 0.f, 0.f, 0.f);
+  P[(int64_t)PL_POS * S + i] = make_float4(zero, zero, zero, zero);
+  P[(int64_t)PL_LINVEL * S + i] = make_float4(zero, zero, zero, __int_as_float(0));
+  P[(int64_t)PL_ANGVEL * S + i] = make_float4(zero, zero, zero, __uint_as_float(pk_make(0u, 0u, (uint32_t)level, (uint32_t)type, 0u)));
+  P[(int64_t)PL_TORQUE * S + i] = make_float4(zero, zero, zero, zero);
+  P[(int64_t)PL_ANGACC * S + i] = make_float4(zero, zero, zero, zero);
+  P[(int64_t)PL_FIFO * S + i] = make_float4(zero, zero, zero, zero);
+  P[(int64_t)PL_DRAG2 * S + i] = make_float4(b2, b2, b2 * cfg.z_drag, m);
+  P[(int64_t)PL_DRAG1 * S + i] = make_float4(b1, b1, b1 * cfg.z_drag, expf(-cfg.dt / thrust_delay));
+  P[(int64_t)PL_KP * S + i] = pack(kp, 1.0f + s[12] * cfg.thr_err_init_std);
+  P[(int64_t)PL_KD * S + i] = pack(kd, 0.f);
+  P[(int64_t)PL_ETAU * S + i] = make_float4(expf(-cfg.dt / torque_delay.x), expf(-cfg.dt / torque_delay.y), expf(-cfg.dt / torque_delay.z), 0.f);
+  P[(int64_t)PL_NOISE0 * S + i] = make_float4(zero, zero, zero, zero);
+  P[(int64_t)PL_NOISE1 * S + i] = make_float4(zero, zero, cfg.cmd_noise_pos, 1.0f);
+  if (st.num_planes >= GR_NUM_PLANES_WITH_STATS) {
+    P[(int64_t)PL_EPSUM0 * S + i] = make_float4(zero, zero, zero, zero);
+    P[(int64_t)PL_EPSUM1 * S + i] = make_float4(zero, zero, zero, zero);
+  }
+}
+
+__global__ void fill_rand_kernel(float4* __restrict__ out, const int num_envs, const int env_id_offset, const uint64_t seed, const uint32_t step) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int calls = GR_RND_STRIDE / 4;
+  if (idx >= num_envs * calls) return;
+  const int i = idx / calls, c = idx - i * calls;
+  GrRandom r; r.rnd = nullptr; r.seed = seed; r.step = step;
+  const RandSrc<true> rs(r, i, env_id_offset + i);
+  out[idx] = rs.get4(c);
+}
+
+__global__ void fill_startup_rand_kernel(float* __restrict__ out, const int num_envs, const int env_id_offset, const uint64_t seed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num_envs) return;
+  float s[GR_SRND_STRIDE];
+  startup_draws(nullptr, seed, i, env_id_offset + i, s);
+#pragma unroll
+  for (int k = 0; k < GR_SRND_STRIDE; ++k) out[(int64_t)i * GR_SRND_STRIDE + k] = s[k];
+}
+
+}  // namespace gr
+
+#ifndef GR_CPU_EMUL   // host API (the CPU emulation harness in tests/emul includes only the device code)
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace gr;
+
+static inline bool misaligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
+
+static int check_common(const GrConfig* cfg, const GrTrack* tr, const GrState* st) {
+  if (!cfg || !tr || !st || !st->planes || !tr->rows || !st->chunk_types) return GR_ERR_NULL;
+  if (st->num_envs <= 0 || st->plane_stride < st->num_envs) return GR_ERR_SIZE;
+  if (st->num_planes != GR_NUM_PLANES && st->num_planes != GR_NUM_PLANES_WITH_STATS) return GR_ERR_SIZE;
+  if (tr->types < 1 || tr->types > 32 || tr->levels < 1 || tr->levels > 64 || tr->gates < 1 || tr->gates > GR_MAX_GATES) return GR_ERR_SIZE;
+  if (misaligned16(st->planes) || misaligned16(tr->rows)) return GR_ERR_ALIGN;
+  if (st->max_types_per_block < 1 || st->max_types_per_block > tr->types) return GR_ERR_SIZE;
+  return GR_OK;
+}
+
+static constexpr int kBlock = 128;
+
+static inline size_t track_smem_bytes(const GrTrack* tr, const GrState* st) {
+  return (size_t)st->max_types_per_block * tr->levels * (tr->gates + 1) * sizeof(float4);
+}
+
+template <typename K>
+static int prepare_smem(K kernel, size_t bytes) {
+  if (bytes > 200 * 1024) return GR_ERR_SMEM;
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return GR_OK;
+}
+
+template <bool kNoise, bool kDiff, bool kPhilox, bool kStats>
+static int launch_step(const GrConfig* cfg, const GrTrack* tr, const GrState* st, const GrRandom* rng, const GrStepIO* io, cudaStream_t s) {
+  auto kernel = racing_step_fwd_kernel<kNoise, kDiff, kPhilox, kStats>;
+  const size_t bytes = track_smem_bytes(tr, st);
+  int rc = prepare_smem(kernel, bytes);
+  if (rc != GR_OK) return rc;
+  const int grid = (st->num_envs + kBlock - 1) / kBlock;
+  kernel<<<grid, kBlock, bytes, s>>>(*cfg, *tr, *st, *rng, *io);
+  return (int)cudaGetLastError();
+}
+
+template <bool kNoise, bool kDiff, bool kPhilox>
+static int dispatch_stats(bool stats, const GrConfig* cfg, const GrTrack* tr, const GrState* st, const GrRandom* rng, const GrStepIO* io, cudaStream_t s) {
+  return stats ? launch_step<kNoise, kDiff, kPhilox, true>(cfg, tr, st, rng, io, s) : launch_step<kNoise, kDiff, kPhilox, false>(cfg, tr, st, rng, io, s);
+}
+template <bool kNoise, bool kDiff>
+static int dispatch_philox(bool philox, bool stats, const GrConfig* cfg, const GrTrack* tr, const GrState* st, const GrRandom* rng, const GrStepIO* io, cudaStream_t s) {
+  return philox ? dispatch_stats<kNoise, kDiff, true>(stats, cfg, tr, st, rng, io, s) : dispatch_stats<kNoise, kDiff, false>(stats, cfg, tr, st, rng, io, s);
+}
+template <bool kNoise>
+static int dispatch_diff(bool diff, bool philox, bool stats, const GrConfig* cfg, const GrTrack* tr, const GrState* st, const GrRandom* rng, const GrStepIO* io, cudaStream_t s) {
+  return diff ? dispatch_philox<kNoise, true>(philox, stats, cfg, tr, st, rng, io, s) : dispatch_philox<kNoise, false>(philox, stats, cfg, tr, st, rng, io, s);
+}
+
+extern "C" int gr_abi_version(void) { return GR_ABI_VERSION; }
+
+extern "C" int gr_step_fwd(const GrConfig* cfg, const GrTrack* track, const GrState* st, const GrRandom* rng, const GrStepIO* io, void* stream) {
+  int rc = check_common(cfg, track, st);
+  if (rc != GR_OK) return rc;
+  if (!rng || !io || !io->action || !io->obs || !io->reward || !io->terminated || !io->time_out) return GR_ERR_NULL;
+  if (misaligned16(io->action) || misaligned16(io->obs) || (io->critic_obs && misaligned16(io->critic_obs)) ||
+      (rng->rnd && misaligned16(rng->rnd)) || (io->tape && misaligned16(io->tape)))
+    return GR_ERR_ALIGN;
+  if (io->tape && io->tape_stride < st->num_envs) return GR_ERR_SIZE;
+  const bool diff = io->loss != nullptr || io->tape != nullptr || io->loss_terms != nullptr;
+  const bool stats = st->num_planes == GR_NUM_PLANES_WITH_STATS;
+  const bool philox = rng->rnd == nullptr;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return cfg->add_cmd_noise ? dispatch_diff<true>(diff, philox, stats, cfg, track, st, rng, io, s)
+                            : dispatch_diff<false>(diff, philox, stats, cfg, track, st, rng, io, s);
+}
+
+template <bool kNoise, bool kPhilox>
+static int launch_reset(bool stats, const GrConfig* cfg, const GrTrack* tr, const GrState* st, const GrRandom* rng, const uint8_t* mask, int mode,
+                        float* obs, float* critic, float* aux, cudaStream_t s) {
+  const size_t bytes = track_smem_bytes(tr, st);
+  const int grid = (st->num_envs + kBlock - 1) / kBlock;
+  if (stats) {
+    auto kernel = racing_reset_kernel<kNoise, kPhilox, true>;
+    int rc = prepare_smem(kernel, bytes);
+    if (rc != GR_OK) return rc;
+    kernel<<<grid, kBlock, bytes, s>>>(*cfg, *tr, *st, *rng, mask, mode, obs, critic, aux);
+  } else {
+    auto kernel = racing_reset_kernel<kNoise, kPhilox, false>;
+    int rc = prepare_smem(kernel, bytes);
+    if (rc != GR_OK) return rc;
+    kernel<<<grid, kBlock, bytes, s>>>(*cfg, *tr, *st, *rng, mask, mode, obs, critic, aux);
+  }
+  return (int)cudaGetLastError();
+}
+
+static int reset_impl(const GrConfig* cfg, const GrTrack* track, const GrState* st, const GrRandom* rng, const uint8_t* mask, int mode,
+                      float* obs, float* critic, float* aux, void* stream) {
+  int rc = check_common(cfg, track, st);
+  if (rc != GR_OK) return rc;
+  if (!rng) return GR_ERR_NULL;
+  if ((obs && misaligned16(obs)) || (critic && misaligned16(critic)) || (rng->rnd && misaligned16(rng->rnd))) return GR_ERR_ALIGN;
+  if (critic && !obs) return GR_ERR_NULL;
+  const bool stats = st->num_planes == GR_NUM_PLANES_WITH_STATS;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const bool philox = rng->rnd == nullptr;
+  if (cfg->add_cmd_noise)
+    return philox ? launch_reset<true, true>(stats, cfg, track, st, rng, mask, mode, obs, critic, aux, s)
+                  : launch_reset<true, false>(stats, cfg, track, st, rng, mask, mode, obs, critic, aux, s);
+  return philox ? launch_reset<false, true>(stats, cfg, track, st, rng, mask, mode, obs, critic, aux, s)
+                : launch_reset<false, false>(stats, cfg, track, st, rng, mask, mode, obs, critic, aux, s);
+}
+
+extern "C" int gr_env_reset(const GrConfig* cfg, const GrTrack* track, const GrState* st, const GrRandom* rng, const uint8_t* reset_mask,
+                            float* obs, float* critic_obs, float* aux_obs, void* stream) {
+  return reset_impl(cfg, track, st, rng, reset_mask, reset_mask ? 0 : 1, obs, critic_obs, aux_obs, stream);
+}
+
+extern "C" int gr_env_observe(const GrConfig* cfg, const GrTrack* track, const GrState* st, const GrRandom* rng, float* obs, float* critic_obs,
+                              float* aux_obs, void* stream) {
+  if (!obs) return GR_ERR_NULL;
+  return reset_impl(cfg, track, st, rng, nullptr, 2, obs, critic_obs, aux_obs, stream);
+}
+
+extern "C" int gr_env_startup(const GrConfig* cfg, const GrTrack* track, const GrState* st, const int32_t* terrain_types, int32_t* chunk_types_out,
+                              const float* srnd, uint64_t seed, void* stream) {
+  if (!cfg || !track || !st || !st->planes || !terrain_types || !chunk_types_out) return GR_ERR_NULL;
+  if (st->num_envs <= 0 || st->plane_stride < st->num_envs) return GR_ERR_SIZE;
+  if (st->num_planes != GR_NUM_PLANES && st->num_planes != GR_NUM_PLANES_WITH_STATS) return GR_ERR_SIZE;
+  if (misaligned16(st->planes) || (srnd && misaligned16(srnd))) return GR_ERR_ALIGN;
+  if (track->types < 1 || track->types > 32 || track->levels < 1 || track->levels > 64) return GR_ERR_SIZE;
+  const int grid = (st->num_envs + 127) / 128;
+  racing_startup_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*cfg, *track, *st, terrain_types, chunk_types_out, srnd, seed);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int gr_fill_rand(float* rnd, int32_t num_envs, int32_t env_id_offset, uint64_t seed, uint32_t step, void* stream) {
+  if (!rnd) return GR_ERR_NULL;
+  if (num_envs <= 0) return GR_ERR_SIZE;
+  if (misaligned16(rnd)) return GR_ERR_ALIGN;
+  const int total = num_envs * (GR_RND_STRIDE / 4);
+  fill_rand_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<float4*>(rnd), num_envs, env_id_offset, seed, step);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int gr_fill_startup_rand(float* srnd, int32_t num_envs, int32_t env_id_offset, uint64_t seed, void* stream) {
+  if (!srnd) return GR_ERR_NULL;
+  if (num_envs <= 0) return GR_ERR_SIZE;
+  fill_startup_rand_kernel<<<(num_envs + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(srnd, num_envs, env_id_offset, seed);
+  return (int)cudaGetLastError();
+}
+#endif  // GR_CPU_EMUL

@@ -1,0 +1,237 @@
+// rollout.cu -- rsl_rl PPO rollout storage on sm_100a: fused add_transitions (+ time-out bootstrap),
+// GAE + advantage normalisation in two launches, fused mini-batch gather.
+//
+// Reference path replaced (S = standalone): S/rsl_rl/ext/storage/rollout_storage.py:71-88 (9 copy_ launches
+// per step), :113-127 (~8T+6 launches of [N,1] elementwise ops), :152-191 (9 fancy-index gathers per
+// mini-batch) and S/rsl_rl/ext/algorithms/ppo.py:85-97.  All of it is HBM-bound copy / scan work: one thread
+// per env for the time scan (coalesced across envs at every t), 128-bit vector copies for the rows.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/gracing.h"
+
+namespace gr {
+
+// ---------------------------------------------------------------------------------------------
+// add_transitions: one launch; a thread copies one float4 of one of the row-shaped fields, the first N
+// threads additionally handle the scalar columns (reward with bootstrap, done, value, log-prob).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void copy_rows(const float* __restrict__ src, float* __restrict__ dst, int64_t k4) {
+  reinterpret_cast<float4*>(dst)[k4] = __ldcs(reinterpret_cast<const float4*>(src) + k4);
+}
+
+__global__ void storage_add_kernel(const GrStorage s, const GrTransition tr, const int step) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t N = s.N;
+  const int64_t n_obs4 = N * s.obs_dim / 4, n_cri4 = s.critic_obs ? N * s.critic_dim / 4 : 0, n_act4 = N * s.act_dim / 4;
+  int64_t k = tid;
+  if (k < n_obs4) { copy_rows(tr.obs, s.obs + (int64_t)step * N * s.obs_dim, k); }
+  else if ((k -= n_obs4) < n_cri4) { copy_rows(tr.critic_obs, s.critic_obs + (int64_t)step * N * s.critic_dim, k); }
+  else if ((k -= n_cri4) < n_act4) { copy_rows(tr.actions, s.actions + (int64_t)step * N * s.act_dim, k); }
+  else if ((k -= n_act4) < n_act4) { if (s.mu) copy_rows(tr.mu, s.mu + (int64_t)step * N * s.act_dim, k); }
+  else if ((k -= n_act4) < n_act4) { if (s.sigma) copy_rows(tr.sigma, s.sigma + (int64_t)step * N * s.act_dim, k); }
+  else if ((k -= n_act4) < N) {
+    const int64_t n = k;
+    const float v = tr.values ? tr.values[n] : 0.0f;
+    float r = tr.rewards[n];
+    // ppo.py:89-92: rewards += gamma * squeeze(values * time_outs.unsqueeze(1), 1)
+    if (tr.time_outs) r += tr.gamma * (v * (tr.time_outs[n] ? 1.0f : 0.0f));
+    s.rewards[(int64_t)step * N + n] = r;
+    const bool d = tr.dones_is_int64 ? (reinterpret_cast<const int64_t*>(tr.dones)[n] != 0) : (reinterpret_cast<const uint8_t*>(tr.dones)[n] != 0);
+    s.dones[(int64_t)step * N + n] = d ? 1 : 0;
+    if (s.values) s.values[(int64_t)step * N + n] = v;
+    if (s.log_prob) s.log_prob[(int64_t)step * N + n] = tr.log_prob[n];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GAE: thread per env scans t = T-1..0 (rollout_storage.py:113-123), writes returns and raw advantages and
+// accumulates (count, mean, M2) in fp64 (Chan/Welford merge: warp shuffle -> block -> one partial per block).
+// ---------------------------------------------------------------------------------------------
+struct Moments { double n, mean, m2; };
+__device__ __forceinline__ Moments merge(Moments a, Moments b) {
+  if (b.n == 0.0) return a;
+  if (a.n == 0.0) return b;
+  const double n = a.n + b.n, d = b.mean - a.mean;
+  return Moments{n, a.mean + d * (b.n / n), a.m2 + b.m2 + d * d * (a.n * b.n / n)};
+}
+__device__ __forceinline__ Moments warp_merge(Moments m) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Moments b{__shfl_down_sync(0xffffffffu, m.n, o), __shfl_down_sync(0xffffffffu, m.mean, o), __shfl_down_sync(0xffffffffu, m.m2, o)};
+    m = merge(m, b);
+  }
+  return m;
+}
+__device__ __forceinline__ Moments block_merge(Moments m, Moments* sh) {
+  m = warp_merge(m);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) sh[wid] = m;
+  __syncthreads();
+  if (wid == 0) {
+    m = lane < nw ? sh[lane] : Moments{0.0, 0.0, 0.0};
+    m = warp_merge(m);
+  }
+  return m;   // valid in thread 0
+}
+
+constexpr int kGaeBlock = 128;
+
+__global__ void __launch_bounds__(kGaeBlock) gae_kernel(const GrStorage s, const float* __restrict__ last_values, const float gamma, const float lam,
+                                                        double* __restrict__ partials) {
+  __shared__ Moments sh[kGaeBlock / 32];
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t N = s.N;
+  Moments mom{0.0, 0.0, 0.0};
+  if (n < N) {
+    float next_value = last_values[n];
+    float adv = 0.0f;
+    for (int t = s.T - 1; t >= 0; --t) {
+      const int64_t k = (int64_t)t * N + n;
+      const float not_term = 1.0f - (float)s.dones[k];
+      const float v = s.values[k];
+      const float delta = s.rewards[k] + not_term * gamma * next_value - v;
+      adv = delta + not_term * gamma * lam * adv;
+      const float ret = adv + v;
+      s.returns[k] = ret;
+      const float a = ret - v;              // rollout_storage.py:126 (returns - values, not `adv`)
+      s.advantages[k] = a;
+      mom.n += 1.0;
+      const double d = (double)a - mom.mean;
+      mom.mean += d / mom.n;
+      mom.m2 += d * ((double)a - mom.mean);
+      next_value = v;
+    }
+  }
+  mom = block_merge(mom, sh);
+  if (threadIdx.x == 0) { partials[3 * blockIdx.x] = mom.n; partials[3 * blockIdx.x + 1] = mom.mean; partials[3 * blockIdx.x + 2] = mom.m2; }
+}
+
+// merge the per-block partials (single block), optionally export them
+__global__ void gae_moments_kernel(const double* __restrict__ partials, const int num_partials, double* __restrict__ moments) {
+  __shared__ Moments sh[32];
+  Moments m{0.0, 0.0, 0.0};
+  for (int k = threadIdx.x; k < num_partials; k += blockDim.x) m = merge(m, Moments{partials[3 * k], partials[3 * k + 1], partials[3 * k + 2]});
+  m = block_merge(m, sh);
+  if (threadIdx.x == 0) { moments[0] = m.n; moments[1] = m.mean; moments[2] = m.m2; }
+}
+
+// (adv - mean) / (std_unbiased + 1e-8)   (rollout_storage.py:127)
+__global__ void adv_normalize_kernel(float* __restrict__ adv, const int64_t total, const double* __restrict__ moments) {
+  const double n = moments[0], mean = moments[1], m2 = moments[2];
+  const float mu = (float)mean;
+  const float sd = (float)sqrt(m2 / (n - 1.0));
+  const float inv_den = sd + 1e-8f;
+  const int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t base = i4 * 4;
+  if (base + 3 < total && ((reinterpret_cast<uintptr_t>(adv) & 15u) == 0)) {
+    float4 a = reinterpret_cast<float4*>(adv)[i4];
+    a.x = (a.x - mu) / inv_den; a.y = (a.y - mu) / inv_den; a.z = (a.z - mu) / inv_den; a.w = (a.w - mu) / inv_den;
+    reinterpret_cast<float4*>(adv)[i4] = a;
+  } else {
+    for (int64_t k = base; k < total && k < base + 4; ++k) adv[k] = (adv[k] - mu) / inv_den;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// mini-batch gather: one launch for the nine fields; a thread moves one float4 of a row-shaped field
+// or one element of the five scalar fields.
+// ---------------------------------------------------------------------------------------------
+__global__ void storage_gather_kernel(const GrStorage s, const int64_t* __restrict__ idx, const int B, const GrMiniBatch o) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int o4 = s.obs_dim / 4, c4 = s.critic_obs ? s.critic_dim / 4 : 0, a4 = s.act_dim / 4;
+  const int per_row = o4 + c4 + 3 * a4 + 1;
+  const int64_t b = tid / per_row;
+  if (b >= B) return;
+  int k = (int)(tid - b * per_row);
+  const int64_t r = __ldg(idx + b);
+  if (k < o4) { reinterpret_cast<float4*>(o.obs)[b * o4 + k] = __ldg(reinterpret_cast<const float4*>(s.obs) + r * o4 + k); return; }
+  k -= o4;
+  if (k < c4) { reinterpret_cast<float4*>(o.critic_obs)[b * c4 + k] = __ldg(reinterpret_cast<const float4*>(s.critic_obs) + r * c4 + k); return; }
+  k -= c4;
+  if (k < a4) { reinterpret_cast<float4*>(o.actions)[b * a4 + k] = __ldg(reinterpret_cast<const float4*>(s.actions) + r * a4 + k); return; }
+  k -= a4;
+  if (k < a4) { reinterpret_cast<float4*>(o.mu)[b * a4 + k] = __ldg(reinterpret_cast<const float4*>(s.mu) + r * a4 + k); return; }
+  k -= a4;
+  if (k < a4) { reinterpret_cast<float4*>(o.sigma)[b * a4 + k] = __ldg(reinterpret_cast<const float4*>(s.sigma) + r * a4 + k); return; }
+  o.values[b] = __ldg(s.values + r);
+  o.advantages[b] = __ldg(s.advantages + r);
+  o.returns[b] = __ldg(s.returns + r);
+  o.log_prob[b] = __ldg(s.log_prob + r);
+}
+
+}  // namespace gr
+
+using namespace gr;
+
+static inline bool mis16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
+
+static int check_storage(const GrStorage* s) {
+  if (!s || !s->obs || !s->actions || !s->rewards || !s->dones) return GR_ERR_NULL;
+  if (s->T <= 0 || s->N <= 0 || s->obs_dim <= 0 || s->act_dim <= 0) return GR_ERR_SIZE;
+  if ((s->obs_dim & 3) || (s->act_dim & 3) || (s->critic_obs && (s->critic_dim & 3))) return GR_ERR_SIZE;
+  if (mis16(s->obs) || mis16(s->actions) || (s->critic_obs && mis16(s->critic_obs)) || (s->mu && mis16(s->mu)) || (s->sigma && mis16(s->sigma)))
+    return GR_ERR_ALIGN;
+  return GR_OK;
+}
+
+extern "C" int gr_storage_add(const GrStorage* s, const GrTransition* tr, int32_t step, void* stream) {
+  int rc = check_storage(s);
+  if (rc != GR_OK) return rc;
+  if (!tr || !tr->obs || !tr->actions || !tr->rewards || !tr->dones) return GR_ERR_NULL;
+  if (s->critic_obs && !tr->critic_obs) return GR_ERR_NULL;
+  if ((s->values && !tr->values) || (s->log_prob && !tr->log_prob) || (s->mu && !tr->mu) || (s->sigma && !tr->sigma)) return GR_ERR_NULL;
+  if (tr->time_outs && !tr->values) return GR_ERR_NULL;
+  if (step < 0 || step >= s->T) return GR_ERR_SIZE;
+  if (mis16(tr->obs) || mis16(tr->actions) || (tr->critic_obs && mis16(tr->critic_obs)) || (tr->mu && mis16(tr->mu)) || (tr->sigma && mis16(tr->sigma)))
+    return GR_ERR_ALIGN;
+  const int64_t N = s->N;
+  const int64_t total = N * s->obs_dim / 4 + (s->critic_obs ? N * s->critic_dim / 4 : 0) + 3 * (N * s->act_dim / 4) + N;
+  storage_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*s, *tr, step);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int64_t gr_gae_scratch_bytes(int32_t N) {
+  const int64_t blocks = ((int64_t)N + kGaeBlock - 1) / kGaeBlock;
+  return (blocks * 3 + 3) * (int64_t)sizeof(double);
+}
+
+extern "C" int gr_advantage_normalize(const GrStorage* s, const double* moments, void* stream) {
+  if (!s || !s->advantages || !moments) return GR_ERR_NULL;
+  const int64_t total = (int64_t)s->T * s->N;
+  if (total <= 0) return GR_ERR_SIZE;
+  const int64_t n4 = (total + 3) / 4;
+  adv_normalize_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(s->advantages, total, moments);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int gr_compute_returns(const GrStorage* s, const float* last_values, float gamma, float lam, void* scratch, double* moments,
+                                  int32_t normalize, void* stream) {
+  if (!s || !s->rewards || !s->dones || !s->values || !s->returns || !s->advantages || !last_values || !scratch) return GR_ERR_NULL;
+  if (s->T <= 0 || s->N <= 0) return GR_ERR_SIZE;
+  if (reinterpret_cast<uintptr_t>(scratch) & 7u) return GR_ERR_ALIGN;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int blocks = (s->N + kGaeBlock - 1) / kGaeBlock;
+  double* partials = reinterpret_cast<double*>(scratch);
+  double* mom = moments ? moments : partials + 3 * (int64_t)blocks;
+  gae_kernel<<<blocks, kGaeBlock, 0, st>>>(*s, last_values, gamma, lam, partials);
+  gae_moments_kernel<<<1, 256, 0, st>>>(partials, blocks, mom);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if (normalize) return gr_advantage_normalize(s, mom, stream);
+  return GR_OK;
+}
+
+extern "C" int gr_storage_gather(const GrStorage* s, const int64_t* indices, int32_t B, const GrMiniBatch* out, void* stream) {
+  int rc = check_storage(s);
+  if (rc != GR_OK) return rc;
+  if (!indices || !out || !out->obs || !out->actions || !out->values || !out->advantages || !out->returns || !out->log_prob || !out->mu || !out->sigma)
+    return GR_ERR_NULL;
+  if (!s->values || !s->advantages || !s->returns || !s->log_prob || !s->mu || !s->sigma) return GR_ERR_NULL;
+  if (s->critic_obs && !out->critic_obs) return GR_ERR_NULL;
+  if (B <= 0) return GR_ERR_SIZE;
+  if (mis16(out->obs) || mis16(out->actions) || mis16(out->mu) || mis16(out->sigma) || (out->critic_obs && mis16(out->critic_obs))) return GR_ERR_ALIGN;
+  const int per_row = s->obs_dim / 4 + (s->critic_obs ? s->critic_dim / 4 : 0) + 3 * (s->act_dim / 4) + 1;
+  const int64_t total = (int64_t)B * per_row;
+  storage_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*s, indices, B, *out);
+  return (int)cudaGetLastError();
+}

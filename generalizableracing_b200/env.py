@@ -1,0 +1,325 @@
+"""RacingVecEnv -- the reference's vectorised racing env surface on top of libgracing.so.
+
+Mirrors what ``OnPolicyRunner`` / ``AlgoRunner`` see of the reference env through Isaac Lab's
+``RslRlVecEnvWrapper``: ``get_observations() -> (obs, {"observations": {...}})``,
+``step(actions) -> (obs, rew, dones, extras)`` with ``extras["observations"]["critic"]``,
+``extras["time_outs"]``, ``extras["log"]`` and, when ``cfg.is_differentiable_physics``,
+``extras["losses"]`` (requires grad) / ``["losses_detached"]`` / ``["loss_terms"]``;
+attributes ``num_envs, num_actions, num_obs, device, cfg, episode_length_buf`` (assignable),
+``max_episode_length``, ``unwrapped.detach()``, ``reset()``, ``close()``.
+Reference: extensions/diff.lab/diff/lab/envs/manager_based_diff_rl_env.py:160-267,362-416.
+
+Every step is ONE kernel launch (gr_step_fwd); there is no host synchronisation and no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib as B
+from . import layout as L
+from .config import RacingCfg
+from .tracks import GateTable
+
+
+def make_gr_config(cfg: RacingCfg) -> B.GrConfig:
+    """RacingCfg -> GrConfig; derived constants are formed in fp32 in the order torch forms them."""
+    f32 = np.float32
+    g = B.GrConfig()
+    g.dt = cfg.step_dt
+    g.max_episode_length = cfg.max_episode_length
+    g.gravity = cfg.gravity
+    g.grad_decay = cfg.grad_decay
+    g.inertia[:] = cfg.inertia_diag
+    # QD/mdp/diff_action.py:56,261: weight = mass*|g| ; scale = weight*ratio/(1-(-1))   (fp32 tensor ops)
+    weight = f32(cfg.mass) * f32(abs(-cfg.gravity))
+    g.action_scale0 = float(f32(f32(weight * f32(cfg.max_thrust_weight_ratio)) / f32(2.0)))
+    g.body_rate_bound = cfg.body_rate_bound
+    g.thrust_lo, g.thrust_hi = cfg.gross_thrust_bound
+    g.update_threshold = cfg.update_threshold
+    g.drag1, g.drag1_rand, g.drag2, g.drag2_rand = cfg.drag_1, cfg.drag_1_rand, cfg.drag_2, cfg.drag_2_rand
+    g.z_drag, g.z_drag_rand = cfg.z_drag, cfg.z_drag_rand
+    g.random_drag = int(cfg.random_drag)
+    g.thr_err_reset_std, g.thr_err_init_std = cfg.thr_est_error_reset_std, cfg.thr_est_error_init_std
+    g.default_pos[:] = cfg.default_root_pos
+    g.reset_pos, g.reset_roll_pitch, g.reset_yaw, g.reset_vel = cfg.reset_pos, cfg.reset_roll_pitch, cfg.reset_yaw, cfg.reset_vel
+    g.kp[:] = cfg.rate_gain_p
+    g.kd[:] = cfg.rate_gain_d
+    g.thrust_delay = cfg.thrust_ctrl_delay
+    g.torque_delay[:] = cfg.torque_ctrl_delay
+    g.pid_scale_lo, g.pid_scale_span = cfg.pid_scale[0], cfg.pid_scale[1] - cfg.pid_scale[0]
+    g.delay_scale_lo, g.delay_scale_span = cfg.delay_scale[0], cfg.delay_scale[1] - cfg.delay_scale[0]
+    g.mass = cfg.mass
+    g.max_init_level = cfg.max_init_terrain_level
+    g.term_oob, g.term_bad_pose = int(cfg.term_out_of_bound), int(cfg.term_bad_pose)
+    g.oob_lo, g.oob_hi = cfg.oob_lo, cfg.oob_hi
+    g.w_reward[:] = [cfg.w_progress, cfg.w_bodyrate, cfg.w_action_rate, cfg.w_perception, cfg.w_success, cfg.w_bad_pose]
+    g.add_cmd_noise = int(cfg.add_cmd_noise)
+    g.cmd_noise_pos, g.cmd_noise_yaw = cfg.cmd_noise_pos, cfg.cmd_noise_yaw
+    g.level_up_gates, g.level_down_gates = cfg.level_up_gates, cfg.level_down_gates
+    g.noise_curriculum = int(cfg.noise_curriculum and cfg.add_cmd_noise)
+    g.noise_up_gates, g.noise_down_gates = cfg.noise_up_gates, cfg.noise_down_gates
+    g.noise_up, g.noise_down = 1.0 + cfg.noise_up, 1.0 - cfg.noise_down      # the factors torch.where() selects
+    g.w_loss[:] = [cfg.w_loss_target, cfg.w_loss_vel, cfg.w_loss_fall]
+    g.obs_vel_noise, g.obs_euler_noise = cfg.obs_vel_noise, cfg.obs_euler_noise
+    if cfg.action_lag != 1:
+        raise ValueError("only action_lag == 1 (QD/racing_ctbr_env.py:136) is built")
+    return g
+
+
+def pack_track_rows(table: GateTable) -> np.ndarray:
+    """GateTable -> [types*levels*(G+1), 4] float32 rows (layout documented on GrTrack in include/gracing.h)."""
+    t, l, g = table.num_types, table.num_levels, table.num_gates
+    rows = np.zeros((t, l, g + 1, 4), dtype=np.float32)
+    rows[:, :, 0, :3] = np.transpose(table.terrain_origins, (1, 0, 2))
+    rows[:, :, 0, 3] = table.next_gate_id.astype(np.int32).view(np.float32)
+    rows[:, :, 1:, :3] = table.gate_pose[..., :3]
+    return rows.reshape(-1, 4)
+
+
+def default_terrain_types(num_envs: int, num_types: int, env_id_offset: int = 0, global_num_envs: Optional[int] = None) -> torch.Tensor:
+    """Isaac Lab TerrainImporter: ``torch.div(arange(N), N / num_cols, rounding_mode='floor')`` on the GLOBAL env ids."""
+    n_glob = global_num_envs or num_envs
+    ids = torch.arange(env_id_offset, env_id_offset + num_envs)
+    return torch.div(ids, (n_glob / num_types), rounding_mode="floor").to(torch.int32).clamp_(max=num_types - 1)
+
+
+class _Extras(dict):
+    """extras dict whose "log" entry is built on demand from the device-side accumulators (no host sync on the
+    hot loop: the reference builds it eagerly inside _reset_idx, manager_based_diff_rl_env.py:380-407)."""
+
+    def __init__(self, env):
+        super().__init__()
+        self._env = env
+
+    def __contains__(self, k):
+        return k == "log" or super().__contains__(k)
+
+    def __getitem__(self, k):
+        if k == "log" and not super().__contains__("log"):
+            return self._env._build_log()
+        return super().__getitem__(k)
+
+    def get(self, k, default=None):
+        return self[k] if k in self else default
+
+
+class RacingVecEnv:
+    num_actions = L.NUM_ACTIONS
+    num_obs = L.OBS_DIM
+    num_privileged_obs = L.OBS_DIM
+
+    def __init__(self, cfg: RacingCfg, table: GateTable, num_envs: int, device="cuda:0", seed: int = 42,
+                 rng_mode: str = "philox", episode_stats: bool = True, env_id_offset: int = 0,
+                 global_num_envs: Optional[int] = None, terrain_types: Optional[torch.Tensor] = None,
+                 startup_rnd: Optional[torch.Tensor] = None, bptt_horizon: int = 0, _lib=None):
+        self.cfg = cfg
+        self.table = table
+        self.num_envs = N = int(num_envs)
+        self.device = torch.device(device)
+        if _lib is None:
+            if self.device.type != "cuda":
+                raise RuntimeError("RacingVecEnv runs only on a CUDA device (sm_100a); there is no CPU fallback")
+            _lib = B.load()
+        self._lib = _lib
+        if rng_mode not in ("philox", "dense"):
+            raise ValueError("rng_mode must be 'philox' or 'dense'")
+        self.rng_mode = rng_mode
+        self.seed = int(seed)
+        self.max_episode_length = cfg.max_episode_length
+        self.step_dt = cfg.step_dt
+        self._gcfg = make_gr_config(cfg)
+        dev = self.device
+        # ---- track
+        self._rows = torch.from_numpy(pack_track_rows(table)).to(dev).contiguous()
+        self._track = B.GrTrack(self._rows.data_ptr(), table.num_types, table.num_levels, table.num_gates)
+        # ---- state planes
+        self.num_planes = L.NUM_PLANES_WITH_STATS if episode_stats else L.NUM_PLANES
+        self._stride = (N + 7) // 8 * 8
+        self.planes = torch.zeros(self.num_planes, self._stride, 4, dtype=torch.float32, device=dev)
+        if terrain_types is None:
+            terrain_types = default_terrain_types(N, table.num_types, env_id_offset, global_num_envs)
+        tt = terrain_types.to(torch.int32).cpu()
+        if tt.numel() != N or (N > 1 and bool((tt[1:] < tt[:-1]).any())) or int(tt.min()) < 0 or int(tt.max()) >= table.num_types:
+            raise ValueError("terrain_types must be N non-decreasing ids in [0, num_types)")
+        # distinct types inside any 256-aligned env span bound the shared-memory slice of one thread block
+        spans = [int(tt[s:s + 256].max() - tt[s:s + 256].min()) + 1 for s in range(0, N, 256)]
+        self._terrain_types = tt.to(dev)
+        self._chunk_types = torch.zeros(((N + 63) // 64) * 2, dtype=torch.int32, device=dev)
+        self._state = B.GrState(self.planes.data_ptr(), self._stride, N, self.num_planes, int(env_id_offset), max(spans),
+                                self._chunk_types.data_ptr())
+        self._rng = B.GrRandom(None, self.seed, 0)
+        self._step_count = 0
+        # ---- outputs (ping-pong so that the tensors returned by step t stay valid during step t+1)
+        def outs():
+            return dict(obs=torch.zeros(N, L.OBS_DIM, device=dev), critic=torch.zeros(N, L.OBS_DIM, device=dev),
+                        aux=torch.zeros(N, 1, device=dev), reward=torch.zeros(N, device=dev),
+                        terminated=torch.zeros(N, dtype=torch.uint8, device=dev), time_out=torch.zeros(N, dtype=torch.uint8, device=dev),
+                        dones=torch.zeros(N, dtype=torch.int64, device=dev), reward_terms=torch.zeros(N, L.NUM_REWARD_TERMS, device=dev),
+                        gate_passed=torch.zeros(N, dtype=torch.uint8, device=dev))
+        self._outs = [outs(), outs()]
+        self._flip = 0
+        self._log_accum = torch.zeros(B.GR_LOG_SLOTS, device=dev)
+        self._log_total = torch.zeros(B.GR_LOG_SLOTS, device=dev)
+        self.extras = _Extras(self)
+        self.export_reward_terms = False
+        self.export_gate_passed = False
+        # ---- BPTT window (cfg.is_differentiable_physics)
+        self._bptt = None
+        if cfg.is_differentiable_physics:
+            from .bptt import BpttWindow
+            self._bptt = BpttWindow(self, bptt_horizon or 64)
+        # ---- startup DR
+        srnd_ptr = None
+        if startup_rnd is not None:
+            self._startup_rnd = startup_rnd.to(dev, torch.float32).contiguous()
+            assert self._startup_rnd.shape == (N, L.SRND_STRIDE)
+            srnd_ptr = self._startup_rnd.data_ptr()
+        B.check(self._lib.gr_env_startup(C.byref(self._gcfg), C.byref(self._track), C.byref(self._state), self._terrain_types.data_ptr(),
+                                         self._chunk_types.data_ptr(), srnd_ptr, self.seed, self._stream()), "gr_env_startup")
+        self._last = self._outs[0]
+        self._needs_reset = True
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
+
+    def _rand(self, rnd):
+        if rnd is not None:
+            rnd = rnd.to(self.device, torch.float32).contiguous()
+            if rnd.shape != (self.num_envs, L.RND_STRIDE):
+                raise ValueError(f"rnd must be [{self.num_envs}, {L.RND_STRIDE}]")
+            self._rnd_keepalive = rnd
+            self._rng.rnd = rnd.data_ptr()
+        else:
+            if self.rng_mode == "dense":
+                raise ValueError("rng_mode='dense' needs an explicit rnd tensor every call")
+            self._rng.rnd = None
+        self._rng.step = self._step_count & 0xFFFFFFFF
+        self._step_count += 1
+        return self._rng
+
+    @property
+    def unwrapped(self):
+        return self
+
+    @property
+    def episode_length_buf(self) -> torch.Tensor:
+        """Live int32 view into the state planes (assignable, as on_policy_runner.py:118-121 does)."""
+        return self.planes[L.PL_LINVEL, : self.num_envs, 3].view(torch.int32)
+
+    @episode_length_buf.setter
+    def episode_length_buf(self, value: torch.Tensor):
+        self.planes[L.PL_LINVEL, : self.num_envs, 3].view(torch.int32).copy_(value.to(self.device, torch.int32))
+
+    def state_dict_view(self) -> dict:
+        """Named views of the SoA state (diagnostics / tests); world-frame root state like robot.data."""
+        P, N = self.planes, self.num_envs
+        pk = P[L.PL_ANGVEL, :N, 3].view(torch.int32)
+        return {
+            "root_quat_w": P[L.PL_QUAT, :N], "root_pos_w": P[L.PL_POS, :N, :3], "gross_thrust": P[L.PL_POS, :N, 3],
+            "root_lin_vel_w": P[L.PL_LINVEL, :N, :3], "episode_length": P[L.PL_LINVEL, :N, 3].view(torch.int32),
+            "root_ang_vel_w": P[L.PL_ANGVEL, :N, :3], "torque": P[L.PL_TORQUE, :N, :3], "ang_acc_w": P[L.PL_ANGACC, :N, :3],
+            "action_fifo": P[L.PL_FIFO, :N], "drag_coeffs": P[L.PL_DRAG2, :N, :3], "mass": P[L.PL_DRAG2, :N, 3],
+            "h_force_drag_coeffs": P[L.PL_DRAG1, :N, :3], "exp_thrust_delay": P[L.PL_DRAG1, :N, 3],
+            "rate_gain_p": P[L.PL_KP, :N, :3], "thr_est_error": P[L.PL_KP, :N, 3], "rate_gain_d": P[L.PL_KD, :N, :3],
+            "exp_torque_delay": P[L.PL_ETAU, :N, :3],
+            "gate_noise": torch.cat([P[L.PL_NOISE0, :N, :3], P[L.PL_NOISE0, :N, 3:], P[L.PL_NOISE1, :N, :2]], dim=-1),
+            "noise_pos_hi": P[L.PL_NOISE1, :N, 2], "noise_level": P[L.PL_NOISE1, :N, 3],
+            "gate_id": (pk >> L.PK_GATE_SHIFT) & 0xFF, "accumulate_gates": (pk >> L.PK_ACC_SHIFT) & 0xFFF,
+            "terrain_levels": (pk >> L.PK_LEVEL_SHIFT) & 0x3F, "terrain_types": (pk >> L.PK_TYPE_SHIFT) & 0x1F,
+            "fresh": (pk >> L.PK_FRESH_SHIFT) & 0x1,
+        }
+
+    def _obs_dict(self, o):
+        return {"policy": o["obs"], "critic": o["critic"], "auxiliary": o["aux"]}
+
+    def _build_log(self) -> dict:
+        """extras["log"] of the reference (_reset_idx, manager_based_diff_rl_env.py:380-407): means over the envs reset
+        since the last read, as 0-dim device tensors (the runner's logger accepts tensors)."""
+        acc = self._log_accum
+        n = acc[B_LOG_NUM_RESET].clamp(min=1.0)
+        log = {}
+        if self.num_planes == L.NUM_PLANES_WITH_STATS:
+            w = [self.cfg.w_progress, self.cfg.w_bodyrate, self.cfg.w_action_rate, self.cfg.w_perception, self.cfg.w_success, self.cfg.w_bad_pose]
+            for k, name in enumerate(L.REWARD_TERM_NAMES):
+                if w[k] != 0.0:
+                    log["Episode_Reward/" + name] = acc[B_LOG_SUM_EPSUM + k] / n / self.cfg.episode_length_s
+        log["Metrics/next_gate_pose/accumulate_gates"] = acc[B_LOG_SUM_GATES] / n
+        log["Episode_Termination/time_out"] = acc[B_LOG_NUM_TIMEOUT].clone()
+        log["Episode_Termination/terminated"] = acc[B_LOG_NUM_TERMINATED].clone()
+        sv = self.state_dict_view()
+        log["Curriculum/terrain_levels"] = sv["terrain_levels"].float().mean()
+        if self.cfg.noise_curriculum and self.cfg.add_cmd_noise:
+            log["Curriculum/command_noise_level"] = sv["noise_level"].mean()
+        self._log_total += acc
+        self._log_accum = torch.zeros_like(acc)
+        self._io_cache = None
+        return log
+
+    # ------------------------------------------------------------------ API
+    def reset(self, rnd: Optional[torch.Tensor] = None):
+        """ManagerBasedRLEnv.reset(): reset every env, return (obs, extras)."""
+        o = self._outs[self._flip]
+        self._flip ^= 1
+        B.check(self._lib.gr_env_reset(C.byref(self._gcfg), C.byref(self._track), C.byref(self._state), C.byref(self._rand(rnd)), None,
+                                       o["obs"].data_ptr(), o["critic"].data_ptr(), o["aux"].data_ptr(), self._stream()), "gr_env_reset")
+        self._last = o
+        self._needs_reset = False
+        if self._bptt is not None:
+            self._bptt.start_window()
+        self.extras["observations"] = self._obs_dict(o)
+        return o["obs"], self.extras
+
+    def get_observations(self):
+        """RslRlVecEnvWrapper.get_observations: (policy obs, {"observations": obs_dict}).  Returns the observation of
+        the last reset/step (same values the reference would recompute, minus a fresh noise draw -- DESIGN.md)."""
+        if self._needs_reset:
+            self.reset()
+        o = self._last
+        return o["obs"], {"observations": self._obs_dict(o)}
+
+    def detach(self):
+        """env.unwrapped.detach() (manager_based_diff_rl_env.py:412-416): start a new BPTT window."""
+        if self._bptt is not None:
+            self._bptt.start_window()
+
+    def close(self):
+        pass
+
+    def step(self, actions: torch.Tensor, rnd: Optional[torch.Tensor] = None):
+        if self._needs_reset:
+            self.reset()
+        o = self._outs[self._flip]
+        self._flip ^= 1
+        act = actions.detach()
+        if act.dtype != torch.float32 or not act.is_contiguous() or act.device != self.device:
+            act = act.to(self.device, torch.float32).contiguous()
+        if act.shape != (self.num_envs, L.NUM_ACTIONS):
+            raise ValueError(f"Invalid action shape, expected: ({self.num_envs}, {L.NUM_ACTIONS}), received: {tuple(act.shape)}.")
+        io = B.GrStepIO()
+        io.action = act.data_ptr()
+        io.obs, io.critic_obs, io.aux_obs = o["obs"].data_ptr(), o["critic"].data_ptr(), o["aux"].data_ptr()
+        io.reward, io.terminated, io.time_out, io.dones = o["reward"].data_ptr(), o["terminated"].data_ptr(), o["time_out"].data_ptr(), o["dones"].data_ptr()
+        io.reward_terms = o["reward_terms"].data_ptr() if self.export_reward_terms else None
+        io.gate_passed = o["gate_passed"].data_ptr() if self.export_gate_passed else None
+        io.log_accum = self._log_accum.data_ptr()
+        if self._bptt is not None:
+            self._bptt.bind_step(io)
+        B.check(self._lib.gr_step_fwd(C.byref(self._gcfg), C.byref(self._track), C.byref(self._state), C.byref(self._rand(rnd)), C.byref(io),
+                                      self._stream()), "gr_step_fwd")
+        self._last = o
+        ex = self.extras
+        dict.pop(ex, "log", None)
+        ex["observations"] = self._obs_dict(o)
+        ex["time_outs"] = o["time_out"].view(torch.bool)
+        ex["terminated"] = o["terminated"].view(torch.bool)
+        if self._bptt is not None:
+            self._bptt.after_step(actions, ex)
+        return o["obs"], o["reward"], o["dones"], ex
+
+
+B_LOG_NUM_RESET, B_LOG_SUM_GATES, B_LOG_SUM_EPSUM, B_LOG_NUM_TIMEOUT, B_LOG_NUM_TERMINATED = 0, 1, 2, 8, 9

@@ -1,0 +1,238 @@
+/* gracing.h -- C ABI of libgracing.so, the B200 (sm_100a) racing hot path.
+ *
+ * The reference (yufengsjtu/GeneralizableRacing) is pure Python/torch; there is no
+ * FFI in it.  Each entry point below replaces a group of reference *Python* calls on
+ * the hot path (file:line relative to the reference root; QD = extensions/
+ * diff.lab_tasks/diff/lab_tasks/tasks/quadcopter_diff, L = extensions/diff.lab/diff/lab,
+ * S = standalone).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *  - all pointers are DEVICE pointers owned by the caller (torch-allocated); the
+ *    library never allocates, frees or keeps them; no global state.
+ *  - every call is asynchronous and stream-ordered on `stream` (pass
+ *    torch.cuda.current_stream().cuda_stream); no host synchronisation, no host reads:
+ *    every call is CUDA-graph capturable.
+ *  - return value: 0 = ok, negative = GrStatus argument error (nothing launched),
+ *    positive = cudaError_t of the launch.  Never throws, never exits.
+ *  - fp32 everywhere; masks are uint8; ids/counters are int32.
+ */
+#ifndef GRACING_H_
+#define GRACING_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GR_ABI_VERSION 1
+
+/* ---- layout constants (mirrored by generalizableracing_b200/layout.py) ---- */
+#define GR_OBS_DIM 16
+#define GR_NUM_ACTIONS 4
+#define GR_NUM_REWARD_TERMS 6
+#define GR_RND_STRIDE 52
+#define GR_SRND_STRIDE 16
+#define GR_NUM_HOT_PLANES 7
+#define GR_NUM_PLANES 14
+#define GR_NUM_PLANES_WITH_STATS 16
+#define GR_TAPE_PLANES 7
+#define GR_MAX_GATES 32
+
+typedef enum GrStatus {
+  GR_OK = 0,
+  GR_ERR_NULL = -1,       /* a required pointer is NULL */
+  GR_ERR_SIZE = -2,       /* num_envs <= 0, bad stride, bad table shape */
+  GR_ERR_ALIGN = -3,      /* a vectorised buffer is not 16-byte aligned */
+  GR_ERR_CONFIG = -4,     /* inconsistent GrConfig (e.g. action_lag != 1) */
+  GR_ERR_SMEM = -5        /* track slice does not fit in shared memory */
+} GrStatus;
+
+/* Task constants: QD/racing_ctbr_env.py, QD/mdp/dynamics/dynamics.yaml,
+ * L/controllers/controller_diff_cfg.py (see generalizableracing_b200/config.py for
+ * the line of each field). */
+typedef struct GrConfig {
+  float dt;                 /* sim.dt * decimation = 0.03 */
+  int32_t max_episode_length;
+  float gravity;            /* 9.81 */
+  float grad_decay;         /* 0.92 */
+  float inertia[3];         /* diag J */
+  float action_scale0;      /* m*g*ratio/2 (thrust scale == offset) */
+  float body_rate_bound;    /* 6 */
+  float thrust_lo, thrust_hi;        /* gross_thrust_bound (-4.65, 86.83) */
+  float update_threshold;   /* 0.35 */
+  /* drag model */
+  float drag1, drag1_rand, drag2, drag2_rand, z_drag, z_drag_rand;
+  int32_t random_drag;
+  float thr_err_reset_std, thr_err_init_std;
+  /* reset sampler */
+  float default_pos[3];
+  float reset_pos, reset_roll_pitch, reset_yaw, reset_vel;
+  /* startup DR + nominal controller constants */
+  float kp[3], kd[3], thrust_delay, torque_delay[3];
+  float pid_scale_lo, pid_scale_span, delay_scale_lo, delay_scale_span;  /* span = hi - lo formed in double, as torch does */
+  float mass;
+  int32_t max_init_level;
+  /* terminations */
+  int32_t term_oob, term_bad_pose;
+  float oob_lo, oob_hi;
+  /* rewards: progress, bodyrate, action_rate, perception, success_cross, bad_pose */
+  float w_reward[GR_NUM_REWARD_TERMS];
+  /* command noise + curricula */
+  int32_t add_cmd_noise;
+  float cmd_noise_pos, cmd_noise_yaw;
+  int32_t level_up_gates, level_down_gates;
+  int32_t noise_curriculum, noise_up_gates, noise_down_gates;
+  float noise_up, noise_down;
+  /* BPTT losses: target, vel, fall */
+  float w_loss[3];
+  /* observation noise */
+  float obs_vel_noise, obs_euler_noise;
+} GrConfig;
+
+/* Gate table (QD/mdp/commands.py:188,272; L/terrains/terrain_importer.py:47-55), packed
+ * for shared-memory staging: rows[(type*levels + level)*(gates+1) + k] is a float4:
+ *   k == 0 : env origin xyz of tile (level,type) | next_gate_id as int32 bits
+ *   k >= 1 : position of gate k-1 relative to the tile origin | unused            */
+typedef struct GrTrack {
+  const float* rows;        /* [types*levels*(gates+1)*4] floats, 16-byte aligned */
+  int32_t types, levels, gates;
+} GrTrack;
+
+/* SoA env state: `planes` is [num_planes][plane_stride] float4; plane ids GR_PL_*. */
+typedef struct GrState {
+  float* planes;            /* 16-byte aligned */
+  int64_t plane_stride;     /* in float4 elements, >= num_envs */
+  int32_t num_envs;
+  int32_t num_planes;       /* GR_NUM_PLANES or GR_NUM_PLANES_WITH_STATS */
+  int32_t env_id_offset;    /* global id of env 0 of this shard (Philox key; multi-GPU) */
+  int32_t max_types_per_block; /* host-computed bound of distinct terrain types inside one 256-env span */
+  const int32_t* chunk_types;  /* [ceil(N/64)][2] (lowest, highest) terrain type of each 64-env chunk;
+                                  written by gr_env_startup, read by every kernel that stages the track */
+} GrState;
+
+/* Random source: dense tensor (parity mode) or in-kernel Philox4x32-10 (throughput mode). */
+typedef struct GrRandom {
+  const float* rnd;         /* [num_envs, GR_RND_STRIDE] or NULL => Philox */
+  uint64_t seed;
+  uint32_t step;            /* Philox counter word 1: the caller increments it every call */
+} GrRandom;
+
+/* One env.step(): replaces ManagerBasedDiffRLEnv.step (L/envs/manager_based_diff_rl_env.py:160-267)
+ * = DiffActionManager.process_action (L/managers/action_manager.py:31-52), DiffActions.process_actions
+ * (QD/mdp/diff_action.py:156-206), CTBRController.compute (L/controllers/controller_diff.py:120-138),
+ * DroneDynamics.step/align (QD/mdp/dynamics/droneDynamics.py:119-135,156-181), terminations
+ * (QD/mdp/termination.py:15-33), rewards (QD/mdp/rewards.py:154-253), _reset_idx (:362-410) with
+ * reset_root_state_racing (QD/mdp/events.py:139-177) and curricula (QD/mdp/curriculums.py:25-54),
+ * RacingCommand (QD/mdp/commands.py:208-350), losses (QD/mdp/losses.py:72-117) and observations
+ * (QD/mdp/observation.py:22-104).  Optional outputs may be NULL. */
+typedef struct GrStepIO {
+  const float* action;      /* [N,4] */
+  float* obs;               /* [N,16] policy observation (noisy)                    required */
+  float* critic_obs;        /* [N,16] privileged observation                         optional */
+  float* aux_obs;           /* [N]    cross_obs                                       optional */
+  float* reward;            /* [N]                                                   required */
+  uint8_t* terminated;      /* [N]                                                   required */
+  uint8_t* time_out;        /* [N]                                                   required */
+  int64_t* dones;           /* [N] (terminated|time_out) as int64, RslRlVecEnvWrapper optional */
+  float* reward_terms;      /* [N,6] unweighted-by-dt step rewards (RewardManager._step_reward) optional */
+  uint8_t* gate_passed;     /* [N] gate switched in this step (diagnostic)           optional */
+  float* loss;              /* [N] BPTT loss (extras["losses"])                      optional */
+  float* loss_terms;        /* [N,3] weighted loss terms                             optional */
+  float* tape;              /* [GR_TAPE_PLANES][tape_stride] float4 of THIS step     optional (BPTT) */
+  int64_t tape_stride;      /* in float4 elements */
+  float* log_accum;         /* [GR_LOG_SLOTS] float atomics, see GR_LOG_*            optional */
+} GrStepIO;
+
+#define GR_LOG_NUM_RESET 0          /* number of envs reset in this step                          */
+#define GR_LOG_SUM_GATES 1          /* sum of accumulate_gates of reset envs                      */
+#define GR_LOG_SUM_EPSUM 2          /* +k: sum over reset envs of episode sum of reward term k (6) */
+#define GR_LOG_NUM_TIMEOUT 8
+#define GR_LOG_NUM_TERMINATED 9
+#define GR_LOG_SLOTS 16
+
+int gr_abi_version(void);
+
+/* Construction-time domain randomisation: randomize_rate_controller_gain_and_thrust_delay
+ * (QD/mdp/events.py:105-137), DiffActions.__init__ thr_est_error (QD/mdp/diff_action.py:86),
+ * DroneDynamics.__init__ drag tables (droneDynamics.py:23-34), terrain type/level assignment.
+ * srnd: [N, GR_SRND_STRIDE] or NULL => Philox.  terrain_types: [N] int32 (non-decreasing). */
+int gr_env_startup(const GrConfig* cfg, const GrTrack* track, const GrState* st,
+                   const int32_t* terrain_types, int32_t* chunk_types_out, const float* srnd, uint64_t seed,
+                   void* stream);
+
+/* ManagerBasedRLEnv.reset(): _reset_idx(all envs) then observations.  reset_mask NULL => all. */
+int gr_env_reset(const GrConfig* cfg, const GrTrack* track, const GrState* st, const GrRandom* rng,
+                 const uint8_t* reset_mask, float* obs, float* critic_obs, float* aux_obs, void* stream);
+
+/* observation_manager.compute() alone (RslRlVecEnvWrapper.get_observations). */
+int gr_env_observe(const GrConfig* cfg, const GrTrack* track, const GrState* st, const GrRandom* rng,
+                   float* obs, float* critic_obs, float* aux_obs, void* stream);
+
+int gr_step_fwd(const GrConfig* cfg, const GrTrack* track, const GrState* st, const GrRandom* rng,
+                const GrStepIO* io, void* stream);
+
+/* Reverse sweep of the BPTT window over tape steps [t_begin, t_end) (analytic backward of
+ * DroneDynamics.step/align + CTBRController.compute + the tanh action map; replaces
+ * torch.autograd through QD/mdp/dynamics/droneDynamics.py:119-181, L/controllers/
+ * controller_diff.py:120-138, QD/mdp/diff_action.py:160-176 as driven by S/diff_rl/algorithms/bptt.py:38-44).
+ *   tape        [T][GR_TAPE_PLANES][tape_stride] float4 written by gr_step_fwd
+ *   grad_loss   [T][N] upstream gradient of extras["losses"], or NULL => uniform `grad_scale`
+ *   adjoint     [5][adj_stride] float4: carried adjoints (zero at the end of the window); in/out
+ *   grad_action [T][N][4]: row t-1 receives dL/da_{t-1} produced by step t (1-step action lag);
+ *               rows are OVERWRITTEN for t-1 in [t_begin-1, t_end-2]; row T-1 is not touched. */
+typedef struct GrBwdIO {
+  const float* tape;
+  int64_t tape_stride;
+  int32_t t_begin, t_end;
+  const float* grad_loss;
+  float grad_scale;
+  float* adjoint;
+  int64_t adj_stride;
+  float* grad_action;
+} GrBwdIO;
+int gr_step_bwd(const GrConfig* cfg, const GrState* st, const GrBwdIO* io, void* stream);
+
+/* Dense random tensor exactly as the in-kernel Philox path would draw it (parity chain). */
+int gr_fill_rand(float* rnd, int32_t num_envs, int32_t env_id_offset, uint64_t seed, uint32_t step, void* stream);
+int gr_fill_startup_rand(float* srnd, int32_t num_envs, int32_t env_id_offset, uint64_t seed, void* stream);
+
+/* ---- rollout storage (S/rsl_rl/ext/storage/rollout_storage.py) ---- */
+
+/* add_transitions (:71-88) fused with the time-out bootstrap of PPO.process_env_step
+ * (S/rsl_rl/ext/algorithms/ppo.py:85-97): one launch copies one transition into slot `step`. */
+typedef struct GrTransition {
+  const float* obs; const float* critic_obs; const float* actions; const float* rewards;
+  const void* dones; int32_t dones_is_int64;         /* uint8 or int64 [N] */
+  const float* values; const float* log_prob; const float* mu; const float* sigma;
+  const uint8_t* time_outs; float gamma;             /* NULL => no bootstrap */
+} GrTransition;
+typedef struct GrStorage {
+  float* obs; float* critic_obs; float* actions; float* rewards; uint8_t* dones;
+  float* values; float* log_prob; float* mu; float* sigma; float* returns; float* advantages;
+  int32_t T, N, obs_dim, critic_dim, act_dim;
+} GrStorage;
+int gr_storage_add(const GrStorage* s, const GrTransition* tr, int32_t step, void* stream);
+
+/* compute_returns (:113-127): GAE + advantage normalisation (unbiased std + 1e-8).
+ * scratch: >= gr_gae_scratch_bytes(N) bytes.  If moments != NULL the un-normalised
+ * (count, mean, M2) of this shard are written there as 3 doubles and, when
+ * `normalize` == 0, normalisation is left to gr_advantage_normalize (multi-GPU: all-reduce
+ * the moments in between). */
+int64_t gr_gae_scratch_bytes(int32_t N);
+int gr_compute_returns(const GrStorage* s, const float* last_values, float gamma, float lam,
+                       void* scratch, double* moments, int32_t normalize, void* stream);
+int gr_advantage_normalize(const GrStorage* s, const double* moments, void* stream);
+
+/* mini_batch_generator gather (:179-187): one launch gathers all nine fields for one mini-batch.
+ * indices: [B] int64 into the flattened [T*N] transitions. */
+typedef struct GrMiniBatch {
+  float* obs; float* critic_obs; float* actions; float* values; float* advantages; float* returns;
+  float* log_prob; float* mu; float* sigma;
+} GrMiniBatch;
+int gr_storage_gather(const GrStorage* s, const int64_t* indices, int32_t B, const GrMiniBatch* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRACING_H_ */

@@ -1,0 +1,68 @@
+"""TEST INFRASTRUCTURE: CPU emulation of the step/reset/startup/bwd kernels (same .cu sources, g++).
+
+Lets the kernel logic be debugged against the oracle without a GPU.  Only tests import this; the product
+(`RacingVecEnv` without the private ``_lib`` argument) loads libgracing.so and refuses non-CUDA devices.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+from generalizableracing_b200 import _lib as B
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libgracing_emul.so")
+_CSRC = os.path.join(_HERE, "..", "..", "generalizableracing_b200", "csrc")
+
+
+def _stale():
+    if not os.path.isfile(_SO):
+        return True
+    t = os.path.getmtime(_SO)
+    deps = [os.path.join(_HERE, f) for f in ("emul.cpp", "cuda_shim.h")] + \
+           [os.path.join(_CSRC, f) for f in ("racing_step.cu", "racing_bwd.cu", "gr_math.cuh", "gr_common.cuh")] + \
+           [os.path.join(_HERE, "..", "..", "include", "gracing.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build():
+    if _stale():
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", _SO,
+                        os.path.join(_HERE, "emul.cpp")], check=True)
+    return _SO
+
+
+class EmulLib:
+    """Duck-types the subset of libgracing.so that RacingVecEnv / BpttWindow call (stream argument ignored)."""
+
+    def __init__(self):
+        self._l = C.CDLL(build())
+        P = C.POINTER
+        self._l.emul_step_fwd.argtypes = [P(B.GrConfig), P(B.GrTrack), P(B.GrState), P(B.GrRandom), P(B.GrStepIO)]
+        self._l.emul_env_reset.argtypes = [P(B.GrConfig), P(B.GrTrack), P(B.GrState), P(B.GrRandom), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        self._l.emul_env_startup.argtypes = [P(B.GrConfig), P(B.GrTrack), P(B.GrState), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        self._l.emul_step_bwd.argtypes = [P(B.GrConfig), P(B.GrState), P(B.GrBwdIO)]
+        self._l.emul_fill_rand.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32]
+        self._l.emul_fill_startup_rand.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64]
+
+    def gr_step_fwd(self, cfg, tr, st, rng, io, stream):
+        return self._l.emul_step_fwd(cfg, tr, st, rng, io)
+
+    def gr_env_reset(self, cfg, tr, st, rng, mask, obs, critic, aux, stream):
+        return self._l.emul_env_reset(cfg, tr, st, rng, mask, 0 if mask else 1, obs, critic, aux)
+
+    def gr_env_observe(self, cfg, tr, st, rng, obs, critic, aux, stream):
+        return self._l.emul_env_reset(cfg, tr, st, rng, None, 2, obs, critic, aux)
+
+    def gr_env_startup(self, cfg, tr, st, types, chunk, srnd, seed, stream):
+        return self._l.emul_env_startup(cfg, tr, st, types, chunk, srnd, seed)
+
+    def gr_step_bwd(self, cfg, st, io, stream):
+        return self._l.emul_step_bwd(cfg, st, io)
+
+    def gr_fill_rand(self, rnd, n, off, seed, step, stream):
+        return self._l.emul_fill_rand(rnd, n, off, seed, step)
+
+    def gr_fill_startup_rand(self, srnd, n, off, seed, stream):
+        return self._l.emul_fill_startup_rand(srnd, n, off, seed)

@@ -1,0 +1,60 @@
+// TEST INFRASTRUCTURE -- see cuda_shim.h.  Exposes emul_* twins of the step/reset/startup/bwd/fill entry
+// points of include/gracing.h that execute the kernel sources on the CPU (1 thread per block, sequential).
+#define GR_CPU_EMUL 1
+#include "cuda_shim.h"
+#include "../../generalizableracing_b200/csrc/racing_step.cu"
+#include "../../generalizableracing_b200/csrc/racing_bwd.cu"
+
+using namespace gr;
+
+template <typename F>
+static void run_grid(int n, F&& f) {
+  blockDim_.x = 1; gridDim_.x = (unsigned)n; threadIdx_.x = 0;
+  for (int b = 0; b < n; ++b) { blockIdx_.x = (unsigned)b; f(); }
+}
+
+extern "C" {
+
+int emul_step_fwd(const GrConfig* cfg, const GrTrack* tr, const GrState* st, const GrRandom* rng, const GrStepIO* io) {
+  const bool diff = io->loss || io->tape || io->loss_terms, stats = st->num_planes == GR_NUM_PLANES_WITH_STATS, philox = rng->rnd == nullptr,
+             noise = cfg->add_cmd_noise != 0;
+#define GO(a, b, c, d) if (noise == a && diff == b && philox == c && stats == d) { run_grid(st->num_envs, [&] { racing_step_fwd_kernel<a, b, c, d>(*cfg, *tr, *st, *rng, *io); }); return 0; }
+  GO(false, false, false, false) GO(false, false, false, true) GO(false, false, true, false) GO(false, false, true, true)
+  GO(false, true, false, false) GO(false, true, false, true) GO(false, true, true, false) GO(false, true, true, true)
+  GO(true, false, false, false) GO(true, false, false, true) GO(true, false, true, false) GO(true, false, true, true)
+  GO(true, true, false, false) GO(true, true, false, true) GO(true, true, true, false) GO(true, true, true, true)
+#undef GO
+  return -100;
+}
+
+int emul_env_reset(const GrConfig* cfg, const GrTrack* tr, const GrState* st, const GrRandom* rng, const uint8_t* mask, int mode, float* obs,
+                   float* critic, float* aux) {
+  const bool stats = st->num_planes == GR_NUM_PLANES_WITH_STATS, philox = rng->rnd == nullptr, noise = cfg->add_cmd_noise != 0;
+#define GO(a, c, d) if (noise == a && philox == c && stats == d) { run_grid(st->num_envs, [&] { racing_reset_kernel<a, c, d>(*cfg, *tr, *st, *rng, mask, mode, obs, critic, aux); }); return 0; }
+  GO(false, false, false) GO(false, false, true) GO(false, true, false) GO(false, true, true)
+  GO(true, false, false) GO(true, false, true) GO(true, true, false) GO(true, true, true)
+#undef GO
+  return -100;
+}
+
+int emul_env_startup(const GrConfig* cfg, const GrTrack* tr, const GrState* st, const int32_t* types, int32_t* chunk_types, const float* srnd,
+                     uint64_t seed) {
+  run_grid(st->num_envs, [&] { racing_startup_kernel(*cfg, *tr, *st, types, chunk_types, srnd, seed); });
+  return 0;
+}
+
+int emul_step_bwd(const GrConfig* cfg, const GrState* st, const GrBwdIO* io) {
+  run_grid(st->num_envs, [&] { racing_step_bwd_kernel(*cfg, *st, *io); });
+  return 0;
+}
+
+int emul_fill_rand(float* rnd, int32_t num_envs, int32_t env_id_offset, uint64_t seed, uint32_t step) {
+  run_grid(num_envs * (GR_RND_STRIDE / 4), [&] { fill_rand_kernel(reinterpret_cast<float4*>(rnd), num_envs, env_id_offset, seed, step); });
+  return 0;
+}
+
+int emul_fill_startup_rand(float* srnd, int32_t num_envs, int32_t env_id_offset, uint64_t seed) {
+  run_grid(num_envs, [&] { fill_startup_rand_kernel(srnd, num_envs, env_id_offset, seed); });
+  return 0;
+}
+}
