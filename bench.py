@@ -1,0 +1,446 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the racing hot path on N B200s (contract: see the task prompt / DESIGN.md §Measurement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (CUDA kernels through the C ABI)
+  python bench.py --impl reference [--gpus N] ...                # reference arm: the oracle (CPU torch port of the
+                                                                 # reference's own implementation) on the host cores
+
+A "step" = ONE env.step() over one batch of 65,536 envs (BASELINE.json configs[3]: randomized tracks, per-env domain
+randomisation, resets): one launch of gr_step_fwd.  `value` = device-timed throughput with inputs resident in HBM,
+`e2e` = the same metric through RacingVecEnv.step() with pinned HOST actions in and obs/reward/dones out every step.
+L2 hygiene: the step's working set (~40 MB at 65,536 envs) would live in the 126 MB L2, so the timed loop rotates over
+R independent env batches (R x working set >= 3 x L2): every step reads its state from HBM.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+NUM_ENVS = 65536
+STAGE = 1
+L2_BYTES = 126e6
+METRIC = "env-steps/sec (fwd)"
+UNIT = "env-steps/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+def algorithmic_bytes(cfg, stats: bool, critic: bool = True, dones64: bool = True) -> int:
+    """Every persistent column read once + written once, every API output written once."""
+    rd = 7 * 16 + 5 * 16 + 16                      # hot planes, cold planes, action
+    wr = 7 * 16 + 64 + 4 + 1 + 1                   # hot planes, policy obs, reward, terminated, time_out
+    if critic:
+        wr += 64
+    if dones64:
+        wr += 8
+    if cfg.add_cmd_noise:
+        rd += 32                                   # gate-noise planes (read-only except on gate switch / reset)
+    if stats:
+        rd += 32
+        wr += 32
+    return rd + wr
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def dist_setup(n_gpus: int):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def max_over_ranks(x: float, world: int, device) -> float:
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_ours(args):
+    from generalizableracing_b200 import build as BLD
+    BLD.build()
+    from generalizableracing_b200 import _lib as B
+    from generalizableracing_b200.config import RacingCfg
+    from generalizableracing_b200.env import RacingVecEnv
+    from generalizableracing_b200.tracks import synthetic_track_table
+
+    rank, world, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    N = args.envs
+    cfg = RacingCfg.for_stage(STAGE)
+    table = synthetic_track_table()
+    stats = not args.no_stats
+    b_alg = algorithmic_bytes(cfg, stats)
+    working_set = N * (b_alg + 0)                                      # bytes touched by one step
+    R = max(2, int(3 * L2_BYTES / working_set) + 1)
+    envs = [RacingVecEnv(cfg, table, N, device=dev, seed=42 + r, episode_stats=stats, env_id_offset=rank * N,
+                         global_num_envs=world * N) for r in range(R)]
+    for e in envs:
+        e.reset()
+        # PPO's init_at_random_ep_len (on_policy_runner.py:118-121): staggered time-outs, ~1/200 of the envs reset per step
+        e.episode_length_buf = torch.randint(0, cfg.max_episode_length, (N,), device=dev, dtype=torch.int32)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    actions = [torch.randn(N, 4, device=dev, generator=g) * 0.5 for _ in range(R)]      # resident in HBM before the timed region
+    lib = B.load()
+
+    # ---- one "round" = one step on each of the R env batches, captured once in a CUDA graph (launch-bound otherwise)
+    ios = []
+    for e, a in zip(envs, actions):
+        o = e._outs[0]
+        io = B.GrStepIO()
+        io.action = a.data_ptr()
+        io.obs, io.critic_obs, io.aux_obs = o["obs"].data_ptr(), o["critic"].data_ptr(), o["aux"].data_ptr()
+        io.reward, io.terminated, io.time_out, io.dones = o["reward"].data_ptr(), o["terminated"].data_ptr(), o["time_out"].data_ptr(), o["dones"].data_ptr()
+        io.log_accum = e._log_accum.data_ptr()
+        ios.append(io)
+    launches = [0]
+
+    def one_round(step0: int):
+        s = torch.cuda.current_stream(dev).cuda_stream
+        for k, (e, io) in enumerate(zip(envs, ios)):
+            rng = B.GrRandom(None, e.seed, (step0 + k) & 0xFFFFFFFF)
+            B.check(lib.gr_step_fwd(C.byref(e._gcfg), C.byref(e._track), C.byref(e._state), C.byref(rng), C.byref(io), s), "gr_step_fwd")
+            launches[0] += 1
+
+    # warm-up (eager), then capture
+    rounds_w = max(1, -(-args.warmup // R))
+    for w in range(rounds_w):
+        one_round(w * R)
+    torch.cuda.synchronize(dev)
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        one_round(10_000)            # warm the capture stream
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    with torch.cuda.graph(graph):
+        one_round(20_000)
+    graph.replay()
+    torch.cuda.synchronize(dev)
+
+    K = args.steps
+    rounds = max(1, -(-K // R))
+    K = rounds * R                                                     # timed steps are a whole number of rounds
+    barrier(world)
+    torch.cuda.synchronize(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for e in envs:
+        e._log_accum.zero_()
+    replays = 0
+    with ClockSampler(local) as clk:
+        ev0.record()
+        for _ in range(rounds):
+            graph.replay()
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        ms_local = ev0.elapsed_time(ev1)
+        replays += rounds
+        # keep the GPU under the same load a little longer so the 100 ms sampler sees it
+        t_end = time.time() + (0.6 if rank == 0 else 0.0)
+        while time.time() < t_end:
+            graph.replay()
+            replays += 1
+        torch.cuda.synchronize(dev)
+    barrier(world)
+    # emergent reset rate of the timed workload (warm-up + timed + load-holding replays), from the kernels' own log accumulators
+    tot = torch.stack([e._log_accum.sum(dim=0) for e in envs]).sum(dim=0)
+    reset_rate = float(tot[0].item()) / (replays * R * N)
+    ms = max_over_ranks(ms_local, world, dev)
+    value = world * N * K / (ms * 1e-3)
+    kernel_us = ms_local * 1e3 / K
+    peak, peak_src, _ = load_peaks()
+    achieved = b_alg * N / (kernel_us * 1e-6) / 1e9
+
+    # ---- e2e: public API, host buffers, H2D + D2H inside the timed region
+    env = envs[0]
+    h_act = torch.randn(N, 4).pin_memory()
+    h_obs = torch.empty(N, 16).pin_memory()
+    h_rew = torch.empty(N).pin_memory()
+    h_done = torch.empty(N, dtype=torch.int64).pin_memory()
+    d_act = torch.empty(N, 4, device=dev)
+
+    def e2e_step():
+        d_act.copy_(h_act, non_blocking=True)
+        obs, rew, dones, _ = env.step(d_act)
+        h_obs.copy_(obs, non_blocking=True)
+        h_rew.copy_(rew, non_blocking=True)
+        h_done.copy_(dones, non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        e2e_step()
+    Ke = max(10, min(args.steps, 200))
+    barrier(world)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(Ke):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3), world, dev)
+    e2e_value = world * N * Ke / (e2e_ms * 1e-3)
+    h2d = N * 4 * 4
+    d2h = N * 16 * 4 + N * 4 + N * 8
+
+    # ---- extras: fwd+bwd BPTT (C3) and GAE (C2) device timings, rank 0 only
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        extra = bench_extras(dev, cfg, table)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(sample_s=args.cpu_seconds)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": rounds_w * R,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"C4: {N} envs/GPU, STAGE {STAGE}, synthetic 20x10 curriculum tracks x 8 gates, per-env DR, "
+                                   f"staggered resets, in-kernel Philox, episode_stats={stats}",
+                       "envs_per_gpu": N, "l2": f"rotating {R} independent env batches ({R}x{working_set / 1e6:.0f} MB > 126 MB L2), "
+                                               f"K timed steps = {rounds} CUDA-graph replays of {R} launches",
+                       "mass_kg": cfg.mass, "actions": "N(0, 0.5^2) resident in HBM", "resets_per_env_step": reset_rate},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                    "api": "RacingVecEnv.step (pinned host actions in; obs, reward, dones out; sync per step)"},
+            "gpu_launches": K,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "racing_step_fwd_kernel<noise,nodiff,philox,stats>",
+                         "bytes_per_env_step": b_alg, "kernel_us": kernel_us, "peak_source": peak_src},
+            "clocks": clk.summary(),
+            "cpu_baseline": cpu,
+            "extra": extra,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def bench_extras(dev, cfg, table):
+    """Device timings of the other §8 kernels (reported, not the headline): BPTT fwd+bwd (C3) and GAE (C2)."""
+    import dataclasses
+    from generalizableracing_b200.env import RacingVecEnv
+    from generalizableracing_b200.storage import RolloutStorage
+    out = {}
+    # C3: 16384 envs, horizon 32, forward with tape + one reverse sweep
+    N, H = 16384, 32
+    dcfg = dataclasses.replace(cfg, is_differentiable_physics=True)
+    env = RacingVecEnv(dcfg, table, N, device=dev, seed=7, episode_stats=False, bptt_horizon=H)
+    env.reset()
+    env.episode_length_buf = torch.randint(0, cfg.max_episode_length, (N,), device=dev, dtype=torch.int32)
+    acts = torch.randn(H, N, 4, device=dev) * 0.5
+
+    def window():
+        env.detach()
+        for t in range(H):
+            env.step(acts[t])
+        return env._bptt.backward_window()
+
+    for _ in range(3):
+        window()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        window()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    out["bptt_fwd_bwd"] = {"envs": N, "horizon": H, "ms_per_window": ms, "env_steps_per_s": N * H / (ms * 1e-3),
+                           "note": "python-driven launches (33 per window); host-bound, see DESIGN.md"}
+    # bwd sweep alone
+    e0.record()
+    for _ in range(reps):
+        env._bptt.backward_window()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_b = e0.elapsed_time(e1) / reps
+    out["bptt_bwd_sweep"] = {"ms": ms_b, "GBps_algorithmic": N * H * (7 * 16 + 16) / (ms_b * 1e-3) / 1e9}
+    # C2: GAE on [24, 4096]
+    T, N2 = 24, 4096
+    sto = RolloutStorage("rl", N2, T, [16], [16], [4], device=dev)
+    sto.rewards.normal_()
+    sto.values.normal_()
+    last = torch.randn(N2, 1, device=dev)
+    for _ in range(3):
+        sto.compute_returns(last, 0.99, 0.95)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(50):
+        sto.compute_returns(last, 0.99, 0.95)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    out["gae_24x4096_us"] = e0.elapsed_time(e1) * 1e3 / 50
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _oracle_env(N, threads):
+    """The reference arm: the oracle = CPU torch restatement of the reference's own implementation of the path
+    (the reference itself needs Isaac Sim; /root/reference does not exist on the GPU box)."""
+    from generalizableracing_b200 import layout as L_
+    from generalizableracing_b200.config import RacingCfg
+    from generalizableracing_b200.tracks import synthetic_track_table
+    from oracle import racing_oracle as RO
+    torch.set_num_threads(threads)
+    cfg = RacingCfg.for_stage(STAGE)
+    g = torch.Generator().manual_seed(0)
+    srnd = torch.rand(N, L_.SRND_STRIDE, generator=g)
+    srnd[:, 12:] = torch.randn(N, 4, generator=g)
+    env = RO.OracleRacingEnv(cfg, synthetic_track_table(), N, srnd)
+
+    def draw():
+        r = torch.rand(N, L_.RND_STRIDE, generator=g)
+        r[:, :8] = torch.randn(N, 8, generator=g)
+        return r
+
+    env.reset(draw())
+    env.episode_length_buf[:] = torch.randint(0, cfg.max_episode_length, (N,), generator=g)
+    return env, draw, g
+
+
+def cpu_baseline(sample_s: float = 15.0, N: int = NUM_ENVS):
+    threads = os.cpu_count() or 1
+    env, draw, g = _oracle_env(N, threads)
+    a = torch.randn(N, 4, generator=g) * 0.5
+    with torch.no_grad():
+        for _ in range(2):
+            env.step(a, draw())
+        n, t_used = 0, 0.0
+        while t_used < sample_s and n < 200:
+            r = draw()
+            t0 = time.perf_counter()
+            env.step(a, r)
+            t_used += time.perf_counter() - t0
+            n += 1
+    return {"value": N * n / t_used, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} steps of the same C4 workload ({N} envs, STAGE {STAGE}) on the oracle (CPU torch port of the reference), "
+                      f"{t_used:.1f} s, torch.set_num_threads({threads}), no_grad"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    N = args.envs
+    env, draw, g = _oracle_env(N, threads)
+    a = torch.randn(N, 4, generator=g) * 0.5
+    W, K = max(1, min(args.warmup, 3)), max(1, min(args.steps, 20))
+    with torch.no_grad():
+        for _ in range(W):
+            env.step(a, draw())
+        rs = [draw() for _ in range(K)]
+        t0 = time.perf_counter()
+        for r in rs:
+            env.step(a, r)
+        dt = time.perf_counter() - t0
+    value = N * K / dt
+    cfg = env.cfg
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": K, "warmup": W,
+        "ms_per_step": dt * 1e3 / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C4: {N} envs, STAGE {STAGE}, synthetic 20x10 curriculum tracks x 8 gates, per-env DR, staggered resets "
+                               f"(each step = one full env.step over the {N}-env batch on the host cores)", "envs_per_gpu": N, "mass_kg": cfg.mass},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{K} timed steps, oracle = CPU torch port of the reference path (reference needs Isaac Sim), {threads} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=NUM_ENVS, help="envs per GPU (BASELINE configs[3]: 65536)")
+    ap.add_argument("--no-stats", action="store_true", help="drop the per-env episode-sum planes (extras['log'] reward terms)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the racing hot path has no CPU fallback (use --impl reference for the CPU arm)")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

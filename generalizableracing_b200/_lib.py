@@ -41,7 +41,7 @@ class GrTrack(C.Structure):
 
 class GrState(C.Structure):
     _fields_ = [("planes", c_p), ("plane_stride", C.c_int64), ("num_envs", c_i), ("num_planes", c_i),
-                ("env_id_offset", c_i), ("max_types_per_block", c_i), ("chunk_types", c_p)]
+                ("env_id_offset", c_i), ("max_types_per_block", c_i), ("block_threads", c_i), ("chunk_types", c_p)]
 
 
 class GrRandom(C.Structure):
@@ -76,6 +76,7 @@ class GrMiniBatch(C.Structure):
 
 
 GR_LOG_SLOTS = 16
+GR_LOG_SHARDS = 32
 STATUS = {0: "GR_OK", -1: "GR_ERR_NULL", -2: "GR_ERR_SIZE", -3: "GR_ERR_ALIGN", -4: "GR_ERR_CONFIG", -5: "GR_ERR_SMEM"}
 
 # symbol -> (restype, argtypes); every symbol include/gracing.h declares

@@ -17,7 +17,7 @@ SOURCES = ["racing_step.cu", "racing_bwd.cu", "rollout.cu"]
 HEADERS = ["gr_math.cuh", "gr_common.cuh", os.path.join("..", "..", "include", "gracing.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"]
+              "--expt-relaxed-constexpr", "-prec-div=false", "-prec-sqrt=false", "-Xcompiler", "-fPIC"]
 
 
 def _nvcc() -> str:

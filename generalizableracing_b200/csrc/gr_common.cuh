@@ -67,6 +67,15 @@ struct RandSrc<true> {
   }
 };
 
+// full-warp sum (all 32 lanes participate)
+__device__ __forceinline__ float warp_sum(float v) {
+#ifndef GR_CPU_EMUL
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+  return v;
+}
+
 // Gate table slice staged in shared memory: rows of types [type_lo, type_lo + ntypes).
 struct TrackSmem {
   const float4* rows;   // shared

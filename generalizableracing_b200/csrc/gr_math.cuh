@@ -104,6 +104,43 @@ __device__ __forceinline__ bool bad_pose(Q4 q) {
   return (fabsf(roll) > GR_HALF_PI_F) || (fabsf(pitch) > GR_HALF_PI_F);
 }
 
+// ---- fast math (hot path only; the rare reset path keeps libm accuracy) ---------------------------
+// Absolute errors ~1e-7 on O(1) results, far inside the 1e-5 relative tolerance of the parity tests.
+#ifdef GR_CPU_EMUL
+__device__ __forceinline__ float fm_rcp(float x) { return 1.0f / x; }
+__device__ __forceinline__ float fm_rsqrt(float x) { return 1.0f / sqrtf(x); }
+__device__ __forceinline__ float fm_sqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ float fm_exp2(float x) { return exp2f(x); }
+__device__ __forceinline__ float fm_log2(float x) { return log2f(x); }
+__device__ __forceinline__ void fm_sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __forceinline__ float sqrt_rn(float x) { return sqrtf(x); }
+#else
+__device__ __forceinline__ float fm_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fm_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fm_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fm_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fm_log2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void fm_sincos(float x, float* s, float* c) { *s = __sinf(x); *c = __cosf(x); }
+__device__ __forceinline__ float sqrt_rn(float x) { return __fsqrt_rn(x); }      // correctly rounded: gate predicate
+#endif
+// tanh(x) = 1 - 2/(1 + e^{2x}); saturates correctly for |x| large (e^{2x} -> inf / 0)
+__device__ __forceinline__ float fm_tanh(float x) { return 1.0f - 2.0f * fm_rcp(1.0f + fm_exp2(x * 2.8853900817779268f)); }
+
+// Rotation by a quaternion with the shared terms hoisted (same literal formula, re-associated):
+//   rot(q,v) = s v + w2 (u x v) + u2 (u.v),  rotinv: minus on the cross term;  s = 2w^2-1, w2 = 2w, u2 = 2u
+struct RotQ {
+  V3 u, u2; float s, w2;
+  __device__ __forceinline__ explicit RotQ(Q4 q) : u(v3(q.x, q.y, q.z)), u2(v3(2.0f * q.x, 2.0f * q.y, 2.0f * q.z)), s(2.0f * q.w * q.w - 1.0f), w2(2.0f * q.w) {}
+  __device__ __forceinline__ V3 rot(V3 v) const {
+    const V3 c = cross(u, v); const float d = dot(u, v);
+    return V3{v.x * s + c.x * w2 + u2.x * d, v.y * s + c.y * w2 + u2.y * d, v.z * s + c.z * w2 + u2.z * d};
+  }
+  __device__ __forceinline__ V3 rotinv(V3 v) const {
+    const V3 c = cross(u, v); const float d = dot(u, v);
+    return V3{v.x * s - c.x * w2 + u2.x * d, v.y * s - c.y * w2 + u2.y * d, v.z * s - c.z * w2 + u2.z * d};
+  }
+};
+
 // ---- Philox4x32-10 (Salmon et al. 2011) ------------------------------------------------
 struct Philox {
   uint32_t k0, k1;      // key = seed
@@ -129,9 +166,10 @@ __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.96
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   const float u1 = (float)((a >> 8) + 1u) * 5.9604644775390625e-8f;    // (0,1]
   const float u2 = (float)(b >> 8) * 5.9604644775390625e-8f;
-  const float r = sqrtf(-2.0f * logf(u1));
+  // r = sqrt(-2 ln u1) = sqrt(-2 ln2 * log2 u1); angle in (-pi, pi] so the MUFU sin/cos stay in their accurate range
+  const float r = fm_sqrt(-1.3862943611198906f * fm_log2(u1));
   float s, c;
-  sincospif(2.0f * u2, &s, &c);
+  fm_sincos((u2 - 0.5f) * GR_2PI_F, &s, &c);
   return make_float2(r * c, r * s);
 }
 

@@ -168,7 +168,15 @@ __device__ __forceinline__ void store_env(const EnvRegs& e, float4* __restrict__
 
 // =============================================================================================
 // the step kernel
+//
+// Latency notes (ncu, 65,536 envs = one wave of ~14 warps/SM): the kernel is bound by the per-warp dependent
+// instruction chain, not by issue slots or DRAM, so the hot path uses MUFU-based fast math (no slow-path
+// branches / calls), hoists the shared quaternion terms (RotQ), and computes every view of the post-step
+// state once: the reward section and the observation section share them unless the env was reset or
+// switched gate in this step (rare, recomputed in a divergent tail).
 // =============================================================================================
+__device__ __forceinline__ float4 fm_tanh4(float4 a) { return make_float4(fm_tanh(a.x), fm_tanh(a.y), fm_tanh(a.z), fm_tanh(a.w)); }
+
 template <bool kNoise, bool kDiff, bool kPhilox, bool kStats>
 __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg, const GrTrack track, const GrState st,
                                                               const GrRandom rng, const GrStepIO io) {
@@ -188,37 +196,40 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
   const float4 n01 = rs.get4(0), n23 = rs.get4(1);   // obs normals (slots 0..5), thr_est_error normal (slot 6)
 
   const TrackSmem tr = stage_track(track, reinterpret_cast<const int2*>(st.chunk_types), st.num_envs, smem_rows);
-  if (!active) return;
+  // a warp that is entirely past the last env leaves; in the (single) ragged warp the inactive lanes keep shadowing
+  // the last env so the warp collectives below stay full-width, and skip every store
+  if (!__any_sync(0xffffffffu, active)) return;
 
   const int type = (int)pk_type(e.pk);
   int level = (int)pk_level(e.pk);
   int gate_id = (int)pk_gate(e.pk);
   const uint32_t fresh = pk_fresh(e.pk);
   V3 origin = xyz(tr.origin_row(type, level));
+  V3 gate_rel = tr.gate(type, level, gate_id);
   const float dt = cfg.dt;
   const V3 J = v3(cfg.inertia[0], cfg.inertia[1], cfg.inertia[2]);
-  const V3 Jinv = v3(1.0f / J.x, 1.0f / J.y, 1.0f / J.z);
+  const V3 Jinv = v3(fm_rcp(J.x), fm_rcp(J.y), fm_rcp(J.z));
+  const float inv_m = fm_rcp(e.m);
+  const float s0 = cfg.action_scale0, sb = cfg.body_rate_bound;
 
   // ---- 1. process_action (L/managers/action_manager.py:44-45; QD/mdp/diff_action.py:160-176) ----
   // FIFO (lag 1): the applied action is a_{t-1}; prev_action is a_{t-1} unless the latches were zeroed by a reset
-  const float4 th_lag = tanh4(e.fifo);
-  const float4 th_a = tanh4(a_t);
+  const float4 th_lag = fm_tanh4(e.fifo);
+  const float4 th_a = fm_tanh4(a_t);
   const float4 th_prev = fresh ? make_float4(0.f, 0.f, 0.f, 0.f) : th_lag;
   // get_state_from_sim (QD/mdp/diff_action.py:126-154)
+  const RotQ R0(e.q);
   const V3 p = e.w - origin;
-  const V3 om_b = quat_rotate_inverse(e.q, e.om);
-  const V3 v_b = quat_rotate_inverse(e.q, e.v);
-  const V3 aacc_b = quat_rotate_inverse(e.q, e.aacc);
-  float cmd0 = th_lag.x * cfg.action_scale0 + cfg.action_scale0;
-  cmd0 *= e.thr;
-  const V3 cmd_rate = v3(th_lag.y * cfg.body_rate_bound + 0.0f, th_lag.z * cfg.body_rate_bound + 0.0f, th_lag.w * cfg.body_rate_bound + 0.0f);
+  const V3 om_b = R0.rotinv(e.om);
+  const V3 v_b = R0.rotinv(e.v);
+  const V3 aacc_b = R0.rotinv(e.aacc);
+  const float cmd0 = (th_lag.x * s0 + s0) * e.thr;
+  const V3 cmd_rate = v3(th_lag.y * sb, th_lag.z * sb, th_lag.w * sb);
 
   // ---- CTBRController.compute (L/controllers/controller_diff.py:120-138) ----
   const float thrust_des = fminf(fmaxf(cmd0, cfg.thrust_lo), cfg.thrust_hi);
   const float f_new = (1.0f - e.ef) * thrust_des + e.ef * e.f;
-  const V3 rate_c = v3(fminf(fmaxf(cmd_rate.x, -cfg.body_rate_bound), cfg.body_rate_bound),
-                       fminf(fmaxf(cmd_rate.y, -cfg.body_rate_bound), cfg.body_rate_bound),
-                       fminf(fmaxf(cmd_rate.z, -cfg.body_rate_bound), cfg.body_rate_bound));
+  const V3 rate_c = v3(fminf(fmaxf(cmd_rate.x, -sb), sb), fminf(fmaxf(cmd_rate.y, -sb), sb), fminf(fmaxf(cmd_rate.z, -sb), sb));
   const V3 gyro = cross(om_b, J * om_b);
   const V3 torque_des = J * (e.kp * (rate_c - om_b)) + gyro - e.kd * aacc_b;
   const V3 one_m_etau = v3(1.0f - e.etau.x, 1.0f - e.etau.y, 1.0f - e.etau.z);
@@ -226,26 +237,30 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
 
   // ---- DroneDynamics.step (QD/mdp/dynamics/droneDynamics.py:119-135) ----
   const V3 F_b = v3(0.f, 0.f, f_new) - e.k2 * v_b * vabs(v_b) - e.k1 * v_b;
-  const V3 acc = v3(0.f, 0.f, -cfg.gravity) + quat_rotate(e.q, F_b) / e.m;
-  const V3 alpha = Jinv * tau_new - Jinv * gyro;
-  const V3 p1 = p + e.v * dt + 0.5f * acc * dt * dt;
-  const Q4 dq = quat_mul(e.q, Q4{0.f, om_b.x, om_b.y, om_b.z});
-  Q4 qt = Q4{e.q.w + 0.5f * dq.w * dt, e.q.x + 0.5f * dq.x * dt, e.q.y + 0.5f * dq.y * dt, e.q.z + 0.5f * dq.z * dt};
-  const float qn = sqrtf(qt.w * qt.w + qt.x * qt.x + qt.y * qt.y + qt.z * qt.z);
-  const Q4 q1 = Q4{qt.w / qn, qt.x / qn, qt.y / qn, qt.z / qn};
+  const V3 acc = v3(0.f, 0.f, -cfg.gravity) + R0.rot(F_b) * inv_m;
+  const V3 alpha = Jinv * (tau_new - gyro);
+  const V3 p1 = p + e.v * dt + (0.5f * dt * dt) * acc;
+  const float hdt = 0.5f * dt;
+  // q + 0.5*dt*qmul(q, (0, om_b)): Hamilton product with a pure quaternion
+  const Q4 qt = Q4{e.q.w - hdt * (e.q.x * om_b.x + e.q.y * om_b.y + e.q.z * om_b.z),
+                   e.q.x + hdt * (e.q.w * om_b.x + e.q.y * om_b.z - e.q.z * om_b.y),
+                   e.q.y + hdt * (e.q.w * om_b.y + e.q.z * om_b.x - e.q.x * om_b.z),
+                   e.q.z + hdt * (e.q.w * om_b.z + e.q.x * om_b.y - e.q.y * om_b.x)};
+  const float inv_qn = fm_rsqrt(qt.w * qt.w + qt.x * qt.x + qt.y * qt.y + qt.z * qt.z);
+  const Q4 q1 = Q4{qt.w * inv_qn, qt.x * inv_qn, qt.y * inv_qn, qt.z * inv_qn};
   const V3 v1 = e.v + acc * dt;
   const V3 omb1 = om_b + alpha * dt;
-  const V3 omw1 = quat_rotate(q1, omb1);
+  const RotQ R1(q1);
+  const V3 omw1 = R1.rot(omb1);
 
   // ---- BPTT tape planes 0..5 of this step (consumer: racing_bwd.cu; SURVEY.md A.6/A.7, derived form) ----
-  if (kDiff && io.tape) {
+  if (kDiff && io.tape && active) {
     float4* __restrict__ T = reinterpret_cast<float4*>(io.tape);
     const int64_t TS = io.tape_stride;
-    const float b = cfg.body_rate_bound;
     const float m0 = (cmd0 >= cfg.thrust_lo && cmd0 <= cfg.thrust_hi) ? 1.0f : 0.0f;
-    const float A0 = m0 * e.thr * cfg.action_scale0 * (1.0f - th_lag.x * th_lag.x) * (1.0f - e.ef);
-    const V3 mk = v3((cmd_rate.x >= -b && cmd_rate.x <= b) ? b : 0.0f, (cmd_rate.y >= -b && cmd_rate.y <= b) ? b : 0.0f,
-                     (cmd_rate.z >= -b && cmd_rate.z <= b) ? b : 0.0f);
+    const float A0 = m0 * e.thr * s0 * (1.0f - th_lag.x * th_lag.x) * (1.0f - e.ef);
+    const V3 mk = v3((cmd_rate.x >= -sb && cmd_rate.x <= sb) ? sb : 0.0f, (cmd_rate.y >= -sb && cmd_rate.y <= sb) ? sb : 0.0f,
+                     (cmd_rate.z >= -sb && cmd_rate.z <= sb) ? sb : 0.0f);
     const V3 A = mk * v3(1.0f - th_lag.y * th_lag.y, 1.0f - th_lag.z * th_lag.z, 1.0f - th_lag.w * th_lag.w) * one_m_etau * J * e.kp;
     const V3 D = -(2.0f * (e.k2 * vabs(v_b)) + e.k1);
     __stcs(T + 0 * TS + i, pack(e.q));
@@ -257,7 +272,7 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
   }
 
   // ---- 2. "physics": closure A.1, truth := nominal; world pose, last angular acceleration ----
-  e.w = p1 + origin; e.q = q1; e.v = v1; e.om = omw1; e.aacc = quat_rotate(q1, alpha);
+  e.w = p1 + origin; e.q = q1; e.v = v1; e.om = omw1; e.aacc = R1.rot(alpha);
   e.f = f_new; e.tau = tau_new;
   // ---- 3. align (droneDynamics.py:156-181): value = sim-derived state; aligned local position for the loss ----
   const V3 p_al = e.w - origin;
@@ -268,44 +283,41 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
   const bool time_out = e.eplen >= cfg.max_episode_length;
   bool terminated = false;
   if (cfg.term_oob) terminated = terminated || (e.w.z < cfg.oob_lo) || (e.w.z > cfg.oob_hi);
-  bool bad = false;
-  if (cfg.term_bad_pose || cfg.w_reward[5] != 0.0f) bad = bad_pose(q1);
+  // bad_pose: |wrap_to_pi(roll)| > pi/2  <=>  cos_roll < 0 ; the pitch clause can never fire (|asin| <= pi/2).
+  // Equivalent to the literal atan2/asin/%2pi/wrap_to_pi chain of termination.py:29-33 except inside the few-ulp
+  // band |cos_roll| ~ 1e-7 where the literal form is itself a rounding lottery (tests/test_bad_pose.py).
+  const bool bad = (1.0f - 2.0f * (q1.x * q1.x + q1.y * q1.y)) < 0.0f;
   if (cfg.term_bad_pose) terminated = terminated || bad;
 
   // ---- 6. rewards (QD/mdp/rewards.py:154-253; RewardManager.compute: sum_i term_i * w_i * dt) ----
+  const V3 vec = (gate_rel + origin) - e.w;                       // gate_pose_gt_w - root_pos_w
+  const float d2 = vec.x * vec.x + vec.y * vec.y + vec.z * vec.z;
+  const float dist = sqrt_rn(d2);
+  const bool pass_pre = dist < cfg.update_threshold;
+  const V3 vb1 = R1.rotinv(v1);
+  const V3 cg0 = R1.rotinv(vec);                                  // command_gt[:, :3]
   float terms[GR_NUM_REWARD_TERMS];
   float reward = 0.0f;
   {
-    const V3 g_gt = tr.gate(type, level, gate_id) + origin;
-    const V3 vec = g_gt - e.w;
-    const V3 vb1 = quat_rotate_inverse(q1, v1);
-    const V3 cmd_gt0 = quat_rotate_inverse(q1, vec);
-    terms[0] = cosine_similarity(vb1, cmd_gt0);                                                   // :154-161
-    const V3 br = v3(th_a.y * cfg.body_rate_bound, th_a.z * cfg.body_rate_bound, th_a.w * cfg.body_rate_bound);
-    terms[1] = norm(br);                                                                          // :188-194
+    const float inv_nc = fm_rsqrt(fmaxf(dot(cg0, cg0), 1e-16f));
+    const float inv_nv = fm_rsqrt(fmaxf(dot(vb1, vb1), 1e-16f));
+    terms[0] = dot(vb1, cg0) * inv_nv * inv_nc;                                                   // :154-161
+    terms[1] = sb * fm_sqrt(th_a.y * th_a.y + th_a.z * th_a.z + th_a.w * th_a.w);                 // :188-194
     {
-      const float s0 = cfg.action_scale0, sb = cfg.body_rate_bound;                                // :196-206
-      const float d0 = (th_a.x * s0 + s0) - (th_prev.x * s0 + s0), d1 = (th_a.y * sb + 0.0f) - (th_prev.y * sb + 0.0f),
-                  d2 = (th_a.z * sb + 0.0f) - (th_prev.z * sb + 0.0f), d3 = (th_a.w * sb + 0.0f) - (th_prev.w * sb + 0.0f);
-      terms[2] = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+      const float d0 = (th_a.x - th_prev.x) * s0, d1 = (th_a.y - th_prev.y) * sb, d2r = (th_a.z - th_prev.z) * sb,
+                  d3 = (th_a.w - th_prev.w) * sb;                                                  // :196-206
+      terms[2] = d0 * d0 + d1 * d1 + d2r * d2r + d3 * d3;
     }
-    {
-      const float n = fmaxf(norm(cmd_gt0), 1e-12f);                                                // :171-179
-      terms[3] = cosine_similarity(cmd_gt0 / n, v3(1.0f, 0.0f, 0.0f));
-    }
-    const float d = norm(vec);                                                                     // :215-224
-    terms[4] = (d < cfg.update_threshold ? 1.0f : 0.0f) * (1.0f / (d * d + 1.0f));
+    terms[3] = cg0.x * inv_nc;                                                                    // :171-179
+    terms[4] = pass_pre ? fm_rcp(d2 + 1.0f) : 0.0f;                                               // :215-224
     terms[5] = bad ? 1.0f : 0.0f;                                                                  // :244-253
 #pragma unroll
     for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k) {
-      if (cfg.w_reward[k] != 0.0f) {
-        const float value = terms[k] * cfg.w_reward[k] * dt;
-        reward = reward + value;
-        terms[k] = value / dt;
-        if (kStats) { if (k < 4) (&eps0.x)[k] += value; else (&eps1.x)[k - 4] += value; }
-      } else {
-        terms[k] = 0.0f;
-      }
+      const float tw = cfg.w_reward[k] != 0.0f ? terms[k] * cfg.w_reward[k] : 0.0f;
+      const float value = tw * dt;
+      reward += value;
+      terms[k] = tw;                                              // RewardManager._step_reward = value / dt
+      if (kStats) { if (k < 4) (&eps0.x)[k] += value; else (&eps1.x)[k - 4] += value; }
     }
   }
   e.aux = terms[4] > 0.0f ? 1.0f : 0.0f;                 // cross_obs (QD/mdp/observation.py:97-104)
@@ -313,54 +325,74 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
   // ---- 7. reset (L/envs/manager_based_diff_rl_env.py:232-247,362-410) ----
   const bool reset = terminated || time_out;
   bool noise_dirty = false;
-  if (reset) {
-    if (io.log_accum) {
-      atomicAdd(io.log_accum + GR_LOG_NUM_RESET, 1.0f);
-      atomicAdd(io.log_accum + GR_LOG_SUM_GATES, (float)pk_acc(e.pk));
-      if (time_out) atomicAdd(io.log_accum + GR_LOG_NUM_TIMEOUT, 1.0f);
-      if (terminated) atomicAdd(io.log_accum + GR_LOG_NUM_TERMINATED, 1.0f);
-      if (kStats) {
+  bool passed = pass_pre;                                 // 8. on an env that did not reset this is the same test
+  // episode log (extras["log"], manager_based_diff_rl_env.py:380-407): warp-aggregated, sharded atomics -- a plain
+  // atomicAdd per resetting env serialises on one L2 line and cost 3x the whole kernel at a 5 % reset rate.
+  if (io.log_accum) {
+    const unsigned rm = __ballot_sync(0xffffffffu, reset && active);
+    if (rm) {
+      const bool r = reset && active;
+      float v[4 + GR_NUM_REWARD_TERMS];
+      v[0] = r ? 1.0f : 0.0f;
+      v[1] = r ? (float)pk_acc(e.pk) : 0.0f;
+      v[2] = (r && time_out) ? 1.0f : 0.0f;
+      v[3] = (r && terminated) ? 1.0f : 0.0f;
 #pragma unroll
-        for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k)
-          atomicAdd(io.log_accum + GR_LOG_SUM_EPSUM + k, k < 4 ? (&eps0.x)[k] : (&eps1.x)[k - 4]);
+      for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k) v[4 + k] = (kStats && r) ? (k < 4 ? (&eps0.x)[k] : (&eps1.x)[k - 4]) : 0.0f;
+#pragma unroll
+      for (int k = 0; k < 4 + GR_NUM_REWARD_TERMS; ++k) {
+        if (!kStats && k >= 4) break;
+        v[k] = warp_sum(v[k]);
+      }
+      if ((threadIdx.x & 31) == 0) {
+        float* acc_row = io.log_accum + (size_t)(blockIdx.x & (GR_LOG_SHARDS - 1)) * GR_LOG_SLOTS;
+        atomicAdd(acc_row + GR_LOG_NUM_RESET, v[0]);
+        atomicAdd(acc_row + GR_LOG_SUM_GATES, v[1]);
+        if (v[2] != 0.0f) atomicAdd(acc_row + GR_LOG_NUM_TIMEOUT, v[2]);
+        if (v[3] != 0.0f) atomicAdd(acc_row + GR_LOG_NUM_TERMINATED, v[3]);
+        if (kStats) {
+#pragma unroll
+          for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k) atomicAdd(acc_row + GR_LOG_SUM_EPSUM + k, v[4 + k]);
+        }
       }
     }
+  }
+  if (reset) {
     if (kStats) { eps0 = make_float4(0.f, 0.f, 0.f, 0.f); eps1 = eps0; }
     origin = reset_env<kNoise, kPhilox>(cfg, tr, e, rs, n23.z);
     level = (int)pk_level(e.pk);
     gate_id = (int)pk_gate(e.pk);
+    gate_rel = tr.gate(type, level, gate_id);
     noise_dirty = true;
+    // ---- 8. on the fresh state (QD/mdp/commands.py:247-260,308-312)
+    const V3 dv = (gate_rel + origin) - e.w;
+    passed = sqrt_rn(dv.x * dv.x + dv.y * dv.y + dv.z * dv.z) < cfg.update_threshold;
   } else {
     e.pk &= 0x7FFFFFFFu;      // latches hold a_t again
   }
 
-  // ---- 8. command update (QD/mdp/commands.py:247-260 then :308-350), on the post-reset state ----
-  V3 gate_rel = tr.gate(type, level, gate_id);
-  bool passed;
-  {
-    const V3 diff = (gate_rel + origin) - e.w;
-    passed = norm(diff) < cfg.update_threshold;
-    if (passed) {
-      uint32_t acc_g = pk_acc(e.pk) + 1u;
-      gate_id = (gate_id + 1) % tr.gates;
-      e.pk = pk_make((uint32_t)gate_id, acc_g, (uint32_t)level, (uint32_t)type, pk_fresh(e.pk));
-      gate_rel = tr.gate(type, level, gate_id);
-      if (kNoise) {
-        const float4 u0 = rs.get4(10), u1 = rs.get4(11);     // slots 40..45 gate, 46..51 next
-        e.dcur = gate_noise(e.noise_hi, u0.x, u0.y, u0.z);
-        e.dnext = gate_noise(e.noise_hi, u1.z, u1.w, rs.get4(12).x);
-        noise_dirty = true;
-      }
+  // ---- 8. command update (QD/mdp/commands.py:247-260 then :308-350) ----
+  if (passed) {
+    const uint32_t acc_g = pk_acc(e.pk) + 1u;
+    gate_id = (gate_id + 1) % tr.gates;
+    e.pk = pk_make((uint32_t)gate_id, acc_g, (uint32_t)level, (uint32_t)type, pk_fresh(e.pk));
+    gate_rel = tr.gate(type, level, gate_id);
+    if (kNoise) {
+      const float4 u0 = rs.get4(10), u1 = rs.get4(11);     // slots 40..45 gate, 46..51 next
+      e.dcur = gate_noise(e.noise_hi, u0.x, u0.y, u0.z);
+      e.dnext = gate_noise(e.noise_hi, u1.z, u1.w, rs.get4(12).x);
+      noise_dirty = true;
     }
   }
   const V3 next_rel = tr.gate(type, level, (gate_id + 1) % tr.gates);
+  const V3 g_gt = gate_rel + origin, gn_gt = next_rel + origin;
 
-  // ---- 9. BPTT losses (QD/mdp/losses.py:72-80,95-101,111-117) + tape of this step ----
-  if (kDiff) {
-    const V3 desired = (gate_rel + origin) - origin;
+  // ---- 9. BPTT losses (QD/mdp/losses.py:72-80,95-101,111-117) + tape plane 6 ----
+  if (kDiff && active) {
+    const V3 desired = g_gt - origin;
     const V3 dvec = desired - p_al;
-    const float dist = norm(dvec);
-    const float l_target = dist * cfg.w_loss[0];
+    const float ld = norm(dvec);
+    const float l_target = ld * cfg.w_loss[0];
     const float l_vel = ((v_al.x * v_al.x + v_al.y * v_al.y + v_al.z * v_al.z) / 3.0f) * cfg.w_loss[1];
     const float z = p_al.z;
     const float den = 1.0f + 1.0f * z + 10.0f * (z * z);
@@ -369,15 +401,62 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
     if (io.loss_terms) { io.loss_terms[i * 3 + 0] = l_target; io.loss_terms[i * 3 + 1] = l_vel; io.loss_terms[i * 3 + 2] = l_fall; }
     if (io.tape) {
       // plane 6: d loss / d aligned position (target + falling terms); d loss / d velocity is rebuilt from v1
-      const float inv = dist > 0.0f ? cfg.w_loss[0] / dist : 0.0f;
+      const float inv = ld > 0.0f ? cfg.w_loss[0] / ld : 0.0f;
       const float dfall = -cfg.w_loss[2] * (1.0f + 20.0f * z) / (den * den);
       __stcs(reinterpret_cast<float4*>(io.tape) + 6 * io.tape_stride + i,
              make_float4(-dvec.x * inv, -dvec.y * inv, -dvec.z * inv + dfall, 0.0f));
     }
   }
 
-  // ---- 11. observations on the post-reset state (QD/mdp/observation.py) ----
-  write_observations<kNoise>(cfg, e, origin, gate_rel, next_rel, th_lag, n01, n23, e.aux, i, io.obs, io.critic_obs, io.aux_obs);
+  if (!active) return;      // no warp collectives below
+
+  // ---- 11. observations on the post-reset state (QD/racing_ctbr_env.py:139-174, QD/mdp/observation.py:22-104) ----
+  {
+    V3 vb = vb1, d0 = cg0;                       // common case: same state and gate as the reward section
+    RotQ Rq = R1;
+    if (reset || passed) {                       // rare: recompute the views on the new state / gate
+      Rq = RotQ(e.q);
+      vb = Rq.rotinv(e.v);
+      d0 = Rq.rotinv(g_gt - e.w);
+    }
+    const V3 d1 = Rq.rotinv(gn_gt - g_gt);
+    V3 c0 = d0, c1 = d1;
+    if (kNoise) {
+      const V3 g_pol = g_gt + e.dcur, gn_pol = gn_gt + e.dnext;
+      c0 = Rq.rotinv(g_pol - e.w);
+      c1 = Rq.rotinv(gn_pol - g_pol);
+    }
+    // modified_last_action (:55-63): ctbr of the lagged raw action, thrust / mass
+    const float4 ctbr = make_float4((th_lag.x * s0 + s0) * inv_m, th_lag.y * sb, th_lag.z * sb, th_lag.w * sb);
+    // noisy lin vel (:52) and noisy attitude row (:27-32): R(q (x) q_noise)[2,:]
+    const float nv = cfg.obs_vel_noise, ne = cfg.obs_euler_noise;
+    const V3 vn = v3(vb.x * (1.0f + n01.x * nv), vb.y * (1.0f + n01.y * nv), vb.z * (1.0f + n01.z * nv));
+    float sr, cr, sp, cp, sy, cy;
+    fm_sincos(0.5f * ne * n01.w, &sr, &cr);
+    fm_sincos(0.5f * ne * n23.x, &sp, &cp);
+    fm_sincos(0.5f * ne * n23.y, &sy, &cy);
+    const Q4 qn = Q4{cy * cr * cp + sy * sr * sp, cy * sr * cp - sy * cr * sp, cy * cr * sp + sy * sr * cp, sy * cr * cp - cy * sr * sp};
+    const Q4 a = e.q;
+    const Q4 qq = Q4{a.w * qn.w - a.x * qn.x - a.y * qn.y - a.z * qn.z, a.w * qn.x + a.x * qn.w + a.y * qn.z - a.z * qn.y,
+                     a.w * qn.y - a.x * qn.z + a.y * qn.w + a.z * qn.x, a.w * qn.z + a.x * qn.y - a.y * qn.x + a.z * qn.w};
+    const float two_s = 2.0f * fm_rcp(qq.w * qq.w + qq.x * qq.x + qq.y * qq.y + qq.z * qq.z);
+    const V3 rn = v3(two_s * (qq.x * qq.z - qq.y * qq.w), two_s * (qq.y * qq.z + qq.x * qq.w), 1.0f - two_s * (qq.x * qq.x + qq.y * qq.y));
+    float4* o = reinterpret_cast<float4*>(io.obs) + (int64_t)i * 4;
+    __stcs(o + 0, make_float4(vn.x, vn.y, vn.z, rn.x));
+    __stcs(o + 1, make_float4(rn.y, rn.z, c0.x, c0.y));
+    __stcs(o + 2, make_float4(c0.z, c1.x, c1.y, c1.z));
+    __stcs(o + 3, ctbr);
+    if (io.critic_obs) {
+      const float ts = 2.0f * fm_rcp(a.w * a.w + a.x * a.x + a.y * a.y + a.z * a.z);
+      const V3 r = v3(ts * (a.x * a.z - a.y * a.w), ts * (a.y * a.z + a.x * a.w), 1.0f - ts * (a.x * a.x + a.y * a.y));
+      float4* c = reinterpret_cast<float4*>(io.critic_obs) + (int64_t)i * 4;
+      __stcs(c + 0, make_float4(vb.x, vb.y, vb.z, r.x));
+      __stcs(c + 1, make_float4(r.y, r.z, d0.x, d0.y));
+      __stcs(c + 2, make_float4(d0.z, d1.x, d1.y, d1.z));
+      __stcs(c + 3, ctbr);
+    }
+    if (io.aux_obs) io.aux_obs[i] = e.aux;
+  }
 
   // ---- 12. outputs + state write-back ----
   e.fifo = a_t;
@@ -394,7 +473,6 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
     for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k) io.reward_terms[i * GR_NUM_REWARD_TERMS + k] = terms[k];
   }
 }
-
 
 // =============================================================================================
 // reset / observe: ManagerBasedRLEnv.reset() = _reset_idx(ids) + observation_manager.compute();
@@ -535,10 +613,11 @@ static int check_common(const GrConfig* cfg, const GrTrack* tr, const GrState* s
   if (tr->types < 1 || tr->types > 32 || tr->levels < 1 || tr->levels > 64 || tr->gates < 1 || tr->gates > GR_MAX_GATES) return GR_ERR_SIZE;
   if (misaligned16(st->planes) || misaligned16(tr->rows)) return GR_ERR_ALIGN;
   if (st->max_types_per_block < 1 || st->max_types_per_block > tr->types) return GR_ERR_SIZE;
+  if (st->block_threads < 0 || st->block_threads > 256 || (st->block_threads & 31)) return GR_ERR_SIZE;
   return GR_OK;
 }
 
-static constexpr int kBlock = 128;
+static inline int block_threads(const GrState* st) { return st->block_threads > 0 ? st->block_threads : 64; }
 
 static inline size_t track_smem_bytes(const GrTrack* tr, const GrState* st) {
   return (size_t)st->max_types_per_block * tr->levels * (tr->gates + 1) * sizeof(float4);
@@ -560,6 +639,7 @@ static int launch_step(const GrConfig* cfg, const GrTrack* tr, const GrState* st
   const size_t bytes = track_smem_bytes(tr, st);
   int rc = prepare_smem(kernel, bytes);
   if (rc != GR_OK) return rc;
+  const int kBlock = block_threads(st);
   const int grid = (st->num_envs + kBlock - 1) / kBlock;
   kernel<<<grid, kBlock, bytes, s>>>(*cfg, *tr, *st, *rng, *io);
   return (int)cudaGetLastError();
@@ -600,6 +680,7 @@ template <bool kNoise, bool kPhilox>
 static int launch_reset(bool stats, const GrConfig* cfg, const GrTrack* tr, const GrState* st, const GrRandom* rng, const uint8_t* mask, int mode,
                         float* obs, float* critic, float* aux, cudaStream_t s) {
   const size_t bytes = track_smem_bytes(tr, st);
+  const int kBlock = block_threads(st);
   const int grid = (st->num_envs + kBlock - 1) / kBlock;
   if (stats) {
     auto kernel = racing_reset_kernel<kNoise, kPhilox, true>;

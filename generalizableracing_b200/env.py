@@ -115,7 +115,7 @@ class RacingVecEnv:
     def __init__(self, cfg: RacingCfg, table: GateTable, num_envs: int, device="cuda:0", seed: int = 42,
                  rng_mode: str = "philox", episode_stats: bool = True, env_id_offset: int = 0,
                  global_num_envs: Optional[int] = None, terrain_types: Optional[torch.Tensor] = None,
-                 startup_rnd: Optional[torch.Tensor] = None, bptt_horizon: int = 0, _lib=None):
+                 startup_rnd: Optional[torch.Tensor] = None, bptt_horizon: int = 0, block_threads: int = 0, _lib=None):
         self.cfg = cfg
         self.table = table
         self.num_envs = N = int(num_envs)
@@ -150,7 +150,7 @@ class RacingVecEnv:
         self._terrain_types = tt.to(dev)
         self._chunk_types = torch.zeros(((N + 63) // 64) * 2, dtype=torch.int32, device=dev)
         self._state = B.GrState(self.planes.data_ptr(), self._stride, N, self.num_planes, int(env_id_offset), max(spans),
-                                self._chunk_types.data_ptr())
+                                int(block_threads), self._chunk_types.data_ptr())
         self._rng = B.GrRandom(None, self.seed, 0)
         self._step_count = 0
         # ---- outputs (ping-pong so that the tensors returned by step t stay valid during step t+1)
@@ -162,7 +162,7 @@ class RacingVecEnv:
                         gate_passed=torch.zeros(N, dtype=torch.uint8, device=dev))
         self._outs = [outs(), outs()]
         self._flip = 0
-        self._log_accum = torch.zeros(B.GR_LOG_SLOTS, device=dev)
+        self._log_accum = torch.zeros(B.GR_LOG_SHARDS, B.GR_LOG_SLOTS, device=dev)
         self._log_total = torch.zeros(B.GR_LOG_SLOTS, device=dev)
         self.extras = _Extras(self)
         self.export_reward_terms = False
@@ -240,7 +240,7 @@ class RacingVecEnv:
     def _build_log(self) -> dict:
         """extras["log"] of the reference (_reset_idx, manager_based_diff_rl_env.py:380-407): means over the envs reset
         since the last read, as 0-dim device tensors (the runner's logger accepts tensors)."""
-        acc = self._log_accum
+        acc = self._log_accum.sum(dim=0)
         n = acc[B_LOG_NUM_RESET].clamp(min=1.0)
         log = {}
         if self.num_planes == L.NUM_PLANES_WITH_STATS:
@@ -256,8 +256,7 @@ class RacingVecEnv:
         if self.cfg.noise_curriculum and self.cfg.add_cmd_noise:
             log["Curriculum/command_noise_level"] = sv["noise_level"].mean()
         self._log_total += acc
-        self._log_accum = torch.zeros_like(acc)
-        self._io_cache = None
+        self._log_accum = torch.zeros_like(self._log_accum)
         return log
 
     # ------------------------------------------------------------------ API

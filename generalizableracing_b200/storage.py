@@ -1,0 +1,190 @@
+"""Drop-in ``RolloutStorage`` (standalone/rsl_rl/ext/storage/rollout_storage.py:12-254 of the reference).
+
+Same constructor, tensors (``[T,N,.]``), ``Transition``, ``add_transitions``, ``compute_returns``,
+``mini_batch_generator``, ``get_statistics``, ``clear`` and ``step``; the three hot methods are one or two
+launches of libgracing.so instead of 9 copies / ~8T+6 elementwise ops / 9 gathers.  CUDA only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as B
+
+
+class RolloutStorage:
+    class Transition:
+        def __init__(self):
+            self.observations = None
+            self.privileged_observations = None
+            self.actions = None
+            self.privileged_actions = None
+            self.rewards = None
+            self.dones = None
+            self.values = None
+            self.actions_log_prob = None
+            self.action_mean = None
+            self.action_sigma = None
+            self.hidden_states = None
+            self.time_outs = None        # extension: lets add_transitions fuse the time-out bootstrap (ppo.py:89-92)
+            self.gamma = 0.0
+
+        def clear(self):
+            self.__init__()
+
+    def __init__(self, training_type, num_envs, num_transitions_per_env, obs_shape, privileged_obs_shape, actions_shape, device="cuda:0", _lib=None):
+        self.device = torch.device(device)
+        if _lib is None:
+            if self.device.type != "cuda":
+                raise RuntimeError("RolloutStorage runs only on a CUDA device; there is no CPU fallback")
+            _lib = B.load()
+        self._lib = _lib
+        if training_type != "rl":
+            raise ValueError("only training_type='rl' (PPO) is built; distillation storage is out of scope")
+        self.training_type = training_type
+        self.obs_shape = obs_shape
+        self.privileged_obs_shape = privileged_obs_shape
+        self.actions_shape = actions_shape
+        T, N, dev = num_transitions_per_env, num_envs, self.device
+        if len(obs_shape) != 1 or len(actions_shape) != 1 or obs_shape[0] % 4 or actions_shape[0] % 4:
+            raise ValueError("observation / action rows must be 1-D with a multiple of 4 floats (128-bit row copies)")
+        self.observations = torch.zeros(T, N, *obs_shape, device=dev)
+        if privileged_obs_shape[0] is not None:
+            if privileged_obs_shape[0] % 4:
+                raise ValueError("privileged observation rows must hold a multiple of 4 floats")
+            self.privileged_observations = torch.zeros(T, N, *privileged_obs_shape, device=dev)
+        else:
+            self.privileged_observations = None
+        self.rewards = torch.zeros(T, N, 1, device=dev)
+        self.actions = torch.zeros(T, N, *actions_shape, device=dev)
+        self.dones = torch.zeros(T, N, 1, device=dev).byte()
+        self.actions_log_prob = torch.zeros(T, N, 1, device=dev)
+        self.values = torch.zeros(T, N, 1, device=dev)
+        self.returns = torch.zeros(T, N, 1, device=dev)
+        self.advantages = torch.zeros(T, N, 1, device=dev)
+        self.mu = torch.zeros(T, N, *actions_shape, device=dev)
+        self.sigma = torch.zeros(T, N, *actions_shape, device=dev)
+        self.num_transitions_per_env = T
+        self.num_envs = N
+        self.saved_hidden_states_a = None
+        self.saved_hidden_states_c = None
+        self.step = 0
+        self._scratch = torch.zeros(int(self._lib.gr_gae_scratch_bytes(N)) // 8 + 1, dtype=torch.float64, device=dev)
+        self.moments = torch.zeros(3, dtype=torch.float64, device=dev)     # (count, mean, M2) of the raw advantages
+        self._keep = None
+
+    # ------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
+
+    def _desc(self) -> B.GrStorage:
+        s = B.GrStorage()
+        s.obs = self.observations.data_ptr()
+        s.critic_obs = None if self.privileged_observations is None else self.privileged_observations.data_ptr()
+        s.actions, s.rewards, s.dones = self.actions.data_ptr(), self.rewards.data_ptr(), self.dones.data_ptr()
+        s.values, s.log_prob, s.mu, s.sigma = self.values.data_ptr(), self.actions_log_prob.data_ptr(), self.mu.data_ptr(), self.sigma.data_ptr()
+        s.returns, s.advantages = self.returns.data_ptr(), self.advantages.data_ptr()
+        s.T, s.N = self.num_transitions_per_env, self.num_envs
+        s.obs_dim = self.obs_shape[0]
+        s.critic_dim = self.privileged_obs_shape[0] or 0
+        s.act_dim = self.actions_shape[0]
+        return s
+
+    def _f32(self, t, shape=None):
+        t = t.detach()
+        if t.dtype != torch.float32 or t.device != self.device or not t.is_contiguous():
+            t = t.to(self.device, torch.float32).contiguous()
+        return t
+
+    def add_transitions(self, transition: "RolloutStorage.Transition"):
+        """rollout_storage.py:71-88 in one launch; when ``transition.time_outs`` is set the reward bootstrap
+        ``r += gamma * V * time_out`` of PPO.process_env_step (ppo.py:89-92) is fused in."""
+        if self.step >= self.num_transitions_per_env:
+            raise AssertionError("Rollout buffer overflow")
+        if transition.hidden_states is not None and transition.hidden_states != (None, None):
+            raise NotImplementedError("recurrent hidden states are out of scope (SURVEY.md §8f rank 4)")
+        tr = B.GrTransition()
+        keep = [self._f32(transition.observations), self._f32(transition.actions), self._f32(transition.rewards),
+                self._f32(transition.values), self._f32(transition.actions_log_prob), self._f32(transition.action_mean),
+                self._f32(transition.action_sigma)]
+        tr.obs, tr.actions, tr.rewards, tr.values, tr.log_prob, tr.mu, tr.sigma = (k.data_ptr() for k in keep)
+        if self.privileged_observations is not None:
+            po = self._f32(transition.privileged_observations)
+            keep.append(po)
+            tr.critic_obs = po.data_ptr()
+        d = transition.dones.detach()
+        if d.dtype == torch.bool:
+            d = d.view(torch.uint8)
+        if d.dtype not in (torch.uint8, torch.int64) or d.device != self.device or not d.is_contiguous():
+            d = d.to(self.device, torch.int64).contiguous()
+        keep.append(d)
+        tr.dones = d.data_ptr()
+        tr.dones_is_int64 = int(d.dtype == torch.int64)
+        if transition.time_outs is not None:
+            to = transition.time_outs.detach()
+            to = to.view(torch.uint8) if to.dtype == torch.bool else to.to(torch.uint8)
+            to = to.to(self.device).contiguous()
+            keep.append(to)
+            tr.time_outs = to.data_ptr()
+            tr.gamma = float(transition.gamma)
+        self._keep = keep
+        desc = self._desc()
+        B.check(self._lib.gr_storage_add(C.byref(desc), C.byref(tr), self.step, self._stream()), "gr_storage_add")
+        self.step += 1
+
+    def clear(self):
+        self.step = 0
+
+    def compute_returns(self, last_values, gamma, lam, normalize: bool = True):
+        """rollout_storage.py:113-127: GAE scan + advantage normalisation (unbiased std + 1e-8).  With
+        ``normalize=False`` the raw advantages and their (count, mean, M2) in ``self.moments`` are left for a
+        cross-rank merge followed by :meth:`normalize_advantages`."""
+        lv = self._f32(last_values)
+        desc = self._desc()
+        B.check(self._lib.gr_compute_returns(C.byref(desc), lv.data_ptr(), float(gamma), float(lam), self._scratch.data_ptr(),
+                                             self.moments.data_ptr(), int(normalize), self._stream()), "gr_compute_returns")
+
+    def normalize_advantages(self, moments: torch.Tensor = None):
+        m = self.moments if moments is None else moments.to(self.device, torch.float64).contiguous()
+        desc = self._desc()
+        B.check(self._lib.gr_advantage_normalize(C.byref(desc), m.data_ptr(), self._stream()), "gr_advantage_normalize")
+
+    def get_statistics(self):
+        # rollout_storage.py:129-137 (logging helper; plain torch, not on the hot path)
+        done = self.dones
+        done[-1] = 1
+        flat_dones = done.permute(1, 0, 2).reshape(-1, 1)
+        done_indices = torch.cat((flat_dones.new_tensor([-1], dtype=torch.int64), flat_dones.nonzero(as_tuple=False)[:, 0]))
+        trajectory_lengths = done_indices[1:] - done_indices[:-1]
+        return trajectory_lengths.float().mean(), self.rewards.mean()
+
+    def mini_batch_generator(self, num_mini_batches, num_epochs=8, indices: torch.Tensor = None):
+        """rollout_storage.py:152-191; the nine fancy-index gathers of one mini-batch are one launch."""
+        batch_size = self.num_envs * self.num_transitions_per_env
+        mb = batch_size // num_mini_batches
+        if indices is None:
+            indices = torch.randperm(num_mini_batches * mb, requires_grad=False, device=self.device)
+        indices = indices.to(self.device, torch.int64).contiguous()
+        dev = self.device
+        od, ad = self.obs_shape[0], self.actions_shape[0]
+        cd = self.privileged_obs_shape[0] or 0
+        desc = self._desc()
+        for _ in range(num_epochs):
+            for i in range(num_mini_batches):
+                idx = indices[i * mb:(i + 1) * mb]
+                out = dict(obs=torch.empty(mb, od, device=dev), actions=torch.empty(mb, ad, device=dev), values=torch.empty(mb, 1, device=dev),
+                           advantages=torch.empty(mb, 1, device=dev), returns=torch.empty(mb, 1, device=dev), log_prob=torch.empty(mb, 1, device=dev),
+                           mu=torch.empty(mb, ad, device=dev), sigma=torch.empty(mb, ad, device=dev))
+                if cd:
+                    out["critic_obs"] = torch.empty(mb, cd, device=dev)
+                g = B.GrMiniBatch()
+                for k, v in out.items():
+                    setattr(g, k, v.data_ptr())
+                B.check(self._lib.gr_storage_gather(C.byref(desc), idx.data_ptr(), mb, C.byref(g), self._stream()), "gr_storage_gather")
+                priv = out["critic_obs"] if cd else out["obs"]
+                yield (out["obs"], priv, out["actions"], out["values"], out["advantages"], out["returns"], out["log_prob"],
+                       out["mu"], out["sigma"], (None, None), None)
+
+    def reccurent_mini_batch_generator(self, num_mini_batches, num_epochs=8):
+        raise NotImplementedError("recurrent mini-batches are out of scope this round (SURVEY.md §8f rank 4)")

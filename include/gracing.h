@@ -107,6 +107,7 @@ typedef struct GrState {
   int32_t num_planes;       /* GR_NUM_PLANES or GR_NUM_PLANES_WITH_STATS */
   int32_t env_id_offset;    /* global id of env 0 of this shard (Philox key; multi-GPU) */
   int32_t max_types_per_block; /* host-computed bound of distinct terrain types inside one 256-env span */
+  int32_t block_threads;    /* threads per block of the env kernels: 0 => default (64); multiple of 32, <= 256 */
   const int32_t* chunk_types;  /* [ceil(N/64)][2] (lowest, highest) terrain type of each 64-env chunk;
                                   written by gr_env_startup, read by every kernel that stages the track */
 } GrState;
@@ -141,7 +142,7 @@ typedef struct GrStepIO {
   float* loss_terms;        /* [N,3] weighted loss terms                             optional */
   float* tape;              /* [GR_TAPE_PLANES][tape_stride] float4 of THIS step     optional (BPTT) */
   int64_t tape_stride;      /* in float4 elements */
-  float* log_accum;         /* [GR_LOG_SLOTS] float atomics, see GR_LOG_*            optional */
+  float* log_accum;         /* [GR_LOG_SHARDS][GR_LOG_SLOTS] float atomics (sum the shards), see GR_LOG_*  optional */
 } GrStepIO;
 
 #define GR_LOG_NUM_RESET 0          /* number of envs reset in this step                          */
@@ -150,6 +151,7 @@ typedef struct GrStepIO {
 #define GR_LOG_NUM_TIMEOUT 8
 #define GR_LOG_NUM_TERMINATED 9
 #define GR_LOG_SLOTS 16
+#define GR_LOG_SHARDS 32           /* accumulator rows, one 64-byte row per (block index mod 32) */
 
 int gr_abi_version(void);
 
