@@ -41,7 +41,7 @@ class GrTrack(C.Structure):
 
 class GrState(C.Structure):
     _fields_ = [("planes", c_p), ("plane_stride", C.c_int64), ("num_envs", c_i), ("num_planes", c_i),
-                ("env_id_offset", c_i), ("max_types_per_block", c_i), ("block_threads", c_i), ("chunk_types", c_p)]
+                ("env_id_offset", c_i), ("max_types_per_block", c_i), ("block_threads", c_i), ("launch_flags", c_i), ("chunk_types", c_p)]
 
 
 class GrRandom(C.Structure):
@@ -51,7 +51,7 @@ class GrRandom(C.Structure):
 class GrStepIO(C.Structure):
     _fields_ = [("action", c_p), ("obs", c_p), ("critic_obs", c_p), ("aux_obs", c_p), ("reward", c_p),
                 ("terminated", c_p), ("time_out", c_p), ("dones", c_p), ("reward_terms", c_p), ("gate_passed", c_p),
-                ("loss", c_p), ("loss_terms", c_p), ("tape", c_p), ("tape_stride", C.c_int64), ("log_accum", c_p)]
+                ("loss", c_p), ("loss_terms", c_p), ("tape", c_p), ("tape_stride", C.c_int64), ("phase_times", c_p), ("log_accum", c_p)]
 
 
 class GrBwdIO(C.Structure):
@@ -75,8 +75,9 @@ class GrMiniBatch(C.Structure):
                 ("log_prob", c_p), ("mu", c_p), ("sigma", c_p)]
 
 
+GR_LAUNCH_PDL = 1
 GR_LOG_SLOTS = 16
-GR_LOG_SHARDS = 32
+GR_LOG_SHARDS = 256
 STATUS = {0: "GR_OK", -1: "GR_ERR_NULL", -2: "GR_ERR_SIZE", -3: "GR_ERR_ALIGN", -4: "GR_ERR_CONFIG", -5: "GR_ERR_SMEM"}
 
 # symbol -> (restype, argtypes); every symbol include/gracing.h declares

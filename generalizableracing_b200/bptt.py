@@ -55,7 +55,7 @@ class BpttWindow:
     def _alloc(self, capacity: int):
         env = self.env
         dev, N = env.device, env.num_envs
-        self.tape = torch.zeros(capacity, L.TAPE_PLANES, env._stride, 4, device=dev)
+        self.tape = torch.zeros(capacity, env.num_tiles, L.TAPE_PLANES, L.TILE, 4, device=dev)     # per-warp tiles, like the state
         self.loss = torch.zeros(capacity, N, device=dev)
         self.loss_terms = torch.zeros(capacity, N, 3, device=dev)
         self.grad_loss = torch.zeros(capacity, N, device=dev)

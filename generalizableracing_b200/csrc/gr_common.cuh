@@ -12,11 +12,20 @@
 
 namespace gr {
 
+// State layout: array of 32-env TILES, each tile = 16 planes x 32 lanes x float4 (8 KB, contiguous).  A warp owns one
+// tile: its 16 plane loads are consecutive 512 B rows of the same 8 KB block, so DRAM serves them together and warps
+// complete their loads one after the other (load -> compute -> store pipelines ACROSS warps).  With plane-major arrays
+// the memory system streams plane by plane and every warp gets its last plane only at the end of the transfer.
+// Written planes come first (0..8 = 4.5 KB contiguous write-back), read-mostly planes after.
 enum Plane : int {
   PL_QUAT = 0, PL_POS = 1, PL_LINVEL = 2, PL_ANGVEL = 3, PL_TORQUE = 4, PL_ANGACC = 5, PL_FIFO = 6,
-  PL_DRAG2 = 7, PL_DRAG1 = 8, PL_KP = 9, PL_KD = 10, PL_ETAU = 11, PL_NOISE0 = 12, PL_NOISE1 = 13,
-  PL_EPSUM0 = 14, PL_EPSUM1 = 15
+  PL_EPSUM0 = 7, PL_EPSUM1 = 8,
+  PL_DRAG2 = 9, PL_DRAG1 = 10, PL_KP = 11, PL_KD = 12, PL_ETAU = 13, PL_NOISE0 = 14, PL_NOISE1 = 15
 };
+constexpr int kTile = 32, kTilePlanes = 16;
+__device__ __forceinline__ int64_t pidx(int plane, int i) { return ((int64_t)(i >> 5) * kTilePlanes + plane) * kTile + (i & 31); }
+// BPTT tape of one step: tiles of 7 planes x 32 lanes x float4
+__device__ __forceinline__ int64_t tidx(int plane, int i) { return ((int64_t)(i >> 5) * GR_TAPE_PLANES + plane) * kTile + (i & 31); }
 
 // packed ints in PL_ANGVEL.w : gate_id[0:8) | acc_gates[8:20) | level[20:26) | type[26:31) | fresh[31]
 __device__ __forceinline__ uint32_t pk_gate(uint32_t p) { return p & 0xFFu; }
@@ -30,18 +39,16 @@ __device__ __forceinline__ uint32_t pk_make(uint32_t gate, uint32_t acc, uint32_
 
 // 128-bit plane access.  Hot planes are read once and written once per step: streaming hints keep
 // them from displacing the (tiny, reused) gate table in L1.
-__device__ __forceinline__ float4 ld_plane(const float4* __restrict__ base, int64_t stride, int plane, int i) {
-  return __ldcs(base + (int64_t)plane * stride + i);
-}
-__device__ __forceinline__ float4 ld_plane_ro(const float4* __restrict__ base, int64_t stride, int plane, int i) {
-  return __ldg(base + (int64_t)plane * stride + i);
-}
-__device__ __forceinline__ void st_plane(float4* __restrict__ base, int64_t stride, int plane, int i, float4 v) {
-  __stcs(base + (int64_t)plane * stride + i, v);
-}
+// `tile` = address of lane (i & 31) in plane 0 of env i's tile: plane p is at the constant offset p * 32.
+__device__ __forceinline__ float4* tile_ptr(float4* base, int i) { return base + (int64_t)(i >> 5) * (kTilePlanes * kTile) + (i & 31); }
+__device__ __forceinline__ float4 ld_plane(const float4* __restrict__ tile, int plane) { return __ldcs(tile + plane * kTile); }
+__device__ __forceinline__ float4 ld_plane_ro(const float4* __restrict__ tile, int plane) { return __ldg(tile + plane * kTile); }
+__device__ __forceinline__ void st_plane(float4* __restrict__ tile, int plane, float4 v) { __stcs(tile + plane * kTile, v); }
 
-// Random source.  get4(call) returns slots [4*call, 4*call+4): calls 0,1 are standard normals,
-// calls >= 2 uniforms in [0,1).  Dense mode reads the caller's tensor, Philox mode generates.
+// Random source.  normals8() returns slots 0..7 (standard normals), get4(call >= 2) returns the uniform slots
+// [4*call, 4*call+4).  Dense mode reads the caller's tensor; Philox mode generates: the eight normals come from ONE
+// Philox call (each 32-bit word feeds a Box-Muller pair with two 16-bit uniforms: 4.7 sigma tails, ample for the
+// 3 % / 0.05 rad observation noise), uniforms use 24 bits of each word.
 template <bool kPhilox>
 struct RandSrc;
 
@@ -51,6 +58,7 @@ struct RandSrc<false> {
   __device__ __forceinline__ RandSrc(const GrRandom& r, int i, int /*env_id*/)
       : row(reinterpret_cast<const float4*>(r.rnd) + (int64_t)i * (GR_RND_STRIDE / 4)) {}
   __device__ __forceinline__ float4 get4(int call) const { return __ldg(row + call); }
+  __device__ __forceinline__ void normals8(float4& a, float4& b) const { a = __ldg(row); b = __ldg(row + 1); }
 };
 
 template <>
@@ -59,13 +67,29 @@ struct RandSrc<true> {
   __device__ __forceinline__ RandSrc(const GrRandom& r, int /*i*/, int env_id) : ph(r.seed, (uint32_t)env_id, r.step) {}
   __device__ __forceinline__ float4 get4(int call) const {
     const uint4 x = ph((uint32_t)call);
-    if (call < 2) {
-      const float2 a = box_muller(x.x, x.y), b = box_muller(x.z, x.w);
-      return make_float4(a.x, a.y, b.x, b.y);
-    }
     return make_float4(u01(x.x), u01(x.y), u01(x.z), u01(x.w));
   }
+  __device__ __forceinline__ void normals8(float4& a, float4& b) const {
+    const uint4 x = ph(0u);
+    const float2 p0 = box_muller16(x.x), p1 = box_muller16(x.y), p2 = box_muller16(x.z), p3 = box_muller16(x.w);
+    a = make_float4(p0.x, p0.y, p1.x, p1.y);
+    b = make_float4(p2.x, p2.y, p3.x, p3.y);
+  }
 };
+
+// Programmatic dependent launch (sm_90+): wait = block until the previous kernel in the stream has completed and its
+// writes are visible; launch_dependents = allow the next PDL-launched kernel to start its prologue.  Both are no-ops
+// when the kernel was not launched with the programmatic-stream-serialization attribute.
+__device__ __forceinline__ void pdl_wait() {
+#ifndef GR_CPU_EMUL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_launch_dependents() {
+#ifndef GR_CPU_EMUL
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 
 // full-warp sum (all 32 lanes participate)
 __device__ __forceinline__ float warp_sum(float v) {
@@ -75,6 +99,23 @@ __device__ __forceinline__ float warp_sum(float v) {
 #endif
   return v;
 }
+
+// Draws of the rare paths (reset: calls 2..8, gate pass: calls 10..11).  In Philox mode the step kernel generates
+// them speculatively for every env while its state loads are in flight (the warp would idle otherwise) and parks
+// them in shared memory, so the divergent reset / pass tails -- the stragglers that set the kernel's makespan -- only
+// read them back.  Dense mode and the standalone reset kernel read / generate directly.
+__device__ __forceinline__ int spec_slot(int call) { return call < 10 ? call - 2 : call - 3; }     // 2..8 -> 0..6, 10..11 -> 7..8
+constexpr int kSpecCalls = 9;
+
+template <bool kPhilox>
+struct Draws {
+  const RandSrc<kPhilox>& rs;
+  const float4* spec;       // shared: [kSpecCalls][blockDim.x] or nullptr
+  __device__ __forceinline__ float4 get4(int call) const {
+    if (kPhilox && spec) return spec[spec_slot(call) * blockDim.x + threadIdx.x];
+    return rs.get4(call);
+  }
+};
 
 // Gate table slice staged in shared memory: rows of types [type_lo, type_lo + ntypes).
 struct TrackSmem {

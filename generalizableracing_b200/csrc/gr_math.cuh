@@ -72,6 +72,8 @@ __device__ __forceinline__ Q4 quat_from_euler_xyz(float roll, float pitch, float
   return Q4{cy * cr * cp + sy * sr * sp, cy * sr * cp - sy * cr * sp,
             cy * cr * sp + sy * sr * cp, sy * cr * cp - cy * sr * sp};
 }
+// same with MUFU sin/cos; |angle/2| stays below ~2 rad on the reset path (abs error < 5e-7)
+__device__ __forceinline__ Q4 quat_from_euler_xyz_fast(float roll, float pitch, float yaw);
 // third row of matrix_from_quat (QD/mdp/observation.py:31-32)
 __device__ __forceinline__ V3 rotmat_row2(Q4 q) {
   const float two_s = 2.0f / (q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
@@ -91,6 +93,12 @@ __device__ __forceinline__ float remainder_pos(float a, float b) {
 }
 __device__ __forceinline__ float wrap_to_pi(float a) {
   const float w = remainder_pos(a + GR_PI_F, GR_2PI_F);
+  return (w == 0.0f && a > 0.0f) ? GR_PI_F : w - GR_PI_F;
+}
+// wrap_to_pi restricted to a in [-pi, pi] (the range of atan2f): bit-identical to the general form, no fmod
+__device__ __forceinline__ float wrap_to_pi_atan2(float a) {
+  float w = a + GR_PI_F;
+  if (w >= GR_2PI_F) w -= GR_2PI_F;
   return (w == 0.0f && a > 0.0f) ? GR_PI_F : w - GR_PI_F;
 }
 // bad_pose (QD/mdp/termination.py:24-33): euler_xyz_from_quat -> % 2pi -> wrap_to_pi -> |.| > pi/2
@@ -141,6 +149,14 @@ struct RotQ {
   }
 };
 
+__device__ __forceinline__ Q4 quat_from_euler_xyz_fast(float roll, float pitch, float yaw) {
+  float sy, cy, sr, cr, sp, cp;
+  fm_sincos(yaw * 0.5f, &sy, &cy);
+  fm_sincos(roll * 0.5f, &sr, &cr);
+  fm_sincos(pitch * 0.5f, &sp, &cp);
+  return Q4{cy * cr * cp + sy * sr * sp, cy * sr * cp - sy * cr * sp, cy * cr * sp + sy * sr * cp, sy * cr * cp - cy * sr * sp};
+}
+
 // ---- Philox4x32-10 (Salmon et al. 2011) ------------------------------------------------
 struct Philox {
   uint32_t k0, k1;      // key = seed
@@ -167,6 +183,16 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   const float u1 = (float)((a >> 8) + 1u) * 5.9604644775390625e-8f;    // (0,1]
   const float u2 = (float)(b >> 8) * 5.9604644775390625e-8f;
   // r = sqrt(-2 ln u1) = sqrt(-2 ln2 * log2 u1); angle in (-pi, pi] so the MUFU sin/cos stay in their accurate range
+  const float r = fm_sqrt(-1.3862943611198906f * fm_log2(u1));
+  float s, c;
+  fm_sincos((u2 - 0.5f) * GR_2PI_F, &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+// Box-Muller pair from ONE 32-bit word: u1 = (low16 + 1) / 65536 in (0,1], u2 = high16 / 65536 in [0,1)
+__device__ __forceinline__ float2 box_muller16(uint32_t x) {
+  const float u1 = (float)((x & 0xFFFFu) + 1u) * 1.52587890625e-5f;
+  const float u2 = (float)(x >> 16) * 1.52587890625e-5f;
   const float r = fm_sqrt(-1.3862943611198906f * fm_log2(u1));
   float s, c;
   fm_sincos((u2 - 0.5f) * GR_2PI_F, &s, &c);

@@ -41,10 +41,9 @@ __global__ void __launch_bounds__(kBwdBlock) racing_step_bwd_kernel(const GrConf
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= st.num_envs) return;
   const float4* __restrict__ P = reinterpret_cast<const float4*>(st.planes);
-  const int64_t S = st.plane_stride;
-  const float m = __ldg(&P[(int64_t)PL_DRAG2 * S + i]).w;
-  const float ef = __ldg(&P[(int64_t)PL_DRAG1 * S + i]).w;
-  const V3 etau = xyz(__ldg(&P[(int64_t)PL_ETAU * S + i]));
+  const float m = __ldg(&P[pidx(PL_DRAG2, i)]).w;
+  const float ef = __ldg(&P[pidx(PL_DRAG1, i)]).w;
+  const V3 etau = xyz(__ldg(&P[pidx(PL_ETAU, i)]));
   const V3 J = v3(cfg.inertia[0], cfg.inertia[1], cfg.inertia[2]);
   const V3 Jinv = v3(1.0f / J.x, 1.0f / J.y, 1.0f / J.z);
   const float dt = cfg.dt, decay = cfg.grad_decay;
@@ -67,7 +66,7 @@ __global__ void __launch_bounds__(kBwdBlock) racing_step_bwd_kernel(const GrConf
   if (io.t_end > io.t_begin) {
     const int t = io.t_end - 1;
 #pragma unroll
-    for (int k = 0; k < GR_TAPE_PLANES; ++k) nx[k] = __ldcs(T + ((int64_t)t * GR_TAPE_PLANES + k) * TS + i);
+    for (int k = 0; k < GR_TAPE_PLANES; ++k) nx[k] = __ldcs(T + (int64_t)t * GR_TAPE_PLANES * TS + tidx(k, i));
     if (io.grad_loss) ng = __ldg(io.grad_loss + (int64_t)t * N + i);
   }
 
@@ -78,7 +77,7 @@ __global__ void __launch_bounds__(kBwdBlock) racing_step_bwd_kernel(const GrConf
     const float g = ng;
     if (t - 1 >= io.t_begin) {     // prefetch the next (earlier) step while this one is processed
 #pragma unroll
-      for (int k = 0; k < GR_TAPE_PLANES; ++k) nx[k] = __ldcs(T + ((int64_t)(t - 1) * GR_TAPE_PLANES + k) * TS + i);
+      for (int k = 0; k < GR_TAPE_PLANES; ++k) nx[k] = __ldcs(T + (int64_t)(t - 1) * GR_TAPE_PLANES * TS + tidx(k, i));
       if (io.grad_loss) ng = __ldg(io.grad_loss + (int64_t)(t - 1) * N + i);
     }
     const Q4 q = quat(c[0]);
@@ -188,7 +187,7 @@ using namespace gr;
 
 extern "C" int gr_step_bwd(const GrConfig* cfg, const GrState* st, const GrBwdIO* io, void* stream) {
   if (!cfg || !st || !io || !st->planes || !io->tape || !io->adjoint || !io->grad_action) return GR_ERR_NULL;
-  if (st->num_envs <= 0 || st->plane_stride < st->num_envs || io->tape_stride < st->num_envs || io->adj_stride < st->num_envs) return GR_ERR_SIZE;
+  if (st->num_envs <= 0 || st->plane_stride < ((st->num_envs + 31) & ~31) || io->tape_stride < ((st->num_envs + 31) & ~31) || io->adj_stride < st->num_envs) return GR_ERR_SIZE;
   if (io->t_begin < 0 || io->t_end < io->t_begin) return GR_ERR_SIZE;
   auto mis = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; };
   if (mis(st->planes) || mis(io->tape) || mis(io->adjoint) || mis(io->grad_action)) return GR_ERR_ALIGN;

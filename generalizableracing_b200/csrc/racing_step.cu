@@ -17,18 +17,20 @@ struct EnvRegs {
   float aux;      // last cross_obs value (RewardManager._step_reward survives resets)
 };
 
+// EnvRegs.om / .aacc hold the BODY-frame angular velocity / acceleration (PL_ANGVEL / PL_ANGACC): the reference
+// round-trips them through the world frame every step (rot(q', w_b') stored, rotinv(q', .) read back: identity up to
+// rounding); only w_b is ever consumed.  EnvRegs.fifo holds tanh(a_{t-1}): the lagged action is only used through tanh.
 template <bool kNoise>
-__device__ __forceinline__ void load_env(EnvRegs& e, const float4* __restrict__ P, int64_t S, int i) {
-  const float4 a0 = ld_plane(P, S, PL_QUAT, i), a1 = ld_plane(P, S, PL_POS, i), a2 = ld_plane(P, S, PL_LINVEL, i),
-               a3 = ld_plane(P, S, PL_ANGVEL, i), a4 = ld_plane(P, S, PL_TORQUE, i), a5 = ld_plane(P, S, PL_ANGACC, i),
-               a6 = ld_plane(P, S, PL_FIFO, i);
-  const float4 c0 = ld_plane_ro(P, S, PL_DRAG2, i), c1 = ld_plane_ro(P, S, PL_DRAG1, i), c2 = ld_plane_ro(P, S, PL_KP, i),
-               c3 = ld_plane_ro(P, S, PL_KD, i), c4 = ld_plane_ro(P, S, PL_ETAU, i);
+__device__ __forceinline__ void load_env(EnvRegs& e, const float4* __restrict__ tile) {
+  const float4 a0 = ld_plane(tile, PL_QUAT), a1 = ld_plane(tile, PL_POS), a2 = ld_plane(tile, PL_LINVEL), a3 = ld_plane(tile, PL_ANGVEL),
+               a4 = ld_plane(tile, PL_TORQUE), a5 = ld_plane(tile, PL_ANGACC), a6 = ld_plane(tile, PL_FIFO);
+  const float4 c0 = ld_plane_ro(tile, PL_DRAG2), c1 = ld_plane_ro(tile, PL_DRAG1), c2 = ld_plane_ro(tile, PL_KP), c3 = ld_plane_ro(tile, PL_KD),
+               c4 = ld_plane_ro(tile, PL_ETAU);
   e.q = quat(a0); e.w = xyz(a1); e.f = a1.w; e.v = xyz(a2); e.eplen = __float_as_int(a2.w);
   e.om = xyz(a3); e.pk = __float_as_uint(a3.w); e.tau = xyz(a4); e.aux = a4.w; e.aacc = xyz(a5); e.fifo = a6;
   e.k2 = xyz(c0); e.m = c0.w; e.k1 = xyz(c1); e.ef = c1.w; e.kp = xyz(c2); e.thr = c2.w; e.kd = xyz(c3); e.etau = xyz(c4);
   if (kNoise) {
-    const float4 n0 = ld_plane_ro(P, S, PL_NOISE0, i), n1 = ld_plane_ro(P, S, PL_NOISE1, i);
+    const float4 n0 = ld_plane_ro(tile, PL_NOISE0), n1 = ld_plane_ro(tile, PL_NOISE1);
     e.dcur = xyz(n0); e.dnext = v3(n0.w, n1.x, n1.y); e.noise_hi = n1.z; e.noise_level = n1.w;
   } else {
     e.dcur = v3(0.f, 0.f, 0.f); e.dnext = v3(0.f, 0.f, 0.f); e.noise_hi = 0.f; e.noise_level = 1.f;
@@ -89,7 +91,7 @@ __device__ __forceinline__ void write_observations(const GrConfig& cfg, const En
 // _reset_idx for one env (L/envs/manager_based_diff_rl_env.py:362-410): curricula, root-state sampler,
 // controller/dynamics/command reset.  Mutates e; returns the new origin.
 template <bool kNoise, bool kPhilox>
-__device__ __forceinline__ V3 reset_env(const GrConfig& cfg, const TrackSmem& tr, EnvRegs& e, const RandSrc<kPhilox>& rs, float thr_normal) {
+__device__ __forceinline__ V3 reset_env(const GrConfig& cfg, const TrackSmem& tr, EnvRegs& e, const Draws<kPhilox>& rs, float thr_normal) {
   const int type = (int)pk_type(e.pk);
   int level = (int)pk_level(e.pk);
   const int acc = (int)pk_acc(e.pk);
@@ -119,11 +121,12 @@ __device__ __forceinline__ V3 reset_env(const GrConfig& cfg, const TrackSmem& tr
   const float dyaw = u_pose1.y * sy + (-cfg.reset_yaw);
   const V3 pos = v3(cfg.default_pos[0], cfg.default_pos[1], cfg.default_pos[2]) + origin + dpos;
   const V3 towards = (tr.gate(type, level, start_gate) + origin) - pos;
-  const float yaw = wrap_to_pi(atan2f(towards.y, towards.x)) + dyaw;
-  e.q = quat_mul(Q4{1.f, 0.f, 0.f, 0.f}, quat_from_euler_xyz(roll, pitch, yaw));
+  const float yaw = wrap_to_pi_atan2(atan2f(towards.y, towards.x)) + dyaw;
+  e.q = quat_mul(Q4{1.f, 0.f, 0.f, 0.f}, quat_from_euler_xyz_fast(roll, pitch, yaw));
   e.w = pos;
   e.v = v3(u_pose1.z * sv + (-cfg.reset_vel), u_pose1.w * sv + (-cfg.reset_vel), u_vel.x * sv + (-cfg.reset_vel));
-  e.om = v3(u_vel.y * sv + (-cfg.reset_vel), u_vel.z * sv + (-cfg.reset_vel), u_vel.w * sv + (-cfg.reset_vel));
+  // DroneDynamics.reset_state (droneDynamics.py:116): ang_vel_b = rotinv(q, ang_vel_w)
+  e.om = quat_rotate_inverse(e.q, v3(u_vel.y * sv + (-cfg.reset_vel), u_vel.z * sv + (-cfg.reset_vel), u_vel.w * sv + (-cfg.reset_vel)));
   e.aacc = v3(0.f, 0.f, 0.f);                      // closure A.1
   // -- CTBRController.reset_idx (L/controllers/controller_diff.py:146-160)
   e.f = 0.f; e.tau = v3(0.f, 0.f, 0.f);
@@ -136,33 +139,34 @@ __device__ __forceinline__ V3 reset_env(const GrConfig& cfg, const TrackSmem& tr
   }
   // -- DiffActions.reset_idx (QD/mdp/diff_action.py:233)
   e.thr = 1.0f + thr_normal * cfg.thr_err_reset_std;
-  // -- RacingCommand._resample_command (QD/mdp/commands.py:262-306): slots 28..33 gate, 34..39 next gate
+  // -- RacingCommand._resample_command (QD/mdp/commands.py:262-306)
   if (kNoise) {
-    const float4 u_g0 = rs.get4(7), u_g1 = rs.get4(8);
+    const float4 u_g0 = rs.get4(7), u_g1 = rs.get4(8);          // slots 28..30 current gate xyz, 31..33 next gate xyz
     e.dcur = gate_noise(e.noise_hi, u_g0.x, u_g0.y, u_g0.z);
-    e.dnext = gate_noise(e.noise_hi, u_g1.z, u_g1.w, rs.get4(9).x);
+    e.dnext = gate_noise(e.noise_hi, u_g0.w, u_g1.x, u_g1.y);
   }
   e.pk = pk_make((uint32_t)start_gate, 0u, (uint32_t)level, (uint32_t)type, 1u);
   e.eplen = 0;
   return origin;
 }
 
-template <bool kNoise, bool kStats>
-__device__ __forceinline__ void store_env(const EnvRegs& e, float4* __restrict__ P, int64_t S, int i, bool cold_dirty, bool noise_dirty) {
-  st_plane(P, S, PL_QUAT, i, pack(e.q));
-  st_plane(P, S, PL_POS, i, pack(e.w, e.f));
-  st_plane(P, S, PL_LINVEL, i, pack(e.v, __int_as_float(e.eplen)));
-  st_plane(P, S, PL_ANGVEL, i, pack(e.om, __uint_as_float(e.pk)));
-  st_plane(P, S, PL_TORQUE, i, pack(e.tau, e.aux));
-  st_plane(P, S, PL_ANGACC, i, pack(e.aacc, 0.f));
+template <bool kNoise>
+__device__ __forceinline__ void store_env(const EnvRegs& e, float4* __restrict__ tile, bool cold_dirty, bool noise_dirty) {
+  st_plane(tile, PL_QUAT, pack(e.q));
+  st_plane(tile, PL_POS, pack(e.w, e.f));
+  st_plane(tile, PL_LINVEL, pack(e.v, __int_as_float(e.eplen)));
+  st_plane(tile, PL_ANGVEL, pack(e.om, __uint_as_float(e.pk)));
+  st_plane(tile, PL_TORQUE, pack(e.tau, e.aux));
+  st_plane(tile, PL_ANGACC, pack(e.aacc, 0.f));
+  st_plane(tile, PL_FIFO, e.fifo);
   if (cold_dirty) {
-    P[(int64_t)PL_DRAG2 * S + i] = pack(e.k2, e.m);
-    P[(int64_t)PL_DRAG1 * S + i] = pack(e.k1, e.ef);
-    P[(int64_t)PL_KP * S + i] = pack(e.kp, e.thr);
+    tile[PL_DRAG2 * kTile] = pack(e.k2, e.m);
+    tile[PL_DRAG1 * kTile] = pack(e.k1, e.ef);
+    tile[PL_KP * kTile] = pack(e.kp, e.thr);
   }
   if (kNoise && noise_dirty) {
-    P[(int64_t)PL_NOISE0 * S + i] = make_float4(e.dcur.x, e.dcur.y, e.dcur.z, e.dnext.x);
-    P[(int64_t)PL_NOISE1 * S + i] = make_float4(e.dnext.y, e.dnext.z, e.noise_hi, e.noise_level);
+    tile[PL_NOISE0 * kTile] = make_float4(e.dcur.x, e.dcur.y, e.dcur.z, e.dnext.x);
+    tile[PL_NOISE1 * kTile] = make_float4(e.dnext.y, e.dnext.z, e.noise_hi, e.noise_level);
   }
 }
 
@@ -175,6 +179,13 @@ __device__ __forceinline__ void store_env(const EnvRegs& e, float4* __restrict__
 // state once: the reward section and the observation section share them unless the env was reset or
 // switched gate in this step (rare, recomputed in a divergent tail).
 // =============================================================================================
+#ifdef GR_PHASE_TIMING
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define GR_STAMP(k) do { if (io.phase_times && (threadIdx.x & 31) == 0) io.phase_times[(size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 5 + (k)] = gtime(); } while (0)
+#else
+#define GR_STAMP(k) do { } while (0)
+#endif
+
 __device__ __forceinline__ float4 fm_tanh4(float4 a) { return make_float4(fm_tanh(a.x), fm_tanh(a.y), fm_tanh(a.z), fm_tanh(a.w)); }
 
 template <bool kNoise, bool kDiff, bool kPhilox, bool kStats>
@@ -184,18 +195,37 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = i < st.num_envs;
   const int li = active ? i : st.num_envs - 1;        // inactive threads shadow the last env (loads only)
-  float4* __restrict__ P = reinterpret_cast<float4*>(st.planes);
-  const int64_t S = st.plane_stride;
+  float4* __restrict__ tile = tile_ptr(reinterpret_cast<float4*>(st.planes), li);
 
+  // Two orderings of the same prologue.  Launched with programmatic dependent launch (st.launch_flags & GR_LAUNCH_PDL)
+  // the part that does not depend on earlier kernels -- Philox draws, gate-table staging -- runs BEFORE the grid
+  // dependency wait and overlaps the tail of the previous kernel; otherwise the state loads are issued first so that
+  // the same work hides under their latency.
+  const bool pdl = (st.launch_flags & GR_LAUNCH_PDL) != 0;
+  GR_STAMP(0);
   EnvRegs e;
-  load_env<kNoise>(e, P, S, li);
-  const float4 a_t = __ldcs(reinterpret_cast<const float4*>(io.action) + li);
-  float4 eps0 = make_float4(0.f, 0.f, 0.f, 0.f), eps1 = eps0;
-  if (kStats) { eps0 = ld_plane(P, S, PL_EPSUM0, li); eps1 = ld_plane(P, S, PL_EPSUM1, li); }
+  float4 a_t, eps0 = make_float4(0.f, 0.f, 0.f, 0.f), eps1 = eps0;
+  if (!pdl) {
+    load_env<kNoise>(e, tile);
+    a_t = __ldcs(reinterpret_cast<const float4*>(io.action) + li);
+    if (kStats) { eps0 = ld_plane(tile, PL_EPSUM0); eps1 = ld_plane(tile, PL_EPSUM1); }
+  }
   const RandSrc<kPhilox> rs(rng, li, st.env_id_offset + li);
-  const float4 n01 = rs.get4(0), n23 = rs.get4(1);   // obs normals (slots 0..5), thr_est_error normal (slot 6)
-
+  float4 n01, n23;                                     // obs normals (slots 0..5), thr_est_error normal (slot 6)
+  if (kPhilox || !pdl) rs.normals8(n01, n23);
   const TrackSmem tr = stage_track(track, reinterpret_cast<const int2*>(st.chunk_types), st.num_envs, smem_rows);
+  if (pdl) {
+    pdl_wait();
+    GR_STAMP(1);
+    load_env<kNoise>(e, tile);
+    a_t = __ldcs(reinterpret_cast<const float4*>(io.action) + li);
+    if (kStats) { eps0 = ld_plane(tile, PL_EPSUM0); eps1 = ld_plane(tile, PL_EPSUM1); }
+    if (!kPhilox) rs.normals8(n01, n23);
+  }
+  // (measured: generating the rare-path draws speculatively for every env while the loads are in flight costs more
+  //  than it saves -- +1.2 us median compute, stragglers unchanged -- so the reset / pass tails draw on demand)
+  const Draws<kPhilox> draws{rs, nullptr};
+  pdl_launch_dependents();
   // a warp that is entirely past the last env leaves; in the (single) ragged warp the inactive lanes keep shadowing
   // the last env so the warp collectives below stay full-width, and skip every store
   if (!__any_sync(0xffffffffu, active)) return;
@@ -204,6 +234,9 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
   int level = (int)pk_level(e.pk);
   int gate_id = (int)pk_gate(e.pk);
   const uint32_t fresh = pk_fresh(e.pk);
+#ifdef GR_PHASE_TIMING
+  if (__float_as_uint(e.q.w + e.w.x + e.v.x + e.om.x + e.tau.x + e.aacc.x + e.fifo.x + e.k2.x + e.k1.x + e.kp.x + e.kd.x + e.etau.x + a_t.x + eps0.x + eps1.x + e.dcur.x + e.noise_hi) != 0x7fc12345u) GR_STAMP(2);
+#endif
   V3 origin = xyz(tr.origin_row(type, level));
   V3 gate_rel = tr.gate(type, level, gate_id);
   const float dt = cfg.dt;
@@ -214,15 +247,15 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
 
   // ---- 1. process_action (L/managers/action_manager.py:44-45; QD/mdp/diff_action.py:160-176) ----
   // FIFO (lag 1): the applied action is a_{t-1}; prev_action is a_{t-1} unless the latches were zeroed by a reset
-  const float4 th_lag = fm_tanh4(e.fifo);
+  const float4 th_lag = e.fifo;                 // tanh(a_{t-1}), stored by the previous step
   const float4 th_a = fm_tanh4(a_t);
   const float4 th_prev = fresh ? make_float4(0.f, 0.f, 0.f, 0.f) : th_lag;
   // get_state_from_sim (QD/mdp/diff_action.py:126-154)
   const RotQ R0(e.q);
   const V3 p = e.w - origin;
-  const V3 om_b = R0.rotinv(e.om);
+  const V3 om_b = e.om;
   const V3 v_b = R0.rotinv(e.v);
-  const V3 aacc_b = R0.rotinv(e.aacc);
+  const V3 aacc_b = e.aacc;
   const float cmd0 = (th_lag.x * s0 + s0) * e.thr;
   const V3 cmd_rate = v3(th_lag.y * sb, th_lag.z * sb, th_lag.w * sb);
 
@@ -251,28 +284,26 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
   const V3 v1 = e.v + acc * dt;
   const V3 omb1 = om_b + alpha * dt;
   const RotQ R1(q1);
-  const V3 omw1 = R1.rot(omb1);
 
   // ---- BPTT tape planes 0..5 of this step (consumer: racing_bwd.cu; SURVEY.md A.6/A.7, derived form) ----
   if (kDiff && io.tape && active) {
     float4* __restrict__ T = reinterpret_cast<float4*>(io.tape);
-    const int64_t TS = io.tape_stride;
     const float m0 = (cmd0 >= cfg.thrust_lo && cmd0 <= cfg.thrust_hi) ? 1.0f : 0.0f;
     const float A0 = m0 * e.thr * s0 * (1.0f - th_lag.x * th_lag.x) * (1.0f - e.ef);
     const V3 mk = v3((cmd_rate.x >= -sb && cmd_rate.x <= sb) ? sb : 0.0f, (cmd_rate.y >= -sb && cmd_rate.y <= sb) ? sb : 0.0f,
                      (cmd_rate.z >= -sb && cmd_rate.z <= sb) ? sb : 0.0f);
     const V3 A = mk * v3(1.0f - th_lag.y * th_lag.y, 1.0f - th_lag.z * th_lag.z, 1.0f - th_lag.w * th_lag.w) * one_m_etau * J * e.kp;
     const V3 D = -(2.0f * (e.k2 * vabs(v_b)) + e.k1);
-    __stcs(T + 0 * TS + i, pack(e.q));
-    __stcs(T + 1 * TS + i, pack(om_b, A0));
-    __stcs(T + 2 * TS + i, pack(F_b, A.x));
-    __stcs(T + 3 * TS + i, pack(D, A.y));
-    __stcs(T + 4 * TS + i, pack(v1, A.z));
-    __stcs(T + 5 * TS + i, pack(omb1, __uint_as_float(fresh)));
+    __stcs(T + tidx(0, i), pack(e.q));
+    __stcs(T + tidx(1, i), pack(om_b, A0));
+    __stcs(T + tidx(2, i), pack(F_b, A.x));
+    __stcs(T + tidx(3, i), pack(D, A.y));
+    __stcs(T + tidx(4, i), pack(v1, A.z));
+    __stcs(T + tidx(5, i), pack(omb1, __uint_as_float(fresh)));
   }
 
   // ---- 2. "physics": closure A.1, truth := nominal; world pose, last angular acceleration ----
-  e.w = p1 + origin; e.q = q1; e.v = v1; e.om = omw1; e.aacc = R1.rot(alpha);
+  e.w = p1 + origin; e.q = q1; e.v = v1; e.om = omb1; e.aacc = alpha;
   e.f = f_new; e.tau = tau_new;
   // ---- 3. align (droneDynamics.py:156-181): value = sim-derived state; aligned local position for the loss ----
   const V3 p_al = e.w - origin;
@@ -316,8 +347,7 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
       const float tw = cfg.w_reward[k] != 0.0f ? terms[k] * cfg.w_reward[k] : 0.0f;
       const float value = tw * dt;
       reward += value;
-      terms[k] = tw;                                              // RewardManager._step_reward = value / dt
-      if (kStats) { if (k < 4) (&eps0.x)[k] += value; else (&eps1.x)[k - 4] += value; }
+      terms[k] = tw;                                              // RewardManager._step_reward = value / dt; episode sums below
     }
   }
   e.aux = terms[4] > 0.0f ? 1.0f : 0.0f;                 // cross_obs (QD/mdp/observation.py:97-104)
@@ -326,40 +356,26 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
   const bool reset = terminated || time_out;
   bool noise_dirty = false;
   bool passed = pass_pre;                                 // 8. on an env that did not reset this is the same test
-  // episode log (extras["log"], manager_based_diff_rl_env.py:380-407): warp-aggregated, sharded atomics -- a plain
-  // atomicAdd per resetting env serialises on one L2 line and cost 3x the whole kernel at a 5 % reset rate.
-  if (io.log_accum) {
-    const unsigned rm = __ballot_sync(0xffffffffu, reset && active);
-    if (rm) {
-      const bool r = reset && active;
-      float v[4 + GR_NUM_REWARD_TERMS];
-      v[0] = r ? 1.0f : 0.0f;
-      v[1] = r ? (float)pk_acc(e.pk) : 0.0f;
-      v[2] = (r && time_out) ? 1.0f : 0.0f;
-      v[3] = (r && terminated) ? 1.0f : 0.0f;
+  if (reset) {
+    if (kStats) {          // RewardManager.compute adds this step's values to the episode sums before the reset logs them
 #pragma unroll
-      for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k) v[4 + k] = (kStats && r) ? (k < 4 ? (&eps0.x)[k] : (&eps1.x)[k - 4]) : 0.0f;
+      for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k) { if (k < 4) (&eps0.x)[k] += terms[k] * dt; else (&eps1.x)[k - 4] += terms[k] * dt; }
+    }
+    // episode log (extras["log"], manager_based_diff_rl_env.py:380-407): fire-and-forget RED ops on one of GR_LOG_SHARDS
+    // accumulator rows picked by warp id (a single row serialises on one L2 line: 3x the kernel time at a 5 % reset rate)
+    if (io.log_accum && active) {
+      float* acc_row = io.log_accum + (size_t)((i >> 5) & (GR_LOG_SHARDS - 1)) * GR_LOG_SLOTS;
+      atomicAdd(acc_row + GR_LOG_NUM_RESET, 1.0f);
+      atomicAdd(acc_row + GR_LOG_SUM_GATES, (float)pk_acc(e.pk));
+      if (time_out) atomicAdd(acc_row + GR_LOG_NUM_TIMEOUT, 1.0f);
+      if (terminated) atomicAdd(acc_row + GR_LOG_NUM_TERMINATED, 1.0f);
+      if (kStats) {
 #pragma unroll
-      for (int k = 0; k < 4 + GR_NUM_REWARD_TERMS; ++k) {
-        if (!kStats && k >= 4) break;
-        v[k] = warp_sum(v[k]);
-      }
-      if ((threadIdx.x & 31) == 0) {
-        float* acc_row = io.log_accum + (size_t)(blockIdx.x & (GR_LOG_SHARDS - 1)) * GR_LOG_SLOTS;
-        atomicAdd(acc_row + GR_LOG_NUM_RESET, v[0]);
-        atomicAdd(acc_row + GR_LOG_SUM_GATES, v[1]);
-        if (v[2] != 0.0f) atomicAdd(acc_row + GR_LOG_NUM_TIMEOUT, v[2]);
-        if (v[3] != 0.0f) atomicAdd(acc_row + GR_LOG_NUM_TERMINATED, v[3]);
-        if (kStats) {
-#pragma unroll
-          for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k) atomicAdd(acc_row + GR_LOG_SUM_EPSUM + k, v[4 + k]);
-        }
+        for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k) atomicAdd(acc_row + GR_LOG_SUM_EPSUM + k, k < 4 ? (&eps0.x)[k] : (&eps1.x)[k - 4]);
       }
     }
-  }
-  if (reset) {
     if (kStats) { eps0 = make_float4(0.f, 0.f, 0.f, 0.f); eps1 = eps0; }
-    origin = reset_env<kNoise, kPhilox>(cfg, tr, e, rs, n23.z);
+    origin = reset_env<kNoise, kPhilox>(cfg, tr, e, draws, n23.z);
     level = (int)pk_level(e.pk);
     gate_id = (int)pk_gate(e.pk);
     gate_rel = tr.gate(type, level, gate_id);
@@ -378,9 +394,9 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
     e.pk = pk_make((uint32_t)gate_id, acc_g, (uint32_t)level, (uint32_t)type, pk_fresh(e.pk));
     gate_rel = tr.gate(type, level, gate_id);
     if (kNoise) {
-      const float4 u0 = rs.get4(10), u1 = rs.get4(11);     // slots 40..45 gate, 46..51 next
+      const float4 u0 = draws.get4(10), u1 = draws.get4(11);     // slots 40..42 gate xyz, 43..45 next gate xyz
       e.dcur = gate_noise(e.noise_hi, u0.x, u0.y, u0.z);
-      e.dnext = gate_noise(e.noise_hi, u1.z, u1.w, rs.get4(12).x);
+      e.dnext = gate_noise(e.noise_hi, u0.w, u1.x, u1.y);
       noise_dirty = true;
     }
   }
@@ -403,7 +419,7 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
       // plane 6: d loss / d aligned position (target + falling terms); d loss / d velocity is rebuilt from v1
       const float inv = ld > 0.0f ? cfg.w_loss[0] / ld : 0.0f;
       const float dfall = -cfg.w_loss[2] * (1.0f + 20.0f * z) / (den * den);
-      __stcs(reinterpret_cast<float4*>(io.tape) + 6 * io.tape_stride + i,
+      __stcs(reinterpret_cast<float4*>(io.tape) + tidx(6, i),
              make_float4(-dvec.x * inv, -dvec.y * inv, -dvec.z * inv + dfall, 0.0f));
     }
   }
@@ -458,11 +474,18 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
     if (io.aux_obs) io.aux_obs[i] = e.aux;
   }
 
+  GR_STAMP(3);
   // ---- 12. outputs + state write-back ----
-  e.fifo = a_t;
-  store_env<kNoise, kStats>(e, P, S, i, reset, noise_dirty);
-  st_plane(P, S, PL_FIFO, i, e.fifo);
-  if (kStats) { st_plane(P, S, PL_EPSUM0, i, eps0); st_plane(P, S, PL_EPSUM1, i, eps1); }
+  e.fifo = th_a;
+  store_env<kNoise>(e, tile, reset, noise_dirty);
+  if (kStats) {
+    if (!reset) {        // deferred to here: the episode-sum planes are the last loads to arrive
+#pragma unroll
+      for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k) { if (k < 4) (&eps0.x)[k] += terms[k] * dt; else (&eps1.x)[k - 4] += terms[k] * dt; }
+    }
+    st_plane(tile, PL_EPSUM0, eps0);
+    st_plane(tile, PL_EPSUM1, eps1);
+  }
   io.reward[i] = reward;
   io.terminated[i] = terminated ? 1 : 0;
   io.time_out[i] = time_out ? 1 : 0;
@@ -472,6 +495,7 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
 #pragma unroll
     for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k) io.reward_terms[i * GR_NUM_REWARD_TERMS + k] = terms[k];
   }
+  GR_STAMP(4);
 }
 
 // =============================================================================================
@@ -487,28 +511,28 @@ __global__ void __launch_bounds__(256) racing_reset_kernel(const GrConfig cfg, c
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = i < st.num_envs;
   const int li = active ? i : st.num_envs - 1;
-  float4* __restrict__ P = reinterpret_cast<float4*>(st.planes);
-  const int64_t S = st.plane_stride;
+  float4* __restrict__ tile = tile_ptr(reinterpret_cast<float4*>(st.planes), li);
   EnvRegs e;
-  load_env<kNoise>(e, P, S, li);
+  load_env<kNoise>(e, tile);
   const RandSrc<kPhilox> rs(rng, li, st.env_id_offset + li);
-  const float4 n01 = rs.get4(0), n23 = rs.get4(1);
+  float4 n01, n23;
+  rs.normals8(n01, n23);
   const TrackSmem tr = stage_track(track, reinterpret_cast<const int2*>(st.chunk_types), st.num_envs, smem_rows);
   if (!active) return;
   const bool do_reset = mode == 1 || (mode == 0 && mask[i] != 0);
   const int type = (int)pk_type(e.pk);
   V3 origin;
   if (do_reset) {
-    origin = reset_env<kNoise, kPhilox>(cfg, tr, e, rs, n23.z);
-    store_env<kNoise, kStats>(e, P, S, i, true, true);
-    if (kStats) { st_plane(P, S, PL_EPSUM0, i, make_float4(0.f, 0.f, 0.f, 0.f)); st_plane(P, S, PL_EPSUM1, i, make_float4(0.f, 0.f, 0.f, 0.f)); }
+    origin = reset_env<kNoise, kPhilox>(cfg, tr, e, Draws<kPhilox>{rs, nullptr}, n23.z);
+    store_env<kNoise>(e, tile, true, true);
+    if (kStats) { st_plane(tile, PL_EPSUM0, make_float4(0.f, 0.f, 0.f, 0.f)); st_plane(tile, PL_EPSUM1, make_float4(0.f, 0.f, 0.f, 0.f)); }
   } else {
     origin = xyz(tr.origin_row(type, (int)pk_level(e.pk)));
   }
   const int level = (int)pk_level(e.pk), gate_id = (int)pk_gate(e.pk);
   if (obs) {
     const V3 gate_rel = tr.gate(type, level, gate_id), next_rel = tr.gate(type, level, (gate_id + 1) % tr.gates);
-    write_observations<kNoise>(cfg, e, origin, gate_rel, next_rel, tanh4(e.fifo), n01, n23, e.aux, i, obs, critic, aux_out);
+    write_observations<kNoise>(cfg, e, origin, gate_rel, next_rel, e.fifo, n01, n23, e.aux, i, obs, critic, aux_out);
   }
 }
 
@@ -536,7 +560,6 @@ __global__ void racing_startup_kernel(const GrConfig cfg, const GrTrack track, c
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= st.num_envs) return;
   float4* __restrict__ P = reinterpret_cast<float4*>(st.planes);
-  const int64_t S = st.plane_stride;
   float s[GR_SRND_STRIDE];
   startup_draws(srnd, seed, i, st.env_id_offset + i, s);
   const int type = terrain_types[i];
@@ -557,23 +580,23 @@ __global__ void racing_startup_kernel(const GrConfig cfg, const GrTrack track, c
   const float m = cfg.mass;
   const float b2 = cfg.drag2 * m, b1 = cfg.drag1 * m;
   const float zero = 0.0f;
-  P[(int64_t)PL_QUAT * S + i] = make_float4(1.f, 0.f, 0.f, 0.f);
-  P[(int64_t)PL_POS * S + i] = make_float4(zero, zero, zero, zero);
-  P[(int64_t)PL_LINVEL * S + i] = make_float4(zero, zero, zero, __int_as_float(0));
-  P[(int64_t)PL_ANGVEL * S + i] = make_float4(zero, zero, zero, __uint_as_float(pk_make(0u, 0u, (uint32_t)level, (uint32_t)type, 0u)));
-  P[(int64_t)PL_TORQUE * S + i] = make_float4(zero, zero, zero, zero);
-  P[(int64_t)PL_ANGACC * S + i] = make_float4(zero, zero, zero, zero);
-  P[(int64_t)PL_FIFO * S + i] = make_float4(zero, zero, zero, zero);
-  P[(int64_t)PL_DRAG2 * S + i] = make_float4(b2, b2, b2 * cfg.z_drag, m);
-  P[(int64_t)PL_DRAG1 * S + i] = make_float4(b1, b1, b1 * cfg.z_drag, expf(-cfg.dt / thrust_delay));
-  P[(int64_t)PL_KP * S + i] = pack(kp, 1.0f + s[12] * cfg.thr_err_init_std);
-  P[(int64_t)PL_KD * S + i] = pack(kd, 0.f);
-  P[(int64_t)PL_ETAU * S + i] = make_float4(expf(-cfg.dt / torque_delay.x), expf(-cfg.dt / torque_delay.y), expf(-cfg.dt / torque_delay.z), 0.f);
-  P[(int64_t)PL_NOISE0 * S + i] = make_float4(zero, zero, zero, zero);
-  P[(int64_t)PL_NOISE1 * S + i] = make_float4(zero, zero, cfg.cmd_noise_pos, 1.0f);
+  P[pidx(PL_QUAT, i)] = make_float4(1.f, 0.f, 0.f, 0.f);
+  P[pidx(PL_POS, i)] = make_float4(zero, zero, zero, zero);
+  P[pidx(PL_LINVEL, i)] = make_float4(zero, zero, zero, __int_as_float(0));
+  P[pidx(PL_ANGVEL, i)] = make_float4(zero, zero, zero, __uint_as_float(pk_make(0u, 0u, (uint32_t)level, (uint32_t)type, 0u)));
+  P[pidx(PL_TORQUE, i)] = make_float4(zero, zero, zero, zero);
+  P[pidx(PL_ANGACC, i)] = make_float4(zero, zero, zero, zero);
+  P[pidx(PL_FIFO, i)] = make_float4(zero, zero, zero, zero);
+  P[pidx(PL_DRAG2, i)] = make_float4(b2, b2, b2 * cfg.z_drag, m);
+  P[pidx(PL_DRAG1, i)] = make_float4(b1, b1, b1 * cfg.z_drag, expf(-cfg.dt / thrust_delay));
+  P[pidx(PL_KP, i)] = pack(kp, 1.0f + s[12] * cfg.thr_err_init_std);
+  P[pidx(PL_KD, i)] = pack(kd, 0.f);
+  P[pidx(PL_ETAU, i)] = make_float4(expf(-cfg.dt / torque_delay.x), expf(-cfg.dt / torque_delay.y), expf(-cfg.dt / torque_delay.z), 0.f);
+  P[pidx(PL_NOISE0, i)] = make_float4(zero, zero, zero, zero);
+  P[pidx(PL_NOISE1, i)] = make_float4(zero, zero, cfg.cmd_noise_pos, 1.0f);
   if (st.num_planes >= GR_NUM_PLANES_WITH_STATS) {
-    P[(int64_t)PL_EPSUM0 * S + i] = make_float4(zero, zero, zero, zero);
-    P[(int64_t)PL_EPSUM1 * S + i] = make_float4(zero, zero, zero, zero);
+    P[pidx(PL_EPSUM0, i)] = make_float4(zero, zero, zero, zero);
+    P[pidx(PL_EPSUM1, i)] = make_float4(zero, zero, zero, zero);
   }
 }
 
@@ -584,7 +607,13 @@ __global__ void fill_rand_kernel(float4* __restrict__ out, const int num_envs, c
   const int i = idx / calls, c = idx - i * calls;
   GrRandom r; r.rnd = nullptr; r.seed = seed; r.step = step;
   const RandSrc<true> rs(r, i, env_id_offset + i);
-  out[idx] = rs.get4(c);
+  if (c < 2) {
+    float4 a, b;
+    rs.normals8(a, b);
+    out[idx] = c == 0 ? a : b;
+  } else {
+    out[idx] = rs.get4(c);
+  }
 }
 
 __global__ void fill_startup_rand_kernel(float* __restrict__ out, const int num_envs, const int env_id_offset, const uint64_t seed) {
@@ -608,7 +637,7 @@ static inline bool misaligned16(const void* p) { return (reinterpret_cast<uintpt
 
 static int check_common(const GrConfig* cfg, const GrTrack* tr, const GrState* st) {
   if (!cfg || !tr || !st || !st->planes || !tr->rows || !st->chunk_types) return GR_ERR_NULL;
-  if (st->num_envs <= 0 || st->plane_stride < st->num_envs) return GR_ERR_SIZE;
+  if (st->num_envs <= 0 || st->plane_stride < ((st->num_envs + 31) & ~31)) return GR_ERR_SIZE;
   if (st->num_planes != GR_NUM_PLANES && st->num_planes != GR_NUM_PLANES_WITH_STATS) return GR_ERR_SIZE;
   if (tr->types < 1 || tr->types > 32 || tr->levels < 1 || tr->levels > 64 || tr->gates < 1 || tr->gates > GR_MAX_GATES) return GR_ERR_SIZE;
   if (misaligned16(st->planes) || misaligned16(tr->rows)) return GR_ERR_ALIGN;
@@ -641,8 +670,17 @@ static int launch_step(const GrConfig* cfg, const GrTrack* tr, const GrState* st
   if (rc != GR_OK) return rc;
   const int kBlock = block_threads(st);
   const int grid = (st->num_envs + kBlock - 1) / kBlock;
-  kernel<<<grid, kBlock, bytes, s>>>(*cfg, *tr, *st, *rng, *io);
-  return (int)cudaGetLastError();
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)grid);
+  lc.blockDim = dim3((unsigned)kBlock);
+  lc.dynamicSmemBytes = bytes;
+  lc.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = (st->launch_flags & GR_LAUNCH_PDL) ? 1 : 0;
+  return (int)cudaLaunchKernelEx(&lc, kernel, *cfg, *tr, *st, *rng, *io);
 }
 
 template <bool kNoise, bool kDiff, bool kPhilox>
@@ -667,7 +705,7 @@ extern "C" int gr_step_fwd(const GrConfig* cfg, const GrTrack* track, const GrSt
   if (misaligned16(io->action) || misaligned16(io->obs) || (io->critic_obs && misaligned16(io->critic_obs)) ||
       (rng->rnd && misaligned16(rng->rnd)) || (io->tape && misaligned16(io->tape)))
     return GR_ERR_ALIGN;
-  if (io->tape && io->tape_stride < st->num_envs) return GR_ERR_SIZE;
+  if (io->tape && io->tape_stride < ((st->num_envs + 31) & ~31)) return GR_ERR_SIZE;
   const bool diff = io->loss != nullptr || io->tape != nullptr || io->loss_terms != nullptr;
   const bool stats = st->num_planes == GR_NUM_PLANES_WITH_STATS;
   const bool philox = rng->rnd == nullptr;
@@ -727,7 +765,7 @@ extern "C" int gr_env_observe(const GrConfig* cfg, const GrTrack* track, const G
 extern "C" int gr_env_startup(const GrConfig* cfg, const GrTrack* track, const GrState* st, const int32_t* terrain_types, int32_t* chunk_types_out,
                               const float* srnd, uint64_t seed, void* stream) {
   if (!cfg || !track || !st || !st->planes || !terrain_types || !chunk_types_out) return GR_ERR_NULL;
-  if (st->num_envs <= 0 || st->plane_stride < st->num_envs) return GR_ERR_SIZE;
+  if (st->num_envs <= 0 || st->plane_stride < ((st->num_envs + 31) & ~31)) return GR_ERR_SIZE;
   if (st->num_planes != GR_NUM_PLANES && st->num_planes != GR_NUM_PLANES_WITH_STATS) return GR_ERR_SIZE;
   if (misaligned16(st->planes) || (srnd && misaligned16(srnd))) return GR_ERR_ALIGN;
   if (track->types < 1 || track->types > 32 || track->levels < 1 || track->levels > 64) return GR_ERR_SIZE;

@@ -14,6 +14,7 @@ Every step is ONE kernel launch (gr_step_fwd); there is no host synchronisation 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -115,7 +116,7 @@ class RacingVecEnv:
     def __init__(self, cfg: RacingCfg, table: GateTable, num_envs: int, device="cuda:0", seed: int = 42,
                  rng_mode: str = "philox", episode_stats: bool = True, env_id_offset: int = 0,
                  global_num_envs: Optional[int] = None, terrain_types: Optional[torch.Tensor] = None,
-                 startup_rnd: Optional[torch.Tensor] = None, bptt_horizon: int = 0, block_threads: int = 0, _lib=None):
+                 startup_rnd: Optional[torch.Tensor] = None, bptt_horizon: int = 0, block_threads: int = 0, pdl: Optional[bool] = None, _lib=None):
         self.cfg = cfg
         self.table = table
         self.num_envs = N = int(num_envs)
@@ -138,8 +139,10 @@ class RacingVecEnv:
         self._track = B.GrTrack(self._rows.data_ptr(), table.num_types, table.num_levels, table.num_gates)
         # ---- state planes
         self.num_planes = L.NUM_PLANES_WITH_STATS if episode_stats else L.NUM_PLANES
-        self._stride = (N + 7) // 8 * 8
-        self.planes = torch.zeros(self.num_planes, self._stride, 4, dtype=torch.float32, device=dev)
+        self.num_tiles = (N + L.TILE - 1) // L.TILE
+        self._stride = self.num_tiles * L.TILE               # env capacity
+        # [tiles, 16 planes, 32 lanes, 4]: one contiguous 8 KB block per warp (layout.py)
+        self.planes = torch.zeros(self.num_tiles, L.TILE_PLANES, L.TILE, 4, dtype=torch.float32, device=dev)
         if terrain_types is None:
             terrain_types = default_terrain_types(N, table.num_types, env_id_offset, global_num_envs)
         tt = terrain_types.to(torch.int32).cpu()
@@ -149,8 +152,11 @@ class RacingVecEnv:
         spans = [int(tt[s:s + 256].max() - tt[s:s + 256].min()) + 1 for s in range(0, N, 256)]
         self._terrain_types = tt.to(dev)
         self._chunk_types = torch.zeros(((N + 63) // 64) * 2, dtype=torch.int32, device=dev)
+        if pdl is None:
+            pdl = os.environ.get("GRACING_PDL", "1") != "0"
+        flags = B.GR_LAUNCH_PDL if (pdl and self.device.type == "cuda") else 0
         self._state = B.GrState(self.planes.data_ptr(), self._stride, N, self.num_planes, int(env_id_offset), max(spans),
-                                int(block_threads), self._chunk_types.data_ptr())
+                                int(block_threads), flags, self._chunk_types.data_ptr())
         self._rng = B.GrRandom(None, self.seed, 0)
         self._step_count = 0
         # ---- outputs (ping-pong so that the tensors returned by step t stay valid during step t+1)
@@ -206,29 +212,53 @@ class RacingVecEnv:
     def unwrapped(self):
         return self
 
+    def plane(self, pl: int) -> torch.Tensor:
+        """Live [tiles, 32, 4] view of one state plane (env i = [i // 32, i % 32])."""
+        return self.planes[:, pl]
+
+    def read_plane(self, pl: int) -> torch.Tensor:
+        """[N, 4] copy of one state plane."""
+        return self.planes[:, pl].reshape(-1, 4)[: self.num_envs]
+
+    def write_plane(self, pl: int, cols: slice, value: torch.Tensor):
+        """Write value[N, k] into columns `cols` of a state plane."""
+        v = value.to(self.device)
+        buf = torch.zeros(self._stride, v.shape[-1], dtype=v.dtype, device=self.device)
+        buf[: self.num_envs] = v
+        if self._stride != self.num_envs:        # keep the padding lanes of the last tile untouched
+            buf[self.num_envs:] = self.planes[:, pl].reshape(-1, 4)[self.num_envs:, cols].view(v.dtype) if v.dtype != torch.float32 \
+                else self.planes[:, pl].reshape(-1, 4)[self.num_envs:, cols]
+        if v.dtype == torch.float32:
+            self.planes[:, pl, :, cols] = buf.view(self.num_tiles, L.TILE, -1)
+        else:
+            self.planes[:, pl, :, cols].view(v.dtype).copy_(buf.view(self.num_tiles, L.TILE, -1))
+
     @property
     def episode_length_buf(self) -> torch.Tensor:
-        """Live int32 view into the state planes (assignable, as on_policy_runner.py:118-121 does)."""
-        return self.planes[L.PL_LINVEL, : self.num_envs, 3].view(torch.int32)
+        """int32 [N] copy of the per-env episode step counters; assign to write them (on_policy_runner.py:118-121)."""
+        return self.planes[:, L.PL_LINVEL, :, 3].reshape(-1)[: self.num_envs].view(torch.int32)
 
     @episode_length_buf.setter
     def episode_length_buf(self, value: torch.Tensor):
-        self.planes[L.PL_LINVEL, : self.num_envs, 3].view(torch.int32).copy_(value.to(self.device, torch.int32))
+        self.write_plane(L.PL_LINVEL, slice(3, 4), value.to(self.device, torch.int32).reshape(-1, 1))
 
     def state_dict_view(self) -> dict:
-        """Named views of the SoA state (diagnostics / tests); world-frame root state like robot.data."""
-        P, N = self.planes, self.num_envs
-        pk = P[L.PL_ANGVEL, :N, 3].view(torch.int32)
+        """Named [N, ...] copies of the env state (diagnostics / tests); world-frame root state like robot.data."""
+        R = self.read_plane
+        q, pos, lin, ang, tq, aa, ff = R(L.PL_QUAT), R(L.PL_POS), R(L.PL_LINVEL), R(L.PL_ANGVEL), R(L.PL_TORQUE), R(L.PL_ANGACC), R(L.PL_FIFO)
+        d2, d1, kp, kd, et, n0, n1 = R(L.PL_DRAG2), R(L.PL_DRAG1), R(L.PL_KP), R(L.PL_KD), R(L.PL_ETAU), R(L.PL_NOISE0), R(L.PL_NOISE1)
+        pk = ang[:, 3].contiguous().view(torch.int32)
         return {
-            "root_quat_w": P[L.PL_QUAT, :N], "root_pos_w": P[L.PL_POS, :N, :3], "gross_thrust": P[L.PL_POS, :N, 3],
-            "root_lin_vel_w": P[L.PL_LINVEL, :N, :3], "episode_length": P[L.PL_LINVEL, :N, 3].view(torch.int32),
-            "root_ang_vel_w": P[L.PL_ANGVEL, :N, :3], "torque": P[L.PL_TORQUE, :N, :3], "ang_acc_w": P[L.PL_ANGACC, :N, :3],
-            "action_fifo": P[L.PL_FIFO, :N], "drag_coeffs": P[L.PL_DRAG2, :N, :3], "mass": P[L.PL_DRAG2, :N, 3],
-            "h_force_drag_coeffs": P[L.PL_DRAG1, :N, :3], "exp_thrust_delay": P[L.PL_DRAG1, :N, 3],
-            "rate_gain_p": P[L.PL_KP, :N, :3], "thr_est_error": P[L.PL_KP, :N, 3], "rate_gain_d": P[L.PL_KD, :N, :3],
-            "exp_torque_delay": P[L.PL_ETAU, :N, :3],
-            "gate_noise": torch.cat([P[L.PL_NOISE0, :N, :3], P[L.PL_NOISE0, :N, 3:], P[L.PL_NOISE1, :N, :2]], dim=-1),
-            "noise_pos_hi": P[L.PL_NOISE1, :N, 2], "noise_level": P[L.PL_NOISE1, :N, 3],
+            "root_quat_w": q, "root_pos_w": pos[:, :3], "gross_thrust": pos[:, 3],
+            "root_lin_vel_w": lin[:, :3], "episode_length": lin[:, 3].contiguous().view(torch.int32),
+            "root_ang_vel_b": ang[:, :3], "torque": tq[:, :3], "ang_acc_b": aa[:, :3],
+            "action_fifo_tanh": ff, "drag_coeffs": d2[:, :3], "mass": d2[:, 3],
+            "h_force_drag_coeffs": d1[:, :3], "exp_thrust_delay": d1[:, 3],
+            "rate_gain_p": kp[:, :3], "thr_est_error": kp[:, 3], "rate_gain_d": kd[:, :3],
+            "exp_torque_delay": et[:, :3],
+            "gate_noise": torch.cat([n0[:, :3], n0[:, 3:], n1[:, :2]], dim=-1),
+            "noise_pos_hi": n1[:, 2], "noise_level": n1[:, 3],
+            "episode_sums": torch.cat([R(L.PL_EPSUM0), R(L.PL_EPSUM1)[:, :2]], dim=-1),
             "gate_id": (pk >> L.PK_GATE_SHIFT) & 0xFF, "accumulate_gates": (pk >> L.PK_ACC_SHIFT) & 0xFFF,
             "terrain_levels": (pk >> L.PK_LEVEL_SHIFT) & 0x3F, "terrain_types": (pk >> L.PK_TYPE_SHIFT) & 0x1F,
             "fresh": (pk >> L.PK_FRESH_SHIFT) & 0x1,

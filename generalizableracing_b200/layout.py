@@ -21,11 +21,14 @@ RND_Z_DRAG = 20        # 1 U                                   (QD/mdp/dynamics/
 RND_DRAG2 = 21         # 3 U : quadratic drag                  (droneDynamics.py:54)
 RND_DRAG1 = 24         # 3 U : linear drag                     (droneDynamics.py:56)
 RND_LEVEL = 27         # 1 U : terrain level re-draw when the curriculum tops out
-RND_RESET_GATE = 28    # 6 U : noise of the current gate on resample (QD/mdp/commands.py:286-295)
-RND_RESET_NEXT = 34    # 6 U : noise of the next gate on resample    (commands.py:297-306)
-# --- consumed only by envs that passed a gate this step ------------------------------
-RND_PASS_GATE = 40     # 6 U                                   (commands.py:330-339)
-RND_PASS_NEXT = 46     # 6 U                                   (commands.py:341-350)
+# gate noise on resample (QD/mdp/commands.py:286-306): 6 U for the current gate + 6 U for the next gate, ordered
+# (x y z roll pitch yaw).  Only the positional components are live, so they sit first: the in-kernel
+# Philox path never generates the calls that hold only dead draws.
+RND_RESET_GATE = (28, 29, 30, 34, 35, 36)
+RND_RESET_NEXT = (31, 32, 33, 37, 38, 39)
+# --- consumed only by envs that passed a gate this step (commands.py:330-350), same ordering ----
+RND_PASS_GATE = (40, 41, 42, 46, 47, 48)
+RND_PASS_NEXT = (43, 44, 45, 49, 50, 51)
 RND_STRIDE = 52        # floats per env per step (13 Philox calls)
 
 # --- startup slots (one draw per env at construction) ---------------------------------
@@ -48,30 +51,32 @@ NUM_REWARD_TERMS = 6   # progress, bodyrate, action_rate, perception, success_cr
 REWARD_TERM_NAMES = ("progress_rewards", "command_bodyrate_penalty", "action_rate",
                      "perception_reward", "success_cross", "bad_pose_penalty")
 
-# --- SoA state planes: each plane is a [N] array of float4 (16 B per env) -----------------
-# hot planes (read + written every step)
+# --- env state: array of 32-env tiles, each tile = 16 planes x 32 lanes x float4 (8 KB contiguous) ------------
+# torch view: planes[num_tiles, TILE_PLANES, TILE, 4]; plane p of env i lives at planes[i // 32, p, i % 32].
+# A warp owns one tile, so its loads are one contiguous 8 KB block (see gr_common.cuh for why).
+TILE = 32
+TILE_PLANES = 16
+# planes written every step first (one contiguous write-back per tile) ...
 PL_QUAT = 0      # q.w q.x q.y q.z
 PL_POS = 1       # world pos x y z | thrust filter state f
 PL_LINVEL = 2    # v_w x y z       | episode_length (int32 bits)
 PL_ANGVEL = 3    # omega_w x y z   | packed ints: gate_id | acc_gates<<8 | level<<20 | type<<26 | fresh<<31
-PL_TORQUE = 4    # torque filter state x y z | spare
+PL_TORQUE = 4    # torque filter state x y z | last cross_obs value
 PL_ANGACC = 5    # alpha_w x y z   | spare
 PL_FIFO = 6      # action-lag FIFO (a_{t-1})
 NUM_HOT_PLANES = 7
-# cold planes (read every step, written on reset / startup)
-PL_DRAG2 = 7     # quadratic drag x y z(*z_drag) | mass
-PL_DRAG1 = 8     # linear drag x y z(*z_drag)    | exp(-dt/thrust_delay)
-PL_KP = 9        # rate_gain_p x y z | thr_est_error
-PL_KD = 10       # rate_gain_d x y z | spare
-PL_ETAU = 11     # exp(-dt/torque_delay) x y z | spare
-# command-noise planes (only touched when add_cmd_noise)
-PL_NOISE0 = 12   # delta_cur x y z | delta_next x
-PL_NOISE1 = 13   # delta_next y z | noise_pos_hi | noise_level
-NUM_PLANES = 14
-# optional episode-sum planes (reward logging, extras["log"])
-PL_EPSUM0 = 14   # episode sums of reward terms 0..3
-PL_EPSUM1 = 15   # episode sums of reward terms 4..5 | spare | spare
-NUM_PLANES_WITH_STATS = 16
+PL_EPSUM0 = 7    # episode sums of reward terms 0..3          (touched only with episode_stats)
+PL_EPSUM1 = 8    # episode sums of reward terms 4..5 | spare | spare
+# ... then planes read every step and written on reset / startup
+PL_DRAG2 = 9     # quadratic drag x y z(*z_drag) | mass
+PL_DRAG1 = 10    # linear drag x y z(*z_drag)    | exp(-dt/thrust_delay)
+PL_KP = 11       # rate_gain_p x y z | thr_est_error
+PL_KD = 12       # rate_gain_d x y z | spare
+PL_ETAU = 13     # exp(-dt/torque_delay) x y z | spare
+PL_NOISE0 = 14   # delta_cur x y z | delta_next x            (touched only with add_cmd_noise)
+PL_NOISE1 = 15   # delta_next y z | noise_pos_hi | noise_level
+NUM_PLANES = 14             # GrState.num_planes value meaning "no episode sums"
+NUM_PLANES_WITH_STATS = 16  # GrState.num_planes value meaning "episode sums maintained"
 
 # packed-int field positions in PL_ANGVEL.w
 PK_GATE_BITS, PK_GATE_SHIFT = 8, 0

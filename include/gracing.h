@@ -37,6 +37,7 @@ extern "C" {
 #define GR_NUM_PLANES 14
 #define GR_NUM_PLANES_WITH_STATS 16
 #define GR_TAPE_PLANES 7
+#define GR_TILE_PLANES 16
 #define GR_MAX_GATES 32
 
 typedef enum GrStatus {
@@ -99,18 +100,24 @@ typedef struct GrTrack {
   int32_t types, levels, gates;
 } GrTrack;
 
-/* SoA env state: `planes` is [num_planes][plane_stride] float4; plane ids GR_PL_*. */
+/* Env state: array of 32-env tiles; a tile is GR_TILE_PLANES planes x 32 lanes x float4 (8 KB contiguous), i.e.
+ * plane p of env i is the float4 at planes[((i/32)*GR_TILE_PLANES + p)*32 + i%32].  One warp owns one tile, so its
+ * loads are a single contiguous block and warps finish loading one after the other (plane ids: layout.py). */
 typedef struct GrState {
   float* planes;            /* 16-byte aligned */
-  int64_t plane_stride;     /* in float4 elements, >= num_envs */
+  int64_t plane_stride;     /* env capacity of the buffer = 32 * number of tiles, >= num_envs rounded up to 32 */
   int32_t num_envs;
-  int32_t num_planes;       /* GR_NUM_PLANES or GR_NUM_PLANES_WITH_STATS */
+  int32_t num_planes;       /* GR_NUM_PLANES (episode sums off) or GR_NUM_PLANES_WITH_STATS (on); tiles always hold 16 */
   int32_t env_id_offset;    /* global id of env 0 of this shard (Philox key; multi-GPU) */
   int32_t max_types_per_block; /* host-computed bound of distinct terrain types inside one 256-env span */
   int32_t block_threads;    /* threads per block of the env kernels: 0 => default (64); multiple of 32, <= 256 */
+  int32_t launch_flags;     /* GR_LAUNCH_* */
   const int32_t* chunk_types;  /* [ceil(N/64)][2] (lowest, highest) terrain type of each 64-env chunk;
                                   written by gr_env_startup, read by every kernel that stages the track */
 } GrState;
+
+#define GR_LAUNCH_PDL 1   /* gr_step_fwd: programmatic dependent launch -- the kernel's prologue (Philox, gate-table staging)
+                            overlaps the tail of the previous kernel in the stream; it waits before touching any buffer */
 
 /* Random source: dense tensor (parity mode) or in-kernel Philox4x32-10 (throughput mode). */
 typedef struct GrRandom {
@@ -140,8 +147,9 @@ typedef struct GrStepIO {
   uint8_t* gate_passed;     /* [N] gate switched in this step (diagnostic)           optional */
   float* loss;              /* [N] BPTT loss (extras["losses"])                      optional */
   float* loss_terms;        /* [N,3] weighted loss terms                             optional */
-  float* tape;              /* [GR_TAPE_PLANES][tape_stride] float4 of THIS step     optional (BPTT) */
-  int64_t tape_stride;      /* in float4 elements */
+  float* tape;              /* [tiles][GR_TAPE_PLANES][32] float4 of THIS step       optional (BPTT) */
+  int64_t tape_stride;      /* env capacity of one tape step = 32 * tiles */
+  uint64_t* phase_times;    /* [num_warps][5] %globaltimer stamps; only written by a -DGR_PHASE_TIMING build (tools/)  optional */
   float* log_accum;         /* [GR_LOG_SHARDS][GR_LOG_SLOTS] float atomics (sum the shards), see GR_LOG_*  optional */
 } GrStepIO;
 
@@ -151,7 +159,7 @@ typedef struct GrStepIO {
 #define GR_LOG_NUM_TIMEOUT 8
 #define GR_LOG_NUM_TERMINATED 9
 #define GR_LOG_SLOTS 16
-#define GR_LOG_SHARDS 32           /* accumulator rows, one 64-byte row per (block index mod 32) */
+#define GR_LOG_SHARDS 256          /* accumulator rows (64 B each), picked by warp id: spreads the RED traffic over L2 */
 
 int gr_abi_version(void);
 
@@ -178,7 +186,7 @@ int gr_step_fwd(const GrConfig* cfg, const GrTrack* track, const GrState* st, co
  * DroneDynamics.step/align + CTBRController.compute + the tanh action map; replaces
  * torch.autograd through QD/mdp/dynamics/droneDynamics.py:119-181, L/controllers/
  * controller_diff.py:120-138, QD/mdp/diff_action.py:160-176 as driven by S/diff_rl/algorithms/bptt.py:38-44).
- *   tape        [T][GR_TAPE_PLANES][tape_stride] float4 written by gr_step_fwd
+ *   tape        [T][tiles][GR_TAPE_PLANES][32] float4 written by gr_step_fwd (tape_stride = 32*tiles)
  *   grad_loss   [T][N] upstream gradient of extras["losses"], or NULL => uniform `grad_scale`
  *   adjoint     [5][adj_stride] float4: carried adjoints (zero at the end of the window); in/out
  *   grad_action [T][N][4]: row t-1 receives dL/da_{t-1} produced by step t (1-step action lag);

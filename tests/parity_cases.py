@@ -55,7 +55,9 @@ def oracle_state(orc):
 
 def kernel_state(env):
     sv = env.state_dict_view()
-    return dict(pos=sv["root_pos_w"], quat=sv["root_quat_w"], lin=sv["root_lin_vel_w"], ang=sv["root_ang_vel_w"],
+    from oracle import isaac_math as M
+    ang_w = M.quat_rotate(sv["root_quat_w"].cpu(), sv["root_ang_vel_b"].cpu())     # the kernels keep the body-frame rate
+    return dict(pos=sv["root_pos_w"], quat=sv["root_quat_w"], lin=sv["root_lin_vel_w"], ang=ang_w,
                 f=sv["gross_thrust"], tau=sv["torque"], gate=sv["gate_id"], acc=sv["accumulate_gates"],
                 level=sv["terrain_levels"], eplen=sv["episode_length"], thr=sv["thr_est_error"],
                 k2=sv["drag_coeffs"], k1=sv["h_force_drag_coeffs"])
@@ -87,7 +89,7 @@ def teleport_near_gate(orc, env, g, frac=0.5, radius=0.5):
     orc.root_pos_w = pos.clone()
     orc._get_state_from_sim()
     orc.dyn.reset_state(orc.states_all, torch.arange(N))
-    env.planes[L_.PL_POS, :N, :3] = pos.to(env.device)
+    env.write_plane(L_.PL_POS, slice(0, 3), pos)
     return sel
 
 

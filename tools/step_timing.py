@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--stage", type=int, default=1)
     ap.add_argument("--blocks", default="32,64,128,256")
     ap.add_argument("--no-stats", action="store_true")
+    ap.add_argument("--pdl", type=int, default=1)
+    ap.add_argument("--hover", type=int, default=0, help="1: near-hover actions (time-out resets only, ~0.5%/step)")
     args = ap.parse_args()
     BLD.build()
     lib = B.load()
@@ -44,8 +46,10 @@ def main():
     flush = torch.empty(int(512e6) // 4, device=dev)
     res = []
     for blk in [int(b) for b in args.blocks.split(",")]:
-        envs = [RacingVecEnv(cfg, table, N, device=dev, seed=1 + r, episode_stats=not args.no_stats, block_threads=blk) for r in range(args.sets)]
+        envs = [RacingVecEnv(cfg, table, N, device=dev, seed=1 + r, episode_stats=not args.no_stats, block_threads=blk, pdl=bool(args.pdl)) for r in range(args.sets)]
         acts = [torch.randn(N, 4, device=dev) * 0.5 for _ in envs]
+        if args.hover:
+            acts = [torch.randn(N, 4, device=dev) * 0.1 + torch.tensor([-0.3466, 0.0, 0.0, 0.0], device=dev) for _ in envs]
         for e in envs:
             e.reset()
             e.episode_length_buf = torch.randint(0, cfg.max_episode_length, (N,), device=dev, dtype=torch.int32)
@@ -120,7 +124,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         eager = e0.elapsed_time(e1) * 1e3 / (10 * len(envs))
-        r = {"block": blk, "cold_single_us_median": cold[len(cold) // 2], "cold_single_us_min": cold[0], "graph_rot_us": out, "l2_resident_us": hot, "eager_rot_us": eager}
+        r = {"hover": args.hover, "reset_rate": float(torch.stack([e._log_accum.sum(0) for e in envs]).sum(0)[0]) / (step[0] * N), "pdl": args.pdl, "block": blk, "cold_single_us_median": cold[len(cold) // 2], "cold_single_us_min": cold[0], "graph_rot_us": out, "l2_resident_us": hot, "eager_rot_us": eager}
         print(json.dumps(r), flush=True)
         res.append(r)
         del envs, ios, acts
