@@ -352,3 +352,20 @@ class RacingVecEnv:
 
 
 B_LOG_NUM_RESET, B_LOG_SUM_GATES, B_LOG_SUM_EPSUM, B_LOG_NUM_TIMEOUT, B_LOG_NUM_TERMINATED = 0, 1, 2, 8, 9
+
+
+def make_env(task: str = "DiffLab-Quadcopter-CTBR-Racing-v0", num_envs: int = 2048, device="cuda:0", stage=None, track="complex",
+             differentiable: bool = False, **kwargs) -> RacingVecEnv:
+    """``gym.make(task, cfg=env_cfg)`` + ``RslRlVecEnvWrapper`` of the reference launch scripts (standalone/rsl_rl/train.py:102-120)
+    for the one registered racing task (QD/__init__.py:48-73).  ``track``: "complex" = 20x10 curriculum table shaped like
+    RacingComplexTerrainCfg, "figure8" = RacingTestTerrainCfg.  Under torchrun the envs are sharded over the ranks."""
+    from . import dist_utils as D
+    from .tracks import figure_eight_track, synthetic_track_table
+    if task not in ("DiffLab-Quadcopter-CTBR-Racing-v0", "DiffLab-Quadcopter-CTBR-Racing-Play-v0"):
+        raise ValueError(f"unknown task {task!r}: only the CTBR racing task is built")
+    cfg = RacingCfg.from_env() if stage is None else RacingCfg.for_stage(stage)
+    if differentiable:
+        cfg.is_differentiable_physics = True
+    table = figure_eight_track() if track == "figure8" else synthetic_track_table()
+    rank, world = D.world()
+    return RacingVecEnv(cfg, table, num_envs, device=device, env_id_offset=rank * num_envs, global_num_envs=world * num_envs, **kwargs)

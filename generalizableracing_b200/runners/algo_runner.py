@@ -1,0 +1,106 @@
+"""AlgoRunner (BPTT) with the reference's surface (standalone/diff_rl/algorithms/runner.py:27-302): the horizon loop
+``env.unwrapped.detach()`` -> T x (act, step, process_env_step) -> ``alg.update()`` (:107-155)."""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import torch
+
+from .. import dist_utils as D
+from ..algorithms import BPTT
+from ..modules import BaseModel
+
+
+class AlgoRunner:
+    def __init__(self, env, agent_cfg: dict, log_dir: str = None, device="cuda:0"):
+        self.cfg = dict(agent_cfg)
+        self.alg_cfg = dict(agent_cfg["algorithm"])
+        self.policy_cfg = dict(agent_cfg["policy"])
+        self.device = device
+        self.env = env
+        obs, extras = self.env.get_observations()
+        num_obs = obs.shape[1]
+        num_critic_obs = extras["observations"]["critic"].shape[1] if "critic" in extras["observations"] else num_obs
+        if self.policy_cfg.pop("class_name", "BaseModel") != "BaseModel":
+            raise ValueError("only the state-only BaseModel is built (vision / recurrent models need the depth image)")
+        actor_critic = BaseModel(num_obs, num_critic_obs, self.env.num_actions, **self.policy_cfg).to(self.device)
+        if self.alg_cfg.pop("class_name", "BPTT") != "BPTT":
+            raise ValueError("only BPTT is built")
+        self.alg = BPTT(actor_critic=actor_critic, max_iterations=agent_cfg["max_iterations"], device=self.device, env=self.env.unwrapped, **self.alg_cfg)
+        if getattr(self.env.unwrapped, "_bptt", None) is not None:
+            self.env.unwrapped._bptt.autograd = False          # the algorithm drives the one-launch window sweep itself
+        self.num_steps_per_env = self.cfg["num_steps_per_env"]
+        self.save_interval = self.cfg.get("save_interval", 200)
+        self.log_dir = log_dir
+        self.tot_timesteps = 0
+        self.tot_time = 0
+        self.current_learning_iteration = 0
+        self.history = []
+
+    def train_mode(self):
+        self.alg.train_mode()
+
+    def learn(self, num_learning_iterations: int, init_at_random_ep_len: bool = False):
+        rank, world = D.world()
+        if init_at_random_ep_len:
+            self.env.episode_length_buf = torch.randint_like(self.env.episode_length_buf, high=int(self.env.max_episode_length))
+        obs, extras = self.env.get_observations()
+        critic_obs = extras["observations"].get("critic", obs)
+        self.train_mode()
+        N = self.env.num_envs
+        start_iter = self.current_learning_iteration
+        for it in range(start_iter, start_iter + num_learning_iterations):
+            start = time.time()
+            self.env.unwrapped.detach()                                            # runner.py:110
+            rew_sum = torch.zeros((), device=self.device)
+            for _ in range(self.num_steps_per_env):
+                actions = self.alg.act(obs, critic_obs)
+                obs, rewards, dones, extras = self.env.step(actions)
+                critic_obs = extras["observations"].get("critic", obs)
+                self.alg.process_env_step(extras["losses"], extras["losses_detached"], dones, rewards, extras)
+                rew_sum += rewards.mean()
+            stop = time.time()
+            collection_time = stop - start
+            start = stop
+            _, total_loss_mean = self.alg.update()
+            stop = time.time()
+            learn_time = stop - start
+            self.current_learning_iteration = it
+            self.tot_timesteps += self.num_steps_per_env * N * world
+            self.tot_time += collection_time + learn_time
+            stats = torch.stack([total_loss_mean.detach(), rew_sum / self.num_steps_per_env])
+            if world > 1:
+                torch.distributed.all_reduce(stats)
+                stats /= world
+            rec = {"iteration": it, "Loss/mean_total_loss": float(stats[0]), "Train/mean_step_reward": float(stats[1]),
+                   "Perf/total_fps": int(self.num_steps_per_env * N * world / (collection_time + learn_time)),
+                   "Perf/collection time": collection_time, "Perf/learning_time": learn_time,
+                   "Loss/learning_rate": self.alg.optimizer.param_groups[0]["lr"]}
+            self.history.append(rec)
+            if rank == 0 and self.log_dir is not None:
+                os.makedirs(self.log_dir, exist_ok=True)
+                with open(os.path.join(self.log_dir, "progress.jsonl"), "a") as f:
+                    f.write(json.dumps(rec) + "\n")
+                if it % self.save_interval == 0:
+                    self.save(os.path.join(self.log_dir, f"model_{it}.pt"))
+        return self.history
+
+    def save(self, path, infos=None):
+        torch.save({"model_state_dict": self.alg.actor_critic.state_dict(), "optimizer_state_dict": self.alg.optimizer.state_dict(),
+                    "iter": self.current_learning_iteration, "infos": infos}, path)
+
+    def load(self, path, load_optimizer=True):
+        loaded = torch.load(path, map_location=self.device, weights_only=False)
+        self.alg.actor_critic.load_state_dict(loaded["model_state_dict"])
+        if load_optimizer:
+            self.alg.optimizer.load_state_dict(loaded["optimizer_state_dict"])
+        self.current_learning_iteration = loaded["iter"]
+        return loaded["infos"]
+
+    def get_inference_policy(self, device=None):
+        self.alg.test_mode()
+        if device is not None:
+            self.alg.actor_critic.to(device)
+        return self.alg.actor_critic.act_inference

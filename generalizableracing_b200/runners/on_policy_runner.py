@@ -1,0 +1,145 @@
+"""OnPolicyRunner with the reference's surface (standalone/rsl_rl/ext/runners/on_policy_runner.py:20-374):
+``OnPolicyRunner(env, train_cfg, log_dir, device)``, ``learn(num_learning_iterations, init_at_random_ep_len)``,
+``save/load/get_inference_policy``, ``train_mode/eval_mode``.  The rollout loop is the reference's (:135-183); the
+bookkeeping that forced a host sync every step (``nonzero()`` / ``.cpu()`` at :169-173) stays on the device.
+Logging is a JSON-lines file instead of TensorBoard (not installed here); the scalars are the reference's.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+from collections import deque
+
+import torch
+
+from .. import dist_utils as D
+from ..algorithms import PPO
+from ..modules import ActorCritic
+
+
+class OnPolicyRunner:
+    def __init__(self, env, train_cfg: dict, log_dir=None, device="cuda:0"):
+        self.cfg = dict(train_cfg)
+        self.alg_cfg = dict(train_cfg["algorithm"])
+        self.policy_cfg = dict(train_cfg["policy"])
+        self.device = device
+        self.env = env
+        if self.alg_cfg.get("class_name", "PPO") != "PPO":
+            raise ValueError("only PPO is built (PPOLCP / PPOL2C2 / Distillation are vision / BC variants, out of scope)")
+        self.training_type = "rl"
+        obs, extras = self.env.get_observations()
+        num_obs = obs.shape[1]
+        self.privileged_obs_type = "critic" if "critic" in extras["observations"] else None
+        num_privileged_obs = extras["observations"]["critic"].shape[1] if self.privileged_obs_type else num_obs
+        self.policy_cfg.pop("class_name", None)
+        policy = ActorCritic(num_obs, num_privileged_obs, self.env.num_actions, **self.policy_cfg).to(self.device)
+        self.alg_cfg.pop("class_name", None)
+        self.alg = PPO(policy, env=self.env, device=self.device, **self.alg_cfg)
+        self.num_steps_per_env = self.cfg["num_steps_per_env"]
+        self.save_interval = self.cfg.get("save_interval", 50)
+        if self.cfg.get("empirical_normalization", False):
+            raise NotImplementedError("empirical_normalization=False in the racing cfg (QD/agents/rsl_rl_ppo_cfg.py:21)")
+        self.obs_normalizer = torch.nn.Identity()
+        self.privileged_obs_normalizer = torch.nn.Identity()
+        self.alg.init_storage(self.training_type, self.env.num_envs, self.num_steps_per_env, [num_obs], [num_privileged_obs], [self.env.num_actions])
+        self.log_dir = log_dir
+        self.tot_timesteps = 0
+        self.tot_time = 0
+        self.current_learning_iteration = 0
+        self.history = []
+
+    def train_mode(self):
+        self.alg.policy.train()
+
+    def eval_mode(self):
+        self.alg.policy.eval()
+
+    def learn(self, num_learning_iterations: int, init_at_random_ep_len: bool = False):
+        rank, world = D.world()
+        if init_at_random_ep_len:
+            self.env.episode_length_buf = torch.randint_like(self.env.episode_length_buf, high=int(self.env.max_episode_length))
+        obs, extras = self.env.get_observations()
+        privileged_obs = extras["observations"].get(self.privileged_obs_type, obs)
+        self.train_mode()
+        N = self.env.num_envs
+        cur_reward_sum = torch.zeros(N, dtype=torch.float, device=self.device)
+        cur_episode_length = torch.zeros(N, dtype=torch.float, device=self.device)
+        ep_rew_sum = torch.zeros((), device=self.device)
+        ep_len_sum = torch.zeros((), device=self.device)
+        ep_count = torch.zeros((), device=self.device)
+        start_iter = self.current_learning_iteration
+        tot_iter = start_iter + num_learning_iterations
+        for it in range(start_iter, tot_iter):
+            start = time.time()
+            ep_infos = []
+            with torch.inference_mode():
+                for _ in range(self.num_steps_per_env):
+                    actions = self.alg.act(obs, privileged_obs)
+                    obs, rewards, dones, infos = self.env.step(actions)
+                    privileged_obs = infos["observations"][self.privileged_obs_type] if self.privileged_obs_type else obs
+                    self.alg.process_env_step(rewards, dones, infos)
+                    # episode book keeping (on_policy_runner.py:167-173) without host synchronisation
+                    cur_reward_sum += rewards
+                    cur_episode_length += 1
+                    d = dones > 0
+                    ep_rew_sum += (cur_reward_sum * d).sum()
+                    ep_len_sum += (cur_episode_length * d).sum()
+                    ep_count += d.sum()
+                    cur_reward_sum.masked_fill_(d, 0.0)
+                    cur_episode_length.masked_fill_(d, 0.0)
+                if self.log_dir is not None and "log" in infos:
+                    ep_infos.append(infos["log"])
+                stop = time.time()
+                collection_time = stop - start
+                start = stop
+                self.alg.compute_returns(privileged_obs)
+            loss_dict = self.alg.update()
+            stop = time.time()
+            learn_time = stop - start
+            self.current_learning_iteration = it
+            self.tot_timesteps += self.num_steps_per_env * N * world
+            self.tot_time += collection_time + learn_time
+            stats = torch.stack([ep_rew_sum, ep_len_sum, ep_count])
+            if world > 1:
+                torch.distributed.all_reduce(stats)
+            n_ep = max(float(stats[2]), 1.0)
+            rec = {"iteration": it, "Loss/value_function": loss_dict["value_function"], "Loss/surrogate": loss_dict["surrogate"],
+                   "Loss/learning_rate": self.alg.learning_rate, "Policy/mean_noise_std": float(self.alg.policy.action_std.mean()) if self.alg.policy.distribution is not None else None,
+                   "Perf/total_fps": int(self.num_steps_per_env * N * world / (collection_time + learn_time)),
+                   "Perf/collection time": collection_time, "Perf/learning_time": learn_time,
+                   "Train/mean_reward": float(stats[0]) / n_ep, "Train/mean_episode_length": float(stats[1]) / n_ep, "Train/episodes": int(stats[2]),
+                   "tot_timesteps": self.tot_timesteps}
+            for info in ep_infos:
+                for k, v in info.items():
+                    rec[k] = float(v)
+            ep_rew_sum.zero_(); ep_len_sum.zero_(); ep_count.zero_()
+            self.history.append(rec)
+            if rank == 0 and self.log_dir is not None:
+                os.makedirs(self.log_dir, exist_ok=True)
+                with open(os.path.join(self.log_dir, "progress.jsonl"), "a") as f:
+                    f.write(json.dumps(rec) + "\n")
+                if it % self.save_interval == 0:
+                    self.save(os.path.join(self.log_dir, f"model_{it}.pt"))
+        if rank == 0 and self.log_dir is not None:
+            self.save(os.path.join(self.log_dir, f"model_{self.current_learning_iteration}.pt"))
+        return self.history
+
+    def save(self, path, infos=None):
+        # on_policy_runner.py:288-302 (env state is never checkpointed by the reference either)
+        torch.save({"model_state_dict": self.alg.policy.state_dict(), "optimizer_state_dict": self.alg.optimizer.state_dict(),
+                    "iter": self.current_learning_iteration, "infos": infos}, path)
+
+    def load(self, path, load_optimizer=True):
+        loaded = torch.load(path, map_location=self.device, weights_only=False)
+        self.alg.policy.load_state_dict(loaded["model_state_dict"])
+        if load_optimizer:
+            self.alg.optimizer.load_state_dict(loaded["optimizer_state_dict"])
+        self.current_learning_iteration = loaded["iter"]
+        return loaded["infos"]
+
+    def get_inference_policy(self, device=None):
+        self.eval_mode()
+        if device is not None:
+            self.alg.policy.to(device)
+        return self.alg.policy.act_inference
