@@ -76,6 +76,7 @@ class GrMiniBatch(C.Structure):
 
 
 GR_LAUNCH_PDL = 1
+GR_LAUNCH_PREFETCH = 2
 GR_LOG_SLOTS = 16
 GR_LOG_SHARDS = 256
 STATUS = {0: "GR_OK", -1: "GR_ERR_NULL", -2: "GR_ERR_SIZE", -3: "GR_ERR_ALIGN", -4: "GR_ERR_CONFIG", -5: "GR_ERR_SMEM"}

@@ -61,6 +61,8 @@ class BpttWindow:
         self.grad_loss = torch.zeros(capacity, N, device=dev)
         self.grad_action = torch.zeros(capacity, N, L.NUM_ACTIONS, device=dev)
         self.capacity = capacity
+        self._p_loss, self._p_terms, self._p_tape = self.loss.data_ptr(), self.loss_terms.data_ptr(), self.tape.data_ptr()
+        self._tape_step_bytes = self.tape[0].numel() * 4
 
     # -- called by the env ------------------------------------------------------------------
     def start_window(self):
@@ -74,9 +76,10 @@ class BpttWindow:
         if self.t >= self.capacity:
             raise RuntimeError(f"BPTT horizon exceeded the tape capacity ({self.capacity} steps): call env.unwrapped.detach() "
                                "between windows or construct the env with a larger bptt_horizon")
-        io.loss = self.loss[self.t].data_ptr()
-        io.loss_terms = self.loss_terms[self.t].data_ptr()
-        io.tape = self.tape[self.t].data_ptr()
+        t, n = self.t, self.env.num_envs
+        io.loss = self._p_loss + t * n * 4
+        io.loss_terms = self._p_terms + t * n * 12
+        io.tape = self._p_tape + t * self._tape_step_bytes
         io.tape_stride = self.env._stride
 
     def after_step(self, actions: torch.Tensor, extras: dict):

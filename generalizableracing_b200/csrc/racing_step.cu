@@ -15,26 +15,43 @@ struct EnvRegs {
   V3 k2; float m; V3 k1; float ef; V3 kp; float thr; V3 kd; V3 etau;
   V3 dcur, dnext; float noise_hi, noise_level;
   float aux;      // last cross_obs value (RewardManager._step_reward survives resets)
+  bool noise_dirty_prev;   // PL_ANGACC.w: the noise planes were rewritten by the previous step (gate switch / reset)
 };
 
 // EnvRegs.om / .aacc hold the BODY-frame angular velocity / acceleration (PL_ANGVEL / PL_ANGACC): the reference
 // round-trips them through the world frame every step (rot(q', w_b') stored, rotinv(q', .) read back: identity up to
 // rounding); only w_b is ever consumed.  EnvRegs.fifo holds tanh(a_{t-1}): the lagged action is only used through tanh.
-template <bool kNoise>
-__device__ __forceinline__ void load_env(EnvRegs& e, const float4* __restrict__ tile) {
+__device__ __forceinline__ void load_hot(EnvRegs& e, const float4* __restrict__ tile) {
   const float4 a0 = ld_plane(tile, PL_QUAT), a1 = ld_plane(tile, PL_POS), a2 = ld_plane(tile, PL_LINVEL), a3 = ld_plane(tile, PL_ANGVEL),
                a4 = ld_plane(tile, PL_TORQUE), a5 = ld_plane(tile, PL_ANGACC), a6 = ld_plane(tile, PL_FIFO);
-  const float4 c0 = ld_plane_ro(tile, PL_DRAG2), c1 = ld_plane_ro(tile, PL_DRAG1), c2 = ld_plane_ro(tile, PL_KP), c3 = ld_plane_ro(tile, PL_KD),
-               c4 = ld_plane_ro(tile, PL_ETAU);
   e.q = quat(a0); e.w = xyz(a1); e.f = a1.w; e.v = xyz(a2); e.eplen = __float_as_int(a2.w);
-  e.om = xyz(a3); e.pk = __float_as_uint(a3.w); e.tau = xyz(a4); e.aux = a4.w; e.aacc = xyz(a5); e.fifo = a6;
+  e.om = xyz(a3); e.pk = __float_as_uint(a3.w); e.tau = xyz(a4); e.aux = a4.w; e.aacc = xyz(a5); e.noise_dirty_prev = a5.w != 0.0f; e.fifo = a6;
+}
+// kVolatile: re-read through L2 (ld.global.cv) after the grid dependency when the prefetched copy may be stale
+template <bool kVolatile>
+__device__ __forceinline__ float4 ld_cold(const float4* __restrict__ tile, int plane) {
+  return kVolatile ? __ldcv(tile + plane * kTile) : __ldg(tile + plane * kTile);
+}
+template <bool kVolatile>
+__device__ __forceinline__ void load_cold(EnvRegs& e, const float4* __restrict__ tile) {
+  const float4 c0 = ld_cold<kVolatile>(tile, PL_DRAG2), c1 = ld_cold<kVolatile>(tile, PL_DRAG1), c2 = ld_cold<kVolatile>(tile, PL_KP),
+               c3 = ld_cold<kVolatile>(tile, PL_KD), c4 = ld_cold<kVolatile>(tile, PL_ETAU);
   e.k2 = xyz(c0); e.m = c0.w; e.k1 = xyz(c1); e.ef = c1.w; e.kp = xyz(c2); e.thr = c2.w; e.kd = xyz(c3); e.etau = xyz(c4);
+}
+template <bool kNoise, bool kVolatile>
+__device__ __forceinline__ void load_noise(EnvRegs& e, const float4* __restrict__ tile) {
   if (kNoise) {
-    const float4 n0 = ld_plane_ro(tile, PL_NOISE0), n1 = ld_plane_ro(tile, PL_NOISE1);
+    const float4 n0 = ld_cold<kVolatile>(tile, PL_NOISE0), n1 = ld_cold<kVolatile>(tile, PL_NOISE1);
     e.dcur = xyz(n0); e.dnext = v3(n0.w, n1.x, n1.y); e.noise_hi = n1.z; e.noise_level = n1.w;
   } else {
     e.dcur = v3(0.f, 0.f, 0.f); e.dnext = v3(0.f, 0.f, 0.f); e.noise_hi = 0.f; e.noise_level = 1.f;
   }
+}
+template <bool kNoise>
+__device__ __forceinline__ void load_env(EnvRegs& e, const float4* __restrict__ tile) {
+  load_hot(e, tile);
+  load_cold<false>(e, tile);
+  load_noise<kNoise, false>(e, tile);
 }
 
 __device__ __forceinline__ float4 tanh4(float4 a) { return make_float4(tanhf(a.x), tanhf(a.y), tanhf(a.z), tanhf(a.w)); }
@@ -152,12 +169,13 @@ __device__ __forceinline__ V3 reset_env(const GrConfig& cfg, const TrackSmem& tr
 
 template <bool kNoise>
 __device__ __forceinline__ void store_env(const EnvRegs& e, float4* __restrict__ tile, bool cold_dirty, bool noise_dirty) {
+  // ANGACC.w = "noise planes rewritten in this step": lets the next step trust its pre-dependency prefetch of them
   st_plane(tile, PL_QUAT, pack(e.q));
   st_plane(tile, PL_POS, pack(e.w, e.f));
   st_plane(tile, PL_LINVEL, pack(e.v, __int_as_float(e.eplen)));
   st_plane(tile, PL_ANGVEL, pack(e.om, __uint_as_float(e.pk)));
   st_plane(tile, PL_TORQUE, pack(e.tau, e.aux));
-  st_plane(tile, PL_ANGACC, pack(e.aacc, 0.f));
+  st_plane(tile, PL_ANGACC, pack(e.aacc, (kNoise && noise_dirty) ? 1.0f : 0.0f));
   st_plane(tile, PL_FIFO, e.fifo);
   if (cold_dirty) {
     tile[PL_DRAG2 * kTile] = pack(e.k2, e.m);
@@ -213,14 +231,28 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
   const RandSrc<kPhilox> rs(rng, li, st.env_id_offset + li);
   float4 n01, n23;                                     // obs normals (slots 0..5), thr_est_error normal (slot 6)
   if (kPhilox || !pdl) rs.normals8(n01, n23);
+  // PDL: the read-mostly planes (drag, gains, filter constants, command noise: 112 of the 272 B an env reads) are
+  // fetched BEFORE the grid dependency and overlap the previous kernel's tail.  They are rewritten only by the reset /
+  // gate-switch tail of a step kernel, which flags it in the hot planes (fresh bit, ANGACC.w): a flagged env re-reads
+  // them through L2 after the wait.  (Host-side edits of those planes must clear GR_LAUNCH_PREFETCH for the next step.)
+  const bool prefetch = pdl && (st.launch_flags & GR_LAUNCH_PREFETCH) != 0;
+  if (prefetch) { load_cold<false>(e, tile); load_noise<kNoise, false>(e, tile); }
   const TrackSmem tr = stage_track(track, reinterpret_cast<const int2*>(st.chunk_types), st.num_envs, smem_rows);
   if (pdl) {
     pdl_wait();
     GR_STAMP(1);
-    load_env<kNoise>(e, tile);
+    load_hot(e, tile);
     a_t = __ldcs(reinterpret_cast<const float4*>(io.action) + li);
     if (kStats) { eps0 = ld_plane(tile, PL_EPSUM0); eps1 = ld_plane(tile, PL_EPSUM1); }
     if (!kPhilox) rs.normals8(n01, n23);
+    if (prefetch) {
+      const bool stale = pk_fresh(e.pk) != 0u;
+      if (stale) load_cold<true>(e, tile);
+      if (kNoise && (stale || e.noise_dirty_prev)) load_noise<kNoise, true>(e, tile);
+    } else {
+      load_cold<false>(e, tile);
+      load_noise<kNoise, false>(e, tile);
+    }
   }
   // (measured: generating the rare-path draws speculatively for every env while the loads are in flight costs more
   //  than it saves -- +1.2 us median compute, stragglers unchanged -- so the reset / pass tails draw on demand)
@@ -583,7 +615,7 @@ __global__ void racing_startup_kernel(const GrConfig cfg, const GrTrack track, c
   P[pidx(PL_QUAT, i)] = make_float4(1.f, 0.f, 0.f, 0.f);
   P[pidx(PL_POS, i)] = make_float4(zero, zero, zero, zero);
   P[pidx(PL_LINVEL, i)] = make_float4(zero, zero, zero, __int_as_float(0));
-  P[pidx(PL_ANGVEL, i)] = make_float4(zero, zero, zero, __uint_as_float(pk_make(0u, 0u, (uint32_t)level, (uint32_t)type, 0u)));
+  P[pidx(PL_ANGVEL, i)] = make_float4(zero, zero, zero, __uint_as_float(pk_make(0u, 0u, (uint32_t)level, (uint32_t)type, 1u)));
   P[pidx(PL_TORQUE, i)] = make_float4(zero, zero, zero, zero);
   P[pidx(PL_ANGACC, i)] = make_float4(zero, zero, zero, zero);
   P[pidx(PL_FIFO, i)] = make_float4(zero, zero, zero, zero);

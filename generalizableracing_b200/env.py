@@ -154,7 +154,8 @@ class RacingVecEnv:
         self._chunk_types = torch.zeros(((N + 63) // 64) * 2, dtype=torch.int32, device=dev)
         if pdl is None:
             pdl = os.environ.get("GRACING_PDL", "1") != "0"
-        flags = B.GR_LAUNCH_PDL if (pdl and self.device.type == "cuda") else 0
+        flags = (B.GR_LAUNCH_PDL | (B.GR_LAUNCH_PREFETCH if os.environ.get("GRACING_PREFETCH", "1") != "0" else 0)) if (pdl and self.device.type == "cuda") else 0
+        self._launch_flags = flags
         self._state = B.GrState(self.planes.data_ptr(), self._stride, N, self.num_planes, int(env_id_offset), max(spans),
                                 int(block_threads), flags, self._chunk_types.data_ptr())
         self._rng = B.GrRandom(None, self.seed, 0)
@@ -188,6 +189,9 @@ class RacingVecEnv:
                                          self._chunk_types.data_ptr(), srnd_ptr, self.seed, self._stream()), "gr_env_startup")
         self._last = self._outs[0]
         self._needs_reset = True
+        self._ios = None
+        self._params_edited = False
+        self._p_cfg, self._p_track, self._p_state = C.byref(self._gcfg), C.byref(self._track), C.byref(self._state)
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -228,6 +232,9 @@ class RacingVecEnv:
         if self._stride != self.num_envs:        # keep the padding lanes of the last tile untouched
             buf[self.num_envs:] = self.planes[:, pl].reshape(-1, 4)[self.num_envs:, cols].view(v.dtype) if v.dtype != torch.float32 \
                 else self.planes[:, pl].reshape(-1, 4)[self.num_envs:, cols]
+        if pl >= L.PL_DRAG2:
+            self._state.launch_flags = self._launch_flags & ~B.GR_LAUNCH_PREFETCH      # one step without the pre-dependency prefetch
+            self._params_edited = True
         if v.dtype == torch.float32:
             self.planes[:, pl, :, cols] = buf.view(self.num_tiles, L.TILE, -1)
         else:
@@ -319,33 +326,47 @@ class RacingVecEnv:
     def close(self):
         pass
 
+    def _make_io(self, o) -> B.GrStepIO:
+        io = B.GrStepIO()
+        io.obs, io.critic_obs, io.aux_obs = o["obs"].data_ptr(), o["critic"].data_ptr(), o["aux"].data_ptr()
+        io.reward, io.terminated, io.time_out, io.dones = o["reward"].data_ptr(), o["terminated"].data_ptr(), o["time_out"].data_ptr(), o["dones"].data_ptr()
+        return io
+
     def step(self, actions: torch.Tensor, rnd: Optional[torch.Tensor] = None):
         if self._needs_reset:
             self.reset()
-        o = self._outs[self._flip]
-        self._flip ^= 1
-        act = actions.detach()
+        k = self._flip
+        o = self._outs[k]
+        self._flip = k ^ 1
+        act = actions.detach() if actions.requires_grad else actions
         if act.dtype != torch.float32 or not act.is_contiguous() or act.device != self.device:
             act = act.to(self.device, torch.float32).contiguous()
         if act.shape != (self.num_envs, L.NUM_ACTIONS):
             raise ValueError(f"Invalid action shape, expected: ({self.num_envs}, {L.NUM_ACTIONS}), received: {tuple(act.shape)}.")
-        io = B.GrStepIO()
+        ios = self._ios
+        if ios is None:                       # the argument structs are built once per output set; only pointers that move are patched
+            ios = self._ios = [self._make_io(self._outs[0]), self._make_io(self._outs[1])]
+            self._views = [(x["time_out"].view(torch.bool), x["terminated"].view(torch.bool), self._obs_dict(x)) for x in self._outs]
+        io = ios[k]
         io.action = act.data_ptr()
-        io.obs, io.critic_obs, io.aux_obs = o["obs"].data_ptr(), o["critic"].data_ptr(), o["aux"].data_ptr()
-        io.reward, io.terminated, io.time_out, io.dones = o["reward"].data_ptr(), o["terminated"].data_ptr(), o["time_out"].data_ptr(), o["dones"].data_ptr()
         io.reward_terms = o["reward_terms"].data_ptr() if self.export_reward_terms else None
         io.gate_passed = o["gate_passed"].data_ptr() if self.export_gate_passed else None
         io.log_accum = self._log_accum.data_ptr()
         if self._bptt is not None:
             self._bptt.bind_step(io)
-        B.check(self._lib.gr_step_fwd(C.byref(self._gcfg), C.byref(self._track), C.byref(self._state), C.byref(self._rand(rnd)), C.byref(io),
-                                      self._stream()), "gr_step_fwd")
+        rc = self._lib.gr_step_fwd(self._p_cfg, self._p_track, self._p_state, C.byref(self._rand(rnd)), C.byref(io), self._stream())
+        if rc:
+            B.check(rc, "gr_step_fwd")
+        if self._params_edited:
+            self._state.launch_flags = self._launch_flags
+            self._params_edited = False
         self._last = o
         ex = self.extras
         dict.pop(ex, "log", None)
-        ex["observations"] = self._obs_dict(o)
-        ex["time_outs"] = o["time_out"].view(torch.bool)
-        ex["terminated"] = o["terminated"].view(torch.bool)
+        to, term, obs_dict = self._views[k]
+        ex["observations"] = obs_dict
+        ex["time_outs"] = to
+        ex["terminated"] = term
         if self._bptt is not None:
             self._bptt.after_step(actions, ex)
         return o["obs"], o["reward"], o["dones"], ex

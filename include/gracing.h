@@ -119,6 +119,9 @@ typedef struct GrState {
 #define GR_LAUNCH_PDL 1   /* gr_step_fwd: programmatic dependent launch -- the kernel's prologue (Philox, gate-table staging)
                             overlaps the tail of the previous kernel in the stream; it waits before touching any buffer */
 
+#define GR_LAUNCH_PREFETCH 2   /* with GR_LAUNCH_PDL: fetch the read-mostly planes before the grid dependency (see racing_step.cu);
+                                 clear it for the first step after the HOST rewrote planes 9..15 of the state */
+
 /* Random source: dense tensor (parity mode) or in-kernel Philox4x32-10 (throughput mode). */
 typedef struct GrRandom {
   const float* rnd;         /* [num_envs, GR_RND_STRIDE] or NULL => Philox */

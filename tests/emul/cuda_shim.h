@@ -31,6 +31,7 @@ static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 template <typename T> static inline T __ldcs(const T* p) { return *p; }
+template <typename T> static inline T __ldcv(const T* p) { return *p; }
 template <typename T> static inline void __stcs(T* p, T v) { *p = v; }
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 static inline unsigned __float_as_uint(float f) { unsigned i; std::memcpy(&i, &f, 4); return i; }
