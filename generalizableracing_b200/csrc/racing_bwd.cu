@@ -35,7 +35,28 @@ __device__ __forceinline__ QAdj rotinv_q_adj(Q4 q, V3 v, V3 yb) {
   return QAdj{wb, ub};
 }
 
-constexpr int kBwdBlock = 128;
+constexpr int kBwdBlock = 64;
+constexpr int kBwdStages = 6;
+
+__device__ __forceinline__ void cp_async16(float4* smem_dst, const float4* gmem_src) {
+#ifdef GR_CPU_EMUL
+  *smem_dst = *gmem_src;
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef GR_CPU_EMUL
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int kN>
+__device__ __forceinline__ void cp_async_wait() {
+#ifndef GR_CPU_EMUL
+  asm volatile("cp.async.wait_group %0;" ::"n"(kN) : "memory");
+#endif
+}
 
 __global__ void __launch_bounds__(kBwdBlock) racing_step_bwd_kernel(const GrConfig cfg, const GrState st, const GrBwdIO io) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -61,25 +82,37 @@ __global__ void __launch_bounds__(kBwdBlock) racing_step_bwd_kernel(const GrConf
   const int64_t TS = io.tape_stride;
   const int N = st.num_envs;
 
-  float4 nx[GR_TAPE_PLANES];
-  float ng = io.grad_scale;
-  if (io.t_end > io.t_begin) {
-    const int t = io.t_end - 1;
+  // Tape pipeline: the sweep has only N/32 warps (3.5 per SM at 16,384 envs) and a serial dependence over t, so the
+  // tape of the next kBwdStages steps is kept in flight with cp.async (LDGSTS) into a per-thread shared-memory ring;
+  // every thread reads back only what it copied itself, so commit/wait groups are the only synchronisation.
+  GR_DYN_SMEM(float4, ring);
+  float4* my = ring + threadIdx.x;                                   // slot(stage, plane) = my[(stage*7 + plane) * blockDim.x]
+  const int n_steps = io.t_end - io.t_begin;
+#pragma unroll 1
+  for (int s = 0; s < kBwdStages; ++s) {                              // prologue: steps t_end-1 .. t_end-kBwdStages
+    const int t = io.t_end - 1 - s;
+    if (s < n_steps) {
 #pragma unroll
-    for (int k = 0; k < GR_TAPE_PLANES; ++k) nx[k] = __ldcs(T + (int64_t)t * GR_TAPE_PLANES * TS + tidx(k, i));
-    if (io.grad_loss) ng = __ldg(io.grad_loss + (int64_t)t * N + i);
+      for (int k = 0; k < GR_TAPE_PLANES; ++k) cp_async16(my + (s * GR_TAPE_PLANES + k) * blockDim.x, T + (int64_t)t * GR_TAPE_PLANES * TS + tidx(k, i));
+    }
+    cp_async_commit();
   }
-
+  int stage = 0;
   for (int t = io.t_end - 1; t >= io.t_begin; --t) {
+    cp_async_wait<kBwdStages - 1>();                                  // the oldest group (step t) has landed
     float4 c[GR_TAPE_PLANES];
 #pragma unroll
-    for (int k = 0; k < GR_TAPE_PLANES; ++k) c[k] = nx[k];
-    const float g = ng;
-    if (t - 1 >= io.t_begin) {     // prefetch the next (earlier) step while this one is processed
+    for (int k = 0; k < GR_TAPE_PLANES; ++k) c[k] = my[(stage * GR_TAPE_PLANES + k) * blockDim.x];
+    const float g = io.grad_loss ? __ldg(io.grad_loss + (int64_t)t * N + i) : io.grad_scale;
+    {                                                                  // refill this stage with step t - kBwdStages
+      const int tn = t - kBwdStages;
+      if (tn >= io.t_begin) {
 #pragma unroll
-      for (int k = 0; k < GR_TAPE_PLANES; ++k) nx[k] = __ldcs(T + (int64_t)(t - 1) * GR_TAPE_PLANES * TS + tidx(k, i));
-      if (io.grad_loss) ng = __ldg(io.grad_loss + (int64_t)(t - 1) * N + i);
+        for (int k = 0; k < GR_TAPE_PLANES; ++k) cp_async16(my + (stage * GR_TAPE_PLANES + k) * blockDim.x, T + (int64_t)tn * GR_TAPE_PLANES * TS + tidx(k, i));
+      }
+      cp_async_commit();
     }
+    stage = stage + 1 == kBwdStages ? 0 : stage + 1;
     const Q4 q = quat(c[0]);
     const V3 om_b = xyz(c[1]); const float A0 = c[1].w;
     const V3 F_b = xyz(c[2]);
@@ -192,7 +225,8 @@ extern "C" int gr_step_bwd(const GrConfig* cfg, const GrState* st, const GrBwdIO
   auto mis = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; };
   if (mis(st->planes) || mis(io->tape) || mis(io->adjoint) || mis(io->grad_action)) return GR_ERR_ALIGN;
   const int grid = (st->num_envs + kBwdBlock - 1) / kBwdBlock;
-  racing_step_bwd_kernel<<<grid, kBwdBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*cfg, *st, *io);
+  const size_t smem = (size_t)kBwdStages * GR_TAPE_PLANES * kBwdBlock * sizeof(float4);      // 43 KB ring per block
+  racing_step_bwd_kernel<<<grid, kBwdBlock, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*cfg, *st, *io);
   return (int)cudaGetLastError();
 }
 #endif  // GR_CPU_EMUL
