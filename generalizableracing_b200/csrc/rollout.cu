@@ -75,33 +75,50 @@ __device__ __forceinline__ Moments block_merge(Moments m, Moments* sh) {
 }
 
 constexpr int kGaeBlock = 128;
+constexpr int kGaeChunk = 8;
 
 __global__ void __launch_bounds__(kGaeBlock) gae_kernel(const GrStorage s, const float* __restrict__ last_values, const float gamma, const float lam,
                                                         double* __restrict__ partials) {
   __shared__ Moments sh[kGaeBlock / 32];
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t N = s.N;
-  Moments mom{0.0, 0.0, 0.0};
+  double cnt = 0.0, s1 = 0.0, s2 = 0.0;
   if (n < N) {
     float next_value = last_values[n];
     float adv = 0.0f;
-    for (int t = s.T - 1; t >= 0; --t) {
-      const int64_t k = (int64_t)t * N + n;
-      const float not_term = 1.0f - (float)s.dones[k];
-      const float v = s.values[k];
-      const float delta = s.rewards[k] + not_term * gamma * next_value - v;
-      adv = delta + not_term * gamma * lam * adv;
-      const float ret = adv + v;
-      s.returns[k] = ret;
-      const float a = ret - v;              // rollout_storage.py:126 (returns - values, not `adv`)
-      s.advantages[k] = a;
-      mom.n += 1.0;
-      const double d = (double)a - mom.mean;
-      mom.mean += d / mom.n;
-      mom.m2 += d * ((double)a - mom.mean);
-      next_value = v;
+    // the recurrence is serial in t but its loads are not: fetch kGaeChunk steps at once (independent loads in flight),
+    // then run the scan on registers -- T dependent DRAM latencies become T / kGaeChunk
+    for (int t0 = s.T - 1; t0 >= 0; t0 -= kGaeChunk) {
+      float r[kGaeChunk], v[kGaeChunk];
+      uint8_t d[kGaeChunk];
+#pragma unroll
+      for (int j = 0; j < kGaeChunk; ++j) {
+        const int t = t0 - j;
+        if (t >= 0) {
+          const int64_t k = (int64_t)t * N + n;
+          r[j] = __ldcs(s.rewards + k); v[j] = __ldcs(s.values + k); d[j] = __ldcs(s.dones + k);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kGaeChunk; ++j) {
+        const int t = t0 - j;
+        if (t >= 0) {
+          const int64_t k = (int64_t)t * N + n;
+          const float not_term = 1.0f - (float)d[j];
+          const float delta = r[j] + not_term * gamma * next_value - v[j];
+          adv = delta + not_term * gamma * lam * adv;
+          const float ret = adv + v[j];
+          s.returns[k] = ret;
+          const float a = ret - v[j];          // rollout_storage.py:126 (returns - values, not `adv`)
+          s.advantages[k] = a;
+          cnt += 1.0; s1 += (double)a; s2 += (double)a * (double)a;     // fp64 power sums: no division in the scan
+          next_value = v[j];
+        }
+      }
     }
   }
+  // per-thread power sums -> (count, mean, M2), then the Chan merge over the block (warp shuffles, one partial per block)
+  Moments mom{cnt, cnt > 0.0 ? s1 / cnt : 0.0, cnt > 0.0 ? s2 - s1 * s1 / cnt : 0.0};
   mom = block_merge(mom, sh);
   if (threadIdx.x == 0) { partials[3 * blockIdx.x] = mom.n; partials[3 * blockIdx.x + 1] = mom.mean; partials[3 * blockIdx.x + 2] = mom.m2; }
 }

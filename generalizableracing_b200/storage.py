@@ -73,12 +73,17 @@ class RolloutStorage:
         self._scratch = torch.zeros(int(self._lib.gr_gae_scratch_bytes(N)) // 8 + 1, dtype=torch.float64, device=dev)
         self.moments = torch.zeros(3, dtype=torch.float64, device=dev)     # (count, mean, M2) of the raw advantages
         self._keep = None
+        self._desc_cache = None
+        self._tr = B.GrTransition()
 
     # ------------------------------------------------------------------
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
 
     def _desc(self) -> B.GrStorage:
+        """Argument struct of the buffers (built once: the class never re-binds its tensors; do not re-bind them either)."""
+        if self._desc_cache is not None:
+            return self._desc_cache
         s = B.GrStorage()
         s.obs = self.observations.data_ptr()
         s.critic_obs = None if self.privileged_observations is None else self.privileged_observations.data_ptr()
@@ -89,10 +94,13 @@ class RolloutStorage:
         s.obs_dim = self.obs_shape[0]
         s.critic_dim = self.privileged_obs_shape[0] or 0
         s.act_dim = self.actions_shape[0]
+        self._desc_cache = s
+        self._p_desc = C.byref(s)
         return s
 
     def _f32(self, t, shape=None):
-        t = t.detach()
+        if t.requires_grad:
+            t = t.detach()
         if t.dtype != torch.float32 or t.device != self.device or not t.is_contiguous():
             t = t.to(self.device, torch.float32).contiguous()
         return t
@@ -104,7 +112,9 @@ class RolloutStorage:
             raise AssertionError("Rollout buffer overflow")
         if transition.hidden_states is not None and transition.hidden_states != (None, None):
             raise NotImplementedError("recurrent hidden states are out of scope (SURVEY.md §8f rank 4)")
-        tr = B.GrTransition()
+        tr = self._tr
+        tr.critic_obs = None
+        tr.time_outs = None
         keep = [self._f32(transition.observations), self._f32(transition.actions), self._f32(transition.rewards),
                 self._f32(transition.values), self._f32(transition.actions_log_prob), self._f32(transition.action_mean),
                 self._f32(transition.action_sigma)]
@@ -113,7 +123,7 @@ class RolloutStorage:
             po = self._f32(transition.privileged_observations)
             keep.append(po)
             tr.critic_obs = po.data_ptr()
-        d = transition.dones.detach()
+        d = transition.dones
         if d.dtype == torch.bool:
             d = d.view(torch.uint8)
         if d.dtype not in (torch.uint8, torch.int64) or d.device != self.device or not d.is_contiguous():
@@ -122,15 +132,17 @@ class RolloutStorage:
         tr.dones = d.data_ptr()
         tr.dones_is_int64 = int(d.dtype == torch.int64)
         if transition.time_outs is not None:
-            to = transition.time_outs.detach()
+            to = transition.time_outs
             to = to.view(torch.uint8) if to.dtype == torch.bool else to.to(torch.uint8)
             to = to.to(self.device).contiguous()
             keep.append(to)
             tr.time_outs = to.data_ptr()
             tr.gamma = float(transition.gamma)
         self._keep = keep
-        desc = self._desc()
-        B.check(self._lib.gr_storage_add(C.byref(desc), C.byref(tr), self.step, self._stream()), "gr_storage_add")
+        self._desc()
+        rc = self._lib.gr_storage_add(self._p_desc, C.byref(tr), self.step, self._stream())
+        if rc:
+            B.check(rc, "gr_storage_add")
         self.step += 1
 
     def clear(self):
@@ -141,8 +153,8 @@ class RolloutStorage:
         ``normalize=False`` the raw advantages and their (count, mean, M2) in ``self.moments`` are left for a
         cross-rank merge followed by :meth:`normalize_advantages`."""
         lv = self._f32(last_values)
-        desc = self._desc()
-        B.check(self._lib.gr_compute_returns(C.byref(desc), lv.data_ptr(), float(gamma), float(lam), self._scratch.data_ptr(),
+        self._desc()
+        B.check(self._lib.gr_compute_returns(self._p_desc, lv.data_ptr(), float(gamma), float(lam), self._scratch.data_ptr(),
                                              self.moments.data_ptr(), int(normalize), self._stream()), "gr_compute_returns")
 
     def normalize_advantages(self, moments: torch.Tensor = None):
