@@ -44,6 +44,18 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
+def ncu_traffic(kernel_key: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture (profiles/traffic.json, written by tools/ncu_summary.py from the .ncu-rep); None if no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.isfile(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    e = d.get(kernel_key)
+    return None if e is None else float(e["dram_bytes_read"]) + float(e["dram_bytes_write"])
+
+
 def algorithmic_bytes(cfg, stats: bool, critic: bool = True, dones64: bool = True) -> int:
     """Every persistent column read once + written once, every API output written once."""
     rd = 7 * 16 + 5 * 16 + 16                      # hot planes, cold planes, action
@@ -241,36 +253,41 @@ def run_ours(args):
         low = {"kernel_us": us, "env_steps_per_s_per_gpu": N / (us * 1e-6), "frac_of_hbm_peak": b_alg * N / (us * 1e-6) / 1e9 / peak,
                "resets_per_env_step": rr, "actions": "N((-0.35,0,0,0), 0.1^2): near hover"}
 
-    # ---- e2e: public API, host buffers, H2D + D2H inside the timed region
+    # ---- e2e: public API with HOST buffers (RacingVecEnv.step_host -> gr_host_pipe_*), H2D + D2H inside the timed region.
+    # Every step copies its own actions host->device and its obs / reward / dones device->host; `depth` steps are in flight
+    # so the copies of step t overlap the kernel of step t+1 (the consumer reads step t's results while t+1 runs).
     env = envs[0]
-    h_act = torch.randn(N, 4).pin_memory()
-    h_obs = torch.empty(N, 16).pin_memory()
-    h_rew = torch.empty(N).pin_memory()
-    h_done = torch.empty(N, dtype=torch.int64).pin_memory()
-    d_act = torch.empty(N, 4, device=dev)
+    depth = 3
+    h_act = [(torch.randn(N, 4) * 0.5).pin_memory() for _ in range(depth)]
+    h_obs = [torch.empty(N, 16).pin_memory() for _ in range(depth)]
+    h_rew = [torch.empty(N).pin_memory() for _ in range(depth)]
+    h_done = [torch.empty(N, dtype=torch.int64).pin_memory() for _ in range(depth)]
+    torch.cuda.synchronize(dev)
 
-    def e2e_step():
-        d_act.copy_(h_act, non_blocking=True)
-        obs, rew, dones, _ = env.step(d_act)
-        h_obs.copy_(obs, non_blocking=True)
-        h_rew.copy_(rew, non_blocking=True)
-        h_done.copy_(dones, non_blocking=True)
+    def e2e_loop(n, d):
+        tickets = []
+        for t in range(n):
+            k = t % d
+            if t >= d:
+                env.wait_host(tickets[t - d])            # results of step t-d are on the host before its buffers are reused
+            tickets.append(env.step_host(h_act[k], h_obs[k], h_rew[k], h_done[k], depth=depth))
+        for tk in tickets[-d:]:
+            env.wait_host(tk)
+
+    def timed_e2e(n, d):
+        e2e_loop(max(3, args.warmup), d)
+        barrier(world)
         torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        e2e_loop(n, d)
+        torch.cuda.synchronize(dev)
+        return max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
 
-    for _ in range(max(3, args.warmup)):
-        e2e_step()
-    Ke = max(10, min(args.steps, 200))
-    barrier(world)
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(Ke):
-        e2e_step()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3), world, dev)
+    Ke = max(10, min(args.steps, 300))
+    e2e_ms = timed_e2e(Ke, depth)
     e2e_value = world * N * Ke / (e2e_ms * 1e-3)
+    e2e_sync_ms = timed_e2e(Ke, 1)                       # one step in flight: H2D -> kernel -> D2H strictly in sequence
+    assert torch.isfinite(h_obs[0]).all() and h_done[0].min() >= 0
     h2d = N * 4 * 4
     d2h = N * 16 * 4 + N * 4 + N * 8
 
@@ -283,6 +300,11 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        for e in envs:
+            e.close()
+        del envs, env
+        torch.cuda.empty_cache()
+        extra["torch_eager_gpu_baseline"] = torch_gpu_baseline(dev)
         cpu = cpu_baseline(sample_s=args.cpu_seconds)
 
     if rank == 0:
@@ -296,10 +318,14 @@ def run_ours(args):
                                                f"K timed steps = {rounds} CUDA-graph replays of {R} launches",
                        "mass_kg": cfg.mass, "actions": "N(0, 0.5^2) resident in HBM", "resets_per_env_step": reset_rate},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "api": "RacingVecEnv.step (pinned host actions in; obs, reward, dones out; sync per step)"},
+                    "ms_per_step": e2e_ms / Ke,
+                    "api": f"RacingVecEnv.step_host -> gr_host_pipe_step/wait (C ABI, pinned HOST buffers: actions in; obs, reward, int64 dones out "
+                           f"every step; {depth} steps in flight, results of step t read while step t+1 runs)",
+                    "sync_per_step": {"value": world * N * Ke / (e2e_sync_ms * 1e-3), "ms_per_step": e2e_sync_ms / Ke,
+                                      "note": "same call, one step in flight (H2D -> kernel -> D2H in sequence)"}},
             "gpu_launches": K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "racing_step_fwd_kernel<noise,nodiff,philox,stats>",
+                         "traffic": ncu_traffic("racing_step_fwd_kernel<1,0,1,1>"), "kernel": "racing_step_fwd_kernel<noise,nodiff,philox,stats>",
                          "bytes_per_env_step": b_alg, "kernel_us": kernel_us, "peak_source": peak_src},
             "clocks": clk.summary(),
             "cpu_baseline": cpu,
@@ -414,7 +440,7 @@ def bench_extras(dev, cfg, table):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def _oracle_env(N, threads):
+def _oracle_env(N, threads, device="cpu"):
     """The reference arm: the oracle = CPU torch restatement of the reference's own implementation of the path
     (the reference itself needs Isaac Sim; /root/reference does not exist on the GPU box)."""
     from generalizableracing_b200 import layout as L_
@@ -426,16 +452,36 @@ def _oracle_env(N, threads):
     g = torch.Generator().manual_seed(0)
     srnd = torch.rand(N, L_.SRND_STRIDE, generator=g)
     srnd[:, 12:] = torch.randn(N, 4, generator=g)
-    env = RO.OracleRacingEnv(cfg, synthetic_track_table(), N, srnd)
+    env = RO.OracleRacingEnv(cfg, synthetic_track_table(), N, srnd.to(device), device=device)
 
     def draw():
         r = torch.rand(N, L_.RND_STRIDE, generator=g)
         r[:, :8] = torch.randn(N, 8, generator=g)
-        return r
+        return r.to(device)
 
     env.reset(draw())
-    env.episode_length_buf[:] = torch.randint(0, cfg.max_episode_length, (N,), generator=g)
+    env.episode_length_buf[:] = torch.randint(0, cfg.max_episode_length, (N,), generator=g).to(device)
     return env, draw, g
+
+
+def torch_gpu_baseline(dev, N: int = NUM_ENVS, steps: int = 20):
+    """The reference's implementation style on the SAME GPU: the oracle (torch port of the reference's eager tensor code,
+    ~700 aten launches per env.step) on the B200 -- the denominator of the north star's ">= 100x torch-on-GPU" target.
+    A reported baseline (bench.py's baseline leg), never part of the product path."""
+    env, draw, g = _oracle_env(N, os.cpu_count() or 1, device=dev)
+    a = (torch.randn(N, 4, generator=g) * 0.5).to(dev)
+    rs = [draw() for _ in range(steps + 3)]
+    with torch.no_grad():
+        for k in range(3):
+            env.step(a, rs[k])
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for k in range(steps):
+            env.step(a, rs[3 + k])
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+    return {"value": N * steps / dt, "unit": UNIT, "ms_per_step": dt * 1e3 / steps, "steps": steps,
+            "what": f"oracle (torch eager port of the reference) on cuda, {N} envs, STAGE {STAGE}, no_grad, dense pre-drawn randoms"}
 
 
 def cpu_baseline(sample_s: float = 15.0, N: int = NUM_ENVS):

@@ -75,6 +75,11 @@ class GrMiniBatch(C.Structure):
                 ("log_prob", c_p), ("mu", c_p), ("sigma", c_p)]
 
 
+class GrHostStep(C.Structure):
+    _fields_ = [("action", c_p), ("obs", c_p), ("reward", c_p), ("dones", c_p), ("critic_obs", c_p), ("time_out", c_p)]
+
+
+GR_HOST_PIPE_MAX_DEPTH = 4
 GR_LAUNCH_PDL = 1
 GR_LAUNCH_PREFETCH = 2
 GR_LOG_SLOTS = 16
@@ -96,6 +101,11 @@ PROTOTYPES = {
     "gr_compute_returns": (C.c_int, [C.POINTER(GrStorage), c_p, c_f, c_f, c_p, c_p, c_i, c_p]),
     "gr_advantage_normalize": (C.c_int, [C.POINTER(GrStorage), c_p, c_p]),
     "gr_storage_gather": (C.c_int, [C.POINTER(GrStorage), c_p, c_i, C.POINTER(GrMiniBatch), c_p]),
+    "gr_host_pipe_create": (C.c_int, [c_i, c_i, c_p, C.POINTER(c_p)]),
+    "gr_host_pipe_destroy": (C.c_int, [c_p]),
+    "gr_host_pipe_step": (C.c_int, [c_p, C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom),
+                                    C.POINTER(GrHostStep), c_p, C.POINTER(C.c_int64)]),
+    "gr_host_pipe_wait": (C.c_int, [c_p, C.c_int64]),
 }
 
 

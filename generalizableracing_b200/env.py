@@ -190,6 +190,7 @@ class RacingVecEnv:
         self._last = self._outs[0]
         self._needs_reset = True
         self._ios = None
+        self._pipe = None
         self._params_edited = False
         self._p_cfg, self._p_track, self._p_state = C.byref(self._gcfg), C.byref(self._track), C.byref(self._state)
 
@@ -324,7 +325,9 @@ class RacingVecEnv:
             self._bptt.start_window()
 
     def close(self):
-        pass
+        if self._pipe is not None:
+            self._lib.gr_host_pipe_destroy(self._pipe)
+            self._pipe = None
 
     def _make_io(self, o) -> B.GrStepIO:
         io = B.GrStepIO()
@@ -370,6 +373,46 @@ class RacingVecEnv:
         if self._bptt is not None:
             self._bptt.after_step(actions, ex)
         return o["obs"], o["reward"], o["dones"], ex
+
+
+    # ------------------------------------------------------------------ host-buffer API (gr_host_pipe_*, include/gracing.h)
+    def step_host(self, actions: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, dones: Optional[torch.Tensor] = None,
+                  critic_obs: Optional[torch.Tensor] = None, time_outs: Optional[torch.Tensor] = None, depth: int = 2) -> int:
+        """env.step() for a caller whose tensors live in (pinned) HOST memory: enqueue H2D(actions) -> step kernel ->
+        D2H(obs, reward, dones[, critic_obs, time_outs]) and return a ticket at once; the output tensors hold the step's
+        results after ``wait_host(ticket)``.  Up to ``depth`` steps are in flight (copies overlap the next kernel)."""
+        if self._needs_reset:
+            self.reset()
+        if self._bptt is not None:
+            raise RuntimeError("step_host is a forward-only path; BPTT windows need device tensors (step)")
+        if self._pipe is None:
+            pipe = C.c_void_p()
+            B.check(self._lib.gr_host_pipe_create(self.num_envs, int(depth), self._stream(), C.byref(pipe)), "gr_host_pipe_create")
+            self._pipe = pipe
+        for t, shape, dt in ((actions, (self.num_envs, 4), torch.float32), (obs, (self.num_envs, L.OBS_DIM), torch.float32),
+                             (reward, (self.num_envs,), torch.float32), (dones, (self.num_envs,), torch.int64),
+                             (critic_obs, (self.num_envs, L.OBS_DIM), torch.float32), (time_outs, (self.num_envs,), torch.bool)):
+            if t is not None and (t.device.type != "cpu" or tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous()):
+                raise ValueError(f"step_host: expected a contiguous host tensor of shape {shape} and dtype {dt}")
+        hs = B.GrHostStep(actions.data_ptr(), obs.data_ptr(), reward.data_ptr(), B.ptr(dones), B.ptr(critic_obs), B.ptr(time_outs))
+        ticket = C.c_int64()
+        B.check(self._lib.gr_host_pipe_step(self._pipe, self._p_cfg, self._p_track, self._p_state, C.byref(self._rand(None)), C.byref(hs),
+                                            self._log_accum.data_ptr(), C.byref(ticket)), "gr_host_pipe_step")
+        if self._params_edited:
+            self._state.launch_flags = self._launch_flags
+            self._params_edited = False
+        return ticket.value
+
+    def wait_host(self, ticket: int) -> None:
+        B.check(self._lib.gr_host_pipe_wait(self._pipe, int(ticket)), "gr_host_pipe_wait")
+
+    def __del__(self):
+        pipe = getattr(self, "_pipe", None)
+        if pipe is not None:
+            try:
+                self._lib.gr_host_pipe_destroy(pipe)
+            except Exception:
+                pass
 
 
 B_LOG_NUM_RESET, B_LOG_SUM_GATES, B_LOG_SUM_EPSUM, B_LOG_NUM_TIMEOUT, B_LOG_NUM_TERMINATED = 0, 1, 2, 8, 9

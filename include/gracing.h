@@ -245,6 +245,31 @@ typedef struct GrMiniBatch {
 } GrMiniBatch;
 int gr_storage_gather(const GrStorage* s, const int64_t* indices, int32_t B, const GrMiniBatch* out, void* stream);
 
+/* ---- env.step() with HOST buffers (the e2e boundary) -------------------------------------------------------------
+ * Same call as gr_step_fwd for a caller whose actions / observations live in host memory: replaces
+ * `env.step(torch.as_tensor(a).to(device))` + `.cpu()` of obs / reward / dones around ManagerBasedDiffRLEnv.step
+ * (L/envs/manager_based_diff_rl_env.py:160-267) as a host-side consumer of RslRlVecEnvWrapper.step would write it.
+ * The pipe owns `depth` device staging slots, two copy streams and its events (the ONLY objects this library ever
+ * allocates; freed by gr_host_pipe_destroy).  gr_host_pipe_step enqueues H2D(actions) -> step kernel -> D2H(results)
+ * and returns at once with a ticket; the host buffers of ticket t are valid after gr_host_pipe_wait(t) and must stay
+ * untouched until then.  Up to `depth` steps are in flight, so the copies of step t overlap the kernel of step t+1.
+ * Host buffers should be page-locked (cudaHostAlloc / torch pin_memory), otherwise the copies serialise. */
+#define GR_HOST_PIPE_MAX_DEPTH 4
+typedef struct GrHostPipe GrHostPipe;
+typedef struct GrHostStep {
+  const float* action;      /* host [N,4]                                    required */
+  float* obs;               /* host [N,16]                                   required */
+  float* reward;            /* host [N]                                      required */
+  int64_t* dones;           /* host [N]                                      optional */
+  float* critic_obs;        /* host [N,16]                                   optional */
+  uint8_t* time_out;        /* host [N]                                      optional */
+} GrHostStep;
+int gr_host_pipe_create(int32_t num_envs, int32_t depth, void* compute_stream, GrHostPipe** out);
+int gr_host_pipe_destroy(GrHostPipe* pipe);
+int gr_host_pipe_step(GrHostPipe* pipe, const GrConfig* cfg, const GrTrack* track, const GrState* st, const GrRandom* rng,
+                      const GrHostStep* host, float* log_accum /* device, optional */, int64_t* ticket_out);
+int gr_host_pipe_wait(GrHostPipe* pipe, int64_t ticket);
+
 #ifdef __cplusplus
 }
 #endif

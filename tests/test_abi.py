@@ -52,7 +52,7 @@ def _c_struct_fields(name):
     return fields
 
 
-@pytest.mark.parametrize("name", ["GrConfig", "GrTrack", "GrState", "GrRandom", "GrStepIO", "GrBwdIO", "GrTransition", "GrStorage", "GrMiniBatch"])
+@pytest.mark.parametrize("name", ["GrConfig", "GrTrack", "GrState", "GrRandom", "GrStepIO", "GrBwdIO", "GrTransition", "GrStorage", "GrMiniBatch", "GrHostStep"])
 def test_ctypes_structs_follow_the_header(name):
     assert [f for f, _ in getattr(B, name)._fields_] == _c_struct_fields(name)
 
@@ -65,6 +65,12 @@ def test_argument_errors_are_reported_without_launch(lib):
     assert lib.gr_gae_scratch_bytes(4096) >= 3 * 8 * (4096 // 128)
     st = B.GrStorage()
     assert lib.gr_compute_returns(C.byref(st), None, 0.99, 0.95, None, None, 1, None) == -1
+    pipe = C.c_void_p()
+    assert lib.gr_host_pipe_create(64, 2, None, None) == -1
+    assert lib.gr_host_pipe_create(0, 2, None, C.byref(pipe)) == -2
+    assert lib.gr_host_pipe_create(64, B.GR_HOST_PIPE_MAX_DEPTH + 1, None, C.byref(pipe)) == -2
+    assert lib.gr_host_pipe_step(None, None, None, None, None, None, None, None) == -1
+    assert lib.gr_host_pipe_wait(None, 0) == -1
     with pytest.raises(B.GracingError):
         B.check(-5, "x")
 
