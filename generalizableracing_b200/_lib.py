@@ -75,6 +75,19 @@ class GrMiniBatch(C.Structure):
                 ("log_prob", c_p), ("mu", c_p), ("sigma", c_p)]
 
 
+class GrMlp(C.Structure):
+    _fields_ = [("w1", c_p), ("b1", c_p), ("w2", c_p), ("b2", c_p), ("w3", c_p), ("b3", c_p), ("in_dim", c_i), ("hidden", c_i), ("out_dim", c_i)]
+
+
+class GrPolicy(C.Structure):
+    _fields_ = [("packed", c_p), ("sigma", c_p), ("negative_slope", c_f)]
+
+
+class GrCollectIO(C.Structure):
+    _fields_ = [("obs0", c_p), ("critic_obs0", c_p), ("obs_out", c_p), ("critic_obs_out", c_p), ("aux_out", c_p), ("last_values", c_p),
+                ("episode_acc", c_p), ("log_accum", c_p), ("gamma", c_f), ("groups_per_cta", c_i)]
+
+
 class GrHostStep(C.Structure):
     _fields_ = [("action", c_p), ("obs", c_p), ("reward", c_p), ("dones", c_p), ("critic_obs", c_p), ("time_out", c_p)]
 
@@ -84,6 +97,8 @@ GR_LAUNCH_PDL = 1
 GR_LAUNCH_PREFETCH = 2
 GR_LOG_SLOTS = 16
 GR_LOG_SHARDS = 256
+GR_LOG_EP_REWARD, GR_LOG_EP_LENGTH = 10, 11
+GR_PHILOX_CALL_ACTION = 16
 STATUS = {0: "GR_OK", -1: "GR_ERR_NULL", -2: "GR_ERR_SIZE", -3: "GR_ERR_ALIGN", -4: "GR_ERR_CONFIG", -5: "GR_ERR_SMEM"}
 
 # symbol -> (restype, argtypes); every symbol include/gracing.h declares
@@ -101,6 +116,10 @@ PROTOTYPES = {
     "gr_compute_returns": (C.c_int, [C.POINTER(GrStorage), c_p, c_f, c_f, c_p, c_p, c_i, c_p]),
     "gr_advantage_normalize": (C.c_int, [C.POINTER(GrStorage), c_p, c_p]),
     "gr_storage_gather": (C.c_int, [C.POINTER(GrStorage), c_p, c_i, C.POINTER(GrMiniBatch), c_p]),
+    "gr_policy_packed_bytes": (C.c_int64, []),
+    "gr_policy_pack": (C.c_int, [C.POINTER(GrMlp), C.POINTER(GrMlp), c_p, c_p]),
+    "gr_ppo_collect": (C.c_int, [C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom), C.POINTER(GrPolicy),
+                                 C.POINTER(GrStorage), C.POINTER(GrCollectIO), c_p]),
     "gr_host_pipe_create": (C.c_int, [c_i, c_i, c_p, C.POINTER(c_p)]),
     "gr_host_pipe_destroy": (C.c_int, [c_p]),
     "gr_host_pipe_step": (C.c_int, [c_p, C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom),

@@ -72,9 +72,10 @@ class PPO:
         self.transition.clear()
         self.policy.reset(dones)
 
-    def compute_returns(self, last_critic_obs):
-        # ppo.py:99-101
-        last_values = self.policy.evaluate(last_critic_obs).detach()
+    def compute_returns(self, last_critic_obs, last_values=None):
+        # ppo.py:99-101 (last_values: already evaluated by the fused collection kernel)
+        if last_values is None:
+            last_values = self.policy.evaluate(last_critic_obs).detach()
         _, w = D.world()
         if w == 1:
             self.storage.compute_returns(last_values, self.gamma, self.lam)

@@ -1,0 +1,440 @@
+// ppo_collect.cu -- the whole PPO collection phase in ONE sm_100a kernel: T x [actor MLP -> Normal sample -> log-prob ->
+// critic MLP -> env.step -> time-out bootstrap -> add_transitions], then V(last obs) for the GAE bootstrap.
+//
+// Reference path replaced (S = standalone): the rollout loop of OnPolicyRunner.learn (S/rsl_rl/ext/runners/
+// on_policy_runner.py:141-175): PPO.act (S/rsl_rl/ext/algorithms/ppo.py:71-83; rsl_rl ActorCritic 16->128->128->4 /
+// ->1, lrelu, QD/agents/rsl_rl_ppo_cfg.py:22-27), env.step (the ~700 aten launches racing_step.cu fuses),
+// PPO.process_env_step (ppo.py:85-97), RolloutStorage.add_transitions (S/rsl_rl/ext/storage/rollout_storage.py:71-88),
+// the episode book keeping (on_policy_runner.py:160-173) and PPO.compute_returns' last_values (ppo.py:99-100).
+// Measured on a B200 (profiles/r1_rollout_cost_torch_policy_vs_env.json): per collection step at 65,536 envs the torch
+// policy costs 432 us eager / 296 us under a CUDA graph against 9 us for the env step -- the MLP is the dense
+// contraction that bounds collection, so it goes to the tensor cores here (north star: tensor cores only for the MLP).
+//
+// Design
+//  * one thread per env, 128 envs (4 warps) = one UMMA tile (M = 128); a CTA runs G tiles ("groups") that share one
+//    copy of the packed weights in shared memory and overlap each other's MMA latency; env state lives in REGISTERS for
+//    the whole rollout (loaded once, stored once): per env-step HBM sees only the rollout-storage rows.
+//  * per group and net: X[128x32] . W1 -> D (TMEM) -> lrelu -> H1[128x128] fp16 (smem) . W2 -> D -> +b2, lrelu -> H2 . W3
+//    (N = 16) -> D -> 4 means / 1 value.  tcgen05.mma kind::f16 (fp16 operands, fp32 accumulate), issued by one thread per
+//    group, completion through an mbarrier; accumulator row = TMEM lane = the env's own thread, so the epilogue is
+//    thread-local (tcgen05.ld 32x32b) and each thread writes its own activation row back as the next A operand.
+//    Layer-1 bias rides in the GEMM (two constant-one K columns against fp16 hi/lo bias rows), layer-2 bias is a packed
+//    half2 add in the epilogue, layer-3 bias is fp32.
+//  * operands are K-major, non-swizzled: [K/8 chunks][rows][8 halfs]; a thread's 16-byte chunk stores are conflict-free.
+//  * numerics: policy inference at fp16-operand / fp32-accumulate precision (the error against the fp32 torch MLP is
+//    measured in tests/test_ppo_collect.py and DESIGN.md); everything the env does (state, rewards, dones, observations)
+//    is the same code as gr_step_fwd, bit for bit, given the same actions.
+#include <cuda_fp16.h>
+#include "racing_step_core.cuh"
+#include "umma.cuh"
+
+namespace gr {
+
+using namespace umma;
+
+constexpr int kTileEnvs = 128;                    // M of one UMMA tile = threads per group
+constexpr int kHid = 128, kObsDim = 16, kK1 = 32, kOutPad = 16;
+constexpr int kChunkA = kTileEnvs * 16;           // byte stride between K chunks of an A operand (128 rows x 16 B)
+// packed parameters of one net (bytes); every block is 128-byte aligned
+constexpr int kW1Off = 0, kW1Bytes = kHid * kK1 * 2;              // [4][128][8] halfs: 16 inputs | b1 hi | b1 lo | 0...
+constexpr int kW2Off = kW1Off + kW1Bytes, kW2Bytes = kHid * kHid * 2;      // [16][128][8]
+constexpr int kW3Off = kW2Off + kW2Bytes, kW3Bytes = kOutPad * kHid * 2;   // [16][16][8], rows >= out_dim are zero
+constexpr int kB2Off = kW3Off + kW3Bytes, kB2Bytes = kHid * 2;             // fp16 [128]
+constexpr int kB3Off = kB2Off + kB2Bytes, kB3Bytes = 128;                  // fp32 [16] (+ pad)
+constexpr int kNetBytes = kB3Off + kB3Bytes;                               // 45,440
+constexpr int kHBytes = kTileEnvs * kHid * 2;                              // activation tile of one group: 32 KB
+static_assert(kNetBytes % 128 == 0, "packed net must keep 128-byte alignment");
+
+// ---------------------------------------------------------------------------------------------
+// parameter packing: torch Linear weights [out][in] fp32 -> fp16, UMMA operand order
+// ---------------------------------------------------------------------------------------------
+__global__ void policy_pack_kernel(const GrMlp actor, const GrMlp critic, uint8_t* __restrict__ packed) {
+  const int net = blockIdx.y;
+  const GrMlp& m = net == 0 ? actor : critic;
+  uint8_t* out = packed + (size_t)net * kNetBytes;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  __half* w1 = reinterpret_cast<__half*>(out + kW1Off);
+  __half* w2 = reinterpret_cast<__half*>(out + kW2Off);
+  __half* w3 = reinterpret_cast<__half*>(out + kW3Off);
+  if (idx < kHid * kK1) {
+    const int n = idx / kK1, k = idx % kK1;
+    float v = 0.0f;
+    if (k < kObsDim) v = m.w1[n * kObsDim + k];
+    else if (k == kObsDim) v = __half2float(__float2half_rn(m.b1[n]));
+    else if (k == kObsDim + 1) v = m.b1[n] - __half2float(__float2half_rn(m.b1[n]));
+    w1[(k >> 3) * (kHid * 8) + n * 8 + (k & 7)] = __float2half_rn(v);
+  }
+  if (idx < kHid * kHid) {
+    const int n = idx / kHid, k = idx % kHid;
+    w2[(k >> 3) * (kHid * 8) + n * 8 + (k & 7)] = __float2half_rn(m.w2[n * kHid + k]);
+  }
+  if (idx < kOutPad * kHid) {
+    const int n = idx / kHid, k = idx % kHid;
+    w3[(k >> 3) * (kOutPad * 8) + n * 8 + (k & 7)] = __float2half_rn(n < m.out_dim ? m.w3[n * kHid + k] : 0.0f);
+  }
+  if (idx < kHid) reinterpret_cast<__half*>(out + kB2Off)[idx] = __float2half_rn(m.b2[idx]);
+  if (idx < kB3Bytes / 4) reinterpret_cast<float*>(out + kB3Off)[idx] = idx < m.out_dim ? m.b3[idx] : 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 bits_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint4 pack8(float4 a, float4 b) {
+  return make_uint4(h2_bits(__floats2half2_rn(a.x, a.y)), h2_bits(__floats2half2_rn(a.z, a.w)), h2_bits(__floats2half2_rn(b.x, b.y)),
+                    h2_bits(__floats2half2_rn(b.z, b.w)));
+}
+
+// first-layer operand row of one env: chunks 0,1 = the 16 observations, chunk 2 = (1, 1, 0...) against the bias rows, chunk 3 = 0
+__device__ __forceinline__ void write_x_row(uint8_t* hrow, uint4 c0, uint4 c1) {
+  *reinterpret_cast<uint4*>(hrow) = c0;
+  *reinterpret_cast<uint4*>(hrow + kChunkA) = c1;
+  *reinterpret_cast<uint4*>(hrow + 2 * kChunkA) = make_uint4(0x3C003C00u, 0u, 0u, 0u);      // half2(1, 1)
+  *reinterpret_cast<uint4*>(hrow + 3 * kChunkA) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// hidden-layer epilogue of one env row: D[row][0..127] (TMEM) -> (+ bias) -> leaky relu -> fp16 -> the row of the next A operand
+template <bool kBias>
+__device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint8_t* hrow, const uint4* __restrict__ bias, __half2 slope) {
+#pragma unroll 1
+  for (int c4 = 0; c4 < 4; ++c4) {
+    uint32_t r[32];
+    tmem_ld_x32(taddr + c4 * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __half2 h[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(__uint_as_float(r[8 * j + 2 * q]), __uint_as_float(r[8 * j + 2 * q + 1]));
+      if (kBias) {
+        const uint4 b = bias[c4 * 4 + j];
+        h[0] = __hadd2(h[0], bits_h2(b.x)); h[1] = __hadd2(h[1], bits_h2(b.y)); h[2] = __hadd2(h[2], bits_h2(b.z)); h[3] = __hadd2(h[3], bits_h2(b.w));
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) h[q] = __hmax2(h[q], __hmul2(h[q], slope));
+      *reinterpret_cast<uint4*>(hrow + (c4 * 4 + j) * kChunkA) = make_uint4(h2_bits(h[0]), h2_bits(h[1]), h2_bits(h[2]), h2_bits(h[3]));
+    }
+  }
+}
+
+// one thread: D[tmem] = A[smem: ksteps x 16 K-columns] . B[smem]^T, then arrive on `bar` when done
+__device__ __forceinline__ void issue_layer(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, int ksteps, uint32_t lbo_b, uint32_t idesc, uint64_t* bar) {
+  tc_fence_after_sync();
+#pragma unroll 1
+  for (int kk = 0; kk < ksteps; ++kk)
+    mma_f16_ss(d_tmem, make_smem_desc(a_addr + kk * 2 * kChunkA, kChunkA, 128), make_smem_desc(b_addr + kk * 2 * lbo_b, lbo_b, 128), idesc, kk > 0);
+  tc_commit(bar);
+}
+
+// what one group needs to run a net
+struct GroupCtx {
+  uint8_t* hbuf;        // this group's activation tile (shared)
+  uint8_t* hrow;        // hbuf + row * 16
+  uint32_t hbuf_addr;   // shared-space address of hbuf
+  uint32_t d_tmem;      // accumulator columns of this group
+  uint32_t taddr;       // d_tmem + (lane quarter << 16): what this warp may tcgen05.ld
+  uint64_t* bar;
+  uint32_t phase;
+  int bar_id;           // named barrier of the group
+  bool issuer;
+  __half2 slope;
+};
+
+// All 128 threads of the group call this with their X row already written.  Returns the first 4 layer-3 outputs (+ bias).
+__device__ __forceinline__ float4 run_net(GroupCtx& g, const uint8_t* net_smem, uint32_t net_addr) {
+  // ---- layer 1: [128 x 32] . W1
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  bar_sync(g.bar_id, kTileEnvs);
+  if (g.issuer) issue_layer(g.d_tmem, g.hbuf_addr, net_addr + kW1Off, kK1 / 16, kHid * 16, make_idesc_f16(kTileEnvs, kHid), g.bar);
+  mbar_wait(g.bar, g.phase); g.phase ^= 1u;
+  tc_fence_after_sync();
+  hidden_epilogue<false>(g.taddr, g.hrow, nullptr, g.slope);
+  // ---- layer 2: [128 x 128] . W2
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  bar_sync(g.bar_id, kTileEnvs);
+  if (g.issuer) issue_layer(g.d_tmem, g.hbuf_addr, net_addr + kW2Off, kHid / 16, kHid * 16, make_idesc_f16(kTileEnvs, kHid), g.bar);
+  mbar_wait(g.bar, g.phase); g.phase ^= 1u;
+  tc_fence_after_sync();
+  hidden_epilogue<true>(g.taddr, g.hrow, reinterpret_cast<const uint4*>(net_smem + kB2Off), g.slope);
+  // ---- layer 3: [128 x 128] . W3 (N = 16)
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  bar_sync(g.bar_id, kTileEnvs);
+  if (g.issuer) issue_layer(g.d_tmem, g.hbuf_addr, net_addr + kW3Off, kHid / 16, kOutPad * 16, make_idesc_f16(kTileEnvs, kOutPad), g.bar);
+  mbar_wait(g.bar, g.phase); g.phase ^= 1u;
+  tc_fence_after_sync();
+  uint32_t r[4];
+  tmem_ld_x4(g.taddr, r);
+  tmem_ld_wait();
+  tc_fence_before_sync();                     // the next layer-1 MMA of this group overwrites these columns
+  const float4 b3 = *reinterpret_cast<const float4*>(net_smem + kB3Off);
+  return make_float4(__uint_as_float(r[0]) + b3.x, __uint_as_float(r[1]) + b3.y, __uint_as_float(r[2]) + b3.z, __uint_as_float(r[3]) + b3.w);
+}
+
+// observation sink of the fused kernel: fp32 rows go to the rollout storage (or to the "next observation" buffers after
+// the last step); the policy row also becomes the next layer-1 operand, the critic row waits in 8 registers as fp16
+struct FusedObsSink {
+  float4* obs_row; float4* critic_row; float* aux_ptr;
+  uint8_t* hrow; uint4* critic_pk;     // critic_pk -> two uint4 in the caller's registers
+  __device__ __forceinline__ void policy(int, float4 o0, float4 o1, float4 o2, float4 o3) const {
+    __stcs(obs_row + 0, o0); __stcs(obs_row + 1, o1); __stcs(obs_row + 2, o2); __stcs(obs_row + 3, o3);
+    write_x_row(hrow, pack8(o0, o1), pack8(o2, o3));
+  }
+  __device__ __forceinline__ bool wants_critic() const { return true; }
+  __device__ __forceinline__ void critic(int, float4 c0, float4 c1, float4 c2, float4 c3) const {
+    __stcs(critic_row + 0, c0); __stcs(critic_row + 1, c1); __stcs(critic_row + 2, c2); __stcs(critic_row + 3, c3);
+    critic_pk[0] = pack8(c0, c1); critic_pk[1] = pack8(c2, c3);
+  }
+  __device__ __forceinline__ void aux(int, float v) const { if (aux_ptr) *aux_ptr = v; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// the collection kernel
+// ---------------------------------------------------------------------------------------------
+template <int G, bool kNoise, bool kStats>
+__global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrConfig cfg, const GrTrack track, const GrState st, const GrRandom rng,
+                                                                      const GrPolicy pol, const GrStorage sto, const GrCollectIO cio,
+                                                                      const int track_in_smem) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* w_smem = smem;                                        // actor net | critic net
+  uint8_t* h_smem = smem + 2 * kNetBytes;                        // G activation tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(h_smem + G * kHBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + G);
+  float4* track_rows = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + 128);
+
+  const int tid = threadIdx.x, grp = tid / kTileEnvs, row = tid % kTileEnvs;
+  const int i = blockIdx.x * (G * kTileEnvs) + tid;
+  const bool active = i < st.num_envs;
+  const int li = active ? i : st.num_envs - 1;
+  const int N = st.num_envs, T = sto.T;
+
+  // ---- one-time setup: weights -> smem, gate-table slice, barriers, tensor memory
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(pol.packed);
+    uint4* dst = reinterpret_cast<uint4*>(w_smem);
+    for (int k = tid; k < 2 * kNetBytes / 16; k += G * kTileEnvs) dst[k] = __ldg(src + k);
+  }
+  if (tid < G) mbar_init(&bars[tid], 1);
+  __syncwarp();
+  if (tid < 32) tmem_alloc(tmem_slot, G * kHid < 32 ? 32 : G * kHid);
+  // gate table: the slice of the terrain types this CTA spans goes to shared memory when it fits next to the weights and
+  // activation tiles, otherwise the (L1-resident, <= 29 KB) table is read in place
+  TrackSmem tr{reinterpret_cast<const float4*>(track.rows), 0, track.levels, track.gates};
+  if (track_in_smem) tr = stage_track(track, reinterpret_cast<const int2*>(st.chunk_types), N, track_rows);     // ends with __syncthreads()
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+
+  GroupCtx g;
+  g.hbuf = h_smem + grp * kHBytes;
+  g.hrow = g.hbuf + row * 16;
+  g.hbuf_addr = smem_u32(g.hbuf);
+  g.d_tmem = *tmem_slot + (uint32_t)(grp * kHid);
+  g.taddr = g.d_tmem + ((uint32_t)((row >> 5) * 32) << 16);
+  g.bar = &bars[grp];
+  g.phase = 0u;
+  g.bar_id = 1 + grp;
+  g.issuer = row == 0;
+  g.slope = __float2half2_rn(pol.negative_slope);
+  const uint32_t w_addr = smem_u32(w_smem);
+
+  // ---- env state -> registers (once per rollout)
+  float4* __restrict__ tile = tile_ptr(reinterpret_cast<float4*>(st.planes), li);
+  EnvRegs e;
+  load_env<kNoise>(e, tile);
+  float4 eps0 = make_float4(0.f, 0.f, 0.f, 0.f), eps1 = eps0;
+  if (kStats) { eps0 = ld_plane(tile, PL_EPSUM0); eps1 = ld_plane(tile, PL_EPSUM1); }
+  float2 epacc = cio.episode_acc ? reinterpret_cast<const float2*>(cio.episode_acc)[li] : make_float2(0.f, 0.f);
+  const float4 sigma = *reinterpret_cast<const float4*>(pol.sigma);
+  const float4 log_sigma = make_float4(logf(sigma.x), logf(sigma.y), logf(sigma.z), logf(sigma.w));
+  bool any_reset = false, any_noise_dirty = false, last_noise_dirty = false;
+  GrStepIO io = {};
+  io.log_accum = cio.log_accum;
+
+  // ---- observations the rollout starts from -> storage slot 0 + operand rows
+  uint4 critic_pk[2];
+  {
+    const float4* o = reinterpret_cast<const float4*>(cio.obs0) + (int64_t)li * 4;
+    const float4* c = reinterpret_cast<const float4*>(cio.critic_obs0) + (int64_t)li * 4;
+    const float4 o0 = __ldg(o), o1 = __ldg(o + 1), o2 = __ldg(o + 2), o3 = __ldg(o + 3);
+    const float4 c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2), c3 = __ldg(c + 3);
+    if (active) {
+      float4* so = reinterpret_cast<float4*>(sto.obs) + (int64_t)i * 4;
+      float4* sc = reinterpret_cast<float4*>(sto.critic_obs) + (int64_t)i * 4;
+      __stcs(so, o0); __stcs(so + 1, o1); __stcs(so + 2, o2); __stcs(so + 3, o3);
+      __stcs(sc, c0); __stcs(sc + 1, c1); __stcs(sc + 2, c2); __stcs(sc + 3, c3);
+    }
+    write_x_row(g.hrow, pack8(o0, o1), pack8(o2, o3));
+    critic_pk[0] = pack8(c0, c1); critic_pk[1] = pack8(c2, c3);
+  }
+
+#pragma unroll 1
+  for (int t = 0; t < T; ++t) {
+    const int64_t tn = (int64_t)t * N + i;
+    // ---- PPO.act: actor mean, sample, log-prob (ppo.py:71-83; Normal(mean, std).sample() / .log_prob().sum(-1))
+    const float4 mu = run_net(g, w_smem, w_addr);
+    GrRandom rt = rng;
+    rt.step = rng.step + (uint32_t)t;
+    const RandSrc<true> rs(rt, li, st.env_id_offset + li);
+    float4 a_t;
+    float logp;
+    {
+      const uint4 x = rs.ph(GR_PHILOX_CALL_ACTION);
+      const float2 n0 = box_muller(x.x, x.y), n1 = box_muller(x.z, x.w);
+      a_t = make_float4(mu.x + sigma.x * n0.x, mu.y + sigma.y * n0.y, mu.z + sigma.z * n1.x, mu.w + sigma.w * n1.y);
+      const float dx = a_t.x - mu.x, dy = a_t.y - mu.y, dz = a_t.z - mu.z, dw = a_t.w - mu.w;
+      const float kLogSqrt2Pi = 0.91893853320467274178f;
+      logp = (-(dx * dx) / (2.0f * sigma.x * sigma.x) - log_sigma.x - kLogSqrt2Pi) + (-(dy * dy) / (2.0f * sigma.y * sigma.y) - log_sigma.y - kLogSqrt2Pi) +
+             (-(dz * dz) / (2.0f * sigma.z * sigma.z) - log_sigma.z - kLogSqrt2Pi) + (-(dw * dw) / (2.0f * sigma.w * sigma.w) - log_sigma.w - kLogSqrt2Pi);
+    }
+    if (active) {
+      __stcs(reinterpret_cast<float4*>(sto.actions) + tn, a_t);
+      __stcs(reinterpret_cast<float4*>(sto.mu) + tn, mu);
+      __stcs(reinterpret_cast<float4*>(sto.sigma) + tn, sigma);
+      sto.log_prob[tn] = logp;
+    }
+    // ---- critic value of the same state
+    write_x_row(g.hrow, critic_pk[0], critic_pk[1]);
+    const float value = run_net(g, w_smem + kNetBytes, w_addr + kNetBytes).x;
+
+    // ---- env.step (same body as gr_step_fwd); its observations are the next step's operands / storage rows
+    float4 n01, n23;
+    rs.normals8(n01, n23);
+    const Draws<true> draws{rs, nullptr};
+    const bool last = t == T - 1;
+    FusedObsSink sink;
+    sink.obs_row = (last ? reinterpret_cast<float4*>(cio.obs_out) : reinterpret_cast<float4*>(sto.obs) + (int64_t)(t + 1) * N * 4) + (int64_t)i * 4;
+    sink.critic_row = (last ? reinterpret_cast<float4*>(cio.critic_obs_out) : reinterpret_cast<float4*>(sto.critic_obs) + (int64_t)(t + 1) * N * 4) + (int64_t)i * 4;
+    sink.aux_ptr = (last && cio.aux_out) ? cio.aux_out + i : nullptr;
+    sink.hrow = g.hrow;
+    sink.critic_pk = critic_pk;
+    StepOut so;
+    const bool alive = racing_step_body<kNoise, false, true, kStats>(cfg, tr, e, a_t, n01, n23, draws, eps0, eps1, io, i, active, sink, so);
+    if (alive) {
+      if (kStats && !so.reset) {
+#pragma unroll
+        for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k) { if (k < 4) (&eps0.x)[k] += so.terms[k] * cfg.dt; else (&eps1.x)[k - 4] += so.terms[k] * cfg.dt; }
+      }
+      any_reset |= so.reset;
+      any_noise_dirty |= so.noise_dirty;
+      last_noise_dirty = so.noise_dirty;
+      // ---- PPO.process_env_step (ppo.py:85-97) + add_transitions: bootstrap on time-outs with V(s_t)
+      sto.rewards[tn] = so.reward + cio.gamma * (value * (so.time_out ? 1.0f : 0.0f));
+      sto.dones[tn] = so.reset ? 1 : 0;
+      sto.values[tn] = value;
+      // ---- episode book keeping of the runner (on_policy_runner.py:160-173)
+      epacc.x += so.reward;
+      epacc.y += 1.0f;
+      if (so.reset) {
+        if (cio.log_accum) {
+          float* acc_row = cio.log_accum + (size_t)((i >> 5) & (GR_LOG_SHARDS - 1)) * GR_LOG_SLOTS;
+          atomicAdd(acc_row + GR_LOG_EP_REWARD, epacc.x);
+          atomicAdd(acc_row + GR_LOG_EP_LENGTH, epacc.y);
+        }
+        epacc = make_float2(0.f, 0.f);
+      }
+    }
+  }
+
+  // ---- V(observation after the last step) for the GAE bootstrap (ppo.py:99-100)
+  write_x_row(g.hrow, critic_pk[0], critic_pk[1]);
+  const float last_value = run_net(g, w_smem + kNetBytes, w_addr + kNetBytes).x;
+  if (active) {
+    cio.last_values[i] = last_value;
+    // ---- env state -> HBM (once per rollout).  Every env that reset at ANY step rewrote its read-mostly planes: the
+    // caller clears GR_LAUNCH_PREFETCH for the next single-step launch (env.py).
+    store_env<kNoise>(e, tile, any_reset, any_noise_dirty);
+    if (kNoise && any_noise_dirty && !last_noise_dirty) st_plane(tile, PL_ANGACC, pack(e.aacc, 0.0f));   // the flag means "rewritten by the LAST step"
+    if (kStats) { st_plane(tile, PL_EPSUM0, eps0); st_plane(tile, PL_EPSUM1, eps1); }
+    if (cio.episode_acc) reinterpret_cast<float2*>(cio.episode_acc)[i] = epacc;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(*tmem_slot, G * kHid < 32 ? 32 : G * kHid);
+}
+
+}  // namespace gr
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace gr;
+
+static inline bool bad16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
+
+extern "C" int64_t gr_policy_packed_bytes(void) { return 2 * (int64_t)kNetBytes; }
+
+extern "C" int gr_policy_pack(const GrMlp* actor, const GrMlp* critic, void* packed, void* stream) {
+  if (!actor || !critic || !packed) return GR_ERR_NULL;
+  for (const GrMlp* m : {actor, critic}) {
+    if (!m->w1 || !m->b1 || !m->w2 || !m->b2 || !m->w3 || !m->b3) return GR_ERR_NULL;
+    if (m->in_dim != kObsDim || m->hidden != kHid || m->out_dim < 1 || m->out_dim > 4) return GR_ERR_SIZE;
+  }
+  if (bad16(packed)) return GR_ERR_ALIGN;
+  policy_pack_kernel<<<dim3((kHid * kHid + 255) / 256, 2), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*actor, *critic, static_cast<uint8_t*>(packed));
+  return (int)cudaGetLastError();
+}
+
+template <int G, bool kNoise, bool kStats>
+static int launch_collect(const GrConfig* cfg, const GrTrack* tr, const GrState* st, const GrRandom* rng, const GrPolicy* pol, const GrStorage* sto,
+                          const GrCollectIO* io, cudaStream_t s) {
+  int types = ((G * kTileEnvs + 255) / 256) * st->max_types_per_block;
+  if (types > tr->types) types = tr->types;
+  size_t track_bytes = (size_t)types * tr->levels * (tr->gates + 1) * sizeof(float4);
+  const size_t fixed = 2 * (size_t)kNetBytes + (size_t)G * kHBytes + 128;
+  const int track_in_smem = fixed + track_bytes <= 227 * 1024;
+  if (!track_in_smem) track_bytes = 0;
+  const size_t bytes = fixed + track_bytes;
+  auto kernel = ppo_collect_kernel<G, kNoise, kStats>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return (int)e;
+  const int grid = (st->num_envs + G * kTileEnvs - 1) / (G * kTileEnvs);
+  kernel<<<grid, G * kTileEnvs, bytes, s>>>(*cfg, *tr, *st, *rng, *pol, *sto, *io, track_in_smem);
+  return (int)cudaGetLastError();
+}
+
+template <int G>
+static int dispatch_collect(const GrConfig* cfg, const GrTrack* tr, const GrState* st, const GrRandom* rng, const GrPolicy* pol, const GrStorage* sto,
+                            const GrCollectIO* io, cudaStream_t s) {
+  const bool stats = st->num_planes == GR_NUM_PLANES_WITH_STATS;
+  if (cfg->add_cmd_noise) return stats ? launch_collect<G, true, true>(cfg, tr, st, rng, pol, sto, io, s) : launch_collect<G, true, false>(cfg, tr, st, rng, pol, sto, io, s);
+  return stats ? launch_collect<G, false, true>(cfg, tr, st, rng, pol, sto, io, s) : launch_collect<G, false, false>(cfg, tr, st, rng, pol, sto, io, s);
+}
+
+extern "C" int gr_ppo_collect(const GrConfig* cfg, const GrTrack* track, const GrState* st, const GrRandom* rng, const GrPolicy* policy,
+                              const GrStorage* storage, const GrCollectIO* io, void* stream) {
+  if (!cfg || !track || !st || !rng || !policy || !storage || !io) return GR_ERR_NULL;
+  if (!st->planes || !track->rows || !st->chunk_types || !policy->packed || !policy->sigma) return GR_ERR_NULL;
+  if (!io->obs0 || !io->critic_obs0 || !io->obs_out || !io->critic_obs_out || !io->last_values) return GR_ERR_NULL;
+  if (!storage->obs || !storage->critic_obs || !storage->actions || !storage->rewards || !storage->dones || !storage->values || !storage->log_prob ||
+      !storage->mu || !storage->sigma)
+    return GR_ERR_NULL;
+  if (rng->rnd) return GR_ERR_CONFIG;                     // the fused path draws in-kernel (Philox) only
+  if (st->num_envs <= 0 || storage->N != st->num_envs || storage->T < 1) return GR_ERR_SIZE;
+  if (storage->obs_dim != kObsDim || storage->critic_dim != kObsDim || storage->act_dim != GR_NUM_ACTIONS) return GR_ERR_SIZE;
+  if (st->num_planes != GR_NUM_PLANES && st->num_planes != GR_NUM_PLANES_WITH_STATS) return GR_ERR_SIZE;
+  if (st->plane_stride < ((st->num_envs + 31) & ~31)) return GR_ERR_SIZE;
+  if (track->types < 1 || track->types > 32 || track->levels < 1 || track->levels > 64 || track->gates < 1 || track->gates > GR_MAX_GATES) return GR_ERR_SIZE;
+  if (st->max_types_per_block < 1 || st->max_types_per_block > track->types) return GR_ERR_SIZE;
+  if (policy->negative_slope < 0.0f || policy->negative_slope > 1.0f) return GR_ERR_CONFIG;
+  if (bad16(st->planes) || bad16(track->rows) || bad16(policy->packed) || bad16(policy->sigma) || bad16(io->obs0) || bad16(io->critic_obs0) ||
+      bad16(io->obs_out) || bad16(io->critic_obs_out) || bad16(storage->obs) || bad16(storage->critic_obs) || bad16(storage->actions) ||
+      bad16(storage->mu) || bad16(storage->sigma) || (io->episode_acc && (reinterpret_cast<uintptr_t>(io->episode_acc) & 7u)))
+    return GR_ERR_ALIGN;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int G = io->groups_per_cta;
+  if (G == 0) {            // smallest CTA that still fits the rollout in one wave of 148 SMs
+    const int tiles = (st->num_envs + kTileEnvs - 1) / kTileEnvs;
+    G = tiles <= 148 ? 1 : (tiles <= 2 * 148 ? 2 : 4);
+  }
+  switch (G) {
+    case 1: return dispatch_collect<1>(cfg, track, st, rng, policy, storage, io, s);
+    case 2: return dispatch_collect<2>(cfg, track, st, rng, policy, storage, io, s);
+    case 4: return dispatch_collect<4>(cfg, track, st, rng, policy, storage, io, s);
+    default: return GR_ERR_SIZE;
+  }
+}

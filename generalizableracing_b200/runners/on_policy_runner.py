@@ -43,6 +43,11 @@ class OnPolicyRunner:
         self.obs_normalizer = torch.nn.Identity()
         self.privileged_obs_normalizer = torch.nn.Identity()
         self.alg.init_storage(self.training_type, self.env.num_envs, self.num_steps_per_env, [num_obs], [num_privileged_obs], [self.env.num_actions])
+        # opt-in: the whole rollout loop as one launch (collect.py / csrc/ppo_collect.cu); policy inference on the tensor cores
+        self.collector = None
+        if self.cfg.get("fused_collection", False):
+            from ..collect import FusedCollector
+            self.collector = FusedCollector(self.env, policy, self.alg.storage, gamma=self.alg.gamma, groups_per_cta=int(self.cfg.get("fused_groups_per_cta", 0)))
         self.log_dir = log_dir
         self.tot_timesteps = 0
         self.tot_time = 0
@@ -74,7 +79,13 @@ class OnPolicyRunner:
             start = time.time()
             ep_infos = []
             with torch.inference_mode():
-                for _ in range(self.num_steps_per_env):
+                if self.collector is not None:
+                    self.collector.pack()
+                    obs, privileged_obs, last_values = self.collector.collect()
+                    st = self.collector.episode_stats()
+                    ep_rew_sum += st[0]; ep_len_sum += st[1]; ep_count += st[2]
+                    infos = self.env.extras
+                for _ in range(self.num_steps_per_env if self.collector is None else 0):
                     actions = self.alg.act(obs, privileged_obs)
                     obs, rewards, dones, infos = self.env.step(actions)
                     privileged_obs = infos["observations"][self.privileged_obs_type] if self.privileged_obs_type else obs
@@ -93,7 +104,7 @@ class OnPolicyRunner:
                 stop = time.time()
                 collection_time = stop - start
                 start = stop
-                self.alg.compute_returns(privileged_obs)
+                self.alg.compute_returns(privileged_obs, last_values=None if self.collector is None else last_values)
             loss_dict = self.alg.update()
             stop = time.time()
             learn_time = stop - start

@@ -161,6 +161,8 @@ typedef struct GrStepIO {
 #define GR_LOG_SUM_EPSUM 2          /* +k: sum over reset envs of episode sum of reward term k (6) */
 #define GR_LOG_NUM_TIMEOUT 8
 #define GR_LOG_NUM_TERMINATED 9
+#define GR_LOG_EP_REWARD 10         /* gr_ppo_collect: sum over finished episodes of the episode reward (runner book keeping) */
+#define GR_LOG_EP_LENGTH 11         /* gr_ppo_collect: sum over finished episodes of the episode length                    */
 #define GR_LOG_SLOTS 16
 #define GR_LOG_SHARDS 256          /* accumulator rows (64 B each), picked by warp id: spreads the RED traffic over L2 */
 
@@ -244,6 +246,42 @@ typedef struct GrMiniBatch {
   float* log_prob; float* mu; float* sigma;
 } GrMiniBatch;
 int gr_storage_gather(const GrStorage* s, const int64_t* indices, int32_t B, const GrMiniBatch* out, void* stream);
+
+/* ---- fused PPO collection (policy MLP on the tensor cores + env.step + add_transitions in one launch) --------------
+ * Replaces the rollout loop of OnPolicyRunner.learn (S/rsl_rl/ext/runners/on_policy_runner.py:141-175) for the racing
+ * task's state-only ActorCritic (QD/agents/rsl_rl_ppo_cfg.py:22-27: 16 -> 128 -> 128 -> 4 / 1, leaky relu, scalar std):
+ * T = storage->T steps of PPO.act (S/rsl_rl/ext/algorithms/ppo.py:71-83), env.step, PPO.process_env_step (:85-97) and
+ * RolloutStorage.add_transitions (S/rsl_rl/ext/storage/rollout_storage.py:71-88), then last_values = V(last critic obs)
+ * (ppo.py:99-100).  Env semantics are those of gr_step_fwd bit for bit (Philox draws of step rng->step + t); the MLPs
+ * run with fp16 operands and fp32 accumulation on tcgen05 (measured error vs the fp32 torch modules: DESIGN.md). */
+#define GR_PHILOX_CALL_ACTION 16    /* Philox call index of the 4 action-noise normals (calls 0..12 belong to env.step) */
+typedef struct GrMlp {               /* torch.nn.Linear parameters, row-major [out][in] fp32, device pointers */
+  const float* w1; const float* b1;  /* [hidden, in_dim], [hidden] */
+  const float* w2; const float* b2;  /* [hidden, hidden], [hidden] */
+  const float* w3; const float* b3;  /* [out_dim, hidden], [out_dim] */
+  int32_t in_dim, hidden, out_dim;   /* 16, 128, 1..4 */
+} GrMlp;
+typedef struct GrPolicy {
+  const void* packed;                /* gr_policy_packed_bytes() bytes written by gr_policy_pack (actor, then critic) */
+  const float* sigma;                /* device [4]: ActorCritic.std (or exp(log_std)); 16-byte aligned */
+  float negative_slope;              /* leaky-relu slope in [0,1] (nn.LeakyReLU default 0.01; 0 = relu) */
+} GrPolicy;
+typedef struct GrCollectIO {
+  const float* obs0;                 /* [N,16] policy observation the rollout starts from (last step's output) */
+  const float* critic_obs0;          /* [N,16] */
+  float* obs_out;                    /* [N,16] observations after the last step (must not alias obs0) */
+  float* critic_obs_out;             /* [N,16] */
+  float* aux_out;                    /* [N] optional */
+  float* last_values;                /* [N] V(critic_obs_out) */
+  float* episode_acc;                /* [N,2] running (reward sum, length) of each env's current episode; in/out, optional */
+  float* log_accum;                  /* [GR_LOG_SHARDS][GR_LOG_SLOTS], optional (see GR_LOG_*) */
+  float gamma;                       /* time-out bootstrap r += gamma * V(s_t) * time_out */
+  int32_t groups_per_cta;            /* 128-env tiles per thread block: 1, 2, 4 or 0 = pick (fewest that fit one wave) */
+} GrCollectIO;
+int64_t gr_policy_packed_bytes(void);
+int gr_policy_pack(const GrMlp* actor, const GrMlp* critic, void* packed, void* stream);
+int gr_ppo_collect(const GrConfig* cfg, const GrTrack* track, const GrState* st, const GrRandom* rng, const GrPolicy* policy,
+                   const GrStorage* storage, const GrCollectIO* io, void* stream);
 
 /* ---- env.step() with HOST buffers (the e2e boundary) -------------------------------------------------------------
  * Same call as gr_step_fwd for a caller whose actions / observations live in host memory: replaces

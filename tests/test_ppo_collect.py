@@ -1,0 +1,161 @@
+"""gr_ppo_collect (fused PPO collection: tensor-core policy MLPs + env.step + add_transitions in one launch) against the
+step-by-step path: the env / storage side must be BIT-IDENTICAL given the same actions; the policy outputs are checked
+against the fp32 torch modules (fp16-operand tolerance, written below) and against an fp16-emulating torch model."""
+import pytest
+import torch
+
+from generalizableracing_b200.config import RacingCfg
+from generalizableracing_b200.tracks import synthetic_track_table
+
+pytestmark = pytest.mark.gpu
+
+# policy inference runs with fp16 operands (11-bit significands) and fp32 accumulation: |err| <= TOL_ABS + TOL_REL * |ref|
+TOL_ABS, TOL_REL = 1e-2, 1e-2          # worst element; the mean error is asserted below 1e-3 (measured ~2e-4)
+
+
+def _setup(N, T, stage=1, seed=11, groups=0, stats=True, weight_scale=1.0):
+    from generalizableracing_b200.collect import FusedCollector
+    from generalizableracing_b200.env import RacingVecEnv
+    from generalizableracing_b200.modules import ActorCritic
+    from generalizableracing_b200.storage import RolloutStorage
+    cfg, table = RacingCfg.for_stage(stage), synthetic_track_table()
+    torch.manual_seed(seed)
+    pol = ActorCritic(16, 16, 4).cuda()
+    with torch.no_grad():
+        for p in pol.parameters():
+            if p.dim() == 2:
+                p.mul_(weight_scale)
+        pol.std.copy_(torch.tensor([0.9, 0.5, 0.7, 1.1]))
+    envs = []
+    for _ in range(2):
+        e = RacingVecEnv(cfg, table, N, seed=seed, episode_stats=stats)
+        e.reset()
+        e.episode_length_buf = torch.randint(0, cfg.max_episode_length, (N,), generator=torch.Generator().manual_seed(seed), dtype=torch.int32)
+        envs.append(e)
+    stos = [RolloutStorage("rl", N, T, [16], [16], [4], device="cuda:0") for _ in range(2)]
+    col = FusedCollector(envs[0], pol, stos[0], gamma=0.99, groups_per_cta=groups)
+    col.pack()
+    return cfg, pol, envs, stos, col
+
+
+def _emulate_fp16_mlp(seq, x):
+    """The kernel's arithmetic in torch: fp16 operands, fp32 accumulation, activations rounded to fp16 between layers,
+    layer-2 bias added in fp16, leaky relu as max(h, h * slope) in fp16."""
+    l1, a1, l2, a2, l3 = seq
+    slope = torch.tensor(getattr(a1, "negative_slope", 0.0), dtype=torch.float16, device=x.device)
+    b1 = l1.bias.half().float() + (l1.bias - l1.bias.half().float()).half().float()
+    h = (x.half().float() @ l1.weight.half().float().T + b1).half()
+    h = torch.maximum(h, h * slope)
+    h = ((h.float() @ l2.weight.half().float().T).half() + l2.bias.half())
+    h = torch.maximum(h, h * slope)
+    return h.float() @ l3.weight.half().float().T + l3.bias
+
+
+@pytest.mark.parametrize("N,T,groups", [(1000, 24, 1), (1000, 24, 4), (4096, 24, 0), (300, 5, 2)])
+def test_fused_collection_matches_step_by_step(cuda_lib, N, T, groups):
+    cfg, pol, (env_f, env_u), (sto_f, sto_u), col = _setup(N, T, groups=groups)
+    obs_u, ex = env_u.get_observations()
+    critic_u = ex["observations"]["critic"]
+    obs_f, critic_f, last_values = col.collect()
+    torch.cuda.synchronize()
+    sigma = pol.std.detach()
+    with torch.no_grad():
+        for t in range(T):
+            # --- the fused kernel saw the same observations ...
+            assert torch.equal(sto_f.observations[t], obs_u), t
+            assert torch.equal(sto_f.privileged_observations[t], critic_u), t
+            # --- ... its tensor-core MLPs agree with the fp32 modules within fp16-operand accuracy, and tightly with the emulation
+            mu_ref, v_ref = pol.actor(obs_u), pol.critic(critic_u)
+            mu, v, a = sto_f.mu[t], sto_f.values[t], sto_f.actions[t]
+            assert ((mu - mu_ref).abs() <= TOL_ABS + TOL_REL * mu_ref.abs()).all(), (t, float((mu - mu_ref).abs().max()))
+            assert ((v - v_ref).abs() <= TOL_ABS + TOL_REL * v_ref.abs()).all(), (t, float((v - v_ref).abs().max()))
+            assert float((mu - mu_ref).abs().mean()) < 1e-3 and float((v - v_ref).abs().mean()) < 1e-3
+            mu_em, v_em = _emulate_fp16_mlp(pol.actor, obs_u), _emulate_fp16_mlp(pol.critic, critic_u)
+            assert float((mu - mu_em).abs().mean()) < 2e-5 and float((v - v_em).abs().mean()) < 2e-5
+            assert float((mu - mu_em).abs().max()) < 2e-3 and float((v - v_em).abs().max()) < 2e-3
+            assert torch.equal(sto_f.sigma[t], sigma.expand(N, 4))
+            lp_ref = torch.distributions.Normal(mu, sigma).log_prob(a).sum(-1, keepdim=True)
+            assert float((sto_f.actions_log_prob[t] - lp_ref).abs().max()) < 2e-5
+            # --- stepping the reference env with the SAME actions reproduces the stored transition bit for bit
+            tr = sto_u.Transition()
+            tr.observations, tr.privileged_observations = obs_u, critic_u
+            tr.actions, tr.values, tr.actions_log_prob, tr.action_mean, tr.action_sigma = a, v, sto_f.actions_log_prob[t], mu, sto_f.sigma[t]
+            obs_u, rew, dones, infos = env_u.step(a)
+            critic_u = infos["observations"]["critic"]
+            tr.rewards, tr.dones, tr.time_outs, tr.gamma = rew, dones, infos["time_outs"], 0.99
+            sto_u.add_transitions(tr)
+    torch.cuda.synchronize()
+    for name in ("observations", "privileged_observations", "actions", "rewards", "dones", "values", "actions_log_prob", "mu", "sigma"):
+        assert torch.equal(getattr(sto_f, name), getattr(sto_u, name)), name
+    assert torch.equal(env_f.planes, env_u.planes)
+    assert torch.equal(obs_f, obs_u) and torch.equal(critic_f, critic_u)
+    assert torch.equal(env_f._log_accum.sum(0)[:10], env_u._log_accum.sum(0)[:10])
+    with torch.no_grad():
+        lv_ref = pol.critic(critic_u)
+    assert ((last_values - lv_ref).abs() <= TOL_ABS + TOL_REL * lv_ref.abs()).all()
+    # --- the action noise is a fresh standard normal per env, step and component
+    eps = ((sto_f.actions - sto_f.mu) / sto_f.sigma).reshape(-1, 4)
+    assert float(eps.mean().abs()) < 0.03 and float((eps.std() - 1).abs()) < 0.03
+    assert float(torch.corrcoef(eps.T).fill_diagonal_(0).abs().max()) < 0.05
+    # --- and the env keeps working step by step afterwards (prefetch flag handling)
+    a = torch.zeros(N, 4, device="cuda")
+    o1 = env_f.step(a)[0].clone()
+    o2 = env_u.step(a)[0].clone()
+    assert torch.equal(o1, o2)
+
+
+def test_second_rollout_continues_the_first(cuda_lib):
+    """Two fused rollouts of T == one of 2T (state, Philox counters, episode accumulators carry over)."""
+    N, T = 512, 6
+    cfg, pol, (env_a, env_b), (sto_a, _), col_a = _setup(N, T)
+    from generalizableracing_b200.collect import FusedCollector
+    from generalizableracing_b200.storage import RolloutStorage
+    sto_b = RolloutStorage("rl", N, 2 * T, [16], [16], [4], device="cuda:0")
+    col_b = FusedCollector(env_b, pol, sto_b, gamma=0.99)
+    col_b.pack()
+    col_b.collect()
+    col_a.collect()
+    first = {k: getattr(sto_a, k).clone() for k in ("observations", "actions", "rewards", "dones", "values")}
+    sto_a.clear()
+    col_a.collect()
+    for k, v in first.items():
+        assert torch.equal(v, getattr(sto_b, k)[:T]), k
+        assert torch.equal(getattr(sto_a, k), getattr(sto_b, k)[T:]), k
+    assert torch.equal(env_a.planes, env_b.planes)
+    assert torch.equal(col_a.episode_acc, col_b.episode_acc)
+    assert torch.allclose(col_a.episode_stats(), col_b.episode_stats(), rtol=1e-5)
+
+
+def test_episode_book_keeping_matches_the_runner(cuda_lib):
+    """GR_LOG_EP_REWARD / EP_LENGTH reproduce on_policy_runner.py:160-173 computed from the stored raw rewards / dones."""
+    N, T = 2048, 24
+    cfg, pol, (env_f, env_u), (sto_f, sto_u), col = _setup(N, T)
+    col.collect()
+    stats = col.episode_stats()
+    cur_r, cur_l = torch.zeros(N, device="cuda"), torch.zeros(N, device="cuda")
+    tot = torch.zeros(3, device="cuda", dtype=torch.float64)
+    for t in range(T):
+        a = sto_f.actions[t]
+        _, rew, dones, _ = env_u.step(a)
+        cur_r += rew
+        cur_l += 1
+        d = dones > 0
+        tot += torch.stack([(cur_r * d).sum(), (cur_l * d).sum(), d.sum()]).double()
+        cur_r[d] = 0
+        cur_l[d] = 0
+    assert int(stats[2]) == int(tot[2]) > 0
+    assert torch.allclose(stats.double(), tot, rtol=1e-4)
+    assert torch.allclose(col.episode_acc[:, 0], cur_r, atol=1e-5) and torch.equal(col.episode_acc[:, 1], cur_l)
+
+
+def test_collector_refuses_what_it_cannot_run(cuda_lib):
+    from generalizableracing_b200.collect import FusedCollector
+    from generalizableracing_b200.env import RacingVecEnv
+    from generalizableracing_b200.modules import ActorCritic
+    from generalizableracing_b200.storage import RolloutStorage
+    env = RacingVecEnv(RacingCfg.for_stage(1), synthetic_track_table(), 256)
+    sto = RolloutStorage("rl", 256, 4, [16], [16], [4], device="cuda:0")
+    with pytest.raises(ValueError):
+        FusedCollector(env, ActorCritic(16, 16, 4, activation="elu").cuda(), sto, 0.99)
+    with pytest.raises(ValueError):
+        FusedCollector(env, ActorCritic(16, 16, 4, actor_hidden_dims=(256, 128)).cuda(), sto, 0.99)
