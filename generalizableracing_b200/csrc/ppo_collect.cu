@@ -94,27 +94,37 @@ __device__ __forceinline__ void write_x_row(uint8_t* hrow, uint4 c0, uint4 c1) {
   *reinterpret_cast<uint4*>(hrow + 3 * kChunkA) = make_uint4(0u, 0u, 0u, 0u);
 }
 
-// hidden-layer epilogue of one env row: D[row][0..127] (TMEM) -> (+ bias) -> leaky relu -> fp16 -> the row of the next A operand
+// 8 accumulator columns (fp32 bits) -> (+ bias) -> leaky relu -> 8 halfs
+template <bool kBias>
+__device__ __forceinline__ uint4 activate8(const uint32_t* r, const uint4* __restrict__ bias, int chunk, __half2 slope) {
+  __half2 h[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1]));
+  if (kBias) {
+    const uint4 b = bias[chunk];
+    h[0] = __hadd2(h[0], bits_h2(b.x)); h[1] = __hadd2(h[1], bits_h2(b.y)); h[2] = __hadd2(h[2], bits_h2(b.z)); h[3] = __hadd2(h[3], bits_h2(b.w));
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) h[q] = __hmax2(h[q], __hmul2(h[q], slope));
+  return make_uint4(h2_bits(h[0]), h2_bits(h[1]), h2_bits(h[2]), h2_bits(h[3]));
+}
+
+// hidden-layer epilogue of one env row: D[row][0..127] (TMEM) -> (+ bias) -> leaky relu -> fp16 -> the row of the next A
+// operand.  The TMEM loads are double-buffered (16 columns each): the next load is in flight while this one is processed.
 template <bool kBias>
 __device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint8_t* hrow, const uint4* __restrict__ bias, __half2 slope) {
+  uint32_t ra[16], rb[16];
+  tmem_ld_x16(taddr, ra);
 #pragma unroll 1
-  for (int c4 = 0; c4 < 4; ++c4) {
-    uint32_t r[32];
-    tmem_ld_x32(taddr + c4 * 32, r);
+  for (int c = 0; c < 8; c += 2) {          // c = index of the 16-column block held by ra
     tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      __half2 h[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(__uint_as_float(r[8 * j + 2 * q]), __uint_as_float(r[8 * j + 2 * q + 1]));
-      if (kBias) {
-        const uint4 b = bias[c4 * 4 + j];
-        h[0] = __hadd2(h[0], bits_h2(b.x)); h[1] = __hadd2(h[1], bits_h2(b.y)); h[2] = __hadd2(h[2], bits_h2(b.z)); h[3] = __hadd2(h[3], bits_h2(b.w));
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) h[q] = __hmax2(h[q], __hmul2(h[q], slope));
-      *reinterpret_cast<uint4*>(hrow + (c4 * 4 + j) * kChunkA) = make_uint4(h2_bits(h[0]), h2_bits(h[1]), h2_bits(h[2]), h2_bits(h[3]));
-    }
+    tmem_ld_x16(taddr + (c + 1) * 16, rb);
+    *reinterpret_cast<uint4*>(hrow + (2 * c) * kChunkA) = activate8<kBias>(ra, bias, 2 * c, slope);
+    *reinterpret_cast<uint4*>(hrow + (2 * c + 1) * kChunkA) = activate8<kBias>(ra + 8, bias, 2 * c + 1, slope);
+    tmem_ld_wait();
+    if (c + 2 < 8) tmem_ld_x16(taddr + (c + 2) * 16, ra);
+    *reinterpret_cast<uint4*>(hrow + (2 * c + 2) * kChunkA) = activate8<kBias>(rb, bias, 2 * c + 2, slope);
+    *reinterpret_cast<uint4*>(hrow + (2 * c + 3) * kChunkA) = activate8<kBias>(rb + 8, bias, 2 * c + 3, slope);
   }
 }
 
@@ -141,47 +151,51 @@ struct GroupCtx {
   __half2 slope;
 };
 
-// All 128 threads of the group call this with their X row already written.  Returns the first 4 layer-3 outputs (+ bias).
-__device__ __forceinline__ float4 run_net(GroupCtx& g, const uint8_t* net_smem, uint32_t net_addr) {
-  // ---- layer 1: [128 x 32] . W1
-  fence_proxy_async_smem();
-  tc_fence_before_sync();
+// A layer = [every thread of the group has written its operand row] -> group barrier -> one thread issues the MMAs ->
+// ... independent work ... -> stage_wait -> the accumulator is readable.
+enum Layer : int { kL1 = 0, kL2 = 1, kL3 = 2 };
+__device__ __forceinline__ void stage_issue(const GroupCtx& g, uint32_t net_addr, const int layer) {
+  fence_proxy_async_smem();                 // this thread's st.shared operand rows -> async proxy
+  tc_fence_before_sync();                   // this thread's tcgen05.ld of the columns about to be overwritten
   bar_sync(g.bar_id, kTileEnvs);
-  if (g.issuer) issue_layer(g.d_tmem, g.hbuf_addr, net_addr + kW1Off, kK1 / 16, kHid * 16, make_idesc_f16(kTileEnvs, kHid), g.bar);
-  mbar_wait(g.bar, g.phase); g.phase ^= 1u;
+  if (g.issuer) {
+    if (layer == kL1) issue_layer(g.d_tmem, g.hbuf_addr, net_addr + kW1Off, kK1 / 16, kHid * 16, make_idesc_f16(kTileEnvs, kHid), g.bar);
+    else if (layer == kL2) issue_layer(g.d_tmem, g.hbuf_addr, net_addr + kW2Off, kHid / 16, kHid * 16, make_idesc_f16(kTileEnvs, kHid), g.bar);
+    else issue_layer(g.d_tmem, g.hbuf_addr, net_addr + kW3Off, kHid / 16, kOutPad * 16, make_idesc_f16(kTileEnvs, kOutPad), g.bar);
+  }
+}
+__device__ __forceinline__ void stage_wait(GroupCtx& g) {
+  mbar_wait(g.bar, g.phase);
+  g.phase ^= 1u;
   tc_fence_after_sync();
-  hidden_epilogue<false>(g.taddr, g.hrow, nullptr, g.slope);
-  // ---- layer 2: [128 x 128] . W2
-  fence_proxy_async_smem();
-  tc_fence_before_sync();
-  bar_sync(g.bar_id, kTileEnvs);
-  if (g.issuer) issue_layer(g.d_tmem, g.hbuf_addr, net_addr + kW2Off, kHid / 16, kHid * 16, make_idesc_f16(kTileEnvs, kHid), g.bar);
-  mbar_wait(g.bar, g.phase); g.phase ^= 1u;
-  tc_fence_after_sync();
-  hidden_epilogue<true>(g.taddr, g.hrow, reinterpret_cast<const uint4*>(net_smem + kB2Off), g.slope);
-  // ---- layer 3: [128 x 128] . W3 (N = 16)
-  fence_proxy_async_smem();
-  tc_fence_before_sync();
-  bar_sync(g.bar_id, kTileEnvs);
-  if (g.issuer) issue_layer(g.d_tmem, g.hbuf_addr, net_addr + kW3Off, kHid / 16, kOutPad * 16, make_idesc_f16(kTileEnvs, kOutPad), g.bar);
-  mbar_wait(g.bar, g.phase); g.phase ^= 1u;
-  tc_fence_after_sync();
+}
+// first 4 outputs of layer 3 (+ fp32 bias)
+__device__ __forceinline__ float4 read_head(const GroupCtx& g, const uint8_t* net_smem) {
   uint32_t r[4];
   tmem_ld_x4(g.taddr, r);
   tmem_ld_wait();
-  tc_fence_before_sync();                     // the next layer-1 MMA of this group overwrites these columns
   const float4 b3 = *reinterpret_cast<const float4*>(net_smem + kB3Off);
   return make_float4(__uint_as_float(r[0]) + b3.x, __uint_as_float(r[1]) + b3.y, __uint_as_float(r[2]) + b3.z, __uint_as_float(r[3]) + b3.w);
 }
+// a whole net with nothing overlapped (last_values pass)
+__device__ __forceinline__ float4 run_net(GroupCtx& g, const uint8_t* net_smem, uint32_t net_addr) {
+  stage_issue(g, net_addr, kL1); stage_wait(g);
+  hidden_epilogue<false>(g.taddr, g.hrow, nullptr, g.slope);
+  stage_issue(g, net_addr, kL2); stage_wait(g);
+  hidden_epilogue<true>(g.taddr, g.hrow, reinterpret_cast<const uint4*>(net_smem + kB2Off), g.slope);
+  stage_issue(g, net_addr, kL3); stage_wait(g);
+  return read_head(g, net_smem);
+}
 
 // observation sink of the fused kernel: fp32 rows go to the rollout storage (or to the "next observation" buffers after
-// the last step); the policy row also becomes the next layer-1 operand, the critic row waits in 8 registers as fp16
+// the last step); both rows also wait in 8 registers each, as fp16, to become layer-1 operands once the group's
+// activation tile is free (the env step runs while the critic's layer-2 MMAs still read it)
 struct FusedObsSink {
   float4* obs_row; float4* critic_row; float* aux_ptr;
-  uint8_t* hrow; uint4* critic_pk;     // critic_pk -> two uint4 in the caller's registers
+  uint4* policy_pk; uint4* critic_pk;     // -> two uint4 each in the caller's registers
   __device__ __forceinline__ void policy(int, float4 o0, float4 o1, float4 o2, float4 o3) const {
     __stcs(obs_row + 0, o0); __stcs(obs_row + 1, o1); __stcs(obs_row + 2, o2); __stcs(obs_row + 3, o3);
-    write_x_row(hrow, pack8(o0, o1), pack8(o2, o3));
+    policy_pk[0] = pack8(o0, o1); policy_pk[1] = pack8(o2, o3);
   }
   __device__ __forceinline__ bool wants_critic() const { return true; }
   __device__ __forceinline__ void critic(int, float4 c0, float4 c1, float4 c2, float4 c3) const {
@@ -272,48 +286,72 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
     critic_pk[0] = pack8(c0, c1); critic_pk[1] = pack8(c2, c3);
   }
 
+  const uint8_t* critic_smem = w_smem + kNetBytes;
+  const uint32_t critic_addr = w_addr + kNetBytes;
+  const uint4* actor_b2 = reinterpret_cast<const uint4*>(w_smem + kB2Off);
+  const uint4* critic_b2 = reinterpret_cast<const uint4*>(critic_smem + kB2Off);
+  uint4 policy_pk[2] = {critic_pk[0], critic_pk[1]};       // (lanes past the last env never refresh it)
+
+  // Per step: actor L1 L2 L3 -> sample -> critic L1 L2 L3, env.step.  Work that does not depend on the MMA in flight is
+  // placed between its issue and its wait: the Philox draws under actor L1, the storage rows of the action under critic L1,
+  // the whole env step under critic L2 (the longest MMA), the episode sums under critic L3.
 #pragma unroll 1
   for (int t = 0; t < T; ++t) {
     const int64_t tn = (int64_t)t * N + i;
     // ---- PPO.act: actor mean, sample, log-prob (ppo.py:71-83; Normal(mean, std).sample() / .log_prob().sum(-1))
-    const float4 mu = run_net(g, w_smem, w_addr);
+    stage_issue(g, w_addr, kL1);
     GrRandom rt = rng;
     rt.step = rng.step + (uint32_t)t;
     const RandSrc<true> rs(rt, li, st.env_id_offset + li);
-    float4 a_t;
-    float logp;
-    {
-      const uint4 x = rs.ph(GR_PHILOX_CALL_ACTION);
-      const float2 n0 = box_muller(x.x, x.y), n1 = box_muller(x.z, x.w);
-      a_t = make_float4(mu.x + sigma.x * n0.x, mu.y + sigma.y * n0.y, mu.z + sigma.z * n1.x, mu.w + sigma.w * n1.y);
-      const float dx = a_t.x - mu.x, dy = a_t.y - mu.y, dz = a_t.z - mu.z, dw = a_t.w - mu.w;
-      const float kLogSqrt2Pi = 0.91893853320467274178f;
-      logp = (-(dx * dx) / (2.0f * sigma.x * sigma.x) - log_sigma.x - kLogSqrt2Pi) + (-(dy * dy) / (2.0f * sigma.y * sigma.y) - log_sigma.y - kLogSqrt2Pi) +
-             (-(dz * dz) / (2.0f * sigma.z * sigma.z) - log_sigma.z - kLogSqrt2Pi) + (-(dw * dw) / (2.0f * sigma.w * sigma.w) - log_sigma.w - kLogSqrt2Pi);
-    }
-    if (active) {
-      __stcs(reinterpret_cast<float4*>(sto.actions) + tn, a_t);
-      __stcs(reinterpret_cast<float4*>(sto.mu) + tn, mu);
-      __stcs(reinterpret_cast<float4*>(sto.sigma) + tn, sigma);
-      sto.log_prob[tn] = logp;
-    }
-    // ---- critic value of the same state
-    write_x_row(g.hrow, critic_pk[0], critic_pk[1]);
-    const float value = run_net(g, w_smem + kNetBytes, w_addr + kNetBytes).x;
-
-    // ---- env.step (same body as gr_step_fwd); its observations are the next step's operands / storage rows
     float4 n01, n23;
     rs.normals8(n01, n23);
+    float2 an0, an1;
+    {
+      const uint4 x = rs.ph(GR_PHILOX_CALL_ACTION);
+      an0 = box_muller(x.x, x.y); an1 = box_muller(x.z, x.w);
+    }
+    stage_wait(g);
+    hidden_epilogue<false>(g.taddr, g.hrow, nullptr, g.slope);
+    stage_issue(g, w_addr, kL2); stage_wait(g);
+    hidden_epilogue<true>(g.taddr, g.hrow, actor_b2, g.slope);
+    stage_issue(g, w_addr, kL3); stage_wait(g);
+    const float4 mu = read_head(g, w_smem);
+    const float4 a_t = make_float4(mu.x + sigma.x * an0.x, mu.y + sigma.y * an0.y, mu.z + sigma.z * an1.x, mu.w + sigma.w * an1.y);
+    // ---- critic value of the same state
+    write_x_row(g.hrow, critic_pk[0], critic_pk[1]);
+    stage_issue(g, critic_addr, kL1);
+    {
+      const float dx = a_t.x - mu.x, dy = a_t.y - mu.y, dz = a_t.z - mu.z, dw = a_t.w - mu.w;
+      const float kLogSqrt2Pi = 0.91893853320467274178f;
+      const float logp = (-(dx * dx) / (2.0f * sigma.x * sigma.x) - log_sigma.x - kLogSqrt2Pi) + (-(dy * dy) / (2.0f * sigma.y * sigma.y) - log_sigma.y - kLogSqrt2Pi) +
+                         (-(dz * dz) / (2.0f * sigma.z * sigma.z) - log_sigma.z - kLogSqrt2Pi) + (-(dw * dw) / (2.0f * sigma.w * sigma.w) - log_sigma.w - kLogSqrt2Pi);
+      if (active) {
+        __stcs(reinterpret_cast<float4*>(sto.actions) + tn, a_t);
+        __stcs(reinterpret_cast<float4*>(sto.mu) + tn, mu);
+        __stcs(reinterpret_cast<float4*>(sto.sigma) + tn, sigma);
+        sto.log_prob[tn] = logp;
+      }
+    }
+    stage_wait(g);
+    hidden_epilogue<false>(g.taddr, g.hrow, nullptr, g.slope);
+    stage_issue(g, critic_addr, kL2);
+
+    // ---- env.step (same body as gr_step_fwd) while the critic's layer 2 runs; its observations are the next step's
+    //      operands (kept packed in registers until the activation tile is free) and storage rows
     const Draws<true> draws{rs, nullptr};
     const bool last = t == T - 1;
     FusedObsSink sink;
     sink.obs_row = (last ? reinterpret_cast<float4*>(cio.obs_out) : reinterpret_cast<float4*>(sto.obs) + (int64_t)(t + 1) * N * 4) + (int64_t)i * 4;
     sink.critic_row = (last ? reinterpret_cast<float4*>(cio.critic_obs_out) : reinterpret_cast<float4*>(sto.critic_obs) + (int64_t)(t + 1) * N * 4) + (int64_t)i * 4;
     sink.aux_ptr = (last && cio.aux_out) ? cio.aux_out + i : nullptr;
-    sink.hrow = g.hrow;
+    sink.policy_pk = policy_pk;
     sink.critic_pk = critic_pk;
     StepOut so;
     const bool alive = racing_step_body<kNoise, false, true, kStats>(cfg, tr, e, a_t, n01, n23, draws, eps0, eps1, io, i, active, sink, so);
+
+    stage_wait(g);
+    hidden_epilogue<true>(g.taddr, g.hrow, critic_b2, g.slope);
+    stage_issue(g, critic_addr, kL3);
     if (alive) {
       if (kStats && !so.reset) {
 #pragma unroll
@@ -322,9 +360,14 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
       any_reset |= so.reset;
       any_noise_dirty |= so.noise_dirty;
       last_noise_dirty = so.noise_dirty;
+      sto.dones[tn] = so.reset ? 1 : 0;
+    }
+    stage_wait(g);
+    const float value = read_head(g, critic_smem).x;
+    write_x_row(g.hrow, policy_pk[0], policy_pk[1]);          // the tile is free again: next step's actor operand
+    if (alive) {
       // ---- PPO.process_env_step (ppo.py:85-97) + add_transitions: bootstrap on time-outs with V(s_t)
       sto.rewards[tn] = so.reward + cio.gamma * (value * (so.time_out ? 1.0f : 0.0f));
-      sto.dones[tn] = so.reset ? 1 : 0;
       sto.values[tn] = value;
       // ---- episode book keeping of the runner (on_policy_runner.py:160-173)
       epacc.x += so.reward;
@@ -342,7 +385,7 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
 
   // ---- V(observation after the last step) for the GAE bootstrap (ppo.py:99-100)
   write_x_row(g.hrow, critic_pk[0], critic_pk[1]);
-  const float last_value = run_net(g, w_smem + kNetBytes, w_addr + kNetBytes).x;
+  const float last_value = run_net(g, critic_smem, critic_addr).x;
   if (active) {
     cio.last_values[i] = last_value;
     // ---- env state -> HBM (once per rollout).  Every env that reset at ANY step rewrote its read-mostly planes: the
