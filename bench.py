@@ -436,6 +436,64 @@ def bench_extras(dev, cfg, table):
     e1.record()
     torch.cuda.synchronize(dev)
     out["add_transitions_4096_us"] = e0.elapsed_time(e1) * 1e3 / (20 * T)
+    del sto
+    out["ppo_collection"] = bench_collection(dev, cfg, table)
+    return out
+
+
+def bench_collection(dev, cfg, table, T: int = 24):
+    """PPO collection throughput INCLUDING policy inference and rollout storage (the reference's rollout loop,
+    on_policy_runner.py:141-175): fused kernel (gr_ppo_collect: tcgen05 MLPs + env.step + add_transitions, one launch per
+    rollout) vs the step-by-step path (torch ActorCritic + gr_step_fwd + gr_storage_add), C2 and C4 env counts."""
+    from generalizableracing_b200.algorithms.ppo import PPO
+    from generalizableracing_b200.collect import FusedCollector
+    from generalizableracing_b200.env import RacingVecEnv
+    from generalizableracing_b200.modules import ActorCritic
+    out = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for N in (4096, 65536):
+        env = RacingVecEnv(cfg, table, N, device=dev, seed=3)
+        env.reset()
+        env.episode_length_buf = torch.randint(0, cfg.max_episode_length, (N,), device=dev, dtype=torch.int32)
+        pol = ActorCritic(16, 16, 4).to(dev)
+        alg = PPO(pol, device=dev, gamma=0.99)
+        alg.init_storage("rl", N, T, [16], [16], [4])
+        col = FusedCollector(env, pol, alg.storage, gamma=0.99)
+        col.pack()
+
+        def fused():
+            alg.storage.clear()
+            col.collect()
+
+        def stepwise():
+            alg.storage.clear()
+            obs, ex = env.get_observations()
+            critic = ex["observations"]["critic"]
+            with torch.inference_mode():
+                for _ in range(T):
+                    a = alg.act(obs, critic)
+                    obs, r, d, info = env.step(a)
+                    critic = info["observations"]["critic"]
+                    alg.process_env_step(r, d, info)
+
+        row = {}
+        for name, fn, reps in (("fused", fused, 20), ("step_by_step", stepwise, 3)):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / reps
+            row[name] = {"ms_per_rollout": ms, "us_per_step": ms * 1e3 / T, "env_steps_per_s": N * T / (ms * 1e-3)}
+        row["speedup"] = row["step_by_step"]["ms_per_rollout"] / row["fused"]["ms_per_rollout"]
+        out[str(N)] = row
+        env.close()
+        del env, alg, col
+        torch.cuda.empty_cache()
+    out["note"] = "env-steps/s of a 24-step rollout incl. actor+critic inference, sampling, log-prob, time-out bootstrap and storage rows; fused = 1 launch"
     return out
 
 

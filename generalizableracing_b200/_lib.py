@@ -85,7 +85,7 @@ class GrPolicy(C.Structure):
 
 class GrCollectIO(C.Structure):
     _fields_ = [("obs0", c_p), ("critic_obs0", c_p), ("obs_out", c_p), ("critic_obs_out", c_p), ("aux_out", c_p), ("last_values", c_p),
-                ("episode_acc", c_p), ("log_accum", c_p), ("gamma", c_f), ("groups_per_cta", c_i)]
+                ("episode_acc", c_p), ("log_accum", c_p), ("episode_log", c_p), ("gamma", c_f), ("groups_per_cta", c_i)]
 
 
 class GrHostStep(C.Structure):
@@ -97,7 +97,6 @@ GR_LAUNCH_PDL = 1
 GR_LAUNCH_PREFETCH = 2
 GR_LOG_SLOTS = 16
 GR_LOG_SHARDS = 256
-GR_LOG_EP_REWARD, GR_LOG_EP_LENGTH = 10, 11
 GR_PHILOX_CALL_ACTION = 16
 STATUS = {0: "GR_OK", -1: "GR_ERR_NULL", -2: "GR_ERR_SIZE", -3: "GR_ERR_ALIGN", -4: "GR_ERR_CONFIG", -5: "GR_ERR_SMEM"}
 

@@ -63,6 +63,7 @@ class FusedCollector:
         self.sigma = torch.ones(4, device=dev)
         self.last_values = torch.zeros(env.num_envs, 1, device=dev)
         self.episode_acc = torch.zeros(env.num_envs, 2, device=dev)
+        self.episode_log = torch.zeros(B.GR_LOG_SHARDS, 4, device=dev)
         self.gamma = float(gamma)
         self.groups_per_cta = int(groups_per_cta)
         self._pol = B.GrPolicy(self.packed.data_ptr(), self.sigma.data_ptr(), self.slope)
@@ -94,7 +95,7 @@ class FusedCollector:
             dst = env._outs[k]
         env._flip = k ^ 1
         io = B.GrCollectIO(src["obs"].data_ptr(), src["critic"].data_ptr(), dst["obs"].data_ptr(), dst["critic"].data_ptr(), dst["aux"].data_ptr(),
-                           self.last_values.data_ptr(), self.episode_acc.data_ptr(), env._log_accum.data_ptr(), self.gamma, self.groups_per_cta)
+                           self.last_values.data_ptr(), self.episode_acc.data_ptr(), env._log_accum.data_ptr(), self.episode_log.data_ptr(), self.gamma, self.groups_per_cta)
         rng = env._rng
         rng.rnd = None
         rng.step = env._step_count & 0xFFFFFFFF
@@ -113,7 +114,7 @@ class FusedCollector:
         return dst["obs"], dst["critic"], self.last_values
 
     def episode_stats(self) -> torch.Tensor:
-        """(sum of episode rewards, sum of episode lengths, finished episodes) since the env's log accumulators were last read
-        (read this BEFORE ``env.extras["log"]``, which resets them)."""
-        acc = self.env._log_accum.sum(dim=0)
-        return torch.stack([acc[B.GR_LOG_EP_REWARD], acc[B.GR_LOG_EP_LENGTH], acc[0]])
+        """(sum of episode rewards, sum of episode lengths, finished episodes) since the last call (device tensor, no sync)."""
+        acc = self.episode_log.sum(dim=0)[:3]
+        self.episode_log.zero_()
+        return acc

@@ -373,10 +373,11 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
       epacc.x += so.reward;
       epacc.y += 1.0f;
       if (so.reset) {
-        if (cio.log_accum) {
-          float* acc_row = cio.log_accum + (size_t)((i >> 5) & (GR_LOG_SHARDS - 1)) * GR_LOG_SLOTS;
-          atomicAdd(acc_row + GR_LOG_EP_REWARD, epacc.x);
-          atomicAdd(acc_row + GR_LOG_EP_LENGTH, epacc.y);
+        if (cio.episode_log) {
+          float* acc_row = cio.episode_log + (size_t)((i >> 5) & (GR_LOG_SHARDS - 1)) * 4;
+          atomicAdd(acc_row + 0, epacc.x);
+          atomicAdd(acc_row + 1, epacc.y);
+          atomicAdd(acc_row + 2, 1.0f);
         }
         epacc = make_float2(0.f, 0.f);
       }

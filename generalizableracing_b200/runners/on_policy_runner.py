@@ -101,6 +101,8 @@ class OnPolicyRunner:
                     cur_episode_length.masked_fill_(d, 0.0)
                 if self.log_dir is not None and "log" in infos:
                     ep_infos.append(infos["log"])
+                if self.collector is not None:
+                    torch.cuda.synchronize(self.device)        # the fused rollout is one asynchronous launch: time it, not its enqueue
                 stop = time.time()
                 collection_time = stop - start
                 start = stop

@@ -161,8 +161,6 @@ typedef struct GrStepIO {
 #define GR_LOG_SUM_EPSUM 2          /* +k: sum over reset envs of episode sum of reward term k (6) */
 #define GR_LOG_NUM_TIMEOUT 8
 #define GR_LOG_NUM_TERMINATED 9
-#define GR_LOG_EP_REWARD 10         /* gr_ppo_collect: sum over finished episodes of the episode reward (runner book keeping) */
-#define GR_LOG_EP_LENGTH 11         /* gr_ppo_collect: sum over finished episodes of the episode length                    */
 #define GR_LOG_SLOTS 16
 #define GR_LOG_SHARDS 256          /* accumulator rows (64 B each), picked by warp id: spreads the RED traffic over L2 */
 
@@ -275,6 +273,8 @@ typedef struct GrCollectIO {
   float* last_values;                /* [N] V(critic_obs_out) */
   float* episode_acc;                /* [N,2] running (reward sum, length) of each env's current episode; in/out, optional */
   float* log_accum;                  /* [GR_LOG_SHARDS][GR_LOG_SLOTS], optional (see GR_LOG_*) */
+  float* episode_log;                /* [GR_LOG_SHARDS][4] float atomics, optional: per finished episode += (reward sum, length, 1, 0)
+                                        -- the runner's rewbuffer / lenbuffer book keeping (on_policy_runner.py:160-173) */
   float gamma;                       /* time-out bootstrap r += gamma * V(s_t) * time_out */
   int32_t groups_per_cta;            /* 128-env tiles per thread block: 1, 2, 4 or 0 = pick (fewest that fit one wave) */
 } GrCollectIO;

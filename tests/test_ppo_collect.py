@@ -89,7 +89,7 @@ def test_fused_collection_matches_step_by_step(cuda_lib, N, T, groups):
         assert torch.equal(getattr(sto_f, name), getattr(sto_u, name)), name
     assert torch.equal(env_f.planes, env_u.planes)
     assert torch.equal(obs_f, obs_u) and torch.equal(critic_f, critic_u)
-    assert torch.equal(env_f._log_accum.sum(0)[:10], env_u._log_accum.sum(0)[:10])
+    assert torch.equal(env_f._log_accum.sum(0), env_u._log_accum.sum(0))
     with torch.no_grad():
         lv_ref = pol.critic(critic_u)
     assert ((last_values - lv_ref).abs() <= TOL_ABS + TOL_REL * lv_ref.abs()).all()
@@ -115,6 +115,7 @@ def test_second_rollout_continues_the_first(cuda_lib):
     col_b.pack()
     col_b.collect()
     col_a.collect()
+    stats_a = col_a.episode_stats()
     first = {k: getattr(sto_a, k).clone() for k in ("observations", "actions", "rewards", "dones", "values")}
     sto_a.clear()
     col_a.collect()
@@ -123,7 +124,8 @@ def test_second_rollout_continues_the_first(cuda_lib):
         assert torch.equal(getattr(sto_a, k), getattr(sto_b, k)[T:]), k
     assert torch.equal(env_a.planes, env_b.planes)
     assert torch.equal(col_a.episode_acc, col_b.episode_acc)
-    assert torch.allclose(col_a.episode_stats(), col_b.episode_stats(), rtol=1e-5)
+    sa = stats_a + col_a.episode_stats()
+    assert torch.allclose(sa, col_b.episode_stats(), rtol=1e-5) and float(sa[2]) > 0
 
 
 def test_episode_book_keeping_matches_the_runner(cuda_lib):

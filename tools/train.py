@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--log_dir", default=None)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--noise_std", type=float, default=None)
+    ap.add_argument("--fused", action="store_true", help="PPO: collect each rollout with the fused kernel (gr_ppo_collect)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -45,6 +46,7 @@ def main():
         cfg = json.loads(json.dumps(PPO_CFG))
         if args.noise_std is not None:
             cfg["policy"]["init_noise_std"] = args.noise_std
+        cfg["fused_collection"] = bool(args.fused)
         runner = OnPolicyRunner(env, cfg, log_dir=args.log_dir, device=dev)
     else:
         cfg = json.loads(json.dumps(BPTT_CFG))
@@ -57,7 +59,7 @@ def main():
     hist = runner.learn(args.iters, init_at_random_ep_len=True)
     if int(os.environ.get("RANK", 0)) == 0:
         keys = [k for k in ("Train/mean_reward", "Train/mean_episode_length", "Loss/mean_total_loss", "Train/mean_step_reward",
-                            "Metrics/next_gate_pose/accumulate_gates", "Curriculum/terrain_levels", "Perf/total_fps") if k in hist[-1]]
+                            "Metrics/next_gate_pose/accumulate_gates", "Curriculum/terrain_levels", "Perf/total_fps", "Perf/collection time", "Perf/learning_time") if k in hist[-1]]
         for i in sorted(set(list(range(0, len(hist), max(1, len(hist) // 15))) + [len(hist) - 1])):
             print(i, {k: (round(hist[i][k], 4) if isinstance(hist[i][k], float) else hist[i][k]) for k in keys}, flush=True)
     if world > 1:
