@@ -128,12 +128,14 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint8_t* hrow, c
   }
 }
 
-// one thread: D[tmem] = A[smem: ksteps x 16 K-columns] . B[smem]^T, then arrive on `bar` when done
-__device__ __forceinline__ void issue_layer(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, int ksteps, uint32_t lbo_b, uint32_t idesc, uint64_t* bar) {
+// one thread: D[tmem] = A[smem: KSTEPS x 16 K-columns] . B[smem]^T, then arrive on `bar` when done.  The descriptors of
+// successive K steps differ only in the start-address field (bytes >> 4), so they are formed by integer adds.
+template <int KSTEPS, int LBO_B>
+__device__ __forceinline__ void issue_layer(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint64_t* bar) {
   tc_fence_after_sync();
-#pragma unroll 1
-  for (int kk = 0; kk < ksteps; ++kk)
-    mma_f16_ss(d_tmem, make_smem_desc(a_addr + kk * 2 * kChunkA, kChunkA, 128), make_smem_desc(b_addr + kk * 2 * lbo_b, lbo_b, 128), idesc, kk > 0);
+#pragma unroll
+  for (int kk = 0; kk < KSTEPS; ++kk)
+    mma_f16_ss(d_tmem, a_desc + (uint64_t)(kk * ((2 * kChunkA) >> 4)), b_desc + (uint64_t)(kk * ((2 * LBO_B) >> 4)), idesc, kk > 0);
   tc_commit(bar);
 }
 
@@ -159,14 +161,21 @@ __device__ __forceinline__ void stage_issue(const GroupCtx& g, uint32_t net_addr
   tc_fence_before_sync();                   // this thread's tcgen05.ld of the columns about to be overwritten
   bar_sync(g.bar_id, kTileEnvs);
   if (g.issuer) {
-    if (layer == kL1) issue_layer(g.d_tmem, g.hbuf_addr, net_addr + kW1Off, kK1 / 16, kHid * 16, make_idesc_f16(kTileEnvs, kHid), g.bar);
-    else if (layer == kL2) issue_layer(g.d_tmem, g.hbuf_addr, net_addr + kW2Off, kHid / 16, kHid * 16, make_idesc_f16(kTileEnvs, kHid), g.bar);
-    else issue_layer(g.d_tmem, g.hbuf_addr, net_addr + kW3Off, kHid / 16, kOutPad * 16, make_idesc_f16(kTileEnvs, kOutPad), g.bar);
+    const uint64_t a_desc = make_smem_desc(g.hbuf_addr, kChunkA, 128);
+    if (layer == kL1) issue_layer<kK1 / 16, kHid * 16>(g.d_tmem, a_desc, make_smem_desc(net_addr + kW1Off, kHid * 16, 128), make_idesc_f16(kTileEnvs, kHid), g.bar);
+    else if (layer == kL2) issue_layer<kHid / 16, kHid * 16>(g.d_tmem, a_desc, make_smem_desc(net_addr + kW2Off, kHid * 16, 128), make_idesc_f16(kTileEnvs, kHid), g.bar);
+    else issue_layer<kHid / 16, kOutPad * 16>(g.d_tmem, a_desc, make_smem_desc(net_addr + kW3Off, kOutPad * 16, 128), make_idesc_f16(kTileEnvs, kOutPad), g.bar);
   }
 }
+// Only the issuing thread polls the mbarrier; everybody else blocks in hardware on the group's second named barrier
+// (128 threads spinning on try_wait cost ~15 % of the kernel's issue slots).
 __device__ __forceinline__ void stage_wait(GroupCtx& g) {
-  mbar_wait(g.bar, g.phase);
-  g.phase ^= 1u;
+  if (g.issuer) {
+    mbar_wait(g.bar, g.phase);
+    g.phase ^= 1u;
+  }
+  __syncwarp();
+  bar_sync(g.bar_id + 8, kTileEnvs);
   tc_fence_after_sync();
 }
 // first 4 outputs of layer 3 (+ fp32 bias)
@@ -252,7 +261,7 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
   g.bar = &bars[grp];
   g.phase = 0u;
   g.bar_id = 1 + grp;
-  g.issuer = row == 0;
+  g.issuer = row == 32 * (grp & 3);            // lane 0 of a different warp per group: the four issuers sit on four SM sub-partitions
   g.slope = __float2half2_rn(pol.negative_slope);
   const uint32_t w_addr = smem_u32(w_smem);
 
@@ -295,6 +304,10 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
   // Per step: actor L1 L2 L3 -> sample -> critic L1 L2 L3, env.step.  Work that does not depend on the MMA in flight is
   // placed between its issue and its wait: the Philox draws under actor L1, the storage rows of the action under critic L1,
   // the whole env step under critic L2 (the longest MMA), the episode sums under critic L3.
+  // Groups that start together stay in lock step (same work per step): all of them in the ALU-heavy epilogues at once,
+  // then all of them waiting on the tensor pipe.  A one-time skew of a fraction of a step de-phases them for the whole
+  // rollout, so one group's MMA latency is covered by another group's ALU work.
+  if (G > 1 && cio.group_skew_ns > 0) __nanosleep((unsigned)(grp * cio.group_skew_ns));
 #pragma unroll 1
   for (int t = 0; t < T; ++t) {
     const int64_t tn = (int64_t)t * N + i;
@@ -470,6 +483,9 @@ extern "C" int gr_ppo_collect(const GrConfig* cfg, const GrTrack* track, const G
       bad16(storage->mu) || bad16(storage->sigma) || (io->episode_acc && (reinterpret_cast<uintptr_t>(io->episode_acc) & 7u)))
     return GR_ERR_ALIGN;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  GrCollectIO io_resolved = *io;
+  if (io_resolved.group_skew_ns < 0) io_resolved.group_skew_ns = 1500;       // ~1/4 of a 4-tile step (measured sweep: DESIGN.md)
+  io = &io_resolved;
   int G = io->groups_per_cta;
   if (G == 0) {            // smallest CTA that still fits the rollout in one wave of 148 SMs
     const int tiles = (st->num_envs + kTileEnvs - 1) / kTileEnvs;

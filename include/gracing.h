@@ -277,6 +277,7 @@ typedef struct GrCollectIO {
                                         -- the runner's rewbuffer / lenbuffer book keeping (on_policy_runner.py:160-173) */
   float gamma;                       /* time-out bootstrap r += gamma * V(s_t) * time_out */
   int32_t groups_per_cta;            /* 128-env tiles per thread block: 1, 2, 4 or 0 = pick (fewest that fit one wave) */
+  int32_t group_skew_ns;             /* one-time start skew between the tiles of a block (de-phases them); 0 = none, -1 = default */
 } GrCollectIO;
 int64_t gr_policy_packed_bytes(void);
 int gr_policy_pack(const GrMlp* actor, const GrMlp* critic, void* packed, void* stream);
