@@ -218,7 +218,7 @@ def run_ours(args):
         ms_local = ev0.elapsed_time(ev1)
         replays += rounds
         # keep the GPU under the same load a little longer so the 100 ms sampler sees it
-        t_end = time.time() + (0.6 if rank == 0 else 0.0)
+        t_end = time.time() + (1.5 if rank == 0 else 0.0)
         while time.time() < t_end:
             graph.replay()
             replays += 1
@@ -291,11 +291,19 @@ def run_ours(args):
     h2d = N * 4 * 4
     d2h = N * 16 * 4 + N * 4 + N * 8
 
-    # ---- extras: fwd+bwd BPTT (C3) and GAE (C2) device timings, rank 0 only
+    # every collective of this run is behind us: leave the process group BEFORE anything rank 0 does on its own (a module
+    # built on rank 0 alone would otherwise wait for the other ranks in its parameter broadcast)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+    # ---- extras: the other kernels of the path (BPTT C3, GAE / add_transitions C2, fused collection), single-GPU runs only
     extra = {}
-    if rank == 0 and not args.no_extra:
+    if rank == 0 and world == 1 and not args.no_extra:
         del graph
         extra = bench_extras(dev, cfg, table)
+    if rank == 0 and low is not None:
         extra["fwd_low_reset"] = low
 
     cpu = None
@@ -332,9 +340,6 @@ def run_ours(args):
             "extra": extra,
         }
         print(json.dumps(line))
-    if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
 
 
 def bench_extras(dev, cfg, table):
