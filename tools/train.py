@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--log_dir", default=None)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--noise_std", type=float, default=None)
+    ap.add_argument("--graphed", action="store_true", help="PPO: replay the mini-batch update from a CUDA graph")
     ap.add_argument("--fused", action="store_true", help="PPO: collect each rollout with the fused kernel (gr_ppo_collect)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -47,6 +48,7 @@ def main():
         if args.noise_std is not None:
             cfg["policy"]["init_noise_std"] = args.noise_std
         cfg["fused_collection"] = bool(args.fused)
+        cfg["algorithm"]["graphed_update"] = bool(args.graphed)
         runner = OnPolicyRunner(env, cfg, log_dir=args.log_dir, device=dev)
     else:
         cfg = json.loads(json.dumps(BPTT_CFG))
