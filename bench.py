@@ -142,14 +142,14 @@ def run_ours(args):
     from generalizableracing_b200 import _lib as B
     from generalizableracing_b200.config import RacingCfg
     from generalizableracing_b200.env import RacingVecEnv
-    from generalizableracing_b200.tracks import synthetic_track_table
+    from generalizableracing_b200.track_gen import generate_track_table, racing_complex_cfg
 
     rank, world, local = dist_setup(args.gpus)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     N = args.envs
     cfg = RacingCfg.for_stage(STAGE)
-    table = synthetic_track_table()
+    table = generate_track_table(racing_complex_cfg())      # RacingComplexTerrainCfg: 20 types x 10 levels x 8 gates, obstacle-free
     stats = not args.no_stats
     b_alg = algorithmic_bytes(cfg, stats)
     working_set = N * (b_alg + 0)                                      # bytes touched by one step
@@ -320,7 +320,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": rounds_w * R,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"C4: {N} envs/GPU, STAGE {STAGE}, synthetic 20x10 curriculum tracks x 8 gates, per-env DR, "
+            "config": {"workload": f"C4: {N} envs/GPU, STAGE {STAGE}, RacingComplexTerrainCfg gate table (20 types x 10 levels x 8 gates, restated generators, seed 42, no obstacles), per-env DR, "
                                    f"staggered resets, in-kernel Philox, episode_stats={stats}",
                        "envs_per_gpu": N, "l2": f"rotating {R} independent env batches ({R}x{working_set / 1e6:.0f} MB > 126 MB L2), "
                                                f"K timed steps = {rounds} CUDA-graph replays of {R} launches",
@@ -508,14 +508,14 @@ def _oracle_env(N, threads, device="cpu"):
     (the reference itself needs Isaac Sim; /root/reference does not exist on the GPU box)."""
     from generalizableracing_b200 import layout as L_
     from generalizableracing_b200.config import RacingCfg
-    from generalizableracing_b200.tracks import synthetic_track_table
+    from generalizableracing_b200.track_gen import generate_track_table, racing_complex_cfg
     from oracle import racing_oracle as RO
     torch.set_num_threads(threads)
     cfg = RacingCfg.for_stage(STAGE)
     g = torch.Generator().manual_seed(0)
     srnd = torch.rand(N, L_.SRND_STRIDE, generator=g)
     srnd[:, 12:] = torch.randn(N, 4, generator=g)
-    env = RO.OracleRacingEnv(cfg, synthetic_track_table(), N, srnd.to(device), device=device)
+    env = RO.OracleRacingEnv(cfg, generate_track_table(racing_complex_cfg()), N, srnd.to(device), device=device)
 
     def draw():
         r = torch.rand(N, L_.RND_STRIDE, generator=g)
@@ -588,7 +588,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": K, "warmup": W,
         "ms_per_step": dt * 1e3 / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"C4: {N} envs, STAGE {STAGE}, synthetic 20x10 curriculum tracks x 8 gates, per-env DR, staggered resets "
+        "config": {"workload": f"C4: {N} envs, STAGE {STAGE}, RacingComplexTerrainCfg gate table (20 types x 10 levels x 8 gates), per-env DR, staggered resets "
                                f"(each step = one full env.step over the {N}-env batch on the host cores)", "envs_per_gpu": N, "mass_kg": cfg.mass},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{K} timed steps, oracle = CPU torch port of the reference path (reference needs Isaac Sim), {threads} threads"},

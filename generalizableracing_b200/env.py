@@ -421,8 +421,9 @@ B_LOG_NUM_RESET, B_LOG_SUM_GATES, B_LOG_SUM_EPSUM, B_LOG_NUM_TIMEOUT, B_LOG_NUM_
 def make_env(task: str = "DiffLab-Quadcopter-CTBR-Racing-v0", num_envs: int = 2048, device="cuda:0", stage=None, track="complex",
              differentiable: bool = False, **kwargs) -> RacingVecEnv:
     """``gym.make(task, cfg=env_cfg)`` + ``RslRlVecEnvWrapper`` of the reference launch scripts (standalone/rsl_rl/train.py:102-120)
-    for the one registered racing task (QD/__init__.py:48-73).  ``track``: "complex" = 20x10 curriculum table shaped like
-    RacingComplexTerrainCfg, "figure8" = RacingTestTerrainCfg.  Under torchrun the envs are sharded over the ranks."""
+    for the one registered racing task (QD/__init__.py:48-73).  ``track``: "complex" = the 20x10 curriculum table of
+    RacingComplexTerrainCfg built by the restated family generators (track_gen.py; obstacle-free), "synthetic" = the
+    simplified centre-line table of tracks.py, "figure8" = RacingTestTerrainCfg.  Under torchrun the envs are sharded."""
     from . import dist_utils as D
     from .tracks import figure_eight_track, synthetic_track_table
     if task not in ("DiffLab-Quadcopter-CTBR-Racing-v0", "DiffLab-Quadcopter-CTBR-Racing-Play-v0"):
@@ -430,6 +431,14 @@ def make_env(task: str = "DiffLab-Quadcopter-CTBR-Racing-v0", num_envs: int = 20
     cfg = RacingCfg.from_env() if stage is None else RacingCfg.for_stage(stage)
     if differentiable:
         cfg.is_differentiable_physics = True
-    table = figure_eight_track() if track == "figure8" else synthetic_track_table()
+    if track == "figure8":
+        table = figure_eight_track()
+    elif track == "synthetic":
+        table = synthetic_track_table()
+    elif track == "complex":
+        from .track_gen import generate_track_table, racing_complex_cfg
+        table = generate_track_table(racing_complex_cfg(), name="RacingComplexTerrainCfg")
+    else:
+        raise ValueError(f"unknown track {track!r}")
     rank, world = D.world()
     return RacingVecEnv(cfg, table, num_envs, device=device, env_id_offset=rank * num_envs, global_num_envs=world * num_envs, **kwargs)

@@ -93,3 +93,38 @@ def ctbr_cfg(cfg):
         thrust_ctrl_delay=cfg.thrust_ctrl_delay, torque_ctrl_delay=tuple(cfg.torque_ctrl_delay),
         use_motor_model=False,
     )
+
+
+def load_track_families():
+    """The reference's track-family functions (L/terrains/trimesh/racing_terrains.py), executed where they lie with the mesh
+    layer stubbed out: ``trimesh`` and the ``make_*`` helpers of L/terrains/trimesh/utils.py build meshes only (out of
+    scope) and, for ``add_obs=False``, draw no random numbers, so gate poses / origins / next_gate_id are the reference's."""
+    if "tracks" in _cache:
+        return _cache["tracks"]
+    if not available():
+        raise FileNotFoundError(f"reference tree not found under {REF_ROOT}")
+    _install_stubs()
+    for name in ("omni.isaac.lab.terrains", "omni.isaac.lab.terrains.trimesh", "omni.isaac.lab.terrains.trimesh.utils"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+    sys.modules["omni.isaac.lab.terrains.trimesh.utils"].make_border = lambda *a, **k: []
+    tm = types.SimpleNamespace(creation=types.SimpleNamespace(box=lambda *a, **k: None),
+                               transformations=types.SimpleNamespace(translation_matrix=lambda *a, **k: None))
+    pkg = types.ModuleType("_gr_ref_trimesh_terrains")
+    pkg.__path__ = []                                   # no real path: the stub below IS the package's `utils`
+    sys.modules["_gr_ref_trimesh_terrains"] = pkg
+    utils = types.ModuleType("_gr_ref_trimesh_terrains.utils")
+    import random as _r
+    import numpy as _np
+    import scipy.spatial.transform as _tf
+    utils.np, utils.tf, utils.random, utils.trimesh = _np, _tf, _r, tm
+    for fn in ("make_gate", "make_wall", "make_orbit", "make_ground_high_obs", "make_ground_little_obj"):
+        setattr(utils, fn, lambda *a, **k: None)
+    sys.modules["_gr_ref_trimesh_terrains.utils"] = utils
+    mod = _load("_gr_ref_trimesh_terrains.racing_terrains", os.path.join(REF_ROOT, _L, "terrains/trimesh/racing_terrains.py"))
+    ns = types.SimpleNamespace(square=mod.SquareRacingTrackTerrain, zigzag=mod.ZigzagRacingTerrain, ellipse=mod.EllipseRacingTerrain,
+                               figure_eight=mod.FigureEightTrackTerrain)
+    _cache["tracks"] = ns
+    return ns
