@@ -23,7 +23,8 @@
 //  * operands are K-major, non-swizzled: [K/8 chunks][rows][8 halfs]; a thread's 16-byte chunk stores are conflict-free.
 //  * numerics: policy inference at fp16-operand / fp32-accumulate precision (the error against the fp32 torch MLP is
 //    measured in tests/test_ppo_collect.py and DESIGN.md); everything the env does (state, rewards, dones, observations)
-//    is the same code as gr_step_fwd, bit for bit, given the same actions.
+//    is the same code as gr_step_fwd: bit for bit given the same actions in the default variant <noise, stats>; within ~1 ulp
+//    per step in the others (FMA contraction of the inlined body differs between the two kernels).
 #include <cuda_fp16.h>
 #include "racing_step_core.cuh"
 #include "umma.cuh"

@@ -18,7 +18,8 @@ def _setup(N, T, stage=1, seed=11, groups=0, stats=True, weight_scale=1.0):
     from generalizableracing_b200.env import RacingVecEnv
     from generalizableracing_b200.modules import ActorCritic
     from generalizableracing_b200.storage import RolloutStorage
-    cfg, table = RacingCfg.for_stage(stage), synthetic_track_table()
+    from generalizableracing_b200.tracks import figure_eight_track
+    cfg, table = RacingCfg.for_stage(stage), (figure_eight_track() if stage == 0 else synthetic_track_table())
     torch.manual_seed(seed)
     pol = ActorCritic(16, 16, 4).cuda()
     with torch.no_grad():
@@ -51,9 +52,16 @@ def _emulate_fp16_mlp(seq, x):
     return h.float() @ l3.weight.half().float().T + l3.bias
 
 
-@pytest.mark.parametrize("N,T,groups", [(1000, 24, 1), (1000, 24, 4), (4096, 24, 0), (300, 5, 2)])
-def test_fused_collection_matches_step_by_step(cuda_lib, N, T, groups):
-    cfg, pol, (env_f, env_u), (sto_f, sto_u), col = _setup(N, T, groups=groups)
+@pytest.mark.parametrize("N,T,groups,stage,stats", [(1000, 24, 1, 1, True), (1000, 24, 4, 1, True), (4096, 24, 0, 1, True), (300, 5, 2, 1, True),
+                                                    (64, 8, 0, 0, False), (777, 12, 2, 0, True), (512, 12, 4, 2, False)])
+def test_fused_collection_matches_step_by_step(cuda_lib, N, T, groups, stage, stats):
+    """Default configuration (STAGE 1, episode sums on): every tensor bit-identical.  The other template variants inline the same
+    step body into a different kernel, where nvcc contracts a few mul+add pairs differently: masks / ids still identical, floats
+    within a few ulp per step (asserted at 1e-5, the oracle tolerance)."""
+    exact = stage == 1 and stats
+    same = torch.equal if exact else (lambda a, b: a.dtype in (torch.uint8, torch.int64, torch.bool) and torch.equal(a, b)
+                                      or a.is_floating_point() and torch.allclose(a, b, rtol=1e-5, atol=1e-5))
+    cfg, pol, (env_f, env_u), (sto_f, sto_u), col = _setup(N, T, groups=groups, stage=stage, stats=stats)
     obs_u, ex = env_u.get_observations()
     critic_u = ex["observations"]["critic"]
     obs_f, critic_f, last_values = col.collect()
@@ -62,15 +70,15 @@ def test_fused_collection_matches_step_by_step(cuda_lib, N, T, groups):
     with torch.no_grad():
         for t in range(T):
             # --- the fused kernel saw the same observations ...
-            assert torch.equal(sto_f.observations[t], obs_u), t
-            assert torch.equal(sto_f.privileged_observations[t], critic_u), t
+            assert same(sto_f.observations[t], obs_u), t
+            assert same(sto_f.privileged_observations[t], critic_u), t
             # --- ... its tensor-core MLPs agree with the fp32 modules within fp16-operand accuracy, and tightly with the emulation
             mu_ref, v_ref = pol.actor(obs_u), pol.critic(critic_u)
             mu, v, a = sto_f.mu[t], sto_f.values[t], sto_f.actions[t]
             assert ((mu - mu_ref).abs() <= TOL_ABS + TOL_REL * mu_ref.abs()).all(), (t, float((mu - mu_ref).abs().max()))
             assert ((v - v_ref).abs() <= TOL_ABS + TOL_REL * v_ref.abs()).all(), (t, float((v - v_ref).abs().max()))
             assert float((mu - mu_ref).abs().mean()) < 1e-3 and float((v - v_ref).abs().mean()) < 1e-3
-            mu_em, v_em = _emulate_fp16_mlp(pol.actor, obs_u), _emulate_fp16_mlp(pol.critic, critic_u)
+            mu_em, v_em = _emulate_fp16_mlp(pol.actor, sto_f.observations[t]), _emulate_fp16_mlp(pol.critic, sto_f.privileged_observations[t])
             assert float((mu - mu_em).abs().mean()) < 2e-5 and float((v - v_em).abs().mean()) < 2e-5
             assert float((mu - mu_em).abs().max()) < 2e-3 and float((v - v_em).abs().max()) < 2e-3
             assert torch.equal(sto_f.sigma[t], sigma.expand(N, 4))
@@ -78,7 +86,7 @@ def test_fused_collection_matches_step_by_step(cuda_lib, N, T, groups):
             assert float((sto_f.actions_log_prob[t] - lp_ref).abs().max()) < 2e-5
             # --- stepping the reference env with the SAME actions reproduces the stored transition bit for bit
             tr = sto_u.Transition()
-            tr.observations, tr.privileged_observations = obs_u, critic_u
+            tr.observations, tr.privileged_observations = sto_f.observations[t], sto_f.privileged_observations[t]
             tr.actions, tr.values, tr.actions_log_prob, tr.action_mean, tr.action_sigma = a, v, sto_f.actions_log_prob[t], mu, sto_f.sigma[t]
             obs_u, rew, dones, infos = env_u.step(a)
             critic_u = infos["observations"]["critic"]
@@ -86,22 +94,30 @@ def test_fused_collection_matches_step_by_step(cuda_lib, N, T, groups):
             sto_u.add_transitions(tr)
     torch.cuda.synchronize()
     for name in ("observations", "privileged_observations", "actions", "rewards", "dones", "values", "actions_log_prob", "mu", "sigma"):
-        assert torch.equal(getattr(sto_f, name), getattr(sto_u, name)), name
-    assert torch.equal(env_f.planes, env_u.planes)
-    assert torch.equal(obs_f, obs_u) and torch.equal(critic_f, critic_u)
-    assert torch.equal(env_f._log_accum.sum(0), env_u._log_accum.sum(0))
+        assert same(getattr(sto_f, name), getattr(sto_u, name)), name
+    if exact:
+        assert torch.equal(env_f.planes, env_u.planes)
+        assert torch.equal(env_f._log_accum.sum(0), env_u._log_accum.sum(0))
+    else:
+        sf, su = env_f.state_dict_view(), env_u.state_dict_view()
+        for k in ("gate_id", "accumulate_gates", "terrain_levels", "episode_length", "fresh"):
+            assert torch.equal(sf[k], su[k]), k
+        for k in ("root_pos_w", "root_quat_w", "root_lin_vel_w", "root_ang_vel_b", "torque", "gross_thrust"):
+            assert torch.allclose(sf[k], su[k], rtol=1e-5, atol=1e-5), k
+    assert same(obs_f, obs_u) and same(critic_f, critic_u)
     with torch.no_grad():
         lv_ref = pol.critic(critic_u)
     assert ((last_values - lv_ref).abs() <= TOL_ABS + TOL_REL * lv_ref.abs()).all()
     # --- the action noise is a fresh standard normal per env, step and component
     eps = ((sto_f.actions - sto_f.mu) / sto_f.sigma).reshape(-1, 4)
-    assert float(eps.mean().abs()) < 0.03 and float((eps.std() - 1).abs()) < 0.03
-    assert float(torch.corrcoef(eps.T).fill_diagonal_(0).abs().max()) < 0.05
+    tol = 5.0 / (N * T) ** 0.5
+    assert float(eps.mean().abs()) < tol and float((eps.std() - 1).abs()) < tol
+    assert float(torch.corrcoef(eps.T).fill_diagonal_(0).abs().max()) < tol
     # --- and the env keeps working step by step afterwards (prefetch flag handling)
     a = torch.zeros(N, 4, device="cuda")
     o1 = env_f.step(a)[0].clone()
     o2 = env_u.step(a)[0].clone()
-    assert torch.equal(o1, o2)
+    assert same(o1, o2)
 
 
 def test_second_rollout_continues_the_first(cuda_lib):
