@@ -76,7 +76,7 @@ class GrMiniBatch(C.Structure):
 
 
 class GrMlp(C.Structure):
-    _fields_ = [("w1", c_p), ("b1", c_p), ("w2", c_p), ("b2", c_p), ("w3", c_p), ("b3", c_p), ("in_dim", c_i), ("hidden", c_i), ("out_dim", c_i)]
+    _fields_ = [("w1", c_p), ("b1", c_p), ("w2", c_p), ("b2", c_p), ("w3", c_p), ("b3", c_p), ("in_dim", c_i), ("hidden", c_i), ("hidden2", c_i), ("out_dim", c_i)]
 
 
 class GrPolicy(C.Structure):
@@ -86,6 +86,12 @@ class GrPolicy(C.Structure):
 class GrCollectIO(C.Structure):
     _fields_ = [("obs0", c_p), ("critic_obs0", c_p), ("obs_out", c_p), ("critic_obs_out", c_p), ("aux_out", c_p), ("last_values", c_p),
                 ("episode_acc", c_p), ("log_accum", c_p), ("episode_log", c_p), ("gamma", c_f), ("groups_per_cta", c_i), ("group_skew_ns", c_i)]
+
+
+class GrBpttCollectIO(C.Structure):
+    _fields_ = [("obs0", c_p), ("obs_out", c_p), ("critic_obs_out", c_p), ("aux_out", c_p), ("obs_seq", c_p), ("eps_seq", c_p), ("actions", c_p),
+                ("loss", c_p), ("loss_terms", c_p), ("reward", c_p), ("dones", c_p), ("tape", c_p), ("tape_stride", C.c_int64), ("log_accum", c_p),
+                ("T", c_i), ("groups_per_cta", c_i)]
 
 
 class GrHostStep(C.Structure):
@@ -115,7 +121,9 @@ PROTOTYPES = {
     "gr_compute_returns": (C.c_int, [C.POINTER(GrStorage), c_p, c_f, c_f, c_p, c_p, c_i, c_p]),
     "gr_advantage_normalize": (C.c_int, [C.POINTER(GrStorage), c_p, c_p]),
     "gr_storage_gather": (C.c_int, [C.POINTER(GrStorage), c_p, c_i, C.POINTER(GrMiniBatch), c_p]),
-    "gr_policy_packed_bytes": (C.c_int64, []),
+    "gr_policy_packed_bytes": (C.c_int64, [c_i, c_i, c_i]),
+    "gr_bptt_collect": (C.c_int, [C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom), C.POINTER(GrPolicy), c_i, c_i,
+                                  C.POINTER(GrBpttCollectIO), c_p]),
     "gr_policy_pack": (C.c_int, [C.POINTER(GrMlp), C.POINTER(GrMlp), c_p, c_p]),
     "gr_ppo_collect": (C.c_int, [C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom), C.POINTER(GrPolicy),
                                  C.POINTER(GrStorage), C.POINTER(GrCollectIO), c_p]),

@@ -47,6 +47,19 @@ class BPTT:
         self.rewards.append(rewards)
         self.actor_critic.reset(dones)
 
+    def update_fused(self, collector):
+        """update() after a fused window (collect.FusedBpttCollector): one reverse sweep + ONE batched actor backward."""
+        win = self.env._bptt
+        T = win.t
+        total_loss_mean = win.loss[:T].mean()
+        self.optimizer.zero_grad()
+        grad_actions = win.backward_window(grad_scale=1.0 / (T * self.env.num_envs))
+        collector.policy_backward(grad_actions)
+        D.allreduce_mean_grads(self.actor_critic.parameters())
+        self.optimizer.step()
+        self.schedule.step()
+        return 0.0, total_loss_mean
+
     def update(self):
         losses = torch.stack([l.detach() for l in self.losses])
         losses_detached = torch.stack(self.losses_detached)

@@ -59,7 +59,7 @@ class FusedCollector:
             raise ValueError("storage does not match the env")
         self._layers = ((a1, a2, a3, L.NUM_ACTIONS), (c1, c2, c3, 1))
         self.slope = sa
-        self.packed = torch.zeros(int(self._lib.gr_policy_packed_bytes()), dtype=torch.uint8, device=dev)
+        self.packed = torch.zeros(int(self._lib.gr_policy_packed_bytes(128, 128, 2)), dtype=torch.uint8, device=dev)
         self.sigma = torch.ones(4, device=dev)
         self.last_values = torch.zeros(env.num_envs, 1, device=dev)
         self.episode_acc = torch.zeros(env.num_envs, 2, device=dev)
@@ -71,7 +71,7 @@ class FusedCollector:
 
     def _mlp(self, l1, l2, l3, out) -> B.GrMlp:
         return B.GrMlp(l1.weight.data_ptr(), l1.bias.data_ptr(), l2.weight.data_ptr(), l2.bias.data_ptr(), l3.weight.data_ptr(), l3.bias.data_ptr(),
-                       L.OBS_DIM, 128, out)
+                       L.OBS_DIM, 128, 128, out)
 
     def pack(self):
         """fp32 torch parameters -> packed fp16 operands + action std (call after every optimiser update; two tiny launches)."""
@@ -119,3 +119,89 @@ class FusedCollector:
         acc = self.episode_log.sum(dim=0)[:3]
         self.episode_log.zero_()
         return acc
+
+
+class FusedBpttCollector:
+    """The forward half of a BPTT window (``AlgoRunner.learn``'s rollout loop, standalone/diff_rl/algorithms/runner.py:110-126
+    of the reference) as ONE launch of ``gr_bptt_collect``: actor MLP on the tensor cores + rsample + differentiable env.step
+    with tape and losses, T times.  The backward is ``BpttWindow.backward_window()`` (one ``gr_step_bwd`` launch) followed by
+    ONE batched torch forward/backward of the actor over the recorded ``[T*N]`` (observation, noise) rows
+    (:meth:`policy_backward`) -- the same function ``sum_t actor(obs_t) + std * eps_t`` the reference differentiates step by
+    step.  Actor widths (128, 128) or (256, 128), LeakyReLU / ReLU.  Opt-in (``train_cfg["fused_collection"]``)."""
+
+    def __init__(self, env, policy, horizon: int, groups_per_cta: int = 0):
+        if env._bptt is None or env.rng_mode != "philox":
+            raise ValueError("fused BPTT collection needs a differentiable env drawing in-kernel (is_differentiable_physics, rng_mode='philox')")
+        (l1, l2, l3), slope = _mlp_layers(policy.actor)
+        dims = (l1.in_features, l1.out_features, l2.in_features, l2.out_features, l3.in_features, l3.out_features)
+        if dims not in ((L.OBS_DIM, 128, 128, 128, 128, L.NUM_ACTIONS), (L.OBS_DIM, 256, 256, 128, 128, L.NUM_ACTIONS)):
+            raise ValueError("fused BPTT collection is built for 16 -> 128 -> 128 -> 4 and 16 -> 256 -> 128 -> 4 actors")
+        for l in (l1, l2, l3):
+            if l.bias is None or l.weight.dtype != torch.float32 or not l.weight.is_contiguous() or l.weight.device != env.device:
+                raise ValueError("fused collection needs contiguous fp32 Linear layers with bias on the env's device")
+        if horizon > env._bptt.capacity:
+            raise ValueError("horizon exceeds the env's tape capacity (bptt_horizon)")
+        self.env, self.policy, self.T = env, policy, int(horizon)
+        self._lib, self._layers, self.slope = env._lib, (l1, l2, l3), slope
+        self.h1, self.h2 = l1.out_features, l2.out_features
+        dev, N, T = env.device, env.num_envs, self.T
+        self.packed = torch.zeros(int(self._lib.gr_policy_packed_bytes(self.h1, self.h2, 1)), dtype=torch.uint8, device=dev)
+        self.sigma = torch.ones(4, device=dev)
+        self.obs_seq = torch.zeros(T, N, L.OBS_DIM, device=dev)
+        self.eps_seq = torch.zeros(T, N, L.NUM_ACTIONS, device=dev)
+        self.actions = torch.zeros(T, N, L.NUM_ACTIONS, device=dev)
+        self.rewards = torch.zeros(T, N, device=dev)
+        self.dones = torch.zeros(T, N, dtype=torch.uint8, device=dev)
+        self.groups_per_cta = int(groups_per_cta)
+        self._pol = B.GrPolicy(self.packed.data_ptr(), self.sigma.data_ptr(), self.slope)
+
+    def pack(self):
+        l1, l2, l3 = self._layers
+        a = B.GrMlp(l1.weight.data_ptr(), l1.bias.data_ptr(), l2.weight.data_ptr(), l2.bias.data_ptr(), l3.weight.data_ptr(), l3.bias.data_ptr(),
+                    L.OBS_DIM, self.h1, self.h2, L.NUM_ACTIONS)
+        B.check(self._lib.gr_policy_pack(C.byref(a), None, self.packed.data_ptr(), self.env._stream()), "gr_policy_pack")
+        with torch.no_grad():
+            p = self.policy
+            self.sigma.copy_(p.std if p.noise_std_type == "scalar" else torch.exp(p.log_std))
+
+    def collect(self):
+        """One window of ``horizon`` steps (call ``env.unwrapped.detach()`` first, as the runner does).  Afterwards the env's BPTT
+        window holds the tape and the losses of the T steps; returns (obs, critic_obs) after the last step."""
+        env, win, T = self.env, self.env._bptt, self.T
+        if env._needs_reset:
+            env.reset()
+        if win.t != 0:
+            raise RuntimeError("fused BPTT collection starts a window: call env.unwrapped.detach() first")
+        src = env._last
+        k = env._flip
+        dst = env._outs[k]
+        if dst is src:
+            k ^= 1
+            dst = env._outs[k]
+        env._flip = k ^ 1
+        io = B.GrBpttCollectIO(src["obs"].data_ptr(), dst["obs"].data_ptr(), dst["critic"].data_ptr(), dst["aux"].data_ptr(), self.obs_seq.data_ptr(),
+                               self.eps_seq.data_ptr(), self.actions.data_ptr(), win.loss.data_ptr(), win.loss_terms.data_ptr(), self.rewards.data_ptr(),
+                               self.dones.data_ptr(), win.tape.data_ptr(), env._stride, env._log_accum.data_ptr(), T, self.groups_per_cta)
+        rng = env._rng
+        rng.rnd = None
+        rng.step = env._step_count & 0xFFFFFFFF
+        env._step_count += T
+        B.check(self._lib.gr_bptt_collect(env._p_cfg, env._p_track, env._p_state, C.byref(rng), C.byref(self._pol), self.h1, self.h2, C.byref(io),
+                                          env._stream()), "gr_bptt_collect")
+        win.t = T
+        env._state.launch_flags = env._launch_flags & ~B.GR_LAUNCH_PREFETCH
+        env._params_edited = True
+        env._last = dst
+        ex = env.extras
+        dict.pop(ex, "log", None)
+        ex["observations"] = env._obs_dict(dst)
+        return dst["obs"], dst["critic"]
+
+    def policy_backward(self, grad_actions: torch.Tensor):
+        """Accumulate d(loss)/d(policy parameters) from the sweep's ``grad_actions`` [T,N,4]: one batched actor pass."""
+        T, N = self.T, self.env.num_envs
+        p = self.policy
+        mu = p.actor(self.obs_seq.reshape(T * N, L.OBS_DIM))
+        std = p.std if p.noise_std_type == "scalar" else torch.exp(p.log_std)
+        a = mu + std * self.eps_seq.reshape(T * N, L.NUM_ACTIONS)
+        torch.autograd.backward([a], [grad_actions.reshape(T * N, L.NUM_ACTIONS)])

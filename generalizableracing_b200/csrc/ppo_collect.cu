@@ -25,177 +25,14 @@
 //    measured in tests/test_ppo_collect.py and DESIGN.md); everything the env does (state, rewards, dones, observations)
 //    is the same code as gr_step_fwd: bit for bit given the same actions in the default variant <noise, stats>; within ~1 ulp
 //    per step in the others (FMA contraction of the inlined body differs between the two kernels).
-#include <cuda_fp16.h>
 #include "racing_step_core.cuh"
-#include "umma.cuh"
+#include "mlp_tc.cuh"
 
 namespace gr {
 
-using namespace umma;
-
-constexpr int kTileEnvs = 128;                    // M of one UMMA tile = threads per group
-constexpr int kHid = 128, kObsDim = 16, kK1 = 32, kOutPad = 16;
-constexpr int kChunkA = kTileEnvs * 16;           // byte stride between K chunks of an A operand (128 rows x 16 B)
-// packed parameters of one net (bytes); every block is 128-byte aligned
-constexpr int kW1Off = 0, kW1Bytes = kHid * kK1 * 2;              // [4][128][8] halfs: 16 inputs | b1 hi | b1 lo | 0...
-constexpr int kW2Off = kW1Off + kW1Bytes, kW2Bytes = kHid * kHid * 2;      // [16][128][8]
-constexpr int kW3Off = kW2Off + kW2Bytes, kW3Bytes = kOutPad * kHid * 2;   // [16][16][8], rows >= out_dim are zero
-constexpr int kB2Off = kW3Off + kW3Bytes, kB2Bytes = kHid * 2;             // fp16 [128]
-constexpr int kB3Off = kB2Off + kB2Bytes, kB3Bytes = 128;                  // fp32 [16] (+ pad)
-constexpr int kNetBytes = kB3Off + kB3Bytes;                               // 45,440
-constexpr int kHBytes = kTileEnvs * kHid * 2;                              // activation tile of one group: 32 KB
-static_assert(kNetBytes % 128 == 0, "packed net must keep 128-byte alignment");
-
-// ---------------------------------------------------------------------------------------------
-// parameter packing: torch Linear weights [out][in] fp32 -> fp16, UMMA operand order
-// ---------------------------------------------------------------------------------------------
-__global__ void policy_pack_kernel(const GrMlp actor, const GrMlp critic, uint8_t* __restrict__ packed) {
-  const int net = blockIdx.y;
-  const GrMlp& m = net == 0 ? actor : critic;
-  uint8_t* out = packed + (size_t)net * kNetBytes;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  __half* w1 = reinterpret_cast<__half*>(out + kW1Off);
-  __half* w2 = reinterpret_cast<__half*>(out + kW2Off);
-  __half* w3 = reinterpret_cast<__half*>(out + kW3Off);
-  if (idx < kHid * kK1) {
-    const int n = idx / kK1, k = idx % kK1;
-    float v = 0.0f;
-    if (k < kObsDim) v = m.w1[n * kObsDim + k];
-    else if (k == kObsDim) v = __half2float(__float2half_rn(m.b1[n]));
-    else if (k == kObsDim + 1) v = m.b1[n] - __half2float(__float2half_rn(m.b1[n]));
-    w1[(k >> 3) * (kHid * 8) + n * 8 + (k & 7)] = __float2half_rn(v);
-  }
-  if (idx < kHid * kHid) {
-    const int n = idx / kHid, k = idx % kHid;
-    w2[(k >> 3) * (kHid * 8) + n * 8 + (k & 7)] = __float2half_rn(m.w2[n * kHid + k]);
-  }
-  if (idx < kOutPad * kHid) {
-    const int n = idx / kHid, k = idx % kHid;
-    w3[(k >> 3) * (kOutPad * 8) + n * 8 + (k & 7)] = __float2half_rn(n < m.out_dim ? m.w3[n * kHid + k] : 0.0f);
-  }
-  if (idx < kHid) reinterpret_cast<__half*>(out + kB2Off)[idx] = __float2half_rn(m.b2[idx]);
-  if (idx < kB3Bytes / 4) reinterpret_cast<float*>(out + kB3Off)[idx] = idx < m.out_dim ? m.b3[idx] : 0.0f;
-}
-
-// ---------------------------------------------------------------------------------------------
-// device helpers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
-__device__ __forceinline__ __half2 bits_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
-__device__ __forceinline__ uint4 pack8(float4 a, float4 b) {
-  return make_uint4(h2_bits(__floats2half2_rn(a.x, a.y)), h2_bits(__floats2half2_rn(a.z, a.w)), h2_bits(__floats2half2_rn(b.x, b.y)),
-                    h2_bits(__floats2half2_rn(b.z, b.w)));
-}
-
-// first-layer operand row of one env: chunks 0,1 = the 16 observations, chunk 2 = (1, 1, 0...) against the bias rows, chunk 3 = 0
-__device__ __forceinline__ void write_x_row(uint8_t* hrow, uint4 c0, uint4 c1) {
-  *reinterpret_cast<uint4*>(hrow) = c0;
-  *reinterpret_cast<uint4*>(hrow + kChunkA) = c1;
-  *reinterpret_cast<uint4*>(hrow + 2 * kChunkA) = make_uint4(0x3C003C00u, 0u, 0u, 0u);      // half2(1, 1)
-  *reinterpret_cast<uint4*>(hrow + 3 * kChunkA) = make_uint4(0u, 0u, 0u, 0u);
-}
-
-// 8 accumulator columns (fp32 bits) -> (+ bias) -> leaky relu -> 8 halfs
-template <bool kBias>
-__device__ __forceinline__ uint4 activate8(const uint32_t* r, const uint4* __restrict__ bias, int chunk, __half2 slope) {
-  __half2 h[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1]));
-  if (kBias) {
-    const uint4 b = bias[chunk];
-    h[0] = __hadd2(h[0], bits_h2(b.x)); h[1] = __hadd2(h[1], bits_h2(b.y)); h[2] = __hadd2(h[2], bits_h2(b.z)); h[3] = __hadd2(h[3], bits_h2(b.w));
-  }
-#pragma unroll
-  for (int q = 0; q < 4; ++q) h[q] = __hmax2(h[q], __hmul2(h[q], slope));
-  return make_uint4(h2_bits(h[0]), h2_bits(h[1]), h2_bits(h[2]), h2_bits(h[3]));
-}
-
-// hidden-layer epilogue of one env row: D[row][0..127] (TMEM) -> (+ bias) -> leaky relu -> fp16 -> the row of the next A
-// operand.  The TMEM loads are double-buffered (16 columns each): the next load is in flight while this one is processed.
-template <bool kBias>
-__device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint8_t* hrow, const uint4* __restrict__ bias, __half2 slope) {
-  uint32_t ra[16], rb[16];
-  tmem_ld_x16(taddr, ra);
-#pragma unroll 1
-  for (int c = 0; c < 8; c += 2) {          // c = index of the 16-column block held by ra
-    tmem_ld_wait();
-    tmem_ld_x16(taddr + (c + 1) * 16, rb);
-    *reinterpret_cast<uint4*>(hrow + (2 * c) * kChunkA) = activate8<kBias>(ra, bias, 2 * c, slope);
-    *reinterpret_cast<uint4*>(hrow + (2 * c + 1) * kChunkA) = activate8<kBias>(ra + 8, bias, 2 * c + 1, slope);
-    tmem_ld_wait();
-    if (c + 2 < 8) tmem_ld_x16(taddr + (c + 2) * 16, ra);
-    *reinterpret_cast<uint4*>(hrow + (2 * c + 2) * kChunkA) = activate8<kBias>(rb, bias, 2 * c + 2, slope);
-    *reinterpret_cast<uint4*>(hrow + (2 * c + 3) * kChunkA) = activate8<kBias>(rb + 8, bias, 2 * c + 3, slope);
-  }
-}
-
-// one thread: D[tmem] = A[smem: KSTEPS x 16 K-columns] . B[smem]^T, then arrive on `bar` when done.  The descriptors of
-// successive K steps differ only in the start-address field (bytes >> 4), so they are formed by integer adds.
-template <int KSTEPS, int LBO_B>
-__device__ __forceinline__ void issue_layer(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint64_t* bar) {
-  tc_fence_after_sync();
-#pragma unroll
-  for (int kk = 0; kk < KSTEPS; ++kk)
-    mma_f16_ss(d_tmem, a_desc + (uint64_t)(kk * ((2 * kChunkA) >> 4)), b_desc + (uint64_t)(kk * ((2 * LBO_B) >> 4)), idesc, kk > 0);
-  tc_commit(bar);
-}
-
-// what one group needs to run a net
-struct GroupCtx {
-  uint8_t* hbuf;        // this group's activation tile (shared)
-  uint8_t* hrow;        // hbuf + row * 16
-  uint32_t hbuf_addr;   // shared-space address of hbuf
-  uint32_t d_tmem;      // accumulator columns of this group
-  uint32_t taddr;       // d_tmem + (lane quarter << 16): what this warp may tcgen05.ld
-  uint64_t* bar;
-  uint32_t phase;
-  int bar_id;           // named barrier of the group
-  bool issuer;
-  __half2 slope;
-};
-
-// A layer = [every thread of the group has written its operand row] -> group barrier -> one thread issues the MMAs ->
-// ... independent work ... -> stage_wait -> the accumulator is readable.
-enum Layer : int { kL1 = 0, kL2 = 1, kL3 = 2 };
-__device__ __forceinline__ void stage_issue(const GroupCtx& g, uint32_t net_addr, const int layer) {
-  fence_proxy_async_smem();                 // this thread's st.shared operand rows -> async proxy
-  tc_fence_before_sync();                   // this thread's tcgen05.ld of the columns about to be overwritten
-  bar_sync(g.bar_id, kTileEnvs);
-  if (g.issuer) {
-    const uint64_t a_desc = make_smem_desc(g.hbuf_addr, kChunkA, 128);
-    if (layer == kL1) issue_layer<kK1 / 16, kHid * 16>(g.d_tmem, a_desc, make_smem_desc(net_addr + kW1Off, kHid * 16, 128), make_idesc_f16(kTileEnvs, kHid), g.bar);
-    else if (layer == kL2) issue_layer<kHid / 16, kHid * 16>(g.d_tmem, a_desc, make_smem_desc(net_addr + kW2Off, kHid * 16, 128), make_idesc_f16(kTileEnvs, kHid), g.bar);
-    else issue_layer<kHid / 16, kOutPad * 16>(g.d_tmem, a_desc, make_smem_desc(net_addr + kW3Off, kOutPad * 16, 128), make_idesc_f16(kTileEnvs, kOutPad), g.bar);
-  }
-}
-// Only the issuing thread polls the mbarrier; everybody else blocks in hardware on the group's second named barrier
-// (128 threads spinning on try_wait cost ~15 % of the kernel's issue slots).
-__device__ __forceinline__ void stage_wait(GroupCtx& g) {
-  if (g.issuer) {
-    mbar_wait(g.bar, g.phase);
-    g.phase ^= 1u;
-  }
-  __syncwarp();
-  bar_sync(g.bar_id + 8, kTileEnvs);
-  tc_fence_after_sync();
-}
-// first 4 outputs of layer 3 (+ fp32 bias)
-__device__ __forceinline__ float4 read_head(const GroupCtx& g, const uint8_t* net_smem) {
-  uint32_t r[4];
-  tmem_ld_x4(g.taddr, r);
-  tmem_ld_wait();
-  const float4 b3 = *reinterpret_cast<const float4*>(net_smem + kB3Off);
-  return make_float4(__uint_as_float(r[0]) + b3.x, __uint_as_float(r[1]) + b3.y, __uint_as_float(r[2]) + b3.z, __uint_as_float(r[3]) + b3.w);
-}
-// a whole net with nothing overlapped (last_values pass)
-__device__ __forceinline__ float4 run_net(GroupCtx& g, const uint8_t* net_smem, uint32_t net_addr) {
-  stage_issue(g, net_addr, kL1); stage_wait(g);
-  hidden_epilogue<false>(g.taddr, g.hrow, nullptr, g.slope);
-  stage_issue(g, net_addr, kL2); stage_wait(g);
-  hidden_epilogue<true>(g.taddr, g.hrow, reinterpret_cast<const uint4*>(net_smem + kB2Off), g.slope);
-  stage_issue(g, net_addr, kL3); stage_wait(g);
-  return read_head(g, net_smem);
-}
+using NL = NetLayout<128, 128>;          // QD/agents/rsl_rl_ppo_cfg.py:22-27: actor / critic hidden dims [128, 128]
+constexpr int kHid = 128;
+constexpr int kNetBytes = NL::kNetBytes, kHBytes = NL::kHBytes, kB2Off = NL::kB2Off;
 
 // observation sink of the fused kernel: fp32 rows go to the rollout storage (or to the "next observation" buffers after
 // the last step); both rows also wait in 8 registers each, as fp16, to become layer-1 operands once the group's
@@ -253,17 +90,7 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
   __syncthreads();
   tc_fence_after_sync();
 
-  GroupCtx g;
-  g.hbuf = h_smem + grp * kHBytes;
-  g.hrow = g.hbuf + row * 16;
-  g.hbuf_addr = smem_u32(g.hbuf);
-  g.d_tmem = *tmem_slot + (uint32_t)(grp * kHid);
-  g.taddr = g.d_tmem + ((uint32_t)((row >> 5) * 32) << 16);
-  g.bar = &bars[grp];
-  g.phase = 0u;
-  g.bar_id = 1 + grp;
-  g.issuer = row == 32 * (grp & 3);            // lane 0 of a different warp per group: the four issuers sit on four SM sub-partitions
-  g.slope = __float2half2_rn(pol.negative_slope);
+  GroupCtx g = make_group_ctx(h_smem, kHBytes, bars, *tmem_slot, kHid, grp, row, pol.negative_slope);
   const uint32_t w_addr = smem_u32(w_smem);
 
   // ---- env state -> registers (once per rollout)
@@ -298,8 +125,6 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
 
   const uint8_t* critic_smem = w_smem + kNetBytes;
   const uint32_t critic_addr = w_addr + kNetBytes;
-  const uint4* actor_b2 = reinterpret_cast<const uint4*>(w_smem + kB2Off);
-  const uint4* critic_b2 = reinterpret_cast<const uint4*>(critic_smem + kB2Off);
   uint4 policy_pk[2] = {critic_pk[0], critic_pk[1]};       // (lanes past the last env never refresh it)
 
   // Per step: actor L1 L2 L3 -> sample -> critic L1 L2 L3, env.step.  Work that does not depend on the MMA in flight is
@@ -313,7 +138,7 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
   for (int t = 0; t < T; ++t) {
     const int64_t tn = (int64_t)t * N + i;
     // ---- PPO.act: actor mean, sample, log-prob (ppo.py:71-83; Normal(mean, std).sample() / .log_prob().sum(-1))
-    stage_issue(g, w_addr, kL1);
+    stage_issue<NL>(g, w_addr, kL1);
     GrRandom rt = rng;
     rt.step = rng.step + (uint32_t)t;
     const RandSrc<true> rs(rt, li, st.env_id_offset + li);
@@ -325,15 +150,15 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
       an0 = box_muller(x.x, x.y); an1 = box_muller(x.z, x.w);
     }
     stage_wait(g);
-    hidden_epilogue<false>(g.taddr, g.hrow, nullptr, g.slope);
-    stage_issue(g, w_addr, kL2); stage_wait(g);
-    hidden_epilogue<true>(g.taddr, g.hrow, actor_b2, g.slope);
-    stage_issue(g, w_addr, kL3); stage_wait(g);
-    const float4 mu = read_head(g, w_smem);
+    epilogue1<NL>(g);
+    stage_issue<NL>(g, w_addr, kL2); stage_wait(g);
+    epilogue2<NL>(g, w_smem);
+    stage_issue<NL>(g, w_addr, kL3); stage_wait(g);
+    const float4 mu = read_head<NL>(g, w_smem);
     const float4 a_t = make_float4(mu.x + sigma.x * an0.x, mu.y + sigma.y * an0.y, mu.z + sigma.z * an1.x, mu.w + sigma.w * an1.y);
     // ---- critic value of the same state
     write_x_row(g.hrow, critic_pk[0], critic_pk[1]);
-    stage_issue(g, critic_addr, kL1);
+    stage_issue<NL>(g, critic_addr, kL1);
     {
       const float dx = a_t.x - mu.x, dy = a_t.y - mu.y, dz = a_t.z - mu.z, dw = a_t.w - mu.w;
       const float kLogSqrt2Pi = 0.91893853320467274178f;
@@ -347,8 +172,8 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
       }
     }
     stage_wait(g);
-    hidden_epilogue<false>(g.taddr, g.hrow, nullptr, g.slope);
-    stage_issue(g, critic_addr, kL2);
+    epilogue1<NL>(g);
+    stage_issue<NL>(g, critic_addr, kL2);
 
     // ---- env.step (same body as gr_step_fwd) while the critic's layer 2 runs; its observations are the next step's
     //      operands (kept packed in registers until the activation tile is free) and storage rows
@@ -364,8 +189,8 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
     const bool alive = racing_step_body<kNoise, false, true, kStats>(cfg, tr, e, a_t, n01, n23, draws, eps0, eps1, io, i, active, sink, so);
 
     stage_wait(g);
-    hidden_epilogue<true>(g.taddr, g.hrow, critic_b2, g.slope);
-    stage_issue(g, critic_addr, kL3);
+    epilogue2<NL>(g, critic_smem);
+    stage_issue<NL>(g, critic_addr, kL3);
     if (alive) {
       if (kStats && !so.reset) {
 #pragma unroll
@@ -377,7 +202,7 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
       sto.dones[tn] = so.reset ? 1 : 0;
     }
     stage_wait(g);
-    const float value = read_head(g, critic_smem).x;
+    const float value = read_head<NL>(g, critic_smem).x;
     write_x_row(g.hrow, policy_pk[0], policy_pk[1]);          // the tile is free again: next step's actor operand
     if (alive) {
       // ---- PPO.process_env_step (ppo.py:85-97) + add_transitions: bootstrap on time-outs with V(s_t)
@@ -400,7 +225,7 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
 
   // ---- V(observation after the last step) for the GAE bootstrap (ppo.py:99-100)
   write_x_row(g.hrow, critic_pk[0], critic_pk[1]);
-  const float last_value = run_net(g, critic_smem, critic_addr).x;
+  const float last_value = run_net<NL>(g, critic_smem, critic_addr).x;
   if (active) {
     cio.last_values[i] = last_value;
     // ---- env state -> HBM (once per rollout).  Every env that reset at ANY step rewrote its read-mostly planes: the
@@ -424,16 +249,28 @@ using namespace gr;
 
 static inline bool bad16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
 
-extern "C" int64_t gr_policy_packed_bytes(void) { return 2 * (int64_t)kNetBytes; }
+extern "C" int64_t gr_policy_packed_bytes(int32_t hidden, int32_t hidden2, int32_t nets) {
+  if (nets < 1 || nets > 2) return GR_ERR_SIZE;
+  if (hidden == 128 && hidden2 == 128) return (int64_t)nets * NetLayout<128, 128>::kNetBytes;
+  if (hidden == 256 && hidden2 == 128) return (int64_t)nets * NetLayout<256, 128>::kNetBytes;
+  return GR_ERR_SIZE;
+}
 
 extern "C" int gr_policy_pack(const GrMlp* actor, const GrMlp* critic, void* packed, void* stream) {
-  if (!actor || !critic || !packed) return GR_ERR_NULL;
-  for (const GrMlp* m : {actor, critic}) {
+  if (!actor || !packed) return GR_ERR_NULL;
+  const int nets = critic ? 2 : 1;
+  const GrMlp* ms[2] = {actor, critic};
+  for (int k = 0; k < nets; ++k) {
+    const GrMlp* m = ms[k];
     if (!m->w1 || !m->b1 || !m->w2 || !m->b2 || !m->w3 || !m->b3) return GR_ERR_NULL;
-    if (m->in_dim != kObsDim || m->hidden != kHid || m->out_dim < 1 || m->out_dim > 4) return GR_ERR_SIZE;
+    if (m->in_dim != kObsDim || m->hidden != actor->hidden || m->hidden2 != actor->hidden2 || m->out_dim < 1 || m->out_dim > 4) return GR_ERR_SIZE;
   }
+  if (gr_policy_packed_bytes(actor->hidden, actor->hidden2, nets) < 0) return GR_ERR_SIZE;
   if (bad16(packed)) return GR_ERR_ALIGN;
-  policy_pack_kernel<<<dim3((kHid * kHid + 255) / 256, 2), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*actor, *critic, static_cast<uint8_t*>(packed));
+  const GrMlp second = critic ? *critic : *actor;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (actor->hidden == 128) policy_pack_kernel<NetLayout<128, 128>><<<dim3((128 * 128 + 255) / 256, nets), 256, 0, s>>>(*actor, second, static_cast<uint8_t*>(packed));
+  else policy_pack_kernel<NetLayout<256, 128>><<<dim3((256 * 128 + 255) / 256, nets), 256, 0, s>>>(*actor, second, static_cast<uint8_t*>(packed));
   return (int)cudaGetLastError();
 }
 

@@ -32,6 +32,11 @@ class AlgoRunner:
         if getattr(self.env.unwrapped, "_bptt", None) is not None:
             self.env.unwrapped._bptt.autograd = False          # the algorithm drives the one-launch window sweep itself
         self.num_steps_per_env = self.cfg["num_steps_per_env"]
+        # opt-in: the forward half of the window as one launch (collect.py / csrc/bptt_collect.cu) + one batched actor backward
+        self.collector = None
+        if self.cfg.get("fused_collection", False):
+            from ..collect import FusedBpttCollector
+            self.collector = FusedBpttCollector(self.env.unwrapped, actor_critic, self.num_steps_per_env, groups_per_cta=int(self.cfg.get("fused_groups_per_cta", 0)))
         self.save_interval = self.cfg.get("save_interval", 200)
         self.log_dir = log_dir
         self.tot_timesteps = 0
@@ -55,7 +60,12 @@ class AlgoRunner:
             start = time.time()
             self.env.unwrapped.detach()                                            # runner.py:110
             rew_sum = torch.zeros((), device=self.device)
-            for _ in range(self.num_steps_per_env):
+            if self.collector is not None:
+                self.collector.pack()
+                obs, critic_obs = self.collector.collect()
+                rew_sum = self.collector.rewards.mean() * self.num_steps_per_env
+                torch.cuda.synchronize(self.device)
+            for _ in range(self.num_steps_per_env if self.collector is None else 0):
                 actions = self.alg.act(obs, critic_obs)
                 obs, rewards, dones, extras = self.env.step(actions)
                 critic_obs = extras["observations"].get("critic", obs)
@@ -64,7 +74,7 @@ class AlgoRunner:
             stop = time.time()
             collection_time = stop - start
             start = stop
-            _, total_loss_mean = self.alg.update()
+            _, total_loss_mean = self.alg.update() if self.collector is None else self.alg.update_fused(self.collector)
             stop = time.time()
             learn_time = stop - start
             self.current_learning_iteration = it

@@ -255,9 +255,9 @@ int gr_storage_gather(const GrStorage* s, const int64_t* indices, int32_t B, con
 #define GR_PHILOX_CALL_ACTION 16    /* Philox call index of the 4 action-noise normals (calls 0..12 belong to env.step) */
 typedef struct GrMlp {               /* torch.nn.Linear parameters, row-major [out][in] fp32, device pointers */
   const float* w1; const float* b1;  /* [hidden, in_dim], [hidden] */
-  const float* w2; const float* b2;  /* [hidden, hidden], [hidden] */
-  const float* w3; const float* b3;  /* [out_dim, hidden], [out_dim] */
-  int32_t in_dim, hidden, out_dim;   /* 16, 128, 1..4 */
+  const float* w2; const float* b2;  /* [hidden2, hidden], [hidden2] */
+  const float* w3; const float* b3;  /* [out_dim, hidden2], [out_dim] */
+  int32_t in_dim, hidden, hidden2, out_dim;   /* 16; first / second hidden width: (128,128) or (256,128); 1..4 */
 } GrMlp;
 typedef struct GrPolicy {
   const void* packed;                /* gr_policy_packed_bytes() bytes written by gr_policy_pack (actor, then critic) */
@@ -279,10 +279,41 @@ typedef struct GrCollectIO {
   int32_t groups_per_cta;            /* 128-env tiles per thread block: 1, 2, 4 or 0 = pick (fewest that fit one wave) */
   int32_t group_skew_ns;             /* one-time start skew between the tiles of a block (de-phases them); 0 = none, -1 = default */
 } GrCollectIO;
-int64_t gr_policy_packed_bytes(void);
+/* packed size of `nets` (1 = actor only, 2 = actor + critic) MLPs of widths 16 -> hidden -> hidden2; < 0: unsupported widths */
+int64_t gr_policy_packed_bytes(int32_t hidden, int32_t hidden2, int32_t nets);
+/* critic may be NULL (actor only); both nets must have the same widths */
 int gr_policy_pack(const GrMlp* actor, const GrMlp* critic, void* packed, void* stream);
 int gr_ppo_collect(const GrConfig* cfg, const GrTrack* track, const GrState* st, const GrRandom* rng, const GrPolicy* policy,
                    const GrStorage* storage, const GrCollectIO* io, void* stream);
+
+/* ---- fused BPTT window (policy MLP on the tensor cores + differentiable env.step with tape, one launch per window) -------
+ * Replaces the forward half of AlgoRunner.learn's window (S/diff_rl/algorithms/runner.py:110-126): T x [BaseModel.act =
+ * actor MLP + rsample (S/diff_rl/algorithms/model.py:63-99), env.step with losses (QD/mdp/losses.py:72-117)].  The tape,
+ * the per-step losses and everything env.step does are those of gr_step_fwd; the reverse sweep stays gr_step_bwd.  The
+ * kernel records what the policy's backward needs -- the observation and the noise each action was computed from -- so
+ * that ONE batched torch forward/backward of the actor over [T*N] rows (action = actor(obs) + sigma * eps, cotangent =
+ * gr_step_bwd's grad_action) replaces T small autograd graphs.  Actor widths (128,128) or (256,128)
+ * (QD/agents/diff_rl_naive_cfg.py:26-32); policy inference with fp16 operands / fp32 accumulation as in gr_ppo_collect. */
+typedef struct GrBpttCollectIO {
+  const float* obs0;                 /* [N,16] observation the window starts from */
+  float* obs_out;                    /* [N,16] observations after the last step (must not alias obs0) */
+  float* critic_obs_out;             /* [N,16] */
+  float* aux_out;                    /* [N] optional */
+  float* obs_seq;                    /* [T,N,16] observation behind action t */
+  float* eps_seq;                    /* [T,N,4]  standard-normal draw behind action t (Philox call GR_PHILOX_CALL_ACTION) */
+  float* actions;                    /* [T,N,4]  the actions applied (mu_fp16 + sigma * eps), optional */
+  float* loss;                       /* [T,N]    extras["losses"] of every step */
+  float* loss_terms;                 /* [T,N,3]  optional */
+  float* reward;                     /* [T,N]    optional */
+  uint8_t* dones;                    /* [T,N]    optional */
+  float* tape;                       /* [T][tiles][GR_TAPE_PLANES][32] float4, as gr_step_fwd writes it */
+  int64_t tape_stride;               /* env capacity of one tape step = 32 * tiles */
+  float* log_accum;                  /* optional */
+  int32_t T;
+  int32_t groups_per_cta;            /* 1, 2 (4 for width 128) or 0 = pick */
+} GrBpttCollectIO;
+int gr_bptt_collect(const GrConfig* cfg, const GrTrack* track, const GrState* st, const GrRandom* rng, const GrPolicy* policy,
+                    int32_t hidden, int32_t hidden2, const GrBpttCollectIO* io, void* stream);
 
 /* ---- env.step() with HOST buffers (the e2e boundary) -------------------------------------------------------------
  * Same call as gr_step_fwd for a caller whose actions / observations live in host memory: replaces

@@ -55,6 +55,7 @@ def main():
         cfg["max_iterations"] = args.iters
         if args.noise_std is not None:
             cfg["policy"]["init_noise_std"] = args.noise_std
+        cfg["fused_collection"] = bool(args.fused)
         env = make_env(num_envs=args.num_envs, device=dev, stage=args.stage, track=args.track, seed=args.seed, differentiable=True,
                        bptt_horizon=cfg["num_steps_per_env"])
         runner = AlgoRunner(env, cfg, log_dir=args.log_dir, device=dev)
