@@ -443,6 +443,38 @@ def bench_extras(dev, cfg, table):
     out["add_transitions_4096_us"] = e0.elapsed_time(e1) * 1e3 / (20 * T)
     del sto
     out["ppo_collection"] = bench_collection(dev, cfg, table)
+    out["bptt_training_c3"] = bench_bptt_training(dev, cfg, table)
+    return out
+
+
+def bench_bptt_training(dev, cfg, table, N: int = 16384, H: int = 32):
+    """BASELINE C3 as the trainer runs it (AlgoRunner.learn, runner.py:107-155): one BPTT iteration = window forward WITH the
+    policy in the loop (BaseModel 16->256->128->4, rsample) + reverse sweep + policy backward + AdamW step.  Fused = one
+    gr_bptt_collect launch + gr_step_bwd + one batched actor backward; step-by-step = torch policy + gr_step_fwd per step."""
+    import dataclasses
+    from generalizableracing_b200.env import RacingVecEnv
+    from generalizableracing_b200.runners import AlgoRunner
+    dcfg = dataclasses.replace(cfg, is_differentiable_physics=True)
+    agent = {"num_steps_per_env": H, "max_iterations": 1000, "save_interval": 10 ** 9, "empirical_normalization": False,
+             "algorithm": {"class_name": "BPTT", "schedule": "CosineAnnealingLR", "optimizer": "AdamW", "learning_rate": 5e-4},
+             "policy": {"class_name": "BaseModel", "actor_hidden_dims": [256, 128], "critic_hidden_dims": [256, 128], "activation": "lrelu", "init_noise_std": 0.3}}
+    out = {"envs": N, "horizon": H}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, fused, iters in (("fused", True, 30), ("step_by_step", False, 5)):
+        env = RacingVecEnv(dcfg, table, N, device=dev, seed=5, bptt_horizon=H)
+        runner = AlgoRunner(env, {**agent, "fused_collection": fused}, log_dir=None, device=str(dev))
+        runner.learn(3, init_at_random_ep_len=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        runner.learn(iters)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / iters
+        out[name] = {"ms_per_iteration": ms, "env_steps_per_s": N * H / (ms * 1e-3)}
+        env.close()
+        del env, runner
+        torch.cuda.empty_cache()
+    out["speedup"] = out["step_by_step"]["ms_per_iteration"] / out["fused"]["ms_per_iteration"]
     return out
 
 
