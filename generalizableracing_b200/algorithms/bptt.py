@@ -54,7 +54,7 @@ class BPTT:
         total_loss_mean = win.loss[:T].mean()
         self.optimizer.zero_grad()
         grad_actions = win.backward_window(grad_scale=1.0 / (T * self.env.num_envs))
-        collector.policy_backward(grad_actions)
+        collector.policy_backward(grad_actions, tf32=collector.backward_tf32)
         D.allreduce_mean_grads(self.actor_critic.parameters())
         self.optimizer.step()
         self.schedule.step()

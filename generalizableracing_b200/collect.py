@@ -129,7 +129,8 @@ class FusedBpttCollector:
     (:meth:`policy_backward`) -- the same function ``sum_t actor(obs_t) + std * eps_t`` the reference differentiates step by
     step.  Actor widths (128, 128) or (256, 128), LeakyReLU / ReLU.  Opt-in (``train_cfg["fused_collection"]``)."""
 
-    def __init__(self, env, policy, horizon: int, groups_per_cta: int = 0):
+    def __init__(self, env, policy, horizon: int, groups_per_cta: int = 0, backward_tf32: bool = False):
+        self.backward_tf32 = bool(backward_tf32)
         if env._bptt is None or env.rng_mode != "philox":
             raise ValueError("fused BPTT collection needs a differentiable env drawing in-kernel (is_differentiable_physics, rng_mode='philox')")
         (l1, l2, l3), slope = _mlp_layers(policy.actor)
@@ -197,11 +198,17 @@ class FusedBpttCollector:
         ex["observations"] = env._obs_dict(dst)
         return dst["obs"], dst["critic"]
 
-    def policy_backward(self, grad_actions: torch.Tensor):
-        """Accumulate d(loss)/d(policy parameters) from the sweep's ``grad_actions`` [T,N,4]: one batched actor pass."""
+    def policy_backward(self, grad_actions: torch.Tensor, tf32: bool = False):
+        """Accumulate d(loss)/d(policy parameters) from the sweep's ``grad_actions`` [T,N,4]: one batched actor pass over
+        [T*N] rows (fp32 like the reference; ``tf32=True`` lets cuBLAS use TF32 tensor cores for it: 4.9 -> 2.2 ms at 16,384 x 32)."""
         T, N = self.T, self.env.num_envs
         p = self.policy
-        mu = p.actor(self.obs_seq.reshape(T * N, L.OBS_DIM))
-        std = p.std if p.noise_std_type == "scalar" else torch.exp(p.log_std)
-        a = mu + std * self.eps_seq.reshape(T * N, L.NUM_ACTIONS)
-        torch.autograd.backward([a], [grad_actions.reshape(T * N, L.NUM_ACTIONS)])
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
+        try:
+            mu = p.actor(self.obs_seq.reshape(T * N, L.OBS_DIM))
+            std = p.std if p.noise_std_type == "scalar" else torch.exp(p.log_std)
+            a = mu + std * self.eps_seq.reshape(T * N, L.NUM_ACTIONS)
+            torch.autograd.backward([a], [grad_actions.reshape(T * N, L.NUM_ACTIONS)])
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev

@@ -36,7 +36,8 @@ class AlgoRunner:
         self.collector = None
         if self.cfg.get("fused_collection", False):
             from ..collect import FusedBpttCollector
-            self.collector = FusedBpttCollector(self.env.unwrapped, actor_critic, self.num_steps_per_env, groups_per_cta=int(self.cfg.get("fused_groups_per_cta", 0)))
+            self.collector = FusedBpttCollector(self.env.unwrapped, actor_critic, self.num_steps_per_env, groups_per_cta=int(self.cfg.get("fused_groups_per_cta", 0)),
+                                                backward_tf32=bool(self.cfg.get("fused_backward_tf32", False)))
         self.save_interval = self.cfg.get("save_interval", 200)
         self.log_dir = log_dir
         self.tot_timesteps = 0
@@ -75,6 +76,7 @@ class AlgoRunner:
             collection_time = stop - start
             start = stop
             _, total_loss_mean = self.alg.update() if self.collector is None else self.alg.update_fused(self.collector)
+            torch.cuda.synchronize(self.device)                # the update is asynchronous: time it, not its enqueue
             stop = time.time()
             learn_time = stop - start
             self.current_learning_iteration = it
