@@ -94,6 +94,10 @@ class GrBpttCollectIO(C.Structure):
                 ("T", c_i), ("groups_per_cta", c_i)]
 
 
+class GrMlpGrad(C.Structure):
+    _fields_ = [("w1", c_p), ("b1", c_p), ("w2", c_p), ("b2", c_p), ("w3", c_p), ("b3", c_p)]
+
+
 class GrHostStep(C.Structure):
     _fields_ = [("action", c_p), ("obs", c_p), ("reward", c_p), ("dones", c_p), ("critic_obs", c_p), ("time_out", c_p)]
 
@@ -127,6 +131,7 @@ PROTOTYPES = {
     "gr_policy_pack": (C.c_int, [C.POINTER(GrMlp), C.POINTER(GrMlp), c_p, c_p]),
     "gr_ppo_collect": (C.c_int, [C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom), C.POINTER(GrPolicy),
                                  C.POINTER(GrStorage), C.POINTER(GrCollectIO), c_p]),
+    "gr_actor_backward": (C.c_int, [C.POINTER(GrPolicy), c_i, c_i, c_p, c_p, c_p, C.c_int64, C.POINTER(GrMlpGrad), c_p]),
     "gr_host_pipe_create": (C.c_int, [c_i, c_i, c_p, C.POINTER(c_p)]),
     "gr_host_pipe_destroy": (C.c_int, [c_p]),
     "gr_host_pipe_step": (C.c_int, [c_p, C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom),

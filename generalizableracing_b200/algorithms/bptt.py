@@ -52,9 +52,12 @@ class BPTT:
         win = self.env._bptt
         T = win.t
         total_loss_mean = win.loss[:T].mean()
-        self.optimizer.zero_grad()
+        self.optimizer.zero_grad(set_to_none=True)
         grad_actions = win.backward_window(grad_scale=1.0 / (T * self.env.num_envs))
-        collector.policy_backward(grad_actions, tf32=collector.backward_tf32)
+        if collector.backward_kernel:
+            collector.policy_backward_kernel(grad_actions)
+        else:
+            collector.policy_backward(grad_actions, tf32=collector.backward_tf32)
         D.allreduce_mean_grads(self.actor_critic.parameters())
         self.optimizer.step()
         self.schedule.step()

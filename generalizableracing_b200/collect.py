@@ -129,8 +129,9 @@ class FusedBpttCollector:
     (:meth:`policy_backward`) -- the same function ``sum_t actor(obs_t) + std * eps_t`` the reference differentiates step by
     step.  Actor widths (128, 128) or (256, 128), LeakyReLU / ReLU.  Opt-in (``train_cfg["fused_collection"]``)."""
 
-    def __init__(self, env, policy, horizon: int, groups_per_cta: int = 0, backward_tf32: bool = False):
+    def __init__(self, env, policy, horizon: int, groups_per_cta: int = 0, backward_tf32: bool = False, backward_kernel: bool = False):
         self.backward_tf32 = bool(backward_tf32)
+        self.backward_kernel = bool(backward_kernel)
         if env._bptt is None or env.rng_mode != "philox":
             raise ValueError("fused BPTT collection needs a differentiable env drawing in-kernel (is_differentiable_physics, rng_mode='philox')")
         (l1, l2, l3), slope = _mlp_layers(policy.actor)
@@ -197,6 +198,28 @@ class FusedBpttCollector:
         dict.pop(ex, "log", None)
         ex["observations"] = env._obs_dict(dst)
         return dst["obs"], dst["critic"]
+
+    def policy_backward_kernel(self, grad_actions: torch.Tensor):
+        """The same gradients from ONE launch of ``gr_actor_backward`` (csrc/actor_backward.cu): activations recomputed and all
+        weight-gradient GEMMs on the tensor cores with fp16 operands (loss-scaled) and fp32 accumulation in tensor memory."""
+        T, N = self.T, self.env.num_envs
+        p = self.policy
+        g = grad_actions.reshape(T * N, L.NUM_ACTIONS)
+        if not g.is_contiguous():
+            g = g.contiguous()
+        scale = (1024.0 / g.abs().max().clamp_min(1e-30)).reshape(1).float()          # device scalar, no host sync
+        l1, l2, l3 = self._layers
+        grads = [torch.zeros_like(t) for t in (l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias)]
+        out = B.GrMlpGrad(*(t.data_ptr() for t in grads))
+        B.check(self._lib.gr_actor_backward(C.byref(self._pol), self.h1, self.h2, self.obs_seq.data_ptr(), g.data_ptr(), scale.data_ptr(), T * N,
+                                            C.byref(out), self.env._stream()), "gr_actor_backward")
+        for t, gt in zip((l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias), grads):
+            t.grad = gt if t.grad is None else t.grad + gt
+        std = p.std if p.noise_std_type == "scalar" else p.log_std
+        gs = (g * self.eps_seq.reshape(T * N, L.NUM_ACTIONS)).sum(dim=0)
+        if p.noise_std_type != "scalar":
+            gs = gs * torch.exp(p.log_std.detach())
+        std.grad = gs if std.grad is None else std.grad + gs
 
     def policy_backward(self, grad_actions: torch.Tensor, tf32: bool = False):
         """Accumulate d(loss)/d(policy parameters) from the sweep's ``grad_actions`` [T,N,4]: one batched actor pass over

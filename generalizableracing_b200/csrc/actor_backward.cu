@@ -1,0 +1,280 @@
+// actor_backward.cu -- d(loss)/d(parameters) of the BPTT actor MLP (16 -> H1 -> H2 -> 4, leaky relu) over R = T*N rows, on the
+// sm_100a tensor cores, in one persistent kernel.
+//
+// Reference path replaced: loss.backward() through BaseModel.actor (S/diff_rl/algorithms/bptt.py:38-44 over the T graphs
+// built by model.py:63-99), as FusedBpttCollector batches it: rows = the (observation, cotangent) pairs of a whole window,
+// cotangent = gr_step_bwd's d(loss)/d(action) (= d/d(mean): action = mean + sigma * eps).  Measured: the batched fp32 torch
+// version of this (cuBLAS SGEMM over 524,288 rows) is 4.9 ms of a 5.5 ms fused BPTT iteration.
+//
+// Per 128-row tile (one thread per row, as in mlp_tc.cuh): recompute H1, H2 (forward layers 1-2), then
+//     dW3^T += H2^T . dA          dH2 = dA . W3          dH2' = dH2 * lrelu'(H2)
+//     dW2   += dH2'^T . H1        db2 += dH2'^T . 1      dH1 = dH2' . W2      dH1' = dH1 * lrelu'(H1)
+//     dW1|b1 += dH1'^T . [X | 1]
+// Every GEMM is a tcgen05.mma on operands that ALREADY sit in shared memory in the per-row layout the forward uses
+// ([chunk of 8 columns][row][8 halfs]): read K-major when the contraction runs over columns (dgrad), MN-major when it runs
+// over the rows (weight gradients) -- same bytes, two descriptors (tools/umma_probe.cu checks both on hardware); the packed
+// forward weights serve the dgrad GEMMs as MN-major B operands, so no transposed copy exists anywhere.  The weight-gradient
+// accumulators stay in tensor memory across all tiles of the CTA (fp32) and are flushed once with atomics.
+// fp16 operands need a loss scale: the cotangent is multiplied by *scale (device scalar, caller picks ~1024 / max|G|) on
+// load and the accumulators are divided by it at the flush.
+#include "mlp_tc.cuh"
+
+namespace gr {
+
+// leaky-relu derivative applied to 8 accumulator columns, gated by the sign of the stored forward activation (same chunk,
+// same thread), written back in place as the next operand
+__device__ __forceinline__ uint4 dact8(const uint32_t* r, uint4 fwd, __half2 slope) {
+  const __half2 zero = __float2half2_rn(0.0f), one_minus = __hsub2(__float2half2_rn(1.0f), slope);
+  const uint32_t f[4] = {fwd.x, fwd.y, fwd.z, fwd.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const __half2 g = __floats2half2_rn(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1]));
+    const __half2 gate = __hfma2(__hgt2(bits_h2(f[q]), zero), one_minus, slope);        // 1 where the unit was active, slope elsewhere
+    o[q] = h2_bits(__hmul2(g, gate));
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+// D[row][0..128) * lrelu'(stored activation) -> fp16, in place over the activation chunks [chunk0, chunk0 + 16) of the row
+__device__ __forceinline__ void dact_epilogue(uint32_t taddr, uint8_t* row_base, int chunk0, __half2 slope) {
+  uint32_t ra[16], rb[16];
+  tmem_ld_x16(taddr, ra);
+#pragma unroll 1
+  for (int c = 0; c < 8; c += 2) {
+    tmem_ld_wait();
+    tmem_ld_x16(taddr + (c + 1) * 16, rb);
+    uint4* p0 = reinterpret_cast<uint4*>(row_base + (chunk0 + 2 * c) * kChunkA);
+    uint4* p1 = reinterpret_cast<uint4*>(row_base + (chunk0 + 2 * c + 1) * kChunkA);
+    *p0 = dact8(ra, *p0, slope);
+    *p1 = dact8(ra + 8, *p1, slope);
+    tmem_ld_wait();
+    if (c + 2 < 8) tmem_ld_x16(taddr + (c + 2) * 16, ra);
+    uint4* p2 = reinterpret_cast<uint4*>(row_base + (chunk0 + 2 * c + 2) * kChunkA);
+    uint4* p3 = reinterpret_cast<uint4*>(row_base + (chunk0 + 2 * c + 3) * kChunkA);
+    *p2 = dact8(rb, *p2, slope);
+    *p3 = dact8(rb + 8, *p3, slope);
+  }
+}
+
+constexpr uint32_t kMnA = 1u << 15, kMnB = 1u << 16;          // instruction-descriptor bits: A / B operand is MN-major
+
+// descriptors over the per-row layout [chunk][128 rows][8 halfs]
+__device__ __forceinline__ uint64_t desc_rows_k(uint32_t addr) { return make_smem_desc(addr, kChunkA, 128); }     // rows = M, columns = K
+__device__ __forceinline__ uint64_t desc_rows_mn(uint32_t addr) { return make_smem_desc(addr, 128, kChunkA); }    // columns = M|N, rows = K
+
+template <class NL>
+__global__ void __launch_bounds__(kTileEnvs, 1) actor_backward_kernel(const GrPolicy pol, const float* __restrict__ X, const float* __restrict__ G,
+                                                                     const float* __restrict__ scale_ptr, const int64_t R, const GrMlpGrad out) {
+  constexpr int H1 = NL::kH1, H2 = NL::kH2, kHalves = H1 / 128;
+  static_assert(H2 == 128 && (H1 == 128 || H1 == 256), "built for 16 -> 128|256 -> 128 -> 4");
+  // tensor memory: scratch accumulator | dW2 [H2 x H1] | dW1 (+ db1) [H1 x 32] as `kHalves` blocks | dW3^T [H2 x 16] | db2 [H2 x 16]
+  constexpr uint32_t kColD = 0, kColW2 = 128, kColW1 = kColW2 + H1, kColW3 = kColW1 + 32 * kHalves, kColB2 = kColW3 + 16, kColsUsed = kColB2 + 16;
+  static_assert(kColsUsed <= 512, "tensor memory budget");
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* w_smem = smem;                                   // forward-packed actor
+  uint8_t* xs = w_smem + NL::kNetBytes;                     // [4][128][8]   obs | 1 1 0.. | 0
+  uint8_t* h1s = xs + 4 * kChunkA;                          // [H1/8][128][8]
+  uint8_t* h2s = h1s + (H1 / 8) * kChunkA;                  // [H2/8][128][8]
+  uint8_t* das = h2s + (H2 / 8) * kChunkA;                  // [2][128][8]   scaled cotangent (4 columns) | 0
+  uint8_t* ones = das + 2 * kChunkA;                        // [2][128][8]   column 0 = 1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + 2 * kChunkA);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
+
+  const int row = threadIdx.x;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(pol.packed);
+    uint4* dst = reinterpret_cast<uint4*>(w_smem);
+    for (int k = row; k < NL::kNetBytes / 16; k += kTileEnvs) dst[k] = __ldg(src + k);
+  }
+  *reinterpret_cast<uint4*>(ones + row * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);            // half(1) in column 0
+  *reinterpret_cast<uint4*>(ones + kChunkA + row * 16) = make_uint4(0u, 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(das + kChunkA + row * 16) = make_uint4(0u, 0u, 0u, 0u);
+  if (row == 0) mbar_init(&bars[0], 1);
+  __syncwarp();
+  if (row < 32) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+
+  GroupCtx g = make_group_ctx(h1s, 0, bars, *tmem_slot, 0, 0, row, pol.negative_slope);       // (hbuf / hrow are not used through g here)
+  g.issuer = row == 0;
+  const uint32_t tm = *tmem_slot;
+  const uint32_t lane_sel = (uint32_t)((row >> 5) * 32) << 16;
+  const uint32_t w_addr = smem_u32(w_smem), xs_a = smem_u32(xs), h1_a = smem_u32(h1s), h2_a = smem_u32(h2s), da_a = smem_u32(das), ones_a = smem_u32(ones);
+  const float scale = __ldg(scale_ptr);
+  float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);            // db3 = sum of the (unscaled) cotangent rows
+  const int64_t tiles = (R + kTileEnvs - 1) / kTileEnvs;
+  bool first = true;
+
+  // one barrier round = [operands written] -> sync -> thread 0 issues a batch -> commit -> everybody waits
+#define GR_STAGE_BEGIN() do { fence_proxy_async_smem(); tc_fence_before_sync(); bar_sync(g.bar_id, kTileEnvs); } while (0)
+#define GR_STAGE_END() do { if (g.issuer) tc_commit(g.bar); stage_wait(g); } while (0)
+
+#pragma unroll 1
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t r = tile * kTileEnvs + row;
+    // ---- operands of this tile: observation row (+ bias ones), scaled cotangent row
+    float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0, o2 = o0, o3 = o0, gr4 = o0;
+    if (r < R) {
+      const float4* xr = reinterpret_cast<const float4*>(X) + r * 4;
+      o0 = __ldcs(xr); o1 = __ldcs(xr + 1); o2 = __ldcs(xr + 2); o3 = __ldcs(xr + 3);
+      gr4 = __ldcs(reinterpret_cast<const float4*>(G) + r);
+    }
+    gsum.x += gr4.x; gsum.y += gr4.y; gsum.z += gr4.z; gsum.w += gr4.w;
+    // (the previous tile's last batch -- dW1 -- read xs and h1s: it was waited for at the end of that tile)
+    write_x_row(xs + row * 16, pack8(o0, o1), pack8(o2, o3));
+    *reinterpret_cast<uint4*>(das + row * 16) =
+        make_uint4(h2_bits(__floats2half2_rn(gr4.x * scale, gr4.y * scale)), h2_bits(__floats2half2_rn(gr4.z * scale, gr4.w * scale)), 0u, 0u);
+
+    // ---- forward layer 1 (128 units at a time) and layer 2: recompute the activations
+#pragma unroll 1
+    for (int h = 0; h < kHalves; ++h) {
+      GR_STAGE_BEGIN();
+      if (g.issuer) {
+        tc_fence_after_sync();
+#pragma unroll
+        for (int kk = 0; kk < kK1 / 16; ++kk)
+          mma_f16_ss(tm + kColD, desc_rows_k(xs_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW1Off + h * 128 * 16 + kk * 2 * (H1 * 16), H1 * 16, 128),
+                     make_idesc_f16(128, 128), kk > 0);
+      }
+      GR_STAGE_END();
+      hidden_epilogue<false, 128>(tm + kColD + lane_sel, h1s + row * 16 + h * 16 * kChunkA, nullptr, g.slope);
+    }
+    GR_STAGE_BEGIN();
+    if (g.issuer) {
+      tc_fence_after_sync();
+#pragma unroll
+      for (int kk = 0; kk < H1 / 16; ++kk)
+        mma_f16_ss(tm + kColD, desc_rows_k(h1_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW2Off + kk * 2 * (H2 * 16), H2 * 16, 128),
+                   make_idesc_f16(128, H2), kk > 0);
+    }
+    GR_STAGE_END();
+    hidden_epilogue<true, H2>(tm + kColD + lane_sel, h2s + row * 16, reinterpret_cast<const uint4*>(w_smem + NL::kB2Off), g.slope);
+
+    // ---- dW3^T += H2^T . dA   (rows are K: both operands MN-major) ;  dH2 = dA . W3  (forward-packed W3 as MN-major B)
+    GR_STAGE_BEGIN();
+    if (g.issuer) {
+      tc_fence_after_sync();
+#pragma unroll
+      for (int kk = 0; kk < kTileEnvs / 16; ++kk)
+        mma_f16_ss(tm + kColW3, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(da_a + kk * 256), make_idesc_f16(H2, 16) | kMnA | kMnB, !first || kk > 0);
+      mma_f16_ss(tm + kColD, desc_rows_k(da_a), make_smem_desc(w_addr + NL::kW3Off, 128, kOutPad * 16), make_idesc_f16(128, H2) | kMnB, false);
+    }
+    GR_STAGE_END();
+    dact_epilogue(tm + kColD + lane_sel, h2s + row * 16, 0, g.slope);                    // h2s now holds dH2'
+
+    // ---- dW2 += dH2'^T . H1 ; db2 += dH2'^T . 1 ; dH1 = dH2' . W2 (forward-packed W2 as MN-major B), 128 units at a time
+#pragma unroll 1
+    for (int h = 0; h < kHalves; ++h) {
+      GR_STAGE_BEGIN();
+      if (g.issuer) {
+        tc_fence_after_sync();
+        if (h == 0) {
+#pragma unroll
+          for (int kk = 0; kk < kTileEnvs / 16; ++kk) {
+            mma_f16_ss(tm + kColW2, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(h1_a + kk * 256), make_idesc_f16(H2, H1) | kMnA | kMnB, !first || kk > 0);
+            mma_f16_ss(tm + kColB2, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(ones_a + kk * 256), make_idesc_f16(H2, 16) | kMnA | kMnB, !first || kk > 0);
+          }
+        }
+#pragma unroll
+        for (int kk = 0; kk < H2 / 16; ++kk)
+          mma_f16_ss(tm + kColD, desc_rows_k(h2_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW2Off + h * 16 * (H2 * 16) + kk * 256, 128, H2 * 16),
+                     make_idesc_f16(128, 128) | kMnB, kk > 0);
+      }
+      GR_STAGE_END();
+      // (h == 0 with two halves: dW2 above also read ALL of h1s -- it completed with this batch, so overwriting is safe)
+      dact_epilogue(tm + kColD + lane_sel, h1s + row * 16, h * 16, g.slope);              // h1s chunks [16h, 16h+16) now hold dH1'
+    }
+
+    // ---- dW1 | db1 += dH1'^T . [X | 1 1 0..]
+    GR_STAGE_BEGIN();
+    if (g.issuer) {
+      tc_fence_after_sync();
+#pragma unroll
+      for (int h = 0; h < kHalves; ++h)
+#pragma unroll
+        for (int kk = 0; kk < kTileEnvs / 16; ++kk)
+          mma_f16_ss(tm + kColW1 + 32 * h, desc_rows_mn(h1_a + h * 16 * kChunkA + kk * 256), desc_rows_mn(xs_a + kk * 256), make_idesc_f16(128, 32) | kMnA | kMnB,
+                     !first || kk > 0);
+    }
+    GR_STAGE_END();
+    first = false;
+  }
+
+  // ---- flush: accumulator row m = TMEM lane m = this thread; everything divided by the loss scale
+  if (!first) {
+    const float inv = 1.0f / scale;
+    const int j = row;                                       // unit of layer 2 (dW2, db2, dW3) / unit within a 128-block of layer 1 (dW1)
+#pragma unroll 1
+    for (int c0 = 0; c0 < H1; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_x16(tm + kColW2 + lane_sel + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) atomicAdd(out.w2 + (int64_t)j * H1 + c0 + k, __uint_as_float(v[k]) * inv);
+    }
+#pragma unroll 1
+    for (int h = 0; h < kHalves; ++h) {
+      uint32_t v[16], w[16];
+      tmem_ld_x16(tm + kColW1 + 32 * h + lane_sel, v);
+      tmem_ld_x16(tm + kColW1 + 32 * h + lane_sel + 16, w);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) atomicAdd(out.w1 + (int64_t)(128 * h + j) * kObsDim + k, __uint_as_float(v[k]) * inv);
+      atomicAdd(out.b1 + 128 * h + j, __uint_as_float(w[0]) * inv);
+    }
+    {
+      uint32_t v[16], w[16];
+      tmem_ld_x16(tm + kColW3 + lane_sel, v);
+      tmem_ld_x16(tm + kColB2 + lane_sel, w);
+      tmem_ld_wait();
+#pragma unroll
+      for (int a = 0; a < GR_NUM_ACTIONS; ++a) atomicAdd(out.w3 + (int64_t)a * H2 + j, __uint_as_float(v[a]) * inv);
+      atomicAdd(out.b2 + j, __uint_as_float(w[0]) * inv);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      gsum.x += __shfl_xor_sync(0xffffffffu, gsum.x, o); gsum.y += __shfl_xor_sync(0xffffffffu, gsum.y, o);
+      gsum.z += __shfl_xor_sync(0xffffffffu, gsum.z, o); gsum.w += __shfl_xor_sync(0xffffffffu, gsum.w, o);
+    }
+    if ((row & 31) == 0) { atomicAdd(out.b3 + 0, gsum.x); atomicAdd(out.b3 + 1, gsum.y); atomicAdd(out.b3 + 2, gsum.z); atomicAdd(out.b3 + 3, gsum.w); }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (row < 32) tmem_dealloc(tm, 512);
+#undef GR_STAGE_BEGIN
+#undef GR_STAGE_END
+}
+
+}  // namespace gr
+
+using namespace gr;
+
+template <class NL>
+static int launch_actor_backward(const GrPolicy* pol, const float* X, const float* G, const float* scale, int64_t R, const GrMlpGrad* out, cudaStream_t s) {
+  const size_t bytes = (size_t)NL::kNetBytes + (size_t)(4 + NL::kH1 / 8 + NL::kH2 / 8 + 2 + 2) * kChunkA + 128;
+  if (bytes > 227 * 1024) return GR_ERR_SMEM;
+  auto kernel = actor_backward_kernel<NL>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return (int)e;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t tiles = (R + kTileEnvs - 1) / kTileEnvs;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  kernel<<<grid, kTileEnvs, bytes, s>>>(*pol, X, G, scale, R, *out);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int gr_actor_backward(const GrPolicy* policy, int32_t hidden, int32_t hidden2, const float* obs, const float* grad_actions,
+                                 const float* scale, int64_t rows, const GrMlpGrad* out, void* stream) {
+  if (!policy || !policy->packed || !obs || !grad_actions || !scale || !out) return GR_ERR_NULL;
+  if (!out->w1 || !out->b1 || !out->w2 || !out->b2 || !out->w3 || !out->b3) return GR_ERR_NULL;
+  if (rows <= 0) return GR_ERR_SIZE;
+  if (!((hidden == 128 || hidden == 256) && hidden2 == 128)) return GR_ERR_SIZE;
+  if (policy->negative_slope < 0.0f || policy->negative_slope > 1.0f) return GR_ERR_CONFIG;
+  if ((reinterpret_cast<uintptr_t>(policy->packed) | reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(grad_actions)) & 15u) return GR_ERR_ALIGN;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return hidden == 256 ? launch_actor_backward<NetLayout<256, 128>>(policy, obs, grad_actions, scale, rows, out, s)
+                       : launch_actor_backward<NetLayout<128, 128>>(policy, obs, grad_actions, scale, rows, out, s);
+}

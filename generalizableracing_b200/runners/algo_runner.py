@@ -37,7 +37,8 @@ class AlgoRunner:
         if self.cfg.get("fused_collection", False):
             from ..collect import FusedBpttCollector
             self.collector = FusedBpttCollector(self.env.unwrapped, actor_critic, self.num_steps_per_env, groups_per_cta=int(self.cfg.get("fused_groups_per_cta", 0)),
-                                                backward_tf32=bool(self.cfg.get("fused_backward_tf32", False)))
+                                                backward_tf32=bool(self.cfg.get("fused_backward_tf32", False)),
+                                                backward_kernel=bool(self.cfg.get("fused_backward_kernel", False)))
         self.save_interval = self.cfg.get("save_interval", 200)
         self.log_dir = log_dir
         self.tot_timesteps = 0

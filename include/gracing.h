@@ -315,6 +315,17 @@ typedef struct GrBpttCollectIO {
 int gr_bptt_collect(const GrConfig* cfg, const GrTrack* track, const GrState* st, const GrRandom* rng, const GrPolicy* policy,
                     int32_t hidden, int32_t hidden2, const GrBpttCollectIO* io, void* stream);
 
+/* ---- actor backward (weight gradients of the BPTT actor on the tensor cores) ------------------------------------------
+ * d(loss)/d(parameters) of `actions = actor(obs) (+ sigma * eps)` over `rows` (observation, cotangent) pairs, cotangent =
+ * d(loss)/d(action): replaces loss.backward() through BaseModel.actor (S/diff_rl/algorithms/bptt.py:38-44 over the graphs of
+ * S/diff_rl/algorithms/model.py:63-99) as FusedBpttCollector batches it.  The activations are recomputed from `obs` with the
+ * packed fp16 weights (as gr_bptt_collect evaluated them); gradients are ACCUMULATED into `out` (zero it first).
+ * `scale`: device scalar; the cotangent is multiplied by it before the fp16 conversion and the result divided by it
+ * (pick ~1024 / max|grad_actions|). */
+typedef struct GrMlpGrad { float* w1; float* b1; float* w2; float* b2; float* w3; float* b3; } GrMlpGrad;   /* shapes as GrMlp, fp32 */
+int gr_actor_backward(const GrPolicy* policy, int32_t hidden, int32_t hidden2, const float* obs /* [rows,16] */,
+                      const float* grad_actions /* [rows,4] */, const float* scale, int64_t rows, const GrMlpGrad* out, void* stream);
+
 /* ---- env.step() with HOST buffers (the e2e boundary) -------------------------------------------------------------
  * Same call as gr_step_fwd for a caller whose actions / observations live in host memory: replaces
  * `env.step(torch.as_tensor(a).to(device))` + `.cpu()` of obs / reward / dones around ManagerBasedDiffRLEnv.step

@@ -89,13 +89,15 @@ def test_fused_bptt_training_runs_and_learns(cuda_lib):
             "algorithm": {"class_name": "BPTT", "schedule": "CosineAnnealingLR", "optimizer": "AdamW", "learning_rate": 5e-4},
             "policy": {"class_name": "BaseModel", "actor_hidden_dims": [256, 128], "critic_hidden_dims": [256, 128], "activation": "lrelu", "init_noise_std": 0.3}}
     curves = {}
-    for fused in (False, True):
+    for mode in ("step_by_step", "fused", "fused+kernel_backward"):
         torch.manual_seed(1)
         env = make_env(num_envs=2048, stage=0, track="figure8", seed=1, differentiable=True, bptt_horizon=32)
-        r = AlgoRunner(env, {**cfgd, "fused_collection": fused}, log_dir=None)
+        r = AlgoRunner(env, {**cfgd, "fused_collection": mode != "step_by_step", "fused_backward_kernel": mode.endswith("backward")}, log_dir=None)
         h = r.learn(40, init_at_random_ep_len=True)
-        curves[fused] = [x["Loss/mean_total_loss"] for x in h]
+        curves[mode] = [x["Loss/mean_total_loss"] for x in h]
     for c in curves.values():
         assert sum(c[-5:]) / 5 < 0.9 * sum(c[:5]) / 5, c
-    a, b = sum(curves[False][-5:]) / 5, sum(curves[True][-5:]) / 5
-    assert abs(a - b) < 0.15 * abs(a), (a, b)
+    a = sum(curves["step_by_step"][-5:]) / 5
+    for mode in ("fused", "fused+kernel_backward"):
+        b = sum(curves[mode][-5:]) / 5
+        assert abs(a - b) < 0.15 * abs(a), (mode, a, b)

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--log_dir", default=None)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--noise_std", type=float, default=None)
+    ap.add_argument("--fused_backward", action="store_true", help="BPTT with --fused: actor weight gradients from gr_actor_backward (tcgen05)")
     ap.add_argument("--graphed", action="store_true", help="PPO: replay the mini-batch update from a CUDA graph")
     ap.add_argument("--fused", action="store_true", help="PPO: collect each rollout with the fused kernel (gr_ppo_collect)")
     args = ap.parse_args()
@@ -56,6 +57,7 @@ def main():
         if args.noise_std is not None:
             cfg["policy"]["init_noise_std"] = args.noise_std
         cfg["fused_collection"] = bool(args.fused)
+        cfg["fused_backward_kernel"] = bool(args.fused_backward)
         env = make_env(num_envs=args.num_envs, device=dev, stage=args.stage, track=args.track, seed=args.seed, differentiable=True,
                        bptt_horizon=cfg["num_steps_per_env"])
         runner = AlgoRunner(env, cfg, log_dir=args.log_dir, device=dev)

@@ -60,6 +60,76 @@ __global__ void __launch_bounds__(128) probe_kernel(const __half* __restrict__ A
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
+// MN-major operands: the SAME per-row layout ([chunk of 8 columns][row][8 halfs], a thread writes its own row) read
+// "transposed": D[m][n] = sum over rows r of P[r][m] * Q[r][n]  (weight-gradient GEMMs: the row dimension is K).
+//   A = P as MN-major: 8 m contiguous (16 B), K = rows at 16 B stride inside a core matrix; LBO = 128 B (next 8 rows),
+//   SBO = R*16 B (next 8 columns); same for B = Q.
+template <int M, int N>
+__global__ void __launch_bounds__(128) probe_mn_kernel(const __half* __restrict__ P, const __half* __restrict__ Q, float* __restrict__ D, const int R) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint8_t* sP = smem;                              // [M/8][R][8]
+  uint8_t* sQ = smem + (size_t)M * R * 2;          // [N/8][R][8]
+  for (int r = tid; r < R; r += 128) {
+    for (int c = 0; c < M / 8; ++c) *reinterpret_cast<uint4*>(sP + (size_t)c * R * 16 + r * 16) = *reinterpret_cast<const uint4*>(P + (size_t)r * M + c * 8);
+    for (int c = 0; c < N / 8; ++c) *reinterpret_cast<uint4*>(sQ + (size_t)c * R * 16 + r * 16) = *reinterpret_cast<const uint4*>(Q + (size_t)r * N + c * 8);
+  }
+  if (tid == 0) mbar_init(&bar, 1);
+  if (warp == 0) tmem_alloc(&tmem_base_slot, 256);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_slot;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_f16(M, N) | (1u << 15) | (1u << 16);          // A and B MN-major
+    for (int kk = 0; kk < R / 16; ++kk) {           // 16 rows (K) per instruction = two 8-row core-matrix groups: +256 B
+      const uint64_t da = make_smem_desc(smem_u32(sP) + kk * 256, 128, R * 16);
+      const uint64_t db = make_smem_desc(smem_u32(sQ) + kk * 256, 128, R * 16);
+      mma_f16_ss(tmem, da, db, idesc, kk > 0);
+    }
+    tc_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after_sync();
+  const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld_x16(taddr + c0, r);
+    tmem_ld_wait();
+    if (tid < M) for (int j = 0; j < 16; ++j) D[(size_t)tid * N + c0 + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+template <int M, int N>
+static double run_mn(int R) {
+  std::vector<__half> hP((size_t)R * M), hQ((size_t)R * N);
+  std::vector<float> ref((size_t)M * N), out((size_t)M * N);
+  srand(11 + R + N);
+  for (auto* v : {&hP, &hQ}) for (auto& x : *v) x = __float2half((float)(rand() % 2001 - 1000) / 1000.0f);
+  for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) { double s = 0; for (int r = 0; r < R; ++r) s += (double)__half2float(hP[(size_t)r * M + m]) * __half2float(hQ[(size_t)r * N + n]); ref[(size_t)m * N + n] = (float)s; }
+  __half *dP, *dQ; float* dD;
+  cudaMalloc(&dP, hP.size() * 2); cudaMalloc(&dQ, hQ.size() * 2); cudaMalloc(&dD, out.size() * 4);
+  cudaMemcpy(dP, hP.data(), hP.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(dQ, hQ.data(), hQ.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemset(dD, 0, out.size() * 4);
+  const size_t smem = (size_t)R * (M + N) * 2;
+  cudaFuncSetAttribute(probe_mn_kernel<M, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  probe_mn_kernel<M, N><<<1, 128, smem>>>(dP, dQ, dD, R);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("  CUDA error (MN-major probe): %s\n", cudaGetErrorString(e)); exit(2); }
+  cudaMemcpy(out.data(), dD, out.size() * 4, cudaMemcpyDeviceToHost);
+  double err = 0;
+  for (size_t i = 0; i < out.size(); ++i) err = fmax(err, fabs((double)out[i] - ref[i]));
+  cudaFree(dP); cudaFree(dQ); cudaFree(dD);
+  return err;
+}
+
 template <int N>
 static double run(int K, int swap_offsets) {
   std::vector<__half> hA(128 * K), hB(N * K);
@@ -93,6 +163,11 @@ int main() {
     printf("%s: max|err| N=128,K=32: %.3g   N=128,K=128: %.3g   N=16,K=128: %.3g\n",
            swap_offsets ? "desc(start, SBO-first)" : "desc(start, LBO=chunk stride, SBO=128)", e1, e2, e3);
     if (!swap_offsets && (e1 > 1e-3 || e2 > 1e-3 || e3 > 1e-3)) bad = 1;
+  }
+  {
+    const double m1 = run_mn<128, 16>(128), m2 = run_mn<128, 256>(128), m3 = run_mn<128, 32>(128);
+    printf("MN-major A and B (K = rows): max|err| M=128,N=16: %.3g   M=128,N=256: %.3g   M=128,N=32: %.3g\n", m1, m2, m3);
+    if (m1 > 1e-3 || m2 > 1e-3 || m3 > 1e-3) bad = 1;
   }
   printf(bad ? "PROBE FAILED for the convention ppo_collect.cu uses\n" : "PROBE OK\n");
   return bad;
