@@ -460,9 +460,9 @@ def bench_bptt_training(dev, cfg, table, N: int = 16384, H: int = 32):
              "policy": {"class_name": "BaseModel", "actor_hidden_dims": [256, 128], "critic_hidden_dims": [256, 128], "activation": "lrelu", "init_noise_std": 0.3}}
     out = {"envs": N, "horizon": H}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for name, fused, iters in (("fused", True, 30), ("step_by_step", False, 5)):
+    for name, fused, kbw, iters in (("fused_kernel_backward", True, True, 30), ("fused", True, False, 30), ("step_by_step", False, False, 5)):
         env = RacingVecEnv(dcfg, table, N, device=dev, seed=5, bptt_horizon=H)
-        runner = AlgoRunner(env, {**agent, "fused_collection": fused}, log_dir=None, device=str(dev))
+        runner = AlgoRunner(env, {**agent, "fused_collection": fused, "fused_backward_kernel": kbw}, log_dir=None, device=str(dev))
         runner.learn(3, init_at_random_ep_len=True)
         torch.cuda.synchronize(dev)
         e0.record()
@@ -475,6 +475,9 @@ def bench_bptt_training(dev, cfg, table, N: int = 16384, H: int = 32):
         del env, runner
         torch.cuda.empty_cache()
     out["speedup"] = out["step_by_step"]["ms_per_iteration"] / out["fused"]["ms_per_iteration"]
+    out["speedup_kernel_backward"] = out["step_by_step"]["ms_per_iteration"] / out["fused_kernel_backward"]["ms_per_iteration"]
+    out["note"] = ("fused = gr_bptt_collect + gr_step_bwd + one batched fp32 torch actor backward; fused_kernel_backward = the actor's "
+                   "weight gradients from gr_actor_backward (tcgen05) instead")
     return out
 
 
