@@ -95,7 +95,13 @@ class GrBpttCollectIO(C.Structure):
 
 
 class GrMlpGrad(C.Structure):
-    _fields_ = [("w1", c_p), ("b1", c_p), ("w2", c_p), ("b2", c_p), ("w3", c_p), ("b3", c_p)]
+    _fields_ = [("w1", c_p), ("b1", c_p), ("w2", c_p), ("b2", c_p), ("w3", c_p), ("b3", c_p), ("out_dim", c_i)]
+
+
+class GrPpoBatch(C.Structure):
+    _fields_ = [("mu", c_p), ("value", c_p), ("sigma", c_p), ("actions", c_p), ("old_log_prob", c_p), ("advantages", c_p), ("returns", c_p),
+                ("old_values", c_p), ("old_mu", c_p), ("old_sigma", c_p), ("clip_param", c_f), ("value_loss_coef", c_f), ("entropy_coef", c_f),
+                ("use_clipped_value_loss", c_i)]
 
 
 class GrHostStep(C.Structure):
@@ -132,6 +138,8 @@ PROTOTYPES = {
     "gr_ppo_collect": (C.c_int, [C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom), C.POINTER(GrPolicy),
                                  C.POINTER(GrStorage), C.POINTER(GrCollectIO), c_p]),
     "gr_actor_backward": (C.c_int, [C.POINTER(GrPolicy), c_i, c_i, c_p, c_p, c_p, C.c_int64, C.POINTER(GrMlpGrad), c_p]),
+    "gr_policy_forward": (C.c_int, [C.POINTER(GrPolicy), c_p, c_p, c_p, c_p, C.c_int64, c_p]),
+    "gr_ppo_loss_grad": (C.c_int, [C.POINTER(GrPpoBatch), C.c_int64, c_p, c_p, c_p, c_p]),
     "gr_host_pipe_create": (C.c_int, [c_i, c_i, c_p, C.POINTER(c_p)]),
     "gr_host_pipe_destroy": (C.c_int, [c_p]),
     "gr_host_pipe_step": (C.c_int, [c_p, C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom),

@@ -19,7 +19,7 @@ from ..storage import RolloutStorage
 class PPO:
     def __init__(self, policy, env=None, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998, lam=0.95,
                  value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, max_grad_norm=1.0, use_clipped_value_loss=True,
-                 schedule="fixed", desired_kl=0.01, device="cuda:0", graphed_update=False, **kwargs):
+                 schedule="fixed", desired_kl=0.01, device="cuda:0", graphed_update=False, kernel_update=False, **kwargs):
         self.env = env
         self.device = device
         self.desired_kl = desired_kl
@@ -42,7 +42,10 @@ class PPO:
         self.use_clipped_value_loss = use_clipped_value_loss
         # opt-in: one mini-batch step (gather -> forward -> losses -> backward -> clip -> Adam, adaptive LR on the device) captured
         # once in a CUDA graph and replayed num_learning_epochs * num_mini_batches times per iteration (single-GPU runs)
-        self.graphed_update = bool(graphed_update)
+        self.graphed_update = bool(graphed_update) or bool(kernel_update)
+        # opt-in on top: the step's forward, loss gradients and weight gradients from libgracing kernels (tensor cores, fp16
+        # operands) instead of torch autograd; clipping and Adam stay torch, everything still replayed from one CUDA graph
+        self.kernel_update = bool(kernel_update)
         self._graph = None
 
     def init_storage(self, training_type, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
@@ -110,6 +113,79 @@ class PPO:
         loss = surrogate_loss + self.value_loss_coef * value_loss - self.entropy_coef * entropy_batch.mean()
         return loss, surrogate_loss, value_loss, mu_batch, sigma_batch
 
+    def _kernel_step_factory(self, g, mbs, desc, lr, mb):
+        """The captured step of `kernel_update`: gather -> pack -> gr_policy_forward -> gr_ppo_loss_grad -> 2 x gr_actor_backward
+        -> (torch) adaptive LR, clip, Adam.  ppo.py:118-178 of the reference without autograd."""
+        import ctypes as C
+        from .. import _lib as B
+        from ..collect import _mlp_layers
+        dev, sto, lib, pol = self.device, self.storage, self.storage._lib, self.policy
+        (a1, a2, a3), slope = _mlp_layers(pol.actor)
+        (c1, c2, c3), slope_c = _mlp_layers(pol.critic)
+        if slope != slope_c or pol.noise_std_type != "scalar":
+            raise ValueError("kernel_update needs one activation for both nets and a scalar action std")
+        for l1, l2, l3, out in ((a1, a2, a3, 4), (c1, c2, c3, 1)):
+            if (l1.in_features, l1.out_features, l2.out_features, l3.out_features) != (16, 128, 128, out):
+                raise ValueError("kernel_update is built for 16 -> 128 -> 128 -> 4 / 1 MLPs")
+        net_bytes = int(lib.gr_policy_packed_bytes(128, 128, 1))
+        g["packed"] = torch.zeros(2 * net_bytes, dtype=torch.uint8, device=dev)
+        g["sigma4"] = torch.ones(4, device=dev)
+        g["mu_new"], g["v_new"] = torch.zeros(mb, 4, device=dev), torch.zeros(mb, device=dev)
+        g["grad_mu"], g["grad_v"] = torch.zeros(mb, 4, device=dev), torch.zeros(mb, 4, device=dev)
+        g["ksums"] = torch.zeros(8, device=dev)
+        # static gradient storage: one flat buffer, the parameters' .grad are views of it for the life of the graph
+        params = list(pol.parameters())
+        flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+        off = 0
+        for p in params:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        g["flat_grad"] = flat
+        mk = lambda l1, l2, l3, out: B.GrMlp(l1.weight.data_ptr(), l1.bias.data_ptr(), l2.weight.data_ptr(), l2.bias.data_ptr(), l3.weight.data_ptr(),
+                                             l3.bias.data_ptr(), 16, 128, 128, out)
+        mlp_a, mlp_c = mk(a1, a2, a3, 4), mk(c1, c2, c3, 1)
+        gr_a = B.GrMlpGrad(a1.weight.grad.data_ptr(), a1.bias.grad.data_ptr(), a2.weight.grad.data_ptr(), a2.bias.grad.data_ptr(), a3.weight.grad.data_ptr(),
+                           a3.bias.grad.data_ptr(), 4)
+        gr_c = B.GrMlpGrad(c1.weight.grad.data_ptr(), c1.bias.grad.data_ptr(), c2.weight.grad.data_ptr(), c2.bias.grad.data_ptr(), c3.weight.grad.data_ptr(),
+                           c3.bias.grad.data_ptr(), 1)
+        pol_both = B.GrPolicy(g["packed"].data_ptr(), g["sigma4"].data_ptr(), slope)
+        pol_c = B.GrPolicy(g["packed"].data_ptr() + net_bytes, g["sigma4"].data_ptr(), slope)
+        batch = B.GrPpoBatch(g["mu_new"].data_ptr(), g["v_new"].data_ptr(), g["sigma4"].data_ptr(), g["actions"].data_ptr(), g["log_prob"].data_ptr(),
+                             g["advantages"].data_ptr(), g["returns"].data_ptr(), g["values"].data_ptr(), g["mu"].data_ptr(), g["sigma"].data_ptr(),
+                             float(self.clip_param), float(self.value_loss_coef), float(self.entropy_coef), int(self.use_clipped_value_loss))
+        g["keep_k"] = (mlp_a, mlp_c, gr_a, gr_c, pol_both, pol_c, batch)
+        adaptive = self.desired_kl is not None and self.schedule == "adaptive"
+
+        def step():
+            st = torch.cuda.current_stream(dev).cuda_stream
+            B.check(lib.gr_storage_gather(C.byref(desc), g["idx"].data_ptr(), mb, C.byref(mbs), st), "gr_storage_gather")
+            B.check(lib.gr_policy_pack(C.byref(mlp_a), C.byref(mlp_c), g["packed"].data_ptr(), st), "gr_policy_pack")
+            with torch.no_grad():
+                g["sigma4"].copy_(pol.std)
+            B.check(lib.gr_policy_forward(C.byref(pol_both), g["obs"].data_ptr(), g["critic_obs"].data_ptr(), g["mu_new"].data_ptr(), g["v_new"].data_ptr(), mb, st),
+                    "gr_policy_forward")
+            with torch.no_grad():
+                g["ksums"].zero_()
+            B.check(lib.gr_ppo_loss_grad(C.byref(batch), mb, g["grad_mu"].data_ptr(), g["grad_v"].data_ptr(), g["ksums"].data_ptr(), st), "gr_ppo_loss_grad")
+            with torch.no_grad():
+                if adaptive:
+                    kl_mean = g["ksums"][2] / g["ksums"][7]
+                    down, up = (lr / 1.5).clamp(min=1e-5), (lr * 1.5).clamp(max=1e-2)
+                    lr.copy_(torch.where(kl_mean > self.desired_kl * 2.0, down, torch.where((kl_mean < self.desired_kl / 2.0) & (kl_mean > 0.0), up, lr)))
+                flat.zero_()
+                g["scale_a"] = (1024.0 / g["grad_mu"].abs().max().clamp_min(1e-30)).reshape(1)
+                g["scale_c"] = (1024.0 / g["grad_v"].abs().max().clamp_min(1e-30)).reshape(1)
+            B.check(lib.gr_actor_backward(C.byref(pol_both), 128, 128, g["obs"].data_ptr(), g["grad_mu"].data_ptr(), g["scale_a"].data_ptr(), mb, C.byref(gr_a), st),
+                    "gr_actor_backward(actor)")
+            B.check(lib.gr_actor_backward(C.byref(pol_c), 128, 128, g["critic_obs"].data_ptr(), g["grad_v"].data_ptr(), g["scale_c"].data_ptr(), mb, C.byref(gr_c), st),
+                    "gr_actor_backward(critic)")
+            with torch.no_grad():
+                pol.std.grad.copy_(g["ksums"][3:7])
+                nn.utils.clip_grad_norm_(pol.parameters(), self.max_grad_norm)
+                self.optimizer.step()
+                g["sums"] += torch.stack([g["ksums"][1], g["ksums"][0]]) / g["ksums"][7]
+        return step
+
     def _build_graph(self):
         """Static mini-batch buffers + one captured optimisation step.  Called after an eager update() (optimizer state exists)."""
         import ctypes as C
@@ -157,11 +233,14 @@ class PPO:
             self.optimizer.step()
             g["sums"] += torch.stack([value_loss.detach(), surrogate_loss.detach()])
 
+        if self.kernel_update:
+            step = self._kernel_step_factory(g, mbs, desc, lr, mb)
         g["keep"] = (mbs, desc)
         # No autograd graph of an earlier (default-stream) step may survive into the capture: its AccumulateGrad nodes are bound
         # to the stream they were created on and would make the engine synchronise across streams while capturing.
         self.policy.distribution = None
-        self.optimizer.zero_grad(set_to_none=True)
+        if not self.kernel_update:             # (the kernel step owns static .grad views)
+            self.optimizer.zero_grad(set_to_none=True)
         torch.cuda.synchronize(dev)
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -169,10 +248,13 @@ class PPO:
             for _ in range(3):
                 step()
                 self.policy.distribution = None
+            if self.kernel_update:             # the step re-binds these two scalars: make the captured instances the live ones
+                g["scale_a"], g["scale_c"] = g["scale_a"].clone(), g["scale_c"].clone()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
-        self.optimizer.zero_grad(set_to_none=True)
+        if not self.kernel_update:
+            self.optimizer.zero_grad(set_to_none=True)
         with torch.cuda.graph(graph, stream=side):
             step()
         g["graph"] = graph

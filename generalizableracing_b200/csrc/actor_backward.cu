@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kTileEnvs, 1) actor_backward_kernel(const GrPo
       tmem_ld_x16(tm + kColB2 + lane_sel, w);
       tmem_ld_wait();
 #pragma unroll
-      for (int a = 0; a < GR_NUM_ACTIONS; ++a) atomicAdd(out.w3 + (int64_t)a * H2 + j, __uint_as_float(v[a]) * inv);
+      for (int a = 0; a < GR_NUM_ACTIONS; ++a) if (a < out.out_dim) atomicAdd(out.w3 + (int64_t)a * H2 + j, __uint_as_float(v[a]) * inv);
       atomicAdd(out.b2 + j, __uint_as_float(w[0]) * inv);
     }
 #pragma unroll
@@ -238,7 +238,12 @@ __global__ void __launch_bounds__(kTileEnvs, 1) actor_backward_kernel(const GrPo
       gsum.x += __shfl_xor_sync(0xffffffffu, gsum.x, o); gsum.y += __shfl_xor_sync(0xffffffffu, gsum.y, o);
       gsum.z += __shfl_xor_sync(0xffffffffu, gsum.z, o); gsum.w += __shfl_xor_sync(0xffffffffu, gsum.w, o);
     }
-    if ((row & 31) == 0) { atomicAdd(out.b3 + 0, gsum.x); atomicAdd(out.b3 + 1, gsum.y); atomicAdd(out.b3 + 2, gsum.z); atomicAdd(out.b3 + 3, gsum.w); }
+    if ((row & 31) == 0) {
+      atomicAdd(out.b3 + 0, gsum.x);
+      if (out.out_dim > 1) atomicAdd(out.b3 + 1, gsum.y);
+      if (out.out_dim > 2) atomicAdd(out.b3 + 2, gsum.z);
+      if (out.out_dim > 3) atomicAdd(out.b3 + 3, gsum.w);
+    }
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -270,7 +275,7 @@ extern "C" int gr_actor_backward(const GrPolicy* policy, int32_t hidden, int32_t
                                  const float* scale, int64_t rows, const GrMlpGrad* out, void* stream) {
   if (!policy || !policy->packed || !obs || !grad_actions || !scale || !out) return GR_ERR_NULL;
   if (!out->w1 || !out->b1 || !out->w2 || !out->b2 || !out->w3 || !out->b3) return GR_ERR_NULL;
-  if (rows <= 0) return GR_ERR_SIZE;
+  if (rows <= 0 || out->out_dim < 1 || out->out_dim > 4) return GR_ERR_SIZE;
   if (!((hidden == 128 || hidden == 256) && hidden2 == 128)) return GR_ERR_SIZE;
   if (policy->negative_slope < 0.0f || policy->negative_slope > 1.0f) return GR_ERR_CONFIG;
   if ((reinterpret_cast<uintptr_t>(policy->packed) | reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(grad_actions)) & 15u) return GR_ERR_ALIGN;

@@ -1,0 +1,183 @@
+// ppo_update.cu -- one PPO mini-batch step without autograd: policy forward on the tensor cores and the loss gradients.
+//
+// Reference path replaced (S = standalone): the body of PPO.update's mini-batch loop (S/rsl_rl/ext/algorithms/ppo.py:118-171):
+//   policy.act / get_actions_log_prob / evaluate            -> policy_forward_kernel  (mu = actor(obs), v = critic(critic_obs))
+//   ratio, clipped surrogate, clipped value loss, entropy,  -> ppo_loss_grad_kernel   (d loss / d mu, d loss / d v, d loss / d std,
+//   KL for the adaptive learning rate, loss.backward() up      loss and KL sums)
+//   to the network outputs
+// The weight gradients then come from gr_actor_backward (actor with d/d mu, critic with d/d v); clipping and Adam stay torch.
+#include "mlp_tc.cuh"
+
+namespace gr {
+
+using NLp = NetLayout<128, 128>;
+constexpr int kFwdGroups = 2;                // two 128-row tiles in flight per CTA (one covers the other's MMA latency)
+
+// mu [rows,4], value [rows]: persistent over 128-row tiles, both nets resident in shared memory
+__global__ void __launch_bounds__(kFwdGroups * kTileEnvs, 1) policy_forward_kernel(const GrPolicy pol, const float* __restrict__ obs,
+                                                                                  const float* __restrict__ critic_obs, float* __restrict__ mu,
+                                                                                  float* __restrict__ value, const int64_t R) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* w_smem = smem;
+  uint8_t* h_smem = smem + 2 * NLp::kNetBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(h_smem + kFwdGroups * NLp::kHBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kFwdGroups);
+  const int tid = threadIdx.x, grp = tid / kTileEnvs, row = tid % kTileEnvs;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(pol.packed);
+    uint4* dst = reinterpret_cast<uint4*>(w_smem);
+    for (int k = tid; k < 2 * NLp::kNetBytes / 16; k += kFwdGroups * kTileEnvs) dst[k] = __ldg(src + k);
+  }
+  if (tid < kFwdGroups) mbar_init(&bars[tid], 1);
+  __syncwarp();
+  if (tid < 32) tmem_alloc(tmem_slot, kFwdGroups * NLp::kCols);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  GroupCtx g = make_group_ctx(h_smem, NLp::kHBytes, bars, *tmem_slot, NLp::kCols, grp, row, pol.negative_slope);
+  const uint32_t w_addr = smem_u32(w_smem);
+  const int64_t tiles = (R + kTileEnvs - 1) / kTileEnvs;
+  // both groups of a CTA run the same number of rounds (the named barriers are per group, the tile loop is not)
+#pragma unroll 1
+  for (int64_t base = (int64_t)blockIdx.x * kFwdGroups; base < tiles; base += (int64_t)gridDim.x * kFwdGroups) {
+    const int64_t tile = base + grp;
+    const int64_t r = tile * kTileEnvs + row;
+    const bool live = tile < tiles && r < R;
+    float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0, o2 = o0, o3 = o0, c0 = o0, c1 = o0, c2 = o0, c3 = o0;
+    if (live) {
+      const float4* xo = reinterpret_cast<const float4*>(obs) + r * 4;
+      const float4* xc = reinterpret_cast<const float4*>(critic_obs) + r * 4;
+      o0 = __ldcs(xo); o1 = __ldcs(xo + 1); o2 = __ldcs(xo + 2); o3 = __ldcs(xo + 3);
+      c0 = __ldcs(xc); c1 = __ldcs(xc + 1); c2 = __ldcs(xc + 2); c3 = __ldcs(xc + 3);
+    }
+    write_x_row(g.hrow, pack8(o0, o1), pack8(o2, o3));
+    const float4 m = run_net<NLp>(g, w_smem, w_addr);
+    tc_fence_before_sync();
+    write_x_row(g.hrow, pack8(c0, c1), pack8(c2, c3));
+    const float4 v = run_net<NLp>(g, w_smem + NLp::kNetBytes, w_addr + NLp::kNetBytes);
+    tc_fence_before_sync();
+    if (live) {
+      __stcs(reinterpret_cast<float4*>(mu) + r, m);
+      value[r] = v.x;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(*tmem_slot, kFwdGroups * NLp::kCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// loss gradients of one mini-batch (ppo.py:118-171), one thread per row
+//   sums[0] += sum surrogate, [1] += sum value loss, [2] += sum KL, [3..6] += d loss / d std, [7] += rows
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) ppo_loss_grad_kernel(const GrPpoBatch b, const int64_t R, float* __restrict__ grad_mu, float* __restrict__ grad_value,
+                                                           float* __restrict__ sums) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (r < R) {
+    const float inv_rows = 1.0f / (float)R;
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(b.mu) + r), a = __ldg(reinterpret_cast<const float4*>(b.actions) + r);
+    const float4 sg = __ldg(reinterpret_cast<const float4*>(b.sigma));
+    const float4 omu = __ldg(reinterpret_cast<const float4*>(b.old_mu) + r), osg = __ldg(reinterpret_cast<const float4*>(b.old_sigma) + r);
+    const float mus[4] = {mu.x, mu.y, mu.z, mu.w}, as[4] = {a.x, a.y, a.z, a.w}, sgs[4] = {sg.x, sg.y, sg.z, sg.w};
+    const float omus[4] = {omu.x, omu.y, omu.z, omu.w}, osgs[4] = {osg.x, osg.y, osg.z, osg.w};
+    // log-prob of the stored action under the current policy (Normal.log_prob summed over the action dims), KL(old || new) (ppo.py:126-129)
+    float logp = 0.0f, kl = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float d = as[k] - mus[k];
+      logp += -(d * d) / (2.0f * sgs[k] * sgs[k]) - logf(sgs[k]) - 0.91893853320467274178f;
+      const float dm = omus[k] - mus[k];
+      kl += logf(sgs[k] / osgs[k] + 1.0e-5f) + (osgs[k] * osgs[k] + dm * dm) / (2.0f * sgs[k] * sgs[k]) - 0.5f;
+    }
+    const float adv = b.advantages[r];
+    const float ratio = expf(logp - b.old_log_prob[r]);
+    const float s1 = -adv * ratio;
+    const float s2 = -adv * fminf(fmaxf(ratio, 1.0f - b.clip_param), 1.0f + b.clip_param);
+    const float surrogate = fmaxf(s1, s2);
+    // d max(s1, s2) / d logp: s1 carries -adv * ratio; s2 carries it only inside the clip range (where s1 == s2: the tie's two halves add up)
+    const float g_logp = (s1 >= s2 ? -adv * ratio : 0.0f) * inv_rows;
+    // value loss (ppo.py:153-160)
+    const float v = b.value[r], ret = b.returns[r];
+    float vloss, g_v;
+    if (b.use_clipped_value_loss) {
+      const float ov = b.old_values[r];
+      const float dv = v - ov;
+      const bool inside = dv >= -b.clip_param && dv <= b.clip_param;     // torch.clamp passes the gradient at the bounds
+      const float vc = ov + fminf(fmaxf(dv, -b.clip_param), b.clip_param);
+      const float l1 = (v - ret) * (v - ret), l2 = (vc - ret) * (vc - ret);
+      vloss = fmaxf(l1, l2);
+      g_v = l1 >= l2 ? 2.0f * (v - ret) : (inside ? 2.0f * (vc - ret) : 0.0f);
+      if (l1 == l2 && !inside) g_v *= 0.5f;                              // exact tie outside the range: only the l1 half has a gradient
+    } else {
+      vloss = (ret - v) * (ret - v);
+      g_v = 2.0f * (v - ret);
+    }
+    g_v *= b.value_loss_coef * inv_rows;
+    float4 gm;
+    float gs[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float d = as[k] - mus[k], inv_s = 1.0f / sgs[k];
+      (&gm.x)[k] = g_logp * d * inv_s * inv_s;
+      // d logp / d std = d^2 / std^3 - 1 / std ; entropy = sum(0.5 + 0.5 log 2pi + log std) enters with -entropy_coef * mean
+      gs[k] = g_logp * (d * d * inv_s * inv_s * inv_s - inv_s) - b.entropy_coef * inv_rows * inv_s;
+    }
+    __stcs(reinterpret_cast<float4*>(grad_mu) + r, gm);
+    __stcs(reinterpret_cast<float4*>(grad_value) + r, make_float4(g_v, 0.f, 0.f, 0.f));
+    acc[0] = surrogate; acc[1] = vloss; acc[2] = kl; acc[3] = gs[0]; acc[4] = gs[1]; acc[5] = gs[2]; acc[6] = gs[3]; acc[7] = 1.0f;
+  }
+  __shared__ float part[8][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float s = warp_sum_f(acc[k]);
+    if (lane == 0) part[wid][k] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float s = 0.0f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += part[w][threadIdx.x];
+    atomicAdd(sums + threadIdx.x, s);
+  }
+}
+
+}  // namespace gr
+
+using namespace gr;
+
+extern "C" int gr_policy_forward(const GrPolicy* policy, const float* obs, const float* critic_obs, float* mu, float* value, int64_t rows, void* stream) {
+  if (!policy || !policy->packed || !obs || !critic_obs || !mu || !value) return GR_ERR_NULL;
+  if (rows <= 0) return GR_ERR_SIZE;
+  if (policy->negative_slope < 0.0f || policy->negative_slope > 1.0f) return GR_ERR_CONFIG;
+  if ((reinterpret_cast<uintptr_t>(policy->packed) | reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(critic_obs) | reinterpret_cast<uintptr_t>(mu)) & 15u)
+    return GR_ERR_ALIGN;
+  const size_t bytes = 2 * (size_t)NLp::kNetBytes + (size_t)kFwdGroups * NLp::kHBytes + 128;
+  cudaError_t e = cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return (int)e;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t pairs = ((rows + kTileEnvs - 1) / kTileEnvs + kFwdGroups - 1) / kFwdGroups;
+  const int grid = (int)(pairs < sms ? pairs : sms);
+  policy_forward_kernel<<<grid, kFwdGroups * kTileEnvs, bytes, reinterpret_cast<cudaStream_t>(stream)>>>(*policy, obs, critic_obs, mu, value, rows);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int gr_ppo_loss_grad(const GrPpoBatch* b, int64_t rows, float* grad_mu, float* grad_value, float* sums, void* stream) {
+  if (!b || !grad_mu || !grad_value || !sums) return GR_ERR_NULL;
+  if (!b->mu || !b->value || !b->sigma || !b->actions || !b->old_log_prob || !b->advantages || !b->returns || !b->old_mu || !b->old_sigma) return GR_ERR_NULL;
+  if (b->use_clipped_value_loss && !b->old_values) return GR_ERR_NULL;
+  if (rows <= 0) return GR_ERR_SIZE;
+  if ((reinterpret_cast<uintptr_t>(b->mu) | reinterpret_cast<uintptr_t>(b->actions) | reinterpret_cast<uintptr_t>(b->old_mu) | reinterpret_cast<uintptr_t>(b->old_sigma) |
+       reinterpret_cast<uintptr_t>(b->sigma) | reinterpret_cast<uintptr_t>(grad_mu) | reinterpret_cast<uintptr_t>(grad_value)) & 15u)
+    return GR_ERR_ALIGN;
+  ppo_loss_grad_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*b, rows, grad_mu, grad_value, sums);
+  return (int)cudaGetLastError();
+}

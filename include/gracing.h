@@ -322,9 +322,28 @@ int gr_bptt_collect(const GrConfig* cfg, const GrTrack* track, const GrState* st
  * packed fp16 weights (as gr_bptt_collect evaluated them); gradients are ACCUMULATED into `out` (zero it first).
  * `scale`: device scalar; the cotangent is multiplied by it before the fp16 conversion and the result divided by it
  * (pick ~1024 / max|grad_actions|). */
-typedef struct GrMlpGrad { float* w1; float* b1; float* w2; float* b2; float* w3; float* b3; } GrMlpGrad;   /* shapes as GrMlp, fp32 */
+typedef struct GrMlpGrad { float* w1; float* b1; float* w2; float* b2; float* w3; float* b3; int32_t out_dim; } GrMlpGrad;   /* shapes as GrMlp, fp32; w3 [out_dim, hidden2] */
 int gr_actor_backward(const GrPolicy* policy, int32_t hidden, int32_t hidden2, const float* obs /* [rows,16] */,
                       const float* grad_actions /* [rows,4] */, const float* scale, int64_t rows, const GrMlpGrad* out, void* stream);
+
+/* ---- PPO update on the kernels (forward, loss gradients; the weight gradients come from gr_actor_backward) -----------------
+ * One mini-batch step of PPO.update (S/rsl_rl/ext/algorithms/ppo.py:118-171) without autograd:
+ *   gr_policy_forward : mu = actor(obs), v = critic(critic_obs) for `rows` rows (packed fp16 nets, tensor cores)
+ *   gr_ppo_loss_grad  : clipped surrogate + clipped value loss + entropy bonus of the batch -> d(loss)/d(mu) [rows,4],
+ *                       d(loss)/d(v) [rows,4] (column 0), and sums[0..7] += (surrogate, value loss, KL, d/d(std) x 4, rows)
+ * followed by two gr_actor_backward launches (actor with d/d(mu), critic with d/d(v)). */
+int gr_policy_forward(const GrPolicy* policy /* packed actor + critic, widths (128,128) */, const float* obs, const float* critic_obs,
+                      float* mu /* [rows,4] */, float* value /* [rows] */, int64_t rows, void* stream);
+typedef struct GrPpoBatch {
+  const float* mu; const float* value;                 /* current policy outputs [rows,4], [rows] */
+  const float* sigma;                                  /* device [4]: current action std */
+  const float* actions; const float* old_log_prob; const float* advantages; const float* returns; const float* old_values;
+  const float* old_mu; const float* old_sigma;         /* [rows,4] each */
+  float clip_param, value_loss_coef, entropy_coef;
+  int32_t use_clipped_value_loss;
+} GrPpoBatch;
+int gr_ppo_loss_grad(const GrPpoBatch* batch, int64_t rows, float* grad_mu /* [rows,4] */, float* grad_value /* [rows,4] */,
+                     float* sums /* [8] accumulated */, void* stream);
 
 /* ---- env.step() with HOST buffers (the e2e boundary) -------------------------------------------------------------
  * Same call as gr_step_fwd for a caller whose actions / observations live in host memory: replaces

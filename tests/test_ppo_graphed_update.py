@@ -9,13 +9,13 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _make(graphed, N=512, T=24, seed=3):
+def _make(graphed, N=512, T=24, seed=3, kernel=False):
     from generalizableracing_b200.algorithms.ppo import PPO
     from generalizableracing_b200.modules import ActorCritic
     torch.manual_seed(seed)
     pol = ActorCritic(16, 16, 4).cuda()
     alg = PPO(pol, device="cuda:0", num_learning_epochs=5, num_mini_batches=4, schedule="adaptive", learning_rate=5e-4, gamma=0.99, lam=0.95,
-              desired_kl=0.01, graphed_update=graphed)
+              desired_kl=0.01, graphed_update=graphed, kernel_update=kernel)
     alg.init_storage("rl", N, T, [16], [16], [4])
     return alg
 
@@ -62,3 +62,25 @@ def test_graphed_update_matches_eager(cuda_lib):
         assert abs(eager.last["value_function"] - graphed.last["value_function"]) < 1e-3 * abs(eager.last["value_function"]) + 1e-6
         assert abs(eager.last["surrogate"] - graphed.last["surrogate"]) < 2e-4 + 1e-2 * abs(eager.last["surrogate"])
     assert graphed._graph is not None
+
+
+def test_kernel_update_tracks_eager(cuda_lib):
+    """kernel_update: forward, loss gradients and weight gradients from the libgracing kernels (fp16 operands on the tensor
+    cores).  Same mini-batches => the same losses to fp16-forward accuracy, and the policies stay close as functions."""
+    eager, kern = _make(False, N=2048), _make(True, N=2048, kernel=True)
+    kern.policy.load_state_dict(copy.deepcopy(eager.policy.state_dict()))
+    probe = torch.randn(4096, 16, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    for it in range(3):
+        for alg in (eager, kern):
+            _fill(alg, 200 + it)
+            torch.manual_seed(17 + it)
+            alg.last = alg.update()
+        with torch.no_grad():
+            da = float((eager.policy.actor(probe) - kern.policy.actor(probe)).abs().max())
+            dc = float((eager.policy.critic(probe) - kern.policy.critic(probe)).abs().max())
+        print(it, eager.last, kern.last, eager.learning_rate, kern.learning_rate, da, dc)
+        assert abs(eager.last["value_function"] - kern.last["value_function"]) < 2e-2 * abs(eager.last["value_function"]) + 1e-4, it
+        assert abs(eager.last["surrogate"] - kern.last["surrogate"]) < 2e-3 + 5e-2 * abs(eager.last["surrogate"]), it
+        assert da < 5e-2 and dc < 5e-2, (it, da, dc)
+        assert float((eager.policy.std - kern.policy.std).abs().max()) < 5e-3
+    assert kern._graph is not None and "ksums" in kern._graph

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--noise_std", type=float, default=None)
     ap.add_argument("--fused_backward", action="store_true", help="BPTT with --fused: actor weight gradients from gr_actor_backward (tcgen05)")
     ap.add_argument("--graphed", action="store_true", help="PPO: replay the mini-batch update from a CUDA graph")
+    ap.add_argument("--kernel_update", action="store_true", help="PPO: graphed update with forward / loss / weight gradients from libgracing kernels")
     ap.add_argument("--fused", action="store_true", help="PPO: collect each rollout with the fused kernel (gr_ppo_collect)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -50,6 +51,7 @@ def main():
             cfg["policy"]["init_noise_std"] = args.noise_std
         cfg["fused_collection"] = bool(args.fused)
         cfg["algorithm"]["graphed_update"] = bool(args.graphed)
+        cfg["algorithm"]["kernel_update"] = bool(args.kernel_update)
         runner = OnPolicyRunner(env, cfg, log_dir=args.log_dir, device=dev)
     else:
         cfg = json.loads(json.dumps(BPTT_CFG))
