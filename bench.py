@@ -444,6 +444,42 @@ def bench_extras(dev, cfg, table):
     del sto
     out["ppo_collection"] = bench_collection(dev, cfg, table)
     out["bptt_training_c3"] = bench_bptt_training(dev, cfg, table)
+    out["ppo_training_c2"] = bench_ppo_training(dev, cfg, table)
+    return out
+
+
+def bench_ppo_training(dev, cfg, table, N: int = 4096, T: int = 24):
+    """BASELINE C2 as the trainer runs it (OnPolicyRunner.learn, on_policy_runner.py:135-183): one PPO iteration = 24-step
+    rollout + GAE + 5 epochs x 4 mini-batches.  step_by_step = torch policy + gr_step_fwd + gr_storage_add, eager torch update (the
+    reference's structure on our env kernels); fused = gr_ppo_collect + CUDA-graph torch update; fused_kernel_update = the
+    update's forward / loss / weight gradients from libgracing kernels as well."""
+    from generalizableracing_b200.env import RacingVecEnv
+    from generalizableracing_b200.runners import OnPolicyRunner
+    agent = {"num_steps_per_env": T, "save_interval": 10 ** 9, "empirical_normalization": False,
+             "policy": {"class_name": "ActorCritic", "init_noise_std": 1.0, "actor_hidden_dims": [128, 128], "critic_hidden_dims": [128, 128], "activation": "lrelu"},
+             "algorithm": {"class_name": "PPO", "value_loss_coef": 1.0, "use_clipped_value_loss": True, "clip_param": 0.2, "entropy_coef": 0.0,
+                           "num_learning_epochs": 5, "num_mini_batches": 4, "learning_rate": 5.0e-4, "schedule": "adaptive", "gamma": 0.99, "lam": 0.95,
+                           "desired_kl": 0.01, "max_grad_norm": 1.0}}
+    out = {"envs": N, "steps_per_env": T}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, fused, graphed, kern, iters in (("fused_kernel_update", True, True, True, 20), ("fused_graphed_update", True, True, False, 10), ("step_by_step", False, False, False, 5)):
+        a = json.loads(json.dumps(agent))
+        a["fused_collection"] = fused
+        a["algorithm"]["graphed_update"], a["algorithm"]["kernel_update"] = graphed, kern
+        env = RacingVecEnv(cfg, table, N, device=dev, seed=9)
+        runner = OnPolicyRunner(env, a, log_dir=None, device=str(dev))
+        runner.learn(3, init_at_random_ep_len=True)          # eager first update, graph capture on the second
+        torch.cuda.synchronize(dev)
+        e0.record()
+        runner.learn(iters)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / iters
+        out[name] = {"ms_per_iteration": ms, "env_steps_per_s": N * T / (ms * 1e-3)}
+        env.close()
+        del env, runner
+        torch.cuda.empty_cache()
+    out["speedup_kernel_update"] = out["step_by_step"]["ms_per_iteration"] / out["fused_kernel_update"]["ms_per_iteration"]
     return out
 
 
