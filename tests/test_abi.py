@@ -65,6 +65,19 @@ def test_argument_errors_are_reported_without_launch(lib):
     assert lib.gr_gae_scratch_bytes(4096) >= 3 * 8 * (4096 // 128)
     st = B.GrStorage()
     assert lib.gr_compute_returns(C.byref(st), None, 0.99, 0.95, None, None, 1, None) == -1
+    # fused collection / update entry points: argument errors come back before anything is launched
+    assert lib.gr_ppo_collect(None, None, None, None, None, None, None, None) == -1
+    assert lib.gr_bptt_collect(None, None, None, None, None, 256, 128, None, None) == -1
+    assert lib.gr_actor_backward(None, 256, 128, None, None, None, 128, None, None) == -1
+    assert lib.gr_policy_forward(None, None, None, None, None, 128, None) == -1
+    assert lib.gr_ppo_loss_grad(None, 128, None, None, None, None) == -1
+    assert lib.gr_policy_pack(None, None, None, None) == -1
+    assert lib.gr_policy_packed_bytes(128, 128, 2) == 2 * 45440 and lib.gr_policy_packed_bytes(256, 128, 1) == 86400
+    assert lib.gr_policy_packed_bytes(64, 64, 1) < 0 and lib.gr_policy_packed_bytes(128, 128, 3) < 0
+    pol, grads = B.GrPolicy(16, 16, 0.01), B.GrMlpGrad(16, 16, 16, 16, 16, 16, 4)
+    assert lib.gr_actor_backward(C.byref(pol), 64, 128, C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), 128, C.byref(grads), None) == -2      # widths
+    assert lib.gr_actor_backward(C.byref(pol), 256, 128, C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), 0, C.byref(grads), None) == -2       # rows
+    assert lib.gr_actor_backward(C.byref(pol), 256, 128, C.c_void_p(8), C.c_void_p(16), C.c_void_p(16), 128, C.byref(grads), None) == -3      # alignment
     pipe = C.c_void_p()
     assert lib.gr_host_pipe_create(64, 2, None, None) == -1
     assert lib.gr_host_pipe_create(0, 2, None, C.byref(pipe)) == -2
