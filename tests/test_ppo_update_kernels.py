@@ -1,0 +1,75 @@
+"""gr_ppo_loss_grad against torch.autograd on the reference's loss expression (standalone/rsl_rl/ext/algorithms/ppo.py:143-171),
+for every option (clipped / plain value loss, entropy bonus), and gr_policy_forward against the fp32 modules."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rows,clipped,entropy_coef", [(1000, True, 0.0), (24576, True, 0.005), (777, False, 0.01)])
+def test_loss_gradients_match_autograd(cuda_lib, rows, clipped, entropy_coef):
+    from generalizableracing_b200 import _lib as B
+    lib = cuda_lib
+    g = torch.Generator(device="cuda").manual_seed(rows)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    mu, v = rn(rows, 4).requires_grad_(True), rn(rows).requires_grad_(True)
+    std = (0.5 + torch.rand(4, device="cuda", generator=g)).requires_grad_(True)
+    old_mu, old_sigma = mu.detach() + 0.3 * rn(rows, 4), (std.detach() * (1 + 0.1 * rn(4))).abs().expand(rows, 4).contiguous()
+    actions = old_mu + old_sigma * rn(rows, 4)
+    old_logp = torch.distributions.Normal(old_mu, old_sigma).log_prob(actions).sum(-1)
+    adv, ret, old_v = rn(rows), rn(rows), v.detach() + 0.3 * rn(rows)
+    clip, vcoef = 0.2, 1.0
+    # --- reference expression
+    dist = torch.distributions.Normal(mu, std.expand_as(mu))
+    logp = dist.log_prob(actions).sum(-1)
+    ratio = torch.exp(logp - old_logp)
+    surrogate = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 1 - clip, 1 + clip)).mean()
+    if clipped:
+        vc = old_v + (v - old_v).clamp(-clip, clip)
+        vloss = torch.max((v - ret).pow(2), (vc - ret).pow(2)).mean()
+    else:
+        vloss = (ret - v).pow(2).mean()
+    loss = surrogate + vcoef * vloss - entropy_coef * dist.entropy().sum(-1).mean()
+    loss.backward()
+    kl = torch.sum(torch.log(std.detach() / old_sigma + 1e-5) + (old_sigma ** 2 + (old_mu - mu.detach()) ** 2) / (2 * std.detach() ** 2) - 0.5, dim=-1).mean()
+    # --- kernel
+    gm, gv, sums = torch.zeros(rows, 4, device="cuda"), torch.zeros(rows, 4, device="cuda"), torch.zeros(8, device="cuda")
+    sig = std.detach().contiguous()
+    b = B.GrPpoBatch(mu.data_ptr(), v.data_ptr(), sig.data_ptr(), actions.data_ptr(), old_logp.data_ptr(), adv.data_ptr(), ret.data_ptr(), old_v.data_ptr(),
+                     old_mu.data_ptr(), old_sigma.data_ptr(), clip, vcoef, entropy_coef, int(clipped))
+    B.check(lib.gr_ppo_loss_grad(C.byref(b), rows, gm.data_ptr(), gv.data_ptr(), sums.data_ptr(), torch.cuda.current_stream().cuda_stream), "gr_ppo_loss_grad")
+    torch.cuda.synchronize()
+    assert torch.allclose(gm, mu.grad, rtol=2e-4, atol=1e-9 + 1e-5 * float(mu.grad.abs().max()))
+    assert torch.allclose(gv[:, 0], v.grad, rtol=2e-4, atol=1e-9 + 1e-5 * float(v.grad.abs().max())) and float(gv[:, 1:].abs().max()) == 0.0
+    assert torch.allclose(sums[3:7], std.grad, rtol=2e-3, atol=1e-5 * float(std.grad.abs().max()) + 1e-7)
+    assert int(sums[7]) == rows
+    assert abs(float(sums[0]) / rows - float(surrogate)) < 1e-5 + 1e-4 * abs(float(surrogate))
+    assert abs(float(sums[1]) / rows - float(vloss)) < 1e-4 * abs(float(vloss))
+    assert abs(float(sums[2]) / rows - float(kl)) < 1e-4 * abs(float(kl)) + 1e-6
+
+
+@pytest.mark.parametrize("rows", [100, 4096, 24576 + 5])
+def test_policy_forward_matches_modules(cuda_lib, rows):
+    from generalizableracing_b200 import _lib as B
+    from generalizableracing_b200.modules import ActorCritic
+    lib = cuda_lib
+    torch.manual_seed(rows)
+    pol = ActorCritic(16, 16, 4).cuda()
+    la, lc = [m for m in pol.actor if isinstance(m, torch.nn.Linear)], [m for m in pol.critic if isinstance(m, torch.nn.Linear)]
+    mk = lambda l, out: B.GrMlp(l[0].weight.data_ptr(), l[0].bias.data_ptr(), l[1].weight.data_ptr(), l[1].bias.data_ptr(), l[2].weight.data_ptr(), l[2].bias.data_ptr(), 16, 128, 128, out)
+    packed = torch.zeros(int(lib.gr_policy_packed_bytes(128, 128, 2)), dtype=torch.uint8, device="cuda")
+    a, c = mk(la, 4), mk(lc, 1)
+    st = torch.cuda.current_stream().cuda_stream
+    B.check(lib.gr_policy_pack(C.byref(a), C.byref(c), packed.data_ptr(), st), "pack")
+    sigma = torch.ones(4, device="cuda")
+    p = B.GrPolicy(packed.data_ptr(), sigma.data_ptr(), 0.01)
+    obs, cobs = torch.randn(rows, 16, device="cuda") * 3, torch.randn(rows, 16, device="cuda") * 3
+    mu, val = torch.zeros(rows, 4, device="cuda"), torch.zeros(rows, device="cuda")
+    B.check(lib.gr_policy_forward(C.byref(p), obs.data_ptr(), cobs.data_ptr(), mu.data_ptr(), val.data_ptr(), rows, st), "gr_policy_forward")
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        mu_ref, v_ref = pol.actor(obs), pol.critic(cobs)[:, 0]
+    assert float((mu - mu_ref).abs().max()) < 1e-2 and float((mu - mu_ref).abs().mean()) < 1e-3
+    assert float((val - v_ref).abs().max()) < 1e-2 and float((val - v_ref).abs().mean()) < 1e-3
