@@ -85,7 +85,7 @@ class GrPolicy(C.Structure):
 
 class GrCollectIO(C.Structure):
     _fields_ = [("obs0", c_p), ("critic_obs0", c_p), ("obs_out", c_p), ("critic_obs_out", c_p), ("aux_out", c_p), ("last_values", c_p),
-                ("episode_acc", c_p), ("log_accum", c_p), ("episode_log", c_p), ("gamma", c_f), ("groups_per_cta", c_i), ("group_skew_ns", c_i)]
+                ("episode_acc", c_p), ("log_accum", c_p), ("episode_log", c_p), ("gamma", c_f), ("groups_per_cta", c_i)]
 
 
 class GrBpttCollectIO(C.Structure):

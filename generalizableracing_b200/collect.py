@@ -37,7 +37,7 @@ def _mlp_layers(seq: nn.Sequential):
 
 
 class FusedCollector:
-    def __init__(self, env, policy, storage, gamma: float, groups_per_cta: int = 0, group_skew_ns: int = -1):
+    def __init__(self, env, policy, storage, gamma: float, groups_per_cta: int = 0):
         if env._bptt is not None or env.rng_mode != "philox":
             raise ValueError("fused collection needs a non-differentiable env drawing in-kernel (rng_mode='philox')")
         if policy.is_recurrent:
@@ -66,7 +66,6 @@ class FusedCollector:
         self.episode_log = torch.zeros(B.GR_LOG_SHARDS, 4, device=dev)
         self.gamma = float(gamma)
         self.groups_per_cta = int(groups_per_cta)
-        self.group_skew_ns = int(group_skew_ns)
         self._pol = B.GrPolicy(self.packed.data_ptr(), self.sigma.data_ptr(), self.slope)
 
     def _mlp(self, l1, l2, l3, out) -> B.GrMlp:
@@ -96,7 +95,7 @@ class FusedCollector:
             dst = env._outs[k]
         env._flip = k ^ 1
         io = B.GrCollectIO(src["obs"].data_ptr(), src["critic"].data_ptr(), dst["obs"].data_ptr(), dst["critic"].data_ptr(), dst["aux"].data_ptr(),
-                           self.last_values.data_ptr(), self.episode_acc.data_ptr(), env._log_accum.data_ptr(), self.episode_log.data_ptr(), self.gamma, self.groups_per_cta, self.group_skew_ns)
+                           self.last_values.data_ptr(), self.episode_acc.data_ptr(), env._log_accum.data_ptr(), self.episode_log.data_ptr(), self.gamma, self.groups_per_cta)
         rng = env._rng
         rng.rnd = None
         rng.step = env._step_count & 0xFFFFFFFF

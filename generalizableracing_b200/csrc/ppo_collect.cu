@@ -130,10 +130,6 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
   // Per step: actor L1 L2 L3 -> sample -> critic L1 L2 L3, env.step.  Work that does not depend on the MMA in flight is
   // placed between its issue and its wait: the Philox draws under actor L1, the storage rows of the action under critic L1,
   // the whole env step under critic L2 (the longest MMA), the episode sums under critic L3.
-  // Groups that start together stay in lock step (same work per step): all of them in the ALU-heavy epilogues at once,
-  // then all of them waiting on the tensor pipe.  A one-time skew of a fraction of a step de-phases them for the whole
-  // rollout, so one group's MMA latency is covered by another group's ALU work.
-  if (G > 1 && cio.group_skew_ns > 0) __nanosleep((unsigned)(grp * cio.group_skew_ns));
 #pragma unroll 1
   for (int t = 0; t < T; ++t) {
     const int64_t tn = (int64_t)t * N + i;
@@ -321,9 +317,6 @@ extern "C" int gr_ppo_collect(const GrConfig* cfg, const GrTrack* track, const G
       bad16(storage->mu) || bad16(storage->sigma) || (io->episode_acc && (reinterpret_cast<uintptr_t>(io->episode_acc) & 7u)))
     return GR_ERR_ALIGN;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  GrCollectIO io_resolved = *io;
-  if (io_resolved.group_skew_ns < 0) io_resolved.group_skew_ns = 1500;       // ~1/4 of a 4-tile step (measured sweep: DESIGN.md)
-  io = &io_resolved;
   int G = io->groups_per_cta;
   if (G == 0) {            // smallest CTA that still fits the rollout in one wave of 148 SMs
     const int tiles = (st->num_envs + kTileEnvs - 1) / kTileEnvs;

@@ -277,7 +277,6 @@ typedef struct GrCollectIO {
                                         -- the runner's rewbuffer / lenbuffer book keeping (on_policy_runner.py:160-173) */
   float gamma;                       /* time-out bootstrap r += gamma * V(s_t) * time_out */
   int32_t groups_per_cta;            /* 128-env tiles per thread block: 1, 2, 4 or 0 = pick (fewest that fit one wave) */
-  int32_t group_skew_ns;             /* one-time start skew between the tiles of a block (de-phases them); 0 = none, -1 = default */
 } GrCollectIO;
 /* packed size of `nets` (1 = actor only, 2 = actor + critic) MLPs of widths 16 -> hidden -> hidden2; < 0: unsupported widths */
 int64_t gr_policy_packed_bytes(int32_t hidden, int32_t hidden2, int32_t nets);

@@ -44,7 +44,7 @@ def main():
         alg.init_storage("rl", N, T, [16], [16], [4])
         row = {}
         for G in groups:
-            col = FusedCollector(env, pol, alg.storage, gamma=0.99, groups_per_cta=G, group_skew_ns=int(os.environ.get('SKEW', '-1')))
+            col = FusedCollector(env, pol, alg.storage, gamma=0.99, groups_per_cta=G)
             col.pack()
 
             def fused():
