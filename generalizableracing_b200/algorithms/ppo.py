@@ -135,11 +135,11 @@ class PPO:
         g["ksums"] = torch.zeros(8, device=dev)
         # static gradient storage: one flat buffer, the parameters' .grad are views of it for the life of the graph
         params = list(pol.parameters())
-        flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+        flat = torch.zeros(sum((p.numel() + 3) // 4 * 4 for p in params), device=dev)
         off = 0
-        for p in params:
+        for p in params:                        # every view starts on a 16-byte boundary (the kernels flush with 128-bit reductions)
             p.grad = flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+            off += (p.numel() + 3) // 4 * 4
         g["flat_grad"] = flat
         mk = lambda l1, l2, l3, out: B.GrMlp(l1.weight.data_ptr(), l1.bias.data_ptr(), l2.weight.data_ptr(), l2.bias.data_ptr(), l3.weight.data_ptr(),
                                              l3.bias.data_ptr(), 16, 128, 128, out)

@@ -56,6 +56,11 @@ __device__ __forceinline__ void dact_epilogue(uint32_t taddr, uint8_t* row_base,
   }
 }
 
+// fire-and-forget vector reduction: 4 consecutive floats in one L2 operation (sm_90+), 16-byte aligned
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 constexpr uint32_t kMnA = 1u << 15, kMnB = 1u << 16;          // instruction-descriptor bits: A / B operand is MN-major
 
 // descriptors over the per-row layout [chunk][128 rows][8 halfs]
@@ -212,7 +217,9 @@ __global__ void __launch_bounds__(kTileEnvs, 1) actor_backward_kernel(const GrPo
       tmem_ld_x16(tm + kColW2 + lane_sel + c0, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < 16; ++k) atomicAdd(out.w2 + (int64_t)j * H1 + c0 + k, __uint_as_float(v[k]) * inv);
+      for (int k = 0; k < 16; k += 4)
+        red_add_v4(out.w2 + (int64_t)j * H1 + c0 + k, __uint_as_float(v[k]) * inv, __uint_as_float(v[k + 1]) * inv, __uint_as_float(v[k + 2]) * inv,
+                   __uint_as_float(v[k + 3]) * inv);
     }
 #pragma unroll 1
     for (int h = 0; h < kHalves; ++h) {
@@ -221,7 +228,9 @@ __global__ void __launch_bounds__(kTileEnvs, 1) actor_backward_kernel(const GrPo
       tmem_ld_x16(tm + kColW1 + 32 * h + lane_sel + 16, w);
       tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < 16; ++k) atomicAdd(out.w1 + (int64_t)(128 * h + j) * kObsDim + k, __uint_as_float(v[k]) * inv);
+      for (int k = 0; k < 16; k += 4)
+        red_add_v4(out.w1 + (int64_t)(128 * h + j) * kObsDim + k, __uint_as_float(v[k]) * inv, __uint_as_float(v[k + 1]) * inv, __uint_as_float(v[k + 2]) * inv,
+                   __uint_as_float(v[k + 3]) * inv);
       atomicAdd(out.b1 + 128 * h + j, __uint_as_float(w[0]) * inv);
     }
     {
@@ -278,7 +287,9 @@ extern "C" int gr_actor_backward(const GrPolicy* policy, int32_t hidden, int32_t
   if (rows <= 0 || out->out_dim < 1 || out->out_dim > 4) return GR_ERR_SIZE;
   if (!((hidden == 128 || hidden == 256) && hidden2 == 128)) return GR_ERR_SIZE;
   if (policy->negative_slope < 0.0f || policy->negative_slope > 1.0f) return GR_ERR_CONFIG;
-  if ((reinterpret_cast<uintptr_t>(policy->packed) | reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(grad_actions)) & 15u) return GR_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(policy->packed) | reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(grad_actions) |
+       reinterpret_cast<uintptr_t>(out->w1) | reinterpret_cast<uintptr_t>(out->w2)) & 15u)
+    return GR_ERR_ALIGN;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   return hidden == 256 ? launch_actor_backward<NetLayout<256, 128>>(policy, obs, grad_actions, scale, rows, out, s)
                        : launch_actor_backward<NetLayout<128, 128>>(policy, obs, grad_actions, scale, rows, out, s);
