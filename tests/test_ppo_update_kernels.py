@@ -73,3 +73,51 @@ def test_policy_forward_matches_modules(cuda_lib, rows):
         mu_ref, v_ref = pol.actor(obs), pol.critic(cobs)[:, 0]
     assert float((mu - mu_ref).abs().max()) < 1e-2 and float((mu - mu_ref).abs().mean()) < 1e-3
     assert float((val - v_ref).abs().max()) < 1e-2 and float((val - v_ref).abs().mean()) < 1e-3
+
+
+def test_kernels_do_not_write_past_their_rows(cuda_lib):
+    """Ragged row counts (not a multiple of the 128-row tile): outputs live inside sentinel-filled buffers, the sentinels
+    survive (the sanitizer is not available on the GPU pool, so the bounds are checked this way)."""
+    from generalizableracing_b200 import _lib as B
+    from generalizableracing_b200.modules import ActorCritic
+    lib = cuda_lib
+    rows, pad, S = 333, 512, 12345.0
+    torch.manual_seed(0)
+    pol = ActorCritic(16, 16, 4).cuda()
+    la, lc = [m for m in pol.actor if isinstance(m, torch.nn.Linear)], [m for m in pol.critic if isinstance(m, torch.nn.Linear)]
+    mk = lambda l, out: B.GrMlp(l[0].weight.data_ptr(), l[0].bias.data_ptr(), l[1].weight.data_ptr(), l[1].bias.data_ptr(), l[2].weight.data_ptr(), l[2].bias.data_ptr(), 16, 128, 128, out)
+    packed = torch.zeros(int(lib.gr_policy_packed_bytes(128, 128, 2)), dtype=torch.uint8, device="cuda")
+    a, c = mk(la, 4), mk(lc, 1)
+    st = torch.cuda.current_stream().cuda_stream
+    B.check(lib.gr_policy_pack(C.byref(a), C.byref(c), packed.data_ptr(), st), "pack")
+    sigma = torch.ones(4, device="cuda")
+    p = B.GrPolicy(packed.data_ptr(), sigma.data_ptr(), 0.01)
+    obs = torch.randn(rows, 16, device="cuda")
+    guard = lambda n: torch.full((pad + n + pad,), S, device="cuda")
+    mu_buf, v_buf = guard(rows * 4), guard(rows)
+    mu, val = mu_buf[pad:pad + rows * 4], v_buf[pad:pad + rows]
+    B.check(lib.gr_policy_forward(C.byref(p), obs.data_ptr(), obs.data_ptr(), mu.data_ptr(), val.data_ptr(), rows, st), "gr_policy_forward")
+    # gradient buffers of the actor inside one guarded arena
+    sizes = [t.numel() for t in (la[0].weight, la[0].bias, la[1].weight, la[1].bias, la[2].weight, la[2].bias)]
+    arena = torch.full((pad + sum(sizes) + pad * 7,), S, device="cuda")
+    ptrs, off = [], pad
+    views = []
+    for n in sizes:
+        views.append(arena[off:off + n])
+        arena[off:off + n] = 0.0
+        ptrs.append(views[-1].data_ptr())
+        off += n + pad
+    g = torch.randn(rows, 4, device="cuda")
+    scale = torch.ones(1, device="cuda")
+    out = B.GrMlpGrad(*ptrs, 4)
+    B.check(lib.gr_actor_backward(C.byref(p), 128, 128, obs.data_ptr(), g.data_ptr(), scale.data_ptr(), rows, C.byref(out), st), "gr_actor_backward")
+    torch.cuda.synchronize()
+    assert bool((mu_buf[:pad] == S).all()) and bool((mu_buf[pad + rows * 4:] == S).all()) and bool((v_buf[:pad] == S).all()) and bool((v_buf[pad + rows:] == S).all())
+    assert bool(torch.isfinite(mu).all()) and bool((mu != S).all())
+    mask = torch.ones_like(arena, dtype=torch.bool)
+    off = pad
+    for n in sizes:
+        mask[off:off + n] = False
+        off += n + pad
+    assert bool((arena[mask] == S).all())
+    assert all(bool(torch.isfinite(v).all()) and float(v.abs().max()) > 0 for v in views)
