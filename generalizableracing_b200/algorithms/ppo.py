@@ -135,7 +135,8 @@ class PPO:
         g["ksums"] = torch.zeros(8, device=dev)
         # static gradient storage: one flat buffer, the parameters' .grad are views of it for the life of the graph
         params = list(pol.parameters())
-        flat = torch.zeros(sum((p.numel() + 3) // 4 * 4 for p in params), device=dev)
+        world = D.world()[1]
+        flat = torch.zeros(sum((p.numel() + 3) // 4 * 4 for p in params) + 4, device=dev)      # + (KL sum, rows, -, -) riding the same all-reduce
         off = 0
         for p in params:                        # every view starts on a 16-byte boundary (the kernels flush with 128-bit reductions)
             p.grad = flat[off:off + p.numel()].view_as(p)
@@ -168,10 +169,6 @@ class PPO:
                 g["ksums"].zero_()
             B.check(lib.gr_ppo_loss_grad(C.byref(batch), mb, g["grad_mu"].data_ptr(), g["grad_v"].data_ptr(), g["ksums"].data_ptr(), st), "gr_ppo_loss_grad")
             with torch.no_grad():
-                if adaptive:
-                    kl_mean = g["ksums"][2] / g["ksums"][7]
-                    down, up = (lr / 1.5).clamp(min=1e-5), (lr * 1.5).clamp(max=1e-2)
-                    lr.copy_(torch.where(kl_mean > self.desired_kl * 2.0, down, torch.where((kl_mean < self.desired_kl / 2.0) & (kl_mean > 0.0), up, lr)))
                 flat.zero_()
                 g["scale_a"] = (1024.0 / g["grad_mu"].abs().max().clamp_min(1e-30)).reshape(1)
                 g["scale_c"] = (1024.0 / g["grad_v"].abs().max().clamp_min(1e-30)).reshape(1)
@@ -181,6 +178,14 @@ class PPO:
                     "gr_actor_backward(critic)")
             with torch.no_grad():
                 pol.std.grad.copy_(g["ksums"][3:7])
+                flat[-4:-2].copy_(torch.stack([g["ksums"][2], g["ksums"][7]]))
+                if world > 1:          # env-sharded data parallelism: ONE all-reduce per step carries the gradients and the KL statistics
+                    torch.distributed.all_reduce(flat)
+                    flat[:-4].div_(world)
+                if adaptive:           # ppo.py:124-141 on the device (the learning rate only matters at optimizer.step)
+                    kl_mean = flat[-4] / flat[-3]
+                    down, up = (lr / 1.5).clamp(min=1e-5), (lr * 1.5).clamp(max=1e-2)
+                    lr.copy_(torch.where(kl_mean > self.desired_kl * 2.0, down, torch.where((kl_mean < self.desired_kl / 2.0) & (kl_mean > 0.0), up, lr)))
                 nn.utils.clip_grad_norm_(pol.parameters(), self.max_grad_norm)
                 self.optimizer.step()
                 g["sums"] += torch.stack([g["ksums"][1], g["ksums"][0]]) / g["ksums"][7]
@@ -292,9 +297,19 @@ class PPO:
         self.storage.clear()
         return {"value_function": out[0], "surrogate": out[1]}
 
+    def close(self):
+        """Drop the captured update graph (it holds NCCL work when the run is multi-GPU: release it before the process group)."""
+        if self._graph is not None:
+            torch.cuda.synchronize(self.device)
+            self._graph.pop("graph", None)
+            self._graph = None
+            import gc
+            gc.collect()
+            torch.cuda.synchronize(self.device)
+
     def update(self):
         # ppo.py:103-190
-        if self.graphed_update and D.world()[1] == 1 and getattr(self, "_eager_updates", 0) >= 1:
+        if self.graphed_update and (D.world()[1] == 1 or self.kernel_update) and getattr(self, "_eager_updates", 0) >= 1:
             return self._update_graphed()
         self._eager_updates = getattr(self, "_eager_updates", 0) + 1
         mean_value_loss = torch.zeros((), device=self.device)

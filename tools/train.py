@@ -69,7 +69,10 @@ def main():
                             "Metrics/next_gate_pose/accumulate_gates", "Curriculum/terrain_levels", "Perf/total_fps", "Perf/collection time", "Perf/learning_time") if k in hist[-1]]
         for i in sorted(set(list(range(0, len(hist), max(1, len(hist) // 15))) + [len(hist) - 1])):
             print(i, {k: (round(hist[i][k], 4) if isinstance(hist[i][k], float) else hist[i][k]) for k in keys}, flush=True)
+    if hasattr(runner.alg, "close"):
+        runner.alg.close()
     if world > 1:
+        torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 
 
