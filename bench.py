@@ -339,6 +339,10 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "extra": extra,
         }
+        if "bptt_fwd_bwd_c3" in extra:          # the second half of BASELINE's metric ("fwd, and fwd+bwd BPTT"), C3 = 16,384 envs x 32
+            line["fwd_bwd_bptt"] = {"unit": UNIT, "config": "C3: 16384 envs, horizon 32",
+                                    "dynamics_only": extra["bptt_fwd_bwd_c3"]["env_steps_per_s"],
+                                    "training_iteration_with_policy": extra.get("bptt_training_c3", {}).get("fused_kernel_backward", {}).get("env_steps_per_s")}
         print(json.dumps(line))
 
 
