@@ -114,8 +114,10 @@ class PPO:
         return loss, surrogate_loss, value_loss, mu_batch, sigma_batch
 
     def _kernel_step_factory(self, g, mbs, desc, lr, mb):
-        """The captured step of `kernel_update`: gather -> pack -> gr_policy_forward -> gr_ppo_loss_grad -> 2 x gr_actor_backward
-        -> (torch) adaptive LR, clip, Adam.  ppo.py:118-178 of the reference without autograd."""
+        """The captured step of `kernel_update` (ppo.py:118-178 of the reference without autograd), ten launches:
+        gather -> pack -> sigma -> zero(flat) -> gr_policy_forward -> gr_ppo_loss_grad -> 2 x gr_actor_backward -> [all-reduce] ->
+        gr_adam_clip_step (2).  One flat fp32 buffer holds every gradient (the parameters' .grad are views of it) and, in its
+        last 16 floats, the loss kernel's sums (losses, KL, d/d std, loss scales): a multi-GPU run all-reduces exactly that."""
         import ctypes as C
         from .. import _lib as B
         from ..collect import _mlp_layers
@@ -127,35 +129,64 @@ class PPO:
         for l1, l2, l3, out in ((a1, a2, a3, 4), (c1, c2, c3, 1)):
             if (l1.in_features, l1.out_features, l2.out_features, l3.out_features) != (16, 128, 128, out):
                 raise ValueError("kernel_update is built for 16 -> 128 -> 128 -> 4 / 1 MLPs")
+        if not isinstance(self.optimizer, optim.Adam) or self.optimizer.param_groups[0].get("weight_decay", 0) or self.optimizer.param_groups[0].get("amsgrad", False):
+            raise ValueError("kernel_update implements plain Adam")
+        world = D.world()[1]
         net_bytes = int(lib.gr_policy_packed_bytes(128, 128, 1))
         g["packed"] = torch.zeros(2 * net_bytes, dtype=torch.uint8, device=dev)
         g["sigma4"] = torch.ones(4, device=dev)
         g["mu_new"], g["v_new"] = torch.zeros(mb, 4, device=dev), torch.zeros(mb, device=dev)
         g["grad_mu"], g["grad_v"] = torch.zeros(mb, 4, device=dev), torch.zeros(mb, 4, device=dev)
-        g["ksums"] = torch.zeros(8, device=dev)
-        # static gradient storage: one flat buffer, the parameters' .grad are views of it for the life of the graph
-        params = list(pol.parameters())
-        world = D.world()[1]
-        flat = torch.zeros(sum((p.numel() + 3) // 4 * 4 for p in params) + 4, device=dev)      # + (KL sum, rows, -, -) riding the same all-reduce
-        off = 0
-        for p in params:                        # every view starts on a 16-byte boundary (the kernels flush with 128-bit reductions)
-            p.grad = flat[off:off + p.numel()].view_as(p)
+        # ---- flat gradient / moment buffers: every tensor starts on a 16-byte boundary; pol.std's gradient IS sums[3:7] of the tail
+        params = [p for p in pol.parameters() if p is not pol.std]
+        offs, off = [], 0
+        for p in params:
+            offs.append(off)
             off += (p.numel() + 3) // 4 * 4
-        g["flat_grad"] = flat
+        tail = off                                   # 16 floats: gr_ppo_loss_grad's sums
+        n_flat = tail + 16
+        flat, flat_m, flat_v = (torch.zeros(n_flat, device=dev) for _ in range(3))
+        ksums = flat[tail:tail + 16]
+        segs = [(p, o, p.numel()) for p, o in zip(params, offs)] + [(pol.std, tail + 3, 4)]
+        old_state = self.optimizer.state
+        for p, o, n in segs:                         # adopt the moments of the eager iterations; from here on torch's optimizer state aliases ours
+            st = old_state.get(p, {})
+            if "exp_avg" in st:
+                flat_m[o:o + n].copy_(st["exp_avg"].reshape(-1))
+                flat_v[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+            p.grad = flat[o:o + n].view_as(p)
+        step0 = max([float(st["step"]) for st in old_state.values() if "step" in st] or [0.0])
+        state = torch.zeros(16, device=dev)
+        state[0], state[1] = float(self.learning_rate), step0
+        for p, o, n in segs:
+            old_state[p] = {"step": state[1], "exp_avg": flat_m[o:o + n].view_as(p), "exp_avg_sq": flat_v[o:o + n].view_as(p)}
+        g["lr"] = state[0:1]
+        g["flat_grad"], g["flat_m"], g["flat_v"], g["adam_state"] = flat, flat_m, flat_v, state
+        ptrs = torch.tensor([p.data_ptr() for p, _, _ in segs], dtype=torch.int64, device=dev)
+        seg_off = torch.tensor([o for _, o, _ in segs], dtype=torch.int32, device=dev)
+        seg_n = torch.tensor([n for _, _, n in segs], dtype=torch.int32, device=dev)
+        order = torch.argsort(seg_off)               # the apply kernel walks the segments in offset order
+        ptrs, seg_off, seg_n = ptrs[order].contiguous(), seg_off[order].contiguous(), seg_n[order].contiguous()
+        b1, b2 = self.optimizer.param_groups[0]["betas"]
+        adaptive = self.desired_kl is not None and self.schedule == "adaptive"
+        adam = B.GrAdamStep(ptrs.data_ptr(), seg_off.data_ptr(), seg_n.data_ptr(), len(segs), n_flat, flat.data_ptr(), flat_m.data_ptr(), flat_v.data_ptr(),
+                            state.data_ptr(), ksums.data_ptr() if adaptive else None, 1.0 / world, float(b1), float(b2), float(self.optimizer.param_groups[0]["eps"]),
+                            float(self.max_grad_norm), float(self.desired_kl or 0.0), 1e-5, 1e-2)
         mk = lambda l1, l2, l3, out: B.GrMlp(l1.weight.data_ptr(), l1.bias.data_ptr(), l2.weight.data_ptr(), l2.bias.data_ptr(), l3.weight.data_ptr(),
                                              l3.bias.data_ptr(), 16, 128, 128, out)
         mlp_a, mlp_c = mk(a1, a2, a3, 4), mk(c1, c2, c3, 1)
         gr_a = B.GrMlpGrad(a1.weight.grad.data_ptr(), a1.bias.grad.data_ptr(), a2.weight.grad.data_ptr(), a2.bias.grad.data_ptr(), a3.weight.grad.data_ptr(),
-                           a3.bias.grad.data_ptr(), 4)
+                           a3.bias.grad.data_ptr(), 4, 1)
         gr_c = B.GrMlpGrad(c1.weight.grad.data_ptr(), c1.bias.grad.data_ptr(), c2.weight.grad.data_ptr(), c2.bias.grad.data_ptr(), c3.weight.grad.data_ptr(),
-                           c3.bias.grad.data_ptr(), 1)
+                           c3.bias.grad.data_ptr(), 1, 1)
         pol_both = B.GrPolicy(g["packed"].data_ptr(), g["sigma4"].data_ptr(), slope)
         pol_c = B.GrPolicy(g["packed"].data_ptr() + net_bytes, g["sigma4"].data_ptr(), slope)
         batch = B.GrPpoBatch(g["mu_new"].data_ptr(), g["v_new"].data_ptr(), g["sigma4"].data_ptr(), g["actions"].data_ptr(), g["log_prob"].data_ptr(),
                              g["advantages"].data_ptr(), g["returns"].data_ptr(), g["values"].data_ptr(), g["mu"].data_ptr(), g["sigma"].data_ptr(),
                              float(self.clip_param), float(self.value_loss_coef), float(self.entropy_coef), int(self.use_clipped_value_loss))
-        g["keep_k"] = (mlp_a, mlp_c, gr_a, gr_c, pol_both, pol_c, batch)
-        adaptive = self.desired_kl is not None and self.schedule == "adaptive"
+        g["keep_k"] = (mlp_a, mlp_c, gr_a, gr_c, pol_both, pol_c, batch, adam, ptrs, seg_off, seg_n)
+        p_max_mu, p_max_v = ksums.data_ptr() + 8 * 4, ksums.data_ptr() + 9 * 4
+        g["kernel_sums"] = True                      # the running loss sums live in adam_state[5:7]
 
         def step():
             st = torch.cuda.current_stream(dev).cuda_stream
@@ -163,32 +194,15 @@ class PPO:
             B.check(lib.gr_policy_pack(C.byref(mlp_a), C.byref(mlp_c), g["packed"].data_ptr(), st), "gr_policy_pack")
             with torch.no_grad():
                 g["sigma4"].copy_(pol.std)
+                flat.zero_()
             B.check(lib.gr_policy_forward(C.byref(pol_both), g["obs"].data_ptr(), g["critic_obs"].data_ptr(), g["mu_new"].data_ptr(), g["v_new"].data_ptr(), mb, st),
                     "gr_policy_forward")
-            with torch.no_grad():
-                g["ksums"].zero_()
-            B.check(lib.gr_ppo_loss_grad(C.byref(batch), mb, g["grad_mu"].data_ptr(), g["grad_v"].data_ptr(), g["ksums"].data_ptr(), st), "gr_ppo_loss_grad")
-            with torch.no_grad():
-                flat.zero_()
-                g["scale_a"] = (1024.0 / g["grad_mu"].abs().max().clamp_min(1e-30)).reshape(1)
-                g["scale_c"] = (1024.0 / g["grad_v"].abs().max().clamp_min(1e-30)).reshape(1)
-            B.check(lib.gr_actor_backward(C.byref(pol_both), 128, 128, g["obs"].data_ptr(), g["grad_mu"].data_ptr(), g["scale_a"].data_ptr(), mb, C.byref(gr_a), st),
-                    "gr_actor_backward(actor)")
-            B.check(lib.gr_actor_backward(C.byref(pol_c), 128, 128, g["critic_obs"].data_ptr(), g["grad_v"].data_ptr(), g["scale_c"].data_ptr(), mb, C.byref(gr_c), st),
-                    "gr_actor_backward(critic)")
-            with torch.no_grad():
-                pol.std.grad.copy_(g["ksums"][3:7])
-                flat[-4:-2].copy_(torch.stack([g["ksums"][2], g["ksums"][7]]))
-                if world > 1:          # env-sharded data parallelism: ONE all-reduce per step carries the gradients and the KL statistics
-                    torch.distributed.all_reduce(flat)
-                    flat[:-4].div_(world)
-                if adaptive:           # ppo.py:124-141 on the device (the learning rate only matters at optimizer.step)
-                    kl_mean = flat[-4] / flat[-3]
-                    down, up = (lr / 1.5).clamp(min=1e-5), (lr * 1.5).clamp(max=1e-2)
-                    lr.copy_(torch.where(kl_mean > self.desired_kl * 2.0, down, torch.where((kl_mean < self.desired_kl / 2.0) & (kl_mean > 0.0), up, lr)))
-                nn.utils.clip_grad_norm_(pol.parameters(), self.max_grad_norm)
-                self.optimizer.step()
-                g["sums"] += torch.stack([g["ksums"][1], g["ksums"][0]]) / g["ksums"][7]
+            B.check(lib.gr_ppo_loss_grad(C.byref(batch), mb, g["grad_mu"].data_ptr(), g["grad_v"].data_ptr(), ksums.data_ptr(), st), "gr_ppo_loss_grad")
+            B.check(lib.gr_actor_backward(C.byref(pol_both), 128, 128, g["obs"].data_ptr(), g["grad_mu"].data_ptr(), p_max_mu, mb, C.byref(gr_a), st), "gr_actor_backward(actor)")
+            B.check(lib.gr_actor_backward(C.byref(pol_c), 128, 128, g["critic_obs"].data_ptr(), g["grad_v"].data_ptr(), p_max_v, mb, C.byref(gr_c), st), "gr_actor_backward(critic)")
+            if world > 1:              # env-sharded data parallelism: ONE all-reduce per step carries the gradients and the loss / KL sums
+                torch.distributed.all_reduce(flat)
+            B.check(lib.gr_adam_clip_step(C.byref(adam), st), "gr_adam_clip_step")
         return step
 
     def _build_graph(self):
@@ -253,8 +267,6 @@ class PPO:
             for _ in range(3):
                 step()
                 self.policy.distribution = None
-            if self.kernel_update:             # the step re-binds these two scalars: make the captured instances the live ones
-                g["scale_a"], g["scale_c"] = g["scale_a"].clone(), g["scale_c"].clone()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
@@ -286,13 +298,16 @@ class PPO:
                 self._graph["lr"].fill_(float(self.learning_rate))
         g = self._graph
         g["sums"].zero_()
+        if g.get("kernel_sums"):
+            g["adam_state"][5:7].zero_()
         indices = torch.randperm(self.num_mini_batches * mb, requires_grad=False, device=self.device)
         for _ in range(self.num_learning_epochs):
             for i in range(self.num_mini_batches):
                 g["idx"].copy_(indices[i * mb:(i + 1) * mb])
                 g["graph"].replay()
         num_updates = self.num_learning_epochs * self.num_mini_batches
-        out = torch.cat([g["sums"] / num_updates, g["lr"].reshape(1)]).tolist()          # the iteration's only host read
+        sums = g["adam_state"][5:7] if g.get("kernel_sums") else g["sums"]
+        out = torch.cat([sums / num_updates, g["lr"].reshape(1)]).tolist()          # the iteration's only host read
         self.learning_rate = out[2]
         self.storage.clear()
         return {"value_function": out[0], "surrogate": out[1]}

@@ -209,7 +209,7 @@ class FusedBpttCollector:
         scale = (1024.0 / g.abs().max().clamp_min(1e-30)).reshape(1).float()          # device scalar, no host sync
         l1, l2, l3 = self._layers
         grads = [torch.zeros_like(t) for t in (l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias)]
-        out = B.GrMlpGrad(*(t.data_ptr() for t in grads), L.NUM_ACTIONS)
+        out = B.GrMlpGrad(*(t.data_ptr() for t in grads), L.NUM_ACTIONS, 0)
         B.check(self._lib.gr_actor_backward(C.byref(self._pol), self.h1, self.h2, self.obs_seq.data_ptr(), g.data_ptr(), scale.data_ptr(), T * N,
                                             C.byref(out), self.env._stream()), "gr_actor_backward")
         for t, gt in zip((l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias), grads):

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kTileEnvs, 1) actor_backward_kernel(const GrPo
   const uint32_t tm = *tmem_slot;
   const uint32_t lane_sel = (uint32_t)((row >> 5) * 32) << 16;
   const uint32_t w_addr = smem_u32(w_smem), xs_a = smem_u32(xs), h1_a = smem_u32(h1s), h2_a = smem_u32(h2s), da_a = smem_u32(das), ones_a = smem_u32(ones);
-  const float scale = __ldg(scale_ptr);
+  const float scale = out.scale_is_maxabs ? 1024.0f / fmaxf(__ldg(scale_ptr), 1e-30f) : __ldg(scale_ptr);
   float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);            // db3 = sum of the (unscaled) cotangent rows
   const int64_t tiles = (R + kTileEnvs - 1) / kTileEnvs;
   bool first = true;

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(256) ppo_loss_grad_kernel(const GrPpoBatch b, 
                                                            float* __restrict__ sums) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float max_gm = 0.0f, max_gv = 0.0f;
   if (r < R) {
     const float inv_rows = 1.0f / (float)R;
     const float4 mu = __ldg(reinterpret_cast<const float4*>(b.mu) + r), a = __ldg(reinterpret_cast<const float4*>(b.actions) + r);
@@ -132,6 +133,8 @@ __global__ void __launch_bounds__(256) ppo_loss_grad_kernel(const GrPpoBatch b, 
     }
     __stcs(reinterpret_cast<float4*>(grad_mu) + r, gm);
     __stcs(reinterpret_cast<float4*>(grad_value) + r, make_float4(g_v, 0.f, 0.f, 0.f));
+    max_gm = fmaxf(fmaxf(fabsf(gm.x), fabsf(gm.y)), fmaxf(fabsf(gm.z), fabsf(gm.w)));
+    max_gv = fabsf(g_v);
     acc[0] = surrogate; acc[1] = vloss; acc[2] = kl; acc[3] = gs[0]; acc[4] = gs[1]; acc[5] = gs[2]; acc[6] = gs[3]; acc[7] = 1.0f;
   }
   __shared__ float part[8][8];
@@ -146,6 +149,89 @@ __global__ void __launch_bounds__(256) ppo_loss_grad_kernel(const GrPpoBatch b, 
     float s = 0.0f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += part[w][threadIdx.x];
     atomicAdd(sums + threadIdx.x, s);
+  }
+  // loss scales of the two backward launches: non-negative floats order like their bit patterns
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { max_gm = fmaxf(max_gm, __shfl_xor_sync(0xffffffffu, max_gm, o)); max_gv = fmaxf(max_gv, __shfl_xor_sync(0xffffffffu, max_gv, o)); }
+  if (lane == 0) {
+    atomicMax(reinterpret_cast<unsigned int*>(sums) + 8, __float_as_uint(max_gm));
+    atomicMax(reinterpret_cast<unsigned int*>(sums) + 9, __float_as_uint(max_gv));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// clip_grad_norm_ + Adam + KL-adaptive learning rate in two launches over the flat parameter view
+// ---------------------------------------------------------------------------------------------
+enum AdamState : int { kLr = 0, kStep = 1, kClip = 2, kStepSize = 3, kInvSqrtBc2 = 4, kSumVLoss = 5, kSumSurr = 6, kSumSq = 8, kCounter = 9 };
+
+// tensor k owns flat[offs[k], offs[k] + sizes[k]); everything else in the flat buffer (alignment padding, the loss kernel's sums) is skipped
+__device__ __forceinline__ int segment_of(int i, const int* offs, const int* sizes, int n_seg) {
+  int k = 0;
+  while (k + 1 < n_seg && i >= offs[k + 1]) ++k;
+  return (i >= offs[k] && i - offs[k] < sizes[k]) ? k : -1;
+}
+
+__global__ void __launch_bounds__(256) adam_norm_kernel(const GrAdamStep a) {
+  __shared__ int offs[32], sizes[32];
+  if (threadIdx.x < a.n_seg) { offs[threadIdx.x] = a.seg_offsets[threadIdx.x]; sizes[threadIdx.x] = a.seg_sizes[threadIdx.x]; }
+  __syncthreads();
+  float s = 0.0f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_flat; i += gridDim.x * blockDim.x) {
+    if (segment_of(i, offs, sizes, a.n_seg) < 0) continue;
+    const float g = a.grad[i] * a.grad_scale;
+    s += g * g;
+  }
+  s = warp_sum_f(s);
+  __shared__ float part[8];
+  __shared__ bool last;
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w];
+    atomicAdd(a.state + kSumSq, t);
+    __threadfence();
+    last = atomicAdd(reinterpret_cast<unsigned int*>(a.state) + kCounter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {                       // the last block to finish sees every partial sum: finalise the step's scalars
+    __threadfence();
+    const float norm = sqrtf(*reinterpret_cast<volatile float*>(a.state + kSumSq));
+    float lr = a.state[kLr];
+    if (a.kl_stats) {                                   // ppo.py:124-141
+      const float kl_mean = a.kl_stats[2] / a.kl_stats[7];
+      if (kl_mean > a.desired_kl * 2.0f) lr = fmaxf(a.lr_min, lr / 1.5f);
+      else if (kl_mean < a.desired_kl / 2.0f && kl_mean > 0.0f) lr = fminf(a.lr_max, lr * 1.5f);
+      a.state[kSumSurr] += a.kl_stats[0] / a.kl_stats[7];
+      a.state[kSumVLoss] += a.kl_stats[1] / a.kl_stats[7];
+    }
+    const float step = a.state[kStep] + 1.0f;
+    a.state[kLr] = lr;
+    a.state[kStep] = step;
+    a.state[kClip] = fminf(1.0f, a.max_grad_norm / (norm + 1e-6f));            // clip_grad_norm_: clamp(max_norm / (total_norm + 1e-6), max=1)
+    a.state[kStepSize] = lr / (1.0f - powf(a.beta1, step));
+    a.state[kInvSqrtBc2] = rsqrtf(1.0f - powf(a.beta2, step));
+    a.state[kSumSq] = 0.0f;
+    reinterpret_cast<unsigned int*>(a.state)[kCounter] = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_apply_kernel(const GrAdamStep a) {
+  __shared__ int offs[32], sizes[32];
+  __shared__ float* ptrs[32];
+  if (threadIdx.x < a.n_seg) { offs[threadIdx.x] = a.seg_offsets[threadIdx.x]; sizes[threadIdx.x] = a.seg_sizes[threadIdx.x]; ptrs[threadIdx.x] = reinterpret_cast<float*>(a.param_ptrs[threadIdx.x]); }
+  __syncthreads();
+  const float clip = a.state[kClip] * a.grad_scale, step_size = a.state[kStepSize], inv_sqrt_bc2 = a.state[kInvSqrtBc2];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_flat; i += gridDim.x * blockDim.x) {
+    const int k = segment_of(i, offs, sizes, a.n_seg);
+    if (k < 0) continue;
+    const int j = i - offs[k];
+    const float g = a.grad[i] * clip;
+    const float m = a.beta1 * a.exp_avg[i] + (1.0f - a.beta1) * g;
+    const float v = a.beta2 * a.exp_avg_sq[i] + (1.0f - a.beta2) * g * g;
+    a.exp_avg[i] = m;
+    a.exp_avg_sq[i] = v;
+    ptrs[k][j] -= step_size * m / (sqrtf(v) * inv_sqrt_bc2 + a.eps);
   }
 }
 
@@ -167,6 +253,16 @@ extern "C" int gr_policy_forward(const GrPolicy* policy, const float* obs, const
   const int64_t pairs = ((rows + kTileEnvs - 1) / kTileEnvs + kFwdGroups - 1) / kFwdGroups;
   const int grid = (int)(pairs < sms ? pairs : sms);
   policy_forward_kernel<<<grid, kFwdGroups * kTileEnvs, bytes, reinterpret_cast<cudaStream_t>(stream)>>>(*policy, obs, critic_obs, mu, value, rows);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int gr_adam_clip_step(const GrAdamStep* a, void* stream) {
+  if (!a || !a->param_ptrs || !a->seg_offsets || !a->seg_sizes || !a->grad || !a->exp_avg || !a->exp_avg_sq || !a->state) return GR_ERR_NULL;
+  if (a->n_seg < 1 || a->n_seg > 32 || a->n_flat < 1) return GR_ERR_SIZE;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int blocks = (a->n_flat + 256 * 4 - 1) / (256 * 4);
+  adam_norm_kernel<<<blocks < 148 ? blocks : 148, 256, 0, s>>>(*a);
+  adam_apply_kernel<<<(a->n_flat + 255) / 256, 256, 0, s>>>(*a);
   return (int)cudaGetLastError();
 }
 

@@ -321,7 +321,11 @@ int gr_bptt_collect(const GrConfig* cfg, const GrTrack* track, const GrState* st
  * packed fp16 weights (as gr_bptt_collect evaluated them); gradients are ACCUMULATED into `out` (zero it first).
  * `scale`: device scalar; the cotangent is multiplied by it before the fp16 conversion and the result divided by it
  * (pick ~1024 / max|grad_actions|). */
-typedef struct GrMlpGrad { float* w1; float* b1; float* w2; float* b2; float* w3; float* b3; int32_t out_dim; } GrMlpGrad;   /* shapes as GrMlp, fp32; w3 [out_dim, hidden2] */
+typedef struct GrMlpGrad {           /* shapes as GrMlp, fp32; w3 [out_dim, hidden2]; w1 / w2 16-byte aligned */
+  float* w1; float* b1; float* w2; float* b2; float* w3; float* b3;
+  int32_t out_dim;
+  int32_t scale_is_maxabs;           /* 1: `*scale` holds max|grad_actions| (gr_ppo_loss_grad's sums[8|9]); the kernel uses 1024 / it */
+} GrMlpGrad;
 int gr_actor_backward(const GrPolicy* policy, int32_t hidden, int32_t hidden2, const float* obs /* [rows,16] */,
                       const float* grad_actions /* [rows,4] */, const float* scale, int64_t rows, const GrMlpGrad* out, void* stream);
 
@@ -329,7 +333,8 @@ int gr_actor_backward(const GrPolicy* policy, int32_t hidden, int32_t hidden2, c
  * One mini-batch step of PPO.update (S/rsl_rl/ext/algorithms/ppo.py:118-171) without autograd:
  *   gr_policy_forward : mu = actor(obs), v = critic(critic_obs) for `rows` rows (packed fp16 nets, tensor cores)
  *   gr_ppo_loss_grad  : clipped surrogate + clipped value loss + entropy bonus of the batch -> d(loss)/d(mu) [rows,4],
- *                       d(loss)/d(v) [rows,4] (column 0), and sums[0..7] += (surrogate, value loss, KL, d/d(std) x 4, rows)
+ *                       d(loss)/d(v) [rows,4] (column 0), sums[0..7] += (surrogate, value loss, KL, d/d(std) x 4, rows) and
+ *                       sums[8], sums[9] = max(.., max|d/d(mu)|), max(.., max|d/d(v)|)   (sums: 16 floats, zero them first)
  * followed by two gr_actor_backward launches (actor with d/d(mu), critic with d/d(v)). */
 int gr_policy_forward(const GrPolicy* policy /* packed actor + critic, widths (128,128) */, const float* obs, const float* critic_obs,
                       float* mu /* [rows,4] */, float* value /* [rows] */, int64_t rows, void* stream);
@@ -342,7 +347,25 @@ typedef struct GrPpoBatch {
   int32_t use_clipped_value_loss;
 } GrPpoBatch;
 int gr_ppo_loss_grad(const GrPpoBatch* batch, int64_t rows, float* grad_mu /* [rows,4] */, float* grad_value /* [rows,4] */,
-                     float* sums /* [8] accumulated */, void* stream);
+                     float* sums /* [16] accumulated */, void* stream);
+
+/* Gradient clipping + Adam + the KL-adaptive learning rate of one optimiser step (nn.utils.clip_grad_norm_, torch.optim.Adam.step
+ * and ppo.py:124-141), two launches over a flat view of the parameters: replaces ~40 element-wise torch launches of the
+ * captured step.  grad / exp_avg / exp_avg_sq are flat buffers indexed alike (tensor k occupies [seg_offsets[k], seg_offsets[k] +
+ * seg_sizes[k])); state: device [16] = {lr, step, clip_coef, step_size, 1/sqrt(bias2), sum value loss, sum surrogate, -, sumsq, counter..}
+ * (initialise lr and step, zero the rest).  kl_stats: device {.., .., KL sum, .., .., .., .., rows} = gr_ppo_loss_grad's sums, or NULL. */
+typedef struct GrAdamStep {
+  const int64_t* param_ptrs;         /* device [n_seg]: address of each parameter tensor (fp32, contiguous) */
+  const int32_t* seg_offsets;        /* device [n_seg] */
+  const int32_t* seg_sizes;          /* device [n_seg] */
+  int32_t n_seg, n_flat;
+  float* grad; float* exp_avg; float* exp_avg_sq;
+  float* state;
+  const float* kl_stats;
+  float grad_scale;                  /* gradients are multiplied by it first (1 / world size after a sum all-reduce) */
+  float beta1, beta2, eps, max_grad_norm, desired_kl, lr_min, lr_max;
+} GrAdamStep;
+int gr_adam_clip_step(const GrAdamStep* a, void* stream);
 
 /* ---- env.step() with HOST buffers (the e2e boundary) -------------------------------------------------------------
  * Same call as gr_step_fwd for a caller whose actions / observations live in host memory: replaces

@@ -45,7 +45,7 @@ def test_actor_backward_matches_autograd(cuda_lib, rows, hidden):
     polc = B.GrPolicy(packed.data_ptr(), sigma.data_ptr(), 0.01)
     params = (l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias)
     grads = [torch.zeros_like(t) for t in params]
-    out = B.GrMlpGrad(*(t.data_ptr() for t in grads), 4)
+    out = B.GrMlpGrad(*(t.data_ptr() for t in grads), 4, 0)
     scale = (1024.0 / g.abs().max()).reshape(1)
     B.check(lib.gr_actor_backward(C.byref(polc), hidden[0], hidden[1], x.data_ptr(), g.data_ptr(), scale.data_ptr(), rows, C.byref(out),
                                   torch.cuda.current_stream().cuda_stream), "gr_actor_backward")
@@ -58,7 +58,7 @@ def test_actor_backward_matches_autograd(cuda_lib, rows, hidden):
     # against the fp32 module, with a cotangent that does not cancel
     g2 = (torch.tanh(x[:, :4]) + 1.5) * 1e-6
     grads2 = [torch.zeros_like(t) for t in params]
-    out2 = B.GrMlpGrad(*(t.data_ptr() for t in grads2), 4)
+    out2 = B.GrMlpGrad(*(t.data_ptr() for t in grads2), 4, 0)
     scale2 = (1024.0 / g2.abs().max()).reshape(1)
     B.check(lib.gr_actor_backward(C.byref(polc), hidden[0], hidden[1], x.data_ptr(), g2.data_ptr(), scale2.data_ptr(), rows, C.byref(out2),
                                   torch.cuda.current_stream().cuda_stream), "gr_actor_backward")

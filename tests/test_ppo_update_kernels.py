@@ -35,7 +35,7 @@ def test_loss_gradients_match_autograd(cuda_lib, rows, clipped, entropy_coef):
     loss.backward()
     kl = torch.sum(torch.log(std.detach() / old_sigma + 1e-5) + (old_sigma ** 2 + (old_mu - mu.detach()) ** 2) / (2 * std.detach() ** 2) - 0.5, dim=-1).mean()
     # --- kernel
-    gm, gv, sums = torch.zeros(rows, 4, device="cuda"), torch.zeros(rows, 4, device="cuda"), torch.zeros(8, device="cuda")
+    gm, gv, sums = torch.zeros(rows, 4, device="cuda"), torch.zeros(rows, 4, device="cuda"), torch.zeros(16, device="cuda")
     sig = std.detach().contiguous()
     b = B.GrPpoBatch(mu.data_ptr(), v.data_ptr(), sig.data_ptr(), actions.data_ptr(), old_logp.data_ptr(), adv.data_ptr(), ret.data_ptr(), old_v.data_ptr(),
                      old_mu.data_ptr(), old_sigma.data_ptr(), clip, vcoef, entropy_coef, int(clipped))
@@ -109,7 +109,7 @@ def test_kernels_do_not_write_past_their_rows(cuda_lib):
         off += n + pad
     g = torch.randn(rows, 4, device="cuda")
     scale = torch.ones(1, device="cuda")
-    out = B.GrMlpGrad(*ptrs, 4)
+    out = B.GrMlpGrad(*ptrs, 4, 0)
     B.check(lib.gr_actor_backward(C.byref(p), 128, 128, obs.data_ptr(), g.data_ptr(), scale.data_ptr(), rows, C.byref(out), st), "gr_actor_backward")
     torch.cuda.synchronize()
     assert bool((mu_buf[:pad] == S).all()) and bool((mu_buf[pad + rows * 4:] == S).all()) and bool((v_buf[:pad] == S).all()) and bool((v_buf[pad + rows:] == S).all())
@@ -121,3 +121,51 @@ def test_kernels_do_not_write_past_their_rows(cuda_lib):
         off += n + pad
     assert bool((arena[mask] == S).all())
     assert all(bool(torch.isfinite(v).all()) and float(v.abs().max()) > 0 for v in views)
+
+
+def test_adam_clip_step_matches_torch(cuda_lib):
+    """gr_adam_clip_step == nn.utils.clip_grad_norm_ + torch.optim.Adam.step (+ the KL-adaptive learning rate) over several steps."""
+    from generalizableracing_b200 import _lib as B
+    lib = cuda_lib
+    torch.manual_seed(4)
+    shapes = [(128, 16), (128,), (128, 128), (4, 128), (4,), (3,)]
+    ref = [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+    mine = [p.detach().clone() for p in ref]
+    opt = torch.optim.Adam(ref, lr=5e-4)
+    offs, off = [], 0
+    for p in mine:
+        offs.append(off)
+        off += (p.numel() + 3) // 4 * 4
+    n_flat = off + 16
+    flat, m, v = (torch.zeros(n_flat, device="cuda") for _ in range(3))
+    state = torch.zeros(16, device="cuda")
+    state[0] = 5e-4
+    ptrs = torch.tensor([p.data_ptr() for p in mine], dtype=torch.int64, device="cuda")
+    so, sn = torch.tensor(offs, dtype=torch.int32, device="cuda"), torch.tensor([p.numel() for p in mine], dtype=torch.int32, device="cuda")
+    kl = flat[off:off + 16]
+    a = B.GrAdamStep(ptrs.data_ptr(), so.data_ptr(), sn.data_ptr(), len(mine), n_flat, flat.data_ptr(), m.data_ptr(), v.data_ptr(), state.data_ptr(), kl.data_ptr(),
+                     1.0, 0.9, 0.999, 1e-8, 1.0, 0.01, 1e-5, 1e-2)
+    lr = 5e-4
+    for it in range(6):
+        flat.zero_()
+        scale = [3.0, 0.01, 1.0, 5.0, 0.2, 1.0][it]                       # some steps get clipped, some not
+        for p, q, o in zip(ref, mine, offs):
+            g = torch.randn_like(p) * scale
+            p.grad = g.clone()
+            flat[o:o + p.numel()] = g.reshape(-1)
+        kl_mean = [0.05, 0.001, 0.01, 0.03, 0.0, 0.002][it]               # > 2*desired, < desired/2, in band, ...
+        kl[2], kl[7], kl[0], kl[1] = kl_mean * 100, 100.0, 7.0, 9.0
+        if kl_mean > 0.02:
+            lr = max(1e-5, lr / 1.5)
+        elif 0.0 < kl_mean < 0.005:
+            lr = min(1e-2, lr * 1.5)
+        for gr in opt.param_groups:
+            gr["lr"] = lr
+        torch.nn.utils.clip_grad_norm_(ref, 1.0)
+        opt.step()
+        B.check(lib.gr_adam_clip_step(C.byref(a), torch.cuda.current_stream().cuda_stream), "gr_adam_clip_step")
+        torch.cuda.synchronize()
+        assert abs(float(state[0]) - lr) < 1e-9 and float(state[1]) == it + 1
+        for p, q in zip(ref, mine):
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), (it, float((p - q).abs().max()))
+    assert abs(float(state[5]) - 6 * 0.09) < 1e-5 and abs(float(state[6]) - 6 * 0.07) < 1e-5
