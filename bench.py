@@ -155,7 +155,7 @@ def run_ours(args):
     working_set = N * (b_alg + 0)                                      # bytes touched by one step
     R = max(2, int(3 * L2_BYTES / working_set) + 1)
     envs = [RacingVecEnv(cfg, table, N, device=dev, seed=42 + r, episode_stats=stats, env_id_offset=rank * N,
-                         global_num_envs=world * N) for r in range(R)]
+                         global_num_envs=world * N, block_threads=args.block_threads) for r in range(R)]
     for e in envs:
         e.reset()
         # PPO's init_at_random_ep_len (on_policy_runner.py:118-121): staggered time-outs, ~1/200 of the envs reset per step
@@ -678,6 +678,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=NUM_ENVS, help="envs per GPU (BASELINE configs[3]: 65536)")
+    ap.add_argument("--block-threads", type=int, default=0, help="threads per block of the step kernel (0 = library default)")
     ap.add_argument("--no-stats", action="store_true", help="drop the per-env episode-sum planes (extras['log'] reward terms)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")

@@ -98,6 +98,10 @@ class GrMlpGrad(C.Structure):
     _fields_ = [("w1", c_p), ("b1", c_p), ("w2", c_p), ("b2", c_p), ("w3", c_p), ("b3", c_p), ("out_dim", c_i), ("scale_is_maxabs", c_i)]
 
 
+class GrBackwardJob(C.Structure):
+    _fields_ = [("policy", GrPolicy), ("obs", c_p), ("grad_actions", c_p), ("scale", c_p), ("out", GrMlpGrad)]
+
+
 class GrAdamStep(C.Structure):
     _fields_ = [("param_ptrs", c_p), ("seg_offsets", c_p), ("seg_sizes", c_p), ("n_seg", c_i), ("n_flat", c_i), ("grad", c_p), ("exp_avg", c_p),
                 ("exp_avg_sq", c_p), ("state", c_p), ("kl_stats", c_p), ("grad_scale", c_f), ("beta1", c_f), ("beta2", c_f), ("eps", c_f),
@@ -147,6 +151,7 @@ PROTOTYPES = {
     "gr_policy_forward": (C.c_int, [C.POINTER(GrPolicy), c_p, c_p, c_p, c_p, C.c_int64, c_p]),
     "gr_ppo_loss_grad": (C.c_int, [C.POINTER(GrPpoBatch), C.c_int64, c_p, c_p, c_p, c_p]),
     "gr_adam_clip_step": (C.c_int, [C.POINTER(GrAdamStep), c_p]),
+    "gr_actor_backward_jobs": (C.c_int, [C.POINTER(GrBackwardJob), c_i, c_i, c_i, C.c_int64, c_p]),
     "gr_host_pipe_create": (C.c_int, [c_i, c_i, c_p, C.POINTER(c_p)]),
     "gr_host_pipe_destroy": (C.c_int, [c_p]),
     "gr_host_pipe_step": (C.c_int, [c_p, C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom),

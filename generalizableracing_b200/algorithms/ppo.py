@@ -114,8 +114,8 @@ class PPO:
         return loss, surrogate_loss, value_loss, mu_batch, sigma_batch
 
     def _kernel_step_factory(self, g, mbs, desc, lr, mb):
-        """The captured step of `kernel_update` (ppo.py:118-178 of the reference without autograd), ten launches:
-        gather -> pack -> sigma -> zero(flat) -> gr_policy_forward -> gr_ppo_loss_grad -> 2 x gr_actor_backward -> [all-reduce] ->
+        """The captured step of `kernel_update` (ppo.py:118-178 of the reference without autograd), nine launches:
+        gather -> pack -> sigma -> zero(flat) -> gr_policy_forward -> gr_ppo_loss_grad -> gr_actor_backward_jobs (actor + critic) -> [all-reduce] ->
         gr_adam_clip_step (2).  One flat fp32 buffer holds every gradient (the parameters' .grad are views of it) and, in its
         last 16 floats, the loss kernel's sums (losses, KL, d/d std, loss scales): a multi-GPU run all-reduces exactly that."""
         import ctypes as C
@@ -184,8 +184,10 @@ class PPO:
         batch = B.GrPpoBatch(g["mu_new"].data_ptr(), g["v_new"].data_ptr(), g["sigma4"].data_ptr(), g["actions"].data_ptr(), g["log_prob"].data_ptr(),
                              g["advantages"].data_ptr(), g["returns"].data_ptr(), g["values"].data_ptr(), g["mu"].data_ptr(), g["sigma"].data_ptr(),
                              float(self.clip_param), float(self.value_loss_coef), float(self.entropy_coef), int(self.use_clipped_value_loss))
-        g["keep_k"] = (mlp_a, mlp_c, gr_a, gr_c, pol_both, pol_c, batch, adam, ptrs, seg_off, seg_n)
         p_max_mu, p_max_v = ksums.data_ptr() + 8 * 4, ksums.data_ptr() + 9 * 4
+        jobs = (B.GrBackwardJob * 2)(B.GrBackwardJob(pol_both, g["obs"].data_ptr(), g["grad_mu"].data_ptr(), p_max_mu, gr_a),
+                                     B.GrBackwardJob(pol_c, g["critic_obs"].data_ptr(), g["grad_v"].data_ptr(), p_max_v, gr_c))
+        g["keep_k"] = (mlp_a, mlp_c, gr_a, gr_c, pol_both, pol_c, batch, adam, ptrs, seg_off, seg_n, jobs)
         g["kernel_sums"] = True                      # the running loss sums live in adam_state[5:7]
 
         def step():
@@ -198,8 +200,7 @@ class PPO:
             B.check(lib.gr_policy_forward(C.byref(pol_both), g["obs"].data_ptr(), g["critic_obs"].data_ptr(), g["mu_new"].data_ptr(), g["v_new"].data_ptr(), mb, st),
                     "gr_policy_forward")
             B.check(lib.gr_ppo_loss_grad(C.byref(batch), mb, g["grad_mu"].data_ptr(), g["grad_v"].data_ptr(), ksums.data_ptr(), st), "gr_ppo_loss_grad")
-            B.check(lib.gr_actor_backward(C.byref(pol_both), 128, 128, g["obs"].data_ptr(), g["grad_mu"].data_ptr(), p_max_mu, mb, C.byref(gr_a), st), "gr_actor_backward(actor)")
-            B.check(lib.gr_actor_backward(C.byref(pol_c), 128, 128, g["critic_obs"].data_ptr(), g["grad_v"].data_ptr(), p_max_v, mb, C.byref(gr_c), st), "gr_actor_backward(critic)")
+            B.check(lib.gr_actor_backward_jobs(jobs, 2, 128, 128, mb, st), "gr_actor_backward_jobs")       # actor (d/d mu) and critic (d/d v) in one launch
             if world > 1:              # env-sharded data parallelism: ONE all-reduce per step carries the gradients and the loss / KL sums
                 torch.distributed.all_reduce(flat)
             B.check(lib.gr_adam_clip_step(C.byref(adam), st), "gr_adam_clip_step")

@@ -67,9 +67,15 @@ constexpr uint32_t kMnA = 1u << 15, kMnB = 1u << 16;          // instruction-des
 __device__ __forceinline__ uint64_t desc_rows_k(uint32_t addr) { return make_smem_desc(addr, kChunkA, 128); }     // rows = M, columns = K
 __device__ __forceinline__ uint64_t desc_rows_mn(uint32_t addr) { return make_smem_desc(addr, 128, kChunkA); }    // columns = M|N, rows = K
 
+// blockIdx.y selects the job: the actor and the critic of a PPO step share one launch (same widths, same row count)
 template <class NL>
-__global__ void __launch_bounds__(kTileEnvs, 1) actor_backward_kernel(const GrPolicy pol, const float* __restrict__ X, const float* __restrict__ G,
-                                                                     const float* __restrict__ scale_ptr, const int64_t R, const GrMlpGrad out) {
+__global__ void __launch_bounds__(kTileEnvs, 1) actor_backward_kernel(const GrBackwardJob job0, const GrBackwardJob job1, const int64_t R) {
+  const GrBackwardJob& job = blockIdx.y == 0 ? job0 : job1;
+  const GrPolicy pol = job.policy;
+  const float* __restrict__ X = job.obs;
+  const float* __restrict__ G = job.grad_actions;
+  const float* __restrict__ scale_ptr = job.scale;
+  const GrMlpGrad out = job.out;
   constexpr int H1 = NL::kH1, H2 = NL::kH2, kHalves = H1 / 128;
   static_assert(H2 == 128 && (H1 == 128 || H1 == 256), "built for 16 -> 128|256 -> 128 -> 4");
   // tensor memory: scratch accumulator | dW2 [H2 x H1] | dW1 (+ db1) [H1 x 32] as `kHalves` blocks | dW3^T [H2 x 16] | db2 [H2 x 16]
@@ -266,7 +272,7 @@ __global__ void __launch_bounds__(kTileEnvs, 1) actor_backward_kernel(const GrPo
 using namespace gr;
 
 template <class NL>
-static int launch_actor_backward(const GrPolicy* pol, const float* X, const float* G, const float* scale, int64_t R, const GrMlpGrad* out, cudaStream_t s) {
+static int launch_actor_backward(const GrBackwardJob* jobs, int n_jobs, int64_t R, cudaStream_t s) {
   const size_t bytes = (size_t)NL::kNetBytes + (size_t)(4 + NL::kH1 / 8 + NL::kH2 / 8 + 2 + 2) * kChunkA + 128;
   if (bytes > 227 * 1024) return GR_ERR_SMEM;
   auto kernel = actor_backward_kernel<NL>;
@@ -275,22 +281,37 @@ static int launch_actor_backward(const GrPolicy* pol, const float* X, const floa
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t tiles = (R + kTileEnvs - 1) / kTileEnvs;
-  const int grid = (int)(tiles < sms ? tiles : sms);
-  kernel<<<grid, kTileEnvs, bytes, s>>>(*pol, X, G, scale, R, *out);
+  const int per_job = sms / n_jobs;
+  const int grid = (int)(tiles < per_job ? tiles : per_job);
+  kernel<<<dim3(grid, n_jobs), kTileEnvs, bytes, s>>>(jobs[0], jobs[n_jobs - 1], R);
   return (int)cudaGetLastError();
+}
+
+static int check_job(const GrBackwardJob* j) {
+  if (!j->policy.packed || !j->obs || !j->grad_actions || !j->scale) return GR_ERR_NULL;
+  const GrMlpGrad* out = &j->out;
+  if (!out->w1 || !out->b1 || !out->w2 || !out->b2 || !out->w3 || !out->b3) return GR_ERR_NULL;
+  if (out->out_dim < 1 || out->out_dim > 4) return GR_ERR_SIZE;
+  if (j->policy.negative_slope < 0.0f || j->policy.negative_slope > 1.0f) return GR_ERR_CONFIG;
+  if ((reinterpret_cast<uintptr_t>(j->policy.packed) | reinterpret_cast<uintptr_t>(j->obs) | reinterpret_cast<uintptr_t>(j->grad_actions) |
+       reinterpret_cast<uintptr_t>(out->w1) | reinterpret_cast<uintptr_t>(out->w2)) & 15u)
+    return GR_ERR_ALIGN;
+  return GR_OK;
+}
+
+extern "C" int gr_actor_backward_jobs(const GrBackwardJob* jobs, int32_t n_jobs, int32_t hidden, int32_t hidden2, int64_t rows, void* stream) {
+  if (!jobs) return GR_ERR_NULL;
+  if (n_jobs < 1 || n_jobs > 2 || rows <= 0) return GR_ERR_SIZE;
+  if (!((hidden == 128 || hidden == 256) && hidden2 == 128)) return GR_ERR_SIZE;
+  for (int k = 0; k < n_jobs; ++k) { const int rc = check_job(&jobs[k]); if (rc != GR_OK) return rc; }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return hidden == 256 ? launch_actor_backward<NetLayout<256, 128>>(jobs, n_jobs, rows, s) : launch_actor_backward<NetLayout<128, 128>>(jobs, n_jobs, rows, s);
 }
 
 extern "C" int gr_actor_backward(const GrPolicy* policy, int32_t hidden, int32_t hidden2, const float* obs, const float* grad_actions,
                                  const float* scale, int64_t rows, const GrMlpGrad* out, void* stream) {
-  if (!policy || !policy->packed || !obs || !grad_actions || !scale || !out) return GR_ERR_NULL;
-  if (!out->w1 || !out->b1 || !out->w2 || !out->b2 || !out->w3 || !out->b3) return GR_ERR_NULL;
-  if (rows <= 0 || out->out_dim < 1 || out->out_dim > 4) return GR_ERR_SIZE;
-  if (!((hidden == 128 || hidden == 256) && hidden2 == 128)) return GR_ERR_SIZE;
-  if (policy->negative_slope < 0.0f || policy->negative_slope > 1.0f) return GR_ERR_CONFIG;
-  if ((reinterpret_cast<uintptr_t>(policy->packed) | reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(grad_actions) |
-       reinterpret_cast<uintptr_t>(out->w1) | reinterpret_cast<uintptr_t>(out->w2)) & 15u)
-    return GR_ERR_ALIGN;
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  return hidden == 256 ? launch_actor_backward<NetLayout<256, 128>>(policy, obs, grad_actions, scale, rows, out, s)
-                       : launch_actor_backward<NetLayout<128, 128>>(policy, obs, grad_actions, scale, rows, out, s);
+  if (!policy || !out) return GR_ERR_NULL;
+  GrBackwardJob job;
+  job.policy = *policy; job.obs = obs; job.grad_actions = grad_actions; job.scale = scale; job.out = *out;
+  return gr_actor_backward_jobs(&job, 1, hidden, hidden2, rows, stream);
 }

@@ -328,6 +328,9 @@ typedef struct GrMlpGrad {           /* shapes as GrMlp, fp32; w3 [out_dim, hidd
 } GrMlpGrad;
 int gr_actor_backward(const GrPolicy* policy, int32_t hidden, int32_t hidden2, const float* obs /* [rows,16] */,
                       const float* grad_actions /* [rows,4] */, const float* scale, int64_t rows, const GrMlpGrad* out, void* stream);
+/* one launch for up to two nets of the same widths over the same number of rows (a PPO step's actor and critic) */
+typedef struct GrBackwardJob { GrPolicy policy; const float* obs; const float* grad_actions; const float* scale; GrMlpGrad out; } GrBackwardJob;
+int gr_actor_backward_jobs(const GrBackwardJob* jobs, int32_t n_jobs, int32_t hidden, int32_t hidden2, int64_t rows, void* stream);
 
 /* ---- PPO update on the kernels (forward, loss gradients; the weight gradients come from gr_actor_backward) -----------------
  * One mini-batch step of PPO.update (S/rsl_rl/ext/algorithms/ppo.py:118-171) without autograd:

@@ -52,7 +52,7 @@ def _c_struct_fields(name):
     return fields
 
 
-@pytest.mark.parametrize("name", ["GrConfig", "GrTrack", "GrState", "GrRandom", "GrStepIO", "GrBwdIO", "GrTransition", "GrStorage", "GrMiniBatch", "GrHostStep", "GrMlp", "GrPolicy", "GrCollectIO", "GrBpttCollectIO", "GrMlpGrad", "GrPpoBatch", "GrAdamStep"])
+@pytest.mark.parametrize("name", ["GrConfig", "GrTrack", "GrState", "GrRandom", "GrStepIO", "GrBwdIO", "GrTransition", "GrStorage", "GrMiniBatch", "GrHostStep", "GrMlp", "GrPolicy", "GrCollectIO", "GrBpttCollectIO", "GrMlpGrad", "GrPpoBatch", "GrAdamStep", "GrBackwardJob"])
 def test_ctypes_structs_follow_the_header(name):
     assert [f for f, _ in getattr(B, name)._fields_] == _c_struct_fields(name)
 
@@ -73,6 +73,7 @@ def test_argument_errors_are_reported_without_launch(lib):
     assert lib.gr_ppo_loss_grad(None, 128, None, None, None, None) == -1
     assert lib.gr_policy_pack(None, None, None, None) == -1
     assert lib.gr_adam_clip_step(None, None) == -1
+    assert lib.gr_actor_backward_jobs(None, 2, 128, 128, 128, None) == -1
     assert lib.gr_policy_packed_bytes(128, 128, 2) == 2 * 45440 and lib.gr_policy_packed_bytes(256, 128, 1) == 86400
     assert lib.gr_policy_packed_bytes(64, 64, 1) < 0 and lib.gr_policy_packed_bytes(128, 128, 3) < 0
     pol, grads = B.GrPolicy(16, 16, 0.01), B.GrMlpGrad(16, 16, 16, 16, 16, 16, 4, 0)
