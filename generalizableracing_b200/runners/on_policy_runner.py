@@ -118,7 +118,7 @@ class OnPolicyRunner:
                 torch.distributed.all_reduce(stats)
             n_ep = max(float(stats[2]), 1.0)
             rec = {"iteration": it, "Loss/value_function": loss_dict["value_function"], "Loss/surrogate": loss_dict["surrogate"],
-                   "Loss/learning_rate": self.alg.learning_rate, "Policy/mean_noise_std": float(self.alg.policy.action_std.mean()) if self.alg.policy.distribution is not None else None,
+                   "Loss/learning_rate": self.alg.learning_rate, "Policy/mean_noise_std": float(self.alg.policy.action_std.detach().mean()) if self.alg.policy.distribution is not None else None,
                    "Perf/total_fps": int(self.num_steps_per_env * N * world / (collection_time + learn_time)),
                    "Perf/collection time": collection_time, "Perf/learning_time": learn_time,
                    "Train/mean_reward": float(stats[0]) / n_ep, "Train/mean_episode_length": float(stats[1]) / n_ep, "Train/episodes": int(stats[2]),
@@ -145,6 +145,7 @@ class OnPolicyRunner:
 
     def load(self, path, load_optimizer=True):
         loaded = torch.load(path, map_location=self.device, weights_only=False)
+        self.alg.close()               # a captured update graph aliases the optimizer state: rebuild it from what is loaded
         self.alg.policy.load_state_dict(loaded["model_state_dict"])
         if load_optimizer:
             self.alg.optimizer.load_state_dict(loaded["optimizer_state_dict"])

@@ -35,6 +35,46 @@ def test_ppo_runner_c2(cuda_lib, tmp_path):
     runner.load(str(tmp_path / "m.pt"))
 
 
+def test_ppo_runner_checkpoint_resume_with_kernel_update(cuda_lib, tmp_path):
+    """save() after captured kernel updates, load() into a FRESH runner (and into the live one): the Adam moments / step count /
+    adaptive learning rate survive, and both keep training through the captured path (on_policy_runner.py:288-318)."""
+    from generalizableracing_b200 import make_env
+    from generalizableracing_b200.runners import OnPolicyRunner
+    cfg = dict(PPO_CFG, fused_collection=True)
+    cfg["algorithm"] = dict(PPO_CFG["algorithm"], graphed_update=True, kernel_update=True)
+    torch.manual_seed(0)
+    r1 = OnPolicyRunner(make_env(num_envs=1024, stage=1), cfg, device="cuda:0")
+    r1.learn(4, init_at_random_ep_len=True)
+    assert r1.alg._graph is not None
+    r1.save(str(tmp_path / "ck.pt"))
+    ref_params = [p.detach().clone() for p in r1.alg.policy.parameters()]
+    ref_state = {i: {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                 for i, st in r1.alg.optimizer.state_dict()["state"].items()}
+    steps_done = float(ref_state[0]["step"])
+    assert steps_done == 4 * 5 * 4
+
+    r2 = OnPolicyRunner(make_env(num_envs=1024, stage=1, seed=5), cfg, device="cuda:0")
+    r2.load(str(tmp_path / "ck.pt"))
+    assert r2.current_learning_iteration == 3          # the reference's counter is the last iteration index
+    for p, q in zip(r2.alg.policy.parameters(), ref_params):
+        assert torch.equal(p, q)
+    st2 = r2.alg.optimizer.state_dict()["state"]
+    for i, st in ref_state.items():
+        assert torch.equal(st2[i]["exp_avg"], st["exp_avg"]) and torch.equal(st2[i]["exp_avg_sq"], st["exp_avg_sq"])
+    hist = r2.learn(3)
+    assert r2.alg._graph is not None and r2.current_learning_iteration == 5
+    assert float(r2.alg.optimizer.state_dict()["state"][0]["step"]) == steps_done + 3 * 5 * 4
+    assert all(torch.isfinite(torch.tensor(h["Loss/value_function"])) for h in hist)
+
+    r1.load(str(tmp_path / "ck.pt"))                       # into the live runner: the graph is dropped and rebuilt from the loaded state
+    assert r1.alg._graph is None
+    r1.learn(2)
+    assert r1.alg._graph is not None
+    assert float(r1.alg.optimizer.state_dict()["state"][0]["step"]) == steps_done + 2 * 5 * 4
+    for p in r1.alg.policy.parameters():
+        assert torch.isfinite(p).all()
+
+
 def test_bptt_runner_reduces_loss(cuda_lib):
     """BPTT on the differentiable closure: the analytic gradient must be a descent direction (loss goes down)."""
     from generalizableracing_b200 import make_env
