@@ -122,6 +122,33 @@ GR_HOST_PIPE_MAX_DEPTH = 4
 GR_LAUNCH_PDL = 1
 GR_LAUNCH_PREFETCH = 2
 GR_LOG_SLOTS = 16
+class GrReachConfig(C.Structure):
+    _fields_ = [
+        ("controller", c_i), ("sim2real_test", c_i), ("last_action_modified", c_i), ("random_drag", c_i),
+        ("dt", c_f), ("max_episode_length", c_i), ("gravity", c_f), ("grad_decay", c_f), ("mass", c_f), ("inertia", c_f * 3),
+        ("action_scale", c_f * 4), ("action_offset", c_f * 4), ("thrust_lo", c_f), ("thrust_hi", c_f), ("body_rate_bound", c_f),
+        ("kp", c_f * 3), ("kd", c_f * 3), ("thrust_delay", c_f), ("torque_delay", c_f * 3),
+        ("speed_gain", c_f * 3), ("pose_gain", c_f * 3), ("rate_gain", c_f * 3), ("pos_gain", c_f * 3), ("max_feedback_accel", c_f),
+        ("drag1", c_f), ("drag1_rand", c_f), ("drag2", c_f), ("drag2_rand", c_f), ("z_drag", c_f), ("z_drag_rand", c_f),
+        ("thr_err_reset_std", c_f),
+        ("default_pos", c_f * 3), ("reset_lo", c_f * 6), ("reset_hi", c_f * 6),
+        ("cmd_lo", c_f * 3), ("cmd_hi", c_f * 3), ("resample_time", c_f),
+        ("term_oob", c_i), ("oob_lo", c_f), ("oob_hi", c_f),
+        ("w_reward", c_f * L.REACH_NUM_REWARD_TERMS), ("move_in_dir_thr", c_f), ("reach_thr", c_f), ("hover_thr", c_f), ("hover_ratio", c_f),
+        ("w_loss", c_f * L.REACH_NUM_LOSS_TERMS), ("loss_dir_thr", c_f), ("loss_smooth_ratio", c_f),
+    ]
+
+
+class GrReachState(C.Structure):
+    _fields_ = [("planes", c_p), ("plane_stride", C.c_int64), ("num_envs", c_i), ("env_id_offset", c_i)]
+
+
+class GrReachStepIO(C.Structure):
+    _fields_ = [("action", c_p), ("obs", c_p), ("reward", c_p), ("terminated", c_p), ("time_out", c_p), ("dones", c_p), ("reward_terms", c_p),
+                ("loss", c_p), ("loss_terms", c_p), ("tape", c_p), ("tape_stride", C.c_int64), ("log_accum", c_p)]
+
+
+GR_REACH_LOG_NUM_RESET, GR_REACH_LOG_SUM_POS_ERR, GR_REACH_LOG_SUM_EPSUM, GR_REACH_LOG_NUM_TIMEOUT, GR_REACH_LOG_NUM_TERMINATED = 0, 1, 2, 12, 13
 GR_LOG_SHARDS = 256
 GR_PHILOX_CALL_ACTION = 16
 STATUS = {0: "GR_OK", -1: "GR_ERR_NULL", -2: "GR_ERR_SIZE", -3: "GR_ERR_ALIGN", -4: "GR_ERR_CONFIG", -5: "GR_ERR_SMEM"}
@@ -152,6 +179,11 @@ PROTOTYPES = {
     "gr_ppo_loss_grad": (C.c_int, [C.POINTER(GrPpoBatch), C.c_int64, c_p, c_p, c_p, c_p]),
     "gr_adam_clip_step": (C.c_int, [C.POINTER(GrAdamStep), c_p]),
     "gr_actor_backward_jobs": (C.c_int, [C.POINTER(GrBackwardJob), c_i, c_i, c_i, C.c_int64, c_p]),
+    "gr_reach_reset": (C.c_int, [C.POINTER(GrReachConfig), C.POINTER(GrReachState), C.POINTER(GrRandom), c_p, c_p, c_p]),
+    "gr_reach_observe": (C.c_int, [C.POINTER(GrReachConfig), C.POINTER(GrReachState), c_p, c_p]),
+    "gr_reach_step_fwd": (C.c_int, [C.POINTER(GrReachConfig), C.POINTER(GrReachState), C.POINTER(GrRandom), C.POINTER(GrReachStepIO), c_p]),
+    "gr_reach_step_bwd": (C.c_int, [C.POINTER(GrReachConfig), C.POINTER(GrReachState), C.POINTER(GrBwdIO), c_p]),
+    "gr_reach_fill_rand": (C.c_int, [c_p, c_i, c_i, C.c_uint64, C.c_uint32, c_p]),
     "gr_host_pipe_create": (C.c_int, [c_i, c_i, c_p, C.POINTER(c_p)]),
     "gr_host_pipe_destroy": (C.c_int, [c_p]),
     "gr_host_pipe_step": (C.c_int, [c_p, C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom),

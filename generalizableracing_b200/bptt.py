@@ -55,9 +55,10 @@ class BpttWindow:
     def _alloc(self, capacity: int):
         env = self.env
         dev, N = env.device, env.num_envs
-        self.tape = torch.zeros(capacity, env.num_tiles, L.TAPE_PLANES, L.TILE, 4, device=dev)     # per-warp tiles, like the state
+        self._terms = getattr(env, "_num_loss_terms", 3)               # (the reach-target env: 13 tape planes, 4 loss terms)
+        self.tape = torch.zeros(capacity, env.num_tiles, getattr(env, "_tape_planes", L.TAPE_PLANES), L.TILE, 4, device=dev)     # per-warp tiles, like the state
         self.loss = torch.zeros(capacity, N, device=dev)
-        self.loss_terms = torch.zeros(capacity, N, 3, device=dev)
+        self.loss_terms = torch.zeros(capacity, N, self._terms, device=dev)
         self.grad_loss = torch.zeros(capacity, N, device=dev)
         self.grad_action = torch.zeros(capacity, N, L.NUM_ACTIONS, device=dev)
         self.capacity = capacity
@@ -72,13 +73,13 @@ class BpttWindow:
         self.grad_action.zero_()
         self._token = None
 
-    def bind_step(self, io: B.GrStepIO):
+    def bind_step(self, io):
         if self.t >= self.capacity:
             raise RuntimeError(f"BPTT horizon exceeded the tape capacity ({self.capacity} steps): call env.unwrapped.detach() "
                                "between windows or construct the env with a larger bptt_horizon")
         t, n = self.t, self.env.num_envs
         io.loss = self._p_loss + t * n * 4
-        io.loss_terms = self._p_terms + t * n * 12
+        io.loss_terms = self._p_terms + t * n * 4 * self._terms
         io.tape = self._p_tape + t * self._tape_step_bytes
         io.tape_stride = self.env._stride
 
@@ -107,7 +108,8 @@ class BpttWindow:
         io.adjoint = self.adjoint.data_ptr()
         io.adj_stride = env._stride
         io.grad_action = self.grad_action.data_ptr()
-        B.check(env._lib.gr_step_bwd(C.byref(env._gcfg), C.byref(env._state), C.byref(io), env._stream()), "gr_step_bwd")
+        fn = getattr(env, "_bwd_fn", None) or env._lib.gr_step_bwd
+        B.check(fn(C.byref(env._gcfg), C.byref(env._state), C.byref(io), env._stream()), "gr_step_bwd")
 
     def backward_window(self, grad_scale: float = None, grad_losses: torch.Tensor = None) -> torch.Tensor:
         """One reverse sweep over the whole window.  ``grad_losses`` [T,N] = dL/d(extras["losses"]) or a uniform

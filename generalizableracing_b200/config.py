@@ -146,3 +146,134 @@ class RacingCfg:
 
     def to_dict(self):
         return asdict(self)
+
+
+# =====================================================================================================================
+# Reach-target tasks: the reference's original differentiable tasks, sharing DroneDynamics with
+# the racing path but driven by the other command modes (LVController / PSController) or CTBR, with their own command,
+# reward, observation and loss terms.  QD/reach_target_lv_env.py, QD/reach_target_ctbr_env.py.
+# =====================================================================================================================
+REACH_REWARD_TERM_NAMES = ("move_towards", "orientation_reward", "move_in_dir", "action_rate", "reach_target", "smooth_ang_vel",
+                           "smooth_lin_acc", "smooth_ang_acc", "early_termination", "hover_state")     # QD/reach_target_lv_env.py:129-189
+REACH_LOSS_TERM_NAMES = ("move_towards_goal", "orientation_tracking", "move_in_dir", "smooth_vel")       # :191-219
+CONTROLLERS = ("CTBRController", "LVController", "PSController")
+
+
+@dataclass
+class ReachTargetCfg:
+    """Frozen constants of DiffLab-Quadcopter-{LV,CTBR}-ReachTarget (PhysX-free closure; DESIGN.md §4e lists the substitutions)."""
+
+    controller: str = "LVController"    # DiffActionCfg.command_type, QD/reach_target_lv_env.py:80 / reach_target_ctbr_env.py:81-93
+    sim2real_test: bool = False         # QD/mdp/diff_action.py:168-171: actions are (a_zb, body rates), no tanh, no gradient
+    # --- time ----------------------------------------------------------------
+    sim_dt: float = 0.005               # QD/reach_target_lv_env.py:251
+    decimation: int = 4                 # :246 (6 in the CTBR env, reach_target_ctbr_env.py:258)
+    episode_length_s: float = 6.0       # :247
+    # --- drone (same synthetic mass as the racing closure) -----------------------
+    mass: float = 0.8
+    inertia_diag: Tuple[float, float, float] = (0.0015, 0.002, 0.004)   # QD/mdp/diff_action.py:59
+    gravity: float = 9.81
+    grad_decay: float = 0.92
+    drag_1: float = 0.18
+    drag_1_rand: float = 0.1
+    drag_2: float = 0.01
+    drag_2_rand: float = 0.005
+    z_drag: float = 4.0
+    z_drag_rand: float = 0.4
+    random_drag: bool = True            # QD/mdp/diff_action_cfg.py:38 (False in the CTBR env, :91)
+    # --- action map (QD/mdp/diff_action.py:247-283) --------------------------------
+    max_thrust_weight_ratio: float = 3.0    # CTBR
+    lin_vel_bound: float = 5.0          # LV   (QD/mdp/diff_action_cfg.py:46)
+    pos_bound: float = 1.0              # PS   (:45)
+    action_lag: int = 1
+    thr_est_error_init_std: float = 0.02
+    thr_est_error_reset_std: float = 0.01
+    # --- controllers (L/controllers/controller_diff_cfg.py:43-79) -------------------
+    body_rate_bound: float = 12.0       # 6 in the CTBR env (reach_target_ctbr_env.py:88)
+    rate_gain_p: Tuple[float, float, float] = (50.0, 50.0, 50.0)      # CTBR (35 in the CTBR env)
+    rate_gain_d: Tuple[float, float, float] = (0.0, 0.0, 0.0)         # CTBR (5e-4, 5e-4, 3e-4 in the CTBR env)
+    thrust_ctrl_delay: float = 0.03
+    torque_ctrl_delay: Tuple[float, float, float] = (0.02, 0.02, 0.02)  # CTBR only (0.03 in the CTBR env)
+    max_feedback_accel: float = 20.0    # LV / PS
+    speed_gain: Tuple[float, float, float] = (10.0, 10.0, 20.0)
+    pose_gain: Tuple[float, float, float] = (18.0, 18.0, 20.0)
+    rate_gain: Tuple[float, float, float] = (180.0, 180.0, 200.0)
+    pos_gain: Tuple[float, float, float] = (3.0, 3.0, 3.0)            # PS
+    # --- command: UniformWorldPoseCommand (QD/reach_target_lv_env.py:66-75, QD/mdp/commands.py:113-134) ----
+    cmd_lo: Tuple[float, float, float] = (-2.0, -2.0, 0.5)
+    cmd_hi: Tuple[float, float, float] = (2.0, 2.0, 2.5)
+    resampling_time: float = 10.0
+    # --- reset: reset_root_state_uniform (QD/reach_target_lv_env.py:106-122) -----------
+    default_root_pos: Tuple[float, float, float] = (0.0, 0.0, 0.5)
+    reset_lo: Tuple[float, ...] = (-0.1, -0.1, 1.0, -0.5, -0.5, -3.14)   # x y z roll pitch yaw
+    reset_hi: Tuple[float, ...] = (0.1, 0.1, 2.0, 0.5, 0.5, 3.14)
+    # --- terminations: time_out + illegal_contact (:221-228).  Contacts need PhysX; the closure uses the reference's own
+    #     commented-out alternative `mdp.out_of_bound` (QD/mdp/observation.py:76-84) with the ground plane as lower bound.
+    term_out_of_bound: bool = True
+    oob_lo: float = 0.0
+    oob_hi: float = 10.0
+    # --- rewards (QD/reach_target_lv_env.py:129-189) -------------------------------------
+    w_reward: Tuple[float, ...] = (1.0, 0.5, 1.0, -0.001, 10.0, -0.001, -0.001, -0.0001, -200.0, 1.0)
+    move_in_dir_threshold: float = 0.4
+    reach_threshold: float = 0.1
+    hover_threshold: float = 0.2
+    hover_ratio: float = 0.2
+    # --- losses (:191-219) ------------------------------------------------------------------
+    is_differentiable_physics: bool = True
+    w_loss: Tuple[float, ...] = (1.0, 0.0, 0.0, 0.3)     # target, orientation, move_in_dir, smooth_vel
+    loss_dir_threshold: float = 0.1
+    loss_smooth_ratio: float = 0.5
+    # --- observations (:83-104): last_action = action_manager.action (LV env) or modified_last_action (CTBR env) ----
+    last_action_modified: bool = False
+
+    @staticmethod
+    def lv(**overrides) -> "ReachTargetCfg":
+        """QuadcopterReachTargetLVEnvCfg."""
+        return ReachTargetCfg(**overrides)
+
+    @staticmethod
+    def ps(**overrides) -> "ReachTargetCfg":
+        """The LV env with command_type="PSController" (PSControllerCfg defaults, controller_diff_cfg.py:66-79)."""
+        kw = dict(controller="PSController", speed_gain=(5.0, 5.0, 5.0), pose_gain=(20.0, 20.0, 20.0), rate_gain=(150.0, 150.0, 150.0))
+        kw.update(overrides)
+        return ReachTargetCfg(**kw)
+
+    @staticmethod
+    def ctbr(sim2real_test: bool = False, **overrides) -> "ReachTargetCfg":
+        """QuadcopterReachTargetCTBREnvCfg; the shipped file has SIM2REAL_TEST=True (60 s episodes, raw a_zb / body-rate inputs)."""
+        kw = dict(controller="CTBRController", sim2real_test=sim2real_test, decimation=6, episode_length_s=60.0 if sim2real_test else 6.0,
+                  random_drag=False, body_rate_bound=6.0, rate_gain_p=(35.0, 35.0, 35.0), rate_gain_d=(0.0005, 0.0005, 0.0003),
+                  torque_ctrl_delay=(0.03, 0.03, 0.03), reset_lo=(-0.1, -0.1, 1.0, 0.0, 0.0, -3.14), reset_hi=(0.1, 0.1, 2.0, 0.0, 0.0, 3.14),
+                  w_loss=(1.0, 1.0, 1.0, 0.1), last_action_modified=True)
+        kw.update(overrides)
+        return ReachTargetCfg(**kw)
+
+    @property
+    def step_dt(self) -> float:
+        return self.sim_dt * self.decimation
+
+    @property
+    def max_episode_length(self) -> int:
+        return math.ceil(self.episode_length_s / self.step_dt)
+
+    @property
+    def gross_thrust_bound(self) -> Tuple[float, float]:
+        return (_rotor_thrust(_MOTOR_OMEGA[0]) * 4, _rotor_thrust(_MOTOR_OMEGA[1]) * 4)
+
+    @property
+    def action_scale(self) -> Tuple[float, float, float, float]:
+        # QD/mdp/diff_action.py:257-275 ("medium")
+        if self.controller == "CTBRController":
+            half = self.mass * self.gravity * self.max_thrust_weight_ratio / 2.0
+            return (half, self.body_rate_bound, self.body_rate_bound, self.body_rate_bound)
+        b = self.lin_vel_bound if self.controller == "LVController" else self.pos_bound
+        return (3.1415926, b, b, b)
+
+    @property
+    def action_offset(self) -> Tuple[float, float, float, float]:
+        if self.controller == "CTBRController":
+            return (self.mass * self.gravity * self.max_thrust_weight_ratio / 2.0, 0.0, 0.0, 0.0)
+        return (0.0, 0.0, 0.0, 0.0)
+
+    def to_dict(self):
+        return asdict(self)

@@ -87,3 +87,37 @@ PK_FRESH_SHIFT = 31    # 1 = env was reset at the previous step (action latches 
 
 # --- BPTT tape: 7 float4 planes per env-step ------------------------------------------------
 TAPE_PLANES = 7
+
+# =====================================================================================================================
+# Reach-target tasks (mirrored in include/gracing.h, GR_REACH_*)
+# =====================================================================================================================
+REACH_OBS_DIM = 17          # lin_vel_b 3 | ang_vel_b 3 | last action 4 | root quat 4 | desired_pos_b 3   (QD/reach_target_lv_env.py:83-104)
+REACH_NUM_REWARD_TERMS = 10
+REACH_NUM_LOSS_TERMS = 4
+# per-step random slots, consumed only on reset (U uniform [0,1), N standard normal) ...
+REACH_RND_RESET_POSE = 0    # 6 U : x y z roll pitch yaw            (Isaac Lab mdp.reset_root_state_uniform)
+REACH_RND_Z_DRAG = 6        # 1 U                                   (QD/mdp/dynamics/droneDynamics.py:53)
+REACH_RND_DRAG2 = 7         # 3 U
+REACH_RND_DRAG1 = 10        # 3 U
+REACH_RND_THR_ERR = 13      # 1 N : thr_est_error re-draw on reset  (QD/mdp/diff_action.py:233)
+REACH_RND_CMD = 14          # 3 U : new target, on reset            (QD/mdp/commands.py:113-121)
+REACH_RND_SPARE = 17
+# ... or when the command timer runs out (commands resample every `resampling_time` seconds)
+REACH_RND_CMD_TIMER = 18    # 3 U  (18, 19, 20)
+REACH_RND_STRIDE = 24       # 6 Philox calls
+# env state: 32-env tiles x REACH_PLANES planes x float4 (csrc/reach_core.cuh ReachPlane)
+REACH_PLANES = 13
+RPL_QUAT = 0      # q.w q.x q.y q.z
+RPL_POS = 1       # pos x y z       | thrust filter state f
+RPL_LINVEL = 2    # v_w x y z       | episode_length (int32 bits)
+RPL_ANGVEL = 3    # omega_b x y z   | command time_left
+RPL_TORQUE = 4    # CTBR torque filter state x y z | raw_actions.w
+RPL_ANGACC = 5    # alpha_b x y z   | fresh flag (1.0 = reset at the previous step: action latches are zero)
+RPL_FIFO = 6      # action-lag FIFO (raw a_{t-1})
+RPL_TARGET = 7    # pose_command_w xyz | raw_actions.x
+RPL_EPSUM0 = 8    # episode sums of reward terms 0..3
+RPL_EPSUM1 = 9    # 4..7
+RPL_EPSUM2 = 10   # 8..9 | raw_actions.y | raw_actions.z     (raw_actions = the lagged action the last step applied)
+RPL_DRAG2 = 11    # quadratic drag x y z(*z_drag) | spare           -- planes 11, 12 are rewritten only on reset
+RPL_DRAG1 = 12    # linear drag x y z(*z_drag)    | thr_est_error
+REACH_TAPE_PLANES = 13

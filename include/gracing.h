@@ -395,6 +395,89 @@ int gr_host_pipe_step(GrHostPipe* pipe, const GrConfig* cfg, const GrTrack* trac
                       const GrHostStep* host, float* log_accum /* device, optional */, int64_t* ticket_out);
 int gr_host_pipe_wait(GrHostPipe* pipe, int64_t ticket);
 
+/* ---- reach-target tasks: the other command modes and tasks sharing the dynamics ----------------
+ * QD/reach_target_lv_env.py + QD/reach_target_ctbr_env.py: the same ManagerBasedDiffRLEnv.step ordering as gr_step_fwd
+ * with DiffActions driving LVController / PSController (L/controllers/controller_diff.py:172-443) or CTBRController
+ * (:37-170), UniformWorldPoseCommand (QD/mdp/commands.py:32-134), the reach-target rewards (QD/mdp/rewards.py:30-101 +
+ * Isaac Lab action_rate_l2 / body_lin_acc_l2 / is_terminated), observations (QD/reach_target_lv_env.py:83-104), the
+ * reach-target losses (QD/mdp/losses.py:32-67), Isaac Lab reset_root_state_uniform and time_out.  Closure substitutions:
+ * oracle/reach_oracle.py R.1-R.5 (contacts := z bounds).  State: 32-env tiles of GR_REACH_PLANES float4 planes. */
+#define GR_REACH_OBS_DIM 17
+#define GR_REACH_NUM_REWARD_TERMS 10
+#define GR_REACH_NUM_LOSS_TERMS 4
+#define GR_REACH_RND_STRIDE 24
+#define GR_REACH_PLANES 13
+#define GR_REACH_TAPE_PLANES 13
+#define GR_CTRL_CTBR 0
+#define GR_CTRL_LV 1
+#define GR_CTRL_PS 2
+
+typedef struct GrReachConfig {
+  int32_t controller;       /* GR_CTRL_* = DiffActionCfg.command_type */
+  int32_t sim2real_test;    /* QD/mdp/diff_action.py:168-171: raw (a_zb, body-rate) inputs, no tanh, no gradient */
+  int32_t last_action_modified;   /* observation term: 0 = mdp.last_action, 1 = modified_last_action (QD/mdp/observation.py:55-63) */
+  int32_t random_drag;
+  float dt;
+  int32_t max_episode_length;
+  float gravity, grad_decay, mass;
+  float inertia[3];
+  float action_scale[4], action_offset[4];    /* QD/mdp/diff_action.py:257-275 */
+  float thrust_lo, thrust_hi, body_rate_bound;
+  float kp[3], kd[3], thrust_delay, torque_delay[3];                       /* CTBR */
+  float speed_gain[3], pose_gain[3], rate_gain[3], pos_gain[3], max_feedback_accel;   /* LV / PS */
+  float drag1, drag1_rand, drag2, drag2_rand, z_drag, z_drag_rand;
+  float thr_err_reset_std;
+  float default_pos[3], reset_lo[6], reset_hi[6];      /* reset_root_state_uniform: x y z roll pitch yaw */
+  float cmd_lo[3], cmd_hi[3], resample_time;           /* UniformWorldPoseCommand */
+  int32_t term_oob;
+  float oob_lo, oob_hi;
+  float w_reward[GR_REACH_NUM_REWARD_TERMS];  /* move_towards, orientation, move_in_dir, action_rate, reach_target, smooth_ang_vel,
+                                                 smooth_lin_acc, smooth_ang_acc, early_termination, hover_state */
+  float move_in_dir_thr, reach_thr, hover_thr, hover_ratio;
+  float w_loss[GR_REACH_NUM_LOSS_TERMS];      /* target_diff, orientation_diff, move_in_dir_diff, smooth_vel_diff */
+  float loss_dir_thr, loss_smooth_ratio;
+} GrReachConfig;
+
+typedef struct GrReachState {
+  float* planes;            /* [tiles][GR_REACH_PLANES][32] float4, 16-byte aligned; zero-filled before the first gr_reach_reset */
+  int64_t plane_stride;     /* env capacity = 32 * tiles */
+  int32_t num_envs;
+  int32_t env_id_offset;    /* global id of env 0 of this shard (Philox key) */
+} GrReachState;
+
+typedef struct GrReachStepIO {
+  const float* action;      /* [N,4] */
+  float* obs;               /* [N,17]                                                required */
+  float* reward;            /* [N]                                                   required */
+  uint8_t* terminated;      /* [N]                                                   required */
+  uint8_t* time_out;        /* [N]                                                   required */
+  int64_t* dones;           /* [N]                                                   optional */
+  float* reward_terms;      /* [N,10] RewardManager._step_reward                     optional */
+  float* loss;              /* [N] extras["losses"]                                  optional */
+  float* loss_terms;        /* [N,4] weighted loss terms                             optional */
+  float* tape;              /* [tiles][GR_REACH_TAPE_PLANES][32] float4 of THIS step optional (BPTT) */
+  int64_t tape_stride;
+  float* log_accum;         /* [GR_LOG_SHARDS][GR_LOG_SLOTS], GR_REACH_LOG_*         optional */
+} GrReachStepIO;
+
+#define GR_REACH_LOG_NUM_RESET 0
+#define GR_REACH_LOG_SUM_POS_ERR 1     /* sum over reset envs of Metrics/desired_pos_b/position_error */
+#define GR_REACH_LOG_SUM_EPSUM 2       /* +k: episode sum of reward term k (10) */
+#define GR_REACH_LOG_NUM_TIMEOUT 12
+#define GR_REACH_LOG_NUM_TERMINATED 13
+
+/* ManagerBasedRLEnv.reset() / _reset_idx(mask) then observations.  reset_mask NULL => all envs. */
+int gr_reach_reset(const GrReachConfig* cfg, const GrReachState* st, const GrRandom* rng, const uint8_t* reset_mask, float* obs, void* stream);
+/* observation_manager.compute() alone. */
+int gr_reach_observe(const GrReachConfig* cfg, const GrReachState* st, float* obs, void* stream);
+int gr_reach_step_fwd(const GrReachConfig* cfg, const GrReachState* st, const GrRandom* rng, const GrReachStepIO* io, void* stream);
+/* Reverse sweep over tape steps [t_begin, t_end): analytic backward of DroneDynamics.step/align, the controller (full 4x4
+ * action Jacobian of the LV / PS outer loop, taken in forward mode while the step runs) and the action map; same GrBwdIO
+ * contract as gr_step_bwd. */
+int gr_reach_step_bwd(const GrReachConfig* cfg, const GrReachState* st, const GrBwdIO* io, void* stream);
+/* Dense random tensor [N, GR_REACH_RND_STRIDE] exactly as the in-kernel Philox path draws it. */
+int gr_reach_fill_rand(float* rnd, int32_t num_envs, int32_t env_id_offset, uint64_t seed, uint32_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,7 +76,7 @@ def load():
     _load("_gr_ref_controllers.thrust_controller_diff", os.path.join(REF_ROOT, _L, "controllers/thrust_controller_diff.py"))
     ctrl = _load("_gr_ref_controllers.controller_diff", os.path.join(REF_ROOT, _L, "controllers/controller_diff.py"))
     sto = _load("_gr_ref_rollout_storage", os.path.join(REF_ROOT, "standalone/rsl_rl/ext/storage/rollout_storage.py"))
-    ns = types.SimpleNamespace(DroneDynamics=dyn.DroneDynamics, CTBRController=ctrl.CTBRController,
+    ns = types.SimpleNamespace(DroneDynamics=dyn.DroneDynamics, CTBRController=ctrl.CTBRController, LVController=ctrl.LVController, PSController=ctrl.PSController,
                                RolloutStorage=sto.RolloutStorage)
     _cache["ns"] = ns
     return ns
@@ -92,6 +92,17 @@ def ctbr_cfg(cfg):
         body_rate_bound=[-cfg.body_rate_bound, cfg.body_rate_bound],
         thrust_ctrl_delay=cfg.thrust_ctrl_delay, torque_ctrl_delay=tuple(cfg.torque_ctrl_delay),
         use_motor_model=False,
+    )
+
+
+def outer_loop_cfg(cfg):
+    """Plain object carrying the LVControllerCfg / PSControllerCfg fields (L/controllers/controller_diff_cfg.py:56-79)."""
+    return types.SimpleNamespace(
+        arm_length=0.09, kappa=0.016, motor_tau=0.0001, motor_omega=(150, 3000), g=cfg.gravity,
+        thrustmap=[1.3298253500372892e-06, 0.0038360810526746033, -1.7689986848125325],
+        max_feedback_accel=cfg.max_feedback_accel, body_rate_bound=[-cfg.body_rate_bound, cfg.body_rate_bound],
+        speed_gain=list(cfg.speed_gain), pose_gain=list(cfg.pose_gain), rate_gain=list(cfg.rate_gain), pos_gain=list(cfg.pos_gain),
+        thrust_ctrl_delay=cfg.thrust_ctrl_delay, torque_ctrl_delay=tuple(cfg.torque_ctrl_delay), use_motor_model=False,
     )
 
 

@@ -21,7 +21,7 @@ def _stale():
         return True
     t = os.path.getmtime(_SO)
     deps = [os.path.join(_HERE, f) for f in ("emul.cpp", "cuda_shim.h")] + \
-           [os.path.join(_CSRC, f) for f in ("racing_step.cu", "racing_bwd.cu", "gr_math.cuh", "gr_common.cuh")] + \
+           [os.path.join(_CSRC, f) for f in ("racing_step.cu", "racing_bwd.cu", "gr_math.cuh", "gr_common.cuh", "reach_step.cu", "reach_bwd.cu", "reach_core.cuh", "racing_step_core.cuh")] + \
            [os.path.join(_HERE, "..", "..", "include", "gracing.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -45,6 +45,10 @@ class EmulLib:
         self._l.emul_step_bwd.argtypes = [P(B.GrConfig), P(B.GrState), P(B.GrBwdIO)]
         self._l.emul_fill_rand.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32]
         self._l.emul_fill_startup_rand.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64]
+        self._l.emul_reach_step_fwd.argtypes = [P(B.GrReachConfig), P(B.GrReachState), P(B.GrRandom), P(B.GrReachStepIO)]
+        self._l.emul_reach_reset.argtypes = [P(B.GrReachConfig), P(B.GrReachState), P(B.GrRandom), C.c_void_p, C.c_int, C.c_void_p]
+        self._l.emul_reach_step_bwd.argtypes = [P(B.GrReachConfig), P(B.GrReachState), P(B.GrBwdIO)]
+        self._l.emul_reach_fill_rand.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32]
 
     def gr_step_fwd(self, cfg, tr, st, rng, io, stream):
         return self._l.emul_step_fwd(cfg, tr, st, rng, io)
@@ -66,3 +70,18 @@ class EmulLib:
 
     def gr_fill_startup_rand(self, srnd, n, off, seed, stream):
         return self._l.emul_fill_startup_rand(srnd, n, off, seed)
+
+    def gr_reach_step_fwd(self, cfg, st, rng, io, stream):
+        return self._l.emul_reach_step_fwd(cfg, st, rng, io)
+
+    def gr_reach_reset(self, cfg, st, rng, mask, obs, stream):
+        return self._l.emul_reach_reset(cfg, st, rng, mask, 0 if mask else 1, obs)
+
+    def gr_reach_observe(self, cfg, st, obs, stream):
+        return self._l.emul_reach_reset(cfg, st, None, None, 2, obs)
+
+    def gr_reach_step_bwd(self, cfg, st, io, stream):
+        return self._l.emul_reach_step_bwd(cfg, st, io)
+
+    def gr_reach_fill_rand(self, rnd, n, off, seed, step, stream):
+        return self._l.emul_reach_fill_rand(rnd, n, off, seed, step)

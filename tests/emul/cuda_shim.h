@@ -40,6 +40,8 @@ static inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * (uint64_t)b) >> 32); }
 static inline void sincospif(float a, float* s, float* c) { *s = (float)std::sin(3.14159265358979323846 * (double)a); *c = (float)std::cos(3.14159265358979323846 * (double)a); }
 static inline void __syncthreads() {}
+static inline void __syncwarp(unsigned = 0xffffffffu) {}
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
 static inline bool __any_sync(unsigned, bool p) { return p; }
 static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }

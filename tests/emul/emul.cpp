@@ -4,6 +4,8 @@
 #include "cuda_shim.h"
 #include "../../generalizableracing_b200/csrc/racing_step.cu"
 #include "../../generalizableracing_b200/csrc/racing_bwd.cu"
+#include "../../generalizableracing_b200/csrc/reach_step.cu"
+#include "../../generalizableracing_b200/csrc/reach_bwd.cu"
 
 using namespace gr;
 
@@ -55,6 +57,32 @@ int emul_fill_rand(float* rnd, int32_t num_envs, int32_t env_id_offset, uint64_t
 
 int emul_fill_startup_rand(float* srnd, int32_t num_envs, int32_t env_id_offset, uint64_t seed) {
   run_grid(num_envs, [&] { fill_startup_rand_kernel(srnd, num_envs, env_id_offset, seed); });
+  return 0;
+}
+
+int emul_reach_step_fwd(const GrReachConfig* cfg, const GrReachState* st, const GrRandom* rng, const GrReachStepIO* io) {
+  const bool diff = io->loss || io->tape || io->loss_terms, philox = rng->rnd == nullptr;
+#define GO(a, b) if (diff == a && philox == b) { run_grid(st->num_envs, [&] { reach_step_fwd_kernel<a, b>(*cfg, *st, *rng, *io); }); return 0; }
+  GO(false, false) GO(false, true) GO(true, false) GO(true, true)
+#undef GO
+  return -100;
+}
+
+int emul_reach_reset(const GrReachConfig* cfg, const GrReachState* st, const GrRandom* rng, const uint8_t* mask, int mode, float* obs) {
+  const GrRandom none{nullptr, 0, 0};
+  const GrRandom& r = rng ? *rng : none;
+  if (r.rnd == nullptr) run_grid(st->num_envs, [&] { reach_reset_kernel<true>(*cfg, *st, r, mask, mode, obs); });
+  else run_grid(st->num_envs, [&] { reach_reset_kernel<false>(*cfg, *st, r, mask, mode, obs); });
+  return 0;
+}
+
+int emul_reach_step_bwd(const GrReachConfig* cfg, const GrReachState* st, const GrBwdIO* io) {
+  run_grid(st->num_envs, [&] { reach_step_bwd_kernel(*cfg, *st, *io); });
+  return 0;
+}
+
+int emul_reach_fill_rand(float* rnd, int32_t num_envs, int32_t env_id_offset, uint64_t seed, uint32_t step) {
+  run_grid(num_envs, [&] { reach_fill_rand_kernel(rnd, num_envs, env_id_offset, seed, step); });
   return 0;
 }
 }

@@ -52,7 +52,7 @@ def _c_struct_fields(name):
     return fields
 
 
-@pytest.mark.parametrize("name", ["GrConfig", "GrTrack", "GrState", "GrRandom", "GrStepIO", "GrBwdIO", "GrTransition", "GrStorage", "GrMiniBatch", "GrHostStep", "GrMlp", "GrPolicy", "GrCollectIO", "GrBpttCollectIO", "GrMlpGrad", "GrPpoBatch", "GrAdamStep", "GrBackwardJob"])
+@pytest.mark.parametrize("name", ["GrConfig", "GrTrack", "GrState", "GrRandom", "GrStepIO", "GrBwdIO", "GrTransition", "GrStorage", "GrMiniBatch", "GrHostStep", "GrMlp", "GrPolicy", "GrCollectIO", "GrBpttCollectIO", "GrMlpGrad", "GrPpoBatch", "GrAdamStep", "GrBackwardJob", "GrReachConfig", "GrReachState", "GrReachStepIO"])
 def test_ctypes_structs_follow_the_header(name):
     assert [f for f, _ in getattr(B, name)._fields_] == _c_struct_fields(name)
 
@@ -80,6 +80,21 @@ def test_argument_errors_are_reported_without_launch(lib):
     assert lib.gr_actor_backward(C.byref(pol), 64, 128, C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), 128, C.byref(grads), None) == -2      # widths
     assert lib.gr_actor_backward(C.byref(pol), 256, 128, C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), 0, C.byref(grads), None) == -2       # rows
     assert lib.gr_actor_backward(C.byref(pol), 256, 128, C.c_void_p(8), C.c_void_p(16), C.c_void_p(16), 128, C.byref(grads), None) == -3      # alignment
+    # reach-target entry points
+    assert lib.gr_reach_step_fwd(None, None, None, None, None) == -1
+    assert lib.gr_reach_reset(None, None, None, None, None, None) == -1
+    assert lib.gr_reach_observe(None, None, None, None) == -1
+    assert lib.gr_reach_step_bwd(None, None, None, None) == -1
+    assert lib.gr_reach_fill_rand(None, 4, 0, 0, 0, None) == -1
+    assert lib.gr_reach_fill_rand(C.c_void_p(16), 0, 0, 0, 0, None) == -2
+    assert lib.gr_reach_fill_rand(C.c_void_p(8), 4, 0, 0, 0, None) == -3
+    from generalizableracing_b200.config import ReachTargetCfg
+    from generalizableracing_b200.reach_env import make_gr_reach_config
+    rcfg, rst, rng = make_gr_reach_config(ReachTargetCfg.lv()), B.GrReachState(16, 32, 8, 0), B.GrRandom(None, 0, 0)
+    assert lib.gr_reach_reset(C.byref(rcfg), C.byref(B.GrReachState(16, 0, 8, 0)), C.byref(rng), None, None, None) == -2     # stride < envs
+    assert lib.gr_reach_reset(C.byref(rcfg), C.byref(B.GrReachState(8, 32, 8, 0)), C.byref(rng), None, None, None) == -3     # alignment
+    rcfg.controller = 7
+    assert lib.gr_reach_reset(C.byref(rcfg), C.byref(rst), C.byref(rng), None, None, None) == -4                               # GR_ERR_CONFIG
     pipe = C.c_void_p()
     assert lib.gr_host_pipe_create(64, 2, None, None) == -1
     assert lib.gr_host_pipe_create(0, 2, None, C.byref(pipe)) == -2
@@ -99,3 +114,7 @@ def test_product_refuses_cpu():
         RacingVecEnv(RacingCfg.for_stage(0), figure_eight_track(), 8, device="cpu")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         RolloutStorage("rl", 8, 4, [16], [16], [4], device="cpu")
+    from generalizableracing_b200.config import ReachTargetCfg
+    from generalizableracing_b200.reach_env import ReachTargetVecEnv
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ReachTargetVecEnv(ReachTargetCfg.lv(), 8, device="cpu")
