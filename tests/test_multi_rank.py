@@ -113,6 +113,30 @@ def _w_env_shards(rank, world):
         assert torch.equal(torch.cat(gathered, dim=1), fobs)
 
 
-@pytest.mark.parametrize("fn", ["_w_moments", "_w_grads", "_w_env_shards"])
+def _w_reach_shards(rank, world):
+    """reach-target task: two ranks x 64 envs == one env with 128 envs (Philox keyed by the global env id)."""
+    from generalizableracing_b200.config import ReachTargetCfg
+    from generalizableracing_b200.reach_env import ReachTargetVecEnv
+    from tests.emul import EmulLib
+    lib = EmulLib()
+    cfg, n = ReachTargetCfg.lv(decimation=1, episode_length_s=0.04, is_differentiable_physics=False), 64
+    shard = ReachTargetVecEnv(cfg, n, device="cpu", seed=5, env_id_offset=rank * n, _lib=lib)
+    obs = [shard.reset()[0].clone()]
+    g = torch.Generator().manual_seed(3)
+    acts = torch.randn(20, world * n, 4, generator=g) * 0.5
+    for t in range(20):
+        obs.append(shard.step(acts[t, rank * n:(rank + 1) * n].contiguous())[0].clone())
+    mine = torch.stack(obs)
+    gathered = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    if rank == 0:
+        full = ReachTargetVecEnv(cfg, world * n, device="cpu", seed=5, _lib=lib)
+        fobs = [full.reset()[0].clone()]
+        for t in range(20):
+            fobs.append(full.step(acts[t])[0].clone())
+        assert torch.equal(torch.cat(gathered, dim=1), torch.stack(fobs))
+
+
+@pytest.mark.parametrize("fn", ["_w_moments", "_w_grads", "_w_env_shards", "_w_reach_shards"])
 def test_world_size_2_gloo(fn):
     _run(fn)

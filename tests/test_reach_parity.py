@@ -52,6 +52,25 @@ def test_full_size_invariants(cuda_lib):
     assert float(log["Episode_Termination/time_out"]) > 0 and "Episode_Reward/move_towards" in log
 
 
+def test_ppo_runner_on_the_reach_task(cuda_lib):
+    """OnPolicyRunner (rsl_rl PPO: storage, GAE, mini-batch gather kernels are obs-width agnostic) on the 17-wide reach-target env."""
+    from generalizableracing_b200.config import ReachTargetCfg
+    from generalizableracing_b200.reach_env import make_reach_env
+    from generalizableracing_b200.runners import OnPolicyRunner
+    torch.manual_seed(0)
+    env = make_reach_env("DiffLab-Quadcopter-CTBR-ReachTarget-v0", num_envs=1024, cfg=ReachTargetCfg.ctbr(is_differentiable_physics=False))
+    cfg = {"num_steps_per_env": 24, "save_interval": 1000, "empirical_normalization": False,
+           "policy": {"class_name": "ActorCritic", "init_noise_std": 1.0, "actor_hidden_dims": [128, 128], "critic_hidden_dims": [128, 128], "activation": "lrelu"},
+           "algorithm": {"class_name": "PPO", "value_loss_coef": 1.0, "use_clipped_value_loss": True, "clip_param": 0.2, "entropy_coef": 0.0,
+                         "num_learning_epochs": 5, "num_mini_batches": 4, "learning_rate": 5.0e-4, "schedule": "adaptive", "gamma": 0.99, "lam": 0.95,
+                         "desired_kl": 0.01, "max_grad_norm": 1.0}}
+    runner = OnPolicyRunner(env, cfg, device="cuda:0")
+    hist = runner.learn(4, init_at_random_ep_len=True)
+    assert len(hist) == 4 and all(torch.isfinite(torch.tensor(h["Loss/value_function"])) for h in hist)
+    assert runner.alg.storage.observations.shape == (24, 1024, 17)
+    assert "Episode_Reward/move_towards" in hist[-1] or hist[-1]["Train/episodes"] >= 0
+
+
 def test_bptt_training_reduces_the_reach_loss(cuda_lib):
     """AlgoRunner (BPTT, the reference's `test_hover` schedule: 48-step windows, AdamW + cosine) on the CTBR reach-target task:
     the analytic gradient trains the policy (loss 8.4 -> 4.9 and mean step reward -0.12 -> 0 in 90 iterations at 4096 envs,
