@@ -64,10 +64,13 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
   pdl_launch_dependents();
   // a warp that is entirely past the last env leaves; in the (single) ragged warp the inactive lanes keep shadowing
   // the last env so the warp collectives below stay full-width, and skip every store
-  if (!__any_sync(0xffffffffu, active)) return;
+  const unsigned live = __ballot_sync(0xffffffffu, active);
+  if (live == 0u) return;
+  __shared__ float4 obs_stage[8 * 128];                 // 2 KB per warp, up to 8 warps per block (GlobalObsSink)
 
   StepOut so;
-  if (!racing_step_body<kNoise, kDiff, kPhilox, kStats>(cfg, tr, e, a_t, n01, n23, draws, eps0, eps1, io, i, active, GlobalObsSink{io}, so)) return;
+  if (!racing_step_body<kNoise, kDiff, kPhilox, kStats>(cfg, tr, e, a_t, n01, n23, draws, eps0, eps1, io, i, active,
+                                                        GlobalObsSink{io, live, obs_stage + (threadIdx.x >> 5) * 128}, so)) return;
 
   GR_STAMP(3);
   // ---- 12. outputs + state write-back ----

@@ -210,18 +210,43 @@ struct StepOut {
   bool terminated, time_out, reset, passed, noise_dirty;
 };
 
-// observation sink of the single-step kernel: 128-bit streaming stores into the caller's [N,16] tensors
+// observation sink of the single-step kernel.  A thread owns one 64-byte row; written directly, every store instruction of a
+// warp would touch 32 half-filled sectors.  The warp parks its rows in shared memory (quarter index rotated by row/2: both
+// the 16-byte row writes and the transposed reads are bank-conflict free) and streams them out as four contiguous 512-byte
+// stores.  `live` = the lanes of this warp that own an env (contiguous from lane 0); `stage` = 128 float4 per warp.
 struct GlobalObsSink {
   const GrStepIO& io;
-  __device__ __forceinline__ void policy(int i, float4 o0, float4 o1, float4 o2, float4 o3) const {
-    float4* o = reinterpret_cast<float4*>(io.obs) + (int64_t)i * 4;
-    __stcs(o + 0, o0); __stcs(o + 1, o1); __stcs(o + 2, o2); __stcs(o + 3, o3);
+  unsigned live;
+  float4* stage;
+  __device__ __forceinline__ void rows(float4* __restrict__ out, int i, float4 o0, float4 o1, float4 o2, float4 o3) const {
+#ifdef GR_CPU_EMUL
+    float4* o = out + (int64_t)i * 4;
+    o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3;
+#else
+    const int lane = threadIdx.x & 31, rot = lane >> 1;
+    float4* s = stage + lane * 4;
+    s[(0 + rot) & 3] = o0; s[(1 + rot) & 3] = o1; s[(2 + rot) & 3] = o2; s[(3 + rot) & 3] = o3;
+    __syncwarp(live);
+    float4* dst = out + (int64_t)(i - lane) * 4;
+    if (live == 0xffffffffu) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = k * 32 + lane, r = j >> 2, c = j & 3;
+        __stcs(dst + j, stage[r * 4 + ((c + (r >> 1)) & 3)]);
+      }
+    } else {                                                // the ragged last warp: only the live lanes are here
+      const int nlive = __popc(live);
+      for (int j = lane; j < nlive * 4; j += nlive) {
+        const int r = j >> 2, c = j & 3;
+        __stcs(dst + j, stage[r * 4 + ((c + (r >> 1)) & 3)]);
+      }
+    }
+    __syncwarp(live);                                       // the buffer is reused by the next group of rows
+#endif
   }
+  __device__ __forceinline__ void policy(int i, float4 o0, float4 o1, float4 o2, float4 o3) const { rows(reinterpret_cast<float4*>(io.obs), i, o0, o1, o2, o3); }
   __device__ __forceinline__ bool wants_critic() const { return io.critic_obs != nullptr; }
-  __device__ __forceinline__ void critic(int i, float4 c0, float4 c1, float4 c2, float4 c3) const {
-    float4* c = reinterpret_cast<float4*>(io.critic_obs) + (int64_t)i * 4;
-    __stcs(c + 0, c0); __stcs(c + 1, c1); __stcs(c + 2, c2); __stcs(c + 3, c3);
-  }
+  __device__ __forceinline__ void critic(int i, float4 c0, float4 c1, float4 c2, float4 c3) const { rows(reinterpret_cast<float4*>(io.critic_obs), i, c0, c1, c2, c3); }
   __device__ __forceinline__ void aux(int i, float v) const { if (io.aux_obs) io.aux_obs[i] = v; }
 };
 

@@ -15,14 +15,23 @@ namespace gr {
 // add_transitions: one launch; a thread copies one float4 of one of the row-shaped fields, the first N
 // threads additionally handle the scalar columns (reward with bootstrap, done, value, log-prob).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void copy_rows(const float* __restrict__ src, float* __restrict__ dst, int64_t k4) {
-  reinterpret_cast<float4*>(dst)[k4] = __ldcs(reinterpret_cast<const float4*>(src) + k4);
-}
+// Row widths that are multiples of 4 floats (the racing task: 16 / 16 / 4) move as 128-bit words (V = 4); any other width
+// (the 17-wide reach-target observation) moves as scalars (V = 1).
+template <int V> struct RowVec { using type = float4; };
+template <> struct RowVec<1> { using type = float; };
 
+template <int V>
+__device__ __forceinline__ void copy_rows(const float* __restrict__ src, float* __restrict__ dst, int64_t k4) {
+  using VT = typename RowVec<V>::type;
+  reinterpret_cast<VT*>(dst)[k4] = __ldcs(reinterpret_cast<const VT*>(src) + k4);
+}
+#define copy_rows copy_rows<V>
+
+template <int V>
 __global__ void storage_add_kernel(const GrStorage s, const GrTransition tr, const int step) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t N = s.N;
-  const int64_t n_obs4 = N * s.obs_dim / 4, n_cri4 = s.critic_obs ? N * s.critic_dim / 4 : 0, n_act4 = N * s.act_dim / 4;
+  const int64_t n_obs4 = N * s.obs_dim / V, n_cri4 = s.critic_obs ? N * s.critic_dim / V : 0, n_act4 = N * s.act_dim / V;
   int64_t k = tid;
   if (k < n_obs4) { copy_rows(tr.obs, s.obs + (int64_t)step * N * s.obs_dim, k); }
   else if ((k -= n_obs4) < n_cri4) { copy_rows(tr.critic_obs, s.critic_obs + (int64_t)step * N * s.critic_dim, k); }
@@ -42,6 +51,7 @@ __global__ void storage_add_kernel(const GrStorage s, const GrTransition tr, con
     if (s.log_prob) s.log_prob[(int64_t)step * N + n] = tr.log_prob[n];
   }
 }
+#undef copy_rows
 
 // ---------------------------------------------------------------------------------------------
 // GAE: thread per env scans t = T-1..0 (rollout_storage.py:113-123), writes returns and raw advantages and
@@ -153,9 +163,11 @@ __global__ void adv_normalize_kernel(float* __restrict__ adv, const int64_t tota
 // mini-batch gather: one launch for the nine fields; a thread moves one float4 of a row-shaped field
 // or one element of the five scalar fields.
 // ---------------------------------------------------------------------------------------------
+template <int V>
 __global__ void storage_gather_kernel(const GrStorage s, const int64_t* __restrict__ idx, const int B, const GrMiniBatch o) {
+  using float4 = typename RowVec<V>::type;          // (the row word of this instantiation)
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int o4 = s.obs_dim / 4, c4 = s.critic_obs ? s.critic_dim / 4 : 0, a4 = s.act_dim / 4;
+  const int o4 = s.obs_dim / V, c4 = s.critic_obs ? s.critic_dim / V : 0, a4 = s.act_dim / V;
   const int per_row = o4 + c4 + 3 * a4 + 1;
   const int64_t b = tid / per_row;
   if (b >= B) return;
@@ -182,10 +194,11 @@ using namespace gr;
 
 static inline bool mis16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
 
+static inline bool rows_vec4(const GrStorage* s) { return !((s->obs_dim & 3) || (s->act_dim & 3) || (s->critic_obs && (s->critic_dim & 3))); }
+
 static int check_storage(const GrStorage* s) {
   if (!s || !s->obs || !s->actions || !s->rewards || !s->dones) return GR_ERR_NULL;
   if (s->T <= 0 || s->N <= 0 || s->obs_dim <= 0 || s->act_dim <= 0) return GR_ERR_SIZE;
-  if ((s->obs_dim & 3) || (s->act_dim & 3) || (s->critic_obs && (s->critic_dim & 3))) return GR_ERR_SIZE;
   if (mis16(s->obs) || mis16(s->actions) || (s->critic_obs && mis16(s->critic_obs)) || (s->mu && mis16(s->mu)) || (s->sigma && mis16(s->sigma)))
     return GR_ERR_ALIGN;
   return GR_OK;
@@ -202,8 +215,10 @@ extern "C" int gr_storage_add(const GrStorage* s, const GrTransition* tr, int32_
   if (mis16(tr->obs) || mis16(tr->actions) || (tr->critic_obs && mis16(tr->critic_obs)) || (tr->mu && mis16(tr->mu)) || (tr->sigma && mis16(tr->sigma)))
     return GR_ERR_ALIGN;
   const int64_t N = s->N;
-  const int64_t total = N * s->obs_dim / 4 + (s->critic_obs ? N * s->critic_dim / 4 : 0) + 3 * (N * s->act_dim / 4) + N;
-  storage_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*s, *tr, step);
+  const int V = rows_vec4(s) ? 4 : 1;
+  const int64_t total = N * s->obs_dim / V + (s->critic_obs ? N * s->critic_dim / V : 0) + 3 * (N * s->act_dim / V) + N;
+  if (V == 4) storage_add_kernel<4><<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*s, *tr, step);
+  else storage_add_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*s, *tr, step);
   return (int)cudaGetLastError();
 }
 
@@ -247,8 +262,10 @@ extern "C" int gr_storage_gather(const GrStorage* s, const int64_t* indices, int
   if (s->critic_obs && !out->critic_obs) return GR_ERR_NULL;
   if (B <= 0) return GR_ERR_SIZE;
   if (mis16(out->obs) || mis16(out->actions) || mis16(out->mu) || mis16(out->sigma) || (out->critic_obs && mis16(out->critic_obs))) return GR_ERR_ALIGN;
-  const int per_row = s->obs_dim / 4 + (s->critic_obs ? s->critic_dim / 4 : 0) + 3 * (s->act_dim / 4) + 1;
+  const int V = rows_vec4(s) ? 4 : 1;
+  const int per_row = s->obs_dim / V + (s->critic_obs ? s->critic_dim / V : 0) + 3 * (s->act_dim / V) + 1;
   const int64_t total = (int64_t)B * per_row;
-  storage_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*s, indices, B, *out);
+  if (V == 4) storage_gather_kernel<4><<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*s, indices, B, *out);
+  else storage_gather_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*s, indices, B, *out);
   return (int)cudaGetLastError();
 }

@@ -140,7 +140,12 @@ class OnPolicyRunner:
 
     def save(self, path, infos=None):
         # on_policy_runner.py:288-302 (env state is never checkpointed by the reference either)
-        torch.save({"model_state_dict": self.alg.policy.state_dict(), "optimizer_state_dict": self.alg.optimizer.state_dict(),
+        # With `kernel_update` the optimizer's moments are views of one flat buffer and every parameter's "step" is the SAME
+        # device scalar; torch.save would keep that aliasing and a later eager Adam (_foreach_add_ over 12 aliases of one
+        # address) would race on it.  Checkpoints therefore hold independent copies.
+        opt = self.alg.optimizer.state_dict()
+        opt["state"] = {k: {n: (v.detach().clone() if torch.is_tensor(v) else v) for n, v in st.items()} for k, st in opt["state"].items()}
+        torch.save({"model_state_dict": self.alg.policy.state_dict(), "optimizer_state_dict": opt,
                     "iter": self.current_learning_iteration, "infos": infos}, path)
 
     def load(self, path, load_optimizer=True):

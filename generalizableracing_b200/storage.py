@@ -47,12 +47,10 @@ class RolloutStorage:
         self.privileged_obs_shape = privileged_obs_shape
         self.actions_shape = actions_shape
         T, N, dev = num_transitions_per_env, num_envs, self.device
-        if len(obs_shape) != 1 or len(actions_shape) != 1 or obs_shape[0] % 4 or actions_shape[0] % 4:
-            raise ValueError("observation / action rows must be 1-D with a multiple of 4 floats (128-bit row copies)")
+        if len(obs_shape) != 1 or len(actions_shape) != 1:
+            raise ValueError("observation / action rows must be 1-D (widths that are multiples of 4 floats move as 128-bit words, others as scalars)")
         self.observations = torch.zeros(T, N, *obs_shape, device=dev)
         if privileged_obs_shape[0] is not None:
-            if privileged_obs_shape[0] % 4:
-                raise ValueError("privileged observation rows must hold a multiple of 4 floats")
             self.privileged_observations = torch.zeros(T, N, *privileged_obs_shape, device=dev)
         else:
             self.privileged_observations = None

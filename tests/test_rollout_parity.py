@@ -14,15 +14,15 @@ def _rel(a, b):
     return float((a - b).abs().max() / max(1.0, float(a.abs().max())))
 
 
-def _fill(cuda_lib, T, N, seed, done_p=0.02, to_p=0.01):
+def _fill(cuda_lib, T, N, seed, done_p=0.02, to_p=0.01, od=16, cd=16):
     from generalizableracing_b200.storage import RolloutStorage
     g = torch.Generator().manual_seed(seed)
-    sto = RolloutStorage("rl", N, T, [16], [16], [4], device="cuda:0")
+    sto = RolloutStorage("rl", N, T, [od], [cd], [4], device="cuda:0")
     ref = dict(obs=[], critic=[], actions=[], rewards=[], dones=[], values=[], logp=[], mu=[], sigma=[])
     gamma = 0.99
     for t in range(T):
         tr = sto.Transition()
-        obs, cri, act = torch.randn(N, 16, generator=g), torch.randn(N, 16, generator=g), torch.randn(N, 4, generator=g)
+        obs, cri, act = torch.randn(N, od, generator=g), torch.randn(N, cd, generator=g), torch.randn(N, 4, generator=g)
         rew, val = torch.randn(N, generator=g), torch.randn(N, 1, generator=g)
         dones = (torch.rand(N, generator=g) < done_p)
         tos = dones & (torch.rand(N, generator=g) < 0.5)
@@ -39,9 +39,10 @@ def _fill(cuda_lib, T, N, seed, done_p=0.02, to_p=0.01):
     return sto, ref, g
 
 
-@pytest.mark.parametrize("T,N", [(24, 4096), (1, 1), (7, 130), (24, 65536)])
-def test_add_transitions_and_gae(cuda_lib, T, N):
-    sto, ref, g = _fill(cuda_lib, T, N, seed=T * 1000 + N)
+@pytest.mark.parametrize("T,N,od,cd", [(24, 4096, 16, 16), (1, 1, 16, 16), (7, 130, 16, 16), (24, 65536, 16, 16),
+                                       (24, 1024, 17, 17), (5, 131, 17, 5)])         # 17: the reach-target observation (scalar row path)
+def test_add_transitions_and_gae(cuda_lib, T, N, od, cd):
+    sto, ref, g = _fill(cuda_lib, T, N, seed=T * 1000 + N, od=od, cd=cd)
     assert torch.equal(sto.observations.cpu(), ref["obs"]) and torch.equal(sto.privileged_observations.cpu(), ref["critic"])
     assert torch.equal(sto.actions.cpu(), ref["actions"]) and torch.equal(sto.mu.cpu(), ref["mu"]) and torch.equal(sto.sigma.cpu(), ref["sigma"])
     assert torch.equal(sto.dones.cpu(), ref["dones"]) and torch.equal(sto.values.cpu(), ref["values"])
@@ -74,8 +75,9 @@ def test_split_normalisation_matches_single_shot(cuda_lib):
     assert torch.equal(one, sto.advantages)
 
 
-def test_minibatch_gather(cuda_lib):
-    sto, ref, g = _fill(cuda_lib, 24, 4096, seed=9)
+@pytest.mark.parametrize("od", [16, 17])
+def test_minibatch_gather(cuda_lib, od):
+    sto, ref, g = _fill(cuda_lib, 24, 4096, seed=9, od=od, cd=od)
     sto.compute_returns(torch.randn(4096, 1, generator=g).cuda(), 0.99, 0.95)
     B = 24 * 4096
     idx = torch.randperm(B, generator=g)
