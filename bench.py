@@ -449,6 +449,12 @@ def bench_extras(dev, cfg, table):
     out["ppo_collection"] = bench_collection(dev, cfg, table)
     out["bptt_training_c3"] = bench_bptt_training(dev, cfg, table)
     out["ppo_training_c2"] = bench_ppo_training(dev, cfg, table)
+    # ---- the reach-target tasks / LV command mode (tools/reach_bench.py)
+    from generalizableracing_b200.config import ReachTargetCfg
+    from tools.reach_bench import bench_step, bench_window
+    out["reach_target"] = {"step_lv_65536": bench_step(ReachTargetCfg.lv(decimation=1, is_differentiable_physics=False), 65536),
+                           "bptt_window_ctbr_16384x48": bench_window(ReachTargetCfg.ctbr()),
+                           "bptt_window_lv_16384x48": bench_window(ReachTargetCfg.lv(decimation=1))}
     return out
 
 

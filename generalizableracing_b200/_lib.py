@@ -184,6 +184,10 @@ PROTOTYPES = {
     "gr_reach_step_fwd": (C.c_int, [C.POINTER(GrReachConfig), C.POINTER(GrReachState), C.POINTER(GrRandom), C.POINTER(GrReachStepIO), c_p]),
     "gr_reach_step_bwd": (C.c_int, [C.POINTER(GrReachConfig), C.POINTER(GrReachState), C.POINTER(GrBwdIO), c_p]),
     "gr_reach_fill_rand": (C.c_int, [c_p, c_i, c_i, C.c_uint64, C.c_uint32, c_p]),
+    "gr_traj_index": (C.c_int, [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "gr_traj_pad": (C.c_int, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p]),
+    "gr_traj_unpad": (C.c_int, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "gr_traj_hidden": (C.c_int, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p]),
     "gr_host_pipe_create": (C.c_int, [c_i, c_i, c_p, C.POINTER(c_p)]),
     "gr_host_pipe_destroy": (C.c_int, [c_p]),
     "gr_host_pipe_step": (C.c_int, [c_p, C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom),

@@ -59,6 +59,8 @@ class PPO:
 
     def act(self, obs, critic_obs):
         # ppo.py:71-83
+        if self.policy.is_recurrent:
+            self.transition.hidden_states = self.policy.get_hidden_states()
         self.transition.actions = self.policy.act(obs).detach()
         self.transition.values = self.policy.evaluate(critic_obs).detach()
         self.transition.actions_log_prob = self.policy.get_actions_log_prob(self.transition.actions).detach()
@@ -325,17 +327,25 @@ class PPO:
 
     def update(self):
         # ppo.py:103-190
-        if self.graphed_update and (D.world()[1] == 1 or self.kernel_update) and getattr(self, "_eager_updates", 0) >= 1:
+        if self.graphed_update and not self.policy.is_recurrent and (D.world()[1] == 1 or self.kernel_update) and getattr(self, "_eager_updates", 0) >= 1:
             return self._update_graphed()
         self._eager_updates = getattr(self, "_eager_updates", 0) + 1
         mean_value_loss = torch.zeros((), device=self.device)
         mean_surrogate_loss = torch.zeros((), device=self.device)
-        generator = self.storage.mini_batch_generator(self.num_mini_batches, self.num_learning_epochs)
+        if self.policy.is_recurrent:             # ppo.py:106-109
+            generator = self.storage.reccurent_mini_batch_generator(self.num_mini_batches, self.num_learning_epochs)
+        else:
+            generator = self.storage.mini_batch_generator(self.num_mini_batches, self.num_learning_epochs)
         for (obs_batch, critic_obs_batch, actions_batch, target_values_batch, advantages_batch, returns_batch,
-             old_actions_log_prob_batch, old_mu_batch, old_sigma_batch, _hid, _masks) in generator:
-            self.policy.act(obs_batch)
-            actions_log_prob_batch = self.policy.get_actions_log_prob(actions_batch)
-            value_batch = self.policy.evaluate(critic_obs_batch)
+             old_actions_log_prob_batch, old_mu_batch, old_sigma_batch, hid_states_batch, masks_batch) in generator:
+            if self.policy.is_recurrent:
+                self.policy.act(obs_batch, masks=masks_batch, hidden_states=hid_states_batch[0])
+                actions_log_prob_batch = self.policy.get_actions_log_prob(actions_batch)
+                value_batch = self.policy.evaluate(critic_obs_batch, masks=masks_batch, hidden_states=hid_states_batch[1])
+            else:
+                self.policy.act(obs_batch)
+                actions_log_prob_batch = self.policy.get_actions_log_prob(actions_batch)
+                value_batch = self.policy.evaluate(critic_obs_batch)
             mu_batch = self.policy.action_mean
             sigma_batch = self.policy.action_std
             entropy_batch = self.policy.entropy

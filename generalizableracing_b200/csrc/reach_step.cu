@@ -88,7 +88,8 @@ __device__ __forceinline__ void reach_store(const ReachRegs& e, float4* __restri
   }
 }
 
-__device__ __forceinline__ float4 tanh4p(float4 a) { return make_float4(tanhf(a.x), tanhf(a.y), tanhf(a.z), tanhf(a.w)); }
+// tanh through ex2 + rcp (gr_math.cuh fm_tanh, |err| ~ 1e-7), as in racing_step_core.cuh
+__device__ __forceinline__ float4 tanh4p(float4 a) { return make_float4(fm_tanh(a.x), fm_tanh(a.y), fm_tanh(a.z), fm_tanh(a.w)); }
 
 // _reset_idx for one env (L/envs/manager_based_diff_rl_env.py:362-410): reset_root_state_uniform, ActionManager.reset,
 // controller / dynamics reset with the drag re-draw (droneDynamics.py:50-58), thr_est_error (diff_action.py:233), command resample.

@@ -94,3 +94,68 @@ class BaseModel(ActorCritic):
     def act(self, observations, **kwargs):
         self.update_distribution(observations)
         return self.distribution.rsample()
+
+
+class Memory(nn.Module):
+    """rsl_rl.modules.actor_critic_recurrent.Memory (third party rsl-rl-lib 2.x, restated): the recurrent core in front of
+    the MLPs.  Inference mode carries its own hidden state; batch mode (PPO update) runs whole padded trajectories from the
+    saved start states and un-pads the result (gr_traj_unpad)."""
+
+    def __init__(self, input_size, type="lstm", num_layers=1, hidden_size=256):
+        super().__init__()
+        rnn_cls = nn.GRU if type.lower() == "gru" else nn.LSTM
+        self.rnn = rnn_cls(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers)
+        self.hidden_states = None
+
+    def forward(self, input, masks=None, hidden_states=None):
+        if masks is not None:                                 # batch mode
+            if hidden_states is None:
+                raise ValueError("Hidden states not passed to memory module during policy update")
+            from .trajectories import unpad_trajectories
+            out, _ = self.rnn(input, hidden_states)
+            return unpad_trajectories(out, masks)
+        out, self.hidden_states = self.rnn(input.unsqueeze(0), self.hidden_states)
+        return out
+
+    def reset(self, dones=None, hidden_states=None):
+        if dones is None:
+            self.hidden_states = hidden_states
+        elif self.hidden_states is not None:
+            hs = self.hidden_states if isinstance(self.hidden_states, tuple) else (self.hidden_states,)
+            keep = (dones == 0).to(hs[0].dtype).view(1, -1, 1)
+            new = tuple(h * keep for h in hs)                  # zero the state of the envs that finished (no host sync, no in-place on saved states)
+            self.hidden_states = new if isinstance(self.hidden_states, tuple) else new[0]
+
+    def detach_hidden_states(self, dones=None):
+        if self.hidden_states is not None:
+            hs = self.hidden_states
+            self.hidden_states = tuple(h.detach() for h in hs) if isinstance(hs, tuple) else hs.detach()
+
+
+class ActorCriticRecurrent(ActorCritic):
+    """rsl_rl.modules.ActorCriticRecurrent (restated): Memory -> MLP for actor and critic."""
+    is_recurrent = True
+
+    def __init__(self, num_actor_obs, num_critic_obs, num_actions, actor_hidden_dims=(256, 256, 256), critic_hidden_dims=(256, 256, 256),
+                 activation="elu", rnn_type="lstm", rnn_hidden_dim=256, rnn_num_layers=1, init_noise_std=1.0, **kwargs):
+        if "rnn_hidden_size" in kwargs:
+            rnn_hidden_dim = kwargs.pop("rnn_hidden_size")
+        super().__init__(rnn_hidden_dim, rnn_hidden_dim, num_actions, actor_hidden_dims, critic_hidden_dims, activation, init_noise_std, **kwargs)
+        self.memory_a = Memory(num_actor_obs, type=rnn_type, num_layers=rnn_num_layers, hidden_size=rnn_hidden_dim)
+        self.memory_c = Memory(num_critic_obs, type=rnn_type, num_layers=rnn_num_layers, hidden_size=rnn_hidden_dim)
+
+    def reset(self, dones=None):
+        self.memory_a.reset(dones)
+        self.memory_c.reset(dones)
+
+    def act(self, observations, masks=None, hidden_states=None):
+        return super().act(self.memory_a(observations, masks, hidden_states).squeeze(0))
+
+    def act_inference(self, observations):
+        return super().act_inference(self.memory_a(observations).squeeze(0))
+
+    def evaluate(self, critic_observations, masks=None, hidden_states=None):
+        return super().evaluate(self.memory_c(critic_observations, masks, hidden_states).squeeze(0))
+
+    def get_hidden_states(self):
+        return self.memory_a.hidden_states, self.memory_c.hidden_states

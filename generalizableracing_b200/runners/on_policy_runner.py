@@ -32,8 +32,14 @@ class OnPolicyRunner:
         num_obs = obs.shape[1]
         self.privileged_obs_type = "critic" if "critic" in extras["observations"] else None
         num_privileged_obs = extras["observations"]["critic"].shape[1] if self.privileged_obs_type else num_obs
-        self.policy_cfg.pop("class_name", None)
-        policy = ActorCritic(num_obs, num_privileged_obs, self.env.num_actions, **self.policy_cfg).to(self.device)
+        policy_class = self.policy_cfg.pop("class_name", "ActorCritic")
+        if policy_class == "ActorCriticRecurrent":
+            from ..modules import ActorCriticRecurrent
+            policy = ActorCriticRecurrent(num_obs, num_privileged_obs, self.env.num_actions, **self.policy_cfg).to(self.device)
+        elif policy_class == "ActorCritic":
+            policy = ActorCritic(num_obs, num_privileged_obs, self.env.num_actions, **self.policy_cfg).to(self.device)
+        else:
+            raise ValueError(f"policy class {policy_class!r} is not built (vision / distillation policies are out of scope)")
         self.alg_cfg.pop("class_name", None)
         self.alg = PPO(policy, env=self.env, device=self.device, **self.alg_cfg)
         self.num_steps_per_env = self.cfg["num_steps_per_env"]

@@ -108,8 +108,7 @@ class RolloutStorage:
         ``r += gamma * V * time_out`` of PPO.process_env_step (ppo.py:89-92) is fused in."""
         if self.step >= self.num_transitions_per_env:
             raise AssertionError("Rollout buffer overflow")
-        if transition.hidden_states is not None and transition.hidden_states != (None, None):
-            raise NotImplementedError("recurrent hidden states are out of scope (SURVEY.md §8f rank 4)")
+        self._save_hidden_states(transition.hidden_states)
         tr = self._tr
         tr.critic_obs = None
         tr.time_outs = None
@@ -142,6 +141,20 @@ class RolloutStorage:
         if rc:
             B.check(rc, "gr_storage_add")
         self.step += 1
+
+    def _save_hidden_states(self, hidden_states):
+        # rollout_storage.py:90-108 (GRU states are wrapped into 1-tuples to match the LSTM format)
+        if hidden_states is None or hidden_states == (None, None):
+            return
+        hid_a = hidden_states[0] if isinstance(hidden_states[0], tuple) else (hidden_states[0],)
+        hid_c = hidden_states[1] if isinstance(hidden_states[1], tuple) else (hidden_states[1],)
+        if self.saved_hidden_states_a is None:
+            T = self.observations.shape[0]
+            self.saved_hidden_states_a = [torch.zeros(T, *hid_a[i].shape, device=self.device) for i in range(len(hid_a))]
+            self.saved_hidden_states_c = [torch.zeros(T, *hid_c[i].shape, device=self.device) for i in range(len(hid_c))]
+        for i in range(len(hid_a)):
+            self.saved_hidden_states_a[i][self.step].copy_(hid_a[i])
+            self.saved_hidden_states_c[i][self.step].copy_(hid_c[i])
 
     def clear(self):
         self.step = 0
@@ -197,4 +210,30 @@ class RolloutStorage:
                        out["mu"], out["sigma"], (None, None), None)
 
     def reccurent_mini_batch_generator(self, num_mini_batches, num_epochs=8):
-        raise NotImplementedError("recurrent mini-batches are out of scope this round (SURVEY.md §8f rank 4)")
+        """rollout_storage.py:194-254 (the reference's spelling).  One trajectory index per call (gr_traj_index: a count per
+        env, a scan, one fill), then per mini-batch one pad launch per observation group and one gather launch per saved
+        hidden-state tensor; the remaining fields are views of the storage, as in the reference."""
+        from .trajectories import TrajectoryIndex
+        if self.training_type != "rl":
+            raise ValueError("This function is only available for reinforcement learning training.")
+        mb = self.num_envs // num_mini_batches
+        idx = TrajectoryIndex(self.dones, lib=self._lib, boundaries=[i * mb for i in range(num_mini_batches + 1)])
+        bounds = idx.boundaries
+        for _ in range(num_epochs):
+            for i in range(num_mini_batches):
+                start, stop = i * mb, (i + 1) * mb
+                first, count = bounds[i], bounds[i + 1] - bounds[i]
+                obs_batch, masks_batch = idx.pad(self.observations, first, count)
+                if self.privileged_observations is not None:
+                    privileged_obs_batch = idx.pad(self.privileged_observations, first, count, want_masks=False)
+                else:
+                    privileged_obs_batch = obs_batch
+                hid_a_batch = [idx.hidden(h, first, count) for h in (self.saved_hidden_states_a or [])]
+                hid_c_batch = [idx.hidden(h, first, count) for h in (self.saved_hidden_states_c or [])]
+                hid_a_batch = hid_a_batch[0] if len(hid_a_batch) == 1 else hid_a_batch
+                hid_c_batch = hid_c_batch[0] if len(hid_c_batch) == 1 else hid_c_batch
+                yield (obs_batch, privileged_obs_batch, self.actions[:, start:stop], self.values[:, start:stop], self.advantages[:, start:stop],
+                       self.returns[:, start:stop], self.actions_log_prob[:, start:stop], self.mu[:, start:stop], self.sigma[:, start:stop],
+                       (hid_a_batch, hid_c_batch), masks_batch)
+
+    recurrent_mini_batch_generator = reccurent_mini_batch_generator

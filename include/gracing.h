@@ -478,6 +478,21 @@ int gr_reach_step_bwd(const GrReachConfig* cfg, const GrReachState* st, const Gr
 /* Dense random tensor [N, GR_REACH_RND_STRIDE] exactly as the in-kernel Philox path draws it. */
 int gr_reach_fill_rand(float* rnd, int32_t num_envs, int32_t env_id_offset, uint64_t seed, uint32_t step, void* stream);
 
+/* ---- recurrent mini-batches: RolloutStorage.reccurent_mini_batch_generator
+ * (S/rsl_rl/ext/storage/rollout_storage.py:194-254) = rsl_rl.utils.split_and_pad_trajectories (third party rsl-rl-lib 2.x;
+ * call sites :197-199) + the hidden-state gather at trajectory starts (:226-237); gr_traj_unpad = rsl_rl.utils.unpad_trajectories.
+ * Trajectories are the pieces of every env's [T] column between dones (the last step always closes one), ordered env-major. */
+/* dones [T,N] uint8 -> offsets [N+1] (trajectories of envs < n), and per trajectory (capacity T*N each): env, first step, length. */
+int gr_traj_index(const uint8_t* dones, int32_t T, int32_t N, int32_t* offsets, int32_t* traj_env, int32_t* traj_start, int32_t* traj_len, void* stream);
+/* src [T,N,D] -> padded [T,count,D] (zero padded) and masks [T,count] (optional) for trajectories [first, first+count). */
+int gr_traj_pad(const float* src, int32_t T, int32_t N, int32_t D, const int32_t* traj_env, const int32_t* traj_start, const int32_t* traj_len,
+                int32_t first, int32_t count, float* padded, uint8_t* masks, void* stream);
+/* padded [T,J,D] + masks [T,J] -> out [T,B,D] (B*T valid rows); scratch: 2*J+1 int32. */
+int gr_traj_unpad(const float* padded, const uint8_t* masks, int32_t T, int32_t J, int32_t D, int32_t B, int32_t* scratch, float* out, void* stream);
+/* saved hidden states [T,L,N,H] -> out [L,count,H]: the state each trajectory started from. */
+int gr_traj_hidden(const float* saved, int32_t T, int32_t L, int32_t N, int32_t H, const int32_t* traj_env, const int32_t* traj_start,
+                   int32_t first, int32_t count, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,55 +38,62 @@ def time_graph(fn, iters, warm=3):
     return e0.elapsed_time(e1) / iters
 
 
+def load_peak():
+    try:
+        return json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbps"]
+    except Exception:
+        return 6543.4
+
+
+def bench_step(cfg, N, R=12, iters=30):
+    """One gr_reach_step_fwd per env batch, R independent batches in rotation (R x 19 MB > L2): every step reads HBM."""
+    envs = [ReachTargetVecEnv(cfg, N, seed=s) for s in range(R)]
+    acts = [torch.randn(N, 4, device="cuda:0") * 0.4 for _ in range(R)]
+    for e in envs:
+        e.reset()
+
+    def sweep():
+        for e, x in zip(envs, acts):
+            e.step(x)
+    ms = time_graph(sweep, iters) / R
+    gbps = N * B_FWD / (ms * 1e-3) / 1e9
+    return {"us": ms * 1e3, "env_steps_per_s": N / (ms * 1e-3), "achieved_gbps": gbps, "frac": gbps / load_peak(), "bytes_per_env_step": B_FWD, "envs": N}
+
+
+def bench_window(cfg, Nb=16384, T=48, iters=20):
+    """BPTT window: T forward steps with tape + one reverse sweep (the reference's hover schedule: 48 steps)."""
+    env = ReachTargetVecEnv(cfg, Nb, bptt_horizon=T)
+    env._bptt.autograd = False
+    env.reset()
+    acts = [torch.randn(Nb, 4, device="cuda:0") * 0.4 for _ in range(T)]
+
+    def window():
+        env.detach()
+        for x in acts:
+            env.step(x)
+        env._bptt.backward_window()
+    ms = time_graph(window, iters)
+    ms_b = time_graph(lambda: env._bptt.backward_window(), iters)
+    return {"window_ms": ms, "sweep_us": ms_b * 1e3, "env_steps_per_s": Nb * T / (ms * 1e-3), "T": T, "envs": Nb,
+            "sweep_gbps": Nb * T * (13 * 16 + 16) / (ms_b * 1e-3) / 1e9}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=65536)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--only", default=None, help="lv | ps | ctbr: time only that step kernel (for ncu)")
     a = ap.parse_args()
-    peak = 6543.4
-    try:
-        peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbps"]
-    except Exception:
-        pass
-    out = {"envs": a.envs, "bytes_per_env_step": B_FWD, "peak_gbps": peak}
-    N = a.envs
+    out = {"envs": a.envs, "bytes_per_env_step": B_FWD, "peak_gbps": load_peak()}
     for name, cfg in (("lv", ReachTargetCfg.lv(decimation=1, is_differentiable_physics=False)),
                       ("ps", ReachTargetCfg.ps(decimation=1, is_differentiable_physics=False)),
                       ("ctbr", ReachTargetCfg.ctbr(is_differentiable_physics=False))):
-        R = 12                                     # rotate over 12 independent env batches (12 x 19 MB > L2)
-        envs = [ReachTargetVecEnv(cfg, N, seed=s) for s in range(R)]
-        acts = [torch.randn(N, 4, device="cuda:0") * 0.4 for _ in range(R)]
-        for e in envs:
-            e.reset()
-
-        def sweep():
-            for e, x in zip(envs, acts):
-                e.step(x)
-        ms = time_graph(sweep, 30) / R
-        out[f"step_{name}"] = {"us": ms * 1e3, "env_steps_per_s": N / (ms * 1e-3), "achieved_gbps": N * B_FWD / (ms * 1e-3) / 1e9,
-                               "frac": N * B_FWD / (ms * 1e-3) / 1e9 / peak}
+        if a.only and a.only != name:
+            continue
+        out[f"step_{name}"] = bench_step(cfg, a.envs)
         print(name, out[f"step_{name}"], flush=True)
-        del envs
-    # BPTT window: T forward steps with tape + one reverse sweep (the reference's hover schedule: 48 steps)
-    T, Nb = 48, 16384
-    for name, cfg in (("lv", ReachTargetCfg.lv(decimation=1)), ("ctbr", ReachTargetCfg.ctbr())):
-        env = ReachTargetVecEnv(cfg, Nb, bptt_horizon=T)
-        env._bptt.autograd = False
-        env.reset()
-        acts = [torch.randn(Nb, 4, device="cuda:0") * 0.4 for _ in range(T)]
-
-        def window():
-            env.detach()
-            for x in acts:
-                env.step(x)
-            env._bptt.backward_window()
-        ms = time_graph(window, 20)
-
-        def bwd_only():
-            env._bptt.backward_window()
-        ms_b = time_graph(bwd_only, 20)
-        out[f"bptt_{name}"] = {"window_ms": ms, "sweep_us": ms_b * 1e3, "env_steps_per_s": Nb * T / (ms * 1e-3), "T": T, "envs": Nb,
-                               "sweep_gbps": Nb * T * (13 * 16 + 16) / (ms_b * 1e-3) / 1e9}
+    for name, cfg in () if a.only else (("lv", ReachTargetCfg.lv(decimation=1)), ("ctbr", ReachTargetCfg.ctbr())):
+        out[f"bptt_{name}"] = bench_window(cfg)
         print("bptt", name, out[f"bptt_{name}"], flush=True)
     if a.json:
         json.dump(out, open(a.json, "w"), indent=1)
