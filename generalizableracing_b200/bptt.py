@@ -99,6 +99,10 @@ class BpttWindow:
     # -- reverse sweep -------------------------------------------------------------------------
     def _launch(self, t_begin: int, t_end: int, grad_loss, grad_scale: float):
         env = self.env
+        if getattr(env, "_ops", None) is not None:          # operator layer (ops.py): the same launch through torch.ops.gracing.step_bwd
+            torch.ops.gracing.step_bwd(env._op_handle, env.planes, self.tape, grad_loss, float(grad_scale), self.adjoint, self.grad_action,
+                                       t_begin, t_end)
+            return
         io = B.GrBwdIO()
         io.tape = self.tape.data_ptr()
         io.tape_stride = env._stride

@@ -116,7 +116,8 @@ class RacingVecEnv:
     def __init__(self, cfg: RacingCfg, table: GateTable, num_envs: int, device="cuda:0", seed: int = 42,
                  rng_mode: str = "philox", episode_stats: bool = True, env_id_offset: int = 0,
                  global_num_envs: Optional[int] = None, terrain_types: Optional[torch.Tensor] = None,
-                 startup_rnd: Optional[torch.Tensor] = None, bptt_horizon: int = 0, block_threads: int = 0, pdl: Optional[bool] = None, _lib=None):
+                 startup_rnd: Optional[torch.Tensor] = None, bptt_horizon: int = 0, block_threads: int = 0, pdl: Optional[bool] = None,
+                 op_layer: Optional[bool] = None, _lib=None):
         self.cfg = cfg
         self.table = table
         self.num_envs = N = int(num_envs)
@@ -193,6 +194,15 @@ class RacingVecEnv:
         self._pipe = None
         self._params_edited = False
         self._p_cfg, self._p_track, self._p_state = C.byref(self._gcfg), C.byref(self._track), C.byref(self._state)
+        # ---- operator layer (ops.py): step / reset / BPTT autograd through torch.ops.gracing.* instead of direct ctypes calls
+        if op_layer is None:
+            op_layer = os.environ.get("GRACING_OP_LAYER", "0") == "1"
+        self._op_handle = None
+        self._ops = None
+        if op_layer:
+            from . import ops
+            self._ops = ops
+            ops.register_env(self)
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -300,6 +310,8 @@ class RacingVecEnv:
     # ------------------------------------------------------------------ API
     def reset(self, rnd: Optional[torch.Tensor] = None):
         """ManagerBasedRLEnv.reset(): reset every env, return (obs, extras)."""
+        if self._ops is not None:
+            return self._reset_ops(rnd)
         o = self._outs[self._flip]
         self._flip ^= 1
         B.check(self._lib.gr_env_reset(C.byref(self._gcfg), C.byref(self._track), C.byref(self._state), C.byref(self._rand(rnd)), None,
@@ -338,6 +350,8 @@ class RacingVecEnv:
     def step(self, actions: torch.Tensor, rnd: Optional[torch.Tensor] = None):
         if self._needs_reset:
             self.reset()
+        if self._ops is not None:
+            return self._step_ops(actions, rnd)
         k = self._flip
         o = self._outs[k]
         self._flip = k ^ 1
@@ -374,6 +388,61 @@ class RacingVecEnv:
             self._bptt.after_step(actions, ex)
         return o["obs"], o["reward"], o["dones"], ex
 
+    # ------------------------------------------------------------------ the same two calls through torch.ops.gracing.* (ops.py)
+    def _rnd_step(self, rnd):
+        if rnd is not None:
+            rnd = rnd.to(self.device, torch.float32).contiguous()
+        elif self.rng_mode == "dense":
+            raise ValueError("rng_mode='dense' needs an explicit rnd tensor every call")
+        step = self._step_count & 0xFFFFFFFF
+        self._step_count += 1
+        return rnd, step
+
+    def _reset_ops(self, rnd):
+        rnd, step = self._rnd_step(rnd)
+        obs, critic, aux = torch.ops.gracing.reset(self._op_handle, self.planes, None, rnd, step)
+        self._last = o = dict(obs=obs, critic=critic, aux=aux)
+        self._needs_reset = False
+        if self._bptt is not None:
+            self._bptt.start_window()
+        self.extras["observations"] = self._obs_dict(o)
+        return obs, self.extras
+
+    def _step_ops(self, actions, rnd):
+        win = self._bptt
+        act = actions.detach()
+        if act.dtype != torch.float32 or not act.is_contiguous() or act.device != self.device:
+            act = act.to(self.device, torch.float32).contiguous()
+        rnd, step = self._rnd_step(rnd)
+        export = bool(self.export_reward_terms or self.export_gate_passed)
+        if win is None:
+            out = torch.ops.gracing.step_fwd(self._op_handle, self.planes, act, rnd, step, self._log_accum, export)
+        else:
+            out = torch.ops.gracing.step_fwd_tape(self._op_handle, self.planes, act, rnd, step, self._log_accum, win.tape, win.t, export)
+        obs, critic, aux, reward, terminated, time_out, dones, terms, passed = out[:9]
+        if self._params_edited:
+            self._state.launch_flags = self._launch_flags
+            self._params_edited = False
+        self._last = o = dict(obs=obs, critic=critic, aux=aux, reward=reward, terminated=terminated, time_out=time_out, dones=dones,
+                              reward_terms=terms, gate_passed=passed)
+        ex = self.extras
+        dict.pop(ex, "log", None)
+        ex["observations"] = self._obs_dict(o)
+        ex["time_outs"] = time_out.view(torch.bool)
+        ex["terminated"] = terminated.view(torch.bool)
+        if win is not None:
+            loss, loss_terms = out[9:]
+            win.loss[win.t].copy_(loss)
+            win.loss_terms[win.t].copy_(loss_terms)
+            if win.autograd and actions.requires_grad:
+                if win._token is None:
+                    win._token = torch.zeros(1, device=self.device, requires_grad=True)
+                loss, win._token = torch.ops.gracing.step_loss(self._op_handle, actions, win._token, loss, win.t, win.epoch)
+            win.t += 1
+            ex["losses"] = loss
+            ex["losses_detached"] = win.losses_detached
+            ex["loss_terms"] = loss_terms
+        return obs, reward, dones, ex
 
     # ------------------------------------------------------------------ host-buffer API (gr_host_pipe_*, include/gracing.h)
     def step_host(self, actions: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, dones: Optional[torch.Tensor] = None,
