@@ -253,6 +253,39 @@ def run_ours(args):
         low = {"kernel_us": us, "env_steps_per_s_per_gpu": N / (us * 1e-6), "frac_of_hbm_peak": b_alg * N / (us * 1e-6) / 1e9 / peak,
                "resets_per_env_step": rr, "actions": "N((-0.35,0,0,0), 0.1^2): near hover"}
 
+    # ---- forced reset rates ("also report a forced 1 % and 10 % reset-rate case for C4"): the same launches re-captured
+    # with max_episode_length = 100 / 10 and staggered episode counters, so 1 % / 10 % of the envs time out (and run the reset
+    # tail: curriculum, pose / velocity / drag / noise re-draws) every step, on top of the near-hover crash rate
+    forced = {}
+    if not args.no_extra:
+        for label, max_len in (("1pct", 100), ("10pct", 10)):
+            for e in envs:
+                e._gcfg.max_episode_length = max_len
+                e.episode_length_buf = torch.randint(0, max_len, (N,), device=dev, dtype=torch.int32)
+            torch.cuda.synchronize(dev)
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                one_round(30_000)
+            for _ in range(40):
+                g2.replay()
+            for e in envs:
+                e._log_accum.zero_()
+            torch.cuda.synchronize(dev)
+            ev0.record()
+            for _ in range(rounds):
+                g2.replay()
+            ev1.record()
+            torch.cuda.synchronize(dev)
+            us = ev0.elapsed_time(ev1) * 1e3 / K
+            rr = float(torch.stack([e._log_accum.sum(dim=0) for e in envs]).sum(dim=0)[0].item()) / (rounds * R * N)
+            forced[label] = {"kernel_us": us, "env_steps_per_s_per_gpu": N / (us * 1e-6), "frac_of_hbm_peak": b_alg * N / (us * 1e-6) / 1e9 / peak,
+                             "resets_per_env_step": rr, "max_episode_length": max_len}
+            del g2
+        for e in envs:
+            e._gcfg.max_episode_length = cfg.max_episode_length
+            e.episode_length_buf = torch.randint(0, cfg.max_episode_length, (N,), device=dev, dtype=torch.int32)
+        torch.cuda.synchronize(dev)
+
     # ---- e2e: public API with HOST buffers (RacingVecEnv.step_host -> gr_host_pipe_*), H2D + D2H inside the timed region.
     # Every step copies its own actions host->device and its obs / reward / dones device->host; `depth` steps are in flight
     # so the copies of step t overlap the kernel of step t+1 (the consumer reads step t's results while t+1 runs).
@@ -305,6 +338,7 @@ def run_ours(args):
         extra = bench_extras(dev, cfg, table)
     if rank == 0 and low is not None:
         extra["fwd_low_reset"] = low
+        extra["fwd_forced_reset_rate"] = forced
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

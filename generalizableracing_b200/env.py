@@ -329,6 +329,10 @@ class RacingVecEnv:
         if self._needs_reset:
             self.reset()
         o = self._last
+        if self._ops is not None and o["obs"].is_inference() and not torch.is_inference_mode_enabled():
+            # operator outputs allocated under the runner's torch.inference_mode() (on_policy_runner.py:141): hand normal tensors
+            # to a caller outside it, as the reference's recomputed observations are
+            o.update({k: o[k].clone() for k in ("obs", "critic", "aux")})
         return o["obs"], {"observations": self._obs_dict(o)}
 
     def detach(self):

@@ -74,6 +74,12 @@ def test_step_and_reset_bit_identical_to_direct_path(backend, monkeypatch):
     assert resets > 0
     assert torch.equal(a.planes, b.planes) and torch.equal(a._log_accum, b._log_accum)
     assert torch.equal(a.get_observations()[0], b.get_observations()[0])
+    with torch.inference_mode():                       # the rollout loop of OnPolicyRunner.learn (on_policy_runner.py:141)
+        b.step(act, r)
+    obs = b.get_observations()[0]                      # outside it the observations must be usable under autograd again
+    lin = torch.nn.Linear(L.OBS_DIM, 4).to(dev)
+    lin(obs).sum().backward()
+    assert lin.weight.grad is not None
 
 
 @pytest.mark.parametrize("backend", backend_params(), indirect=True)
