@@ -24,7 +24,10 @@ class BPTT:
         self.actor_critic = actor_critic
         self.actor_critic.to(self.device)
         D.broadcast_module(self.actor_critic)
-        self.optimizer = eval(optimizer)(self.actor_critic.parameters(), lr=self.learning_rate)
+        # algo.py:44 builds `eval(optimizer)(params, lr=lr)`; on CUDA the Adam family / SGD run as torch's single-kernel ("fused")
+        # implementation of the same update: one launch instead of ~8 element-wise ones in an iteration that lasts < 1 ms
+        opt_kw = {"fused": True} if (optimizer in ("Adam", "AdamW", "SGD") and torch.device(self.device).type == "cuda") else {}
+        self.optimizer = eval(optimizer)(self.actor_critic.parameters(), lr=self.learning_rate, **opt_kw)
         self.schedule = eval(schedule)(self.optimizer, max_iterations, self.learning_rate * 0.01)
         self.env = env                      # RacingVecEnv: enables the one-launch window sweep
         self.losses, self.losses_detached, self.dones, self.rewards, self.actions = [], [], [], [], []

@@ -4,7 +4,6 @@ from __future__ import annotations
 
 import json
 import os
-import time
 
 import torch
 
@@ -58,39 +57,51 @@ class AlgoRunner:
         self.train_mode()
         N = self.env.num_envs
         start_iter = self.current_learning_iteration
+        # Timing comes from CUDA events and the log record of an iteration is resolved when the log is flushed (every
+        # ``log_interval`` iterations, default 1 = the reference's per-iteration logging, runner.py:157-191): with an interval > 1 the
+        # loop has no host synchronisation, so the host enqueues iteration i+1 while the GPU still runs iteration i.
+        log_interval = max(1, int(self.cfg.get("log_interval", 1)))
+        last_iter = start_iter + num_learning_iterations - 1
+        pending = []
         for it in range(start_iter, start_iter + num_learning_iterations):
-            start = time.time()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
             self.env.unwrapped.detach()                                            # runner.py:110
             rew_sum = torch.zeros((), device=self.device)
             if self.collector is not None:
                 self.collector.pack()
                 obs, critic_obs = self.collector.collect()
                 rew_sum = self.collector.rewards.mean() * self.num_steps_per_env
-                torch.cuda.synchronize(self.device)
             for _ in range(self.num_steps_per_env if self.collector is None else 0):
                 actions = self.alg.act(obs, critic_obs)
                 obs, rewards, dones, extras = self.env.step(actions)
                 critic_obs = extras["observations"].get("critic", obs)
                 self.alg.process_env_step(extras["losses"], extras["losses_detached"], dones, rewards, extras)
                 rew_sum += rewards.mean()
-            stop = time.time()
-            collection_time = stop - start
-            start = stop
+            ev[1].record()
             _, total_loss_mean = self.alg.update() if self.collector is None else self.alg.update_fused(self.collector)
-            torch.cuda.synchronize(self.device)                # the update is asynchronous: time it, not its enqueue
-            stop = time.time()
-            learn_time = stop - start
+            ev[2].record()
             self.current_learning_iteration = it
             self.tot_timesteps += self.num_steps_per_env * N * world
-            self.tot_time += collection_time + learn_time
             stats = torch.stack([total_loss_mean.detach(), rew_sum / self.num_steps_per_env])
             if world > 1:
                 torch.distributed.all_reduce(stats)
                 stats /= world
-            rec = {"iteration": it, "Loss/mean_total_loss": float(stats[0]), "Train/mean_step_reward": float(stats[1]),
-                   "Perf/total_fps": int(self.num_steps_per_env * N * world / (collection_time + learn_time)),
-                   "Perf/collection time": collection_time, "Perf/learning_time": learn_time,
-                   "Loss/learning_rate": self.alg.optimizer.param_groups[0]["lr"]}
+            pending.append((it, ev, stats, self.alg.optimizer.param_groups[0]["lr"]))
+            if len(pending) >= log_interval or it == last_iter:
+                self._flush_log(pending, N * world, rank)
+                pending = []
+        return self.history
+
+    def _flush_log(self, pending, n_global: int, rank: int):
+        pending[-1][1][2].synchronize()                        # the one host wait per flush
+        vals = torch.stack([p[2] for p in pending]).tolist()
+        for (it, ev, _, lr), v in zip(pending, vals):
+            collection_time, learn_time = ev[0].elapsed_time(ev[1]) * 1e-3, ev[1].elapsed_time(ev[2]) * 1e-3
+            self.tot_time += collection_time + learn_time
+            rec = {"iteration": it, "Loss/mean_total_loss": v[0], "Train/mean_step_reward": v[1],
+                   "Perf/total_fps": int(self.num_steps_per_env * n_global / max(collection_time + learn_time, 1e-9)),
+                   "Perf/collection time": collection_time, "Perf/learning_time": learn_time, "Loss/learning_rate": lr}
             self.history.append(rec)
             if rank == 0 and self.log_dir is not None:
                 os.makedirs(self.log_dir, exist_ok=True)
@@ -98,7 +109,6 @@ class AlgoRunner:
                     f.write(json.dumps(rec) + "\n")
                 if it % self.save_interval == 0:
                     self.save(os.path.join(self.log_dir, f"model_{it}.pt"))
-        return self.history
 
     def save(self, path, infos=None):
         torch.save({"model_state_dict": self.alg.actor_critic.state_dict(), "optimizer_state_dict": self.alg.optimizer.state_dict(),

@@ -8,7 +8,6 @@ from __future__ import annotations
 
 import json
 import os
-import time
 from collections import deque
 
 import torch
@@ -82,7 +81,8 @@ class OnPolicyRunner:
         start_iter = self.current_learning_iteration
         tot_iter = start_iter + num_learning_iterations
         for it in range(start_iter, tot_iter):
-            start = time.time()
+            ev_start, ev_mid, ev_end = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            ev_start.record()
             ep_infos = []
             with torch.inference_mode():
                 if self.collector is not None:
@@ -107,15 +107,14 @@ class OnPolicyRunner:
                     cur_episode_length.masked_fill_(d, 0.0)
                 if self.log_dir is not None and "log" in infos:
                     ep_infos.append(infos["log"])
-                if self.collector is not None:
-                    torch.cuda.synchronize(self.device)        # the fused rollout is one asynchronous launch: time it, not its enqueue
-                stop = time.time()
-                collection_time = stop - start
-                start = stop
+                ev_mid.record()
                 self.alg.compute_returns(privileged_obs, last_values=None if self.collector is None else last_values)
-            loss_dict = self.alg.update()
-            stop = time.time()
-            learn_time = stop - start
+            loss_dict = self.alg.update()                      # ends with the iteration's host read (loss sums / learning rate)
+            ev_end.record()
+            ev_end.synchronize()
+            # device-side timing: no host wait between the rollout and the update, so the host enqueues the update's launches
+            # while the (one-launch, asynchronous) fused rollout still runs
+            collection_time, learn_time = ev_start.elapsed_time(ev_mid) * 1e-3, ev_mid.elapsed_time(ev_end) * 1e-3
             self.current_learning_iteration = it
             self.tot_timesteps += self.num_steps_per_env * N * world
             self.tot_time += collection_time + learn_time
