@@ -100,20 +100,19 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// Draws of the rare paths (reset: calls 2..8, gate pass: calls 10..11).  With GR_LAUNCH_SPEC the step kernel (Philox mode,
-// programmatic dependent launch) generates the seven reset calls for every env BEFORE the grid-dependency wait -- in the
-// shadow of the previous kernel's tail, where the block has nothing else to do -- and parks them in shared memory (each
-// thread reads back only its own slots: no barrier), so the divergent reset tail of the stragglers that set the kernel's
-// makespan only reads them back.  The values are the same Philox outputs either way.  Dense mode, the gate-pass draws and
-// the standalone reset kernel read / generate on demand.
-constexpr int kSpecFirst = 2, kSpecCalls = 7;
+// Draws of the rare paths (reset: calls 2..8, gate pass: calls 10..11).  In Philox mode the step kernel generates
+// them speculatively for every env while its state loads are in flight (the warp would idle otherwise) and parks
+// them in shared memory, so the divergent reset / pass tails -- the stragglers that set the kernel's makespan -- only
+// read them back.  Dense mode and the standalone reset kernel read / generate directly.
+__device__ __forceinline__ int spec_slot(int call) { return call < 10 ? call - 2 : call - 3; }     // 2..8 -> 0..6, 10..11 -> 7..8
+constexpr int kSpecCalls = 9;
 
 template <bool kPhilox>
 struct Draws {
   const RandSrc<kPhilox>& rs;
   const float4* spec;       // shared: [kSpecCalls][blockDim.x] or nullptr
   __device__ __forceinline__ float4 get4(int call) const {
-    if (kPhilox && spec && call < kSpecFirst + kSpecCalls) return spec[(call - kSpecFirst) * blockDim.x + threadIdx.x];
+    if (kPhilox && spec) return spec[spec_slot(call) * blockDim.x + threadIdx.x];
     return rs.get4(call);
   }
 };

@@ -41,16 +41,7 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
   // them through L2 after the wait.  (Host-side edits of those planes must clear GR_LAUNCH_PREFETCH for the next step.)
   const bool prefetch = pdl && (st.launch_flags & GR_LAUNCH_PREFETCH) != 0;
   if (prefetch) { load_cold<false>(e, tile); load_noise<kNoise, false>(e, tile); }
-  // GR_LAUNCH_SPEC: the reset tail's seven Philox calls, generated here -- before the grid dependency -- and parked in the
-  // first kSpecCalls * blockDim.x float4 of the dynamic shared memory (gr_common.cuh, Draws)
-  const bool spec_on = kPhilox && (st.launch_flags & GR_LAUNCH_SPEC) != 0;
-  float4* const spec = spec_on ? smem_rows : nullptr;
-  if (spec_on) {
-#pragma unroll
-    for (int c = 0; c < kSpecCalls; ++c) spec[c * blockDim.x + threadIdx.x] = rs.get4(kSpecFirst + c);
-  }
-  const TrackSmem tr = stage_track(track, reinterpret_cast<const int2*>(st.chunk_types), st.num_envs,
-                                   smem_rows + (spec_on ? kSpecCalls * blockDim.x : 0));
+  const TrackSmem tr = stage_track(track, reinterpret_cast<const int2*>(st.chunk_types), st.num_envs, smem_rows);
   if (pdl) {
     pdl_wait();
     GR_STAMP(1);
@@ -67,9 +58,9 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
       load_noise<kNoise, false>(e, tile);
     }
   }
-  // (measured: generating the rare-path draws speculatively for every env while the loads are in flight -- AFTER the wait --
-  //  costs more than it saves: +1.2 us median compute, stragglers unchanged)
-  const Draws<kPhilox> draws{rs, spec};
+  // (measured: generating the rare-path draws speculatively for every env while the loads are in flight costs more
+  //  than it saves -- +1.2 us median compute, stragglers unchanged -- so the reset / pass tails draw on demand)
+  const Draws<kPhilox> draws{rs, nullptr};
   pdl_launch_dependents();
   // a warp that is entirely past the last env leaves; in the (single) ragged warp the inactive lanes keep shadowing
   // the last env so the warp collectives below stay full-width, and skip every store
@@ -271,10 +262,10 @@ static int prepare_smem(K kernel, size_t bytes) {
 template <bool kNoise, bool kDiff, bool kPhilox, bool kStats>
 static int launch_step(const GrConfig* cfg, const GrTrack* tr, const GrState* st, const GrRandom* rng, const GrStepIO* io, cudaStream_t s) {
   auto kernel = racing_step_fwd_kernel<kNoise, kDiff, kPhilox, kStats>;
-  const int kBlock = block_threads(st);
-  const size_t bytes = track_smem_bytes(tr, st) + ((kPhilox && (st->launch_flags & GR_LAUNCH_SPEC)) ? (size_t)kSpecCalls * kBlock * sizeof(float4) : 0);
+  const size_t bytes = track_smem_bytes(tr, st);
   int rc = prepare_smem(kernel, bytes);
   if (rc != GR_OK) return rc;
+  const int kBlock = block_threads(st);
   const int grid = (st->num_envs + kBlock - 1) / kBlock;
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3((unsigned)grid);

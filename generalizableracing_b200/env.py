@@ -156,8 +156,6 @@ class RacingVecEnv:
         if pdl is None:
             pdl = os.environ.get("GRACING_PDL", "1") != "0"
         flags = (B.GR_LAUNCH_PDL | (B.GR_LAUNCH_PREFETCH if os.environ.get("GRACING_PREFETCH", "1") != "0" else 0)) if (pdl and self.device.type == "cuda") else 0
-        if os.environ.get("GRACING_SPEC", "0") == "1" and rng_mode == "philox":
-            flags |= B.GR_LAUNCH_SPEC          # reset draws generated before the grid dependency (racing_step.cu)
         self._launch_flags = flags
         self._state = B.GrState(self.planes.data_ptr(), self._stride, N, self.num_planes, int(env_id_offset), max(spans),
                                 int(block_threads), flags, self._chunk_types.data_ptr())

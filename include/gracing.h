@@ -122,9 +122,6 @@ typedef struct GrState {
 #define GR_LAUNCH_PREFETCH 2   /* with GR_LAUNCH_PDL: fetch the read-mostly planes before the grid dependency (see racing_step.cu);
                                  clear it for the first step after the HOST rewrote planes 9..15 of the state */
 
-#define GR_LAUNCH_SPEC 4   /* gr_step_fwd in Philox mode: generate the reset tail's seven Philox calls for every env before the grid
-                             dependency and park them in shared memory (+ 7 * block_threads * 16 B per block); same values */
-
 /* Random source: dense tensor (parity mode) or in-kernel Philox4x32-10 (throughput mode). */
 typedef struct GrRandom {
   const float* rnd;         /* [num_envs, GR_RND_STRIDE] or NULL => Philox */

@@ -83,36 +83,3 @@ def test_philox_mode_equals_dense_mode(backend):
             assert torch.equal(x.cpu(), y.cpu())
         assert torch.equal(ra[3]["observations"]["critic"].cpu(), rb[3]["observations"]["critic"].cpu())
     assert torch.equal(ea.planes.cpu(), eb.planes.cpu())
-
-
-@pytest.mark.parametrize("backend", backend_params(), indirect=True)
-@pytest.mark.parametrize("stage", [1, 0])
-def test_speculative_reset_draws_are_the_same_draws(backend, stage, monkeypatch):
-    """GR_LAUNCH_SPEC moves the reset tail's seven Philox calls in front of the grid dependency (parked in shared memory):
-    same counters, same values -- every state plane, output and log accumulator stays bit-identical over resets."""
-    from generalizableracing_b200 import _lib as B
-    from generalizableracing_b200.config import RacingCfg
-    from generalizableracing_b200.env import RacingVecEnv
-    from generalizableracing_b200.tracks import figure_eight_track, synthetic_track_table
-    device, lib = backend
-    N = 333
-    cfg, table = RacingCfg.for_stage(stage), (synthetic_track_table() if stage else figure_eight_track())
-    envs = []
-    for spec in ("0", "1"):
-        monkeypatch.setenv("GRACING_SPEC", spec)
-        e = RacingVecEnv(cfg, table, N, device=device, seed=11, env_id_offset=512, _lib=lib)
-        assert bool(e._launch_flags & B.GR_LAUNCH_SPEC) == (spec == "1")
-        e.reset()
-        e.episode_length_buf = torch.arange(N, dtype=torch.int32) % cfg.max_episode_length        # time-outs from the first step on
-        envs.append(e)
-    g = torch.Generator().manual_seed(1)
-    resets = 0
-    for t in range(90):
-        a = (torch.randn(N, 4, generator=g) * 0.6).to(device)
-        xa, xb = envs[0].step(a), envs[1].step(a)
-        for k in range(3):
-            assert torch.equal(xa[k], xb[k]), (t, k)
-        assert torch.equal(xa[3]["observations"]["critic"], xb[3]["observations"]["critic"])
-        resets += int(xa[2].sum())
-    assert resets > 50
-    assert torch.equal(envs[0].planes, envs[1].planes) and torch.equal(envs[0]._log_accum, envs[1]._log_accum)
