@@ -376,6 +376,7 @@ def run_ours(args):
         if "bptt_fwd_bwd_c3" in extra:          # the second half of BASELINE's metric ("fwd, and fwd+bwd BPTT"), C3 = 16,384 envs x 32
             line["fwd_bwd_bptt"] = {"unit": UNIT, "config": "C3: 16384 envs, horizon 32",
                                     "dynamics_only": extra["bptt_fwd_bwd_c3"]["env_steps_per_s"],
+                                    "dynamics_only_one_launch_window": extra.get("bptt_fwd_bwd_c3_one_launch_window", {}).get("env_steps_per_s"),
                                     "training_iteration_with_policy": extra.get("bptt_training_c3", {}).get("fused_kernel_backward", {}).get("env_steps_per_s"),
                                     "training_iteration_with_policy_log_every_20": extra.get("bptt_training_c3", {}).get("fused_kernel_backward_log_every_20", {}).get("env_steps_per_s")}
         print(json.dumps(line))
@@ -437,6 +438,44 @@ def bench_extras(dev, cfg, table):
                               "ms_per_window_python_driven": ms_py, "bytes_per_env_step": b_fb,
                               "achieved_GBps": b_fb * N * H / (ms_g * 1e-3) / 1e9, "frac_of_hbm_peak": b_fb * N * H / (ms_g * 1e-3) / 1e9 / peak,
                               "l2": f"rotating {R} env sets + tapes ({R}x59 MB), one CUDA graph of {R} windows x (32 fwd + memsets + 1 sweep)"}
+    # ---- the same window as ONE forward launch (gr_rollout_fwd: the actions of a dynamics-only window are known in advance, so
+    # the env state stays in registers over the horizon) + the same reverse sweep; results bit-identical (tests/test_rollout_window.py)
+    def window1(e):
+        e.detach()
+        e.rollout(acts)
+        return e._bptt.backward_window()
+
+    for e in envs:
+        window1(e)
+    torch.cuda.synchronize(dev)
+    graph1 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph1):
+        for e in envs:
+            window1(e)
+    graph1.replay()
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(reps):
+        graph1.replay()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_w = e0.elapsed_time(e1) / (reps * R)
+    e0.record()
+    for _ in range(reps):
+        for e in envs:
+            e.detach()
+            e.rollout(acts)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_wf = e0.elapsed_time(e1) / (reps * R)
+    # bytes per env-step: action 16 + tape 112 + loss 4 + loss terms 12 + reward 4 + 3 masks written, state + observations once per
+    # window ((240 + 112 + 128) / H); sweep 112 + 16
+    b_w = 16 + 112 + 4 + 12 + 4 + 3 + (240 + 112 + 128) / H + 112 + 16
+    out["bptt_fwd_bwd_c3_one_launch_window"] = {
+        "envs": N, "horizon": H, "env_steps_per_s": N * H / (ms_w * 1e-3), "ms_per_window_graph": ms_w, "ms_forward_window_python_driven": ms_wf,
+        "bytes_per_env_step": b_w, "achieved_GBps": b_w * N * H / (ms_w * 1e-3) / 1e9, "frac_of_hbm_peak": b_w * N * H / (ms_w * 1e-3) / 1e9 / peak,
+        "what": "gr_rollout_fwd (32 steps, one launch, state in registers) + gr_step_bwd; same rotation of 4 env sets + tapes"}
+    del graph1
     e0.record()
     for _ in range(reps):
         for e in envs:

@@ -59,6 +59,12 @@ class GrBwdIO(C.Structure):
                 ("grad_scale", c_f), ("adjoint", c_p), ("adj_stride", C.c_int64), ("grad_action", c_p)]
 
 
+class GrRolloutIO(C.Structure):
+    _fields_ = [("actions", c_p), ("obs_out", c_p), ("critic_obs_out", c_p), ("aux_out", c_p), ("obs_seq", c_p), ("reward", c_p), ("dones", c_p),
+                ("terminated", c_p), ("time_out", c_p), ("loss", c_p), ("loss_terms", c_p), ("tape", c_p), ("tape_stride", C.c_int64),
+                ("log_accum", c_p), ("T", c_i)]
+
+
 class GrTransition(C.Structure):
     _fields_ = [("obs", c_p), ("critic_obs", c_p), ("actions", c_p), ("rewards", c_p), ("dones", c_p), ("dones_is_int64", c_i),
                 ("values", c_p), ("log_prob", c_p), ("mu", c_p), ("sigma", c_p), ("time_outs", c_p), ("gamma", c_f)]
@@ -161,6 +167,7 @@ PROTOTYPES = {
     "gr_env_observe": (C.c_int, [C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom), c_p, c_p, c_p, c_p]),
     "gr_step_fwd": (C.c_int, [C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom), C.POINTER(GrStepIO), c_p]),
     "gr_step_bwd": (C.c_int, [C.POINTER(GrConfig), C.POINTER(GrState), C.POINTER(GrBwdIO), c_p]),
+    "gr_rollout_fwd": (C.c_int, [C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom), C.POINTER(GrRolloutIO), c_p]),
     "gr_fill_rand": (C.c_int, [c_p, c_i, c_i, C.c_uint64, C.c_uint32, c_p]),
     "gr_fill_startup_rand": (C.c_int, [c_p, c_i, c_i, C.c_uint64, c_p]),
     "gr_storage_add": (C.c_int, [C.POINTER(GrStorage), C.POINTER(GrTransition), c_i, c_p]),

@@ -8,10 +8,14 @@ tape of the dynamics.  Here the env keeps a tape in HBM and one launch of gr_ste
 from __future__ import annotations
 
 import torch
-from torch.optim import SGD, Adam, Adamax, AdamW, RMSprop  # noqa: F401  (selected by name, algo.py:44)
-from torch.optim.lr_scheduler import CosineAnnealingLR, ExponentialLR, StepLR  # noqa: F401
+from torch.optim import SGD, Adam, Adamax, AdamW, RMSprop
+from torch.optim.lr_scheduler import CosineAnnealingLR, ExponentialLR, StepLR
 
 from .. import dist_utils as D
+
+# algo.py:44-46 selects both by name with eval(); the same names, looked up instead of evaluated
+_OPTIMIZERS = {"SGD": SGD, "Adam": Adam, "Adamax": Adamax, "AdamW": AdamW, "RMSprop": RMSprop}
+_SCHEDULES = {"CosineAnnealingLR": CosineAnnealingLR, "ExponentialLR": ExponentialLR, "StepLR": StepLR}
 
 
 class BPTT:
@@ -24,11 +28,11 @@ class BPTT:
         self.actor_critic = actor_critic
         self.actor_critic.to(self.device)
         D.broadcast_module(self.actor_critic)
-        # algo.py:44 builds `eval(optimizer)(params, lr=lr)`; on CUDA the Adam family / SGD run as torch's single-kernel ("fused")
+        # algo.py:44 builds `<optimizer>(params, lr=lr)`; on CUDA the Adam family / SGD run as torch's single-kernel ("fused")
         # implementation of the same update: one launch instead of ~8 element-wise ones in an iteration that lasts < 1 ms
         opt_kw = {"fused": True} if (optimizer in ("Adam", "AdamW", "SGD") and torch.device(self.device).type == "cuda") else {}
-        self.optimizer = eval(optimizer)(self.actor_critic.parameters(), lr=self.learning_rate, **opt_kw)
-        self.schedule = eval(schedule)(self.optimizer, max_iterations, self.learning_rate * 0.01)
+        self.optimizer = _OPTIMIZERS[optimizer](self.actor_critic.parameters(), lr=self.learning_rate, **opt_kw)
+        self.schedule = _SCHEDULES[schedule](self.optimizer, max_iterations, self.learning_rate * 0.01)
         self.env = env                      # RacingVecEnv: enables the one-launch window sweep
         self.losses, self.losses_detached, self.dones, self.rewards, self.actions = [], [], [], [], []
 

@@ -96,6 +96,96 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
 }
 
 // =============================================================================================
+// T steps in one launch for actions known in advance (gr_rollout_fwd): the same body, the env state in registers over
+// the window.  One thread per env; per step it reads its action (16 B) and writes what the caller asked to record.
+// =============================================================================================
+struct RolloutObsSink {
+  GlobalObsSink g;                                     // rows(): the coalesced warp store through shared memory
+  float4* seq_rows; float4* out_rows; float4* critic_rows; float* aux_ptr;        // destinations of THIS step (nullptr: skip)
+  __device__ __forceinline__ void policy(int i, float4 o0, float4 o1, float4 o2, float4 o3) const {
+    if (seq_rows) g.rows(seq_rows, i, o0, o1, o2, o3);
+    if (out_rows) g.rows(out_rows, i, o0, o1, o2, o3);
+  }
+  __device__ __forceinline__ bool wants_critic() const { return critic_rows != nullptr; }
+  __device__ __forceinline__ void critic(int i, float4 c0, float4 c1, float4 c2, float4 c3) const { g.rows(critic_rows, i, c0, c1, c2, c3); }
+  __device__ __forceinline__ void aux(int i, float v) const { if (aux_ptr) aux_ptr[i] = v; }
+};
+
+template <bool kNoise, bool kDiff, bool kPhilox, bool kStats>
+__global__ void __launch_bounds__(256) racing_rollout_fwd_kernel(const GrConfig cfg, const GrTrack track, const GrState st,
+                                                                 const GrRandom rng, const GrRolloutIO rio) {
+  GR_DYN_SMEM(float4, smem_rows);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = st.num_envs, T = rio.T;
+  const bool active = i < N;
+  const int li = active ? i : N - 1;
+  float4* __restrict__ tile = tile_ptr(reinterpret_cast<float4*>(st.planes), li);
+  EnvRegs e;
+  load_env<kNoise>(e, tile);
+  float4 eps0 = make_float4(0.f, 0.f, 0.f, 0.f), eps1 = eps0;
+  if (kStats) { eps0 = ld_plane(tile, PL_EPSUM0); eps1 = ld_plane(tile, PL_EPSUM1); }
+  const TrackSmem tr = stage_track(track, reinterpret_cast<const int2*>(st.chunk_types), N, smem_rows);
+  const unsigned live = __ballot_sync(0xffffffffu, active);
+  if (live == 0u) return;
+  __shared__ float4 obs_stage[8 * 128];
+  const GrStepIO no_io = {};
+  const GlobalObsSink gsink{no_io, live, obs_stage + (threadIdx.x >> 5) * 128};
+  bool any_reset = false, any_noise_dirty = false, last_noise_dirty = false;
+  const int64_t tape_step = (int64_t)(rio.tape_stride / kTile) * GR_TAPE_PLANES * kTile * 4;       // floats per tape step
+
+  float4 a_next = __ldcs(reinterpret_cast<const float4*>(rio.actions) + li);
+#pragma unroll 1
+  for (int t = 0; t < T; ++t) {
+    const int64_t tn = (int64_t)t * N + i;
+    const float4 a_t = a_next;
+    if (t + 1 < T) a_next = __ldcs(reinterpret_cast<const float4*>(rio.actions) + (int64_t)(t + 1) * N + li);      // one step ahead
+    GrRandom rt = rng;
+    rt.step = rng.step + (uint32_t)t;
+    if (!kPhilox) rt.rnd = rng.rnd + (int64_t)t * N * GR_RND_STRIDE;
+    const RandSrc<kPhilox> rs(rt, li, st.env_id_offset + li);
+    float4 n01, n23;
+    rs.normals8(n01, n23);
+    const Draws<kPhilox> draws{rs, nullptr};
+    GrStepIO io = {};
+    io.log_accum = rio.log_accum;
+    if (kDiff) {
+      io.tape = rio.tape ? rio.tape + (int64_t)t * tape_step : nullptr;
+      io.tape_stride = rio.tape_stride;
+      io.loss = rio.loss ? rio.loss + (int64_t)t * N : nullptr;
+      io.loss_terms = rio.loss_terms ? rio.loss_terms + (int64_t)t * N * 3 : nullptr;
+    }
+    const bool last = t == T - 1;
+    RolloutObsSink sink{gsink, nullptr, nullptr, nullptr, nullptr};
+    if (rio.obs_seq) sink.seq_rows = reinterpret_cast<float4*>(rio.obs_seq) + (int64_t)t * N * 4;
+    if (last) {
+      sink.out_rows = reinterpret_cast<float4*>(rio.obs_out);
+      sink.critic_rows = reinterpret_cast<float4*>(rio.critic_obs_out);
+      sink.aux_ptr = rio.aux_out;
+    }
+    StepOut so;
+    const bool alive = racing_step_body<kNoise, kDiff, kPhilox, kStats>(cfg, tr, e, a_t, n01, n23, draws, eps0, eps1, io, i, active, sink, so);
+    if (alive) {
+      if (kStats && !so.reset) {
+#pragma unroll
+        for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k) { if (k < 4) (&eps0.x)[k] += so.terms[k] * cfg.dt; else (&eps1.x)[k - 4] += so.terms[k] * cfg.dt; }
+      }
+      any_reset |= so.reset;
+      any_noise_dirty |= so.noise_dirty;
+      last_noise_dirty = so.noise_dirty;
+      if (rio.reward) rio.reward[tn] = so.reward;
+      if (rio.dones) rio.dones[tn] = so.reset ? 1 : 0;
+      if (rio.terminated) rio.terminated[tn] = so.terminated ? 1 : 0;
+      if (rio.time_out) rio.time_out[tn] = so.time_out ? 1 : 0;
+    }
+  }
+  if (active) {      // what T single steps leave behind: cold planes rewritten if any step reset, ANGACC.w = the LAST step's flag
+    store_env<kNoise>(e, tile, any_reset, any_noise_dirty);
+    if (kNoise && any_noise_dirty && !last_noise_dirty) st_plane(tile, PL_ANGACC, pack(e.aacc, 0.0f));
+    if (kStats) { st_plane(tile, PL_EPSUM0, eps0); st_plane(tile, PL_EPSUM1, eps1); }
+  }
+}
+
+// =============================================================================================
 // reset / observe: ManagerBasedRLEnv.reset() = _reset_idx(ids) + observation_manager.compute();
 // with an all-zero mask this is observation_manager.compute() alone (get_observations).
 // The "last action" observation uses the FIFO content (a_t) -- see DESIGN.md (get_observations caveat).
@@ -309,6 +399,45 @@ extern "C" int gr_step_fwd(const GrConfig* cfg, const GrTrack* track, const GrSt
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   return cfg->add_cmd_noise ? dispatch_diff<true>(diff, philox, stats, cfg, track, st, rng, io, s)
                             : dispatch_diff<false>(diff, philox, stats, cfg, track, st, rng, io, s);
+}
+
+template <bool kNoise, bool kDiff, bool kPhilox>
+static int launch_rollout(bool stats, const GrConfig* cfg, const GrTrack* tr, const GrState* st, const GrRandom* rng, const GrRolloutIO* io, cudaStream_t s) {
+  const size_t bytes = track_smem_bytes(tr, st);
+  const int kBlock = block_threads(st);
+  const int grid = (st->num_envs + kBlock - 1) / kBlock;
+  if (stats) {
+    auto kernel = racing_rollout_fwd_kernel<kNoise, kDiff, kPhilox, true>;
+    int rc = prepare_smem(kernel, bytes);
+    if (rc != GR_OK) return rc;
+    kernel<<<grid, kBlock, bytes, s>>>(*cfg, *tr, *st, *rng, *io);
+  } else {
+    auto kernel = racing_rollout_fwd_kernel<kNoise, kDiff, kPhilox, false>;
+    int rc = prepare_smem(kernel, bytes);
+    if (rc != GR_OK) return rc;
+    kernel<<<grid, kBlock, bytes, s>>>(*cfg, *tr, *st, *rng, *io);
+  }
+  return (int)cudaGetLastError();
+}
+
+extern "C" int gr_rollout_fwd(const GrConfig* cfg, const GrTrack* track, const GrState* st, const GrRandom* rng, const GrRolloutIO* io, void* stream) {
+  int rc = check_common(cfg, track, st);
+  if (rc != GR_OK) return rc;
+  if (!rng || !io || !io->actions || !io->obs_out) return GR_ERR_NULL;
+  if (io->T < 1) return GR_ERR_SIZE;
+  if (misaligned16(io->actions) || misaligned16(io->obs_out) || (io->critic_obs_out && misaligned16(io->critic_obs_out)) ||
+      (io->obs_seq && misaligned16(io->obs_seq)) || (rng->rnd && misaligned16(rng->rnd)) || (io->tape && misaligned16(io->tape)))
+    return GR_ERR_ALIGN;
+  if (io->tape && (io->tape_stride < ((st->num_envs + 31) & ~31) || (io->tape_stride & 31))) return GR_ERR_SIZE;
+  const bool diff = io->loss != nullptr || io->tape != nullptr || io->loss_terms != nullptr;
+  const bool stats = st->num_planes == GR_NUM_PLANES_WITH_STATS;
+  const bool philox = rng->rnd == nullptr;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+#define GR_GO(a, b, c) if ((cfg->add_cmd_noise != 0) == a && diff == b && philox == c) return launch_rollout<a, b, c>(stats, cfg, track, st, rng, io, s);
+  GR_GO(false, false, false) GR_GO(false, false, true) GR_GO(false, true, false) GR_GO(false, true, true)
+  GR_GO(true, false, false) GR_GO(true, false, true) GR_GO(true, true, false) GR_GO(true, true, true)
+#undef GR_GO
+  return GR_ERR_CONFIG;
 }
 
 template <bool kNoise, bool kPhilox>

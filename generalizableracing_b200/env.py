@@ -392,6 +392,69 @@ class RacingVecEnv:
             self._bptt.after_step(actions, ex)
         return o["obs"], o["reward"], o["dones"], ex
 
+    def rollout(self, actions: torch.Tensor, rnd: Optional[torch.Tensor] = None, record_obs: bool = False) -> dict:
+        """``for t in range(T): env.step(actions[t])`` in ONE launch (gr_rollout_fwd) for actions known in advance
+        (``actions`` [T,N,4]; dense mode: ``rnd`` [T,N,52]): the env state stays in registers over the window.  Bit-identical
+        to the T single steps.  Returns ``{"obs" [N,16] (after the last step), "reward" [T,N], "dones" / "terminated" /
+        "time_outs" [T,N] (bool), "obs_seq" [T,N,16] if record_obs}`` and, with differentiable physics, ``"losses"`` [T,N] /
+        ``"loss_terms"`` [T,N,3] while the window's tape is extended by T steps (``env._bptt.backward_window()`` then returns
+        dL/d(actions) for the whole window).  ``extras`` / ``get_observations()`` afterwards are those of the last step."""
+        if self._needs_reset:
+            self.reset()
+        dev, N = self.device, self.num_envs
+        act = actions.detach()
+        if act.dtype != torch.float32 or not act.is_contiguous() or act.device != dev:
+            act = act.to(dev, torch.float32).contiguous()
+        if act.dim() != 3 or tuple(act.shape[1:]) != (N, L.NUM_ACTIONS) or act.shape[0] < 1:
+            raise ValueError(f"Invalid actions shape, expected: (T, {N}, {L.NUM_ACTIONS}), received: {tuple(act.shape)}.")
+        T = act.shape[0]
+        rng = B.GrRandom(None, self.seed, self._step_count & 0xFFFFFFFF)
+        if rnd is not None:
+            rnd = rnd.to(dev, torch.float32).contiguous()
+            if tuple(rnd.shape) != (T, N, L.RND_STRIDE):
+                raise ValueError(f"rnd must be [{T}, {N}, {L.RND_STRIDE}]")
+            rng.rnd = rnd.data_ptr()
+        elif self.rng_mode == "dense":
+            raise ValueError("rng_mode='dense' needs an explicit rnd tensor every call")
+        self._step_count += T
+        k = self._flip
+        o = self._outs[k]
+        self._flip = k ^ 1
+        out = {"reward": torch.empty(T, N, device=dev), "dones": torch.empty(T, N, dtype=torch.uint8, device=dev),
+               "terminated": torch.empty(T, N, dtype=torch.uint8, device=dev), "time_outs": torch.empty(T, N, dtype=torch.uint8, device=dev)}
+        io = B.GrRolloutIO()
+        io.actions, io.T = act.data_ptr(), T
+        io.obs_out, io.critic_obs_out, io.aux_out = o["obs"].data_ptr(), o["critic"].data_ptr(), o["aux"].data_ptr()
+        io.reward, io.dones, io.terminated, io.time_out = (out[n].data_ptr() for n in ("reward", "dones", "terminated", "time_outs"))
+        if record_obs:
+            out["obs_seq"] = torch.empty(T, N, L.OBS_DIM, device=dev)
+            io.obs_seq = out["obs_seq"].data_ptr()
+        io.log_accum = self._log_accum.data_ptr()
+        win = self._bptt
+        if win is not None:
+            if win.t + T > win.capacity:
+                raise RuntimeError(f"BPTT horizon exceeded the tape capacity ({win.capacity} steps): call env.unwrapped.detach() "
+                                   "between windows or construct the env with a larger bptt_horizon")
+            t0 = win.t
+            io.loss, io.loss_terms, io.tape = win.loss[t0].data_ptr(), win.loss_terms[t0].data_ptr(), win.tape[t0].data_ptr()
+            io.tape_stride = self._stride
+        B.check(self._lib.gr_rollout_fwd(self._p_cfg, self._p_track, self._p_state, C.byref(rng), C.byref(io), self._stream()), "gr_rollout_fwd")
+        # the window kernel rewrites read-mostly planes without the per-step flags a pre-dependency prefetch relies on
+        self._state.launch_flags = self._launch_flags & ~B.GR_LAUNCH_PREFETCH
+        self._params_edited = True
+        self._last = o
+        ex = self.extras
+        dict.pop(ex, "log", None)
+        for n in ("dones", "terminated", "time_outs"):
+            out[n] = out[n].view(torch.bool)
+        ex["observations"] = self._obs_dict(o)
+        ex["time_outs"], ex["terminated"] = out["time_outs"][-1], out["terminated"][-1]
+        out["obs"] = o["obs"]
+        if win is not None:
+            out["losses"], out["loss_terms"] = win.loss[t0:t0 + T], win.loss_terms[t0:t0 + T]
+            win.t += T
+        return out
+
     # ------------------------------------------------------------------ the same two calls through torch.ops.gracing.* (ops.py)
     def _rnd_step(self, rnd):
         if rnd is not None:

@@ -206,6 +206,32 @@ typedef struct GrBwdIO {
 } GrBwdIO;
 int gr_step_bwd(const GrConfig* cfg, const GrState* st, const GrBwdIO* io, void* stream);
 
+/* ---- T consecutive env.step() calls in ONE launch for actions known in advance ("open-loop" window) -----------------------
+ * What the loop `for t in range(T): env.step(actions[t])` does -- the rollout loop of AlgoRunner.learn
+ * (standalone/diff_rl/algorithms/runner.py:110-126) / a play-back of recorded actions -- with the env state held in registers
+ * over the window: the state planes are read once and written once per WINDOW, a step costs its action (16 B) plus whatever it
+ * is asked to record.  Every step is gr_step_fwd's racing_step_body (bit-identical results, tests/test_rollout_window.py); step t
+ * uses the random stream (seed, env, rng->step + t) or, in dense mode, rng->rnd + t * N * GR_RND_STRIDE.  With loss / tape set the
+ * window is differentiable and gr_step_bwd sweeps it exactly as it sweeps T gr_step_fwd launches. */
+typedef struct GrRolloutIO {
+  const float* actions;              /* [T,N,4] */
+  float* obs_out;                    /* [N,16] policy observations after the last step */
+  float* critic_obs_out;             /* [N,16] optional */
+  float* aux_out;                    /* [N] optional */
+  float* obs_seq;                    /* [T,N,16] optional: policy observations after every step */
+  float* reward;                     /* [T,N] optional */
+  uint8_t* dones;                    /* [T,N] optional (terminated | time_out) */
+  uint8_t* terminated;               /* [T,N] optional */
+  uint8_t* time_out;                 /* [T,N] optional */
+  float* loss;                       /* [T,N]   differentiable physics: extras["losses"] of every step */
+  float* loss_terms;                 /* [T,N,3] optional */
+  float* tape;                       /* [T][tiles][GR_TAPE_PLANES][32] float4, as gr_step_fwd writes it */
+  int64_t tape_stride;               /* env capacity of one tape step = 32 * tiles */
+  float* log_accum;                  /* optional */
+  int32_t T;
+} GrRolloutIO;
+int gr_rollout_fwd(const GrConfig* cfg, const GrTrack* track, const GrState* st, const GrRandom* rng, const GrRolloutIO* io, void* stream);
+
 /* Dense random tensor exactly as the in-kernel Philox path would draw it (parity chain). */
 int gr_fill_rand(float* rnd, int32_t num_envs, int32_t env_id_offset, uint64_t seed, uint32_t step, void* stream);
 int gr_fill_startup_rand(float* srnd, int32_t num_envs, int32_t env_id_offset, uint64_t seed, void* stream);

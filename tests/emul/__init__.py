@@ -40,6 +40,7 @@ class EmulLib:
         self._l = C.CDLL(build())
         P = C.POINTER
         self._l.emul_step_fwd.argtypes = [P(B.GrConfig), P(B.GrTrack), P(B.GrState), P(B.GrRandom), P(B.GrStepIO)]
+        self._l.emul_rollout_fwd.argtypes = [P(B.GrConfig), P(B.GrTrack), P(B.GrState), P(B.GrRandom), P(B.GrRolloutIO)]
         self._l.emul_env_reset.argtypes = [P(B.GrConfig), P(B.GrTrack), P(B.GrState), P(B.GrRandom), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         self._l.emul_env_startup.argtypes = [P(B.GrConfig), P(B.GrTrack), P(B.GrState), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         self._l.emul_step_bwd.argtypes = [P(B.GrConfig), P(B.GrState), P(B.GrBwdIO)]
@@ -52,6 +53,9 @@ class EmulLib:
 
     def gr_step_fwd(self, cfg, tr, st, rng, io, stream):
         return self._l.emul_step_fwd(cfg, tr, st, rng, io)
+
+    def gr_rollout_fwd(self, cfg, tr, st, rng, io, stream):
+        return self._l.emul_rollout_fwd(cfg, tr, st, rng, io)
 
     def gr_env_reset(self, cfg, tr, st, rng, mask, obs, critic, aux, stream):
         return self._l.emul_env_reset(cfg, tr, st, rng, mask, 0 if mask else 1, obs, critic, aux)
