@@ -487,6 +487,32 @@ def bench_extras(dev, cfg, table):
     del envs, graph
     torch.cuda.empty_cache()
 
+    # ---- forward-only window at C4 size: 65,536 envs x 24 steps in one launch, observations of every step recorded (play-back of
+    # recorded actions / open-loop evaluation): per env-step 16 B action + 64 B observation + 7 B reward / masks, state once per window
+    Nw, Tw = 65536, 24
+    wenvs = [RacingVecEnv(cfg, table, Nw, device=dev, seed=31 + r) for r in range(2)]
+    wacts = torch.randn(Tw, Nw, 4, device=dev) * 0.5
+    for e in wenvs:
+        e.reset()
+        e.episode_length_buf = torch.randint(0, cfg.max_episode_length, (Nw,), device=dev, dtype=torch.int32)
+        e.rollout(wacts, record_obs=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(reps):
+        for e in wenvs:
+            e.rollout(wacts, record_obs=True)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_fw = e0.elapsed_time(e1) / (reps * len(wenvs))
+    b_fw = 16 + 64 + 7 + algorithmic_bytes(cfg, True) / Tw
+    out["fwd_window_65536x24"] = {"ms_per_window": ms_fw, "us_per_step": ms_fw * 1e3 / Tw, "env_steps_per_s": Nw * Tw / (ms_fw * 1e-3),
+                                  "bytes_per_env_step": b_fw, "achieved_GBps": b_fw * Nw * Tw / (ms_fw * 1e-3) / 1e9,
+                                  "what": "gr_rollout_fwd, STAGE 1, stats on, obs_seq recorded; 2 env sets alternating (each window moves 174 MB > L2)"}
+    for e in wenvs:
+        e.close()
+    del wenvs
+    torch.cuda.empty_cache()
+
     # ---- C2: rollout storage on [24, 4096]
     T, N2 = 24, 4096
     sto = RolloutStorage("rl", N2, T, [16], [16], [4], device=dev)
