@@ -127,8 +127,6 @@ class GrHostStep(C.Structure):
 GR_HOST_PIPE_MAX_DEPTH = 4
 GR_LAUNCH_PDL = 1
 GR_LAUNCH_PREFETCH = 2
-GR_LAUNCH_ROLLOUT_WIDE = 8
-GR_LAUNCH_ROLLOUT_CAPPED = 16
 GR_LOG_SLOTS = 16
 class GrReachConfig(C.Structure):
     _fields_ = [

@@ -111,11 +111,12 @@ struct RolloutObsSink {
   __device__ __forceinline__ void aux(int i, float v) const { if (aux_ptr) aux_ptr[i] = v; }
 };
 
-// kMinBlocks = 2 caps the kernel at 128 registers (a handful of spilled words) so that 65,536 envs are one wave of 8 blocks per SM
-// instead of two waves of 4; kMinBlocks = 1 (216-225 registers, no spills) serves grids that fit one wave anyway.
-template <bool kNoise, bool kDiff, bool kPhilox, bool kStats, int kMinBlocks>
-__global__ void __launch_bounds__(256, kMinBlocks) racing_rollout_fwd_kernel(const GrConfig cfg, const GrTrack track, const GrState st,
-                                                                             const GrRandom rng, const GrRolloutIO rio) {
+// 216-225 registers, no spills: 4 blocks of 64 threads per SM, i.e. two waves at 65,536 envs.  (Measured: capping the kernel at 128
+// registers -- a handful of spilled words, one wave of 8 blocks per SM -- is SLOWER at every size tried: 4.22 vs 3.90 us per step at
+// 65,536 envs, 2.66 vs 2.00 us at 16,384 with tape; tools/rollout_bench.py.)
+template <bool kNoise, bool kDiff, bool kPhilox, bool kStats>
+__global__ void __launch_bounds__(256) racing_rollout_fwd_kernel(const GrConfig cfg, const GrTrack track, const GrState st,
+                                                                 const GrRandom rng, const GrRolloutIO rio) {
   GR_DYN_SMEM(float4, smem_rows);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int N = st.num_envs, T = rio.T;
@@ -408,15 +409,17 @@ static int launch_rollout(bool stats, const GrConfig* cfg, const GrTrack* tr, co
   const size_t bytes = track_smem_bytes(tr, st);
   const int kBlock = block_threads(st);
   const int grid = (st->num_envs + kBlock - 1) / kBlock;
-  // the uncapped build holds 65,536 registers / (225 * kBlock) blocks per SM: past one wave of those, use the 128-register build
-  int capped = (int64_t)grid * kBlock * 225 > (int64_t)148 * 65536;
-  if (st->launch_flags & GR_LAUNCH_ROLLOUT_WIDE) capped = 0;
-  if (st->launch_flags & GR_LAUNCH_ROLLOUT_CAPPED) capped = 1;
-#define GR_LAUNCH_ROLLOUT(STATS, MINB) { auto kernel = racing_rollout_fwd_kernel<kNoise, kDiff, kPhilox, STATS, MINB>; int rc = prepare_smem(kernel, bytes); \
-    if (rc != GR_OK) return rc; kernel<<<grid, kBlock, bytes, s>>>(*cfg, *tr, *st, *rng, *io); }
-  if (stats) { if (capped) GR_LAUNCH_ROLLOUT(true, 2) else GR_LAUNCH_ROLLOUT(true, 1) }
-  else { if (capped) GR_LAUNCH_ROLLOUT(false, 2) else GR_LAUNCH_ROLLOUT(false, 1) }
-#undef GR_LAUNCH_ROLLOUT
+  if (stats) {
+    auto kernel = racing_rollout_fwd_kernel<kNoise, kDiff, kPhilox, true>;
+    int rc = prepare_smem(kernel, bytes);
+    if (rc != GR_OK) return rc;
+    kernel<<<grid, kBlock, bytes, s>>>(*cfg, *tr, *st, *rng, *io);
+  } else {
+    auto kernel = racing_rollout_fwd_kernel<kNoise, kDiff, kPhilox, false>;
+    int rc = prepare_smem(kernel, bytes);
+    if (rc != GR_OK) return rc;
+    kernel<<<grid, kBlock, bytes, s>>>(*cfg, *tr, *st, *rng, *io);
+  }
   return (int)cudaGetLastError();
 }
 

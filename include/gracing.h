@@ -122,9 +122,6 @@ typedef struct GrState {
 #define GR_LAUNCH_PREFETCH 2   /* with GR_LAUNCH_PDL: fetch the read-mostly planes before the grid dependency (see racing_step.cu);
                                  clear it for the first step after the HOST rewrote planes 9..15 of the state */
 
-#define GR_LAUNCH_ROLLOUT_WIDE 8     /* gr_rollout_fwd: force the uncapped-register build of the window kernel (default: picked by grid size) */
-#define GR_LAUNCH_ROLLOUT_CAPPED 16  /* gr_rollout_fwd: force the 128-register build */
-
 /* Random source: dense tensor (parity mode) or in-kernel Philox4x32-10 (throughput mode). */
 typedef struct GrRandom {
   const float* rnd;         /* [num_envs, GR_RND_STRIDE] or NULL => Philox */
