@@ -154,6 +154,11 @@ class GrReachStepIO(C.Structure):
                 ("loss", c_p), ("loss_terms", c_p), ("tape", c_p), ("tape_stride", C.c_int64), ("log_accum", c_p)]
 
 
+class GrReachRolloutIO(C.Structure):
+    _fields_ = [("actions", c_p), ("obs_out", c_p), ("obs_seq", c_p), ("reward", c_p), ("dones", c_p), ("terminated", c_p), ("time_out", c_p),
+                ("loss", c_p), ("loss_terms", c_p), ("tape", c_p), ("tape_stride", C.c_int64), ("log_accum", c_p), ("T", c_i)]
+
+
 GR_REACH_LOG_NUM_RESET, GR_REACH_LOG_SUM_POS_ERR, GR_REACH_LOG_SUM_EPSUM, GR_REACH_LOG_NUM_TIMEOUT, GR_REACH_LOG_NUM_TERMINATED = 0, 1, 2, 12, 13
 GR_LOG_SHARDS = 256
 GR_PHILOX_CALL_ACTION = 16
@@ -189,6 +194,7 @@ PROTOTYPES = {
     "gr_reach_reset": (C.c_int, [C.POINTER(GrReachConfig), C.POINTER(GrReachState), C.POINTER(GrRandom), c_p, c_p, c_p]),
     "gr_reach_observe": (C.c_int, [C.POINTER(GrReachConfig), C.POINTER(GrReachState), c_p, c_p]),
     "gr_reach_step_fwd": (C.c_int, [C.POINTER(GrReachConfig), C.POINTER(GrReachState), C.POINTER(GrRandom), C.POINTER(GrReachStepIO), c_p]),
+    "gr_reach_rollout_fwd": (C.c_int, [C.POINTER(GrReachConfig), C.POINTER(GrReachState), C.POINTER(GrRandom), C.POINTER(GrReachRolloutIO), c_p]),
     "gr_reach_step_bwd": (C.c_int, [C.POINTER(GrReachConfig), C.POINTER(GrReachState), C.POINTER(GrBwdIO), c_p]),
     "gr_reach_fill_rand": (C.c_int, [c_p, c_i, c_i, C.c_uint64, C.c_uint32, c_p]),
     "gr_traj_index": (C.c_int, [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),

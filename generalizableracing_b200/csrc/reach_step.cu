@@ -47,7 +47,7 @@ struct ReachRand {
 };
 
 struct ReachRegs {
-  Q4 q; V3 p; float f; V3 v; int eplen; V3 om; float time_left; V3 tau; V3 aacc; bool fresh; float4 fifo; V3 target; float4 raw;
+  Q4 q; V3 p; float f; V3 v; int eplen; V3 om; float time_left; V3 tau; V3 aacc; bool fresh, cold_stale; float4 fifo; V3 target; float4 raw;
   float4 eps0, eps1; float eps8, eps9; V3 k2, k1; float thr;
 };
 
@@ -62,7 +62,9 @@ __device__ __forceinline__ void reach_load_hot(ReachRegs& e, const float4* __res
                a4 = __ldcs(P + ridx(RPL_TORQUE, i)), a5 = __ldcs(P + ridx(RPL_ANGACC, i)), a6 = __ldcs(P + ridx(RPL_FIFO, i)), a7 = __ldcs(P + ridx(RPL_TARGET, i)),
                a8 = __ldcs(P + ridx(RPL_EPSUM0, i)), a9 = __ldcs(P + ridx(RPL_EPSUM1, i)), a10 = __ldcs(P + ridx(RPL_EPSUM2, i));
   e.q = quat(a0); e.p = xyz(a1); e.f = a1.w; e.v = xyz(a2); e.eplen = __float_as_int(a2.w); e.om = xyz(a3); e.time_left = a3.w;
-  e.tau = xyz(a4); e.aacc = xyz(a5); e.fresh = a5.w != 0.0f; e.fifo = a6; e.target = xyz(a7);
+  // ANGACC.w: 1 = the env was reset by the previous step (ActionManager latches zeroed), 2 = a window kernel rewrote the read-mostly
+  // planes in an earlier step of its window (only the prefetch needs to know), 0 = neither
+  e.tau = xyz(a4); e.aacc = xyz(a5); e.fresh = a5.w == 1.0f; e.cold_stale = a5.w == 2.0f; e.fifo = a6; e.target = xyz(a7);
   e.raw = make_float4(a7.w, a10.z, a10.w, a4.w);
   e.eps0 = a8; e.eps1 = a9; e.eps8 = a10.x; e.eps9 = a10.y;
 }
@@ -70,13 +72,13 @@ __device__ __forceinline__ void reach_load(ReachRegs& e, const float4* __restric
   reach_load_cold<false>(e, P, i);
   reach_load_hot(e, P, i);
 }
-__device__ __forceinline__ void reach_store(const ReachRegs& e, float4* __restrict__ P, int i, bool cold_dirty) {
+__device__ __forceinline__ void reach_store(const ReachRegs& e, float4* __restrict__ P, int i, bool cold_dirty, bool flag_stale = false) {
   __stcs(P + ridx(RPL_QUAT, i), pack(e.q));
   __stcs(P + ridx(RPL_POS, i), pack(e.p, e.f));
   __stcs(P + ridx(RPL_LINVEL, i), pack(e.v, __int_as_float(e.eplen)));
   __stcs(P + ridx(RPL_ANGVEL, i), pack(e.om, e.time_left));
   __stcs(P + ridx(RPL_TORQUE, i), pack(e.tau, e.raw.w));
-  __stcs(P + ridx(RPL_ANGACC, i), pack(e.aacc, e.fresh ? 1.0f : 0.0f));
+  __stcs(P + ridx(RPL_ANGACC, i), pack(e.aacc, e.fresh ? 1.0f : (flag_stale ? 2.0f : 0.0f)));
   __stcs(P + ridx(RPL_FIFO, i), e.fifo);
   __stcs(P + ridx(RPL_TARGET, i), pack(e.target, e.raw.x));
   __stcs(P + ridx(RPL_EPSUM0, i), e.eps0);
@@ -146,33 +148,35 @@ __device__ __forceinline__ void reach_write_obs(const GrReachConfig& c, const Re
   const float* src = stage[threadIdx.x >> 5];
   float* dst = obs + (int64_t)(i - lane) * GR_REACH_OBS_DIM;
   for (int k = lane; k < nlive * GR_REACH_OBS_DIM; k += nlive) __stcs(dst + k, src[k]);
+  __syncwarp(live);                                       // the staging rows are reused by the next call (window kernel)
 #endif
 }
 
-template <bool kDiff, bool kPhilox>
-__global__ void __launch_bounds__(kReachBlock) reach_step_fwd_kernel(const GrReachConfig cfg, const GrReachState st, const GrRandom rng, const GrReachStepIO io) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= st.num_envs) return;
-  const unsigned live = warp_live_mask();
-  float4* __restrict__ P = reinterpret_cast<float4*>(st.planes);
-  ReachRegs e;
-  // Programmatic dependent launch: everything that does not depend on the previous kernel in the stream -- the read-mostly
-  // planes, the filter constants -- is fetched / formed before the grid dependency and overlaps that kernel's tail.
-  reach_load_cold<false>(e, P, i);
-  const ReachRand<kPhilox> rs(rng, i, st.env_id_offset + i);
-  const float dt = cfg.dt;
-  const V3 J = v3(cfg.inertia[0], cfg.inertia[1], cfg.inertia[2]);
-  const V3 Jinv = v3(1.0f / J.x, 1.0f / J.y, 1.0f / J.z);
-  const float inv_m = 1.0f / cfg.mass;
-  const float ef = expf(-dt / cfg.thrust_delay);
-  V3 etau = v3(0.f, 0.f, 0.f);
-  if (cfg.controller == GR_CTRL_CTBR) etau = v3(expf(-dt / cfg.torque_delay[0]), expf(-dt / cfg.torque_delay[1]), expf(-dt / cfg.torque_delay[2]));
-  pdl_wait();
-  reach_load_hot(e, P, i);
-  const float4 a_t = __ldcs(reinterpret_cast<const float4*>(io.action) + i);
-  pdl_launch_dependents();
-  if (e.fresh) reach_load_cold<true>(e, P, i);                  // the previous step reset this env: its prefetched copy may be stale
+// step-invariant constants (formed before the grid dependency in the single-step kernel, once per window in the rollout kernel)
+struct ReachConsts { float dt; V3 J, Jinv; float inv_m, ef; V3 etau; };
+__device__ __forceinline__ ReachConsts reach_consts(const GrReachConfig& cfg) {
+  ReachConsts k;
+  k.dt = cfg.dt;
+  k.J = v3(cfg.inertia[0], cfg.inertia[1], cfg.inertia[2]);
+  k.Jinv = v3(1.0f / k.J.x, 1.0f / k.J.y, 1.0f / k.J.z);
+  k.inv_m = 1.0f / cfg.mass;
+  k.ef = expf(-k.dt / cfg.thrust_delay);
+  k.etau = v3(0.f, 0.f, 0.f);
+  if (cfg.controller == GR_CTRL_CTBR) k.etau = v3(expf(-k.dt / cfg.torque_delay[0]), expf(-k.dt / cfg.torque_delay[1]), expf(-k.dt / cfg.torque_delay[2]));
+  return k;
+}
+// destinations of ONE step (nullptr: skip) and what the body hands back
+struct ReachStepPtrs { float* loss; float* loss_terms; float4* tape; float* log_accum; float* obs; float* obs2; };
+struct ReachStepOut { float reward; bool terminated, time_out, reset; float terms[GR_REACH_NUM_REWARD_TERMS]; };
 
+// Sections 1-11 of ManagerBasedDiffRLEnv.step for ONE env held in registers: shared by the single-step kernel and the
+// multi-step window kernel (gr_reach_rollout_fwd).  `e` = state before the step in, after the step (and a reset) out.
+template <bool kDiff, bool kPhilox>
+__device__ __forceinline__ void reach_step_body(const GrReachConfig& cfg, const ReachConsts& kc, ReachRegs& e, const float4 a_t,
+                                                const ReachRand<kPhilox>& rs, const ReachStepPtrs& io, const int i, const unsigned live,
+                                                ReachStepOut& out) {
+  const float dt = kc.dt, inv_m = kc.inv_m, ef = kc.ef;
+  const V3 J = kc.J, Jinv = kc.Jinv, etau = kc.etau;
   // ---- 1. process_action (L/managers/action_manager.py:44-45; QD/mdp/diff_action.py:156-176) ----
   const bool fresh0 = e.fresh;
   const float4 a_lag = e.fifo;                                   // lag 1: the applied action is a_{t-1}
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(kReachBlock) reach_step_fwd_kernel(const GrRea
   const V3 omw1 = quat_rotate(q1, omb1);
   const V3 Dg = -(2.0f * (e.k2 * vabs(v_b)) + e.k1);             // d F_b / d v_b (diagonal), with the drag of THIS step
 
-  float4* __restrict__ T = reinterpret_cast<float4*>(io.tape);
+  float4* __restrict__ T = io.tape;
   const bool tape = kDiff && io.tape != nullptr;
 
   // ---- 2./3. closure physics (oracle/reach_oracle.py R.1) + align: the carried state is the nominal one ----
@@ -367,17 +371,89 @@ __global__ void __launch_bounds__(kReachBlock) reach_step_fwd_kernel(const GrRea
   }
 
   // ---- 11. observations on the post-reset state ----
-  reach_write_obs(cfg, e, reset ? make_float4(0.f, 0.f, 0.f, 0.f) : a_t, io.obs, i, live);
+  if (io.obs) reach_write_obs(cfg, e, reset ? make_float4(0.f, 0.f, 0.f, 0.f) : a_t, io.obs, i, live);      // (warp-uniform)
+  if (io.obs2) reach_write_obs(cfg, e, reset ? make_float4(0.f, 0.f, 0.f, 0.f) : a_t, io.obs2, i, live);
   e.fifo = a_t;
-  io.reward[i] = reward;
-  io.terminated[i] = terminated ? 1 : 0;
-  io.time_out[i] = time_out ? 1 : 0;
-  if (io.dones) io.dones[i] = reset ? 1 : 0;
+  out.reward = reward; out.terminated = terminated; out.time_out = time_out; out.reset = reset;
+#pragma unroll
+  for (int k = 0; k < GR_REACH_NUM_REWARD_TERMS; ++k) out.terms[k] = terms[k];
+}
+
+template <bool kDiff, bool kPhilox>
+__global__ void __launch_bounds__(kReachBlock) reach_step_fwd_kernel(const GrReachConfig cfg, const GrReachState st, const GrRandom rng, const GrReachStepIO io) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= st.num_envs) return;
+  const unsigned live = warp_live_mask();
+  float4* __restrict__ P = reinterpret_cast<float4*>(st.planes);
+  ReachRegs e;
+  // Programmatic dependent launch: everything that does not depend on the previous kernel in the stream -- the read-mostly
+  // planes, the filter constants -- is fetched / formed before the grid dependency and overlaps that kernel's tail.
+  reach_load_cold<false>(e, P, i);
+  const ReachRand<kPhilox> rs(rng, i, st.env_id_offset + i);
+  const ReachConsts kc = reach_consts(cfg);
+  pdl_wait();
+  reach_load_hot(e, P, i);
+  const float4 a_t = __ldcs(reinterpret_cast<const float4*>(io.action) + i);
+  pdl_launch_dependents();
+  if (e.fresh || e.cold_stale) reach_load_cold<true>(e, P, i);   // a reset rewrote this env's read-mostly planes: the prefetched copy may be stale
+
+  const ReachStepPtrs sp{io.loss, io.loss_terms, reinterpret_cast<float4*>(io.tape), io.log_accum, io.obs, nullptr};
+  ReachStepOut so;
+  reach_step_body<kDiff, kPhilox>(cfg, kc, e, a_t, rs, sp, i, live, so);
+  io.reward[i] = so.reward;
+  io.terminated[i] = so.terminated ? 1 : 0;
+  io.time_out[i] = so.time_out ? 1 : 0;
+  if (io.dones) io.dones[i] = so.reset ? 1 : 0;
   if (io.reward_terms) {
 #pragma unroll
-    for (int k = 0; k < GR_REACH_NUM_REWARD_TERMS; ++k) io.reward_terms[(int64_t)i * GR_REACH_NUM_REWARD_TERMS + k] = terms[k];
+    for (int k = 0; k < GR_REACH_NUM_REWARD_TERMS; ++k) io.reward_terms[(int64_t)i * GR_REACH_NUM_REWARD_TERMS + k] = so.terms[k];
   }
-  reach_store(e, P, i, reset);
+  reach_store(e, P, i, so.reset, false);
+}
+
+// T steps in ONE launch for actions known in advance (gr_reach_rollout_fwd): the same body, the env state in registers over the
+// window.  Step t uses the random stream (seed, env, rng.step + t) or, in dense mode, rng.rnd + t * N * GR_REACH_RND_STRIDE.
+template <bool kDiff, bool kPhilox>
+__global__ void __launch_bounds__(kReachBlock) reach_rollout_fwd_kernel(const GrReachConfig cfg, const GrReachState st, const GrRandom rng, const GrReachRolloutIO rio) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = st.num_envs, T = rio.T;
+  if (i >= N) return;
+  const unsigned live = warp_live_mask();
+  float4* __restrict__ P = reinterpret_cast<float4*>(st.planes);
+  ReachRegs e;
+  reach_load(e, P, i);
+  const ReachConsts kc = reach_consts(cfg);
+  const int64_t tape_step = (int64_t)(rio.tape_stride / 32) * GR_REACH_TAPE_PLANES * 32;          // float4 per tape step
+  bool any_reset = false;
+  float4 a_next = __ldcs(reinterpret_cast<const float4*>(rio.actions) + i);
+#pragma unroll 1
+  for (int t = 0; t < T; ++t) {
+    const int64_t tn = (int64_t)t * N + i;
+    const float4 a_t = a_next;
+    if (t + 1 < T) a_next = __ldcs(reinterpret_cast<const float4*>(rio.actions) + (int64_t)(t + 1) * N + i);     // one step ahead
+    GrRandom rt = rng;
+    rt.step = rng.step + (uint32_t)t;
+    if (!kPhilox) rt.rnd = rng.rnd + (int64_t)t * N * GR_REACH_RND_STRIDE;
+    const ReachRand<kPhilox> rs(rt, i, st.env_id_offset + i);
+    ReachStepPtrs sp{nullptr, nullptr, nullptr, rio.log_accum, nullptr, nullptr};
+    if (kDiff) {
+      sp.loss = rio.loss ? rio.loss + (int64_t)t * N : nullptr;
+      sp.loss_terms = rio.loss_terms ? rio.loss_terms + (int64_t)t * N * GR_REACH_NUM_LOSS_TERMS : nullptr;
+      sp.tape = rio.tape ? reinterpret_cast<float4*>(rio.tape) + (int64_t)t * tape_step : nullptr;
+    }
+    if (rio.obs_seq) sp.obs = rio.obs_seq + (int64_t)t * N * GR_REACH_OBS_DIM;
+    if (t == T - 1) sp.obs2 = rio.obs_out;       // the "observation after the window" buffer
+    ReachStepOut so;
+    reach_step_body<kDiff, kPhilox>(cfg, kc, e, a_t, rs, sp, i, live, so);
+    any_reset |= so.reset;
+    if (rio.reward) rio.reward[tn] = so.reward;
+    if (rio.dones) rio.dones[tn] = so.reset ? 1 : 0;
+    if (rio.terminated) rio.terminated[tn] = so.terminated ? 1 : 0;
+    if (rio.time_out) rio.time_out[tn] = so.time_out ? 1 : 0;
+  }
+  // cold planes rewritten if any step of the window reset this env; unless the LAST step did (fresh), the next single step could not
+  // tell that its pre-dependency prefetch of them is stale: flag it
+  reach_store(e, P, i, any_reset, any_reset && !e.fresh);
 }
 
 // ManagerBasedRLEnv.reset / _reset_idx(mask) + observations; mode 0 = masked, 1 = all, 2 = observe only
@@ -446,6 +522,26 @@ extern "C" int gr_reach_step_fwd(const GrReachConfig* cfg, const GrReachState* s
   lc.numAttrs = 1;
   if (diff) return (int)(philox ? cudaLaunchKernelEx(&lc, reach_step_fwd_kernel<true, true>, *cfg, *st, *rng, *io) : cudaLaunchKernelEx(&lc, reach_step_fwd_kernel<true, false>, *cfg, *st, *rng, *io));
   return (int)(philox ? cudaLaunchKernelEx(&lc, reach_step_fwd_kernel<false, true>, *cfg, *st, *rng, *io) : cudaLaunchKernelEx(&lc, reach_step_fwd_kernel<false, false>, *cfg, *st, *rng, *io));
+}
+
+extern "C" int gr_reach_rollout_fwd(const GrReachConfig* cfg, const GrReachState* st, const GrRandom* rng, const GrReachRolloutIO* io, void* stream) {
+  if (!rng || !io || !io->actions || !io->obs_out) return GR_ERR_NULL;
+  if (const int rc = reach_check(cfg, st)) return rc;
+  if (io->T < 1) return GR_ERR_SIZE;
+  auto mis = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; };
+  if (mis(io->actions) || (io->tape && mis(io->tape)) || (io->loss_terms && mis(io->loss_terms)) || (rng->rnd && mis(rng->rnd))) return GR_ERR_ALIGN;
+  if (io->tape && (io->tape_stride < ((st->num_envs + 31) & ~31) || (io->tape_stride & 31))) return GR_ERR_SIZE;
+  const bool diff = io->loss || io->tape || io->loss_terms, philox = rng->rnd == nullptr;
+  const int grid = (st->num_envs + kReachBlock - 1) / kReachBlock;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (diff) {
+    if (philox) reach_rollout_fwd_kernel<true, true><<<grid, kReachBlock, 0, s>>>(*cfg, *st, *rng, *io);
+    else reach_rollout_fwd_kernel<true, false><<<grid, kReachBlock, 0, s>>>(*cfg, *st, *rng, *io);
+  } else {
+    if (philox) reach_rollout_fwd_kernel<false, true><<<grid, kReachBlock, 0, s>>>(*cfg, *st, *rng, *io);
+    else reach_rollout_fwd_kernel<false, false><<<grid, kReachBlock, 0, s>>>(*cfg, *st, *rng, *io);
+  }
+  return (int)cudaGetLastError();
 }
 
 static int reach_reset_launch(const GrReachConfig* cfg, const GrReachState* st, const GrRandom* rng, const uint8_t* mask, int mode, float* obs, void* stream) {

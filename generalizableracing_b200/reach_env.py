@@ -144,7 +144,7 @@ class ReachTargetVecEnv:
         e0, e1, e2, d2, d1 = (R(p) for p in (L.RPL_EPSUM0, L.RPL_EPSUM1, L.RPL_EPSUM2, L.RPL_DRAG2, L.RPL_DRAG1))
         return {"root_quat_w": q, "root_pos_w": pos[:, :3], "gross_thrust": pos[:, 3], "root_lin_vel_w": lin[:, :3],
                 "episode_length": lin[:, 3].contiguous().view(torch.int32), "root_ang_vel_b": ang[:, :3], "time_left": ang[:, 3],
-                "torque": tq[:, :3], "ang_acc_b": aa[:, :3], "fresh": aa[:, 3] != 0, "action_fifo": ff, "pose_command_w": tg[:, :3],
+                "torque": tq[:, :3], "ang_acc_b": aa[:, :3], "fresh": aa[:, 3] == 1, "action_fifo": ff, "pose_command_w": tg[:, :3],
                 "raw_actions": torch.stack([tg[:, 3], e2[:, 2], e2[:, 3], tq[:, 3]], dim=-1),
                 "episode_sums": torch.cat([e0, e1, e2[:, :2]], dim=-1), "drag_coeffs": d2[:, :3], "h_force_drag_coeffs": d1[:, :3],
                 "thr_est_error": d1[:, 3]}
@@ -229,6 +229,61 @@ class ReachTargetVecEnv:
         if self._bptt is not None:
             self._bptt.after_step(actions, ex)
         return o["obs"], o["reward"], o["dones"], ex
+
+    def rollout(self, actions: torch.Tensor, rnd: Optional[torch.Tensor] = None, record_obs: bool = False) -> dict:
+        """``for t in range(T): env.step(actions[t])`` in ONE launch (gr_reach_rollout_fwd) for actions known in advance
+        (``actions`` [T,N,4]; dense mode: ``rnd`` [T,N,24]); same contract as :meth:`RacingVecEnv.rollout`."""
+        if self._needs_reset:
+            self.reset()
+        dev, N = self.device, self.num_envs
+        act = actions.detach()
+        if act.dtype != torch.float32 or not act.is_contiguous() or act.device != dev:
+            act = act.to(dev, torch.float32).contiguous()
+        if act.dim() != 3 or tuple(act.shape[1:]) != (N, L.NUM_ACTIONS) or act.shape[0] < 1:
+            raise ValueError(f"Invalid actions shape, expected: (T, {N}, {L.NUM_ACTIONS}), received: {tuple(act.shape)}.")
+        T = act.shape[0]
+        rng = B.GrRandom(None, self.seed, self._step_count & 0xFFFFFFFF)
+        if rnd is not None:
+            rnd = rnd.to(dev, torch.float32).contiguous()
+            if tuple(rnd.shape) != (T, N, L.REACH_RND_STRIDE):
+                raise ValueError(f"rnd must be [{T}, {N}, {L.REACH_RND_STRIDE}]")
+            rng.rnd = rnd.data_ptr()
+        elif self.rng_mode == "dense":
+            raise ValueError("rng_mode='dense' needs an explicit rnd tensor every call")
+        self._step_count += T
+        k = self._flip
+        o = self._outs[k]
+        self._flip = k ^ 1
+        out = {"reward": torch.empty(T, N, device=dev), "dones": torch.empty(T, N, dtype=torch.uint8, device=dev),
+               "terminated": torch.empty(T, N, dtype=torch.uint8, device=dev), "time_outs": torch.empty(T, N, dtype=torch.uint8, device=dev)}
+        io = B.GrReachRolloutIO()
+        io.actions, io.T, io.obs_out = act.data_ptr(), T, o["obs"].data_ptr()
+        io.reward, io.dones, io.terminated, io.time_out = (out[n].data_ptr() for n in ("reward", "dones", "terminated", "time_outs"))
+        if record_obs:
+            out["obs_seq"] = torch.empty(T, N, L.REACH_OBS_DIM, device=dev)
+            io.obs_seq = out["obs_seq"].data_ptr()
+        io.log_accum = self._log_accum.data_ptr()
+        win = self._bptt
+        if win is not None:
+            if win.t + T > win.capacity:
+                raise RuntimeError(f"BPTT horizon exceeded the tape capacity ({win.capacity} steps): call env.unwrapped.detach() "
+                                   "between windows or construct the env with a larger bptt_horizon")
+            t0 = win.t
+            io.loss, io.loss_terms, io.tape = win.loss[t0].data_ptr(), win.loss_terms[t0].data_ptr(), win.tape[t0].data_ptr()
+            io.tape_stride = self._stride
+        B.check(self._lib.gr_reach_rollout_fwd(C.byref(self._gcfg), C.byref(self._state), C.byref(rng), C.byref(io), self._stream()), "gr_reach_rollout_fwd")
+        self._last = o
+        ex = self.extras
+        dict.pop(ex, "log", None)
+        for n in ("dones", "terminated", "time_outs"):
+            out[n] = out[n].view(torch.bool)
+        ex["observations"] = {"policy": o["obs"]}
+        ex["time_outs"], ex["terminated"] = out["time_outs"][-1], out["terminated"][-1]
+        out["obs"] = o["obs"]
+        if win is not None:
+            out["losses"], out["loss_terms"] = win.loss[t0:t0 + T], win.loss_terms[t0:t0 + T]
+            win.t += T
+        return out
 
 
 _TASKS = {"DiffLab-Quadcopter-LV-ReachTarget-v0": ReachTargetCfg.lv, "DiffLab-Quadcopter-CTBR-ReachTarget-v0": ReachTargetCfg.ctbr,

@@ -497,6 +497,27 @@ int gr_reach_reset(const GrReachConfig* cfg, const GrReachState* st, const GrRan
 /* observation_manager.compute() alone. */
 int gr_reach_observe(const GrReachConfig* cfg, const GrReachState* st, float* obs, void* stream);
 int gr_reach_step_fwd(const GrReachConfig* cfg, const GrReachState* st, const GrRandom* rng, const GrReachStepIO* io, void* stream);
+
+/* T consecutive gr_reach_step_fwd calls in ONE launch for actions known in advance (see gr_rollout_fwd): the state stays in
+ * registers over the window, results bit-identical to the T single steps (tests/test_reach_rollout.py).  One state word differs on
+ * purpose: plane RPL_ANGACC .w = 2 marks an env whose read-mostly planes were rewritten by a reset in an earlier step of the window,
+ * so that the next single step re-reads them after its grid dependency; that step clears the mark. */
+typedef struct GrReachRolloutIO {
+  const float* actions;     /* [T,N,4] */
+  float* obs_out;           /* [N,17] observations after the last step */
+  float* obs_seq;           /* [T,N,17] optional: observations after every step */
+  float* reward;            /* [T,N] optional */
+  uint8_t* dones;           /* [T,N] optional */
+  uint8_t* terminated;      /* [T,N] optional */
+  uint8_t* time_out;        /* [T,N] optional */
+  float* loss;              /* [T,N]   differentiable physics */
+  float* loss_terms;        /* [T,N,4] optional (16-byte aligned) */
+  float* tape;              /* [T][tiles][GR_REACH_TAPE_PLANES][32] float4 */
+  int64_t tape_stride;      /* env capacity of one tape step = 32 * tiles */
+  float* log_accum;         /* optional */
+  int32_t T;
+} GrReachRolloutIO;
+int gr_reach_rollout_fwd(const GrReachConfig* cfg, const GrReachState* st, const GrRandom* rng, const GrReachRolloutIO* io, void* stream);
 /* Reverse sweep over tape steps [t_begin, t_end): analytic backward of DroneDynamics.step/align, the controller (full 4x4
  * action Jacobian of the LV / PS outer loop, taken in forward mode while the step runs) and the action map; same GrBwdIO
  * contract as gr_step_bwd. */

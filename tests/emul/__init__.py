@@ -47,6 +47,7 @@ class EmulLib:
         self._l.emul_fill_rand.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32]
         self._l.emul_fill_startup_rand.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64]
         self._l.emul_reach_step_fwd.argtypes = [P(B.GrReachConfig), P(B.GrReachState), P(B.GrRandom), P(B.GrReachStepIO)]
+        self._l.emul_reach_rollout_fwd.argtypes = [P(B.GrReachConfig), P(B.GrReachState), P(B.GrRandom), P(B.GrReachRolloutIO)]
         self._l.emul_reach_reset.argtypes = [P(B.GrReachConfig), P(B.GrReachState), P(B.GrRandom), C.c_void_p, C.c_int, C.c_void_p]
         self._l.emul_reach_step_bwd.argtypes = [P(B.GrReachConfig), P(B.GrReachState), P(B.GrBwdIO)]
         self._l.emul_reach_fill_rand.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32]
@@ -77,6 +78,9 @@ class EmulLib:
 
     def gr_reach_step_fwd(self, cfg, st, rng, io, stream):
         return self._l.emul_reach_step_fwd(cfg, st, rng, io)
+
+    def gr_reach_rollout_fwd(self, cfg, st, rng, io, stream):
+        return self._l.emul_reach_rollout_fwd(cfg, st, rng, io)
 
     def gr_reach_reset(self, cfg, st, rng, mask, obs, stream):
         return self._l.emul_reach_reset(cfg, st, rng, mask, 0 if mask else 1, obs)

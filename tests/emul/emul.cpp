@@ -80,6 +80,14 @@ int emul_reach_step_fwd(const GrReachConfig* cfg, const GrReachState* st, const 
   return -100;
 }
 
+int emul_reach_rollout_fwd(const GrReachConfig* cfg, const GrReachState* st, const GrRandom* rng, const GrReachRolloutIO* io) {
+  const bool diff = io->loss || io->tape || io->loss_terms, philox = rng->rnd == nullptr;
+#define GO(a, b) if (diff == a && philox == b) { run_grid(st->num_envs, [&] { reach_rollout_fwd_kernel<a, b>(*cfg, *st, *rng, *io); }); return 0; }
+  GO(false, false) GO(false, true) GO(true, false) GO(true, true)
+#undef GO
+  return -100;
+}
+
 int emul_reach_reset(const GrReachConfig* cfg, const GrReachState* st, const GrRandom* rng, const uint8_t* mask, int mode, float* obs) {
   const GrRandom none{nullptr, 0, 0};
   const GrRandom& r = rng ? *rng : none;

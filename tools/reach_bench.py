@@ -74,8 +74,16 @@ def bench_window(cfg, Nb=16384, T=48, iters=20):
         env._bptt.backward_window()
     ms = time_graph(window, iters)
     ms_b = time_graph(lambda: env._bptt.backward_window(), iters)
+    acts_t = torch.stack(acts)
+
+    def window1():                      # the same window as ONE forward launch (gr_reach_rollout_fwd) + the sweep; bit-identical results
+        env.detach()
+        env.rollout(acts_t)
+        env._bptt.backward_window()
+    ms1 = time_graph(window1, iters)
     return {"window_ms": ms, "sweep_us": ms_b * 1e3, "env_steps_per_s": Nb * T / (ms * 1e-3), "T": T, "envs": Nb,
-            "sweep_gbps": Nb * T * (13 * 16 + 16) / (ms_b * 1e-3) / 1e9}
+            "sweep_gbps": Nb * T * (13 * 16 + 16) / (ms_b * 1e-3) / 1e9,
+            "one_launch_window_ms": ms1, "one_launch_env_steps_per_s": Nb * T / (ms1 * 1e-3)}
 
 
 def main():
