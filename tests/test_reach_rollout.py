@@ -112,3 +112,25 @@ def test_argument_errors(backend):
     cfg, (c, d), g = _twins(backend, "lv", 64, "dense")
     with pytest.raises(ValueError, match="needs an explicit rnd"):
         c.rollout(torch.zeros(3, 64, 4, device=c.device))
+
+
+@pytest.mark.gpu
+def test_full_size_window_equals_single_steps(cuda_lib):
+    """65,536 envs, LV mode, in-kernel Philox: a 12-step window == 12 steps, bit for bit (up to the stale-prefetch marks)."""
+    from generalizableracing_b200.config import ReachTargetCfg
+    N, T = 65536, 12
+    cfg = ReachTargetCfg.lv(decimation=1, is_differentiable_physics=False)
+    a, b = (ReachTargetVecEnv(cfg, N, seed=9) for _ in range(2))
+    for e in (a, b):
+        e.reset()
+        e.episode_length_buf = (torch.arange(N, dtype=torch.int32) * 13) % cfg.max_episode_length
+    g = torch.Generator(device="cuda").manual_seed(0)
+    acts = torch.randn(T, N, 4, device="cuda", generator=g) * 0.5
+    rew, dones = [], []
+    for t in range(T):
+        o, r, d, _ = a.step(acts[t])
+        rew.append(r.clone()); dones.append(d.bool().clone())
+    out = b.rollout(acts)
+    assert torch.equal(torch.stack(rew), out["reward"]) and torch.equal(torch.stack(dones), out["dones"]) and torch.equal(o, out["obs"])
+    _planes_equal_but_stale_mark(a, b)
+    assert int(out["dones"].sum()) > 1000

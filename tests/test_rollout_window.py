@@ -108,3 +108,27 @@ def test_argument_errors(backend):
     cfg, (c, d), g = _twins(backend, 1, 64, "dense")
     with pytest.raises(ValueError, match="needs an explicit rnd"):
         c.rollout(torch.zeros(3, 64, 4, device=c.device))
+
+
+@pytest.mark.gpu
+def test_full_size_window_equals_single_steps(cuda_lib):
+    """BASELINE C4 size (65,536 envs, complex track table, stats on, in-kernel Philox): a 12-step window == 12 steps, bit for bit."""
+    from generalizableracing_b200.track_gen import generate_track_table, racing_complex_cfg
+    N, T = 65536, 12
+    cfg, table = RacingCfg.for_stage(1), generate_track_table(racing_complex_cfg())
+    a, b = (RacingVecEnv(cfg, table, N, seed=42) for _ in range(2))
+    for e in (a, b):
+        e.reset()
+        e.episode_length_buf = (torch.arange(N, dtype=torch.int32) * 13) % cfg.max_episode_length
+    g = torch.Generator(device="cuda").manual_seed(0)
+    acts = torch.randn(T, N, 4, device="cuda", generator=g) * 0.5
+    rew, dones = [], []
+    for t in range(T):
+        o, r, d, _ = a.step(acts[t])
+        rew.append(r.clone()); dones.append(d.bool().clone())
+    out = b.rollout(acts)
+    assert torch.equal(torch.stack(rew), out["reward"]) and torch.equal(torch.stack(dones), out["dones"]) and torch.equal(o, out["obs"])
+    assert torch.equal(a.planes, b.planes)
+    assert int(out["dones"].sum()) > 1000
+    q = b.read_plane(L.PL_QUAT)
+    assert float((q.norm(dim=-1) - 1).abs().max()) < 1e-4
