@@ -348,6 +348,7 @@ def run_ours(args):
         torch.cuda.empty_cache()
         extra["torch_eager_gpu_baseline"] = torch_gpu_baseline(dev)
         cpu = cpu_baseline(sample_s=args.cpu_seconds)
+        extra["cpu_baseline_fwd_bwd_bptt"] = cpu_baseline_bptt()
 
     if rank == 0:
         line = {
@@ -378,7 +379,8 @@ def run_ours(args):
                                     "dynamics_only": extra["bptt_fwd_bwd_c3"]["env_steps_per_s"],
                                     "dynamics_only_one_launch_window": extra.get("bptt_fwd_bwd_c3_one_launch_window", {}).get("env_steps_per_s"),
                                     "training_iteration_with_policy": extra.get("bptt_training_c3", {}).get("fused_kernel_backward", {}).get("env_steps_per_s"),
-                                    "training_iteration_with_policy_log_every_20": extra.get("bptt_training_c3", {}).get("fused_kernel_backward_log_every_20", {}).get("env_steps_per_s")}
+                                    "training_iteration_with_policy_log_every_20": extra.get("bptt_training_c3", {}).get("fused_kernel_backward_log_every_20", {}).get("env_steps_per_s"),
+                                    "cpu_baseline": extra.get("cpu_baseline_fwd_bwd_bptt")}
         print(json.dumps(line))
 
 
@@ -747,6 +749,44 @@ def cpu_baseline(sample_s: float = 15.0, N: int = NUM_ENVS):
     return {"value": N * n / t_used, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{n} steps of the same C4 workload ({N} envs, STAGE {STAGE}) on the oracle (CPU torch port of the reference), "
                       f"{t_used:.1f} s, torch.set_num_threads({threads}), no_grad"}
+
+
+def cpu_baseline_bptt(N: int = 16384, H: int = 32, windows: int = 2):
+    """the reference CPU path for fwd+bwd -- torch.autograd through the oracle over one C3 window (16,384 envs, horizon 32,
+    loss = mean of the per-step losses), a bounded sample of `windows` windows after one warm-up window."""
+    from generalizableracing_b200 import layout as L_
+    from generalizableracing_b200.config import RacingCfg
+    from generalizableracing_b200.track_gen import generate_track_table, racing_complex_cfg
+    from oracle import racing_oracle as RO
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = RacingCfg.for_stage(STAGE, is_differentiable_physics=True)
+    g = torch.Generator().manual_seed(0)
+    srnd = torch.rand(N, L_.SRND_STRIDE, generator=g)
+    srnd[:, 12:] = torch.randn(N, 4, generator=g)
+    env = RO.OracleRacingEnv(cfg, generate_track_table(racing_complex_cfg()), N, srnd)
+
+    def draw():
+        r = torch.rand(N, L_.RND_STRIDE, generator=g)
+        r[:, :8] = torch.randn(N, 8, generator=g)
+        return r
+
+    env.reset(draw())
+    env.episode_length_buf[:] = torch.randint(0, cfg.max_episode_length, (N,), generator=g)
+    times = []
+    for w in range(windows + 1):
+        env.detach()
+        acts = [(torch.randn(N, 4, generator=g) * 0.5).requires_grad_(True) for _ in range(H)]
+        rs = [draw() for _ in range(H)]
+        t0 = time.perf_counter()
+        losses = [env.step(a, r)[4]["losses"] for a, r in zip(acts, rs)]
+        torch.stack(losses).mean().backward()
+        if w:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return {"value": N * H / dt, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_window": dt * 1e3,
+            "sample": f"{windows} windows of C3 ({N} envs x {H} steps, STAGE {STAGE}) on the oracle with torch.autograd (forward with tape + "
+                      f"backward of the mean loss w.r.t. the {H} action tensors), {threads} threads"}
 
 
 def run_reference(args):
