@@ -416,7 +416,10 @@ class RacingVecEnv:
             rng.rnd = rnd.data_ptr()
         elif self.rng_mode == "dense":
             raise ValueError("rng_mode='dense' needs an explicit rnd tensor every call")
+        step0 = self._step_count & 0xFFFFFFFF
         self._step_count += T
+        if self._ops is not None:
+            return self._rollout_ops(act, rnd, step0, record_obs)
         k = self._flip
         o = self._outs[k]
         self._flip = k ^ 1
@@ -451,6 +454,31 @@ class RacingVecEnv:
         ex["time_outs"], ex["terminated"] = out["time_outs"][-1], out["terminated"][-1]
         out["obs"] = o["obs"]
         if win is not None:
+            out["losses"], out["loss_terms"] = win.loss[t0:t0 + T], win.loss_terms[t0:t0 + T]
+            win.t += T
+        return out
+
+    def _rollout_ops(self, act, rnd, step0, record_obs):
+        win, T = self._bptt, act.shape[0]
+        if win is None:
+            r = torch.ops.gracing.rollout_fwd(self._op_handle, self.planes, act, rnd, step0, self._log_accum, record_obs)
+        else:
+            r = torch.ops.gracing.rollout_fwd_tape(self._op_handle, self.planes, act, rnd, step0, self._log_accum, win.tape, win.t, record_obs)
+        obs, critic, aux, reward, dones, terminated, time_out, obs_seq = r[:8]
+        self._state.launch_flags = self._launch_flags & ~B.GR_LAUNCH_PREFETCH
+        self._params_edited = True
+        self._last = o = dict(obs=obs, critic=critic, aux=aux)
+        out = {"reward": reward, "dones": dones.view(torch.bool), "terminated": terminated.view(torch.bool), "time_outs": time_out.view(torch.bool), "obs": obs}
+        if record_obs:
+            out["obs_seq"] = obs_seq
+        ex = self.extras
+        dict.pop(ex, "log", None)
+        ex["observations"] = self._obs_dict(o)
+        ex["time_outs"], ex["terminated"] = out["time_outs"][-1], out["terminated"][-1]
+        if win is not None:
+            t0 = win.t
+            win.loss[t0:t0 + T].copy_(r[8])
+            win.loss_terms[t0:t0 + T].copy_(r[9])
             out["losses"], out["loss_terms"] = win.loss[t0:t0 + T], win.loss_terms[t0:t0 + T]
             win.t += T
         return out

@@ -12,6 +12,7 @@ writes is an explicit operator argument (mutations are declared in the schema), 
                                  so ``extras["losses"].mean().backward()`` of the reference trainers
                                  (standalone/diff_rl/algorithms/bptt.py:38-44) keeps working
 ``gracing::step_bwd``            reverse sweep over tape steps ``[t_begin, t_end)`` -> ``grad_action``
+``gracing::rollout_fwd[_tape]``  T steps in one launch for actions known in advance (gr_rollout_fwd)
 ``gracing::reset``               ``_reset_idx`` (+ observations) of all / masked envs (:362-410)
 ``gracing::gae``                 ``RolloutStorage.compute_returns`` (rollout_storage.py:113-127), functional
 ===============================  =================================================================================
@@ -221,6 +222,82 @@ def _loss_backward(ctx, g_loss, g_token):
 step_loss.register_autograd(_loss_backward, setup_context=_loss_setup)
 
 
+def _launch_rollout(e, planes, actions, rnd, step, log_accum, record_obs, tape, t0):
+    N = e.num_envs
+    if actions.dim() != 3 or tuple(actions.shape[1:]) != (N, L.NUM_ACTIONS) or actions.shape[0] < 1:
+        raise ValueError(f"Invalid actions shape, expected: (T, {N}, {L.NUM_ACTIONS}), received: {tuple(actions.shape)}.")
+    _f32c(actions, "actions")
+    T, dev = actions.shape[0], planes.device
+    f = dict(device=dev, dtype=torch.float32)
+    u8 = dict(device=dev, dtype=torch.uint8)
+    obs, critic, aux = torch.empty(N, L.OBS_DIM, **f), torch.empty(N, L.OBS_DIM, **f), torch.empty(N, 1, **f)
+    reward, dones, terminated, time_out = torch.empty(T, N, **f), torch.empty(T, N, **u8), torch.empty(T, N, **u8), torch.empty(T, N, **u8)
+    obs_seq = torch.empty(T if record_obs else 0, N, L.OBS_DIM, **f)
+    io = B.GrRolloutIO()
+    io.actions, io.T = actions.data_ptr(), T
+    io.obs_out, io.critic_obs_out, io.aux_out = obs.data_ptr(), critic.data_ptr(), aux.data_ptr()
+    io.reward, io.dones, io.terminated, io.time_out = reward.data_ptr(), dones.data_ptr(), terminated.data_ptr(), time_out.data_ptr()
+    if record_obs:
+        io.obs_seq = obs_seq.data_ptr()
+    io.log_accum = log_accum.data_ptr()
+    outs = (obs, critic, aux, reward, dones, terminated, time_out, obs_seq)
+    if tape is not None:
+        if not 0 <= t0 <= t0 + T <= tape.shape[0]:
+            raise RuntimeError(f"BPTT horizon exceeded the tape capacity ({tape.shape[0]} steps): call env.unwrapped.detach() "
+                               "between windows or construct the env with a larger bptt_horizon")
+        loss, loss_terms = torch.empty(T, N, **f), torch.empty(T, N, e._bptt._terms, **f)
+        io.loss, io.loss_terms, io.tape, io.tape_stride = loss.data_ptr(), loss_terms.data_ptr(), tape[t0].data_ptr(), e._stride
+        outs = outs + (loss, loss_terms)
+    rng = B.GrRandom(None, e.seed, step & 0xFFFFFFFF)
+    if rnd is not None:
+        if tuple(rnd.shape) != (T, N, L.RND_STRIDE):
+            raise ValueError(f"gracing: rnd must be [{T}, {N}, {L.RND_STRIDE}]")
+        rng.rnd = _f32c(rnd, "rnd").data_ptr()
+    elif e.rng_mode == "dense":
+        raise ValueError("gracing: rng_mode='dense' needs an explicit rnd tensor every call")
+    st = _state_for(e, planes)
+    B.check(e._lib.gr_rollout_fwd(C.byref(e._gcfg), C.byref(e._track), C.byref(st), C.byref(rng), C.byref(io), _stream(planes)), "gr_rollout_fwd")
+    return outs
+
+
+_T8 = Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]
+_T10 = Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]
+
+
+@torch.library.custom_op("gracing::rollout_fwd", mutates_args=("planes", "log_accum"))
+def rollout_fwd(env: int, planes: Tensor, actions: Tensor, rnd: Optional[Tensor], step: int, log_accum: Tensor, record_obs: bool = False) -> _T8:
+    """T steps in one launch for ``actions`` [T,N,4] known in advance -> (obs[N,16], critic_obs[N,16], aux[N,1] after the last step,
+    reward[T,N], dones / terminated / time_out [T,N] u8, obs_seq[T,N,16] | [0,N,16])."""
+    e = _env(env)
+    if e._bptt is not None:
+        raise RuntimeError("gracing::rollout_fwd on a differentiable env: use gracing::rollout_fwd_tape")
+    return _launch_rollout(e, planes, actions, rnd, step, log_accum, record_obs, None, 0)
+
+
+@rollout_fwd.register_fake
+def _(env, planes, actions, rnd, step, log_accum, record_obs=False):
+    T, N = actions.shape[0], actions.shape[1]
+    f, u = actions.new_empty, lambda *sh: actions.new_empty(*sh, dtype=torch.uint8)
+    return (f(N, L.OBS_DIM), f(N, L.OBS_DIM), f(N, 1), f(T, N), u(T, N), u(T, N), u(T, N), f(T if record_obs else 0, N, L.OBS_DIM))
+
+
+@torch.library.custom_op("gracing::rollout_fwd_tape", mutates_args=("planes", "log_accum", "tape"))
+def rollout_fwd_tape(env: int, planes: Tensor, actions: Tensor, rnd: Optional[Tensor], step: int, log_accum: Tensor, tape: Tensor, t0: int,
+                     record_obs: bool = False) -> _T10:
+    """The same with differentiable physics: tape steps ``[t0, t0 + T)`` are written, + (loss[T,N], loss_terms[T,N,3])."""
+    e = _env(env)
+    if e._bptt is None:
+        raise RuntimeError("gracing::rollout_fwd_tape needs cfg.is_differentiable_physics")
+    return _launch_rollout(e, planes, actions, rnd, step, log_accum, record_obs, tape, t0)
+
+
+@rollout_fwd_tape.register_fake
+def _(env, planes, actions, rnd, step, log_accum, tape, t0, record_obs=False):
+    T, N = actions.shape[0], actions.shape[1]
+    f, u = actions.new_empty, lambda *sh: actions.new_empty(*sh, dtype=torch.uint8)
+    return (f(N, L.OBS_DIM), f(N, L.OBS_DIM), f(N, 1), f(T, N), u(T, N), u(T, N), u(T, N), f(T if record_obs else 0, N, L.OBS_DIM), f(T, N), f(T, N, 3))
+
+
 @torch.library.custom_op("gracing::reset", mutates_args=("planes",))
 def reset(env: int, planes: Tensor, mask: Optional[Tensor], rnd: Optional[Tensor], step: int) -> Tuple[Tensor, Tensor, Tensor]:
     """``_reset_idx`` of the envs with ``mask != 0`` (None: all) followed by the observation pass ->
@@ -284,4 +361,4 @@ def _(rewards, values, dones, last_values, gamma, lam, normalize=True):
     return torch.empty_like(rewards), torch.empty_like(rewards), rewards.new_empty(3, dtype=torch.float64)
 
 
-OPERATORS = ("step_fwd", "step_fwd_tape", "step_loss", "step_bwd", "reset", "gae")
+OPERATORS = ("step_fwd", "step_fwd_tape", "step_loss", "step_bwd", "rollout_fwd", "rollout_fwd_tape", "reset", "gae")

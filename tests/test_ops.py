@@ -26,6 +26,8 @@ def test_operators_are_registered_with_mutation_schemas():
         "step_fwd_tape": ("Tensor(a1!) planes", "Tensor(a6!) tape"),
         "step_loss": (),
         "step_bwd": ("Tensor(a5!) adjoint", "Tensor(a6!) grad_action"),
+        "rollout_fwd": ("Tensor(a1!) planes", "Tensor(a5!) log_accum"),
+        "rollout_fwd_tape": ("Tensor(a1!) planes", "Tensor(a6!) tape"),
         "reset": ("Tensor(a1!) planes",),
         "gae": (),
     }
@@ -205,3 +207,33 @@ def test_gae_operator_equals_storage_kernel(cuda_lib, T, N, normalize):
         assert PC.rel_err(ref_adv, adv) < 5e-5
     torch.library.opcheck(torch.ops.gracing.gae.default, (sto.rewards, sto.values, sto.dones, last, 0.99, 0.95, normalize),
                           test_utils=("test_schema", "test_faketensor"))
+
+
+@pytest.mark.parametrize("backend", backend_params(), indirect=True)
+@pytest.mark.parametrize("diff", [False, True])
+def test_rollout_window_through_the_operators(backend, monkeypatch, diff):
+    N, T = 96, 20
+    kw = dict(stage=0 if diff else 1, N=N, seed=13, diff=diff, horizon=T if diff else 0)
+    _, _, _, a, g = _pair(backend, monkeypatch, False, **kw)
+    _, _, _, b, _ = _pair(backend, monkeypatch, True, **kw)
+    dev = a.device
+    r0 = PC.draw_rnd(N, g).to(dev)
+    a.reset(r0)
+    b.reset(r0)
+    acts = (torch.randn(T, N, 4, generator=g) * 0.5).to(dev)
+    rnd = torch.stack([PC.draw_rnd(N, g) for _ in range(T)]).to(dev)
+    oa, ob = a.rollout(acts, rnd, record_obs=True), b.rollout(acts, rnd, record_obs=True)
+    assert set(oa) == set(ob)
+    for k in oa:
+        assert torch.equal(oa[k], ob[k]), k
+    assert torch.equal(a.planes, b.planes)
+    if diff:
+        assert torch.equal(a._bptt.tape[:T], b._bptt.tape[:T]) and a._bptt.t == b._bptt.t == T
+        assert torch.equal(a._bptt.backward_window().clone(), b._bptt.backward_window().clone())
+    utils = ("test_schema", "test_faketensor")
+    if diff:
+        b.detach()
+        torch.library.opcheck(torch.ops.gracing.rollout_fwd_tape.default,
+                              (b._op_handle, b.planes.clone(), acts, rnd, 3, b._log_accum.clone(), b._bptt.tape.clone(), 0, True), test_utils=utils)
+    else:
+        torch.library.opcheck(torch.ops.gracing.rollout_fwd.default, (b._op_handle, b.planes.clone(), acts, rnd, 3, b._log_accum.clone(), True), test_utils=utils)
