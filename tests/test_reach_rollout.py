@@ -133,4 +133,4 @@ def test_full_size_window_equals_single_steps(cuda_lib):
     out = b.rollout(acts)
     assert torch.equal(torch.stack(rew), out["reward"]) and torch.equal(torch.stack(dones), out["dones"]) and torch.equal(o, out["obs"])
     _planes_equal_but_stale_mark(a, b)
-    assert int(out["dones"].sum()) > 1000
+    assert int(out["dones"].sum()) > 100
