@@ -95,6 +95,30 @@ def test_argument_errors_are_reported_without_launch(lib):
     assert lib.gr_reach_reset(C.byref(rcfg), C.byref(B.GrReachState(8, 32, 8, 0)), C.byref(rng), None, None, None) == -3     # alignment
     rcfg.controller = 7
     assert lib.gr_reach_reset(C.byref(rcfg), C.byref(rst), C.byref(rng), None, None, None) == -4                               # GR_ERR_CONFIG
+    # multi-step window entry points
+    assert lib.gr_rollout_fwd(None, None, None, None, None, None) == -1
+    assert lib.gr_reach_rollout_fwd(None, None, None, None, None) == -1
+    rcfg = make_gr_reach_config(ReachTargetCfg.lv())
+    rio = B.GrReachRolloutIO()
+    assert lib.gr_reach_rollout_fwd(C.byref(rcfg), C.byref(rst), C.byref(rng), C.byref(rio), None) == -1                     # no actions / obs_out
+    rio.actions, rio.obs_out, rio.T = 16, 16, 0
+    assert lib.gr_reach_rollout_fwd(C.byref(rcfg), C.byref(rst), C.byref(rng), C.byref(rio), None) == -2                     # T < 1
+    rio.T, rio.actions = 4, 8
+    assert lib.gr_reach_rollout_fwd(C.byref(rcfg), C.byref(rst), C.byref(rng), C.byref(rio), None) == -3                     # alignment
+    rio.actions, rio.tape, rio.tape_stride = 16, 16, 8
+    assert lib.gr_reach_rollout_fwd(C.byref(rcfg), C.byref(rst), C.byref(rng), C.byref(rio), None) == -2                     # tape stride < envs
+    from generalizableracing_b200.config import RacingCfg
+    from generalizableracing_b200.env import make_gr_config
+    gcfg, trk = make_gr_config(RacingCfg.for_stage(1)), B.GrTrack(16, 2, 3, 4)
+    gst = B.GrState(16, 32, 8, L_.NUM_PLANES, 0, 1, 0, 0, 16)
+    io = B.GrRolloutIO()
+    assert lib.gr_rollout_fwd(C.byref(gcfg), C.byref(trk), C.byref(gst), C.byref(rng), C.byref(io), None) == -1              # no actions / obs_out
+    io.actions, io.obs_out, io.T = 16, 16, 0
+    assert lib.gr_rollout_fwd(C.byref(gcfg), C.byref(trk), C.byref(gst), C.byref(rng), C.byref(io), None) == -2              # T < 1
+    io.T, io.obs_out = 3, 8
+    assert lib.gr_rollout_fwd(C.byref(gcfg), C.byref(trk), C.byref(gst), C.byref(rng), C.byref(io), None) == -3              # alignment
+    io.obs_out, io.tape, io.tape_stride = 16, 16, 40
+    assert lib.gr_rollout_fwd(C.byref(gcfg), C.byref(trk), C.byref(gst), C.byref(rng), C.byref(io), None) == -2              # tape stride not a tile multiple
     pipe = C.c_void_p()
     assert lib.gr_host_pipe_create(64, 2, None, None) == -1
     assert lib.gr_host_pipe_create(0, 2, None, C.byref(pipe)) == -2
