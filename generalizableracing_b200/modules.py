@@ -159,3 +159,55 @@ class ActorCriticRecurrent(ActorCritic):
 
     def get_hidden_states(self):
         return self.memory_a.hidden_states, self.memory_c.hidden_states
+
+
+class EmpiricalNormalization(nn.Module):
+    """rsl_rl.modules.EmpiricalNormalization (third-party, rsl-rl-lib 2.x; restated from its published algorithm): running
+    mean / variance of the observations seen in training mode, batched Welford merge per call, ``(x - mean) / (std + eps)``.
+    Used by OnPolicyRunner when ``empirical_normalization`` is set (on_policy_runner.py:67-73,151-153).  The ``until`` bound is
+    checked against a host-side mirror of ``count`` so that the rollout loop stays free of device->host reads."""
+
+    def __init__(self, shape, eps: float = 1e-2, until=None):
+        super().__init__()
+        self.eps = eps
+        self.until = until
+        self.register_buffer("_mean", torch.zeros(shape).unsqueeze(0))
+        self.register_buffer("_var", torch.ones(shape).unsqueeze(0))
+        self.register_buffer("_std", torch.ones(shape).unsqueeze(0))
+        self.register_buffer("count", torch.tensor(0, dtype=torch.long))
+        self._count_host = 0
+
+    @property
+    def mean(self):
+        return self._mean.squeeze(0).clone()
+
+    @property
+    def std(self):
+        return self._std.squeeze(0).clone()
+
+    def forward(self, x):
+        if self.training:
+            self.update(x)
+        return (x - self._mean) / (self._std + self.eps)
+
+    @torch.no_grad()
+    def update(self, x):
+        if self.until is not None and self._count_host >= self.until:
+            return
+        count_x = x.shape[0]
+        self._count_host += count_x
+        self.count += count_x
+        rate = count_x / self._count_host
+        var_x = torch.var(x, dim=0, unbiased=False, keepdim=True)
+        mean_x = torch.mean(x, dim=0, keepdim=True)
+        delta_mean = mean_x - self._mean
+        self._mean += rate * delta_mean
+        self._var += rate * (var_x - self._var + delta_mean * (mean_x - self._mean))
+        self._std = torch.sqrt(self._var)
+
+    def inverse(self, y):
+        return y * (self._std + self.eps) + self._mean
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._count_host = int(self.count)

@@ -43,10 +43,17 @@ class OnPolicyRunner:
         self.alg = PPO(policy, env=self.env, device=self.device, **self.alg_cfg)
         self.num_steps_per_env = self.cfg["num_steps_per_env"]
         self.save_interval = self.cfg.get("save_interval", 50)
-        if self.cfg.get("empirical_normalization", False):
-            raise NotImplementedError("empirical_normalization=False in the racing cfg (QD/agents/rsl_rl_ppo_cfg.py:21)")
-        self.obs_normalizer = torch.nn.Identity()
-        self.privileged_obs_normalizer = torch.nn.Identity()
+        # on_policy_runner.py:67-73 (False in the racing cfg, QD/agents/rsl_rl_ppo_cfg.py:21)
+        self.empirical_normalization = bool(self.cfg.get("empirical_normalization", False))
+        if self.empirical_normalization:
+            if self.cfg.get("fused_collection", False):
+                raise ValueError("fused_collection evaluates the policy on the raw observations inside the kernel: not with empirical_normalization")
+            from ..modules import EmpiricalNormalization
+            self.obs_normalizer = EmpiricalNormalization(shape=[num_obs], until=1.0e8).to(self.device)
+            self.privileged_obs_normalizer = EmpiricalNormalization(shape=[num_privileged_obs], until=1.0e8).to(self.device)
+        else:
+            self.obs_normalizer = torch.nn.Identity()
+            self.privileged_obs_normalizer = torch.nn.Identity()
         self.alg.init_storage(self.training_type, self.env.num_envs, self.num_steps_per_env, [num_obs], [num_privileged_obs], [self.env.num_actions])
         # opt-in: the whole rollout loop as one launch (collect.py / csrc/ppo_collect.cu); policy inference on the tensor cores
         self.collector = None
@@ -61,9 +68,13 @@ class OnPolicyRunner:
 
     def train_mode(self):
         self.alg.policy.train()
+        self.obs_normalizer.train()
+        self.privileged_obs_normalizer.train()
 
     def eval_mode(self):
         self.alg.policy.eval()
+        self.obs_normalizer.eval()
+        self.privileged_obs_normalizer.eval()
 
     def learn(self, num_learning_iterations: int, init_at_random_ep_len: bool = False):
         rank, world = D.world()
@@ -94,7 +105,8 @@ class OnPolicyRunner:
                 for _ in range(self.num_steps_per_env if self.collector is None else 0):
                     actions = self.alg.act(obs, privileged_obs)
                     obs, rewards, dones, infos = self.env.step(actions)
-                    privileged_obs = infos["observations"][self.privileged_obs_type] if self.privileged_obs_type else obs
+                    obs = self.obs_normalizer(obs)                       # on_policy_runner.py:151-155
+                    privileged_obs = self.privileged_obs_normalizer(infos["observations"][self.privileged_obs_type]) if self.privileged_obs_type else obs
                     self.alg.process_env_step(rewards, dones, infos)
                     # episode book keeping (on_policy_runner.py:167-173) without host synchronisation
                     cur_reward_sum += rewards
@@ -150,13 +162,20 @@ class OnPolicyRunner:
         # address) would race on it.  Checkpoints therefore hold independent copies.
         opt = self.alg.optimizer.state_dict()
         opt["state"] = {k: {n: (v.detach().clone() if torch.is_tensor(v) else v) for n, v in st.items()} for k, st in opt["state"].items()}
-        torch.save({"model_state_dict": self.alg.policy.state_dict(), "optimizer_state_dict": opt,
-                    "iter": self.current_learning_iteration, "infos": infos}, path)
+        saved = {"model_state_dict": self.alg.policy.state_dict(), "optimizer_state_dict": opt,
+                 "iter": self.current_learning_iteration, "infos": infos}
+        if self.empirical_normalization:
+            saved["obs_norm_state_dict"] = self.obs_normalizer.state_dict()
+            saved["privileged_obs_norm_state_dict"] = self.privileged_obs_normalizer.state_dict()
+        torch.save(saved, path)
 
     def load(self, path, load_optimizer=True):
         loaded = torch.load(path, map_location=self.device, weights_only=False)
         self.alg.close()               # a captured update graph aliases the optimizer state: rebuild it from what is loaded
         self.alg.policy.load_state_dict(loaded["model_state_dict"])
+        if self.empirical_normalization:
+            self.obs_normalizer.load_state_dict(loaded["obs_norm_state_dict"])
+            self.privileged_obs_normalizer.load_state_dict(loaded["privileged_obs_norm_state_dict"])
         if load_optimizer:
             self.alg.optimizer.load_state_dict(loaded["optimizer_state_dict"])
         self.current_learning_iteration = loaded["iter"]
@@ -166,4 +185,8 @@ class OnPolicyRunner:
         self.eval_mode()
         if device is not None:
             self.alg.policy.to(device)
+        if self.empirical_normalization:                 # on_policy_runner.py:329-332
+            if device is not None:
+                self.obs_normalizer.to(device)
+            return lambda x: self.alg.policy.act_inference(self.obs_normalizer(x))
         return self.alg.policy.act_inference
