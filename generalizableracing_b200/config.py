@@ -264,7 +264,7 @@ class ReachTargetCfg:
     def action_scale(self) -> Tuple[float, float, float, float]:
         # QD/mdp/diff_action.py:257-275 ("medium")
         if self.controller == "CTBRController":
-            half = self.mass * self.gravity * self.max_thrust_weight_ratio / 2.0
+            half = self._half_max_thrust()
             return (half, self.body_rate_bound, self.body_rate_bound, self.body_rate_bound)
         b = self.lin_vel_bound if self.controller == "LVController" else self.pos_bound
         return (3.1415926, b, b, b)
@@ -272,8 +272,14 @@ class ReachTargetCfg:
     @property
     def action_offset(self) -> Tuple[float, float, float, float]:
         if self.controller == "CTBRController":
-            return (self.mass * self.gravity * self.max_thrust_weight_ratio / 2.0, 0.0, 0.0, 0.0)
+            return (self._half_max_thrust(), 0.0, 0.0, 0.0)
         return (0.0, 0.0, 0.0, 0.0)
+
+    def _half_max_thrust(self) -> float:
+        """m g ratio / 2 with the reference's fp32 roundings (QD/mdp/diff_action.py:56,262: an fp32 mass tensor times python floats)."""
+        import numpy as np
+        weight = np.float32(self.mass) * np.float32(abs(self.gravity))
+        return float(np.float32(weight * np.float32(self.max_thrust_weight_ratio)) / np.float32(2.0))
 
     def to_dict(self):
         return asdict(self)

@@ -159,9 +159,11 @@ class CommandManager:
 
     def compute(self, dt):
         for term in self._terms.values():
-            # recorded for the random-stream replay only (how many envs _update_command will draw noise for)
-            term_pos = term.gate_pose_gt_w[:, :3] - term.robot.data.root_state_w[:, :3]
-            self.last_achieved = torch.norm(term_pos, dim=-1) < term.cfg.update_threshold
+            # recorded for the random-stream replay only (which envs the term is about to draw noise / new targets for)
+            if hasattr(term, "gate_pose_gt_w"):
+                term_pos = term.gate_pose_gt_w[:, :3] - term.robot.data.root_state_w[:, :3]
+                self.last_achieved = torch.norm(term_pos, dim=-1) < term.cfg.update_threshold
+            self.last_timer_ids = ((term.time_left - dt) <= 0.0).nonzero().flatten()
             term.compute(dt)
 
     def reset(self, env_ids=None):
@@ -306,8 +308,9 @@ def quat_unique(q):
 
 
 def compute_pose_error(t01, q01, t02, q02, rot_error_type="axis_angle"):
-    # [isaac] position part only: the reference call site (QD/mdp/commands.py:247-257) uses nothing else
-    return t02 - t01, None
+    # [isaac] position part only: the racing call site (QD/mdp/commands.py:247-257) uses nothing else, the reach one (:98-108)
+    # only logs the norm of the rotation part ("orientation_error", not an input of any term)
+    return t02 - t01, torch.zeros_like(t01)
 
 
 class ManagerBasedRLEnvBase:
@@ -339,6 +342,7 @@ class RobotData:
     root_lin_vel_b = property(lambda s: M.quat_rotate_inverse(s.root_quat_w, s.root_lin_vel_w))
     root_com_lin_vel_b = root_lin_vel_b
     root_ang_vel_b = property(lambda s: M.quat_rotate_inverse(s.root_quat_w, s.root_ang_vel_w))
+    root_vel_w = property(lambda s: torch.cat([s.root_lin_vel_w, s.root_ang_vel_w], dim=-1))
 
 
 class Robot:
@@ -364,6 +368,7 @@ class Robot:
         self.data.root_lin_vel_w[env_ids] = vel[:, :3]
         self.data.root_ang_vel_w[env_ids] = vel[:, 3:]
         self.data.body_ang_acc_w[env_ids] = 0.0            # closure A.1: accelerations restart at zero
+        self.data.body_lin_acc_w[env_ids] = 0.0
 
 
 class Terrain:
@@ -446,6 +451,7 @@ class Sim:
         data.root_lin_vel_w = nom[:, 7:10].clone()
         data.root_ang_vel_w = nom[:, 10:13].clone()
         data.body_ang_acc_w = M.quat_rotate(data.root_quat_w, alpha).unsqueeze(1)
+        data.body_lin_acc_w = term.a.detach().clone().unsqueeze(1)
 
 
 # ----------------------------------------------------------------------------------------------- loading
@@ -626,6 +632,128 @@ def make_reference_env(cfg, table, num_envs, startup_rnd, seed):
     srnd[:, L_.SRND_THRUST_DELAY:L_.SRND_THRUST_DELAY + 1] = torch.rand(n, 1)
     srnd[:, L_.SRND_TORQUE_DELAY:L_.SRND_TORQUE_DELAY + 3] = torch.rand(n, 3)
     return env, srnd
+
+
+# ----------------------------------------------------------------------------------------------- reach-target tasks
+class PlaneTerrain:
+    def __init__(self, n):
+        self.env_origins = torch.zeros(n, 3)            # reach_oracle R.3
+
+
+def reset_root_state_uniform(env, env_ids, pose_range, velocity_range, asset_cfg=SceneEntityCfg("robot")):
+    """[isaac] omni.isaac.lab.envs.mdp.reset_root_state_uniform."""
+    asset = env.scene[asset_cfg.name]
+    root_states = asset.data.default_root_state[env_ids].clone()
+    ranges = torch.tensor([pose_range.get(k, (0.0, 0.0)) for k in ["x", "y", "z", "roll", "pitch", "yaw"]])
+    rs = sample_uniform(ranges[:, 0], ranges[:, 1], (len(env_ids), 6), device="cpu")
+    positions = root_states[:, 0:3] + env.scene.env_origins[env_ids] + rs[:, 0:3]
+    orientations = M.quat_mul(root_states[:, 3:7], M.quat_from_euler_xyz(rs[:, 3], rs[:, 4], rs[:, 5]))
+    ranges = torch.tensor([velocity_range.get(k, (0.0, 0.0)) for k in ["x", "y", "z", "roll", "pitch", "yaw"]])
+    rs = sample_uniform(ranges[:, 0], ranges[:, 1], (len(env_ids), 6), device="cpu")
+    velocities = root_states[:, 7:13] + rs
+    asset.write_root_link_pose_to_sim(torch.cat([positions, orientations], dim=-1), env_ids=env_ids)
+    asset.write_root_com_velocity_to_sim(velocities, env_ids=env_ids)
+
+
+def make_reference_reach_env(cfg, num_envs, seed):
+    """The reference env of DiffLab-Quadcopter-{LV,CTBR}-ReachTarget (QD/reach_target_lv_env.py, reach_target_ctbr_env.py) over
+    the closure simulator, with the substitutions R.1-R.3 of oracle/reach_oracle.py.  [isaac] terms: base_lin_vel, base_ang_vel,
+    last_action, action_rate_l2, body_lin_acc_l2, is_terminated, time_out, reset_root_state_uniform."""
+    ns = load()
+    n = num_envs
+    NS = types.SimpleNamespace
+    env = object.__new__(ns.Env)
+    env.cfg = NS(sim=NS(dt=cfg.sim_dt, gravity=(0.0, 0.0, -cfg.gravity), render_interval=cfg.decimation), decimation=cfg.decimation,
+                 episode_length_s=cfg.episode_length_s, is_differentiable_physics=True, rerender_on_reset=False)
+    robot = Robot(n, cfg.mass, cfg.default_root_pos)
+    env.scene = Scene(n, robot, PlaneTerrain(n))
+    env.sim = Sim(env)
+    env.extras = {}
+    env._sim_step_counter = 0
+    env.common_step_counter = 0
+    env.episode_length_buf = torch.zeros(n, dtype=torch.long)
+    env.recorder_manager = Recorder()
+    lo, hi = cfg.cmd_lo, cfg.cmd_hi
+    cmd_cfg = NS(asset_name="robot", resampling_time_range=(cfg.resampling_time, cfg.resampling_time), debug_vis=False, make_quat_unique=False,
+                 ranges=NS(pos_x=(lo[0], hi[0]), pos_y=(lo[1], hi[1]), pos_z=(lo[2], hi[2]), roll=(0.0, 0.0), pitch=(0.0, 0.0), yaw=(0.0, 0.0)))
+    env.command_manager = CommandManager({}, env)
+    env.command_manager._terms["desired_pos_b"] = ns.commands.UniformWorldPoseCommand(cmd_cfg, env)
+    if cfg.controller == "CTBRController":
+        ctrl_cfg = RM.ctbr_cfg(cfg)
+        ctrl_cfg.class_type = ns.CTBRController
+    else:
+        ctrl_cfg = RM.outer_loop_cfg(cfg)
+        ref = RM.load()
+        ctrl_cfg.class_type = ref.LVController if cfg.controller == "LVController" else ref.PSController
+    b = cfg.lin_vel_bound
+    act_cfg = NS(class_type=ns.diff_action.DiffActions, asset_name="robot", rotor_names="m.*_prop", command_type=cfg.controller,
+                 controller_cfg=ctrl_cfg, gravity=9.81, random_drag=cfg.random_drag, action_lag=cfg.action_lag, sim2real_test=cfg.sim2real_test,
+                 max_thrust_weight_ratio=cfg.max_thrust_weight_ratio, lin_vel_bound=(-b, b), pos_bound=(-cfg.pos_bound, cfg.pos_bound))
+    torch.manual_seed(seed)
+    env.action_manager = ns.DiffActionManager({"force_torque": act_cfg}, env)
+    T = _TermCfg
+    R, O, Te, Lo = ns.rewards, ns.observation, ns.termination, ns.losses
+    data = robot.data
+    last = T(O.modified_last_action, {"action_name": "force_torque"}) if cfg.last_action_modified else T(lambda e, action_name: e.action_manager.action, {"action_name": "force_torque"})
+    env.observation_manager = ObservationManager({"policy": {
+        "base_lin_vel": T(lambda e: data.root_lin_vel_b), "base_ang_vel": T(lambda e: data.root_ang_vel_b), "last_action": last,
+        "base_orientation": T(O.base_orientation_q), "desired_pos_b": T(O.desired_position_b, {"command_name": "desired_pos_b"})}}, env)
+    terms = {"time_out": T(time_out, time_out=True)}
+    if cfg.term_out_of_bound:
+        terms["outofbound"] = T(Te.out_of_bound, {"bounds": (cfg.oob_lo, cfg.oob_hi)})               # R.2
+    env.termination_manager = TerminationManager(terms, env)
+    w = cfg.w_reward
+    body = SceneEntityCfg("robot", body_names="body")
+    rew = {"move_towards": T(R.target_reward, {"command_name": "desired_pos_b"}, w[0]), "orientation_reward": T(R.orientation_reward, {}, w[1]),
+           "move_in_dir": T(R.move_in_dir, {"threshold": cfg.move_in_dir_threshold}, w[2]),
+           "action_rate": T(lambda e: torch.sum(torch.square(e.action_manager.action - e.action_manager.prev_action), dim=1), {}, w[3]),
+           "reach_target": T(R.reach_target, {"threshold": cfg.reach_threshold}, w[4]), "smooth_ang_vel": T(R.ang_vel_reward, {}, w[5]),
+           "smooth_lin_acc": T(lambda e: torch.sum(torch.norm(data.body_lin_acc_w[:, body.body_ids, :], dim=-1), dim=1), {}, w[6]),
+           "smooth_ang_acc": T(R.body_ang_acc_l2, {"robot_cfg": body}, w[7]),
+           "early_termination": T(lambda e: e.termination_manager.terminated.float(), {}, w[8]),
+           "hover_state": T(R.hover_state, {"threshold": cfg.hover_threshold, "ratio": cfg.hover_ratio}, w[9])}
+    env.reward_manager = RewardManager(rew, env)
+
+    def loss_term(func, weight, params=None):
+        t = ns.LossTermCfg()
+        t.func, t.weight, t.params, t.use_diff_states, t.use_action = func, float(weight), dict(params or {}), True, False
+        return t
+    wl = cfg.w_loss
+    env.loss_manager = ns.LossManager({"move_towards_goal": loss_term(Lo.target_diff, wl[0], {"command_name": "desired_pos_b"}),
+                                       "orientation_tracking": loss_term(Lo.orientation_diff, wl[1]),
+                                       "move_in_dir": loss_term(Lo.move_in_dir_diff, wl[2], {"command_name": "desired_pos_b", "threshold": cfg.loss_dir_threshold}),
+                                       "smooth_vel": loss_term(Lo.smooth_vel_diff, wl[3], {"ratio": cfg.loss_smooth_ratio})}, env)
+    env.curriculum_manager = CurriculumManager({}, env)
+    pose = dict(zip(("x", "y", "z", "roll", "pitch", "yaw"), zip(cfg.reset_lo, cfg.reset_hi)))
+    env.event_manager = EventManager({"reset": {"reset_base": T(reset_root_state_uniform, {"pose_range": pose, "velocity_range": {}})}}, env)
+    return env
+
+
+def replay_reach_reset_draws(rnd, ids, random_drag):
+    """The global-generator calls of one reference ``_reset_idx(ids)`` of a reach-target env, into the oracle's REACH_RND_* columns."""
+    n = len(ids)
+    if n == 0:
+        return
+    rnd[ids, L_.REACH_RND_RESET_POSE:L_.REACH_RND_RESET_POSE + 6] = torch.rand(n, 6)     # [isaac] reset_root_state_uniform: pose
+    torch.rand(n, 6)                                                                     # velocity ranges (all zero)
+    if random_drag:                                                                      # droneDynamics.py:52-57
+        rnd[ids, L_.REACH_RND_Z_DRAG] = torch.rand(n)
+        rnd[ids, L_.REACH_RND_DRAG2:L_.REACH_RND_DRAG2 + 3] = torch.rand(n, 3)
+        rnd[ids, L_.REACH_RND_DRAG1:L_.REACH_RND_DRAG1 + 3] = torch.rand(n, 3)
+    rnd[ids, L_.REACH_RND_THR_ERR] = torch.randn(n)                                      # diff_action.py:233
+    replay_reach_command_draws(rnd, ids, L_.REACH_RND_CMD)
+
+
+def replay_reach_command_draws(rnd, ids, col):
+    """[isaac] CommandTerm._resample (time_left) then UniformWorldPoseCommand._resample_command (QD/mdp/commands.py:113-126)."""
+    n = len(ids)
+    if n == 0:
+        return
+    torch.empty(n).uniform_(10.0, 10.0)
+    for k in range(3):
+        rnd[ids, col + k] = torch.empty(n).uniform_()
+    for k in range(3):
+        torch.empty(n).uniform_()                                                        # roll / pitch / yaw ranges (0, 0)
 
 
 def replay_reset_draws(rnd, ids, add_noise):
