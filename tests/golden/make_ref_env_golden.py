@@ -5,7 +5,8 @@ The vectors come from the reference's OWN env step (ManagerBasedDiffRLEnv.step /
 the MDP term functions, unmodified, over the PhysX-free closure simulator of oracle/ref_closure.py) -- the oracle is not
 involved.  Stored per scenario: the inputs (startup draws, actions, the reference's random draws laid out in the rnd[N, 52]
 slots of generalizableracing_b200/layout.py, positions written before a step to put drones on gates) and the reference's outputs
-and state after every step, so that tests/test_ref_env_golden.py can replay them through the oracle (CPU) and through the
+and state after every step (plus one differentiable 16-step window with the reference's autograd gradient of the mean loss with
+respect to every action), so that tests/test_ref_env_golden.py / test_window_gradient_reference_golden.py can replay them through the oracle (CPU) and through the
 kernels (B200) where the reference tree is absent.
 """
 import os
@@ -85,8 +86,61 @@ def scenario(stage, N, T, seed):
     return out
 
 
+def bptt_window(N, H, seed):
+    """One differentiable window of the reference env (STAGE 0, is_differentiable_physics) with time-out resets inside it:
+    d mean_{t,n}(loss) / d action from the reference's own autograd graph (S/diff_rl/algorithms/bptt.py:38-44)."""
+    cfg = RacingCfg.for_stage(0, is_differentiable_physics=True)
+    g = torch.Generator().manual_seed(seed)
+    srnd0 = torch.rand(N, L_.SRND_STRIDE, generator=g)
+    srnd0[:, 12:] = torch.randn(N, 4, generator=g)
+    ref, srnd = RC.make_reference_env(cfg, figure_eight_track(), N, srnd0, seed=3000 + seed)
+    term, cmd, data, ter = ref.action_manager.get_term(TERM), ref.command_manager.get_term(CMD), ref.scene["robot"].data, ref.scene.terrain
+    dyn = term.drone_dynamics
+    ids = torch.arange(N)
+    rnd0 = torch.zeros(N, L_.RND_STRIDE)
+    torch.manual_seed(seed)
+    ref._reset_idx(ids)
+    torch.manual_seed(seed)
+    RC.replay_reset_draws(rnd0, ids, cfg.add_cmd_noise)
+    RC.replay_obs_draws(rnd0)
+    off = (torch.rand(N, 3, generator=g) * 2 - 1) * 1.0 / (3 ** 0.5)
+    pos0 = cmd.gate_pose_gt_w[:, :3] + off
+    data.root_pos_w = pos0.clone()
+    term.get_state_from_sim()
+    dyn.reset_state(term.states_all, ids)
+    ep0 = torch.randint(cfg.max_episode_length - H - 4, cfg.max_episode_length + H, (N,), generator=g) - H
+    ref.episode_length_buf[:] = ep0
+    ref.detach()
+
+    def fresh_copies(env_ids):                     # see tests/test_oracle_vs_reference_env.py: the reference's in-place reset writes
+        term.thr_est_error = term.thr_est_error.clone()
+        dyn.drag_coeffs, dyn.h_force_drag_coeffs = dyn.drag_coeffs.clone(), dyn.h_force_drag_coeffs.clone()
+    ref.recorder_manager.pre_reset_hook = fresh_copies
+    acts = [(torch.randn(N, 4, generator=g) * 0.5).requires_grad_(True) for _ in range(H)]
+    rnds, losses, n_reset = [], [], 0
+    for t in range(H):
+        rnd = torch.zeros(N, L_.RND_STRIDE)
+        rnd[:, L_.RND_LEVEL] = torch.rand(N, generator=g)
+        ter.pending_level_u = rnd[:, L_.RND_LEVEL].clone()
+        torch.manual_seed(500 + t)
+        ex = ref.step(acts[t])[4]
+        reset_ids = ref.reset_buf.nonzero(as_tuple=False).squeeze(-1)
+        n_reset += len(reset_ids)
+        torch.manual_seed(500 + t)
+        RC.replay_reset_draws(rnd, reset_ids, cfg.add_cmd_noise)
+        RC.replay_pass_draws(rnd, ref.command_manager.last_achieved, cfg.add_cmd_noise)
+        RC.replay_obs_draws(rnd)
+        rnds.append(rnd)
+        losses.append(ex["losses"])
+    torch.stack(losses).mean().backward()
+    grad = torch.stack([a.grad if a.grad is not None else torch.zeros(N, 4) for a in acts])
+    print(f"bptt window: resets {n_reset}, |grad| max {float(grad.abs().max()):.3e}")
+    return dict(N=N, H=H, startup_rnd=srnd, rnd0=rnd0, pos0=pos0, episode_length0=ep0, actions=torch.stack([a.detach() for a in acts]),
+                rnd=torch.stack(rnds), losses=torch.stack(losses).detach(), grad_actions=grad, resets=n_reset)
+
+
 if __name__ == "__main__":
-    d = {"stage0_figure8": scenario(0, 24, 64, seed=3), "stage1_table": scenario(1, 24, 64, seed=4)}
+    d = {"stage0_figure8": scenario(0, 24, 64, seed=3), "stage1_table": scenario(1, 24, 64, seed=4), "bptt_window": bptt_window(32, 16, seed=6)}
     path = os.path.join(OUT, "ref_env_closure.pt")
     torch.save(d, path)
     print(path, os.path.getsize(path))
