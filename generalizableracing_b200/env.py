@@ -161,7 +161,9 @@ class RacingVecEnv:
                                 int(block_threads), flags, self._chunk_types.data_ptr())
         self._rng = B.GrRandom(None, self.seed, 0)
         self._step_count = 0
-        # ---- outputs (ping-pong so that the tensors returned by step t stay valid during step t+1)
+        # ---- outputs (ping-pong so that the tensors returned by step t stay valid during step t+1).  The kernels write them through raw
+        #      pointers, which autograd's version counters cannot see: where a policy is differentiated across steps (differentiable
+        #      physics), the policy observation is handed out as a fresh copy (_grad_safe_obs), as the reference's recomputed one is.
         def outs():
             return dict(obs=torch.zeros(N, L.OBS_DIM, device=dev), critic=torch.zeros(N, L.OBS_DIM, device=dev),
                         aux=torch.zeros(N, 1, device=dev), reward=torch.zeros(N, device=dev),
@@ -321,7 +323,12 @@ class RacingVecEnv:
         if self._bptt is not None:
             self._bptt.start_window()
         self.extras["observations"] = self._obs_dict(o)
-        return o["obs"], self.extras
+        return self._grad_safe_obs(o["obs"]), self.extras
+
+    def _grad_safe_obs(self, obs: torch.Tensor, needed: bool = True) -> torch.Tensor:
+        """A policy differentiated over a BPTT window saves its input for the weight gradients; the ping-pong output buffer
+        would be overwritten two steps later behind autograd's back."""
+        return obs.clone() if (self._bptt is not None and needed) else obs
 
     def get_observations(self):
         """RslRlVecEnvWrapper.get_observations: (policy obs, {"observations": obs_dict}).  Returns the observation of
@@ -333,7 +340,7 @@ class RacingVecEnv:
             # operator outputs allocated under the runner's torch.inference_mode() (on_policy_runner.py:141): hand normal tensors
             # to a caller outside it, as the reference's recomputed observations are
             o.update({k: o[k].clone() for k in ("obs", "critic", "aux")})
-        return o["obs"], {"observations": self._obs_dict(o)}
+        return self._grad_safe_obs(o["obs"], self._ops is None), {"observations": self._obs_dict(o)}
 
     def detach(self):
         """env.unwrapped.detach() (manager_based_diff_rl_env.py:412-416): start a new BPTT window."""
@@ -390,7 +397,7 @@ class RacingVecEnv:
         ex["terminated"] = term
         if self._bptt is not None:
             self._bptt.after_step(actions, ex)
-        return o["obs"], o["reward"], o["dones"], ex
+        return self._grad_safe_obs(o["obs"], actions.requires_grad), o["reward"], o["dones"], ex
 
     def rollout(self, actions: torch.Tensor, rnd: Optional[torch.Tensor] = None, record_obs: bool = False) -> dict:
         """``for t in range(T): env.step(actions[t])`` in ONE launch (gr_rollout_fwd) for actions known in advance

@@ -176,13 +176,18 @@ class ReachTargetVecEnv:
         if self._bptt is not None:
             self._bptt.start_window()
         self.extras["observations"] = {"policy": o["obs"]}
-        return o["obs"], self.extras
+        return self._grad_safe_obs(o["obs"]), self.extras
+
+    def _grad_safe_obs(self, obs: torch.Tensor, needed: bool = True) -> torch.Tensor:
+        """See RacingVecEnv._grad_safe_obs: the ping-pong output buffers are rewritten through raw pointers two steps later, which
+        autograd cannot see; a policy differentiated across the steps of a window gets a fresh copy."""
+        return obs.clone() if (self._bptt is not None and needed) else obs
 
     def get_observations(self):
         if self._needs_reset:
             self.reset()
         o = self._last
-        return o["obs"], {"observations": {"policy": o["obs"]}}
+        return self._grad_safe_obs(o["obs"]), {"observations": {"policy": o["obs"]}}
 
     def detach(self):
         if self._bptt is not None:
@@ -228,7 +233,7 @@ class ReachTargetVecEnv:
         ex["terminated"] = term
         if self._bptt is not None:
             self._bptt.after_step(actions, ex)
-        return o["obs"], o["reward"], o["dones"], ex
+        return self._grad_safe_obs(o["obs"], actions.requires_grad), o["reward"], o["dones"], ex
 
     def rollout(self, actions: torch.Tensor, rnd: Optional[torch.Tensor] = None, record_obs: bool = False) -> dict:
         """``for t in range(T): env.step(actions[t])`` in ONE launch (gr_reach_rollout_fwd) for actions known in advance

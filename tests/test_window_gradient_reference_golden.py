@@ -59,3 +59,27 @@ def test_kernel_reverse_sweep_matches_reference_window_gradient(backend):
     err = float((grad - d["grad_actions"]).abs().max() / d["grad_actions"].abs().max())
     print("window losses rel err", worst, "gradient err / max entry", err)
     assert worst < PC.REL_TOL_STEP and err < 1e-4
+
+
+@pytest.mark.parametrize("backend", backend_params(), indirect=True)
+def test_observations_handed_to_a_differentiated_policy_stay_valid(backend):
+    """Differentiable mode: the observation returned by reset / get_observations / step(actions requiring grad) is not one of the
+    ping-pong output buffers the kernels rewrite two steps later (autograd would have saved it for the policy's weight gradients)."""
+    device, lib = backend
+    d, cfg, table = _load()
+    N = d["N"]
+    env = RacingVecEnv(cfg, table, N, device=device, rng_mode="dense", startup_rnd=d["startup_rnd"], bptt_horizon=8, _lib=lib)
+    obs = [env.reset(d["rnd0"].to(device))[0], env.get_observations()[0]]
+    snap = [o.clone() for o in obs]
+    for t in range(5):
+        o = env.step(d["actions"][t].to(device).requires_grad_(True), d["rnd"][t].to(device))[0]
+        obs.append(o)
+        snap.append(o.clone())
+    assert len({o.data_ptr() for o in obs}) == len(obs)
+    for o, s0 in zip(obs, snap):
+        assert torch.equal(o, s0)
+    # without a differentiated policy in the loop the step keeps handing out its own buffers (no extra copy on the hot path)
+    o1 = env.step(d["actions"][5].to(device), d["rnd"][5].to(device))[0]
+    o2 = env.step(d["actions"][6].to(device), d["rnd"][6].to(device))[0]
+    o3 = env.step(d["actions"][7].to(device), d["rnd"][7].to(device))[0]
+    assert o1.data_ptr() == o3.data_ptr() != o2.data_ptr()
