@@ -45,8 +45,11 @@ def _load_reference_bptt():
     return RM._load("standalone.diff_rl.algorithms.bptt", os.path.join(base, "bptt.py")).BPTT
 
 
-@pytest.mark.parametrize("optimizer", ["SGD", "Adam"])
-def test_bptt_training_iterations_match_reference_trainer(emul_lib, optimizer):
+@pytest.mark.parametrize("optimizer,trainer", [("SGD", "repo"), ("Adam", "repo"), ("SGD", "reference"), ("Adam", "reference")])
+def test_bptt_training_iterations_match_reference_trainer(emul_lib, optimizer, trainer):
+    """trainer = "repo": this repo's BPTT (one-launch window sweep) on the kernels; "reference": the reference's own, unmodified BPTT class
+    on the kernels (the drop-in of INTEGRATION.md §3: its ``torch.stack(self.losses).mean().backward()`` runs the chained per-step
+    reverse kernels through the autograd-connected ``extras["losses"]``).  Both against the reference's BPTT on the reference's env."""
     from oracle import ref_closure as RC
     N, H, K = 32, 8, 4
     cfg = RacingCfg.for_stage(0, is_differentiable_physics=True)
@@ -67,7 +70,7 @@ def test_bptt_training_iterations_match_reference_trainer(emul_lib, optimizer):
     init = [p.detach().clone() for p in pol_r.parameters()]
     hp = dict(max_iterations=K, learning_rate=1e-3 if optimizer == "Adam" else 0.05, schedule="CosineAnnealingLR", device="cpu", optimizer=optimizer)
     alg_r = _load_reference_bptt()(pol_r, **hp)
-    alg_k = BPTT(pol_k, env=env, **hp)
+    alg_k = BPTT(pol_k, env=env, **hp) if trainer == "repo" else _load_reference_bptt()(pol_k, **hp)
     # reset (ManagerBasedRLEnv.reset): _reset_idx(all) + observations
     ids = torch.arange(N)
     rnd = torch.zeros(N, L_.RND_STRIDE)
@@ -113,11 +116,75 @@ def test_bptt_training_iterations_match_reference_trainer(emul_lib, optimizer):
         assert abs(float(loss_r.detach()) - float(loss_k.detach())) < 1e-5 * max(1.0, abs(float(loss_r.detach()))), it
         diffs = torch.cat([(p - q).abs().flatten() for p, q in zip(pol_r.parameters(), pol_k.parameters())])
         moved = torch.cat([(p - q).abs().flatten() for p, q in zip(pol_r.parameters(), init)])
-        print(f"{optimizer} iteration {it}: loss {float(loss_r.detach()):.6f} / {float(loss_k.detach()):.6f}, weights moved by <= {float(moved.max()):.2e}, "
+        print(f"{optimizer} / {trainer} trainer on the kernels, iteration {it}: loss {float(loss_r.detach()):.6f} / {float(loss_k.detach()):.6f}, weights moved by <= {float(moved.max()):.2e}, "
               f"differ by <= {float(diffs.max()):.2e}, > 2e-4: {int((diffs > 2e-4).sum())} of {diffs.numel()}")
         if optimizer == "SGD":       # w -= lr g: the weight difference IS the gradient difference (x lr, accumulated over the iterations)
             assert float(diffs.max()) < 1e-4 * float(moved.max()), it
         else:                        # measured 2e-7; Adam's first steps are sign-like, so entries at the fp32 noise floor could move by up to 2 lr
             assert float(diffs.max()) < 2e-5, it
         assert alg_r.optimizer.param_groups[0]["lr"] == pytest.approx(alg_k.optimizer.param_groups[0]["lr"], rel=1e-12)
+    assert n_reset > 0
+
+
+@pytest.mark.parametrize("trainer", ["repo", "reference"])
+def test_reach_bptt_training_iterations_match_reference_trainer(emul_lib, trainer):
+    """The same for the CTBR reach-target task (QD/reach_target_ctbr_env.py; 17-wide observation): the reference's BPTT on the reference's
+    env against this repo's / the reference's BPTT on the reach kernels (emulation), SGD so that weight differences are gradient differences."""
+    from generalizableracing_b200.config import ReachTargetCfg
+    from generalizableracing_b200.reach_env import ReachTargetVecEnv
+    from oracle import ref_closure as RC
+    N, H, K = 32, 8, 4
+    cfg = ReachTargetCfg.ctbr(episode_length_s=0.6, resampling_time=0.3)                 # 20-step episodes, 10-step command timers
+    g = torch.Generator().manual_seed(33)
+    ref = RC.make_reference_reach_env(cfg, N, seed=5000)
+    env = ReachTargetVecEnv(cfg, N, device="cpu", rng_mode="dense", bptt_horizon=H, _lib=emul_lib)
+    term, cmd = ref.action_manager.get_term("force_torque"), ref.command_manager.get_term("desired_pos_b")
+    ref.recorder_manager.pre_reset_hook = lambda env_ids: setattr(term, "thr_est_error", term.thr_est_error.clone())
+    torch.manual_seed(0)
+    pol_r = BaseModel(17, 17, 4, actor_hidden_dims=[128, 128], critic_hidden_dims=[128, 128], activation="elu", init_noise_std=0.3)
+    pol_k = copy.deepcopy(pol_r)
+    init = [p.detach().clone() for p in pol_r.parameters()]
+    hp = dict(max_iterations=K, learning_rate=0.02, schedule="CosineAnnealingLR", device="cpu", optimizer="SGD")
+    alg_r = _load_reference_bptt()(pol_r, **hp)
+    alg_k = BPTT(pol_k, env=env, **hp) if trainer == "repo" else _load_reference_bptt()(pol_k, **hp)
+    ids = torch.arange(N)
+    rnd = torch.zeros(N, L_.REACH_RND_STRIDE)
+    torch.manual_seed(1)
+    ref._reset_idx(ids)
+    cmd._update_command()                                      # reach_oracle R.5
+    obs_r = ref.observation_manager.compute()["policy"]
+    torch.manual_seed(1)
+    RC.replay_reach_reset_draws(rnd, ids, cfg.random_drag)
+    obs_k = env.reset(rnd)[0]
+    n_reset = 0
+    for it in range(K):
+        ref.detach()
+        term.action_buffer = [a.detach() for a in term.action_buffer]
+        env.detach()
+        for t in range(H):
+            torch.manual_seed(10_000 + it * H + t)
+            a_r = alg_r.act(obs_r)
+            torch.manual_seed(10_000 + it * H + t)
+            a_k = alg_k.act(obs_k)
+            rnd = torch.zeros(N, L_.REACH_RND_STRIDE)
+            torch.manual_seed(20_000 + it * H + t)
+            o, rew, terminated, time_outs, ex = ref.step(a_r)
+            reset_ids = ref.reset_buf.nonzero(as_tuple=False).squeeze(-1)
+            n_reset += len(reset_ids)
+            torch.manual_seed(20_000 + it * H + t)
+            RC.replay_reach_reset_draws(rnd, reset_ids, cfg.random_drag)
+            RC.replay_reach_command_draws(rnd, ref.command_manager.last_timer_ids, L_.REACH_RND_CMD_TIMER)
+            obs_r = o["policy"]
+            alg_r.process_env_step(ex["losses"], ex["losses_detached"], (terminated | time_outs).long(), rew, ex)
+            obs_k, rew_k, dones_k, ex_k = env.step(a_k, rnd)
+            alg_k.process_env_step(ex_k["losses"], ex_k["losses_detached"], dones_k, rew_k, ex_k)
+            assert torch.equal(dones_k != 0, terminated | time_outs), (it, t)
+        _, loss_r = alg_r.update()
+        _, loss_k = alg_k.update()
+        assert abs(float(loss_r.detach()) - float(loss_k.detach())) < 1e-5 * max(1.0, abs(float(loss_r.detach()))), it
+        diffs = torch.cat([(p - q).abs().flatten() for p, q in zip(pol_r.parameters(), pol_k.parameters())])
+        moved = torch.cat([(p - q).abs().flatten() for p, q in zip(pol_r.parameters(), init)])
+        print(f"reach / {trainer} trainer on the kernels, iteration {it}: loss {float(loss_r.detach()):.6f} / {float(loss_k.detach()):.6f}, "
+              f"weights moved by <= {float(moved.max()):.2e}, differ by <= {float(diffs.max()):.2e}")
+        assert float(diffs.max()) < 1e-4 * float(moved.max()), it
     assert n_reset > 0
