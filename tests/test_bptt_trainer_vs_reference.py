@@ -22,7 +22,7 @@ from generalizableracing_b200.algorithms.bptt import BPTT
 from generalizableracing_b200.config import RacingCfg
 from generalizableracing_b200.env import RacingVecEnv
 from generalizableracing_b200.modules import BaseModel
-from generalizableracing_b200.tracks import figure_eight_track
+from generalizableracing_b200.tracks import figure_eight_track, synthetic_track_table
 from oracle import ref_modules as RM
 from tests import parity_cases as PC
 
@@ -45,15 +45,16 @@ def _load_reference_bptt():
     return RM._load("standalone.diff_rl.algorithms.bptt", os.path.join(base, "bptt.py")).BPTT
 
 
-@pytest.mark.parametrize("optimizer,trainer", [("SGD", "repo"), ("Adam", "repo"), ("SGD", "reference"), ("Adam", "reference")])
-def test_bptt_training_iterations_match_reference_trainer(emul_lib, optimizer, trainer):
+@pytest.mark.parametrize("optimizer,trainer,stage", [("SGD", "repo", 0), ("Adam", "repo", 0), ("SGD", "reference", 0), ("Adam", "reference", 0),
+                                                     ("SGD", "repo", 1), ("SGD", "repo", 2)])
+def test_bptt_training_iterations_match_reference_trainer(emul_lib, optimizer, trainer, stage):
     """trainer = "repo": this repo's BPTT (one-launch window sweep) on the kernels; "reference": the reference's own, unmodified BPTT class
     on the kernels (the drop-in of INTEGRATION.md §3: its ``torch.stack(self.losses).mean().backward()`` runs the chained per-step
     reverse kernels through the autograd-connected ``extras["losses"]``).  Both against the reference's BPTT on the reference's env."""
     from oracle import ref_closure as RC
     N, H, K = 32, 8, 4
-    cfg = RacingCfg.for_stage(0, is_differentiable_physics=True)
-    table = figure_eight_track()
+    cfg = RacingCfg.for_stage(stage, is_differentiable_physics=True)       # stages 1 / 2: command noise, curricula, bad-pose terminations
+    table = figure_eight_track() if stage == 0 else synthetic_track_table()
     g = torch.Generator().manual_seed(21)
     ref, srnd = RC.make_reference_env(cfg, table, N, PC.draw_startup(N, g), seed=4000)
     env = RacingVecEnv(cfg, table, N, device="cpu", rng_mode="dense", startup_rnd=srnd, bptt_horizon=H, _lib=emul_lib)
@@ -116,7 +117,7 @@ def test_bptt_training_iterations_match_reference_trainer(emul_lib, optimizer, t
         assert abs(float(loss_r.detach()) - float(loss_k.detach())) < 1e-5 * max(1.0, abs(float(loss_r.detach()))), it
         diffs = torch.cat([(p - q).abs().flatten() for p, q in zip(pol_r.parameters(), pol_k.parameters())])
         moved = torch.cat([(p - q).abs().flatten() for p, q in zip(pol_r.parameters(), init)])
-        print(f"{optimizer} / {trainer} trainer on the kernels, iteration {it}: loss {float(loss_r.detach()):.6f} / {float(loss_k.detach()):.6f}, weights moved by <= {float(moved.max()):.2e}, "
+        print(f"stage {stage} {optimizer} / {trainer} trainer on the kernels, iteration {it}: loss {float(loss_r.detach()):.6f} / {float(loss_k.detach()):.6f}, weights moved by <= {float(moved.max()):.2e}, "
               f"differ by <= {float(diffs.max()):.2e}, > 2e-4: {int((diffs > 2e-4).sum())} of {diffs.numel()}")
         if optimizer == "SGD":       # w -= lr g: the weight difference IS the gradient difference (x lr, accumulated over the iterations)
             assert float(diffs.max()) < 1e-4 * float(moved.max()), it
