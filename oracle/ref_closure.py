@@ -655,7 +655,23 @@ def reset_root_state_uniform(env, env_ids, pose_range, velocity_range, asset_cfg
     asset.write_root_com_velocity_to_sim(velocities, env_ids=env_ids)
 
 
-def make_reference_reach_env(cfg, num_envs, seed):
+def _repaired_diff_actions(DiffActions):
+    """DiffActions with the LV / PS branch of ``_get_scale_factor`` repaired: the reference builds ``action_offset`` (and ``action_scale``)
+    as ``torch.tensor([...])[None].repeat(num_envs, 1)`` on an already 2-d literal for the offset (QD/mdp/diff_action.py:272-280), which
+    raises for every num_envs; the evident intent -- one row per env -- is restated here.  Everything else is the reference's class."""
+    class RepairedDiffActions(DiffActions):
+        def _get_scale_factor(self, normal_range=(-1, 1), method="medium"):
+            if self.command_type not in ("LVController", "PSController"):
+                return super()._get_scale_factor(normal_range, method)
+            self.motor_omega, self.thrustmap = self.controller_cfg.motor_omega, self.controller_cfg.thrustmap
+            self.max_thrust_weight_ratio = self.cfg.max_thrust_weight_ratio
+            bound = self.cfg.lin_vel_bound if self.command_type == "LVController" else self.cfg.pos_bound
+            self.action_scale = torch.tensor([3.1415926, bound[1], bound[1], bound[1]], device=self.device)[None].repeat(self.num_envs, 1)
+            self.action_offset = torch.tensor([[0.0, 0.0, 0.0, 0.0]], device=self.device).repeat(self.num_envs, 1)
+    return RepairedDiffActions
+
+
+def make_reference_reach_env(cfg, num_envs, seed, repair_lv_ps=False):
     """The reference env of DiffLab-Quadcopter-{LV,CTBR}-ReachTarget (QD/reach_target_lv_env.py, reach_target_ctbr_env.py) over
     the closure simulator, with the substitutions R.1-R.3 of oracle/reach_oracle.py.  [isaac] terms: base_lin_vel, base_ang_vel,
     last_action, action_rate_l2, body_lin_acc_l2, is_terminated, time_out, reset_root_state_uniform."""
@@ -686,7 +702,8 @@ def make_reference_reach_env(cfg, num_envs, seed):
         ref = RM.load()
         ctrl_cfg.class_type = ref.LVController if cfg.controller == "LVController" else ref.PSController
     b = cfg.lin_vel_bound
-    act_cfg = NS(class_type=ns.diff_action.DiffActions, asset_name="robot", rotor_names="m.*_prop", command_type=cfg.controller,
+    act_cls = _repaired_diff_actions(ns.diff_action.DiffActions) if repair_lv_ps else ns.diff_action.DiffActions
+    act_cfg = NS(class_type=act_cls, asset_name="robot", rotor_names="m.*_prop", command_type=cfg.controller,
                  controller_cfg=ctrl_cfg, gravity=9.81, random_drag=cfg.random_drag, action_lag=cfg.action_lag, sim2real_test=cfg.sim2real_test,
                  max_thrust_weight_ratio=cfg.max_thrust_weight_ratio, lin_vel_bound=(-b, b), pos_bound=(-cfg.pos_bound, cfg.pos_bound))
     torch.manual_seed(seed)
