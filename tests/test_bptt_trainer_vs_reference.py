@@ -127,20 +127,29 @@ def test_bptt_training_iterations_match_reference_trainer(emul_lib, optimizer, t
     assert n_reset > 0
 
 
-@pytest.mark.parametrize("trainer", ["repo", "reference"])
-def test_reach_bptt_training_iterations_match_reference_trainer(emul_lib, trainer):
+@pytest.mark.parametrize("trainer,task", [("repo", "ctbr"), ("reference", "ctbr"), ("repo", "lv"), ("repo", "ps")])
+def test_reach_bptt_training_iterations_match_reference_trainer(emul_lib, trainer, task):
     """The same for the CTBR reach-target task (QD/reach_target_ctbr_env.py; 17-wide observation): the reference's BPTT on the reference's
     env against this repo's / the reference's BPTT on the reach kernels (emulation), SGD so that weight differences are gradient differences."""
     from generalizableracing_b200.config import ReachTargetCfg
     from generalizableracing_b200.reach_env import ReachTargetVecEnv
     from oracle import ref_closure as RC
-    N, H, K = 32, 8, 4
-    cfg = ReachTargetCfg.ctbr(episode_length_s=0.6, resampling_time=0.3)                 # 20-step episodes, 10-step command timers
+    H, K = 8, 4
+    if task == "ctbr":
+        N, cfg = 32, ReachTargetCfg.ctbr(episode_length_s=0.6, resampling_time=0.3)      # 20-step episodes, 10-step command timers
+    else:   # the task the reference's BPTT config ships with (LV) and its PS variant: repaired action term, 3 envs, dt = 5 ms (see
+            # tests/test_reach_oracle_vs_reference_env.py)
+        N, cfg = 3, (ReachTargetCfg.lv if task == "lv" else ReachTargetCfg.ps)(decimation=1, episode_length_s=0.1, resampling_time=0.05)
     g = torch.Generator().manual_seed(33)
-    ref = RC.make_reference_reach_env(cfg, N, seed=5000)
+    ref = RC.make_reference_reach_env(cfg, N, seed=5000, repair_lv_ps=task != "ctbr")
     env = ReachTargetVecEnv(cfg, N, device="cpu", rng_mode="dense", bptt_horizon=H, _lib=emul_lib)
     term, cmd = ref.action_manager.get_term("force_torque"), ref.command_manager.get_term("desired_pos_b")
-    ref.recorder_manager.pre_reset_hook = lambda env_ids: setattr(term, "thr_est_error", term.thr_est_error.clone())
+    dyn = term.drone_dynamics
+
+    def fresh_copies(env_ids):
+        term.thr_est_error = term.thr_est_error.clone()
+        dyn.drag_coeffs, dyn.h_force_drag_coeffs = dyn.drag_coeffs.clone(), dyn.h_force_drag_coeffs.clone()
+    ref.recorder_manager.pre_reset_hook = fresh_copies
     torch.manual_seed(0)
     pol_r = BaseModel(17, 17, 4, actor_hidden_dims=[128, 128], critic_hidden_dims=[128, 128], activation="elu", init_noise_std=0.3)
     pol_k = copy.deepcopy(pol_r)
@@ -185,7 +194,8 @@ def test_reach_bptt_training_iterations_match_reference_trainer(emul_lib, traine
         assert abs(float(loss_r.detach()) - float(loss_k.detach())) < 1e-5 * max(1.0, abs(float(loss_r.detach()))), it
         diffs = torch.cat([(p - q).abs().flatten() for p, q in zip(pol_r.parameters(), pol_k.parameters())])
         moved = torch.cat([(p - q).abs().flatten() for p, q in zip(pol_r.parameters(), init)])
-        print(f"reach / {trainer} trainer on the kernels, iteration {it}: loss {float(loss_r.detach()):.6f} / {float(loss_k.detach()):.6f}, "
+        print(f"reach {task} / {trainer} trainer on the kernels, iteration {it}: loss {float(loss_r.detach()):.6f} / {float(loss_k.detach()):.6f}, "
               f"weights moved by <= {float(moved.max()):.2e}, differ by <= {float(diffs.max()):.2e}")
-        assert float(diffs.max()) < 1e-4 * float(moved.max()), it
+        # LV / PS: the stiff outer loops amplify fp32 round-off (tests/reach_cases.py::check_bptt allows 2e-3 for the same reason; measured 1.5e-4)
+        assert float(diffs.max()) < (1e-4 if task == "ctbr" else 2e-3) * float(moved.max()), it
     assert n_reset > 0
