@@ -175,12 +175,12 @@ class RolloutStorage:
 
     def get_statistics(self):
         # rollout_storage.py:129-137 (logging helper; plain torch, not on the hot path)
-        done = self.dones
-        done[-1] = 1
-        flat_dones = done.permute(1, 0, 2).reshape(-1, 1)
-        done_indices = torch.cat((flat_dones.new_tensor([-1], dtype=torch.int64), flat_dones.nonzero(as_tuple=False)[:, 0]))
-        trajectory_lengths = done_indices[1:] - done_indices[:-1]
-        return trajectory_lengths.float().mean(), self.rewards.mean()
+        # every env's last stored step closes a trajectory (the reference marks it in the buffer itself, so do we); lengths are the gaps
+        # between consecutive end markers of the env-major flattening
+        self.dones[-1] = 1
+        ends = self.dones[..., 0].t().reshape(-1).nonzero(as_tuple=False)[:, 0]
+        starts = torch.cat((ends.new_full((1,), -1), ends[:-1]))
+        return (ends - starts).float().mean(), self.rewards.mean()
 
     def mini_batch_generator(self, num_mini_batches, num_epochs=8, indices: torch.Tensor = None):
         """rollout_storage.py:152-191; the nine fancy-index gathers of one mini-batch are one launch."""
