@@ -230,3 +230,29 @@ def test_closure_term_parameters_are_the_reference_cfg():
                    'func=mdp.penalize_bad_pose', 'weight=-30.0', 'func=mdp.racing_target_diff', 'func=mdp.racing_vel_diff', 'weight=0.05',
                    'func=mdp.racing_falling_diff', 'weight=0.5', 'self.episode_length_s = 6.0 if STAGE != 2 else 8.0'):
         assert needle in src, needle
+
+
+@pytest.mark.parametrize("N", [1, 2])
+def test_single_and_two_env_runs_match_reference_env(N):
+    """With one env every reset is a reset of ALL envs -- the branch the reference's dynamics / controller take for
+    ``len(idx) == num_envs`` (droneDynamics.py:59-66, controller_diff.py:147-152) -- and two envs mix both branches."""
+    RC, cfg, ref, orc, g = _make(1, N, seed=40 + N)
+    _reset(RC, ref, orc, g, seed=3)
+    ep = torch.full((N,), cfg.max_episode_length - 9)
+    ep[-1] -= 5
+    ref.episode_length_buf[:] = ep
+    orc.episode_length_buf[:] = ep
+    n_reset = 0
+    for t in range(60):
+        if t % 5 == 4:
+            _teleport(ref, orc, g, frac=1.0)
+        a = torch.randn(N, 4, generator=g) * (3.0 if t % 7 == 0 else 0.5)
+        (r_obs, r_rew, r_term, r_to, r_ex), (o_obs, o_rew, o_term, o_to, o_ex), achieved = _step(RC, cfg, ref, orc, g, a, seed=900 + t)
+        where = f"N={N} step {t}"
+        assert torch.equal(r_term, o_term) and torch.equal(r_to, o_to) and torch.equal(achieved, orc.last_achieved), where
+        assert torch.equal(r_rew, o_rew), where
+        for k in ("policy", "critic", "auxiliary"):
+            assert torch.equal(r_obs[k], o_obs[k]), (where, k)
+        _assert_state_equal(ref, orc, where)
+        n_reset += int((r_term | r_to).sum())
+    assert n_reset >= N
