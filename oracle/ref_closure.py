@@ -6,7 +6,11 @@ Runs the reference's OWN env step -- ``ManagerBasedDiffRLEnv.step`` / ``_reset_i
 (QD/mdp/diff_action.py), ``RacingCommand`` (QD/mdp/commands.py:166-401) and the free MDP term functions of
 QD/mdp/{rewards,observation,termination,losses,events,curriculums}.py -- UNMODIFIED, executed where they lie under
 /root/reference, so that tests/test_oracle_vs_reference_env.py can pin oracle/racing_oracle.py (rows a1, a5-a10 of
-SURVEY.md §8a and the step order of §3.3) against the reference's code rather than against a reading of it.
+SURVEY.md §8a and the step order of §3.3) against the reference's code rather than against a reading of it.  The same harness
+runs the reach-target tasks (``make_reference_reach_env``: ``UniformWorldPoseCommand`` QD/mdp/commands.py:33-134 and the terms of
+QD/reach_target_lv_env.py / reach_target_ctbr_env.py) for tests/test_reach_oracle_vs_reference_env.py, records the golden vectors of
+tests/golden/make_{ref_env,reach_env,c1}_golden.py, and carries the reference's own trainers (tests/test_bptt_trainer_vs_reference.py,
+tests/test_ppo_trainer_on_kernels_vs_reference.py).
 
 What is NOT the reference here, and therefore restated (marked [isaac] below): Isaac Lab's manager base classes
 (``ActionManager``, ``CommandManager`` / ``CommandTerm``, ``RewardManager``, ``TerminationManager``, ``CurriculumManager``,
