@@ -5,7 +5,9 @@
 // per step), :113-127 (~8T+6 launches of [N,1] elementwise ops), :152-191 (9 fancy-index gathers per
 // mini-batch) and S/rsl_rl/ext/algorithms/ppo.py:85-97.  All of it is HBM-bound copy / scan work: one thread
 // per env for the time scan (coalesced across envs at every t), 128-bit vector copies for the rows.
+#ifndef GR_CPU_EMUL
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include "../../include/gracing.h"
 
@@ -190,6 +192,7 @@ __global__ void storage_gather_kernel(const GrStorage s, const int64_t* __restri
 
 }  // namespace gr
 
+#ifndef GR_CPU_EMUL   // host API (the CPU emulation harness in tests/emul includes only the device code)
 using namespace gr;
 
 static inline bool mis16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
@@ -269,3 +272,4 @@ extern "C" int gr_storage_gather(const GrStorage* s, const int64_t* indices, int
   else storage_gather_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*s, indices, B, *out);
   return (int)cudaGetLastError();
 }
+#endif  // GR_CPU_EMUL

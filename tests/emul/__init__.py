@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE: CPU emulation of the step/reset/startup/bwd kernels (same .cu sources, g++).
+"""TEST INFRASTRUCTURE: CPU emulation of the step/reset/startup/bwd kernels and of the rollout-storage kernels (same .cu sources, g++).
 
 Lets the kernel logic be debugged against the oracle without a GPU.  Only tests import this; the product
 (`RacingVecEnv` without the private ``_lib`` argument) loads libgracing.so and refuses non-CUDA devices.
@@ -21,7 +21,7 @@ def _stale():
         return True
     t = os.path.getmtime(_SO)
     deps = [os.path.join(_HERE, f) for f in ("emul.cpp", "cuda_shim.h")] + \
-           [os.path.join(_CSRC, f) for f in ("racing_step.cu", "racing_bwd.cu", "gr_math.cuh", "gr_common.cuh", "reach_step.cu", "reach_bwd.cu", "reach_core.cuh", "racing_step_core.cuh")] + \
+           [os.path.join(_CSRC, f) for f in ("racing_step.cu", "racing_bwd.cu", "gr_math.cuh", "gr_common.cuh", "reach_step.cu", "reach_bwd.cu", "reach_core.cuh", "racing_step_core.cuh", "rollout.cu")] + \
            [os.path.join(_HERE, "..", "..", "include", "gracing.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -51,6 +51,10 @@ class EmulLib:
         self._l.emul_reach_reset.argtypes = [P(B.GrReachConfig), P(B.GrReachState), P(B.GrRandom), C.c_void_p, C.c_int, C.c_void_p]
         self._l.emul_reach_step_bwd.argtypes = [P(B.GrReachConfig), P(B.GrReachState), P(B.GrBwdIO)]
         self._l.emul_reach_fill_rand.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32]
+        self._l.emul_storage_add.argtypes = [P(B.GrStorage), P(B.GrTransition), C.c_int32]
+        self._l.emul_compute_returns.argtypes = [P(B.GrStorage), C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int32]
+        self._l.emul_advantage_normalize.argtypes = [P(B.GrStorage), C.c_void_p]
+        self._l.emul_storage_gather.argtypes = [P(B.GrStorage), C.c_void_p, C.c_int32, P(B.GrMiniBatch)]
 
     def gr_step_fwd(self, cfg, tr, st, rng, io, stream):
         return self._l.emul_step_fwd(cfg, tr, st, rng, io)
@@ -93,3 +97,19 @@ class EmulLib:
 
     def gr_reach_fill_rand(self, rnd, n, off, seed, step, stream):
         return self._l.emul_reach_fill_rand(rnd, n, off, seed, step)
+
+    # ---- rollout storage (csrc/rollout.cu)
+    def gr_gae_scratch_bytes(self, n):
+        return ((int(n) + 127) // 128 * 3 + 3) * 8
+
+    def gr_storage_add(self, s, tr, step, stream):
+        return self._l.emul_storage_add(s, tr, step)
+
+    def gr_compute_returns(self, s, last_values, gamma, lam, scratch, moments, normalize, stream):
+        return self._l.emul_compute_returns(s, last_values, gamma, lam, scratch, moments, normalize)
+
+    def gr_advantage_normalize(self, s, moments, stream):
+        return self._l.emul_advantage_normalize(s, moments)
+
+    def gr_storage_gather(self, s, idx, b, out, stream):
+        return self._l.emul_storage_gather(s, idx, b, out)

@@ -6,13 +6,18 @@
 #include "../../generalizableracing_b200/csrc/racing_bwd.cu"
 #include "../../generalizableracing_b200/csrc/reach_step.cu"
 #include "../../generalizableracing_b200/csrc/reach_bwd.cu"
+// rollout storage: the block reductions of the GAE moments merge (count, mean, M2) triples pulled from other lanes; with one thread per block
+// there is no other lane, i.e. an empty triple, which merge() skips.  (Valid for this file's merge-style reductions only.)
+static inline double __shfl_down_sync(unsigned, double, int) { return 0.0; }
+#include "../../generalizableracing_b200/csrc/rollout.cu"
+#include <vector>
 
 using namespace gr;
 
 template <typename F>
-static void run_grid(int n, F&& f) {
+static void run_grid(int64_t n, F&& f) {
   blockDim_.x = 1; gridDim_.x = (unsigned)n; threadIdx_.x = 0;
-  for (int b = 0; b < n; ++b) { blockIdx_.x = (unsigned)b; f(); }
+  for (int64_t b = 0; b < n; ++b) { blockIdx_.x = (unsigned)b; f(); }
 }
 
 extern "C" {
@@ -103,6 +108,45 @@ int emul_reach_step_bwd(const GrReachConfig* cfg, const GrReachState* st, const 
 
 int emul_reach_fill_rand(float* rnd, int32_t num_envs, int32_t env_id_offset, uint64_t seed, uint32_t step) {
   run_grid(num_envs, [&] { reach_fill_rand_kernel(rnd, num_envs, env_id_offset, seed, step); });
+  return 0;
+}
+
+// ---- rollout storage (csrc/rollout.cu): the launch arithmetic of gr_storage_add / gr_compute_returns / gr_advantage_normalize / gr_storage_gather
+static inline bool rows_vec4_(const GrStorage* s) { return !((s->obs_dim & 3) || (s->act_dim & 3) || (s->critic_obs && (s->critic_dim & 3))); }
+
+int emul_storage_add(const GrStorage* s, const GrTransition* tr, int32_t step) {
+  if (step < 0 || step >= s->T) return GR_ERR_SIZE;
+  const int64_t N = s->N;
+  const int V = rows_vec4_(s) ? 4 : 1;
+  const int64_t total = N * s->obs_dim / V + (s->critic_obs ? N * s->critic_dim / V : 0) + 3 * (N * s->act_dim / V) + N;
+  if (V == 4) run_grid(total, [&] { storage_add_kernel<4>(*s, *tr, step); });
+  else run_grid(total, [&] { storage_add_kernel<1>(*s, *tr, step); });
+  return 0;
+}
+
+int emul_advantage_normalize(const GrStorage* s, const double* moments) {
+  const int64_t total = (int64_t)s->T * s->N;
+  run_grid((total + 3) / 4, [&] { adv_normalize_kernel(s->advantages, total, moments); });
+  return 0;
+}
+
+int emul_compute_returns(const GrStorage* s, const float* last_values, float gamma, float lam, void* scratch, double* moments, int32_t normalize) {
+  // one partial per (one-thread) block: more partials than the scratch of gr_gae_scratch_bytes holds, so they live here
+  std::vector<double> partials(3 * (size_t)s->N + 3);
+  const int64_t blocks128 = ((int64_t)s->N + 127) / 128;
+  double* mom = moments ? moments : reinterpret_cast<double*>(scratch) + 3 * blocks128;
+  run_grid(s->N, [&] { gae_kernel(*s, last_values, gamma, lam, partials.data()); });
+  run_grid(1, [&] { gae_moments_kernel(partials.data(), s->N, mom); });
+  if (normalize) return emul_advantage_normalize(s, mom);
+  return 0;
+}
+
+int emul_storage_gather(const GrStorage* s, const int64_t* indices, int32_t B, const GrMiniBatch* out) {
+  const int V = rows_vec4_(s) ? 4 : 1;
+  const int per_row = s->obs_dim / V + (s->critic_obs ? s->critic_dim / V : 0) + 3 * (s->act_dim / V) + 1;
+  const int64_t total = (int64_t)B * per_row;
+  if (V == 4) run_grid(total, [&] { storage_gather_kernel<4>(*s, indices, B, *out); });
+  else run_grid(total, [&] { storage_gather_kernel<1>(*s, indices, B, *out); });
   return 0;
 }
 }

@@ -1,4 +1,4 @@
-"""Replays tests/golden/ref_ppo_update.pt on the B200: transitions, the sampled actions and the mini-batch permutation recorded from
+"""Replays tests/golden/ref_ppo_update.pt (on the B200, and here through the g++ emulation of the storage kernels): transitions, the sampled actions and the mini-batch permutation recorded from
 the reference's OWN PPO + RolloutStorage (standalone/rsl_rl/ext/algorithms/ppo.py, ext/storage/rollout_storage.py, unmodified, CPU;
 generator tests/golden/make_ppo_golden.py) go through the CUDA rollout storage (add_transitions with the fused time-out bootstrap,
 GAE + normalisation, mini-batch gathers) and this repo's PPO.update; results must match the reference's.
@@ -12,21 +12,29 @@ import os
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+from tests.conftest import backend_params
+
+pytestmark = pytest.mark.timeout(300)
 G = os.path.join(os.path.dirname(__file__), "golden", "ref_ppo_update.pt")
 
 
-def test_ppo_storage_and_update_match_reference_golden(cuda_lib, monkeypatch):
+@pytest.mark.parametrize("backend", backend_params(), indirect=True)
+def test_ppo_storage_and_update_match_reference_golden(backend, monkeypatch):
+    """``cuda``: libgracing.so on the B200; ``emul``: the same PPO class on CPU with the storage kernels of csrc/rollout.cu compiled by g++."""
     from generalizableracing_b200.algorithms.ppo import PPO
     from generalizableracing_b200.modules import ActorCritic
+    from generalizableracing_b200.storage import RolloutStorage
     from tests.parity_cases import rel_err
+    dev, lib = backend
     d = torch.load(G)
     N, T = d["N"], d["T"]
-    dev = "cuda:0"
     policy = ActorCritic(16, 16, 4, actor_hidden_dims=[128, 128], critic_hidden_dims=[128, 128], activation="lrelu", init_noise_std=1.0)
     policy.load_state_dict(d["init"])
     alg = PPO(policy, None, device=dev, **d["alg"])
-    alg.init_storage("rl", N, T, [16], [16], [4])
+    if lib is None:
+        alg.init_storage("rl", N, T, [16], [16], [4])
+    else:
+        alg.storage = RolloutStorage("rl", N, T, [16], [16], [4], device=dev, _lib=lib)
     real_randperm = torch.randperm
     for it, rec in enumerate(d["iterations"]):
         with torch.no_grad():
