@@ -29,7 +29,13 @@ def _golden_tools():
     return mod
 
 
-def test_reference_ppo_trainer_on_kernels_matches_reference_env(emul_lib):
+@pytest.mark.parametrize("trainer", ["reference", "repo"])
+def test_reference_ppo_trainer_on_kernels_matches_reference_env(emul_lib, trainer):
+    """trainer = "reference": the reference's PPO + RolloutStorage on RacingVecEnv (env drop-in); "repo": this repo's PPO with its RolloutStorage
+    on the emulated storage kernels (csrc/rollout.cu) on RacingVecEnv -- the whole product stack of the PPO path, on CPU.  Both against the
+    reference's PPO on the reference's env."""
+    from generalizableracing_b200.algorithms.ppo import PPO as RepoPPO
+    from generalizableracing_b200.storage import RolloutStorage
     from oracle import ref_closure as RC
     tools = _golden_tools()
     PPO = tools.load_reference_ppo()
@@ -42,9 +48,14 @@ def test_reference_ppo_trainer_on_kernels_matches_reference_env(emul_lib):
     torch.manual_seed(0)
     pol_r = ActorCritic(16, 16, 4, actor_hidden_dims=[128, 128], critic_hidden_dims=[128, 128], activation="lrelu", init_noise_std=1.0)
     pol_k = copy.deepcopy(pol_r)
-    alg_r, alg_k = PPO(pol_r, None, device="cpu", **tools.ALG), PPO(pol_k, None, device="cpu", **tools.ALG)
-    for alg in (alg_r, alg_k):
-        alg.init_storage("rl", N, T, [16], [16], [4])
+    alg_r = PPO(pol_r, None, device="cpu", **tools.ALG)
+    alg_r.init_storage("rl", N, T, [16], [16], [4])
+    if trainer == "reference":
+        alg_k = PPO(pol_k, None, device="cpu", **tools.ALG)
+        alg_k.init_storage("rl", N, T, [16], [16], [4])
+    else:
+        alg_k = RepoPPO(pol_k, None, device="cpu", **tools.ALG)
+        alg_k.storage = RolloutStorage("rl", N, T, [16], [16], [4], device="cpu", _lib=emul_lib)
     ids = torch.arange(N)
     rnd = torch.zeros(N, L_.RND_STRIDE)
     rnd[:, L_.RND_LEVEL] = torch.rand(N, generator=g)
@@ -93,13 +104,13 @@ def test_reference_ppo_trainer_on_kernels_matches_reference_env(emul_lib):
         sr, sk = alg_r.storage, alg_k.storage
         for name in ("observations", "privileged_observations", "actions", "rewards", "values", "returns", "advantages", "actions_log_prob"):
             assert PC.rel_err(getattr(sr, name), getattr(sk, name)) < (1e-3 if it else 1e-4), (it, name)
-        assert torch.equal(sr.dones, sk.dones), it
+        assert torch.equal(sr.dones.long(), sk.dones.long()), it
         torch.manual_seed(30_000 + it)
         loss_r = alg_r.update()
         torch.manual_seed(30_000 + it)
         loss_k = alg_k.update()
         diffs = torch.cat([(p - q).abs().flatten() for p, q in zip(pol_r.parameters(), pol_k.parameters())])
-        print(f"iteration {it}: value loss {loss_r['value_function']:.5f} / {loss_k['value_function']:.5f}, lr {alg_r.learning_rate:.3e} / {alg_k.learning_rate:.3e}, "
+        print(f"{trainer} trainer on the kernels, iteration {it}: value loss {loss_r['value_function']:.5f} / {loss_k['value_function']:.5f}, lr {alg_r.learning_rate:.3e} / {alg_k.learning_rate:.3e}, "
               f"weights differ by <= {float(diffs.max()):.2e}, > 2e-4: {int((diffs > 2e-4).sum())} of {diffs.numel()}")
         assert alg_r.learning_rate == alg_k.learning_rate, it
         assert abs(loss_r["value_function"] - loss_k["value_function"]) < 1e-3 and abs(loss_r["surrogate"] - loss_k["surrogate"]) < 1e-3, it
