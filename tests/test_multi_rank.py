@@ -137,6 +137,50 @@ def _w_reach_shards(rank, world):
         assert torch.equal(torch.cat(gathered, dim=1), torch.stack(fobs))
 
 
-@pytest.mark.parametrize("fn", ["_w_moments", "_w_grads", "_w_env_shards", "_w_reach_shards"])
+def _w_storage_shards(rank, world):
+    """Env-sharded PPO data path: every rank's RolloutStorage (storage kernels through the g++ emulation) runs GAE on its envs
+    with ``normalize=False``, the (count, mean, M2) moments are merged over the ranks and each shard normalises with the GLOBAL mean / std
+    (``PPO.compute_returns``) -- the concatenated shards must equal one storage holding all envs."""
+    from generalizableracing_b200 import dist_utils as D
+    from generalizableracing_b200.storage import RolloutStorage
+    from tests.emul import EmulLib
+    lib = EmulLib()
+    T, n = 12, 48
+    N = world * n
+    g = torch.Generator().manual_seed(7)                      # same stream on every rank: the global batch
+    data = dict(obs=torch.randn(T, N, 16, generator=g), act=torch.randn(T, N, 4, generator=g), rew=torch.randn(T, N, generator=g),
+                val=torch.randn(T, N, 1, generator=g), done=torch.rand(T, N, generator=g) < 0.05, to=torch.rand(T, N, generator=g) < 0.02,
+                logp=torch.randn(T, N, generator=g), mu=torch.randn(T, N, 4, generator=g), sig=torch.rand(T, N, 4, generator=g),
+                last=torch.randn(N, 1, generator=g))
+
+    def fill(lo, hi):
+        sto = RolloutStorage("rl", hi - lo, T, [16], [16], [4], device="cpu", _lib=lib)
+        for t in range(T):
+            tr = sto.Transition()
+            tr.observations = tr.privileged_observations = data["obs"][t, lo:hi].contiguous()
+            tr.actions, tr.rewards, tr.values = data["act"][t, lo:hi].contiguous(), data["rew"][t, lo:hi].contiguous(), data["val"][t, lo:hi].contiguous()
+            tr.dones, tr.time_outs, tr.gamma = data["done"][t, lo:hi].long(), (data["to"][t, lo:hi] & data["done"][t, lo:hi]).contiguous(), 0.99
+            tr.actions_log_prob, tr.action_mean, tr.action_sigma = data["logp"][t, lo:hi].contiguous(), data["mu"][t, lo:hi].contiguous(), data["sig"][t, lo:hi].contiguous()
+            sto.add_transitions(tr)
+        return sto
+    lo, cnt = D.shard_range(N, rank, world)
+    shard = fill(lo, lo + cnt)
+    shard.compute_returns(data["last"][lo:lo + cnt].contiguous(), 0.99, 0.95, normalize=False)
+    shard.normalize_advantages(D.merge_moments(shard.moments))
+    parts = [torch.zeros_like(shard.advantages) for _ in range(world)]
+    dist.all_gather(parts, shard.advantages.contiguous())
+    rets = [torch.zeros_like(shard.returns) for _ in range(world)]
+    dist.all_gather(rets, shard.returns.contiguous())
+    if rank == 0:
+        full = fill(0, N)
+        full.compute_returns(data["last"], 0.99, 0.95)
+        assert torch.equal(torch.cat(rets, dim=1), full.returns)
+        err = float((torch.cat(parts, dim=1) - full.advantages).abs().max())
+        assert err < 1e-6, err
+        a = torch.cat(parts, dim=1).double()
+        assert abs(float(a.mean())) < 1e-6 and abs(float(a.std()) - 1.0) < 1e-6
+
+
+@pytest.mark.parametrize("fn", ["_w_moments", "_w_grads", "_w_env_shards", "_w_reach_shards", "_w_storage_shards"])
 def test_world_size_2_gloo(fn):
     _run(fn)
