@@ -181,6 +181,69 @@ def _w_storage_shards(rank, world):
         assert abs(float(a.mean())) < 1e-6 and abs(float(a.std()) - 1.0) < 1e-6
 
 
-@pytest.mark.parametrize("fn", ["_w_moments", "_w_grads", "_w_env_shards", "_w_reach_shards", "_w_storage_shards"])
+def _w_ppo_update(rank, world):
+    """One env-sharded PPO iteration (this repo's PPO: storage kernels through the emulation, global advantage moments, KL and policy-gradient
+    all-reduce over gloo) equals the same iteration in one process holding all envs: identical learning-rate decisions, weights to fp32 round-off."""
+    import copy
+    from generalizableracing_b200 import dist_utils as D
+    from generalizableracing_b200.algorithms.ppo import PPO
+    from generalizableracing_b200.modules import ActorCritic
+    from generalizableracing_b200.storage import RolloutStorage
+    from tests.emul import EmulLib
+    lib = EmulLib()
+    T, n = 8, 32
+    N = world * n
+    hp = dict(num_learning_epochs=3, num_mini_batches=1, clip_param=0.2, gamma=0.99, lam=0.95, value_loss_coef=1.0, entropy_coef=0.01,
+              learning_rate=5e-4, max_grad_norm=1.0, use_clipped_value_loss=True, schedule="adaptive", desired_kl=0.01)
+    torch.manual_seed(0)
+    policy0 = ActorCritic(16, 16, 4, actor_hidden_dims=[32, 32], critic_hidden_dims=[32, 32], activation="elu", init_noise_std=1.0)
+    g = torch.Generator().manual_seed(11)
+    obs, rew = torch.randn(T, N, 16, generator=g), torch.randn(T, N, generator=g)
+    done, last_obs = (torch.rand(T, N, generator=g) < 0.05).long(), torch.randn(N, 16, generator=g)
+    noise = torch.randn(T, N, 4, generator=g)
+
+    def iterate(lo, hi, sharded):
+        pol = copy.deepcopy(policy0)
+        if not sharded:                       # the single-process reference run must not talk to the other rank
+            real, D.world = D.world, lambda: (0, 1)
+        try:
+            alg = PPO(pol, None, device="cpu", **hp)
+            alg.storage = RolloutStorage("rl", hi - lo, T, [16], [16], [4], device="cpu", _lib=lib)
+            with torch.no_grad():
+                for t in range(T):
+                    o = obs[t, lo:hi].contiguous()
+                    pol.update_distribution(o)
+                    tr = alg.transition
+                    tr.actions = (pol.action_mean + pol.action_std * noise[t, lo:hi]).contiguous()
+                    tr.values, tr.actions_log_prob = pol.evaluate(o), pol.get_actions_log_prob(tr.actions)
+                    tr.action_mean, tr.action_sigma, tr.observations, tr.privileged_observations = pol.action_mean, pol.action_std, o, o
+                    alg.process_env_step(rew[t, lo:hi].contiguous(), done[t, lo:hi].contiguous(), {})
+                alg.compute_returns(last_obs[lo:hi].contiguous())
+            idx = torch.arange((hi - lo) * T)
+            real_perm = torch.randperm
+            torch.randperm = lambda m, **kw: idx
+            try:
+                alg.update()
+            finally:
+                torch.randperm = real_perm
+            return pol, alg.learning_rate
+        finally:
+            if not sharded:
+                D.world = real
+    lo, cnt = D.shard_range(N, rank, world)
+    pol_s, lr_s = iterate(lo, lo + cnt, sharded=True)
+    flat = torch.cat([p.detach().flatten() for p in pol_s.parameters()])
+    both = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(both, flat)
+    assert torch.equal(both[0], both[1])                      # the ranks stay in lock step
+    if rank == 0:
+        pol_1, lr_1 = iterate(0, N, sharded=False)
+        one = torch.cat([p.detach().flatten() for p in pol_1.parameters()])
+        moved = float((one - torch.cat([p.detach().flatten() for p in policy0.parameters()])).abs().max())
+        assert lr_s == lr_1, (lr_s, lr_1)
+        assert float((flat - one).abs().max()) < 1e-3 * moved, (float((flat - one).abs().max()), moved)
+
+
+@pytest.mark.parametrize("fn", ["_w_moments", "_w_grads", "_w_env_shards", "_w_reach_shards", "_w_storage_shards", "_w_ppo_update"])
 def test_world_size_2_gloo(fn):
     _run(fn)
