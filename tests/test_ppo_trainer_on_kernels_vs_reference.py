@@ -117,3 +117,67 @@ def test_reference_ppo_trainer_on_kernels_matches_reference_env(emul_lib, traine
         if it == 0:      # Adam after 20 sign-like steps: see tests/test_ppo_reference_golden.py for the measured sensitivity
             assert float(diffs.max()) < 2e-3 and int((diffs > 2e-4).sum()) <= diffs.numel() // 200
     assert n_done > N // 2
+
+
+def test_reference_ppo_trainer_on_reach_kernels_matches_reference_env(emul_lib):
+    """The same drop-in check for the CTBR reach-target task (17-wide observation, no critic group: the runner falls back to the policy
+    observation, on_policy_runner.py:124): the reference's PPO + RolloutStorage on the reference's env vs on ReachTargetVecEnv (emulation)."""
+    from generalizableracing_b200.config import ReachTargetCfg
+    from generalizableracing_b200.reach_env import ReachTargetVecEnv
+    from oracle import ref_closure as RC
+    tools = _golden_tools()
+    PPO = tools.load_reference_ppo()
+    N, T = 64, 24
+    cfg = ReachTargetCfg.ctbr(episode_length_s=0.6, resampling_time=0.3, is_differentiable_physics=False)
+    ref = RC.make_reference_reach_env(cfg, N, seed=8000)
+    env = ReachTargetVecEnv(cfg, N, device="cpu", rng_mode="dense", _lib=emul_lib)
+    cmd = ref.command_manager.get_term("desired_pos_b")
+    torch.manual_seed(0)
+    pol_r = ActorCritic(17, 17, 4, actor_hidden_dims=[128, 128], critic_hidden_dims=[128, 128], activation="lrelu", init_noise_std=1.0)
+    pol_k = copy.deepcopy(pol_r)
+    alg_r, alg_k = PPO(pol_r, None, device="cpu", **tools.ALG), PPO(pol_k, None, device="cpu", **tools.ALG)
+    for alg in (alg_r, alg_k):
+        alg.init_storage("rl", N, T, [17], [17], [4])
+    ids = torch.arange(N)
+    rnd = torch.zeros(N, L_.REACH_RND_STRIDE)
+    torch.manual_seed(1)
+    ref._reset_idx(ids)
+    cmd._update_command()                                       # reach_oracle R.5
+    obs_r = ref.observation_manager.compute()["policy"]
+    torch.manual_seed(1)
+    RC.replay_reach_reset_draws(rnd, ids, cfg.random_drag)
+    env.reset(rnd)
+    obs_k, ex_k = env.get_observations()
+    assert "critic" not in ex_k["observations"]
+    n_done = 0
+    with torch.inference_mode():
+        for t in range(T):
+            torch.manual_seed(10_000 + t)
+            a_r = alg_r.act(obs_r, obs_r)
+            torch.manual_seed(10_000 + t)
+            a_k = alg_k.act(obs_k, ex_k["observations"].get("critic", obs_k))
+            rnd = torch.zeros(N, L_.REACH_RND_STRIDE)
+            torch.manual_seed(20_000 + t)
+            o, rew_r, terminated, time_outs, _ = ref.step(a_r)
+            reset_ids = ref.reset_buf.nonzero(as_tuple=False).squeeze(-1)
+            torch.manual_seed(20_000 + t)
+            RC.replay_reach_reset_draws(rnd, reset_ids, cfg.random_drag)
+            RC.replay_reach_command_draws(rnd, ref.command_manager.last_timer_ids, L_.REACH_RND_CMD_TIMER)
+            obs_r, dones_r = o["policy"], (terminated | time_outs).to(torch.long)
+            alg_r.process_env_step(rew_r, dones_r, {"time_outs": time_outs})
+            obs_k, rew_k, dones_k, ex_k = env.step(a_k, rnd)
+            alg_k.process_env_step(rew_k, dones_k, ex_k)
+            assert dones_k.dtype == torch.long and torch.equal(dones_k, dones_r) and torch.equal(ex_k["time_outs"], time_outs), t
+            n_done += int(dones_r.sum())
+        alg_r.compute_returns(obs_r)
+        alg_k.compute_returns(obs_k)
+    for name in ("observations", "actions", "rewards", "values", "returns", "advantages", "actions_log_prob"):
+        assert PC.rel_err(getattr(alg_r.storage, name), getattr(alg_k.storage, name)) < 2e-4, name
+    torch.manual_seed(30_000)
+    alg_r.update()
+    torch.manual_seed(30_000)
+    alg_k.update()
+    diffs = torch.cat([(p - q).abs().flatten() for p, q in zip(pol_r.parameters(), pol_k.parameters())])
+    print(f"reach: lr {alg_r.learning_rate:.3e} / {alg_k.learning_rate:.3e}, weights differ by <= {float(diffs.max()):.2e}")
+    assert alg_r.learning_rate == alg_k.learning_rate and n_done > N // 2
+    assert float(diffs.max()) < 2e-3 and int((diffs > 2e-4).sum()) <= diffs.numel() // 200
