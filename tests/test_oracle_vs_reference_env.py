@@ -102,7 +102,9 @@ def _assert_state_equal(ref, orc, where):
         "gate_id": (cmd.gate_id, orc.gate_id), "next_gate_id": (cmd.next_gate_id, orc.next_gate_id),
         "gate_pose_w": (cmd.gate_pose_w, orc.gate_pose_w), "gate_pose_gt_w": (cmd.gate_pose_gt_w, orc.gate_pose_gt_w),
         "next_gate_pose_w": (cmd.next_gate_pose_w, orc.next_gate_pose_w), "next_gate_pose_gt_w": (cmd.next_gate_pose_gt_w, orc.next_gate_pose_gt_w),
-        "accumulate_gates": (cmd.metrics["accumulate_gates"], orc.accumulate_gates), "noise_level": (cmd.noise_level, orc.noise_level),
+        "accumulate_gates": (cmd.metrics["accumulate_gates"], orc.accumulate_gates), 
+        "metric_action_rate": (cmd.metrics["action_rate"], orc.metric_action_rate), "metric_avg_lin_spd": (cmd.metrics["avg_lin_spd"], orc.metric_avg_lin_spd),
+        "metric_avg_ang_spd": (cmd.metrics["avg_ang_spd"], orc.metric_avg_ang_spd), "noise_level": (cmd.noise_level, orc.noise_level),
         "noise_range_pos_x": (cmd.noise_range_pos_x, orc.noise_range_pos_x), "noise_range_yaw": (cmd.noise_range_yaw, orc.noise_range_yaw),
         "terrain_levels": (ter.terrain_levels, orc.terrain_levels), "env_origins": (ter.env_origins, orc.env_origins),
         "episode_length_buf": (ref.episode_length_buf, orc.episode_length_buf),
@@ -150,6 +152,8 @@ def test_step_and_reset_bit_exact_with_reference_env(stage):
             rl, ol = r_ex["log"], o_ex["log"]
             assert float(rl["Curriculum/terrain_levels"]) == float(ol["Curriculum/terrain_levels"]), where
             assert float(rl["Metrics/next_gate_pose/accumulate_gates"]) == float(ol["Metrics/next_gate_pose/accumulate_gates"]), where
+            for name in ("action_rate", "avg_lin_spd", "avg_ang_spd"):     # commands.py:258-260, logged by CommandTerm.reset
+                assert float(rl["Metrics/next_gate_pose/" + name]) == float(ol["Metrics/next_gate_pose/" + name]), (where, name)
             for name in ref.reward_manager._term_names:
                 assert float(rl["Episode_Reward/" + name]) == float(ol["Episode_Reward/" + name]), (where, name)
             if cfg.noise_curriculum:
