@@ -136,6 +136,46 @@ def max_over_ranks(x: float, world: int, device) -> float:
     return float(t.item())
 
 
+def bind_to_gpu_numa(local: int):
+    """Pin this rank's host threads to the CPU set nearest to its GPU (NVML ideal affinity), BEFORE any pinned buffer is allocated, so
+    first-touch places the staging pages on the GPU's NUMA node.  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus ({min(cpus)}-{max(cpus)})"
+    except Exception as ex:                                 # NVML absent / restricted container: leave the scheduler alone
+        return f"unbound ({type(ex).__name__})"
+    return "unbound"
+
+
+def reduce_vector(x, world: int, device, op="max"):
+    """element-wise MAX (or all-gather) of a per-repetition timing vector over the ranks"""
+    t = torch.tensor(x, dtype=torch.float64, device=device)
+    if world == 1:
+        return t.cpu() if op == "max" else t.cpu()[None]
+    import torch.distributed as dist
+    if op == "max":
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.cpu()
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return torch.stack(out).cpu()
+
+
+def med(v):
+    v = sorted(float(x) for x in v)
+    return v[len(v) // 2]
+
+
+CONTRACT_BYTES_FWD = 478        # SURVEY.md 8(d): STAGE >= 1 forward, single-step API (454 B for STAGE 0)
+
+
 def run_ours(args):
     from generalizableracing_b200 import build as BLD
     BLD.build()
@@ -147,12 +187,14 @@ def run_ours(args):
     rank, world, local = dist_setup(args.gpus)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    numa = bind_to_gpu_numa(local)
     N = args.envs
     cfg = RacingCfg.for_stage(STAGE)
-    table = generate_track_table(racing_complex_cfg())      # RacingComplexTerrainCfg: 20 types x 10 levels x 8 gates, obstacle-free
+    table = generate_track_table(racing_complex_cfg())      # RacingComplexTerrainCfg: 20 types x 10 levels x 8 gates (the reference's seed-42 table)
     stats = not args.no_stats
-    b_alg = algorithmic_bytes(cfg, stats)
-    working_set = N * (b_alg + 0)                                      # bytes touched by one step
+    b_cols = algorithmic_bytes(cfg, stats)                   # this build's column set
+    b_alg = CONTRACT_BYTES_FWD if cfg.add_cmd_noise else 454
+    working_set = N * b_cols                                           # bytes touched by one step
     R = max(2, int(3 * L2_BYTES / working_set) + 1)
     envs = [RacingVecEnv(cfg, table, N, device=dev, seed=42 + r, episode_stats=stats, env_id_offset=rank * N,
                          global_num_envs=world * N, block_threads=args.block_threads) for r in range(R)]
@@ -164,7 +206,6 @@ def run_ours(args):
     actions = [torch.randn(N, 4, device=dev, generator=g) * 0.5 for _ in range(R)]      # resident in HBM before the timed region
     lib = B.load()
 
-    # ---- one "round" = one step on each of the R env batches, captured once in a CUDA graph (launch-bound otherwise)
     ios = []
     for e, a in zip(envs, actions):
         o = e._outs[0]
@@ -174,84 +215,146 @@ def run_ours(args):
         io.reward, io.terminated, io.time_out, io.dones = o["reward"].data_ptr(), o["terminated"].data_ptr(), o["time_out"].data_ptr(), o["dones"].data_ptr()
         io.log_accum = e._log_accum.data_ptr()
         ios.append(io)
-    launches = [0]
 
-    def one_round(step0: int):
+    def launch_seq(start: int, n: int, step0: int = 0):
+        """n launches of gr_step_fwd, round-robin over the R env batches beginning with batch `start % R`"""
         s = torch.cuda.current_stream(dev).cuda_stream
-        for k, (e, io) in enumerate(zip(envs, ios)):
-            rng = B.GrRandom(None, e.seed, (step0 + k) & 0xFFFFFFFF)
-            B.check(lib.gr_step_fwd(C.byref(e._gcfg), C.byref(e._track), C.byref(e._state), C.byref(rng), C.byref(io), s), "gr_step_fwd")
-            launches[0] += 1
+        for i in range(n):
+            k = (start + i) % R
+            e = envs[k]
+            rng = B.GrRandom(None, e.seed, (step0 + start + i) & 0xFFFFFFFF)
+            B.check(lib.gr_step_fwd(C.byref(e._gcfg), C.byref(e._track), C.byref(e._state), C.byref(rng), C.byref(ios[k]), s), "gr_step_fwd")
 
-    # warm-up (eager), then capture
-    rounds_w = max(1, -(-args.warmup // R))
-    for w in range(rounds_w):
-        one_round(w * R)
+    # ---- W untimed warm-up steps (eager launches), exactly as requested
+    K, W = args.steps, args.warmup
+    launch_seq(0, W)
     torch.cuda.synchronize(dev)
-    graph = torch.cuda.CUDAGraph()
+
+    # ---- the K timed steps of one repetition = CUDA graphs holding exactly K launches (launch-bound otherwise); repetition r
+    # starts with batch (W + r*K) % R, so a batch is never touched again before the R-1 others (>= 3 x L2 of other traffic)
+    CH = R * 90
     side = torch.cuda.Stream(dev)
     side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
-        one_round(10_000)            # warm the capture stream
+        launch_seq(0, R, 10_000)            # warm the capture stream
     torch.cuda.current_stream(dev).wait_stream(side)
     torch.cuda.synchronize(dev)
-    with torch.cuda.graph(graph):
-        one_round(20_000)
-    graph.replay()
-    torch.cuda.synchronize(dev)
+    gcache = {}
 
-    K = args.steps
-    rounds = max(1, -(-K // R))
-    K = rounds * R                                                     # timed steps are a whole number of rounds
-    barrier(world)
+    def graph_for(start: int, n: int):
+        key = (start % R, n)
+        if key not in gcache:
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                launch_seq(start % R, n, 20_000)
+            gcache[key] = gr
+        return gcache[key]
+
+    def rep_graphs(r: int):
+        s0 = (W + r * K) % R
+        out = [graph_for(s0, CH)] * (K // CH)
+        if K % CH:
+            out.append(graph_for(s0, K % CH))
+        return out
+
+    n_distinct = R // __import__("math").gcd(K, R) if K % R else 1
+    plans = [rep_graphs(r) for r in range(n_distinct)]
+    for pl in plans:                        # first replay of every graph (upload) outside the timed region
+        for gr in pl:
+            gr.replay()
     torch.cuda.synchronize(dev)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for r in range(3):
+        for gr in plans[r % n_distinct]:
+            gr.replay()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    est_rep_ms = max(e0.elapsed_time(e1) / 3, 1e-3)
+    reps = args.repeats or int(min(8000, max(100, 1200.0 / est_rep_ms)))
+    if world > 1:                           # every rank must time the same number of repetitions
+        import torch.distributed as dist
+        t = torch.tensor([reps], device=dev)
+        dist.broadcast(t, 0)
+        reps = int(t.item())
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+
+    # ---- clock sampler (rank 0's GPU) starts >= 0.5 s BEFORE the first timed repetition, under the same load
+    clk = ClockSampler(local) if rank == 0 else None
+    if clk is not None:
+        clk.__enter__()
+    lead_replays = 0
+    t_end = time.time() + 0.6
+    while time.time() < t_end:
+        for gr in plans[lead_replays % n_distinct]:
+            gr.replay()
+        lead_replays += 1
+        if lead_replays % 64 == 0:
+            torch.cuda.synchronize(dev)
     for e in envs:
         e._log_accum.zero_()
-    replays = 0
-    with ClockSampler(local) as clk:
-        ev0.record()
-        for _ in range(rounds):
-            graph.replay()
-        ev1.record()
-        torch.cuda.synchronize(dev)
-        ms_local = ev0.elapsed_time(ev1)
-        replays += rounds
-        # keep the GPU under the same load a little longer so the 100 ms sampler sees it
-        t_end = time.time() + (1.5 if rank == 0 else 0.0)
-        while time.time() < t_end:
-            graph.replay()
-            replays += 1
-        torch.cuda.synchronize(dev)
+    torch.cuda.synchronize(dev)
     barrier(world)
-    # emergent reset rate of the timed workload (warm-up + timed + load-holding replays), from the kernels' own log accumulators
+    torch.cuda.synchronize(dev)
+    # ---- timed: `reps` back-to-back repetitions of EXACTLY K steps, each bracketed by CUDA events on the launching stream.  A
+    # repetition is one or a few graph launches enqueued ahead of the GPU, so a host hiccup cannot land inside one.
+    for r in range(reps):
+        evs[r][0].record()
+        for gr in plans[r % n_distinct]:
+            gr.replay()
+        evs[r][1].record()
+    torch.cuda.synchronize(dev)
+    barrier(world)
+    if clk is not None:
+        clk.__exit__()
+    local_ms = [a.elapsed_time(b) for a, b in evs]
+    rep_ms = reduce_vector(local_ms, world, dev, "max")          # per repetition: max over ranks
+    per_rank = reduce_vector([med(local_ms), min(local_ms), max(local_ms)], world, dev, "gather")
+    ms = med(rep_ms)                                             # reported: the median repetition
+    # emergent reset rate of the timed workload, from the kernels' own log accumulators
     tot = torch.stack([e._log_accum.sum(dim=0) for e in envs]).sum(dim=0)
-    reset_rate = float(tot[0].item()) / (replays * R * N)
-    ms = max_over_ranks(ms_local, world, dev)
+    reset_rate = float(tot[0].item()) / (reps * K * N)
     value = world * N * K / (ms * 1e-3)
-    kernel_us = ms_local * 1e3 / K
+    kernel_us = med(local_ms) * 1e3 / K
     peak, peak_src, _ = load_peaks()
     achieved = b_alg * N / (kernel_us * 1e-6) / 1e9
+    achieved_cols = b_cols * N / (kernel_us * 1e-6) / 1e9
+    timing = {"repeats": reps, "rep_ms_median": ms, "rep_ms_min": float(rep_ms.min()), "rep_ms_max": float(rep_ms.max()), "rep_ms_first": float(rep_ms[0]),
+              "rep_ms_p10": float(rep_ms.kthvalue(max(1, reps // 10)).values), "rep_ms_p90": float(rep_ms.kthvalue(max(1, reps * 9 // 10)).values),
+              "kernel_us_per_rank_median": [float(x) * 1e3 / K for x in per_rank[:, 0]],
+              "kernel_us_per_rank_min": [float(x) * 1e3 / K for x in per_rank[:, 1]],
+              "kernel_us_per_rank_max": [float(x) * 1e3 / K for x in per_rank[:, 2]],
+              "how": f"{reps} back-to-back repetitions of exactly K={K} steps, each CUDA-event timed on the launching stream and max-reduced over ranks; "
+                     f"value = median repetition; barrier + synchronize around the whole set; untimed lead-in of {lead_replays} repetitions for the clock sampler",
+              "host_numa_binding": numa}
 
-    # ---- same graph, near-hover actions (time-out resets only): the low-reset regime of a trained policy
+    def timed_graphs(pls, n_reps):
+        """median device time (ms) of one K-step repetition over n_reps repetitions of the given plans"""
+        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_reps)]
+        for r in range(n_reps):
+            pairs[r][0].record()
+            for gr in pls[r % len(pls)]:
+                gr.replay()
+            pairs[r][1].record()
+        torch.cuda.synchronize(dev)
+        return med([a.elapsed_time(b) for a, b in pairs])
+
+    def sum_resets():
+        return float(torch.stack([e._log_accum.sum(dim=0) for e in envs]).sum(dim=0)[0].item())
+
+    # ---- same graphs, near-hover actions (time-out resets only): the low-reset regime of a trained policy
     low = None
+    sub_reps = max(20, min(reps, 400))
     if not args.no_extra:
         for a in actions:
             a.copy_(torch.randn(N, 4, device=dev, generator=g) * 0.1 + torch.tensor([-0.3466, 0.0, 0.0, 0.0], device=dev))
-        for _ in range(40):
-            graph.replay()
+        timed_graphs(plans, max(4, 440 // max(K, 1)))             # let the tumbling drones of the random-action phase reset
         for e in envs:
             e._log_accum.zero_()
-        torch.cuda.synchronize(dev)
-        ev0.record()
-        for _ in range(rounds):
-            graph.replay()
-        ev1.record()
-        torch.cuda.synchronize(dev)
-        us = ev0.elapsed_time(ev1) * 1e3 / K
-        rr = float(torch.stack([e._log_accum.sum(dim=0) for e in envs]).sum(dim=0)[0].item()) / (rounds * R * N)
+        us = timed_graphs(plans, sub_reps) * 1e3 / K
         low = {"kernel_us": us, "env_steps_per_s_per_gpu": N / (us * 1e-6), "frac_of_hbm_peak": b_alg * N / (us * 1e-6) / 1e9 / peak,
-               "resets_per_env_step": rr, "actions": "N((-0.35,0,0,0), 0.1^2): near hover"}
+               "frac_of_hbm_peak_column_set": b_cols * N / (us * 1e-6) / 1e9 / peak,
+               "resets_per_env_step": sum_resets() / (sub_reps * K * N), "actions": "N((-0.35,0,0,0), 0.1^2): near hover"}
 
     # ---- forced reset rates (SURVEY 8d: "also report a forced 1 % and 10 % reset-rate case for C4"): the same launches re-captured
     # with max_episode_length = 100 / 10 and staggered episode counters, so 1 % / 10 % of the envs time out (and run the reset
@@ -265,21 +368,15 @@ def run_ours(args):
             torch.cuda.synchronize(dev)
             g2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g2):
-                one_round(30_000)
-            for _ in range(40):
+                launch_seq(0, 4 * R, 30_000)
+            for _ in range(10):
                 g2.replay()
             for e in envs:
                 e._log_accum.zero_()
-            torch.cuda.synchronize(dev)
-            ev0.record()
-            for _ in range(rounds):
-                g2.replay()
-            ev1.record()
-            torch.cuda.synchronize(dev)
-            us = ev0.elapsed_time(ev1) * 1e3 / K
-            rr = float(torch.stack([e._log_accum.sum(dim=0) for e in envs]).sum(dim=0)[0].item()) / (rounds * R * N)
+            us = timed_graphs([[g2]], 50) * 1e3 / (4 * R)
             forced[label] = {"kernel_us": us, "env_steps_per_s_per_gpu": N / (us * 1e-6), "frac_of_hbm_peak": b_alg * N / (us * 1e-6) / 1e9 / peak,
-                             "resets_per_env_step": rr, "max_episode_length": max_len}
+                             "frac_of_hbm_peak_column_set": b_cols * N / (us * 1e-6) / 1e9 / peak,
+                             "resets_per_env_step": sum_resets() / (50 * 4 * R * N), "max_episode_length": max_len}
             del g2
         for e in envs:
             e._gcfg.max_episode_length = cfg.max_episode_length
@@ -307,22 +404,42 @@ def run_ours(args):
         for tk in tickets[-d:]:
             env.wait_host(tk)
 
-    def timed_e2e(n, d):
-        e2e_loop(max(3, args.warmup), d)
-        barrier(world)
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        e2e_loop(n, d)
-        torch.cuda.synchronize(dev)
-        return max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
+    def timed_e2e(n, d, n_reps):
+        """n_reps repetitions of n host-API steps; each repetition synchronised on both sides (the results are in host memory when the
+        clock stops, so host time IS the metric here); per repetition max over ranks, median reported"""
+        e2e_loop(max(3, W), d)
+        out = []
+        for _ in range(n_reps):
+            barrier(world)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            e2e_loop(n, d)
+            torch.cuda.synchronize(dev)
+            out.append((time.perf_counter() - t0) * 1e3)
+        return reduce_vector(out, world, dev, "max")
 
-    Ke = max(10, min(args.steps, 300))
-    e2e_ms = timed_e2e(Ke, depth)
+    Ke = max(1, min(K, 2000))
+    e2e_reps = int(min(100, max(9, 1000.0 / (Ke * 0.105))))
+    if world > 1:
+        e2e_reps = min(e2e_reps, 40)
+    e2e_v = timed_e2e(Ke, depth, e2e_reps)
+    e2e_ms = med(e2e_v)
     e2e_value = world * N * Ke / (e2e_ms * 1e-3)
-    e2e_sync_ms = timed_e2e(Ke, 1)                       # one step in flight: H2D -> kernel -> D2H strictly in sequence
+    e2e_sync_ms = med(timed_e2e(Ke, 1, max(5, e2e_reps // 4)))          # one step in flight: H2D -> kernel -> D2H strictly in sequence
     assert torch.isfinite(h_obs[0]).all() and h_done[0].min() >= 0
     h2d = N * 4 * 4
     d2h = N * 16 * 4 + N * 4 + N * 8
+    probe = copy_only_probe(dev, world, h_act, h_obs, h_rew, h_done, h2d, d2h, Ke)
+
+    # ---- C5: the one collective of the path (NCCL policy-gradient all-reduce) and a whole PPO iteration with it inside the captured
+    # update graph, 65,536 envs per GPU (on_policy_runner.py:135-183)
+    collective = None
+    if not args.no_extra and not args.no_collective:
+        for e in envs[1:]:
+            e.close()
+        del envs[1:]
+        torch.cuda.empty_cache()
+        collective = bench_collective(dev, cfg, table, N, rank, world)
 
     # every collective of this run is behind us: leave the process group BEFORE anything rank 0 does on its own (a module
     # built on rank 0 alone would otherwise wait for the other ranks in its parameter broadcast)
@@ -334,7 +451,8 @@ def run_ours(args):
     # ---- extras: the other kernels of the path (BPTT C3, GAE / add_transitions C2, fused collection), single-GPU runs only
     extra = {}
     if rank == 0 and world == 1 and not args.no_extra:
-        del graph
+        gcache.clear()
+        plans.clear()
         extra = bench_extras(dev, cfg, table)
     if rank == 0 and low is not None:
         extra["fwd_low_reset"] = low
@@ -352,26 +470,34 @@ def run_ours(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": rounds_w * R,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"C4: {N} envs/GPU, STAGE {STAGE}, RacingComplexTerrainCfg gate table (20 types x 10 levels x 8 gates, restated generators, seed 42, no obstacles), per-env DR, "
-                                   f"staggered resets, in-kernel Philox, episode_stats={stats}",
-                       "envs_per_gpu": N, "l2": f"rotating {R} independent env batches ({R}x{working_set / 1e6:.0f} MB > 126 MB L2), "
-                                               f"K timed steps = {rounds} CUDA-graph replays of {R} launches",
+            "config": {"workload": f"C4: {N} envs/GPU, STAGE {STAGE}, RacingComplexTerrainCfg gate table (20 types x 10 levels x 8 gates, the reference's seed-42 table incl. its "
+                                   f"obstacle draws), per-env DR, staggered resets, in-kernel Philox, episode_stats={stats}",
+                       "envs_per_gpu": N, "l2": f"inputs larger than L2: rotating {R} independent env batches ({R}x{working_set / 1e6:.0f} MB > 126 MB L2), "
+                                               f"each repetition = CUDA graphs holding exactly K launches",
                        "mass_kg": cfg.mass, "actions": "N(0, 0.5^2) resident in HBM", "resets_per_env_step": reset_rate},
+            "timing": timing,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "ms_per_step": e2e_ms / Ke,
+                    "ms_per_step": e2e_ms / Ke, "repeats": e2e_reps, "rep_ms_min": float(e2e_v.min()), "rep_ms_max": float(e2e_v.max()),
                     "api": f"RacingVecEnv.step_host -> gr_host_pipe_step/wait (C ABI, pinned HOST buffers: actions in; obs, reward, int64 dones out "
                            f"every step; {depth} steps in flight, results of step t read while step t+1 runs)",
                     "sync_per_step": {"value": world * N * Ke / (e2e_sync_ms * 1e-3), "ms_per_step": e2e_sync_ms / Ke,
-                                      "note": "same call, one step in flight (H2D -> kernel -> D2H in sequence)"}},
+                                      "note": "same call, one step in flight (H2D -> kernel -> D2H in sequence)"},
+                    "copy_only_probe": probe},
             "gpu_launches": K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic("racing_step_fwd_kernel<1,0,1,1>"), "kernel": "racing_step_fwd_kernel<noise,nodiff,philox,stats>",
-                         "bytes_per_env_step": b_alg, "kernel_us": kernel_us, "peak_source": peak_src},
+                         "traffic": ncu_traffic("racing_step_fwd_kernel<1,0,1,1>"),
+                         "traffic_note": "static: one `ncu --set full` capture of this kernel (profiles/traffic.json), not measured in this run; ncu flushes the caches "
+                                         "per launch, so the writes that drain after the kernel's end are not in it",
+                         "kernel": "racing_step_fwd_kernel<noise,nodiff,philox,stats>",
+                         "bytes_per_env_step": b_alg, "bytes_rule": "SURVEY 8(d) contract: 454 B STAGE 0 + 24 B gate-noise reads = 478 B",
+                         "bytes_per_env_step_column_set": b_cols, "achieved_column_set": achieved_cols, "frac_column_set": achieved_cols / peak,
+                         "kernel_us": kernel_us, "peak_source": peak_src},
             "clocks": clk.summary(),
             "cpu_baseline": cpu,
+            "collective": collective,
             "extra": extra,
         }
         if "bptt_fwd_bwd_c3" in extra:          # the second half of BASELINE's metric ("fwd, and fwd+bwd BPTT"), C3 = 16,384 envs x 32
@@ -382,6 +508,105 @@ def run_ours(args):
                                     "training_iteration_with_policy_log_every_20": extra.get("bptt_training_c3", {}).get("fused_kernel_backward_log_every_20", {}).get("env_steps_per_s"),
                                     "cpu_baseline": extra.get("cpu_baseline_fwd_bwd_bptt")}
         print(json.dumps(line))
+
+
+def copy_only_probe(dev, world, h_act, h_obs, h_rew, h_done, h2d, d2h, steps):
+    """The platform's ceiling for the e2e loop: the SAME buffers and sizes, one cudaMemcpyAsync per buffer, H2D on one stream and D2H on
+    another, all ranks concurrently, NO kernel and no dependencies -- what PCIe / the host memory system gives this many GPUs."""
+    N = h_obs[0].shape[0]
+    d_act, d_obs, d_rew, d_done = torch.empty(N, 4, device=dev), torch.empty(N, 16, device=dev), torch.empty(N, device=dev), torch.empty(N, dtype=torch.int64, device=dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    depth = len(h_act)
+
+    def loop(n):
+        for t in range(n):
+            k = t % depth
+            with torch.cuda.stream(s_in):
+                d_act.copy_(h_act[k], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                h_obs[k].copy_(d_obs, non_blocking=True)
+                h_rew[k].copy_(d_rew, non_blocking=True)
+                h_done[k].copy_(d_done, non_blocking=True)
+
+    loop(5)
+    out = []
+    n = max(20, min(steps, 500))
+    for _ in range(9):
+        barrier(world)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        loop(n)
+        torch.cuda.synchronize(dev)
+        out.append((time.perf_counter() - t0) * 1e3)
+    ms = med(reduce_vector(out, world, dev, "max"))
+    return {"us_per_step": ms * 1e3 / n, "aggregate_GBps": world * (h2d + d2h) * n / (ms * 1e-3) / 1e9, "per_gpu_GBps": (h2d + d2h) * n / (ms * 1e-3) / 1e9,
+            "env_steps_per_s_ceiling": world * N * n / (ms * 1e-3),
+            "what": f"copies only (same pinned buffers, {h2d} B H2D + {d2h} B D2H per step, two streams, {world} rank(s) concurrently): the platform limit of the e2e loop"}
+
+
+def bench_collective(dev, cfg, table, N, rank, world, T: int = 24):
+    """BASELINE C5: env-sharded N envs per GPU with the NCCL policy-gradient all-reduce.  (1) the all-reduce alone, on the flat buffer of
+    algorithms/ppo.py (all gradients + loss / KL sums), replayed from a CUDA graph; (2) one whole PPO iteration -- fused 24-step
+    collection (gr_ppo_collect), GAE with globally merged moments, 5 x 4 mini-batch steps from libgracing kernels with the all-reduce
+    INSIDE the captured step graph -- device-timed, max over ranks.  Runs at world == 1 too (no collective) so that the 1 -> N curve of
+    the training iteration has its base point."""
+    from generalizableracing_b200.env import RacingVecEnv
+    from generalizableracing_b200.runners import OnPolicyRunner
+    out = {"envs_per_gpu": N, "steps_per_env": T, "world": world}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    agent = {"num_steps_per_env": T, "save_interval": 10 ** 9, "empirical_normalization": False, "fused_collection": True,
+             "policy": {"class_name": "ActorCritic", "init_noise_std": 1.0, "actor_hidden_dims": [128, 128], "critic_hidden_dims": [128, 128], "activation": "lrelu"},
+             "algorithm": {"class_name": "PPO", "value_loss_coef": 1.0, "use_clipped_value_loss": True, "clip_param": 0.2, "entropy_coef": 0.0,
+                           "num_learning_epochs": 5, "num_mini_batches": 4, "learning_rate": 5.0e-4, "schedule": "adaptive", "gamma": 0.99, "lam": 0.95,
+                           "desired_kl": 0.01, "max_grad_norm": 1.0, "graphed_update": True, "kernel_update": True}}
+    env = RacingVecEnv(cfg, table, N, device=dev, seed=9, env_id_offset=rank * N, global_num_envs=world * N)
+    runner = OnPolicyRunner(env, agent, log_dir=None, device=str(dev))
+    runner.learn(3, init_at_random_ep_len=True)          # eager first update, graph capture on the second
+    iters = 10
+    per_it = []
+    for _ in range(3):
+        barrier(world)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        runner.learn(iters)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        per_it.append(e0.elapsed_time(e1) / iters)
+    ms = med(reduce_vector(per_it, world, dev, "max"))
+    flat = runner.alg._graph["flat_grad"]
+    out["ppo_iteration"] = {"ms_per_iteration": ms, "env_steps_per_s": world * N * T / (ms * 1e-3), "allreduces_per_iteration": 20 if world > 1 else 0,
+                            "what": "gr_ppo_collect (24 steps, tcgen05 policy) + GAE + 20 captured mini-batch steps (gather, forward, loss grads, tcgen05 weight grads, "
+                                    "[NCCL all-reduce of the flat gradient buffer], clip + Adam), max over ranks, median of 3 x 10 iterations"}
+    if world > 1:
+        import torch.distributed as dist
+        buf = torch.zeros_like(flat)
+        for _ in range(5):
+            dist.all_reduce(buf)
+        torch.cuda.synchronize(dev)
+        gr = torch.cuda.CUDAGraph()
+        n_in = 20
+        with torch.cuda.graph(gr):
+            for _ in range(n_in):
+                dist.all_reduce(buf)
+        gr.replay()
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(30):
+            e0.record()
+            gr.replay()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1) * 1e3 / n_in)
+        us = reduce_vector(ts, world, dev, "max")
+        out["allreduce"] = {"us": med(us), "us_min": float(us.min()), "us_max": float(us.max()), "floats": int(flat.numel()), "bytes": int(flat.numel()) * 4,
+                            "what": "dist.all_reduce (NCCL, sum) of the flat policy-gradient buffer (all 13 parameter gradients + 16 loss / KL sums), 20 per CUDA-graph "
+                                    "replay, device-timed, max over ranks, median of 30 replays"}
+        del gr
+    runner.alg.close()
+    env.close()
+    del runner, env
+    torch.cuda.empty_cache()
+    return out
 
 
 def bench_extras(dev, cfg, table):
@@ -830,6 +1055,8 @@ def main():
     ap.add_argument("--no-stats", action="store_true", help="drop the per-env episode-sum planes (extras['log'] reward terms)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-collective", action="store_true", help="skip the C5 block (all-reduce + PPO iteration at 65,536 envs per GPU)")
+    ap.add_argument("--repeats", type=int, default=0, help="timed repetitions of the K-step region (0 = ~1.2 s worth, between 100 and 8000)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -593,7 +593,8 @@ def make_env(task: str = "DiffLab-Quadcopter-CTBR-Racing-v0", num_envs: int = 20
              differentiable: bool = False, **kwargs) -> RacingVecEnv:
     """``gym.make(task, cfg=env_cfg)`` + ``RslRlVecEnvWrapper`` of the reference launch scripts (standalone/rsl_rl/train.py:102-120)
     for the one registered racing task (QD/__init__.py:48-73).  ``track``: "complex" = the 20x10 curriculum table of
-    RacingComplexTerrainCfg built by the restated family generators (track_gen.py; obstacle-free), "synthetic" = the
+    RacingComplexTerrainCfg built by the restated family generators (track_gen.py; the reference's own seed-42 table: its obstacle
+    draws are replayed, no obstacle geometry exists), "synthetic" = the
     simplified centre-line table of tracks.py, "figure8" = RacingTestTerrainCfg.  Under torchrun the envs are sharded."""
     from . import dist_utils as D
     from .tracks import figure_eight_track, synthetic_track_table

@@ -18,9 +18,11 @@ The reference draws from the two GLOBAL streams ``random`` and ``np.random`` (se
 are explicit objects (``random.Random`` / ``np.random.RandomState`` = the same MT19937 streams), consumed in exactly the
 reference's order, with the same numpy expressions and dtypes, so that for a given stream state a family returns bit-identical
 ``gate_pose`` / ``origin`` / ``next_gate_id`` (tests/test_track_gen.py runs the unmodified reference functions, with the mesh
-library stubbed out, against these).  Obstacle / wall / ground MESHES are out of scope (trimesh + Warp + USD): the families are
-restated for ``add_obs=False``; with obstacles on the reference consumes extra draws *after* a tile's gates and origin are
-fixed, so single tiles still agree but the stream position of the following tile does not.
+library stubbed out, against these).  Obstacle / wall / ground MESHES are out of scope (trimesh + Warp + USD), but with
+``add_obs=True`` (the setting of all three families in RacingComplexTerrainCfg, QD/terrains/racing_terrains.py:163,184,204) the
+reference consumes draws for them *after* a tile's gates and origin are fixed, which moves the stream position of every FOLLOWING
+tile.  ``_ObstacleReplay`` therefore replays exactly those draws -- the scatter points with their rejection loops, wall sizes, the
+shape lotteries of L/terrains/trimesh/utils.py:56-134 -- without building any geometry, so the whole 20 x 10 table is the reference's.
 """
 from __future__ import annotations
 
@@ -55,7 +57,17 @@ class _FamilyCfg:
     pos_noise_scale: Sequence[float] = (0.2, 1.0)
     rot_noise_scale: Sequence[float] = (0.0, 30.0)
     only_yaw: bool = True
+    # obstacle branch: only the stream position of the following tiles depends on these (L/terrains/trimesh/racing_terrains_cfg.py)
     add_obs: bool = False
+    add_ground_obs: bool = False
+    num_ground_obs: Sequence[float] = (1, 4)
+    num_wall_seg: Sequence[float] = (1, 5)
+    wall_size: Sequence[float] = (0.4, 1.0)
+    wall_thickness: Sequence[float] = (0.04, 0.08)
+    num_orbit_seg: Sequence[float] = (1, 5)
+    adj_dir_shift_prop: Sequence[float] = (0.2, 0.5)
+    radius_dir_shift_prop: Sequence[float] = (0.2, 0.5)
+    no_obs_range: float = 0.8
 
 
 @dataclass
@@ -69,6 +81,8 @@ class ZigzagTrackCfg(_FamilyCfg):
     track_length: float = 35.0
     pos_noise_scale: Sequence[float] = (1.0, 4.0)
     pos_z_noise_scale: Sequence[float] = (0.1, 1.0)
+    adj_dir_shift_prop: Sequence[float] = (1, 2)
+    radius_dir_shift_prop: Sequence[float] = (10, 10)
 
 
 @dataclass
@@ -76,6 +90,8 @@ class EllipseTrackCfg(_FamilyCfg):
     gate_distance: float = 5.0
     short_axis_prop: Sequence[float] = (1.414, 0.8)
     long_axis_prop: Sequence[float] = (3.1414, 4.8)
+    adj_dir_shift_prop: Sequence[float] = (1, 2)
+    radius_dir_shift_prop: Sequence[float] = (10, 10)
 
 
 @dataclass
@@ -104,6 +120,138 @@ def _pose6(gate_pts, gate_euler):
     pose[:, 0:3] = gate_pts
     pose[:, 3:6] = gate_euler
     return pose
+
+
+class _ObstacleReplay:
+    """Draw-only replay of the obstacle branch of one track segment.  Geometry is never built; what is reproduced is the ORDER and
+    COUNT of the draws on the two streams (and the few values that steer them: the collinearity rejection loop, the zigzag
+    family's keep-out test around the gates), so that the next tile starts from the reference's stream position."""
+
+    def __init__(self, s: Streams, cfg: _FamilyCfg, difficulty: float, lateral_scale: float, probe_range: float):
+        self.s, self.cfg = s, cfg
+        self.adj = _lerp(cfg.adj_dir_shift_prop, difficulty)
+        self.lat = _lerp(cfg.radius_dir_shift_prop, difficulty)
+        self.lateral_scale = lateral_scale      # what the unit lateral offset is multiplied with (ring radius / gate distance / half gate size)
+        self.probe_range = probe_range          # range of the random vector crossed with the segment direction (10 or 1)
+
+    def segment(self, a, b):
+        self.mid, self.vec = (a + b) / 2, b - a
+
+    def scatter(self, along=None):
+        """a point next to the segment: along-track shift, then a lateral shift along (segment x random vector)"""
+        s = self.s.np
+        along = self.adj if along is None else along
+        off1 = self.vec / 2 * s.uniform(-along, along)
+        while True:
+            cross = np.cross(self.vec, s.uniform(-self.probe_range, self.probe_range, 3))
+            if not np.allclose(cross, np.zeros(3)):
+                break
+        off2 = cross / np.linalg.norm(cross) * s.uniform(-self.lat, self.lat) * self.lateral_scale
+        return self.mid + off1 + off2
+
+    def raise_point(self, pt):
+        pt[2] = self.s.py.uniform(0.5, 3.0)
+        return pt
+
+    def wall(self):
+        s, c = self.s.np, self.cfg
+        s.uniform(-180, 180, 3)
+        s.uniform(c.wall_size[0], c.wall_size[1], 2)
+        s.uniform(c.wall_thickness[0], c.wall_thickness[1])
+
+    def orbit(self):
+        """utils.py:56-83 (`make_orbit`): euler first (argument), then the shape lottery"""
+        s = self.s
+        s.np.uniform(-180, 180, 3)
+        prob = s.py.random()
+        if prob < 0.2:
+            s.np.uniform(0.1, 0.5, 3)
+        elif 0.4 <= prob < 0.6:
+            s.np.uniform(0.1, 0.3)
+        else:                                   # cylinder, capsule (the reference's cone branch is unreachable: 0.8 <= p < 0.8)
+            s.np.uniform(0.1, 0.3)
+            s.np.uniform(0.2, 0.6)
+
+    def ground_pillar(self):
+        """utils.py:85-104 (`make_ground_high_obs`)"""
+        s = self.s
+        s.np.uniform(-180, 180, 3)
+        s.py.uniform(0.0, 2.0)
+        if s.py.random() < 0.5:
+            s.np.uniform(0.05, 1.0, 2)
+        else:
+            s.np.uniform(0.025, 0.5)
+
+    def ground_clutter(self):
+        """utils.py:106-134 (`make_ground_little_obj`)"""
+        s = self.s
+        s.np.uniform(-180, 180, 3)
+        prob = s.py.random()
+        if prob < 0.33:
+            s.np.uniform(0.1, 1.5, 3)
+            s.py.uniform(-0.2, 0.5)
+        elif prob < 0.66:
+            s.py.uniform(0.025, 0.5)
+            s.py.uniform(0.1, 1.0)
+            s.py.uniform(-0.2, 0.5)
+        else:
+            radius = s.py.uniform(0.05, 0.5)
+            s.py.uniform(-radius, radius)
+            s.py.uniform(-0.2, 0.5)
+
+
+def _closed_loop_obstacles(rp: _ObstacleReplay, pts, start_seg: int, n_wall: int, n_orbit: int, n_ground: int, clutter_hi: int):
+    """Ring / ellipse families (racing_terrains.py:266-321, 751-812): every segment but the spawn segment gets a fixed number of
+    walls, orbits, ground pillars and 1..clutter_hi small ground objects."""
+    n = pts.shape[0]
+    for i in range(n):
+        if i == start_seg:
+            continue
+        rp.segment(pts[i], pts[(i + 1) % n])
+        for _ in range(n_wall):
+            rp.raise_point(rp.scatter())
+            rp.wall()
+        for _ in range(n_orbit):
+            rp.raise_point(rp.scatter())
+            rp.orbit()
+        if rp.cfg.add_ground_obs:
+            for _ in range(n_ground):
+                rp.scatter()
+                rp.ground_pillar()
+            for _ in range(rp.s.py.randint(1, clutter_hi)):
+                rp.scatter()
+                rp.ground_clutter()
+
+
+def _open_line_obstacles(rp: _ObstacleReplay, pts, n_wall: int, n_orbit: int, n_ground: int):
+    """Zigzag family (racing_terrains.py:511-603): between consecutive gates, candidates closer than `no_obs_range` to either gate
+    are redrawn (walls, orbits: 3-D distance after the height draw; ground objects: planar distance); clutter candidates inside
+    the range are dropped, not redrawn."""
+    keep_out = rp.cfg.no_obs_range
+    for i in range(pts.shape[0] - 1):
+        a, b = pts[i], pts[i + 1]
+        rp.segment(a, b)
+        for count, finish in ((n_wall, rp.wall), (n_orbit, rp.orbit)):
+            placed = 0
+            while placed < count:
+                pt = rp.raise_point(rp.scatter())
+                if np.linalg.norm(pt - a) < keep_out or np.linalg.norm(pt - b) < keep_out:
+                    continue
+                finish()
+                placed += 1
+        if rp.cfg.add_ground_obs:
+            placed = 0
+            while placed < n_ground:
+                pt = rp.scatter()
+                if np.linalg.norm(pt[:2] - a[:2]) < keep_out or np.linalg.norm(pt[:2] - b[:2]) < keep_out:
+                    continue
+                rp.ground_pillar()
+                placed += 1
+            for _ in range(rp.s.py.randint(1, 4)):
+                pt = rp.scatter(along=0.5)
+                if np.linalg.norm(pt[:2] - a[:2]) < keep_out or np.linalg.norm(pt[:2] - b[:2]) < keep_out:
+                    continue
+                rp.ground_clutter()
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -144,7 +292,9 @@ def square_track(difficulty: float, cfg: SquareTrackCfg, s: Streams):
     origin = pts[nxt] - reverse * s.py.uniform(2, 4) * np.array([np.cos(heading), np.sin(heading), 0])
     origin[2] = s.py.uniform(0.7, 1.5)
     if cfg.add_obs:
-        raise NotImplementedError("obstacle meshes are out of scope (restated for add_obs=False)")
+        _closed_loop_obstacles(_ObstacleReplay(s, cfg, difficulty, lateral_scale=radius, probe_range=10), pts, start_seg,
+                               int(_lerp(cfg.num_wall_seg, difficulty) * radius / cfg.radius[1]), int(_lerp(cfg.num_orbit_seg, difficulty) * radius / cfg.radius[1]),
+                               int(_lerp(cfg.num_ground_obs, difficulty) * radius / cfg.radius[1]), clutter_hi=4)
     return _pose6(pts, eul), origin, nxt
 
 
@@ -208,7 +358,8 @@ def zigzag_track(difficulty: float, cfg: ZigzagTrackCfg, s: Streams):
     origin = pts[0].copy() - first_dir * s.py.uniform(2, 3)
     origin[2] = s.py.uniform(0.7, 1.5)
     if cfg.add_obs:
-        raise NotImplementedError("obstacle meshes are out of scope (restated for add_obs=False)")
+        _open_line_obstacles(_ObstacleReplay(s, cfg, difficulty, lateral_scale=cfg.gate_size[1] / 2, probe_range=1), pts,
+                             int(_lerp(cfg.num_wall_seg, difficulty)), int(_lerp(cfg.num_orbit_seg, difficulty)), int(_lerp(cfg.num_ground_obs, difficulty)))
     return _pose6(pts, eul), origin, 0
 
 
@@ -265,7 +416,9 @@ def ellipse_track(difficulty: float, cfg: EllipseTrackCfg, s: Streams):
     origin = pts[start_seg % n] + seg * s.py.uniform(2, 3)
     origin[2] = s.py.uniform(0.7, 1.5)
     if cfg.add_obs:
-        raise NotImplementedError("obstacle meshes are out of scope (restated for add_obs=False)")
+        _closed_loop_obstacles(_ObstacleReplay(s, cfg, difficulty, lateral_scale=cfg.gate_distance, probe_range=10), pts, start_seg,
+                               int(_lerp(cfg.num_wall_seg, difficulty)), int(_lerp(cfg.num_orbit_seg, difficulty)), int(_lerp(cfg.num_ground_obs, difficulty)),
+                               clutter_hi=2)
     return _pose6(pts, eul), origin, nxt
 
 
@@ -299,13 +452,19 @@ class TrackGeneratorCfg:
     curriculum: bool = True
 
 
-def racing_complex_cfg() -> TrackGeneratorCfg:
-    """RacingComplexTerrainCfg (QD/terrains/racing_terrains.py:137-211), obstacle-free."""
+def racing_complex_cfg(add_obs: bool = True) -> TrackGeneratorCfg:
+    """RacingComplexTerrainCfg (QD/terrains/racing_terrains.py:137-211).  ``add_obs=True`` is the reference's setting: no obstacle
+    geometry exists here, but its draws are replayed so the gate table is the one the reference builds from seed 42;
+    ``add_obs=False`` gives the obstacle-free variant of the same families (a different table from the second tile on)."""
     size = (40.0, 40.0)
+    obs = dict(add_obs=add_obs, add_ground_obs=True, wall_size=(0.4, 1.0), wall_thickness=(0.04, 0.08), adj_dir_shift_prop=(0.6, 0.6))
     return TrackGeneratorCfg(size=size, num_rows=10, num_cols=20, seed=42, sub_terrains={
-        "zigzag": ZigzagTrackCfg(proportion=0.3, size=size, track_length=35.0, num_gate=8, pos_noise_scale=(1.0, 4.0), pos_z_noise_scale=(0.1, 1.0)),
-        "circular": SquareTrackCfg(proportion=0.3, size=size, radius=(5.0, 8.0), num_gate=8),
-        "ellipse": EllipseTrackCfg(proportion=0.4, size=size, gate_distance=5.0, num_gate=8)})
+        "zigzag": ZigzagTrackCfg(proportion=0.3, size=size, track_length=35.0, num_gate=8, pos_noise_scale=(1.0, 4.0), pos_z_noise_scale=(0.1, 1.0),
+                                 num_wall_seg=(2, 6), num_orbit_seg=(2, 6), num_ground_obs=(1, 4), radius_dir_shift_prop=(6, 6), no_obs_range=1.5, **obs),
+        "circular": SquareTrackCfg(proportion=0.3, size=size, radius=(5.0, 8.0), num_gate=8,
+                                   num_wall_seg=(1, 4), num_orbit_seg=(1, 4), num_ground_obs=(1, 4), radius_dir_shift_prop=(0.5, 0.5), **obs),
+        "ellipse": EllipseTrackCfg(proportion=0.4, size=size, gate_distance=5.0, num_gate=8,
+                                   num_wall_seg=(1, 4), num_orbit_seg=(1, 4), num_ground_obs=(1, 2), radius_dir_shift_prop=(0.5, 0.5), **obs)})
 
 
 def racing_test_cfg() -> TrackGeneratorCfg:

@@ -107,9 +107,12 @@ def outer_loop_cfg(cfg):
 
 
 def load_track_families():
-    """The reference's track-family functions (L/terrains/trimesh/racing_terrains.py), executed where they lie with the mesh
-    layer stubbed out: ``trimesh`` and the ``make_*`` helpers of L/terrains/trimesh/utils.py build meshes only (out of
-    scope) and, for ``add_obs=False``, draw no random numbers, so gate poses / origins / next_gate_id are the reference's."""
+    """The reference's track-family functions (L/terrains/trimesh/racing_terrains.py) AND its mesh helpers
+    (L/terrains/trimesh/utils.py: make_gate / make_wall / make_orbit / make_ground_high_obs / make_ground_little_obj), executed
+    unmodified where they lie.  Only the third-party ``trimesh`` package (absent here) is stubbed: its constructors return an inert
+    object, so no geometry is built, but every ``random`` / ``np.random`` draw of the reference -- including the obstacle branch
+    (``add_obs=True``) and the shape lotteries inside the mesh helpers -- happens exactly as in the reference, which is what fixes
+    the gate poses / origins / next_gate_id of every FOLLOWING tile."""
     if "tracks" in _cache:
         return _cache["tracks"]
     if not available():
@@ -121,20 +124,35 @@ def load_track_families():
             m.__path__ = []
             sys.modules[name] = m
     sys.modules["omni.isaac.lab.terrains.trimesh.utils"].make_border = lambda *a, **k: []
-    tm = types.SimpleNamespace(creation=types.SimpleNamespace(box=lambda *a, **k: None),
-                               transformations=types.SimpleNamespace(translation_matrix=lambda *a, **k: None))
-    pkg = types.ModuleType("_gr_ref_trimesh_terrains")
-    pkg.__path__ = []                                   # no real path: the stub below IS the package's `utils`
-    sys.modules["_gr_ref_trimesh_terrains"] = pkg
-    utils = types.ModuleType("_gr_ref_trimesh_terrains.utils")
-    import random as _r
-    import numpy as _np
-    import scipy.spatial.transform as _tf
-    utils.np, utils.tf, utils.random, utils.trimesh = _np, _tf, _r, tm
-    for fn in ("make_gate", "make_wall", "make_orbit", "make_ground_high_obs", "make_ground_little_obj"):
-        setattr(utils, fn, lambda *a, **k: None)
-    sys.modules["_gr_ref_trimesh_terrains.utils"] = utils
-    mod = _load("_gr_ref_trimesh_terrains.racing_terrains", os.path.join(REF_ROOT, _L, "terrains/trimesh/racing_terrains.py"))
+
+    class _InertMesh:
+        def difference(self, other):
+            return self
+
+        def apply_transform(self, m):
+            return self
+
+        def apply_translation(self, t):
+            return self
+
+    mk = lambda *a, **k: _InertMesh()
+    had_trimesh = sys.modules.get("trimesh")
+    tm = types.ModuleType("trimesh")
+    tm.Trimesh = _InertMesh
+    tm.creation = types.SimpleNamespace(box=mk, cylinder=mk, icosphere=mk, cone=mk, capsule=mk)
+    tm.transformations = types.SimpleNamespace(translation_matrix=lambda *a, **k: None, euler_matrix=lambda *a, **k: None)
+    sys.modules["trimesh"] = tm
+    try:
+        pkg = types.ModuleType("_gr_ref_trimesh_terrains")
+        pkg.__path__ = [os.path.join(REF_ROOT, _L, "terrains/trimesh")]
+        sys.modules["_gr_ref_trimesh_terrains"] = pkg
+        _load("_gr_ref_trimesh_terrains.utils", os.path.join(REF_ROOT, _L, "terrains/trimesh/utils.py"))
+        mod = _load("_gr_ref_trimesh_terrains.racing_terrains", os.path.join(REF_ROOT, _L, "terrains/trimesh/racing_terrains.py"))
+    finally:
+        if had_trimesh is None:
+            sys.modules.pop("trimesh", None)
+        else:
+            sys.modules["trimesh"] = had_trimesh
     ns = types.SimpleNamespace(square=mod.SquareRacingTrackTerrain, zigzag=mod.ZigzagRacingTerrain, ellipse=mod.EllipseRacingTerrain,
                                figure_eight=mod.FigureEightTrackTerrain)
     _cache["tracks"] = ns
