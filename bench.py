@@ -66,9 +66,9 @@ def algorithmic_bytes(cfg, stats: bool, critic: bool = True, dones64: bool = Tru
         wr += 8
     if cfg.add_cmd_noise:
         rd += 32                                   # gate-noise planes (read-only except on gate switch / reset)
-    if stats:
-        rd += 32
-        wr += 32
+    if stats:                                      # episode sums of reward terms 0..3 (terms 4, 5 ride in spare words of the hot planes)
+        rd += 16
+        wr += 16
     return rd + wr
 
 
@@ -477,7 +477,8 @@ def run_ours(args):
                                    f"obstacle draws), per-env DR, staggered resets, in-kernel Philox, episode_stats={stats}",
                        "envs_per_gpu": N, "l2": f"inputs larger than L2: rotating {R} independent env batches ({R}x{working_set / 1e6:.0f} MB > 126 MB L2), "
                                                f"each repetition = CUDA graphs holding exactly K launches",
-                       "mass_kg": cfg.mass, "actions": "N(0, 0.5^2) resident in HBM", "resets_per_env_step": reset_rate},
+                       "mass_kg": cfg.mass, "actions": "N(0, 0.5^2) resident in HBM", "resets_per_env_step": reset_rate,
+                       "prefetch": os.environ.get("GRACING_PREFETCH", "1")},
             "timing": timing,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                     "ms_per_step": e2e_ms / Ke, "repeats": e2e_reps, "rep_ms_min": float(e2e_v.min()), "rep_ms_max": float(e2e_v.max()),
@@ -1053,12 +1054,15 @@ def main():
     ap.add_argument("--envs", type=int, default=NUM_ENVS, help="envs per GPU (BASELINE configs[3]: 65536)")
     ap.add_argument("--block-threads", type=int, default=0, help="threads per block of the step kernel (0 = library default)")
     ap.add_argument("--no-stats", action="store_true", help="drop the per-env episode-sum planes (extras['log'] reward terms)")
+    ap.add_argument("--prefetch", default=None, choices=["0", "1", "l2"], help="GRACING_PREFETCH for this run (read-mostly planes before the grid dependency)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-collective", action="store_true", help="skip the C5 block (all-reduce + PPO iteration at 65,536 envs per GPU)")
     ap.add_argument("--repeats", type=int, default=0, help="timed repetitions of the K-step region (0 = ~1.2 s worth, between 100 and 8000)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
+    if args.prefetch is not None:
+        os.environ["GRACING_PREFETCH"] = args.prefetch
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -51,7 +51,8 @@ class GrRandom(C.Structure):
 class GrStepIO(C.Structure):
     _fields_ = [("action", c_p), ("obs", c_p), ("critic_obs", c_p), ("aux_obs", c_p), ("reward", c_p),
                 ("terminated", c_p), ("time_out", c_p), ("dones", c_p), ("reward_terms", c_p), ("gate_passed", c_p),
-                ("loss", c_p), ("loss_terms", c_p), ("tape", c_p), ("tape_stride", C.c_int64), ("phase_times", c_p), ("log_accum", c_p)]
+                ("loss", c_p), ("loss_terms", c_p), ("tape", c_p), ("tape_stride", C.c_int64), ("phase_times", c_p), ("log_accum", c_p),
+                ("aligned_states", c_p), ("acc", c_p)]
 
 
 class GrBwdIO(C.Structure):
@@ -127,7 +128,10 @@ class GrHostStep(C.Structure):
 GR_HOST_PIPE_MAX_DEPTH = 4
 GR_LAUNCH_PDL = 1
 GR_LAUNCH_PREFETCH = 2
+GR_LAUNCH_PREFETCH_L2 = 4
 GR_LOG_SLOTS = 16
+GR_LOG_NUM_RESET, GR_LOG_SUM_GATES, GR_LOG_SUM_EPSUM, GR_LOG_NUM_TIMEOUT, GR_LOG_NUM_TERMINATED = 0, 1, 2, 8, 9
+GR_LOG_SUM_ACTION_RATE, GR_LOG_SUM_LIN_SPD, GR_LOG_SUM_ANG_SPD, GR_LOG_SUM_LOSS = 10, 11, 12, 13
 class GrReachConfig(C.Structure):
     _fields_ = [
         ("controller", c_i), ("sim2real_test", c_i), ("last_action_modified", c_i), ("random_drag", c_i),
@@ -238,7 +242,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.gr_abi_version() != 1:
+    if lib.gr_abi_version() != 2:
         raise ImportError("libgracing.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -67,8 +67,8 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) bptt_collect_kernel(const Gr
   float4* __restrict__ tile = tile_ptr(reinterpret_cast<float4*>(st.planes), li);
   EnvRegs e;
   load_env<kNoise>(e, tile);
-  float4 eps0 = make_float4(0.f, 0.f, 0.f, 0.f), eps1 = eps0;
-  if (kStats) { eps0 = ld_plane(tile, PL_EPSUM0); eps1 = ld_plane(tile, PL_EPSUM1); }
+  float4 eps0 = make_float4(0.f, 0.f, 0.f, 0.f), lsum = eps0;
+  if (kStats) { eps0 = ld_plane(tile, PL_EPSUM0); lsum = ld_plane(tile, PL_LOSSSUM); }
   const float4 sigma = *reinterpret_cast<const float4*>(pol.sigma);
   bool any_reset = false, any_noise_dirty = false, last_noise_dirty = false;
   const int64_t tape_step = (int64_t)(cio.tape_stride / kTile) * GR_TAPE_PLANES * kTile * 4;       // floats per tape step
@@ -127,13 +127,10 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) bptt_collect_kernel(const Gr
     sink.aux_ptr = (last && cio.aux_out) ? cio.aux_out + i : nullptr;
     sink.policy_pk = policy_pk;
     StepOut so;
-    const bool alive = racing_step_body<kNoise, true, true, kStats>(cfg, tr, e, a_t, n01, n23, draws, eps0, eps1, io, i, active, sink, so);
+    const bool alive = racing_step_body<kNoise, true, true, kStats>(cfg, tr, e, a_t, n01, n23, draws, eps0, lsum, io, i, active, sink, so);
     write_x_row(g.hrow, policy_pk[0], policy_pk[1]);              // layer 3 has been read: the tile is free for the next step's operand
     if (alive) {
-      if (kStats && !so.reset) {
-#pragma unroll
-        for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k) { if (k < 4) (&eps0.x)[k] += so.terms[k] * cfg.dt; else (&eps1.x)[k - 4] += so.terms[k] * cfg.dt; }
-      }
+      if (kStats && !so.reset) add_episode_sums(eps0, e, so.terms, cfg.dt);
       any_reset |= so.reset;
       any_noise_dirty |= so.noise_dirty;
       last_noise_dirty = so.noise_dirty;
@@ -144,8 +141,9 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) bptt_collect_kernel(const Gr
 
   if (active) {
     store_env<kNoise>(e, tile, any_reset, any_noise_dirty);
-    if (kNoise && any_noise_dirty && !last_noise_dirty) st_plane(tile, PL_ANGACC, pack(e.aacc, 0.0f));
-    if (kStats) { st_plane(tile, PL_EPSUM0, eps0); st_plane(tile, PL_EPSUM1, eps1); }
+    if (kNoise && any_noise_dirty && !last_noise_dirty)      // the flag means "rewritten by the LAST step"
+      st_plane(tile, PL_LINVEL, pack(e.v, __uint_as_float(eplen_word(e.eplen, e.aux != 0.0f, false, e.arate, e.metrics_zero))));
+    if (kStats) { st_plane(tile, PL_EPSUM0, eps0); st_plane(tile, PL_LOSSSUM, lsum); }
   }
   tc_fence_before_sync();
   __syncthreads();

@@ -16,10 +16,11 @@ namespace gr {
 // tile: its 16 plane loads are consecutive 512 B rows of the same 8 KB block, so DRAM serves them together and warps
 // complete their loads one after the other (load -> compute -> store pipelines ACROSS warps).  With plane-major arrays
 // the memory system streams plane by plane and every warp gets its last plane only at the end of the transfer.
-// Written planes come first (0..8 = 4.5 KB contiguous write-back), read-mostly planes after.
+// Written planes come first (0..7, plus 8 in differentiable mode), read-mostly planes after.
 enum Plane : int {
   PL_QUAT = 0, PL_POS = 1, PL_LINVEL = 2, PL_ANGVEL = 3, PL_TORQUE = 4, PL_ANGACC = 5, PL_FIFO = 6,
-  PL_EPSUM0 = 7, PL_EPSUM1 = 8,
+  PL_EPSUM0 = 7,      // episode sums of reward terms 0..3 (terms 4, 5: PL_TORQUE.w / PL_ANGACC.w)            -- with episode sums on
+  PL_LOSSSUM = 8,     // LossManager episode sums of the 3 loss terms | spare                              -- sums on + differentiable
   PL_DRAG2 = 9, PL_DRAG1 = 10, PL_KP = 11, PL_KD = 12, PL_ETAU = 13, PL_NOISE0 = 14, PL_NOISE1 = 15
 };
 constexpr int kTile = 32, kTilePlanes = 16;
@@ -44,6 +45,12 @@ __device__ __forceinline__ float4* tile_ptr(float4* base, int i) { return base +
 __device__ __forceinline__ float4 ld_plane(const float4* __restrict__ tile, int plane) { return __ldcs(tile + plane * kTile); }
 __device__ __forceinline__ float4 ld_plane_ro(const float4* __restrict__ tile, int plane) { return __ldg(tile + plane * kTile); }
 __device__ __forceinline__ void st_plane(float4* __restrict__ tile, int plane, float4 v) { __stcs(tile + plane * kTile, v); }
+// pull the line holding *p into L2 (no register, no L1 allocation)
+__device__ __forceinline__ void prefetch_l2_line(const void* p) {
+#ifndef GR_CPU_EMUL
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
 
 // Random source.  normals8() returns slots 0..7 (standard normals), get4(call >= 2) returns the uniform slots
 // [4*call, 4*call+4).  Dense mode reads the caller's tensor; Philox mode generates: the eight normals come from ONE

@@ -97,8 +97,8 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
   float4* __restrict__ tile = tile_ptr(reinterpret_cast<float4*>(st.planes), li);
   EnvRegs e;
   load_env<kNoise>(e, tile);
-  float4 eps0 = make_float4(0.f, 0.f, 0.f, 0.f), eps1 = eps0;
-  if (kStats) { eps0 = ld_plane(tile, PL_EPSUM0); eps1 = ld_plane(tile, PL_EPSUM1); }
+  float4 eps0 = make_float4(0.f, 0.f, 0.f, 0.f), lsum = eps0;
+  if (kStats) { eps0 = ld_plane(tile, PL_EPSUM0); }
   float2 epacc = cio.episode_acc ? reinterpret_cast<const float2*>(cio.episode_acc)[li] : make_float2(0.f, 0.f);
   const float4 sigma = *reinterpret_cast<const float4*>(pol.sigma);
   const float4 log_sigma = make_float4(logf(sigma.x), logf(sigma.y), logf(sigma.z), logf(sigma.w));
@@ -182,16 +182,13 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
     sink.policy_pk = policy_pk;
     sink.critic_pk = critic_pk;
     StepOut so;
-    const bool alive = racing_step_body<kNoise, false, true, kStats>(cfg, tr, e, a_t, n01, n23, draws, eps0, eps1, io, i, active, sink, so);
+    const bool alive = racing_step_body<kNoise, false, true, kStats>(cfg, tr, e, a_t, n01, n23, draws, eps0, lsum, io, i, active, sink, so);
 
     stage_wait(g);
     epilogue2<NL>(g, critic_smem);
     stage_issue<NL>(g, critic_addr, kL3);
     if (alive) {
-      if (kStats && !so.reset) {
-#pragma unroll
-        for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k) { if (k < 4) (&eps0.x)[k] += so.terms[k] * cfg.dt; else (&eps1.x)[k - 4] += so.terms[k] * cfg.dt; }
-      }
+      if (kStats && !so.reset) add_episode_sums(eps0, e, so.terms, cfg.dt);
       any_reset |= so.reset;
       any_noise_dirty |= so.noise_dirty;
       last_noise_dirty = so.noise_dirty;
@@ -227,8 +224,9 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
     // ---- env state -> HBM (once per rollout).  Every env that reset at ANY step rewrote its read-mostly planes: the
     // caller clears GR_LAUNCH_PREFETCH for the next single-step launch (env.py).
     store_env<kNoise>(e, tile, any_reset, any_noise_dirty);
-    if (kNoise && any_noise_dirty && !last_noise_dirty) st_plane(tile, PL_ANGACC, pack(e.aacc, 0.0f));   // the flag means "rewritten by the LAST step"
-    if (kStats) { st_plane(tile, PL_EPSUM0, eps0); st_plane(tile, PL_EPSUM1, eps1); }
+    if (kNoise && any_noise_dirty && !last_noise_dirty)      // the flag means "rewritten by the LAST step"
+      st_plane(tile, PL_LINVEL, pack(e.v, __uint_as_float(eplen_word(e.eplen, e.aux != 0.0f, false, e.arate, e.metrics_zero))));
+    if (kStats) { st_plane(tile, PL_EPSUM0, eps0); }
     if (cio.episode_acc) reinterpret_cast<float2*>(cio.episode_acc)[i] = epacc;
   }
   tc_fence_before_sync();

@@ -26,11 +26,11 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
   const bool pdl = (st.launch_flags & GR_LAUNCH_PDL) != 0;
   GR_STAMP(0);
   EnvRegs e;
-  float4 a_t, eps0 = make_float4(0.f, 0.f, 0.f, 0.f), eps1 = eps0;
+  float4 a_t, eps0 = make_float4(0.f, 0.f, 0.f, 0.f), lsum = eps0;
   if (!pdl) {
     load_env<kNoise>(e, tile);
     a_t = __ldcs(reinterpret_cast<const float4*>(io.action) + li);
-    if (kStats) { eps0 = ld_plane(tile, PL_EPSUM0); eps1 = ld_plane(tile, PL_EPSUM1); }
+    if (kStats) { eps0 = ld_plane(tile, PL_EPSUM0); if (kDiff) lsum = ld_plane(tile, PL_LOSSSUM); }
   }
   const RandSrc<kPhilox> rs(rng, li, st.env_id_offset + li);
   float4 n01, n23;                                     // obs normals (slots 0..5), thr_est_error normal (slot 6)
@@ -39,17 +39,27 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
   // fetched BEFORE the grid dependency and overlap the previous kernel's tail.  They are rewritten only by the reset /
   // gate-switch tail of a step kernel, which flags it in the hot planes (fresh bit, ANGACC.w): a flagged env re-reads
   // them through L2 after the wait.  (Host-side edits of those planes must clear GR_LAUNCH_PREFETCH for the next step.)
-  const bool prefetch = pdl && (st.launch_flags & GR_LAUNCH_PREFETCH) != 0;
+  // GR_LAUNCH_PREFETCH_L2 instead: the same planes are only pulled into L2 here (no registers, nothing to go stale) and loaded
+  // with everything else after the wait, as L2 hits -- no second, data-dependent round trip for the envs that reset.
+  const bool prefetch_l2 = pdl && (st.launch_flags & GR_LAUNCH_PREFETCH_L2) != 0;
+  const bool prefetch = pdl && !prefetch_l2 && (st.launch_flags & GR_LAUNCH_PREFETCH) != 0;
   if (prefetch) { load_cold<false>(e, tile); load_noise<kNoise, false>(e, tile); }
+  if (prefetch_l2) {
+#pragma unroll
+    for (int p = PL_DRAG2; p <= (kNoise ? PL_NOISE1 : PL_ETAU); ++p) prefetch_l2_line(tile + p * kTile);
+  }
   const TrackSmem tr = stage_track(track, reinterpret_cast<const int2*>(st.chunk_types), st.num_envs, smem_rows);
   if (pdl) {
     pdl_wait();
     GR_STAMP(1);
     load_hot(e, tile);
     a_t = __ldcs(reinterpret_cast<const float4*>(io.action) + li);
-    if (kStats) { eps0 = ld_plane(tile, PL_EPSUM0); eps1 = ld_plane(tile, PL_EPSUM1); }
+    if (kStats) { eps0 = ld_plane(tile, PL_EPSUM0); if (kDiff) lsum = ld_plane(tile, PL_LOSSSUM); }
     if (!kPhilox) rs.normals8(n01, n23);
-    if (prefetch) {
+    if (prefetch_l2) {
+      load_cold<true>(e, tile);
+      load_noise<kNoise, true>(e, tile);
+    } else if (prefetch) {
       const bool stale = pk_fresh(e.pk) != 0u;
       if (stale) load_cold<true>(e, tile);
       if (kNoise && (stale || e.noise_dirty_prev)) load_noise<kNoise, true>(e, tile);
@@ -69,19 +79,16 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
   __shared__ float4 obs_stage[8 * 128];                 // 2 KB per warp, up to 8 warps per block (GlobalObsSink)
 
   StepOut so;
-  if (!racing_step_body<kNoise, kDiff, kPhilox, kStats>(cfg, tr, e, a_t, n01, n23, draws, eps0, eps1, io, i, active,
+  if (!racing_step_body<kNoise, kDiff, kPhilox, kStats>(cfg, tr, e, a_t, n01, n23, draws, eps0, lsum, io, i, active,
                                                         GlobalObsSink{io, live, obs_stage + (threadIdx.x >> 5) * 128}, so)) return;
 
   GR_STAMP(3);
   // ---- 12. outputs + state write-back ----
+  if (kStats && !so.reset) add_episode_sums(eps0, e, so.terms, cfg.dt);        // deferred to here: the episode-sum plane is the last load to arrive
   store_env<kNoise>(e, tile, so.reset, so.noise_dirty);
   if (kStats) {
-    if (!so.reset) {        // deferred to here: the episode-sum planes are the last loads to arrive
-#pragma unroll
-      for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k) { if (k < 4) (&eps0.x)[k] += so.terms[k] * cfg.dt; else (&eps1.x)[k - 4] += so.terms[k] * cfg.dt; }
-    }
     st_plane(tile, PL_EPSUM0, eps0);
-    st_plane(tile, PL_EPSUM1, eps1);
+    if (kDiff) st_plane(tile, PL_LOSSSUM, lsum);
   }
   io.reward[i] = so.reward;
   io.terminated[i] = so.terminated ? 1 : 0;
@@ -125,8 +132,8 @@ __global__ void __launch_bounds__(256) racing_rollout_fwd_kernel(const GrConfig 
   float4* __restrict__ tile = tile_ptr(reinterpret_cast<float4*>(st.planes), li);
   EnvRegs e;
   load_env<kNoise>(e, tile);
-  float4 eps0 = make_float4(0.f, 0.f, 0.f, 0.f), eps1 = eps0;
-  if (kStats) { eps0 = ld_plane(tile, PL_EPSUM0); eps1 = ld_plane(tile, PL_EPSUM1); }
+  float4 eps0 = make_float4(0.f, 0.f, 0.f, 0.f), lsum = eps0;
+  if (kStats) { eps0 = ld_plane(tile, PL_EPSUM0); if (kDiff) lsum = ld_plane(tile, PL_LOSSSUM); }
   const TrackSmem tr = stage_track(track, reinterpret_cast<const int2*>(st.chunk_types), N, smem_rows);
   const unsigned live = __ballot_sync(0xffffffffu, active);
   if (live == 0u) return;
@@ -166,12 +173,9 @@ __global__ void __launch_bounds__(256) racing_rollout_fwd_kernel(const GrConfig 
       sink.aux_ptr = rio.aux_out;
     }
     StepOut so;
-    const bool alive = racing_step_body<kNoise, kDiff, kPhilox, kStats>(cfg, tr, e, a_t, n01, n23, draws, eps0, eps1, io, i, active, sink, so);
+    const bool alive = racing_step_body<kNoise, kDiff, kPhilox, kStats>(cfg, tr, e, a_t, n01, n23, draws, eps0, lsum, io, i, active, sink, so);
     if (alive) {
-      if (kStats && !so.reset) {
-#pragma unroll
-        for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k) { if (k < 4) (&eps0.x)[k] += so.terms[k] * cfg.dt; else (&eps1.x)[k - 4] += so.terms[k] * cfg.dt; }
-      }
+      if (kStats && !so.reset) add_episode_sums(eps0, e, so.terms, cfg.dt);
       any_reset |= so.reset;
       any_noise_dirty |= so.noise_dirty;
       last_noise_dirty = so.noise_dirty;
@@ -181,10 +185,11 @@ __global__ void __launch_bounds__(256) racing_rollout_fwd_kernel(const GrConfig 
       if (rio.time_out) rio.time_out[tn] = so.time_out ? 1 : 0;
     }
   }
-  if (active) {      // what T single steps leave behind: cold planes rewritten if any step reset, ANGACC.w = the LAST step's flag
+  if (active) {      // what T single steps leave behind: cold planes rewritten if any step reset, the noise-dirty flag = the LAST step's
     store_env<kNoise>(e, tile, any_reset, any_noise_dirty);
-    if (kNoise && any_noise_dirty && !last_noise_dirty) st_plane(tile, PL_ANGACC, pack(e.aacc, 0.0f));
-    if (kStats) { st_plane(tile, PL_EPSUM0, eps0); st_plane(tile, PL_EPSUM1, eps1); }
+    if (kNoise && any_noise_dirty && !last_noise_dirty)
+      st_plane(tile, PL_LINVEL, pack(e.v, __uint_as_float(eplen_word(e.eplen, e.aux != 0.0f, false, e.arate, e.metrics_zero))));
+    if (kStats) { st_plane(tile, PL_EPSUM0, eps0); if (kDiff) st_plane(tile, PL_LOSSSUM, lsum); }
   }
 }
 
@@ -214,8 +219,9 @@ __global__ void __launch_bounds__(256) racing_reset_kernel(const GrConfig cfg, c
   V3 origin;
   if (do_reset) {
     origin = reset_env<kNoise, kPhilox>(cfg, tr, e, Draws<kPhilox>{rs, nullptr}, n23.z);
+    e.arate = 0.f; e.metrics_zero = true;                 // CommandTerm.reset: metrics logged and zeroed, no command update follows
     store_env<kNoise>(e, tile, true, true);
-    if (kStats) { st_plane(tile, PL_EPSUM0, make_float4(0.f, 0.f, 0.f, 0.f)); st_plane(tile, PL_EPSUM1, make_float4(0.f, 0.f, 0.f, 0.f)); }
+    if (kStats) { st_plane(tile, PL_EPSUM0, make_float4(0.f, 0.f, 0.f, 0.f)); st_plane(tile, PL_LOSSSUM, make_float4(0.f, 0.f, 0.f, 0.f)); }
   } else {
     origin = xyz(tr.origin_row(type, (int)pk_level(e.pk)));
   }
@@ -272,7 +278,7 @@ __global__ void racing_startup_kernel(const GrConfig cfg, const GrTrack track, c
   const float zero = 0.0f;
   P[pidx(PL_QUAT, i)] = make_float4(1.f, 0.f, 0.f, 0.f);
   P[pidx(PL_POS, i)] = make_float4(zero, zero, zero, zero);
-  P[pidx(PL_LINVEL, i)] = make_float4(zero, zero, zero, __int_as_float(0));
+  P[pidx(PL_LINVEL, i)] = make_float4(zero, zero, zero, __uint_as_float(eplen_word(0, false, false, 0.f, true)));
   P[pidx(PL_ANGVEL, i)] = make_float4(zero, zero, zero, __uint_as_float(pk_make(0u, 0u, (uint32_t)level, (uint32_t)type, 1u)));
   P[pidx(PL_TORQUE, i)] = make_float4(zero, zero, zero, zero);
   P[pidx(PL_ANGACC, i)] = make_float4(zero, zero, zero, zero);
@@ -286,7 +292,7 @@ __global__ void racing_startup_kernel(const GrConfig cfg, const GrTrack track, c
   P[pidx(PL_NOISE1, i)] = make_float4(zero, zero, cfg.cmd_noise_pos, 1.0f);
   if (st.num_planes >= GR_NUM_PLANES_WITH_STATS) {
     P[pidx(PL_EPSUM0, i)] = make_float4(zero, zero, zero, zero);
-    P[pidx(PL_EPSUM1, i)] = make_float4(zero, zero, zero, zero);
+    P[pidx(PL_LOSSSUM, i)] = make_float4(zero, zero, zero, zero);
   }
 }
 

@@ -13,8 +13,29 @@ struct EnvRegs {
   V3 k2; float m; V3 k1; float ef; V3 kp; float thr; V3 kd; V3 etau;
   V3 dcur, dnext; float noise_hi, noise_level;
   float aux;      // last cross_obs value (RewardManager._step_reward survives resets)
-  bool noise_dirty_prev;   // PL_ANGACC.w: the noise planes were rewritten by the previous step (gate switch / reset)
+  bool noise_dirty_prev;   // the noise planes were rewritten by the previous step (gate switch / reset)
+  float es4, es5; // episode sums of reward terms 4, 5 (ride in the spare words of PL_TORQUE / PL_ANGACC; terms 0..3: PL_EPSUM0)
+  float arate;    // command metric "action_rate" assigned by the previous step's command update (commands.py:258), a 16-bit float in HBM
+  bool metrics_zero;   // the last command update of this env was a full reset(): CommandTerm.reset zeroed its metrics
 };
+
+// PL_LINVEL.w, as bits: episode_length [0:12) | cross flag [12] | noise-planes-rewritten flag [13] | "action_rate" command metric
+// [14:30) as a 16-bit float (5-bit exponent biased at 2^-21, 11-bit mantissa, round to nearest: rel. error <= 2^-12 on [2^-21, 2^11)) |
+// [30] always 0, so the word never looks like a NaN / Inf to host-side float comparisons of the planes | [31] "metrics are zero" (the
+// env's last command update was a full reset(): CommandTerm.reset zeroed them)
+constexpr uint32_t kEplenMask = 0xFFFu, kAuxBit = 1u << 12, kNoiseDirtyBit = 1u << 13, kMetricsZeroBit = 1u << 31;
+constexpr uint32_t kArateBias = 106u << 11;
+__device__ __forceinline__ uint32_t arate_field(float arate) {
+  const uint32_t r = (__float_as_uint(arate) + 0x800u) >> 12;               // exponent | 11 mantissa bits, rounded
+  return r <= kArateBias ? 0u : (r - kArateBias > 0xFFFFu ? 0xFFFFu : r - kArateBias);
+}
+__device__ __forceinline__ float arate_value(uint32_t field) { return field ? __uint_as_float((field + kArateBias) << 12) : 0.0f; }
+// the value a later load gives back (kernels that keep an env in registers over several steps carry this, like the single steps)
+__device__ __forceinline__ float arate_rounded(float arate) { return arate_value(arate_field(arate)); }
+__device__ __forceinline__ uint32_t eplen_word(int eplen, bool aux, bool noise_dirty, float arate, bool metrics_zero) {
+  return ((uint32_t)eplen & kEplenMask) | (aux ? kAuxBit : 0u) | (noise_dirty ? kNoiseDirtyBit : 0u) | (arate_field(arate) << 14) |
+         (metrics_zero ? kMetricsZeroBit : 0u);
+}
 
 // EnvRegs.om / .aacc hold the BODY-frame angular velocity / acceleration (PL_ANGVEL / PL_ANGACC): the reference
 // round-trips them through the world frame every step (rot(q', w_b') stored, rotinv(q', .) read back: identity up to
@@ -22,8 +43,11 @@ struct EnvRegs {
 __device__ __forceinline__ void load_hot(EnvRegs& e, const float4* __restrict__ tile) {
   const float4 a0 = ld_plane(tile, PL_QUAT), a1 = ld_plane(tile, PL_POS), a2 = ld_plane(tile, PL_LINVEL), a3 = ld_plane(tile, PL_ANGVEL),
                a4 = ld_plane(tile, PL_TORQUE), a5 = ld_plane(tile, PL_ANGACC), a6 = ld_plane(tile, PL_FIFO);
-  e.q = quat(a0); e.w = xyz(a1); e.f = a1.w; e.v = xyz(a2); e.eplen = __float_as_int(a2.w);
-  e.om = xyz(a3); e.pk = __float_as_uint(a3.w); e.tau = xyz(a4); e.aux = a4.w; e.aacc = xyz(a5); e.noise_dirty_prev = a5.w != 0.0f; e.fifo = a6;
+  const uint32_t ew = __float_as_uint(a2.w);
+  e.q = quat(a0); e.w = xyz(a1); e.f = a1.w; e.v = xyz(a2); e.eplen = (int)(ew & kEplenMask);
+  e.aux = (ew & kAuxBit) ? 1.0f : 0.0f; e.noise_dirty_prev = (ew & kNoiseDirtyBit) != 0u;
+  e.metrics_zero = (ew & kMetricsZeroBit) != 0u; e.arate = arate_value((ew >> 14) & 0xFFFFu);
+  e.om = xyz(a3); e.pk = __float_as_uint(a3.w); e.tau = xyz(a4); e.es4 = a4.w; e.aacc = xyz(a5); e.es5 = a5.w; e.fifo = a6;
 }
 // kVolatile: re-read through L2 (ld.global.cv) after the grid dependency when the prefetched copy may be stale
 template <bool kVolatile>
@@ -162,18 +186,19 @@ __device__ __forceinline__ V3 reset_env(const GrConfig& cfg, const TrackSmem& tr
   }
   e.pk = pk_make((uint32_t)start_gate, 0u, (uint32_t)level, (uint32_t)type, 1u);
   e.eplen = 0;
+  e.es4 = 0.f; e.es5 = 0.f;
   return origin;
 }
 
 template <bool kNoise>
 __device__ __forceinline__ void store_env(const EnvRegs& e, float4* __restrict__ tile, bool cold_dirty, bool noise_dirty) {
-  // ANGACC.w = "noise planes rewritten in this step": lets the next step trust its pre-dependency prefetch of them
+  // the noise-dirty flag = "noise planes rewritten in this step": lets the next step trust its pre-dependency prefetch of them
   st_plane(tile, PL_QUAT, pack(e.q));
   st_plane(tile, PL_POS, pack(e.w, e.f));
-  st_plane(tile, PL_LINVEL, pack(e.v, __int_as_float(e.eplen)));
+  st_plane(tile, PL_LINVEL, pack(e.v, __uint_as_float(eplen_word(e.eplen, e.aux != 0.0f, kNoise && noise_dirty, e.arate, e.metrics_zero))));
   st_plane(tile, PL_ANGVEL, pack(e.om, __uint_as_float(e.pk)));
-  st_plane(tile, PL_TORQUE, pack(e.tau, e.aux));
-  st_plane(tile, PL_ANGACC, pack(e.aacc, (kNoise && noise_dirty) ? 1.0f : 0.0f));
+  st_plane(tile, PL_TORQUE, pack(e.tau, e.es4));
+  st_plane(tile, PL_ANGACC, pack(e.aacc, e.es5));
   st_plane(tile, PL_FIFO, e.fifo);
   if (cold_dirty) {
     tile[PL_DRAG2 * kTile] = pack(e.k2, e.m);
@@ -250,23 +275,33 @@ struct GlobalObsSink {
   __device__ __forceinline__ void aux(int i, float v) const { if (io.aux_obs) io.aux_obs[i] = v; }
 };
 
+// episode sums of the reward terms: 0..3 in `eps0` (PL_EPSUM0), 4..5 in the env's hot planes (e.es4 / e.es5)
+__device__ __forceinline__ void add_episode_sums(float4& eps0, EnvRegs& e, const float (&terms)[GR_NUM_REWARD_TERMS], float dt) {
+  eps0.x += terms[0] * dt; eps0.y += terms[1] * dt; eps0.z += terms[2] * dt; eps0.w += terms[3] * dt;
+  e.es4 += terms[4] * dt; e.es5 += terms[5] * dt;
+}
+
 // Sections 1-11.  `e` = state before the step in, state after the step (and after a reset) out, e.fifo included;
-// eps0/eps1 = episode sums (kStats): logged + zeroed here on reset, the non-reset accumulation is left to the caller
-// (out.terms), who knows when its copy of the sums has arrived.  Returns false for a lane past the last env.
+// eps0 / e.es4 / e.es5 = episode sums of the reward terms (kStats): logged + zeroed here on reset, the non-reset accumulation
+// is left to the caller (add_episode_sums with out.terms), who knows when its copy of the sums has arrived; lsum = LossManager
+// episode sums (kDiff && kStats, PL_LOSSSUM).  Returns false for a lane past the last env.
 template <bool kNoise, bool kDiff, bool kPhilox, bool kStats, class ObsSink>
 __device__ __forceinline__ bool racing_step_body(const GrConfig& cfg, const TrackSmem& tr, EnvRegs& e, const float4 a_t, const float4 n01,
-                                                 const float4 n23, const Draws<kPhilox>& draws, float4& eps0, float4& eps1, const GrStepIO& io,
+                                                 const float4 n23, const Draws<kPhilox>& draws, float4& eps0, float4& lsum, const GrStepIO& io,
                                                  const int i, const bool active, const ObsSink& sink, StepOut& out) {
   const int type = (int)pk_type(e.pk);
   int level = (int)pk_level(e.pk);
   int gate_id = (int)pk_gate(e.pk);
   const uint32_t fresh = pk_fresh(e.pk);
 #ifdef GR_PHASE_TIMING
-  if (__float_as_uint(e.q.w + e.w.x + e.v.x + e.om.x + e.tau.x + e.aacc.x + e.fifo.x + e.k2.x + e.k1.x + e.kp.x + e.kd.x + e.etau.x + a_t.x + eps0.x + eps1.x + e.dcur.x + e.noise_hi) != 0x7fc12345u) GR_STAMP(2);
+  if (__float_as_uint(e.q.w + e.w.x + e.v.x + e.om.x + e.tau.x + e.aacc.x + e.fifo.x + e.k2.x + e.k1.x + e.kp.x + e.kd.x + e.etau.x + a_t.x + eps0.x + lsum.x + e.dcur.x + e.noise_hi) != 0x7fc12345u) GR_STAMP(2);
 #endif
   V3 origin = xyz(tr.origin_row(type, level));
   V3 gate_rel = tr.gate(type, level, gate_id);
   const float dt = cfg.dt;
+  // RacingCommand metrics of the previous command update (commands.py:258-260), logged if this step resets the env: functions of
+  // the state entering the step
+  const float lin_spd_in = dot(e.v, e.v), ang_spd_in = dot(e.om, e.om);
   const V3 J = v3(cfg.inertia[0], cfg.inertia[1], cfg.inertia[2]);
   const V3 Jinv = v3(fm_rcp(J.x), fm_rcp(J.y), fm_rcp(J.z));
   const float inv_m = fm_rcp(e.m);
@@ -335,6 +370,13 @@ __device__ __forceinline__ bool racing_step_body(const GrConfig& cfg, const Trac
   // ---- 3. align (droneDynamics.py:156-181): value = sim-derived state; aligned local position for the loss ----
   const V3 p_al = e.w - origin;
   const V3 v_al = v1;
+  if (kDiff && active && io.aligned_states) {       // extras["aligned_states"] / ["nominal_states"] (:205-212), before any reset
+    float* __restrict__ al = io.aligned_states + (int64_t)i * 13;
+    const V3 om_w = R1.rot(omb1);
+    al[0] = p1.x; al[1] = p1.y; al[2] = p1.z; al[3] = q1.w; al[4] = q1.x; al[5] = q1.y; al[6] = q1.z;
+    al[7] = v1.x; al[8] = v1.y; al[9] = v1.z; al[10] = om_w.x; al[11] = om_w.y; al[12] = om_w.z;
+    if (io.acc) { io.acc[(int64_t)i * 3] = acc.x; io.acc[(int64_t)i * 3 + 1] = acc.y; io.acc[(int64_t)i * 3 + 2] = acc.z; }
+  }
 
   // ---- 4./5. counters + terminations (QD/mdp/termination.py:15-33; Isaac Lab mdp.time_out) ----
   e.eplen += 1;
@@ -355,7 +397,7 @@ __device__ __forceinline__ bool racing_step_body(const GrConfig& cfg, const Trac
   const V3 vb1 = R1.rotinv(v1);
   const V3 cg0 = R1.rotinv(vec);                                  // command_gt[:, :3]
   float (&terms)[GR_NUM_REWARD_TERMS] = out.terms;
-  float reward = 0.0f;
+  float reward = 0.0f, arate_now;
   {
     const float inv_nc = fm_rsqrt(fmaxf(dot(cg0, cg0), 1e-16f));
     const float inv_nv = fm_rsqrt(fmaxf(dot(vb1, vb1), 1e-16f));
@@ -366,6 +408,7 @@ __device__ __forceinline__ bool racing_step_body(const GrConfig& cfg, const Trac
                   d3 = (th_a.w - th_prev.w) * sb;                                                  // :196-206
       terms[2] = d0 * d0 + d1 * d1 + d2r * d2r + d3 * d3;
     }
+    arate_now = terms[2];                                                                         // commands.py:258 (same function, step 8)
     terms[3] = cg0.x * inv_nc;                                                                    // :171-179
     terms[4] = pass_pre ? fm_rcp(d2 + 1.0f) : 0.0f;                                               // :215-224
     terms[5] = bad ? 1.0f : 0.0f;                                                                  // :244-253
@@ -384,10 +427,7 @@ __device__ __forceinline__ bool racing_step_body(const GrConfig& cfg, const Trac
   bool noise_dirty = false;
   bool passed = pass_pre;                                 // 8. on an env that did not reset this is the same test
   if (reset) {
-    if (kStats) {          // RewardManager.compute adds this step's values to the episode sums before the reset logs them
-#pragma unroll
-      for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k) { if (k < 4) (&eps0.x)[k] += terms[k] * dt; else (&eps1.x)[k - 4] += terms[k] * dt; }
-    }
+    if (kStats) add_episode_sums(eps0, e, terms, dt);          // RewardManager.compute adds this step's values before the reset logs them
     // episode log (extras["log"], manager_based_diff_rl_env.py:380-407): fire-and-forget RED ops on one of GR_LOG_SHARDS
     // accumulator rows picked by warp id (a single row serialises on one L2 line: 3x the kernel time at a 5 % reset rate)
     if (io.log_accum && active) {
@@ -398,10 +438,18 @@ __device__ __forceinline__ bool racing_step_body(const GrConfig& cfg, const Trac
       if (terminated) atomicAdd(acc_row + GR_LOG_NUM_TERMINATED, 1.0f);
       if (kStats) {
 #pragma unroll
-        for (int k = 0; k < GR_NUM_REWARD_TERMS; ++k) atomicAdd(acc_row + GR_LOG_SUM_EPSUM + k, k < 4 ? (&eps0.x)[k] : (&eps1.x)[k - 4]);
+        for (int k = 0; k < 4; ++k) atomicAdd(acc_row + GR_LOG_SUM_EPSUM + k, (&eps0.x)[k]);
+        atomicAdd(acc_row + GR_LOG_SUM_EPSUM + 4, e.es4);
+        atomicAdd(acc_row + GR_LOG_SUM_EPSUM + 5, e.es5);
+        if (!e.metrics_zero) {
+          atomicAdd(acc_row + GR_LOG_SUM_ACTION_RATE, e.arate);
+          atomicAdd(acc_row + GR_LOG_SUM_LIN_SPD, sqrtf(lin_spd_in));
+          atomicAdd(acc_row + GR_LOG_SUM_ANG_SPD, sqrtf(ang_spd_in));
+        }
+        if (kDiff) { atomicAdd(acc_row + GR_LOG_SUM_LOSS, lsum.x); atomicAdd(acc_row + GR_LOG_SUM_LOSS + 1, lsum.y); atomicAdd(acc_row + GR_LOG_SUM_LOSS + 2, lsum.z); }
       }
     }
-    if (kStats) { eps0 = make_float4(0.f, 0.f, 0.f, 0.f); eps1 = eps0; }
+    if (kStats) { eps0 = make_float4(0.f, 0.f, 0.f, 0.f); lsum = eps0; }       // (e.es4 / e.es5: reset_env)
     origin = reset_env<kNoise, kPhilox>(cfg, tr, e, draws, n23.z);
     level = (int)pk_level(e.pk);
     gate_id = (int)pk_gate(e.pk);
@@ -413,6 +461,9 @@ __device__ __forceinline__ bool racing_step_body(const GrConfig& cfg, const Trac
   } else {
     e.pk &= 0x7FFFFFFFu;      // latches hold a_t again
   }
+  // _update_metrics of this step's command update (step 8): ActionManager.reset zeroed the latches of an env reset in this step
+  e.arate = reset ? 0.0f : arate_rounded(arate_now);
+  e.metrics_zero = false;
 
   // ---- 8. command update (QD/mdp/commands.py:247-260 then :308-350) ----
   if (passed) {
@@ -440,6 +491,7 @@ __device__ __forceinline__ bool racing_step_body(const GrConfig& cfg, const Trac
     const float z = p_al.z;
     const float den = 1.0f + 1.0f * z + 10.0f * (z * z);
     const float l_fall = (1.0f / den) * cfg.w_loss[2];
+    if (kStats) { lsum.x += l_target * dt; lsum.y += l_vel * dt; lsum.z += l_fall * dt; }      // LossManager.compute (:103), after the reset
     if (io.loss) io.loss[i] = ((0.0f + l_target) + l_vel) + l_fall;
     if (io.loss_terms) { io.loss_terms[i * 3 + 0] = l_target; io.loss_terms[i * 3 + 1] = l_vel; io.loss_terms[i * 3 + 2] = l_fall; }
     if (io.tape) {

@@ -90,18 +90,26 @@ def default_terrain_types(num_envs: int, num_types: int, env_id_offset: int = 0,
 
 class _Extras(dict):
     """extras dict whose "log" entry is built on demand from the device-side accumulators (no host sync on the
-    hot loop: the reference builds it eagerly inside _reset_idx, manager_based_diff_rl_env.py:380-407)."""
+    hot loop: the reference builds it eagerly inside _reset_idx, manager_based_diff_rl_env.py:380-407).  With differentiable
+    physics "log_losses" (:257, ``LossManager.log_all_active_terms``: [(term name, mean over envs)]) is built on demand as well,
+    its values 0-dim DEVICE tensors: ``sum(v) / len(v)`` and loggers work on them, nothing waits for the GPU inside the loop."""
 
     def __init__(self, env):
         super().__init__()
         self._env = env
 
+    def _lazy(self, k):
+        return k == "log" or (k == "log_losses" and super().__contains__("loss_terms"))
+
     def __contains__(self, k):
-        return k == "log" or super().__contains__(k)
+        return self._lazy(k) or super().__contains__(k)
 
     def __getitem__(self, k):
         if k == "log" and not super().__contains__("log"):
             return self._env._build_log()
+        if k == "log_losses" and super().__contains__("loss_terms"):
+            m = super().__getitem__("loss_terms").detach().mean(dim=0)
+            return [(name, m[i]) for i, name in enumerate(self._env._loss_term_names)]
         return super().__getitem__(k)
 
     def get(self, k, default=None):
@@ -155,7 +163,9 @@ class RacingVecEnv:
         self._chunk_types = torch.zeros(((N + 63) // 64) * 2, dtype=torch.int32, device=dev)
         if pdl is None:
             pdl = os.environ.get("GRACING_PDL", "1") != "0"
-        flags = (B.GR_LAUNCH_PDL | (B.GR_LAUNCH_PREFETCH if os.environ.get("GRACING_PREFETCH", "1") != "0" else 0)) if (pdl and self.device.type == "cuda") else 0
+        # read-mostly planes before the grid dependency: "1" = into registers with the stale-flag protocol, "l2" = into L2 only, "0" = off
+        pf = {"0": 0, "1": B.GR_LAUNCH_PREFETCH, "l2": B.GR_LAUNCH_PREFETCH_L2}[os.environ.get("GRACING_PREFETCH", "1").lower()]
+        flags = (B.GR_LAUNCH_PDL | pf) if (pdl and self.device.type == "cuda") else 0
         self._launch_flags = flags
         self._state = B.GrState(self.planes.data_ptr(), self._stride, N, self.num_planes, int(env_id_offset), max(spans),
                                 int(block_threads), flags, self._chunk_types.data_ptr())
@@ -177,6 +187,10 @@ class RacingVecEnv:
         self.extras = _Extras(self)
         self.export_reward_terms = False
         self.export_gate_passed = False
+        # opt-in (differentiable physics): extras["aligned_states"] / ["nominal_states"] [N,13] and ["acc"] [N,3] of every step
+        # (manager_based_diff_rl_env.py:205-212; detached values -- nothing outside the reference's own LossManager consumes them)
+        self.export_aligned_states = False
+        self._loss_term_names = L.LOSS_TERM_NAMES
         # ---- BPTT window (cfg.is_differentiable_physics)
         self._bptt = None
         if cfg.is_differentiable_physics:
@@ -256,11 +270,16 @@ class RacingVecEnv:
     @property
     def episode_length_buf(self) -> torch.Tensor:
         """int32 [N] copy of the per-env episode step counters; assign to write them (on_policy_runner.py:118-121)."""
-        return self.planes[:, L.PL_LINVEL, :, 3].reshape(-1)[: self.num_envs].view(torch.int32)
+        return self.planes[:, L.PL_LINVEL, :, 3].reshape(-1)[: self.num_envs].view(torch.int32) & L.EPLEN_MASK
 
     @episode_length_buf.setter
     def episode_length_buf(self, value: torch.Tensor):
-        self.write_plane(L.PL_LINVEL, slice(3, 4), value.to(self.device, torch.int32).reshape(-1, 1))
+        word = self.planes[:, L.PL_LINVEL, :, 3].view(torch.int32)                # the counter shares its word with flags (layout.py)
+        v = torch.zeros(self._stride, dtype=torch.int32, device=self.device)
+        v[: self.num_envs] = value.to(self.device, torch.int32).reshape(-1)
+        if int(self.max_episode_length) > L.EPLEN_MASK:
+            raise ValueError(f"max_episode_length must be <= {L.EPLEN_MASK}")
+        word.copy_((word & ~L.EPLEN_MASK) | (v.view(self.num_tiles, L.TILE) & L.EPLEN_MASK))
 
     def state_dict_view(self) -> dict:
         """Named [N, ...] copies of the env state (diagnostics / tests); world-frame root state like robot.data."""
@@ -268,9 +287,13 @@ class RacingVecEnv:
         q, pos, lin, ang, tq, aa, ff = R(L.PL_QUAT), R(L.PL_POS), R(L.PL_LINVEL), R(L.PL_ANGVEL), R(L.PL_TORQUE), R(L.PL_ANGACC), R(L.PL_FIFO)
         d2, d1, kp, kd, et, n0, n1 = R(L.PL_DRAG2), R(L.PL_DRAG1), R(L.PL_KP), R(L.PL_KD), R(L.PL_ETAU), R(L.PL_NOISE0), R(L.PL_NOISE1)
         pk = ang[:, 3].contiguous().view(torch.int32)
+        ew = lin[:, 3].contiguous().view(torch.int32)
+        field = (ew >> L.EPLEN_METRIC_SHIFT) & L.EPLEN_METRIC_MASK
         return {
             "root_quat_w": q, "root_pos_w": pos[:, :3], "gross_thrust": pos[:, 3],
-            "root_lin_vel_w": lin[:, :3], "episode_length": lin[:, 3].contiguous().view(torch.int32),
+            "root_lin_vel_w": lin[:, :3], "episode_length": ew & L.EPLEN_MASK,
+            "cross_obs": (ew & L.EPLEN_AUX_BIT) != 0,
+            "metric_action_rate": torch.where(field == 0, torch.zeros_like(field), (field + L.EPLEN_METRIC_BIAS) << 12).view(torch.float32),
             "root_ang_vel_b": ang[:, :3], "torque": tq[:, :3], "ang_acc_b": aa[:, :3],
             "action_fifo_tanh": ff, "drag_coeffs": d2[:, :3], "mass": d2[:, 3],
             "h_force_drag_coeffs": d1[:, :3], "exp_thrust_delay": d1[:, 3],
@@ -278,7 +301,8 @@ class RacingVecEnv:
             "exp_torque_delay": et[:, :3],
             "gate_noise": torch.cat([n0[:, :3], n0[:, 3:], n1[:, :2]], dim=-1),
             "noise_pos_hi": n1[:, 2], "noise_level": n1[:, 3],
-            "episode_sums": torch.cat([R(L.PL_EPSUM0), R(L.PL_EPSUM1)[:, :2]], dim=-1),
+            "episode_sums": torch.cat([R(L.PL_EPSUM0), tq[:, 3:], aa[:, 3:]], dim=-1),
+            "loss_episode_sums": R(L.PL_LOSSSUM)[:, :3],
             "gate_id": (pk >> L.PK_GATE_SHIFT) & 0xFF, "accumulate_gates": (pk >> L.PK_ACC_SHIFT) & 0xFFF,
             "terrain_levels": (pk >> L.PK_LEVEL_SHIFT) & 0x3F, "terrain_types": (pk >> L.PK_TYPE_SHIFT) & 0x1F,
             "fresh": (pk >> L.PK_FRESH_SHIFT) & 0x1,
@@ -298,6 +322,13 @@ class RacingVecEnv:
             for k, name in enumerate(L.REWARD_TERM_NAMES):
                 if w[k] != 0.0:
                     log["Episode_Reward/" + name] = acc[B_LOG_SUM_EPSUM + k] / n / self.cfg.episode_length_s
+            # LossManager.reset (L/managers/loss_manager.py:71-78): logged in every mode; the sums only move with differentiable physics
+            for k, name in enumerate(L.LOSS_TERM_NAMES):
+                log["Episode_Loss/" + name] = acc[B.GR_LOG_SUM_LOSS + k] / n / self.cfg.episode_length_s
+            # CommandTerm.reset: every metric of RacingCommand (QD/mdp/commands.py:257-260) as the mean over the reset envs
+            log["Metrics/next_gate_pose/action_rate"] = acc[B.GR_LOG_SUM_ACTION_RATE] / n
+            log["Metrics/next_gate_pose/avg_lin_spd"] = acc[B.GR_LOG_SUM_LIN_SPD] / n
+            log["Metrics/next_gate_pose/avg_ang_spd"] = acc[B.GR_LOG_SUM_ANG_SPD] / n
         log["Metrics/next_gate_pose/accumulate_gates"] = acc[B_LOG_SUM_GATES] / n
         log["Episode_Termination/time_out"] = acc[B_LOG_NUM_TIMEOUT].clone()
         log["Episode_Termination/terminated"] = acc[B_LOG_NUM_TERMINATED].clone()
@@ -330,17 +361,50 @@ class RacingVecEnv:
         would be overwritten two steps later behind autograd's back."""
         return obs.clone() if (self._bptt is not None and needed) else obs
 
-    def get_observations(self):
-        """RslRlVecEnvWrapper.get_observations: (policy obs, {"observations": obs_dict}).  Returns the observation of
-        the last reset/step (same values the reference would recompute, minus a fresh noise draw -- DESIGN.md)."""
+    def get_observations(self, fresh_noise: bool = False, rnd: Optional[torch.Tensor] = None):
+        """RslRlVecEnvWrapper.get_observations: (policy obs, {"observations": obs_dict}).  By default the observation of the last
+        reset / step is handed out again.  ``fresh_noise=True`` is the reference's literal behaviour (``ObservationManager.compute()``,
+        manager_based_diff_rl_env.py:264 / QD/mdp/observation.py:22-63): the observations are recomputed from the current state with a
+        NEW observation-noise draw (a Philox stream no step uses -- counter word with the top bit set -- so the env's step stream
+        does not move; ``rnd`` [N,52] in dense mode), the last-action columns still showing the lagged action the last step applied."""
         if self._needs_reset:
             self.reset()
         o = self._last
+        if fresh_noise:
+            return self._observe_fresh(rnd)
         if self._ops is not None and o["obs"].is_inference() and not torch.is_inference_mode_enabled():
             # operator outputs allocated under the runner's torch.inference_mode() (on_policy_runner.py:141): hand normal tensors
             # to a caller outside it, as the reference's recomputed observations are
             o.update({k: o[k].clone() for k in ("obs", "critic", "aux")})
         return self._grad_safe_obs(o["obs"], self._ops is None), {"observations": self._obs_dict(o)}
+
+    def _observe_fresh(self, rnd):
+        last = self._last
+        k = self._flip
+        o = self._outs[k] if self._ops is None else dict(obs=torch.zeros_like(last["obs"]), critic=torch.zeros_like(last["critic"]), aux=torch.zeros_like(last["aux"]))
+        if self._ops is None:
+            self._flip = k ^ 1
+        self._observe_count = getattr(self, "_observe_count", 0) + 1
+        rng = B.GrRandom(None, self.seed, 0x80000000 | ((self._step_count * 977 + self._observe_count) & 0x7FFFFFFF))       # a stream no step uses
+        if rnd is not None:
+            rnd = rnd.to(self.device, torch.float32).contiguous()
+            if rnd.shape != (self.num_envs, L.RND_STRIDE):
+                raise ValueError(f"rnd must be [{self.num_envs}, {L.RND_STRIDE}]")
+            rng.rnd = rnd.data_ptr()
+        elif self.rng_mode == "dense":
+            raise ValueError("rng_mode='dense' needs an explicit rnd tensor for a fresh noise draw")
+        B.check(self._lib.gr_env_observe(C.byref(self._gcfg), C.byref(self._track), C.byref(self._state), C.byref(rng),
+                                         o["obs"].data_ptr(), o["critic"].data_ptr(), o["aux"].data_ptr(), self._stream()), "gr_env_observe")
+        # modified_last_action (QD/mdp/observation.py:55-63) shows raw_actions = the lagged action of the last process_actions call;
+        # the FIFO the kernel reads already holds a_t, so those four columns come from the last step's own observation
+        o["obs"][:, 12:].copy_(last["obs"][:, 12:])
+        o["critic"][:, 12:].copy_(last["critic"][:, 12:])
+        for name in ("reward", "terminated", "time_out", "dones"):
+            if name in last and o is not last and name in o:
+                o[name].copy_(last[name])
+        self._last = o
+        self.extras["observations"] = self._obs_dict(o)
+        return self._grad_safe_obs(o["obs"]), {"observations": self._obs_dict(o)}
 
     def detach(self):
         """env.unwrapped.detach() (manager_based_diff_rl_env.py:412-416): start a new BPTT window."""
@@ -382,6 +446,10 @@ class RacingVecEnv:
         io.log_accum = self._log_accum.data_ptr()
         if self._bptt is not None:
             self._bptt.bind_step(io)
+            if self.export_aligned_states:
+                if "aligned" not in o:
+                    o["aligned"], o["acc"] = torch.zeros(self.num_envs, 13, device=self.device), torch.zeros(self.num_envs, 3, device=self.device)
+                io.aligned_states, io.acc = o["aligned"].data_ptr(), o["acc"].data_ptr()
         rc = self._lib.gr_step_fwd(self._p_cfg, self._p_track, self._p_state, C.byref(self._rand(rnd)), C.byref(io), self._stream())
         if rc:
             B.check(rc, "gr_step_fwd")
@@ -397,7 +465,13 @@ class RacingVecEnv:
         ex["terminated"] = term
         if self._bptt is not None:
             self._bptt.after_step(actions, ex)
-        return self._grad_safe_obs(o["obs"], actions.requires_grad), o["reward"], o["dones"], ex
+            if self.export_aligned_states:
+                ex["aligned_states"] = ex["nominal_states"] = o["aligned"]
+                ex["acc"] = o["acc"]
+            # a differentiable-physics loop keeps what a step returns for the whole window (naive_train.py:170-172 appends dones and
+            # losses to lists): hand out tensors that the step after next does not overwrite
+            return self._grad_safe_obs(o["obs"], actions.requires_grad), o["reward"].clone(), o["dones"].clone(), ex
+        return o["obs"], o["reward"], o["dones"], ex
 
     def rollout(self, actions: torch.Tensor, rnd: Optional[torch.Tensor] = None, record_obs: bool = False) -> dict:
         """``for t in range(T): env.step(actions[t])`` in ONE launch (gr_rollout_fwd) for actions known in advance

@@ -59,14 +59,19 @@ TILE_PLANES = 16
 # planes written every step first (one contiguous write-back per tile) ...
 PL_QUAT = 0      # q.w q.x q.y q.z
 PL_POS = 1       # world pos x y z | thrust filter state f
-PL_LINVEL = 2    # v_w x y z       | episode_length (int32 bits)
-PL_ANGVEL = 3    # omega_w x y z   | packed ints: gate_id | acc_gates<<8 | level<<20 | type<<26 | fresh<<31
-PL_TORQUE = 4    # torque filter state x y z | last cross_obs value
-PL_ANGACC = 5    # alpha_w x y z   | spare
-PL_FIFO = 6      # action-lag FIFO (a_{t-1})
+PL_LINVEL = 2    # v_w x y z       | bits: episode_length [0:12) | cross_obs flag [12] | noise-planes-rewritten flag [13] |
+                 #                   "action_rate" command metric as a 16-bit float [14:30) (5-bit exponent biased at 2^-21, 11-bit
+                 #                   mantissa) | 0 [30] | metrics-are-zero flag [31]
+PL_ANGVEL = 3    # omega_b x y z   | packed ints: gate_id | acc_gates<<8 | level<<20 | type<<26 | fresh<<31
+PL_TORQUE = 4    # torque filter state x y z | episode sum of reward term 4 (success_cross)
+PL_ANGACC = 5    # alpha_b x y z   | episode sum of reward term 5 (bad_pose)
+PL_FIFO = 6      # action-lag FIFO (tanh(a_{t-1}))
 NUM_HOT_PLANES = 7
 PL_EPSUM0 = 7    # episode sums of reward terms 0..3          (touched only with episode_stats)
-PL_EPSUM1 = 8    # episode sums of reward terms 4..5 | spare | spare
+PL_LOSSSUM = 8   # LossManager episode sums of the 3 loss terms | spare   (episode_stats + differentiable physics)
+EPLEN_MASK = 0xFFF          # PL_LINVEL.w bit fields
+EPLEN_AUX_BIT, EPLEN_NOISE_DIRTY_BIT, EPLEN_METRIC_SHIFT, EPLEN_METRIC_MASK, EPLEN_METRIC_BIAS = 1 << 12, 1 << 13, 14, 0xFFFF, 106 << 11
+LOSS_TERM_NAMES = ("move_towards_goal", "falling", "falling_speed")      # QD/racing_ctbr_env.py:331-353
 # ... then planes read every step and written on reset / startup
 PL_DRAG2 = 9     # quadratic drag x y z(*z_drag) | mass
 PL_DRAG1 = 10    # linear drag x y z(*z_drag)    | exp(-dt/thrust_delay)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GR_ABI_VERSION 1
+#define GR_ABI_VERSION 2
 
 /* ---- layout constants (mirrored by generalizableracing_b200/layout.py) ---- */
 #define GR_OBS_DIM 16
@@ -121,6 +121,9 @@ typedef struct GrState {
 
 #define GR_LAUNCH_PREFETCH 2   /* with GR_LAUNCH_PDL: fetch the read-mostly planes before the grid dependency (see racing_step.cu);
                                  clear it for the first step after the HOST rewrote planes 9..15 of the state */
+#define GR_LAUNCH_PREFETCH_L2 4 /* with GR_LAUNCH_PDL, instead of GR_LAUNCH_PREFETCH: before the grid dependency the read-mostly planes are
+                                 only pulled into L2 (prefetch.global.L2, no registers, no staleness protocol); every plane is then
+                                 loaded after the wait, the read-mostly ones as L2 hits.  Safe after host edits of any plane. */
 
 /* Random source: dense tensor (parity mode) or in-kernel Philox4x32-10 (throughput mode). */
 typedef struct GrRandom {
@@ -154,6 +157,10 @@ typedef struct GrStepIO {
   int64_t tape_stride;      /* env capacity of one tape step = 32 * tiles */
   uint64_t* phase_times;    /* [num_warps][5] %globaltimer stamps; only written by a -DGR_PHASE_TIMING build (tools/)  optional */
   float* log_accum;         /* [GR_LOG_SHARDS][GR_LOG_SLOTS] float atomics (sum the shards), see GR_LOG_*  optional */
+  float* aligned_states;    /* [N,13] extras["aligned_states"] = extras["nominal_states"] in value (closure A.1): local position 3 |
+                               quaternion 4 | world linear velocity 3 | world angular velocity 3 of the step BEFORE any reset
+                               (L/envs/manager_based_diff_rl_env.py:205-212)                                  optional */
+  float* acc;               /* [N,3] extras["acc"]: world linear acceleration of the step (droneDynamics.py:126) optional */
 } GrStepIO;
 
 #define GR_LOG_NUM_RESET 0          /* number of envs reset in this step                          */
@@ -161,6 +168,13 @@ typedef struct GrStepIO {
 #define GR_LOG_SUM_EPSUM 2          /* +k: sum over reset envs of episode sum of reward term k (6) */
 #define GR_LOG_NUM_TIMEOUT 8
 #define GR_LOG_NUM_TERMINATED 9
+/* RacingCommand metrics logged by CommandTerm.reset (QD/mdp/commands.py:258-260): sums over the reset envs of the value the
+ * previous step's command update assigned (0 for an env whose last command update was a full reset()) */
+#define GR_LOG_SUM_ACTION_RATE 10   /* command_rate_penalty: kept per env as a 16-bit float, rel. error <= 2^-12 */
+#define GR_LOG_SUM_LIN_SPD 11       /* |v_w| */
+#define GR_LOG_SUM_ANG_SPD 12       /* |omega_b| */
+#define GR_LOG_SUM_LOSS 13          /* +k: sum over reset envs of the LossManager episode sum of loss term k (3), differentiable physics
+                                       with episode sums on (L/managers/loss_manager.py:71-78); 0 otherwise, as in the reference */
 #define GR_LOG_SLOTS 16
 #define GR_LOG_SHARDS 256          /* accumulator rows (64 B each), picked by warp id: spreads the RED traffic over L2 */
 

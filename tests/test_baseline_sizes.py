@@ -60,7 +60,7 @@ def test_step_parity_at_c2_c4_sizes_on_the_bench_table(backend, mode):
         env.export_gate_passed = True
         if device != "cpu":
             from generalizableracing_b200 import _lib as B
-            assert env._launch_flags & B.GR_LAUNCH_PDL and env._launch_flags & B.GR_LAUNCH_PREFETCH      # the bench's launch configuration
+            assert env._launch_flags & B.GR_LAUNCH_PDL and env._launch_flags & (B.GR_LAUNCH_PREFETCH | B.GR_LAUNCH_PREFETCH_L2)      # the bench's launch configuration
         r0 = PC.draw_rnd(N, g) if mode == "dense" else _fill(env, 0).cpu()
         o_obs, _ = orc.reset(r0)
         k_obs, kex = env.reset(r0.to(device)) if mode == "dense" else env.reset()

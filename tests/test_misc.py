@@ -68,37 +68,67 @@ def test_config_stages():
 
 
 @pytest.mark.parametrize("backend", backend_params(), indirect=True)
-def test_episode_log_accumulators(backend):
-    """extras["log"]: means over the envs reset since the last read == the oracle's per-reset logs, aggregated."""
+@pytest.mark.parametrize("stage,diff", [(0, False), (1, False), (2, False), (1, True)])
+def test_episode_log_accumulators(backend, stage, diff):
+    """extras["log"]: means over the envs reset since the last read == the oracle's per-reset logs, aggregated -- every key the reference
+    writes in _reset_idx (manager_based_diff_rl_env.py:380-407): Episode_Reward/*, Episode_Loss/* (LossManager episode sums),
+    Curriculum/*, Metrics/next_gate_pose/{accumulate_gates, action_rate, avg_lin_spd, avg_ang_spd} (QD/mdp/commands.py:257-260).
+    Half of the envs start one step before their time-out, so the log of the very first step after reset() is exercised too (their
+    command metrics were zeroed by CommandTerm.reset and no command update has run since)."""
     N = 128
-    cfg, table, orc, env, g = PC.make_pair(backend, stage=1, N=N, seed=8)
+    cfg, table, orc, env, g = PC.make_pair(backend, stage=stage, N=N, seed=8 + stage, diff=diff, horizon=130)
     r0 = PC.draw_rnd(N, g)
     orc.reset(r0)
     env.reset(r0.to(env.device))
     _ = env.extras["log"]                                              # drain the reset's own log
     ep = torch.randint(0, cfg.max_episode_length, (N,), generator=g)
+    ep[::2] = cfg.max_episode_length - 1
     orc.episode_length_buf[:] = ep
     env.episode_length_buf = ep
-    n_reset, sum_gates = 0, 0.0
-    sums = {k: 0.0 for k in L_.REWARD_TERM_NAMES}
+    if diff:
+        orc.detach()
+        env.detach()
+    metric_keys = ["Metrics/next_gate_pose/" + k for k in ("accumulate_gates", "action_rate", "avg_lin_spd", "avg_ang_spd")]
+    keys = ["Episode_Reward/" + k for k, w in zip(L_.REWARD_TERM_NAMES, orc.reward_weights) if w != 0.0] + ["Episode_Loss/" + k for k in L_.LOSS_TERM_NAMES] + metric_keys
+    n_reset, sums = 0, {k: 0.0 for k in keys}
     for t in range(120):
         if t % 5 == 4:
             PC.teleport_near_gate(orc, env, g)
         a, r = torch.randn(N, 4, generator=g) * 0.5, PC.draw_rnd(N, g)
         with torch.no_grad():
             _, _, term, to, oex = orc.step(a, r)
-        env.step(a.to(env.device), r.to(env.device))
+        _, _, _, kex = env.step(a.to(env.device), r.to(env.device))
         k = int((term | to).sum())
         if k:
             n_reset += k
-            sum_gates += float(oex["log"]["Metrics/next_gate_pose/accumulate_gates"]) * k
-            for name in sums:
-                sums[name] += float(oex["log"]["Episode_Reward/" + name]) * k
+            for name in keys:
+                sums[name] += float(oex["log"][name]) * k
+        if t == 0:                                # the first step after reset(): N/2 time-outs whose command metrics are still zero
+            assert k >= N // 2
+            first = kex["log"]
+            for name in keys:
+                ref = sums[name] / k
+                tol = (2e-3 if name.endswith("action_rate") else 1e-4) * max(1.0, abs(ref))
+                assert abs(float(first[name]) - ref) < tol, (name, float(first[name]), ref)
+            for name in keys:
+                sums[name] = 0.0
+            n_reset = 0
+        if diff:
+            assert [n for n, _ in kex["log_losses"]] == [n for n, _ in oex["log_losses"]]
+            for (_, kv), (_, ov) in zip(kex["log_losses"], oex["log_losses"]):
+                assert abs(float(kv) - ov) < 1e-5 * max(1.0, abs(ov))
     log = env.extras["log"]
     assert n_reset > 20
-    assert abs(float(log["Metrics/next_gate_pose/accumulate_gates"]) - sum_gates / n_reset) < 1e-4
-    for name in sums:
-        assert abs(float(log["Episode_Reward/" + name]) - sums[name] / n_reset) < 1e-4 * max(1.0, abs(sums[name] / n_reset)), name
+    assert set(keys) <= set(log.keys())
+    for name in keys:
+        ref = sums[name] / n_reset
+        tol = (2e-3 if name.endswith("action_rate") else 1e-4) * max(1.0, abs(ref))       # action_rate rides as a 16-bit float per env (2^-12)
+        assert abs(float(log[name]) - ref) < tol, (name, float(log[name]), ref)
+    if diff:
+        assert abs(sums["Episode_Loss/move_towards_goal"]) > 0
+    else:
+        assert all(float(log["Episode_Loss/" + k]) == 0.0 for k in L_.LOSS_TERM_NAMES)   # the sums only move with differentiable physics
     assert abs(float(log["Curriculum/terrain_levels"]) - float(orc.terrain_levels.float().mean())) < 1e-6
-    assert abs(float(log["Curriculum/command_noise_level"]) - float(orc.noise_level.mean())) < 1e-5
+    if cfg.noise_curriculum and cfg.add_cmd_noise:
+        assert abs(float(log["Curriculum/command_noise_level"]) - float(orc.noise_level.mean())) < 1e-5
     assert float(log["Episode_Termination/time_out"]) + float(log["Episode_Termination/terminated"]) >= n_reset

@@ -156,6 +156,12 @@ def test_step_and_reset_bit_exact_with_reference_env(stage):
                 assert float(rl["Metrics/next_gate_pose/" + name]) == float(ol["Metrics/next_gate_pose/" + name]), (where, name)
             for name in ref.reward_manager._term_names:
                 assert float(rl["Episode_Reward/" + name]) == float(ol["Episode_Reward/" + name]), (where, name)
+            for name in ref.loss_manager._term_names:            # LossManager.reset (loss_manager.py:71-78): the keys exist in every mode; the
+                assert "Episode_Loss/" + name in rl and "Episode_Loss/" + name in ol      # harness runs the reference with the differentiable flag
+                if cfg.is_differentiable_physics:                                           # on, so values compare in that mode only
+                    assert float(rl["Episode_Loss/" + name]) == float(ol["Episode_Loss/" + name]), (where, name)
+                else:
+                    assert float(ol["Episode_Loss/" + name]) == 0.0
             if cfg.noise_curriculum:
                 assert float(rl["Curriculum/command_noise_level"]) == float(ol["Curriculum/command_noise_level"]), where
     assert n_reset >= N and n_pass > 50, (n_reset, n_pass)    # the scenario exercised what it claims to
@@ -205,6 +211,11 @@ def test_bptt_losses_and_gradient_match_reference_env():
         assert torch.equal(r_ex["aligned_states"].detach(), o_ex["aligned_states"].detach()), t
         assert torch.equal(r_ex["nominal_states"].detach(), o_ex["nominal_states"].detach()), t
         assert torch.equal(ref.loss_manager._step_loss, o_ex["loss_terms"]), t
+        assert r_ex["log_losses"] == o_ex["log_losses"], t                      # manager_based_diff_rl_env.py:257 (naive_train.py:173)
+        for i, name in enumerate(ref.loss_manager._term_names):                 # LossManager episode sums, logged as Episode_Loss/* on reset
+            assert torch.equal(ref.loss_manager._episode_sums[name], orc.loss_episode_sums[:, i]), (t, name)
+            if len(reset_ids):
+                assert float(r_ex["log"]["Episode_Loss/" + name]) == float(o_ex["log"]["Episode_Loss/" + name]), (t, name)
         lr.append(r_ex["losses"])
         lo.append(o_ex["losses"])
     assert 0 < n_reset < N * H // 2, n_reset
