@@ -277,7 +277,47 @@ def run_ours(args):
         t = torch.tensor([reps], device=dev)
         dist.broadcast(t, 0)
         reps = int(t.item())
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    # ---- the timed set as ONE graph: M back-to-back repetitions of exactly K launches with a timing event at every repetition
+    # boundary.  The events are event-record NODES on a forked branch of the graph (torch.cuda.Event(external=True)): event r fires when
+    # the last kernel of repetition r-1 has completed, so ev[r+1] - ev[r] is the device time of exactly the K steps of repetition r in
+    # the steady state of the dependent-launch chain (the kernels' own programmatic edges stay intact; no graph-launch ramp inside a
+    # repetition).  Falls back to one graph launch per repetition, events on the stream, if the capture is refused.
+    def build_timed_graph(M):
+        evn = [torch.cuda.Event(enable_timing=True, external=True) for _ in range(M + 1)]
+        gr = torch.cuda.CUDAGraph()
+        branch = torch.cuda.Stream(dev)
+        with torch.cuda.graph(gr):
+            main = torch.cuda.current_stream(dev)
+            for r in range(M + 1):
+                mark = torch.cuda.Event()
+                mark.record(main)
+                branch.wait_event(mark)
+                evn[r].record(branch)
+                if r < M:
+                    launch_seq((W + r * K) % R, K, 40_000)
+            main.wait_stream(branch)
+        return gr, evn
+
+    # M: as many repetitions as ~2000 kernel nodes hold, and a total launch count that leaves the next replay's first batches cold
+    M = max(1, min(reps, 2000 // K if K <= 2000 else 1))
+    while M > 1 and 0 < (M * K) % R < 4:
+        M -= 1
+    timed_graph = None
+    if not args.events_on_stream:
+        try:
+            timed_graph, evn = build_timed_graph(M)
+            timed_graph.replay()
+            torch.cuda.synchronize(dev)
+            chk = med([evn[r].elapsed_time(evn[r + 1]) for r in range(M)])
+            if not (0.4 * est_rep_ms < chk < 1.2 * est_rep_ms):
+                raise RuntimeError(f"in-graph events read {chk} ms against {est_rep_ms} ms per repetition")
+        except Exception as ex:                            # noqa: BLE001 -- any capture problem: the per-launch method still measures
+            sys.stderr.write(f"bench.py: in-graph timing events unavailable ({ex}); timing one graph launch per repetition\n")
+            timed_graph = None
+    n_replays = -(-reps // M) if timed_graph is not None else 0
+    if timed_graph is not None:
+        reps = n_replays * M
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps if timed_graph is None else min(reps, 200))]
 
     # ---- clock sampler (rank 0's GPU) starts >= 0.5 s BEFORE the first timed repetition, under the same load
     clk = ClockSampler(local) if rank == 0 else None
@@ -291,29 +331,40 @@ def run_ours(args):
         lead_replays += 1
         if lead_replays % 64 == 0:
             torch.cuda.synchronize(dev)
-    for e in envs:
-        e._log_accum.zero_()
+    # ---- the same K steps as isolated repetitions (one graph launch each, events on the stream): what a caller who launches K steps
+    # and waits would see, graph-launch ramp included.  Reported beside the headline, and the headline itself in the fallback.
     torch.cuda.synchronize(dev)
     barrier(world)
-    torch.cuda.synchronize(dev)
-    # ---- timed: `reps` back-to-back repetitions of EXACTLY K steps, each bracketed by CUDA events on the launching stream.  A
-    # repetition is one or a few graph launches enqueued ahead of the GPU, so a host hiccup cannot land inside one.
-    for r in range(reps):
+    for r in range(len(evs)):
         evs[r][0].record()
         for gr in plans[r % n_distinct]:
             gr.replay()
         evs[r][1].record()
     torch.cuda.synchronize(dev)
+    isolated_ms = [a.elapsed_time(b) for a, b in evs]
+    for e in envs:
+        e._log_accum.zero_()
+    torch.cuda.synchronize(dev)
+    barrier(world)
+    torch.cuda.synchronize(dev)
+    # ---- timed: `reps` back-to-back repetitions of EXACTLY K steps, each bracketed by CUDA events
+    if timed_graph is not None:
+        local_ms = []
+        for _ in range(n_replays):
+            timed_graph.replay()
+            torch.cuda.synchronize(dev)
+            local_ms += [evn[r].elapsed_time(evn[r + 1]) for r in range(M)]
+    else:
+        local_ms = isolated_ms
     barrier(world)
     if clk is not None:
         clk.__exit__()
-    local_ms = [a.elapsed_time(b) for a, b in evs]
     rep_ms = reduce_vector(local_ms, world, dev, "max")          # per repetition: max over ranks
     per_rank = reduce_vector([med(local_ms), min(local_ms), max(local_ms)], world, dev, "gather")
     ms = med(rep_ms)                                             # reported: the median repetition
     # emergent reset rate of the timed workload, from the kernels' own log accumulators
     tot = torch.stack([e._log_accum.sum(dim=0) for e in envs]).sum(dim=0)
-    reset_rate = float(tot[0].item()) / (reps * K * N)
+    reset_rate = float(tot[0].item()) / ((reps if timed_graph is not None else len(evs)) * K * N)
     value = world * N * K / (ms * 1e-3)
     kernel_us = med(local_ms) * 1e3 / K
     peak, peak_src, _ = load_peaks()
@@ -324,8 +375,13 @@ def run_ours(args):
               "kernel_us_per_rank_median": [float(x) * 1e3 / K for x in per_rank[:, 0]],
               "kernel_us_per_rank_min": [float(x) * 1e3 / K for x in per_rank[:, 1]],
               "kernel_us_per_rank_max": [float(x) * 1e3 / K for x in per_rank[:, 2]],
-              "how": f"{reps} back-to-back repetitions of exactly K={K} steps, each CUDA-event timed on the launching stream and max-reduced over ranks; "
-                     f"value = median repetition; barrier + synchronize around the whole set; untimed lead-in of {lead_replays} repetitions for the clock sampler",
+              "isolated_rep_ms_median": med(isolated_ms), "isolated_kernel_us": med(isolated_ms) * 1e3 / K,
+              "events": "in-graph" if timed_graph is not None else "on-stream",
+              "how": (f"{reps} back-to-back repetitions of exactly K={K} steps = {n_replays} replays of one CUDA graph holding {M} repetitions with a timing-event node "
+                      f"at every repetition boundary (fires when the repetition's last kernel completes); " if timed_graph is not None else
+                      f"{reps} back-to-back repetitions of exactly K={K} steps, one graph launch each, CUDA events on the launching stream; ") +
+                     f"every repetition max-reduced over ranks, value = median repetition; barrier + synchronize around the set; untimed lead-in of {lead_replays} "
+                     f"repetitions for the clock sampler; isolated_* = the same K steps as one graph launch between two stream events (launch ramp included)",
               "host_numa_binding": numa}
 
     def timed_graphs(pls, n_reps):
@@ -428,7 +484,7 @@ def run_ours(args):
     e2e_sync_ms = med(timed_e2e(Ke, 1, max(5, e2e_reps // 4)))          # one step in flight: H2D -> kernel -> D2H strictly in sequence
     assert torch.isfinite(h_obs[0]).all() and h_done[0].min() >= 0
     h2d = N * 4 * 4
-    d2h = N * 16 * 4 + N * 4 + N * 8
+    d2h = N * 16 * 4 + N * 4 + N * 2           # obs, reward, and dones as the two uint8 masks (widened to int64 on the host side of the wait)
     probe = copy_only_probe(dev, world, h_act, h_obs, h_rew, h_done, h2d, d2h, Ke)
 
     # ---- C5: the one collective of the path (NCCL policy-gradient all-reduce) and a whole PPO iteration with it inside the captured
@@ -483,7 +539,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                     "ms_per_step": e2e_ms / Ke, "repeats": e2e_reps, "rep_ms_min": float(e2e_v.min()), "rep_ms_max": float(e2e_v.max()),
                     "api": f"RacingVecEnv.step_host -> gr_host_pipe_step/wait (C ABI, pinned HOST buffers: actions in; obs, reward, int64 dones out "
-                           f"every step; {depth} steps in flight, results of step t read while step t+1 runs)",
+                           f"every step (dones cross PCIe as two uint8 masks); {depth} steps in flight, results of step t read while step t+1 runs)",
                     "sync_per_step": {"value": world * N * Ke / (e2e_sync_ms * 1e-3), "ms_per_step": e2e_sync_ms / Ke,
                                       "note": "same call, one step in flight (H2D -> kernel -> D2H in sequence)"},
                     "copy_only_probe": probe},
@@ -515,7 +571,8 @@ def copy_only_probe(dev, world, h_act, h_obs, h_rew, h_done, h2d, d2h, steps):
     """The platform's ceiling for the e2e loop: the SAME buffers and sizes, one cudaMemcpyAsync per buffer, H2D on one stream and D2H on
     another, all ranks concurrently, NO kernel and no dependencies -- what PCIe / the host memory system gives this many GPUs."""
     N = h_obs[0].shape[0]
-    d_act, d_obs, d_rew, d_done = torch.empty(N, 4, device=dev), torch.empty(N, 16, device=dev), torch.empty(N, device=dev), torch.empty(N, dtype=torch.int64, device=dev)
+    d_act, d_obs, d_rew, d_masks = torch.empty(N, 4, device=dev), torch.empty(N, 16, device=dev), torch.empty(N, device=dev), torch.empty(2 * N, dtype=torch.uint8, device=dev)
+    h_masks = [torch.empty(2 * N, dtype=torch.uint8).pin_memory() for _ in h_act]
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     depth = len(h_act)
 
@@ -527,7 +584,7 @@ def copy_only_probe(dev, world, h_act, h_obs, h_rew, h_done, h2d, d2h, steps):
             with torch.cuda.stream(s_out):
                 h_obs[k].copy_(d_obs, non_blocking=True)
                 h_rew[k].copy_(d_rew, non_blocking=True)
-                h_done[k].copy_(d_done, non_blocking=True)
+                h_masks[k].copy_(d_masks, non_blocking=True)
 
     loop(5)
     out = []
@@ -1058,6 +1115,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-collective", action="store_true", help="skip the C5 block (all-reduce + PPO iteration at 65,536 envs per GPU)")
+    ap.add_argument("--events-on-stream", action="store_true", help="time one graph launch per repetition (events on the stream) instead of in-graph event nodes")
     ap.add_argument("--repeats", type=int, default=0, help="timed repetitions of the K-step region (0 = ~1.2 s worth, between 100 and 8000)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()

@@ -129,6 +129,7 @@ GR_HOST_PIPE_MAX_DEPTH = 4
 GR_LAUNCH_PDL = 1
 GR_LAUNCH_PREFETCH = 2
 GR_LAUNCH_PREFETCH_L2 = 4
+GR_LAUNCH_EARLY_STORE = 8
 GR_LOG_SLOTS = 16
 GR_LOG_NUM_RESET, GR_LOG_SUM_GATES, GR_LOG_SUM_EPSUM, GR_LOG_NUM_TIMEOUT, GR_LOG_NUM_TERMINATED = 0, 1, 2, 8, 9
 GR_LOG_SUM_ACTION_RATE, GR_LOG_SUM_LIN_SPD, GR_LOG_SUM_ANG_SPD, GR_LOG_SUM_LOSS = 10, 11, 12, 13

@@ -79,16 +79,19 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
   __shared__ float4 obs_stage[8 * 128];                 // 2 KB per warp, up to 8 warps per block (GlobalObsSink)
 
   StepOut so;
-  if (!racing_step_body<kNoise, kDiff, kPhilox, kStats>(cfg, tr, e, a_t, n01, n23, draws, eps0, lsum, io, i, active,
-                                                        GlobalObsSink{io, live, obs_stage + (threadIdx.x >> 5) * 128}, so)) return;
+  GlobalObsSink sink{io, live, obs_stage + (threadIdx.x >> 5) * 128};
+  if (st.launch_flags & GR_LAUNCH_EARLY_STORE) sink.tile = tile;
+  if (!racing_step_body<kNoise, kDiff, kPhilox, kStats>(cfg, tr, e, a_t, n01, n23, draws, eps0, lsum, io, i, active, sink, so)) return;
 
   GR_STAMP(3);
   // ---- 12. outputs + state write-back ----
-  if (kStats && !so.reset) add_episode_sums(eps0, e, so.terms, cfg.dt);        // deferred to here: the episode-sum plane is the last load to arrive
-  store_env<kNoise>(e, tile, so.reset, so.noise_dirty);
-  if (kStats) {
-    st_plane(tile, PL_EPSUM0, eps0);
-    if (kDiff) st_plane(tile, PL_LOSSSUM, lsum);
+  if (!so.stored) {
+    if (kStats && !so.reset) add_episode_sums(eps0, e, so.terms, cfg.dt);        // deferred to here: the episode-sum plane is the last load to arrive
+    store_env<kNoise>(e, tile, so.reset, so.noise_dirty);
+    if (kStats) {
+      st_plane(tile, PL_EPSUM0, eps0);
+      if (kDiff) st_plane(tile, PL_LOSSSUM, lsum);
+    }
   }
   io.reward[i] = so.reward;
   io.terminated[i] = so.terminated ? 1 : 0;
@@ -113,6 +116,8 @@ struct RolloutObsSink {
     if (seq_rows) g.rows(seq_rows, i, o0, o1, o2, o3);
     if (out_rows) g.rows(out_rows, i, o0, o1, o2, o3);
   }
+  template <bool kNoise, bool kDiff, bool kStats>
+  __device__ __forceinline__ bool state_final(EnvRegs&, float4&, const float4&, const float (&)[GR_NUM_REWARD_TERMS], float, bool, bool) const { return false; }
   __device__ __forceinline__ bool wants_critic() const { return critic_rows != nullptr; }
   __device__ __forceinline__ void critic(int i, float4 c0, float4 c1, float4 c2, float4 c3) const { g.rows(critic_rows, i, c0, c1, c2, c3); }
   __device__ __forceinline__ void aux(int i, float v) const { if (aux_ptr) aux_ptr[i] = v; }

@@ -233,6 +233,7 @@ __device__ __forceinline__ float4 fm_tanh4(float4 a) { return make_float4(fm_tan
 struct StepOut {
   float reward; float terms[GR_NUM_REWARD_TERMS];     // terms: weighted step rewards / dt (RewardManager._step_reward)
   bool terminated, time_out, reset, passed, noise_dirty;
+  bool stored;       // the sink already wrote the state back (GlobalObsSink with an early store)
 };
 
 // observation sink of the single-step kernel.  A thread owns one 64-byte row; written directly, every store instruction of a
@@ -243,6 +244,12 @@ struct GlobalObsSink {
   const GrStepIO& io;
   unsigned live;
   float4* stage;
+  float4* tile = nullptr;            // set => the state is written back as soon as it is final (before the observation section), so the
+                                     // stores of a warp start draining while it still computes its observations
+  // called by the body when the post-step state (e, sums) is final; returns true if it stored the state
+  template <bool kNoise, bool kDiff, bool kStats>
+  __device__ __forceinline__ bool state_final(EnvRegs& e, float4& eps0, const float4& lsum, const float (&terms)[GR_NUM_REWARD_TERMS], float dt, bool reset,
+                                              bool noise_dirty) const;
   __device__ __forceinline__ void rows(float4* __restrict__ out, int i, float4 o0, float4 o1, float4 o2, float4 o3) const {
 #ifdef GR_CPU_EMUL
     float4* o = out + (int64_t)i * 4;
@@ -279,6 +286,16 @@ struct GlobalObsSink {
 __device__ __forceinline__ void add_episode_sums(float4& eps0, EnvRegs& e, const float (&terms)[GR_NUM_REWARD_TERMS], float dt) {
   eps0.x += terms[0] * dt; eps0.y += terms[1] * dt; eps0.z += terms[2] * dt; eps0.w += terms[3] * dt;
   e.es4 += terms[4] * dt; e.es5 += terms[5] * dt;
+}
+
+template <bool kNoise, bool kDiff, bool kStats>
+__device__ __forceinline__ bool GlobalObsSink::state_final(EnvRegs& e, float4& eps0, const float4& lsum, const float (&terms)[GR_NUM_REWARD_TERMS], float dt,
+                                                           bool reset, bool noise_dirty) const {
+  if (!tile) return false;
+  if (kStats && !reset) add_episode_sums(eps0, e, terms, dt);
+  store_env<kNoise>(e, tile, reset, noise_dirty);
+  if (kStats) { st_plane(tile, PL_EPSUM0, eps0); if (kDiff) st_plane(tile, PL_LOSSSUM, lsum); }
+  return true;
 }
 
 // Sections 1-11.  `e` = state before the step in, state after the step (and after a reset) out, e.fifo included;
@@ -504,6 +521,8 @@ __device__ __forceinline__ bool racing_step_body(const GrConfig& cfg, const Trac
   }
 
   if (!active) return false;      // (the caller leaves too)
+  e.fifo = th_a;
+  out.stored = sink.template state_final<kNoise, kDiff, kStats>(e, eps0, lsum, terms, dt, reset, noise_dirty);
 
   // ---- 11. observations on the post-reset state (QD/racing_ctbr_env.py:139-174, QD/mdp/observation.py:22-104) ----
   {
@@ -544,7 +563,6 @@ __device__ __forceinline__ bool racing_step_body(const GrConfig& cfg, const Trac
     }
     sink.aux(i, e.aux);
   }
-  e.fifo = th_a;
   out.reward = reward; out.terminated = terminated; out.time_out = time_out; out.reset = reset; out.passed = passed; out.noise_dirty = noise_dirty;
   return true;
 }

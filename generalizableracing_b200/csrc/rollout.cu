@@ -7,6 +7,7 @@
 // per env for the time scan (coalesced across envs at every t), 128-bit vector copies for the rows.
 #ifndef GR_CPU_EMUL
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #endif
 #include <stdint.h>
 #include "../../include/gracing.h"
@@ -161,6 +162,73 @@ __global__ void adv_normalize_kernel(float* __restrict__ adv, const int64_t tota
   }
 }
 
+#ifndef GR_CPU_EMUL
+// compute_returns as ONE cooperative launch (the three kernels above are ~5 us of work spread over three dependent launches):
+// phase 1 = gae_kernel's scan and block partial, grid-wide barrier, phase 2 = every block merges the (few hundred) partials itself,
+// phase 3 = each thread normalises the T advantages of its own env (just written: L2 hits).  Needs all blocks co-resident; the host
+// side falls back to the three launches when they are not (more than ~2,000 blocks of 128 envs).
+__global__ void __launch_bounds__(kGaeBlock) gae_fused_kernel(const GrStorage s, const float* __restrict__ last_values, const float gamma, const float lam,
+                                                              double* __restrict__ partials, double* __restrict__ moments, const int normalize) {
+  __shared__ Moments sh[kGaeBlock / 32];
+  __shared__ Moments total;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t N = s.N;
+  double cnt = 0.0, s1 = 0.0, s2 = 0.0;
+  if (n < N) {
+    float next_value = last_values[n];
+    float adv = 0.0f;
+    for (int t0 = s.T - 1; t0 >= 0; t0 -= kGaeChunk) {
+      float r[kGaeChunk], v[kGaeChunk];
+      uint8_t d[kGaeChunk];
+#pragma unroll
+      for (int j = 0; j < kGaeChunk; ++j) {
+        const int t = t0 - j;
+        if (t >= 0) {
+          const int64_t k = (int64_t)t * N + n;
+          r[j] = __ldcs(s.rewards + k); v[j] = __ldcs(s.values + k); d[j] = __ldcs(s.dones + k);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kGaeChunk; ++j) {
+        const int t = t0 - j;
+        if (t >= 0) {
+          const int64_t k = (int64_t)t * N + n;
+          const float not_term = 1.0f - (float)d[j];
+          const float delta = r[j] + not_term * gamma * next_value - v[j];
+          adv = delta + not_term * gamma * lam * adv;
+          const float ret = adv + v[j];
+          s.returns[k] = ret;
+          const float a = ret - v[j];
+          s.advantages[k] = a;
+          cnt += 1.0; s1 += (double)a; s2 += (double)a * (double)a;
+          next_value = v[j];
+        }
+      }
+    }
+  }
+  Moments mom{cnt, cnt > 0.0 ? s1 / cnt : 0.0, cnt > 0.0 ? s2 - s1 * s1 / cnt : 0.0};
+  mom = block_merge(mom, sh);
+  if (threadIdx.x == 0) { partials[3 * blockIdx.x] = mom.n; partials[3 * blockIdx.x + 1] = mom.mean; partials[3 * blockIdx.x + 2] = mom.m2; }
+  cooperative_groups::this_grid().sync();
+  Moments m{0.0, 0.0, 0.0};
+  for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) m = merge(m, Moments{__ldcg(partials + 3 * k), __ldcg(partials + 3 * k + 1), __ldcg(partials + 3 * k + 2)});
+  __syncthreads();                                   // (sh is reused)
+  m = block_merge(m, sh);
+  if (threadIdx.x == 0) {
+    total = m;
+    if (blockIdx.x == 0) { moments[0] = m.n; moments[1] = m.mean; moments[2] = m.m2; }
+  }
+  __syncthreads();
+  if (!normalize || n >= N) return;
+  const float mu = (float)total.mean;
+  const float inv_den = (float)sqrt(total.m2 / (total.n - 1.0)) + 1e-8f;
+  for (int t = 0; t < s.T; ++t) {
+    const int64_t k = (int64_t)t * N + n;
+    s.advantages[k] = (__ldcg(s.advantages + k) - mu) / inv_den;
+  }
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // mini-batch gather: one launch for the nine fields; a thread moves one float4 of a row-shaped field
 // or one element of the five scalar fields.
@@ -248,6 +316,21 @@ extern "C" int gr_compute_returns(const GrStorage* s, const float* last_values, 
   const int blocks = (s->N + kGaeBlock - 1) / kGaeBlock;
   double* partials = reinterpret_cast<double*>(scratch);
   double* mom = moments ? moments : partials + 3 * (int64_t)blocks;
+  // one cooperative launch when every block can be resident at once (always at the sizes of BASELINE's configs), else three launches
+  static int resident_blocks = -1;
+  if (resident_blocks < 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gae_fused_kernel, kGaeBlock, 0);
+    resident_blocks = sms * per_sm;
+  }
+  if (blocks <= resident_blocks) {
+    GrStorage sv = *s;
+    int norm = normalize;
+    void* args[] = {&sv, (void*)&last_values, &gamma, &lam, &partials, &mom, &norm};
+    return (int)cudaLaunchCooperativeKernel((void*)gae_fused_kernel, dim3((unsigned)blocks), dim3(kGaeBlock), args, 0, st);
+  }
   gae_kernel<<<blocks, kGaeBlock, 0, st>>>(*s, last_values, gamma, lam, partials);
   gae_moments_kernel<<<1, 256, 0, st>>>(partials, blocks, mom);
   cudaError_t e = cudaGetLastError();

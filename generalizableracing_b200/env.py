@@ -166,6 +166,8 @@ class RacingVecEnv:
         # read-mostly planes before the grid dependency: "1" = into registers with the stale-flag protocol, "l2" = into L2 only, "0" = off
         pf = {"0": 0, "1": B.GR_LAUNCH_PREFETCH, "l2": B.GR_LAUNCH_PREFETCH_L2}[os.environ.get("GRACING_PREFETCH", "1").lower()]
         flags = (B.GR_LAUNCH_PDL | pf) if (pdl and self.device.type == "cuda") else 0
+        if os.environ.get("GRACING_EARLY_STORE", "0") == "1":
+            flags |= B.GR_LAUNCH_EARLY_STORE
         self._launch_flags = flags
         self._state = B.GrState(self.planes.data_ptr(), self._stride, N, self.num_planes, int(env_id_offset), max(spans),
                                 int(block_threads), flags, self._chunk_types.data_ptr())
@@ -370,7 +372,8 @@ class RacingVecEnv:
         if self._needs_reset:
             self.reset()
         o = self._last
-        if fresh_noise:
+        if fresh_noise or getattr(self, "_host_stale", False):
+            self._host_stale = False
             return self._observe_fresh(rnd)
         if self._ops is not None and o["obs"].is_inference() and not torch.is_inference_mode_enabled():
             # operator outputs allocated under the runner's torch.inference_mode() (on_policy_runner.py:141): hand normal tensors
@@ -625,7 +628,12 @@ class RacingVecEnv:
                   critic_obs: Optional[torch.Tensor] = None, time_outs: Optional[torch.Tensor] = None, depth: int = 2) -> int:
         """env.step() for a caller whose tensors live in (pinned) HOST memory: enqueue H2D(actions) -> step kernel ->
         D2H(obs, reward, dones[, critic_obs, time_outs]) and return a ticket at once; the output tensors hold the step's
-        results after ``wait_host(ticket)``.  Up to ``depth`` steps are in flight (copies overlap the next kernel)."""
+        results after ``wait_host(ticket)``.  Up to ``depth`` steps are in flight (copies overlap the next kernel).
+
+        Rules of the asynchronous call: ``actions`` must not be rewritten before ``wait_host(ticket)`` returned for this step (the
+        host->device copy reads it later); all host steps of an env use the ``depth`` and the CUDA stream of the first one (the pipe
+        is created there: a different value raises); ``get_observations()`` after host steps recomputes the observation from the
+        state, because the last observation lives in the caller's host buffer."""
         if self._needs_reset:
             self.reset()
         if self._bptt is not None:
@@ -634,6 +642,10 @@ class RacingVecEnv:
             pipe = C.c_void_p()
             B.check(self._lib.gr_host_pipe_create(self.num_envs, int(depth), self._stream(), C.byref(pipe)), "gr_host_pipe_create")
             self._pipe = pipe
+            self._pipe_key = (int(depth), self._stream())
+        elif self._pipe_key != (int(depth), self._stream()):
+            raise RuntimeError(f"step_host: the host pipe of this env was created with (depth, stream) = {self._pipe_key}; call close() before "
+                               f"changing them (got {(int(depth), self._stream())})")
         for t, shape, dt in ((actions, (self.num_envs, 4), torch.float32), (obs, (self.num_envs, L.OBS_DIM), torch.float32),
                              (reward, (self.num_envs,), torch.float32), (dones, (self.num_envs,), torch.int64),
                              (critic_obs, (self.num_envs, L.OBS_DIM), torch.float32), (time_outs, (self.num_envs,), torch.bool)):
@@ -646,6 +658,7 @@ class RacingVecEnv:
         if self._params_edited:
             self._state.launch_flags = self._launch_flags
             self._params_edited = False
+        self._host_stale = True                    # the device-side copy of "the last observation" is no longer the env's last one
         return ticket.value
 
     def wait_host(self, ticket: int) -> None:

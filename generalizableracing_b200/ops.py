@@ -164,7 +164,8 @@ def step_fwd_tape(env: int, planes: Tensor, action: Tensor, rnd: Optional[Tensor
 @step_fwd_tape.register_fake
 def _(env, planes, action, rnd, step, log_accum, tape, t, export_terms=False):
     N = action.shape[0]
-    return _step_outputs(N, action.device, export_terms) + (action.new_empty(N), action.new_empty(N, 3))
+    terms = _env(env)._bptt._terms if env in _ENVS and _env(env)._bptt is not None else 3         # 3 racing loss terms, 4 on the reach-target env
+    return _step_outputs(N, action.device, export_terms) + (action.new_empty(N), action.new_empty(N, terms))
 
 
 @torch.library.custom_op("gracing::step_bwd", mutates_args=("adjoint", "grad_action"))

@@ -39,6 +39,9 @@ class AlgoRunner:
                                                 backward_tf32=bool(self.cfg.get("fused_backward_tf32", False)),
                                                 backward_kernel=bool(self.cfg.get("fused_backward_kernel", False)))
         self.save_interval = self.cfg.get("save_interval", 200)
+        if self.cfg.get("empirical_normalization", False):
+            raise ValueError("AlgoRunner: empirical_normalization is not built for the BPTT runner (the racing / reach-target agent cfgs keep it off, "
+                             "QD/agents/diff_rl_naive_cfg.py); pass empirical_normalization=False")
         self.log_dir = log_dir
         self.tot_timesteps = 0
         self.tot_time = 0
@@ -88,9 +91,16 @@ class AlgoRunner:
                 torch.distributed.all_reduce(stats)
                 stats /= world
             pending.append((it, ev, stats, self.alg.optimizer.param_groups[0]["lr"]))
+            # interval checkpoints are written HERE, with the weights of iteration `it` (runner.py:193-194), not from the deferred log flush
+            if rank == 0 and self.log_dir is not None and it % self.save_interval == 0:
+                os.makedirs(self.log_dir, exist_ok=True)
+                self.save(os.path.join(self.log_dir, f"model_{it}.pt"))
             if len(pending) >= log_interval or it == last_iter:
                 self._flush_log(pending, N * world, rank)
                 pending = []
+        if rank == 0 and self.log_dir is not None and num_learning_iterations > 0:        # the final checkpoint (runner.py:197-199)
+            os.makedirs(self.log_dir, exist_ok=True)
+            self.save(os.path.join(self.log_dir, f"model_{self.current_learning_iteration}.pt"))
         return self.history
 
     def _flush_log(self, pending, n_global: int, rank: int):
@@ -107,8 +117,6 @@ class AlgoRunner:
                 os.makedirs(self.log_dir, exist_ok=True)
                 with open(os.path.join(self.log_dir, "progress.jsonl"), "a") as f:
                     f.write(json.dumps(rec) + "\n")
-                if it % self.save_interval == 0:
-                    self.save(os.path.join(self.log_dir, f"model_{it}.pt"))
 
     def save(self, path, infos=None):
         torch.save({"model_state_dict": self.alg.actor_critic.state_dict(), "optimizer_state_dict": self.alg.optimizer.state_dict(),

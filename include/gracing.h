@@ -125,6 +125,8 @@ typedef struct GrState {
                                  only pulled into L2 (prefetch.global.L2, no registers, no staleness protocol); every plane is then
                                  loaded after the wait, the read-mostly ones as L2 hits.  Safe after host edits of any plane. */
 
+#define GR_LAUNCH_EARLY_STORE 8 /* gr_step_fwd: write the state planes back before the observation section instead of at the end of the kernel */
+
 /* Random source: dense tensor (parity mode) or in-kernel Philox4x32-10 (throughput mode). */
 typedef struct GrRandom {
   const float* rnd;         /* [num_envs, GR_RND_STRIDE] or NULL => Philox */
@@ -425,10 +427,12 @@ typedef struct GrHostStep {
   const float* action;      /* host [N,4]                                    required */
   float* obs;               /* host [N,16]                                   required */
   float* reward;            /* host [N]                                      required */
-  int64_t* dones;           /* host [N]                                      optional */
+  int64_t* dones;           /* host [N]                                      optional (crosses PCIe as two uint8 masks, widened in wait) */
   float* critic_obs;        /* host [N,16]                                   optional */
   uint8_t* time_out;        /* host [N]                                      optional */
 } GrHostStep;
+/* `action` must stay untouched until gr_host_pipe_wait(ticket) of that step returned; one calling thread per pipe;
+ * gr_host_pipe_destroy synchronises the three streams before it frees the staging buffers. */
 int gr_host_pipe_create(int32_t num_envs, int32_t depth, void* compute_stream, GrHostPipe** out);
 int gr_host_pipe_destroy(GrHostPipe* pipe);
 int gr_host_pipe_step(GrHostPipe* pipe, const GrConfig* cfg, const GrTrack* track, const GrState* st, const GrRandom* rng,

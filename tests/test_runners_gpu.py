@@ -91,6 +91,36 @@ def test_bptt_runner_reduces_loss(cuda_lib):
     assert last < first
 
 
+def test_bptt_runner_checkpoints(cuda_lib, tmp_path):
+    """runner.py:193-199: interval checkpoints hold the weights of THEIR iteration (also with deferred logging), and the run ends with
+    model_{last iteration}.pt -- the last updates are never lost."""
+    import os
+    from generalizableracing_b200 import make_env
+    from generalizableracing_b200.runners import AlgoRunner
+    torch.manual_seed(0)
+    env = make_env(num_envs=256, stage=0, track="figure8", differentiable=True, bptt_horizon=8)
+    cfg = dict(BPTT_CFG, num_steps_per_env=8, save_interval=4, log_interval=3)
+    runner = AlgoRunner(env, cfg, log_dir=str(tmp_path), device="cuda:0")
+    snaps = {}
+    orig = runner.alg.update
+
+    def update():
+        out = orig()
+        snaps[len(snaps)] = {k: v.clone() for k, v in runner.alg.actor_critic.state_dict().items()}
+        return out
+    runner.alg.update = update
+    runner.learn(7)
+    files = sorted(f for f in os.listdir(tmp_path) if f.startswith("model_"))
+    assert files == ["model_0.pt", "model_4.pt", "model_6.pt"], files
+    for it in (0, 4, 6):
+        ck = torch.load(str(tmp_path / f"model_{it}.pt"), map_location="cuda:0", weights_only=False)
+        assert ck["iter"] == it
+        for k, v in ck["model_state_dict"].items():
+            assert torch.equal(v, snaps[it][k]), (it, k)
+    with pytest.raises(ValueError, match="empirical_normalization"):
+        AlgoRunner(env, dict(cfg, empirical_normalization=True), device="cuda:0")
+
+
 def test_bptt_algorithm_fast_path_equals_autograd_path(cuda_lib):
     """BPTT.update through backward_window == BPTT through the chained autograd Function (same policy gradient)."""
     from generalizableracing_b200 import make_env
