@@ -52,12 +52,12 @@ class GrStepIO(C.Structure):
     _fields_ = [("action", c_p), ("obs", c_p), ("critic_obs", c_p), ("aux_obs", c_p), ("reward", c_p),
                 ("terminated", c_p), ("time_out", c_p), ("dones", c_p), ("reward_terms", c_p), ("gate_passed", c_p),
                 ("loss", c_p), ("loss_terms", c_p), ("tape", c_p), ("tape_stride", C.c_int64), ("phase_times", c_p), ("log_accum", c_p),
-                ("aligned_states", c_p), ("acc", c_p)]
+                ("aligned_states", c_p), ("acc", c_p), ("dones_u8", c_p)]
 
 
 class GrBwdIO(C.Structure):
     _fields_ = [("tape", c_p), ("tape_stride", C.c_int64), ("t_begin", c_i), ("t_end", c_i), ("grad_loss", c_p),
-                ("grad_scale", c_f), ("adjoint", c_p), ("adj_stride", C.c_int64), ("grad_action", c_p)]
+                ("grad_scale", c_f), ("adjoint", c_p), ("adj_stride", C.c_int64), ("grad_action", c_p), ("lanes", c_i)]
 
 
 class GrRolloutIO(C.Structure):
@@ -122,7 +122,7 @@ class GrPpoBatch(C.Structure):
 
 
 class GrHostStep(C.Structure):
-    _fields_ = [("action", c_p), ("obs", c_p), ("reward", c_p), ("dones", c_p), ("critic_obs", c_p), ("time_out", c_p)]
+    _fields_ = [("action", c_p), ("obs", c_p), ("reward", c_p), ("dones", c_p), ("critic_obs", c_p), ("time_out", c_p), ("dones_u8", c_p)]
 
 
 GR_HOST_PIPE_MAX_DEPTH = 4
@@ -211,6 +211,7 @@ PROTOTYPES = {
     "gr_host_pipe_step": (C.c_int, [c_p, C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom),
                                     C.POINTER(GrHostStep), c_p, C.POINTER(C.c_int64)]),
     "gr_host_pipe_wait": (C.c_int, [c_p, C.c_int64]),
+    "gr_host_copy_probe": (C.c_int, [c_i, c_i, c_i, C.POINTER(C.c_double)]),
 }
 
 

@@ -28,6 +28,7 @@ struct BpttObsSink {
     __stcs(critic_row + 0, c0); __stcs(critic_row + 1, c1); __stcs(critic_row + 2, c2); __stcs(critic_row + 3, c3);
   }
   __device__ __forceinline__ void aux(int, float v) const { if (aux_ptr) *aux_ptr = v; }
+  __device__ __forceinline__ constexpr bool wants_policy() const { return true; }
   template <bool kNoise, bool kDiff, bool kStats>          // (the state stays in registers over the rollout)
   __device__ __forceinline__ bool state_final(EnvRegs&, float4&, const float4&, const float (&)[GR_NUM_REWARD_TERMS], float, bool, bool) const { return false; }
 };

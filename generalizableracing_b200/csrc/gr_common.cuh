@@ -66,6 +66,7 @@ struct RandSrc<false> {
       : row(reinterpret_cast<const float4*>(r.rnd) + (int64_t)i * (GR_RND_STRIDE / 4)) {}
   __device__ __forceinline__ float4 get4(int call) const { return __ldg(row + call); }
   __device__ __forceinline__ void normals8(float4& a, float4& b) const { a = __ldg(row); b = __ldg(row + 1); }
+  __device__ __forceinline__ float normal6() const { return __ldg(row + 1).z; }        // slot 6 alone
 };
 
 template <>
@@ -82,6 +83,7 @@ struct RandSrc<true> {
     a = make_float4(p0.x, p0.y, p1.x, p1.y);
     b = make_float4(p2.x, p2.y, p3.x, p3.y);
   }
+  __device__ __forceinline__ float normal6() const { return box_muller16(ph(0u).w).x; }        // slot 6 alone: the same bits normals8 gives
 };
 
 // Programmatic dependent launch (sm_90+): wait = block until the previous kernel in the stream has completed and its
@@ -118,10 +120,13 @@ template <bool kPhilox>
 struct Draws {
   const RandSrc<kPhilox>& rs;
   const float4* spec;       // shared: [kSpecCalls][blockDim.x] or nullptr
+  bool have_normals = true; // false: the caller skipped normals8() (a window step that records no observation); slot 6 is then drawn on demand
   __device__ __forceinline__ float4 get4(int call) const {
     if (kPhilox && spec) return spec[spec_slot(call) * blockDim.x + threadIdx.x];
     return rs.get4(call);
   }
+  // slot 6 (thr_est_error normal, consumed by a reset only)
+  __device__ __forceinline__ float thr_normal(float from_normals8) const { return have_normals ? from_normals8 : rs.normal6(); }
 };
 
 // Gate table slice staged in shared memory: rows of types [type_lo, type_lo + ntypes).

@@ -12,10 +12,11 @@
 //
 // The env state advances in compute-stream order, exactly as with gr_step_fwd.
 //
-// Wire format: `dones` (int64 for the caller, RslRlVecEnvWrapper's `.long()`) crosses PCIe as the two uint8 masks the kernel writes
-// anyway (terminated, time_out: 2 B per env instead of 8) into pinned staging owned by the pipe; gr_host_pipe_wait widens them into
-// the caller's int64 / bool buffers on the host.  Contract for the caller: the `action` buffer of a step must stay untouched until
-// that step's ticket has been waited for (the host->device copy is asynchronous), and every call must come from one thread.
+// `dones` reaches the caller either as int64 (RslRlVecEnvWrapper's `.long()`; 8 B per env over PCIe) or as one byte per env
+// (GrHostStep.dones_u8, written by the kernel itself).  Measured on the B200 box: widening the byte masks to int64 on the HOST instead
+// (a 512 KB store stream per 65,536-env step from the calling thread) costs more than letting the DMA engine carry the 8 bytes
+// (108.6 vs 100.8 us per step), so the int64 form is produced on the device.  Contract for the caller: the `action` buffer of a step
+// must stay untouched until that step's ticket has been waited for (the host->device copy is asynchronous), one calling thread per pipe.
 #include <cuda_runtime.h>
 #include <new>
 #include "../../include/gracing.h"
@@ -25,26 +26,12 @@ struct GrHostPipe {
   cudaStream_t compute, h2d, d2h;
   int64_t issued;                    // tickets handed out so far
   struct Slot {
-    float* action; float* obs; float* critic; float* reward; uint8_t* terminated; uint8_t* time_out;
-    uint8_t* h_masks;                  // pinned host staging: [terminated N][time_out N]
-    int64_t* host_dones; uint8_t* host_time_out;      // the caller's buffers of the step in flight (filled by finish())
+    float* action; float* obs; float* critic; float* reward; uint8_t* terminated; uint8_t* time_out; uint8_t* dones_u8; int64_t* dones;
     cudaEvent_t h2d_done, kernel_done, d2h_done;
-    bool busy, widened;
+    bool busy;
   } slot[GR_HOST_PIPE_MAX_DEPTH];
   void* arena;
-  void* host_arena;
 };
-
-// after the slot's copies have landed: dones = terminated | time_out as int64, time_outs as bytes, into the caller's buffers
-static void finish(GrHostPipe* p, GrHostPipe::Slot& sl) {
-  if (sl.widened) return;
-  const size_t N = (size_t)p->num_envs;
-  const uint8_t* __restrict__ term = sl.h_masks;
-  const uint8_t* __restrict__ to = sl.h_masks + N;
-  if (sl.host_dones) { int64_t* __restrict__ d = sl.host_dones; for (size_t i = 0; i < N; ++i) d[i] = (int64_t)((term[i] | to[i]) != 0); }
-  if (sl.host_time_out) { uint8_t* __restrict__ t = sl.host_time_out; for (size_t i = 0; i < N; ++i) t[i] = to[i]; }
-  sl.widened = true;
-}
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -54,17 +41,15 @@ extern "C" int gr_host_pipe_create(int32_t num_envs, int32_t depth, void* comput
   if (num_envs <= 0 || depth < 1 || depth > GR_HOST_PIPE_MAX_DEPTH) return GR_ERR_SIZE;
   GrHostPipe* p = new (std::nothrow) GrHostPipe();
   if (!p) return (int)cudaErrorMemoryAllocation;
-  p->num_envs = num_envs; p->depth = depth; p->issued = 0; p->arena = nullptr; p->host_arena = nullptr;
+  p->num_envs = num_envs; p->depth = depth; p->issued = 0; p->arena = nullptr;
   p->compute = reinterpret_cast<cudaStream_t>(compute_stream);
   const size_t N = (size_t)num_envs;
-  const size_t per_slot = align256(N * 16) + 2 * align256(N * 64) + align256(N * 4) + align256(2 * N);
+  const size_t per_slot = align256(N * 16) + 2 * align256(N * 64) + align256(N * 4) + 3 * align256(N) + align256(N * 8);
   cudaError_t e = cudaMalloc(&p->arena, per_slot * depth);
   if (e != cudaSuccess) { delete p; return (int)e; }
-  e = cudaHostAlloc(&p->host_arena, align256(2 * N) * depth, cudaHostAllocDefault);
-  if (e != cudaSuccess) { cudaFree(p->arena); delete p; return (int)e; }
   e = cudaStreamCreateWithFlags(&p->h2d, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->d2h, cudaStreamNonBlocking);
-  if (e != cudaSuccess) { cudaFree(p->arena); cudaFreeHost(p->host_arena); delete p; return (int)e; }
+  if (e != cudaSuccess) { cudaFree(p->arena); delete p; return (int)e; }
   char* base = static_cast<char*>(p->arena);
   for (int s = 0; s < depth; ++s) {
     GrHostPipe::Slot& sl = p->slot[s];
@@ -73,11 +58,11 @@ extern "C" int gr_host_pipe_create(int32_t num_envs, int32_t depth, void* comput
     sl.obs = reinterpret_cast<float*>(q); q += align256(N * 64);
     sl.critic = reinterpret_cast<float*>(q); q += align256(N * 64);
     sl.reward = reinterpret_cast<float*>(q); q += align256(N * 4);
-    sl.terminated = reinterpret_cast<uint8_t*>(q);          // the two masks are contiguous: ONE device->host copy
-    sl.time_out = sl.terminated + N;
-    sl.h_masks = static_cast<uint8_t*>(p->host_arena) + align256(2 * N) * s;
-    sl.host_dones = nullptr; sl.host_time_out = nullptr;
-    sl.busy = false; sl.widened = true;
+    sl.terminated = reinterpret_cast<uint8_t*>(q); q += align256(N);
+    sl.time_out = reinterpret_cast<uint8_t*>(q); q += align256(N);
+    sl.dones_u8 = reinterpret_cast<uint8_t*>(q); q += align256(N);
+    sl.dones = reinterpret_cast<int64_t*>(q);
+    sl.busy = false;
     cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&sl.kernel_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&sl.d2h_done, cudaEventDisableTiming);
@@ -92,7 +77,6 @@ extern "C" int gr_host_pipe_destroy(GrHostPipe* p) {
   cudaStreamSynchronize(p->compute);                 // a step kernel may still read / write the slots' device buffers
   cudaStreamSynchronize(p->d2h);
   for (int s = 0; s < p->depth; ++s) {
-    if (p->slot[s].busy) finish(p, p->slot[s]);
     cudaEventDestroy(p->slot[s].h2d_done);
     cudaEventDestroy(p->slot[s].kernel_done);
     cudaEventDestroy(p->slot[s].d2h_done);
@@ -100,7 +84,6 @@ extern "C" int gr_host_pipe_destroy(GrHostPipe* p) {
   cudaStreamDestroy(p->h2d);
   cudaStreamDestroy(p->d2h);
   cudaFree(p->arena);
-  cudaFreeHost(p->host_arena);
   delete p;
   return GR_OK;
 }
@@ -115,7 +98,6 @@ extern "C" int gr_host_pipe_step(GrHostPipe* p, const GrConfig* cfg, const GrTra
   if (sl.busy) {           // the slot's previous device->host copies must have landed before its buffers are rewritten
     e = cudaEventSynchronize(sl.d2h_done);
     if (e != cudaSuccess) return (int)e;
-    finish(p, sl);         // (a caller that never waited for that ticket still gets its dones)
   }
   // stage 1: actions host -> device.  The slot's previous kernel (its reader) finished before d2h_done, waited above.
   e = cudaMemcpyAsync(sl.action, host->action, N * 16, cudaMemcpyHostToDevice, p->h2d);
@@ -125,7 +107,8 @@ extern "C" int gr_host_pipe_step(GrHostPipe* p, const GrConfig* cfg, const GrTra
   cudaStreamWaitEvent(p->compute, sl.h2d_done, 0);
   GrStepIO io = {};
   io.action = sl.action; io.obs = sl.obs; io.critic_obs = host->critic_obs ? sl.critic : nullptr;
-  io.reward = sl.reward; io.terminated = sl.terminated; io.time_out = sl.time_out; io.dones = nullptr;
+  io.reward = sl.reward; io.terminated = sl.terminated; io.time_out = sl.time_out;
+  io.dones = host->dones ? sl.dones : nullptr; io.dones_u8 = host->dones_u8 ? sl.dones_u8 : nullptr;
   io.log_accum = log_accum;
   const int rc = gr_step_fwd(cfg, track, st, rng, &io, p->compute);
   if (rc != GR_OK) return rc;
@@ -134,12 +117,12 @@ extern "C" int gr_host_pipe_step(GrHostPipe* p, const GrConfig* cfg, const GrTra
   cudaStreamWaitEvent(p->d2h, sl.kernel_done, 0);
   e = cudaMemcpyAsync(host->obs, sl.obs, N * 64, cudaMemcpyDeviceToHost, p->d2h);
   if (e == cudaSuccess) e = cudaMemcpyAsync(host->reward, sl.reward, N * 4, cudaMemcpyDeviceToHost, p->d2h);
-  if (e == cudaSuccess && (host->dones || host->time_out)) e = cudaMemcpyAsync(sl.h_masks, sl.terminated, 2 * N, cudaMemcpyDeviceToHost, p->d2h);
+  if (e == cudaSuccess && host->dones) e = cudaMemcpyAsync(host->dones, sl.dones, N * 8, cudaMemcpyDeviceToHost, p->d2h);
+  if (e == cudaSuccess && host->dones_u8) e = cudaMemcpyAsync(host->dones_u8, sl.dones_u8, N, cudaMemcpyDeviceToHost, p->d2h);
   if (e == cudaSuccess && host->critic_obs) e = cudaMemcpyAsync(host->critic_obs, sl.critic, N * 64, cudaMemcpyDeviceToHost, p->d2h);
+  if (e == cudaSuccess && host->time_out) e = cudaMemcpyAsync(host->time_out, sl.time_out, N, cudaMemcpyDeviceToHost, p->d2h);
   if (e != cudaSuccess) return (int)e;
   cudaEventRecord(sl.d2h_done, p->d2h);
-  sl.host_dones = host->dones; sl.host_time_out = reinterpret_cast<uint8_t*>(host->time_out);
-  sl.widened = !(host->dones || host->time_out);
   sl.busy = true;
   if (ticket_out) *ticket_out = p->issued;
   p->issued += 1;
@@ -150,9 +133,46 @@ extern "C" int gr_host_pipe_wait(GrHostPipe* p, int64_t ticket) {
   if (!p) return GR_ERR_NULL;
   if (ticket < 0 || ticket >= p->issued) return GR_ERR_SIZE;
   if (ticket + p->depth < p->issued) return GR_OK;       // slot already recycled: its copies were waited for then
-  GrHostPipe::Slot& sl = p->slot[ticket % p->depth];
-  const cudaError_t e = cudaEventSynchronize(sl.d2h_done);
-  if (e != cudaSuccess) return (int)e;
-  finish(p, sl);
-  return GR_OK;
+  return (int)cudaEventSynchronize(p->slot[ticket % p->depth].d2h_done);
+}
+
+// What the platform gives the pipe's copies alone: `steps` iterations of the same transfers -- actions host->device on one stream,
+// obs / reward / dones device->host on another -- from pinned buffers, no kernel, no dependencies.  Returns the seconds the loop took
+// (host clock between two device synchronisations).  Several ranks call it concurrently to find the aggregate limit of a node.
+#include <chrono>
+extern "C" int gr_host_copy_probe(int32_t num_envs, int32_t steps, int32_t dones_bytes, double* seconds_out) {
+  if (!seconds_out) return GR_ERR_NULL;
+  if (num_envs <= 0 || steps <= 0 || dones_bytes < 0 || dones_bytes > 8) return GR_ERR_SIZE;
+  const size_t N = (size_t)num_envs, in_b = N * 16, out_b[3] = {N * 64, N * 4, N * (size_t)dones_bytes};
+  void *h_in = nullptr, *d_in = nullptr, *h_out = nullptr, *d_out = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  const size_t out_total = align256(out_b[0]) + align256(out_b[1]) + align256(out_b[2] + 1);
+  cudaError_t e = cudaHostAlloc(&h_in, in_b, cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaHostAlloc(&h_out, out_total, cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaMalloc(&d_in, in_b);
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, out_total);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking);
+  if (e == cudaSuccess) {
+    auto loop = [&](int n) {
+      for (int t = 0; t < n; ++t) {
+        cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, s_in);
+        size_t off = 0;
+        for (int k = 0; k < 3; ++k) {
+          if (out_b[k]) cudaMemcpyAsync(static_cast<char*>(h_out) + off, static_cast<char*>(d_out) + off, out_b[k], cudaMemcpyDeviceToHost, s_out);
+          off += align256(out_b[k]);
+        }
+      }
+      cudaStreamSynchronize(s_in);
+      return cudaStreamSynchronize(s_out);
+    };
+    e = loop(3);
+    const auto t0 = std::chrono::steady_clock::now();
+    if (e == cudaSuccess) e = loop(steps);
+    *seconds_out = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  if (s_in) cudaStreamDestroy(s_in);
+  if (s_out) cudaStreamDestroy(s_out);
+  cudaFree(d_in); cudaFree(d_out); cudaFreeHost(h_in); cudaFreeHost(h_out);
+  return (int)e;
 }

@@ -50,6 +50,7 @@ struct FusedObsSink {
     critic_pk[0] = pack8(c0, c1); critic_pk[1] = pack8(c2, c3);
   }
   __device__ __forceinline__ void aux(int, float v) const { if (aux_ptr) *aux_ptr = v; }
+  __device__ __forceinline__ constexpr bool wants_policy() const { return true; }
   template <bool kNoise, bool kDiff, bool kStats>          // (the state stays in registers over the rollout)
   __device__ __forceinline__ bool state_final(EnvRegs&, float4&, const float4&, const float (&)[GR_NUM_REWARD_TERMS], float, bool, bool) const { return false; }
 };

@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
   io.terminated[i] = so.terminated ? 1 : 0;
   io.time_out[i] = so.time_out ? 1 : 0;
   if (io.dones) io.dones[i] = so.reset ? 1 : 0;
+  if (io.dones_u8) io.dones_u8[i] = so.reset ? 1 : 0;
   if (io.gate_passed) io.gate_passed[i] = so.passed ? 1 : 0;
   if (io.reward_terms) {
 #pragma unroll
@@ -118,6 +119,8 @@ struct RolloutObsSink {
   }
   template <bool kNoise, bool kDiff, bool kStats>
   __device__ __forceinline__ bool state_final(EnvRegs&, float4&, const float4&, const float (&)[GR_NUM_REWARD_TERMS], float, bool, bool) const { return false; }
+  // a step whose observation nobody records skips the whole observation section (and its eight normals)
+  __device__ __forceinline__ bool wants_policy() const { return seq_rows != nullptr || out_rows != nullptr; }
   __device__ __forceinline__ bool wants_critic() const { return critic_rows != nullptr; }
   __device__ __forceinline__ void critic(int i, float4 c0, float4 c1, float4 c2, float4 c3) const { g.rows(critic_rows, i, c0, c1, c2, c3); }
   __device__ __forceinline__ void aux(int i, float v) const { if (aux_ptr) aux_ptr[i] = v; }
@@ -158,9 +161,11 @@ __global__ void __launch_bounds__(256) racing_rollout_fwd_kernel(const GrConfig 
     rt.step = rng.step + (uint32_t)t;
     if (!kPhilox) rt.rnd = rng.rnd + (int64_t)t * N * GR_RND_STRIDE;
     const RandSrc<kPhilox> rs(rt, li, st.env_id_offset + li);
-    float4 n01, n23;
-    rs.normals8(n01, n23);
-    const Draws<kPhilox> draws{rs, nullptr};
+    const bool last = t == T - 1;
+    const bool want_obs = rio.obs_seq != nullptr || last;          // (uniform over the grid)
+    float4 n01 = make_float4(0.f, 0.f, 0.f, 0.f), n23 = n01;
+    if (want_obs) rs.normals8(n01, n23);
+    const Draws<kPhilox> draws{rs, nullptr, want_obs};
     GrStepIO io = {};
     io.log_accum = rio.log_accum;
     if (kDiff) {
@@ -169,7 +174,6 @@ __global__ void __launch_bounds__(256) racing_rollout_fwd_kernel(const GrConfig 
       io.loss = rio.loss ? rio.loss + (int64_t)t * N : nullptr;
       io.loss_terms = rio.loss_terms ? rio.loss_terms + (int64_t)t * N * 3 : nullptr;
     }
-    const bool last = t == T - 1;
     RolloutObsSink sink{gsink, nullptr, nullptr, nullptr, nullptr};
     if (rio.obs_seq) sink.seq_rows = reinterpret_cast<float4*>(rio.obs_seq) + (int64_t)t * N * 4;
     if (last) {

@@ -277,6 +277,7 @@ struct GlobalObsSink {
 #endif
   }
   __device__ __forceinline__ void policy(int i, float4 o0, float4 o1, float4 o2, float4 o3) const { rows(reinterpret_cast<float4*>(io.obs), i, o0, o1, o2, o3); }
+  __device__ __forceinline__ constexpr bool wants_policy() const { return true; }
   __device__ __forceinline__ bool wants_critic() const { return io.critic_obs != nullptr; }
   __device__ __forceinline__ void critic(int i, float4 c0, float4 c1, float4 c2, float4 c3) const { rows(reinterpret_cast<float4*>(io.critic_obs), i, c0, c1, c2, c3); }
   __device__ __forceinline__ void aux(int i, float v) const { if (io.aux_obs) io.aux_obs[i] = v; }
@@ -467,7 +468,7 @@ __device__ __forceinline__ bool racing_step_body(const GrConfig& cfg, const Trac
       }
     }
     if (kStats) { eps0 = make_float4(0.f, 0.f, 0.f, 0.f); lsum = eps0; }       // (e.es4 / e.es5: reset_env)
-    origin = reset_env<kNoise, kPhilox>(cfg, tr, e, draws, n23.z);
+    origin = reset_env<kNoise, kPhilox>(cfg, tr, e, draws, draws.thr_normal(n23.z));
     level = (int)pk_level(e.pk);
     gate_id = (int)pk_gate(e.pk);
     gate_rel = tr.gate(type, level, gate_id);
@@ -525,7 +526,7 @@ __device__ __forceinline__ bool racing_step_body(const GrConfig& cfg, const Trac
   out.stored = sink.template state_final<kNoise, kDiff, kStats>(e, eps0, lsum, terms, dt, reset, noise_dirty);
 
   // ---- 11. observations on the post-reset state (QD/racing_ctbr_env.py:139-174, QD/mdp/observation.py:22-104) ----
-  {
+  if (sink.wants_policy()) {
     V3 vb = vb1, d0 = cg0;                       // common case: same state and gate as the reward section
     RotQ Rq = R1;
     if (reset || passed) {                       // rare: recompute the views on the new state / gate

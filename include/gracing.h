@@ -163,6 +163,7 @@ typedef struct GrStepIO {
                                quaternion 4 | world linear velocity 3 | world angular velocity 3 of the step BEFORE any reset
                                (L/envs/manager_based_diff_rl_env.py:205-212)                                  optional */
   float* acc;               /* [N,3] extras["acc"]: world linear acceleration of the step (droneDynamics.py:126) optional */
+  uint8_t* dones_u8;        /* [N] terminated | time_out as one byte (RolloutStorage keeps dones as bytes)   optional */
 } GrStepIO;
 
 #define GR_LOG_NUM_RESET 0          /* number of envs reset in this step                          */
@@ -219,6 +220,7 @@ typedef struct GrBwdIO {
   float* adjoint;
   int64_t adj_stride;
   float* grad_action;
+  int32_t lanes;            /* racing sweep: lanes per env, 0 / 2 = two (translational + rotational half, default), 1 = one */
 } GrBwdIO;
 int gr_step_bwd(const GrConfig* cfg, const GrState* st, const GrBwdIO* io, void* stream);
 
@@ -427,9 +429,10 @@ typedef struct GrHostStep {
   const float* action;      /* host [N,4]                                    required */
   float* obs;               /* host [N,16]                                   required */
   float* reward;            /* host [N]                                      required */
-  int64_t* dones;           /* host [N]                                      optional (crosses PCIe as two uint8 masks, widened in wait) */
+  int64_t* dones;           /* host [N]                                      optional */
   float* critic_obs;        /* host [N,16]                                   optional */
   uint8_t* time_out;        /* host [N]                                      optional */
+  uint8_t* dones_u8;        /* host [N] terminated | time_out as one byte    optional (1 B per env over PCIe instead of 8) */
 } GrHostStep;
 /* `action` must stay untouched until gr_host_pipe_wait(ticket) of that step returned; one calling thread per pipe;
  * gr_host_pipe_destroy synchronises the three streams before it frees the staging buffers. */
@@ -438,6 +441,9 @@ int gr_host_pipe_destroy(GrHostPipe* pipe);
 int gr_host_pipe_step(GrHostPipe* pipe, const GrConfig* cfg, const GrTrack* track, const GrState* st, const GrRandom* rng,
                       const GrHostStep* host, float* log_accum /* device, optional */, int64_t* ticket_out);
 int gr_host_pipe_wait(GrHostPipe* pipe, int64_t ticket);
+/* the copies of one host step alone (actions in; obs, reward and `dones_bytes` bytes of dones per env out), `steps` times, two streams,
+ * pinned buffers, no kernel: seconds_out = host time of the loop.  The platform's ceiling for gr_host_pipe_step (bench.py, e2e). */
+int gr_host_copy_probe(int32_t num_envs, int32_t steps, int32_t dones_bytes, double* seconds_out);
 
 /* ---- reach-target tasks: the other command modes and tasks sharing the dynamics ----------------
  * QD/reach_target_lv_env.py + QD/reach_target_ctbr_env.py: the same ManagerBasedDiffRLEnv.step ordering as gr_step_fwd
