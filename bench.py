@@ -755,26 +755,34 @@ def bench_extras(dev, cfg, table):
         "bytes_per_env_step": b_w, "achieved_GBps": b_w * N * H / (ms_w * 1e-3) / 1e9, "frac_of_hbm_peak": b_w * N * H / (ms_w * 1e-3) / 1e9 / peak,
         "what": "gr_rollout_fwd (32 steps, one launch, state in registers) + gr_step_bwd; same rotation of 4 env sets + tapes"}
     del graph1
-    e0.record()
-    for _ in range(reps):
+
+    def graph_ms(fn, n_rep=10):
+        """device time of fn(e) per env set, replayed from one CUDA graph over the R rotating sets"""
         for e in envs:
-            e._bptt.backward_window()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms_b = e0.elapsed_time(e1) / (reps * R)
+            fn(e)
+        torch.cuda.synchronize(dev)
+        gx = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gx):
+            for e in envs:
+                fn(e)
+        gx.replay()
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(n_rep):
+            gx.replay()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / (n_rep * R)
+
+    def fwd_only(e):
+        e.detach()
+        e.rollout(acts)
+
+    ms_f = graph_ms(fwd_only)
+    ms_b = graph_ms(lambda e: e._bptt.backward_window())
+    out["bptt_fwd_bwd_c3_one_launch_window"]["ms_forward_window_graph"] = ms_f
     out["bptt_bwd_sweep"] = {"ms": ms_b, "achieved_GBps": N * H * 128 / (ms_b * 1e-3) / 1e9, "frac_of_hbm_peak": N * H * 128 / (ms_b * 1e-3) / 1e9 / peak,
-                             "what": "racing_step_bwd2_kernel: two lanes per env (translational / rotational half)"}
-    for e in envs:
-        e._bptt.lanes = 1
-    e0.record()
-    for _ in range(reps):
-        for e in envs:
-            e._bptt.backward_window()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    out["bptt_bwd_sweep"]["ms_one_lane_per_env"] = e0.elapsed_time(e1) / (reps * R)
-    for e in envs:
-        e._bptt.lanes = 0
+                             "what": "gr_step_bwd over the 32-step tape (+ the memset of the carried adjoints), graph-replayed over the 4 rotating env sets"}
     del envs, graph
     torch.cuda.empty_cache()
 

@@ -57,7 +57,7 @@ class GrStepIO(C.Structure):
 
 class GrBwdIO(C.Structure):
     _fields_ = [("tape", c_p), ("tape_stride", C.c_int64), ("t_begin", c_i), ("t_end", c_i), ("grad_loss", c_p),
-                ("grad_scale", c_f), ("adjoint", c_p), ("adj_stride", C.c_int64), ("grad_action", c_p), ("lanes", c_i)]
+                ("grad_scale", c_f), ("adjoint", c_p), ("adj_stride", C.c_int64), ("grad_action", c_p)]
 
 
 class GrRolloutIO(C.Structure):
@@ -130,6 +130,7 @@ GR_LAUNCH_PDL = 1
 GR_LAUNCH_PREFETCH = 2
 GR_LAUNCH_PREFETCH_L2 = 4
 GR_LAUNCH_EARLY_STORE = 8
+GR_LAUNCH_COOP_RESET = 16
 GR_LOG_SLOTS = 16
 GR_LOG_NUM_RESET, GR_LOG_SUM_GATES, GR_LOG_SUM_EPSUM, GR_LOG_NUM_TIMEOUT, GR_LOG_NUM_TERMINATED = 0, 1, 2, 8, 9
 GR_LOG_SUM_ACTION_RATE, GR_LOG_SUM_LIN_SPD, GR_LOG_SUM_ANG_SPD, GR_LOG_SUM_LOSS = 10, 11, 12, 13

@@ -112,7 +112,6 @@ class BpttWindow:
         io.adjoint = self.adjoint.data_ptr()
         io.adj_stride = env._stride
         io.grad_action = self.grad_action.data_ptr()
-        io.lanes = int(getattr(self, "lanes", 0))          # racing sweep: 0 / 2 = two lanes per env (default), 1 = one
         fn = getattr(env, "_bwd_fn", None) or env._lib.gr_step_bwd
         B.check(fn(C.byref(env._gcfg), C.byref(env._state), C.byref(io), env._stream()), "gr_step_bwd")
 

@@ -67,6 +67,7 @@ struct RandSrc<false> {
   __device__ __forceinline__ float4 get4(int call) const { return __ldg(row + call); }
   __device__ __forceinline__ void normals8(float4& a, float4& b) const { a = __ldg(row); b = __ldg(row + 1); }
   __device__ __forceinline__ float normal6() const { return __ldg(row + 1).z; }        // slot 6 alone
+  __device__ __forceinline__ uint32_t ph_env() const { return 0u; }
 };
 
 template <>
@@ -84,6 +85,7 @@ struct RandSrc<true> {
     b = make_float4(p2.x, p2.y, p3.x, p3.y);
   }
   __device__ __forceinline__ float normal6() const { return box_muller16(ph(0u).w).x; }        // slot 6 alone: the same bits normals8 gives
+  __device__ __forceinline__ uint32_t ph_env() const { return ph.c0; }
 };
 
 // Programmatic dependent launch (sm_90+): wait = block until the previous kernel in the stream has completed and its
@@ -109,10 +111,12 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// Draws of the rare paths (reset: calls 2..8, gate pass: calls 10..11).  In Philox mode the step kernel generates
-// them speculatively for every env while its state loads are in flight (the warp would idle otherwise) and parks
-// them in shared memory, so the divergent reset / pass tails -- the stragglers that set the kernel's makespan -- only
-// read them back.  Dense mode and the standalone reset kernel read / generate directly.
+// Draws of the rare paths (reset: calls 2..8, gate pass: calls 10..11).  A resetting env needs seven Philox calls (~110 instructions
+// each); left to the env's own lane they run inside the divergent reset tail with one or two lanes active -- ~770 issue slots of the warp
+// for every warp that holds a resetting env (77 % of the warps at a 4.5 % reset rate).  With `spec` set (GR_LAUNCH_COOP_RESET) the WARP
+// generates them instead: for each resetting lane, lanes 0..6 compute one call each and park the result in shared memory
+// (stage_reset_draws), the reset tail reads them back.  Same counters, same bits.  Dense mode and the standalone reset kernel read /
+// generate directly.
 __device__ __forceinline__ int spec_slot(int call) { return call < 10 ? call - 2 : call - 3; }     // 2..8 -> 0..6, 10..11 -> 7..8
 constexpr int kSpecCalls = 9;
 
@@ -122,12 +126,35 @@ struct Draws {
   const float4* spec;       // shared: [kSpecCalls][blockDim.x] or nullptr
   bool have_normals = true; // false: the caller skipped normals8() (a window step that records no observation); slot 6 is then drawn on demand
   __device__ __forceinline__ float4 get4(int call) const {
-    if (kPhilox && spec) return spec[spec_slot(call) * blockDim.x + threadIdx.x];
+    if (kPhilox && spec && call < 10) return spec[spec_slot(call) * blockDim.x + threadIdx.x];      // reset draws staged by stage_reset_draws()
     return rs.get4(call);
   }
   // slot 6 (thr_est_error normal, consumed by a reset only)
   __device__ __forceinline__ float thr_normal(float from_normals8) const { return have_normals ? from_normals8 : rs.normal6(); }
 };
+
+// Warp-cooperative generation of the reset draws (Philox mode): call with all 32 lanes converged; `reset` = this lane's env resets in
+// this step, `env_id` = its global id.  spec layout: [kSpecCalls][blockDim.x] float4, column = the thread the draws belong to.
+__device__ __forceinline__ void stage_reset_draws(const RandSrc<true>& rs, float4* spec, bool reset, uint32_t env_id, bool with_noise) {
+#ifndef GR_CPU_EMUL
+  unsigned m = __ballot_sync(0xffffffffu, reset);
+  if (m == 0u) return;
+  const int lane = threadIdx.x & 31;
+  const int calls = with_noise ? 7 : 5;                        // calls 2..6: pose, velocity, drag, level; 7..8: gate noise
+  while (m) {
+    const int r = __ffs(m) - 1;
+    m &= m - 1;
+    Philox ph = rs.ph;
+    ph.c0 = __shfl_sync(0xffffffffu, env_id, r);
+    if (lane < calls) {
+      const uint4 x = ph((uint32_t)(2 + lane));
+      spec[lane * blockDim.x + (threadIdx.x - lane + r)] = make_float4(u01(x.x), u01(x.y), u01(x.z), u01(x.w));
+    }
+  }
+  __syncwarp();
+#endif
+}
+__device__ __forceinline__ void stage_reset_draws(const RandSrc<false>&, float4*, bool, uint32_t, bool) {}
 
 // Gate table slice staged in shared memory: rows of types [type_lo, type_lo + ntypes).
 struct TrackSmem {

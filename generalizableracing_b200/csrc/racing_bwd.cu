@@ -166,7 +166,10 @@ __device__ __forceinline__ BwdConst bwd_constants(const GrConfig& cfg, const flo
   return k;
 }
 
-// ---- one lane per env (the g++ emulation runs this one; on the GPU it serves env counts too small to matter) -----------------
+// ---- one lane per env.  Measured dead ends at C3 (16,384 envs x 32 steps, 22.7 us per sweep under graph replay): giving the two
+// halves to two lanes of ONE warp serialises them (47 us); giving them to two partner WARPS (translational warp one step ahead, hand-over
+// through shared memory and a 64-thread named barrier per step) takes 22.5 us -- the rotational half alone is as long a dependent chain
+// as the whole step, the translational work was already filling its latency gaps (profiles/r2_bptt_sweep_variants.md).
 __global__ void __launch_bounds__(kBwdBlock) racing_step_bwd_kernel(const GrConfig cfg, const GrState st, const GrBwdIO io) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= st.num_envs) return;
@@ -235,101 +238,6 @@ __global__ void __launch_bounds__(kBwdBlock) racing_step_bwd_kernel(const GrConf
   A[4 * AS + i] = pack(aR.lWb, aR.lTau.z);
 }
 
-#ifndef GR_CPU_EMUL
-// ---- two lanes per env: lane 0 of a pair runs the translational half, lane 1 the rotational half.  The sweep is a serial chain over t with
-// only N/32 warps (3.5 per SM at 16,384 envs: one warp per scheduler, every instruction waits for the one before); giving each env two
-// lanes doubles the warps and halves the chain.  The tape ring in shared memory is per ENV: the two lanes split the copies (planes 0-3 /
-// 4-6), a __syncwarp after the wait makes each lane's copies visible to its partner, and the halves meet through nine shuffles per step.
-constexpr int kBwd2Block = 128;                                       // 64 envs per block
-__global__ void __launch_bounds__(kBwd2Block) racing_step_bwd2_kernel(const GrConfig cfg, const GrState st, const GrBwdIO io) {
-  const int N = st.num_envs;
-  const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 1;
-  const bool rot = (threadIdx.x & 1) != 0;
-  const bool active = pair < N;
-  const int i = active ? pair : N - 1;                                // a pair past the last env shadows it (full-warp shuffles) and stores nothing
-  const float4* __restrict__ P = reinterpret_cast<const float4*>(st.planes);
-  const BwdConst k = bwd_constants(cfg, P, i);
-  float4* __restrict__ A = reinterpret_cast<float4*>(io.adjoint);
-  const int64_t AS = io.adj_stride;
-  AdjT aT; AdjR aR;
-  {
-    const float4 a2 = A[2 * AS + i], a3 = A[3 * AS + i], a4 = A[4 * AS + i];
-    if (rot) { aR = AdjR{quat(A[1 * AS + i]), xyz(a4), v3(a2.w, a3.w, a4.w)}; }
-    else { const float4 a0 = A[0 * AS + i]; aT = AdjT{xyz(a0), xyz(a2), xyz(a3), a0.w}; }
-  }
-  const float4* __restrict__ T = reinterpret_cast<const float4*>(io.tape);
-  const int64_t TS = io.tape_stride;
-  GR_DYN_SMEM(float4, ring);
-  const int epb = blockDim.x >> 1;                                    // envs per block
-  float4* env_ring = ring + (threadIdx.x >> 1);                       // slot(stage, plane) = env_ring[(stage*7 + plane) * epb]
-  const int p_lo = rot ? 4 : 0, p_hi = rot ? GR_TAPE_PLANES : 4;      // the planes this lane copies
-  const int n_steps = io.t_end - io.t_begin;
-#pragma unroll 1
-  for (int s = 0; s < kBwdStages; ++s) {
-    const int t = io.t_end - 1 - s;
-    if (s < n_steps) {
-      for (int p = p_lo; p < p_hi; ++p) cp_async16(env_ring + (s * GR_TAPE_PLANES + p) * epb, T + (int64_t)t * GR_TAPE_PLANES * TS + tidx(p, i));
-    }
-    cp_async_commit();
-  }
-  int stage = 0;
-  for (int t = io.t_end - 1; t >= io.t_begin; --t) {
-    cp_async_wait<kBwdStages - 1>();
-    __syncwarp();                                                     // the partner lane's copies of step t are visible too
-    const float4* c = env_ring + (stage * GR_TAPE_PLANES) * epb;
-    const float4 c0 = c[0], c1 = c[1 * epb];
-    const Q4 q = quat(c0);
-    const V3 om_b = xyz(c1);
-    const float4 c5 = c[5 * epb];
-    const bool cut = __float_as_uint(c5.w) != 0u;
-    const Q1 r = recompute_q1(q, om_b, k.dt);
-    QAdj qa1{0.f, v3(0.f, 0.f, 0.f)}, qa2 = qa1; float fb = 0.f;
-    float4 c2, c3, c4;
-    if (!rot) {
-      c2 = c[2 * epb]; c3 = c[3 * epb]; c4 = c[4 * epb];
-      const float4 c6 = c[6 * epb];
-      const float g = io.grad_loss ? __ldg(io.grad_loss + (int64_t)t * N + i) : io.grad_scale;
-      bwd_translational(k, aT, q, r.q1, xyz(c2), xyz(c3), xyz(c4), xyz(c6), g, cut, qa1, qa2, fb);
-    } else {
-      c2.w = c[2 * epb].w; c3.w = c[3 * epb].w; c4.w = c[4 * epb].w;   // the torque gains ride in the .w of planes 2..4
-    }
-    __syncwarp();                                                     // both lanes are done reading this stage before it is refilled
-    {
-      const int tn = t - kBwdStages;
-      if (tn >= io.t_begin) {
-        for (int p = p_lo; p < p_hi; ++p) cp_async16(env_ring + (stage * GR_TAPE_PLANES + p) * epb, T + (int64_t)tn * GR_TAPE_PLANES * TS + tidx(p, i));
-      }
-      cp_async_commit();
-    }
-    stage = stage + 1 == kBwdStages ? 0 : stage + 1;
-    // T -> R: the quaternion adjoints of the two rotations of translational quantities, and d loss / d thrust
-    qa1.w = __shfl_xor_sync(0xffffffffu, qa1.w, 1); qa1.u.x = __shfl_xor_sync(0xffffffffu, qa1.u.x, 1);
-    qa1.u.y = __shfl_xor_sync(0xffffffffu, qa1.u.y, 1); qa1.u.z = __shfl_xor_sync(0xffffffffu, qa1.u.z, 1);
-    qa2.w = __shfl_xor_sync(0xffffffffu, qa2.w, 1); qa2.u.x = __shfl_xor_sync(0xffffffffu, qa2.u.x, 1);
-    qa2.u.y = __shfl_xor_sync(0xffffffffu, qa2.u.y, 1); qa2.u.z = __shfl_xor_sync(0xffffffffu, qa2.u.z, 1);
-    fb = __shfl_xor_sync(0xffffffffu, fb, 1);
-    if (rot) {
-      V3 taub;
-      bwd_rotational(k, aR, q, om_b, r.q1, r.qn, xyz(c5), cut, qa1, qa2, taub);
-      if (t >= 1 && active) {
-        reinterpret_cast<float4*>(io.grad_action)[(int64_t)(t - 1) * N + i] = make_float4(c1.w * fb, c2.w * taub.x, c3.w * taub.y, c4.w * taub.z);
-      }
-    }
-  }
-  // the carried adjoints: planes 2 and 3 mix a translational vector with a torque-filter word
-  const float tx = __shfl_xor_sync(0xffffffffu, rot ? aR.lTau.x : 0.f, 1), ty = __shfl_xor_sync(0xffffffffu, rot ? aR.lTau.y : 0.f, 1);
-  if (!active) return;
-  if (rot) {
-    A[1 * AS + i] = pack(aR.lQ);
-    A[4 * AS + i] = pack(aR.lWb, aR.lTau.z);
-  } else {
-    A[0 * AS + i] = pack(aT.lP, aT.lF);
-    A[2 * AS + i] = pack(aT.lV, tx);
-    A[3 * AS + i] = pack(aT.lVb, ty);
-  }
-}
-#endif
-
 }  // namespace gr
 
 #ifndef GR_CPU_EMUL
@@ -342,15 +250,8 @@ extern "C" int gr_step_bwd(const GrConfig* cfg, const GrState* st, const GrBwdIO
   auto mis = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; };
   if (mis(st->planes) || mis(io->tape) || mis(io->adjoint) || mis(io->grad_action)) return GR_ERR_ALIGN;
   const size_t smem = (size_t)kBwdStages * GR_TAPE_PLANES * kBwdBlock * sizeof(float4);      // 43 KB ring per block (64 envs)
-  if (io->lanes != 0 && io->lanes != 1 && io->lanes != 2) return GR_ERR_SIZE;
-  if (io->lanes == 1) {
-    const int grid = (st->num_envs + kBwdBlock - 1) / kBwdBlock;
-    racing_step_bwd_kernel<<<grid, kBwdBlock, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*cfg, *st, *io);
-  } else {
-    const int epb = kBwd2Block / 2;
-    const int grid = (st->num_envs + epb - 1) / epb;
-    racing_step_bwd2_kernel<<<grid, kBwd2Block, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*cfg, *st, *io);
-  }
+  const int grid = (st->num_envs + kBwdBlock - 1) / kBwdBlock;
+  racing_step_bwd_kernel<<<grid, kBwdBlock, smem, reinterpret_cast<cudaStream_t>(stream)>>>(*cfg, *st, *io);
   return (int)cudaGetLastError();
 }
 #endif  // GR_CPU_EMUL

@@ -70,13 +70,16 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
   }
   // (measured: generating the rare-path draws speculatively for every env while the loads are in flight costs more
   //  than it saves -- +1.2 us median compute, stragglers unchanged -- so the reset / pass tails draw on demand)
-  const Draws<kPhilox> draws{rs, nullptr};
+  __shared__ float4 obs_stage[8 * 128];                 // 2 KB per warp, up to 8 warps per block (GlobalObsSink)
+  // stage_reset_draws ([7 calls][<= 64 threads], GR_LAUNCH_COOP_RESET with blocks of <= 64 threads) borrows the part of the staging buffer
+  // that warps 2..7 would use: static shared memory stays at 16 KB (more costs a resident block per SM, i.e. the single wave)
+  const bool coop = kPhilox && (st.launch_flags & GR_LAUNCH_COOP_RESET) != 0 && blockDim.x <= 64;
+  const Draws<kPhilox> draws{rs, coop ? obs_stage + 2 * 128 : nullptr};
   pdl_launch_dependents();
   // a warp that is entirely past the last env leaves; in the (single) ragged warp the inactive lanes keep shadowing
   // the last env so the warp collectives below stay full-width, and skip every store
   const unsigned live = __ballot_sync(0xffffffffu, active);
   if (live == 0u) return;
-  __shared__ float4 obs_stage[8 * 128];                 // 2 KB per warp, up to 8 warps per block (GlobalObsSink)
 
   StepOut so;
   GlobalObsSink sink{io, live, obs_stage + (threadIdx.x >> 5) * 128};
@@ -150,6 +153,8 @@ __global__ void __launch_bounds__(256) racing_rollout_fwd_kernel(const GrConfig 
   const GlobalObsSink gsink{no_io, live, obs_stage + (threadIdx.x >> 5) * 128};
   bool any_reset = false, any_noise_dirty = false, last_noise_dirty = false;
   const int64_t tape_step = (int64_t)(rio.tape_stride / kTile) * GR_TAPE_PLANES * kTile * 4;       // floats per tape step
+  const bool coop = kPhilox && (st.launch_flags & GR_LAUNCH_COOP_RESET) != 0 && blockDim.x <= 64;
+  float4* const coop_draws = obs_stage + 2 * 128;       // (the staging rows of warps 2..7: unused with blocks of <= 64 threads)
 
   float4 a_next = __ldcs(reinterpret_cast<const float4*>(rio.actions) + li);
 #pragma unroll 1
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(256) racing_rollout_fwd_kernel(const GrConfig 
     const bool want_obs = rio.obs_seq != nullptr || last;          // (uniform over the grid)
     float4 n01 = make_float4(0.f, 0.f, 0.f, 0.f), n23 = n01;
     if (want_obs) rs.normals8(n01, n23);
-    const Draws<kPhilox> draws{rs, nullptr, want_obs};
+    const Draws<kPhilox> draws{rs, coop ? coop_draws : nullptr, want_obs};
     GrStepIO io = {};
     io.log_accum = rio.log_accum;
     if (kDiff) {

@@ -442,6 +442,7 @@ __device__ __forceinline__ bool racing_step_body(const GrConfig& cfg, const Trac
 
   // ---- 7. reset (L/envs/manager_based_diff_rl_env.py:232-247,362-410) ----
   const bool reset = terminated || time_out;
+  if (kPhilox && draws.spec) stage_reset_draws(draws.rs, const_cast<float4*>(draws.spec), reset && active, draws.rs.ph_env(), kNoise);
   bool noise_dirty = false;
   bool passed = pass_pre;                                 // 8. on an env that did not reset this is the same test
   if (reset) {

@@ -166,6 +166,8 @@ class RacingVecEnv:
         # read-mostly planes before the grid dependency: "1" = into registers with the stale-flag protocol, "l2" = into L2 only, "0" = off
         pf = {"0": 0, "1": B.GR_LAUNCH_PREFETCH, "l2": B.GR_LAUNCH_PREFETCH_L2}[os.environ.get("GRACING_PREFETCH", "1").lower()]
         flags = (B.GR_LAUNCH_PDL | pf) if (pdl and self.device.type == "cuda") else 0
+        if os.environ.get("GRACING_COOP_RESET", "0") == "1" and self.device.type == "cuda":
+            flags |= B.GR_LAUNCH_COOP_RESET
         if os.environ.get("GRACING_EARLY_STORE", "1") == "1":       # measured on the B200: -0.06 .. -0.15 us per 65,536-env step
             flags |= B.GR_LAUNCH_EARLY_STORE
         self._launch_flags = flags

@@ -125,6 +125,8 @@ typedef struct GrState {
                                  only pulled into L2 (prefetch.global.L2, no registers, no staleness protocol); every plane is then
                                  loaded after the wait, the read-mostly ones as L2 hits.  Safe after host edits of any plane. */
 
+#define GR_LAUNCH_COOP_RESET 16 /* gr_step_fwd / gr_rollout_fwd, in-kernel Philox: the seven Philox calls of a resetting env are generated by seven lanes
+                                 of its warp instead of inside the env's own divergent reset tail (same counters, same bits) */
 #define GR_LAUNCH_EARLY_STORE 8 /* gr_step_fwd: write the state planes back before the observation section instead of at the end of the kernel */
 
 /* Random source: dense tensor (parity mode) or in-kernel Philox4x32-10 (throughput mode). */
@@ -220,7 +222,6 @@ typedef struct GrBwdIO {
   float* adjoint;
   int64_t adj_stride;
   float* grad_action;
-  int32_t lanes;            /* racing sweep: lanes per env, 0 / 2 = two (translational + rotational half, default), 1 = one */
 } GrBwdIO;
 int gr_step_bwd(const GrConfig* cfg, const GrState* st, const GrBwdIO* io, void* stream);
 

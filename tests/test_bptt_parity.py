@@ -98,36 +98,3 @@ def test_second_window_after_detach(backend):
         for _ in range(9):
             env.step(torch.zeros(64, 4, device=dev), PC.draw_rnd(64, g).to(dev))
 
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("N", [64, 130, 4096])
-def test_two_lane_sweep_equals_one_lane_sweep(cuda_lib, N):
-    """racing_step_bwd2_kernel (translational / rotational half of an env on two lanes, nine shuffles per step) against the one-lane
-    kernel that the emulation runs: the same device functions in the same order, so the gradients agree to the last bit or two (the two
-    kernels are compiled separately: fused-multiply-add contraction may differ) -- and both match autograd through the oracle."""
-    H = 32
-    cfg, table, orc, env, g = PC.make_pair(("cuda:0", None), stage=1, N=N, seed=40 + N, diff=True, horizon=H)
-    dev = env.device
-    r0 = PC.draw_rnd(N, g)
-    env.reset(r0.to(dev))
-    env.episode_length_buf = torch.randint(0, cfg.max_episode_length, (N,), generator=g)
-    env.detach()
-    env._bptt.autograd = False
-    acts = (torch.randn(H, N, 4, generator=g) * 0.5).to(dev)
-    rnd = torch.stack([PC.draw_rnd(N, g) for _ in range(H)]).to(dev)
-    env.rollout(acts, rnd)
-    w = torch.rand(H, N, generator=g).to(dev)
-    out = {}
-    for lanes in (1, 2):
-        env._bptt.lanes = lanes
-        out[lanes] = (env._bptt.backward_window(grad_losses=w).clone(), env._bptt.backward_window().clone(), env._bptt.adjoint.clone())
-    for a, b in zip(out[1], out[2]):
-        assert float(a.abs().max()) > 0 or a is out[1][2]
-        assert float((a - b).abs().max()) <= 2e-6 * max(float(a.abs().max()), 1e-30)
-    # chained launches (one step per launch, adjoints carried through HBM between them) == one sweep, on the two-lane kernel
-    env._bptt.lanes = 2
-    env._bptt.adjoint.zero_()
-    env._bptt.grad_loss[:H].copy_(w)
-    for t in range(H - 1, -1, -1):
-        env._bptt._launch(t, t + 1, env._bptt.grad_loss, 0.0)
-    assert float((env._bptt.grad_action[:H] - out[2][0]).abs().max()) <= 2e-6 * float(out[2][0].abs().max())
