@@ -61,6 +61,11 @@ class BpttWindow:
         self.loss_terms = torch.zeros(capacity, N, self._terms, device=dev)
         self.grad_loss = torch.zeros(capacity, N, device=dev)
         self.grad_action = torch.zeros(capacity, N, L.NUM_ACTIONS, device=dev)
+        # reward / dones of every step of the window, written by the step kernel itself: a differentiable-physics loop keeps what a
+        # step returns for the whole window (naive_train.py:170-172), so each step gets its own row instead of a copy of a ping-pong buffer
+        self.reward = torch.zeros(capacity, N, device=dev)
+        self.dones = torch.zeros(capacity, N, dtype=torch.int64, device=dev)
+        self._p_reward, self._p_dones = self.reward.data_ptr(), self.dones.data_ptr()
         self.capacity = capacity
         self._p_loss, self._p_terms, self._p_tape = self.loss.data_ptr(), self.loss_terms.data_ptr(), self.tape.data_ptr()
         self._tape_step_bytes = self.tape[0].numel() * 4
@@ -82,6 +87,13 @@ class BpttWindow:
         io.loss_terms = self._p_terms + t * n * 4 * self._terms
         io.tape = self._p_tape + t * self._tape_step_bytes
         io.tape_stride = self.env._stride
+
+    def bind_outputs(self, io):
+        """Point the step's reward / dones at this step's rows of the window (call after bind_step, before the launch)."""
+        t, n = self.t, self.env.num_envs
+        io.reward = self._p_reward + t * n * 4
+        io.dones = self._p_dones + t * n * 8
+        return self.reward[t], self.dones[t]
 
     def after_step(self, actions: torch.Tensor, extras: dict):
         t = self.t

@@ -113,6 +113,9 @@ __global__ void __launch_bounds__(256) racing_step_fwd_kernel(const GrConfig cfg
 // T steps in one launch for actions known in advance (gr_rollout_fwd): the same body, the env state in registers over
 // the window.  One thread per env; per step it reads its action (16 B) and writes what the caller asked to record.
 // =============================================================================================
+// kObs: does this step record / hand out an observation?  A COMPILE-TIME property of the loop section the step belongs to (measured: as a
+// run-time test inside the body the observation section became a scheduling barrier -- 4.06 -> 4.35 us per step at 65,536 envs).
+template <bool kObs>
 struct RolloutObsSink {
   GlobalObsSink g;                                     // rows(): the coalesced warp store through shared memory
   float4* seq_rows; float4* out_rows; float4* critic_rows; float* aux_ptr;        // destinations of THIS step (nullptr: skip)
@@ -123,16 +126,70 @@ struct RolloutObsSink {
   template <bool kNoise, bool kDiff, bool kStats>
   __device__ __forceinline__ bool state_final(EnvRegs&, float4&, const float4&, const float (&)[GR_NUM_REWARD_TERMS], float, bool, bool) const { return false; }
   // a step whose observation nobody records skips the whole observation section (and its eight normals)
-  __device__ __forceinline__ bool wants_policy() const { return seq_rows != nullptr || out_rows != nullptr; }
+  __device__ __forceinline__ constexpr bool wants_policy() const { return kObs; }
   __device__ __forceinline__ bool wants_critic() const { return critic_rows != nullptr; }
   __device__ __forceinline__ void critic(int i, float4 c0, float4 c1, float4 c2, float4 c3) const { g.rows(critic_rows, i, c0, c1, c2, c3); }
   __device__ __forceinline__ void aux(int i, float v) const { if (aux_ptr) aux_ptr[i] = v; }
 };
 
+// loop-carried bookkeeping of a window (what T single steps would leave behind in the planes)
+struct RolloutCarry { bool any_reset = false, any_noise_dirty = false, last_noise_dirty = false; };
+
+// one step of the window: action a_t is in hand, the next one is fetched one step ahead
+template <bool kNoise, bool kDiff, bool kPhilox, bool kStats, bool kObs>
+__device__ __forceinline__ void rollout_one_step(const GrConfig& cfg, const TrackSmem& tr, const GrState& st, const GrRandom& rng, const GrRolloutIO& rio,
+                                                 const GlobalObsSink& gsink, float4* coop_draws, const int t, const int i, const int li,
+                                                 const bool active, EnvRegs& e, float4& eps0, float4& lsum, float4& a_next, RolloutCarry& c) {
+  const int N = st.num_envs, T = rio.T;
+  const int64_t tn = (int64_t)t * N + i;
+  const float4 a_t = a_next;
+  if (t + 1 < T) a_next = __ldcs(reinterpret_cast<const float4*>(rio.actions) + (int64_t)(t + 1) * N + li);      // one step ahead
+  GrRandom rt = rng;
+  rt.step = rng.step + (uint32_t)t;
+  if (!kPhilox) rt.rnd = rng.rnd + (int64_t)t * N * GR_RND_STRIDE;
+  const RandSrc<kPhilox> rs(rt, li, st.env_id_offset + li);
+  const bool last = t == T - 1;
+  float4 n01 = make_float4(0.f, 0.f, 0.f, 0.f), n23 = n01;
+  if (kObs) rs.normals8(n01, n23);
+  const Draws<kPhilox> draws{rs, coop_draws, kObs};
+  GrStepIO io = {};
+  io.log_accum = rio.log_accum;
+  if (kDiff) {
+    const int64_t tape_step = (int64_t)(rio.tape_stride / kTile) * GR_TAPE_PLANES * kTile * 4;       // floats per tape step
+    io.tape = rio.tape ? rio.tape + (int64_t)t * tape_step : nullptr;
+    io.tape_stride = rio.tape_stride;
+    io.loss = rio.loss ? rio.loss + (int64_t)t * N : nullptr;
+    io.loss_terms = rio.loss_terms ? rio.loss_terms + (int64_t)t * N * 3 : nullptr;
+  }
+  RolloutObsSink<kObs> sink{gsink, nullptr, nullptr, nullptr, nullptr};
+  if (kObs) {
+    if (rio.obs_seq) sink.seq_rows = reinterpret_cast<float4*>(rio.obs_seq) + (int64_t)t * N * 4;
+    if (last) {
+      sink.out_rows = reinterpret_cast<float4*>(rio.obs_out);
+      sink.critic_rows = reinterpret_cast<float4*>(rio.critic_obs_out);
+      sink.aux_ptr = rio.aux_out;
+    }
+  }
+  StepOut so;
+  const bool alive = racing_step_body<kNoise, kDiff, kPhilox, kStats>(cfg, tr, e, a_t, n01, n23, draws, eps0, lsum, io, i, active, sink, so);
+  if (alive) {
+    if (kStats && !so.reset) add_episode_sums(eps0, e, so.terms, cfg.dt);
+    c.any_reset |= so.reset;
+    c.any_noise_dirty |= so.noise_dirty;
+    c.last_noise_dirty = so.noise_dirty;
+    if (rio.reward) rio.reward[tn] = so.reward;
+    if (rio.dones) rio.dones[tn] = so.reset ? 1 : 0;
+    if (rio.terminated) rio.terminated[tn] = so.terminated ? 1 : 0;
+    if (rio.time_out) rio.time_out[tn] = so.time_out ? 1 : 0;
+  }
+}
+
 // 216-225 registers, no spills: 4 blocks of 64 threads per SM, i.e. two waves at 65,536 envs.  (Measured: capping the kernel at 128
 // registers -- a handful of spilled words, one wave of 8 blocks per SM -- is SLOWER at every size tried: 4.22 vs 3.90 us per step at
 // 65,536 envs, 2.66 vs 2.00 us at 16,384 with tape; tools/rollout_bench.py.)
-template <bool kNoise, bool kDiff, bool kPhilox, bool kStats>
+// kRecord: the observation of EVERY step is recorded (rio.obs_seq); otherwise only the last step computes one -- two loop sections, each
+// with its observation section decided at compile time.
+template <bool kNoise, bool kDiff, bool kPhilox, bool kStats, bool kRecord>
 __global__ void __launch_bounds__(256) racing_rollout_fwd_kernel(const GrConfig cfg, const GrTrack track, const GrState st,
                                                                  const GrRandom rng, const GrRolloutIO rio) {
   GR_DYN_SMEM(float4, smem_rows);
@@ -151,57 +208,24 @@ __global__ void __launch_bounds__(256) racing_rollout_fwd_kernel(const GrConfig 
   __shared__ float4 obs_stage[8 * 128];
   const GrStepIO no_io = {};
   const GlobalObsSink gsink{no_io, live, obs_stage + (threadIdx.x >> 5) * 128};
-  bool any_reset = false, any_noise_dirty = false, last_noise_dirty = false;
-  const int64_t tape_step = (int64_t)(rio.tape_stride / kTile) * GR_TAPE_PLANES * kTile * 4;       // floats per tape step
+  RolloutCarry c;
   const bool coop = kPhilox && (st.launch_flags & GR_LAUNCH_COOP_RESET) != 0 && blockDim.x <= 64;
-  float4* const coop_draws = obs_stage + 2 * 128;       // (the staging rows of warps 2..7: unused with blocks of <= 64 threads)
+  float4* const coop_draws = coop ? obs_stage + 2 * 128 : nullptr;       // (the staging rows of warps 2..7: unused with blocks of <= 64 threads)
 
   float4 a_next = __ldcs(reinterpret_cast<const float4*>(rio.actions) + li);
+  if (kRecord) {
 #pragma unroll 1
-  for (int t = 0; t < T; ++t) {
-    const int64_t tn = (int64_t)t * N + i;
-    const float4 a_t = a_next;
-    if (t + 1 < T) a_next = __ldcs(reinterpret_cast<const float4*>(rio.actions) + (int64_t)(t + 1) * N + li);      // one step ahead
-    GrRandom rt = rng;
-    rt.step = rng.step + (uint32_t)t;
-    if (!kPhilox) rt.rnd = rng.rnd + (int64_t)t * N * GR_RND_STRIDE;
-    const RandSrc<kPhilox> rs(rt, li, st.env_id_offset + li);
-    const bool last = t == T - 1;
-    const bool want_obs = rio.obs_seq != nullptr || last;          // (uniform over the grid)
-    float4 n01 = make_float4(0.f, 0.f, 0.f, 0.f), n23 = n01;
-    if (want_obs) rs.normals8(n01, n23);
-    const Draws<kPhilox> draws{rs, coop ? coop_draws : nullptr, want_obs};
-    GrStepIO io = {};
-    io.log_accum = rio.log_accum;
-    if (kDiff) {
-      io.tape = rio.tape ? rio.tape + (int64_t)t * tape_step : nullptr;
-      io.tape_stride = rio.tape_stride;
-      io.loss = rio.loss ? rio.loss + (int64_t)t * N : nullptr;
-      io.loss_terms = rio.loss_terms ? rio.loss_terms + (int64_t)t * N * 3 : nullptr;
-    }
-    RolloutObsSink sink{gsink, nullptr, nullptr, nullptr, nullptr};
-    if (rio.obs_seq) sink.seq_rows = reinterpret_cast<float4*>(rio.obs_seq) + (int64_t)t * N * 4;
-    if (last) {
-      sink.out_rows = reinterpret_cast<float4*>(rio.obs_out);
-      sink.critic_rows = reinterpret_cast<float4*>(rio.critic_obs_out);
-      sink.aux_ptr = rio.aux_out;
-    }
-    StepOut so;
-    const bool alive = racing_step_body<kNoise, kDiff, kPhilox, kStats>(cfg, tr, e, a_t, n01, n23, draws, eps0, lsum, io, i, active, sink, so);
-    if (alive) {
-      if (kStats && !so.reset) add_episode_sums(eps0, e, so.terms, cfg.dt);
-      any_reset |= so.reset;
-      any_noise_dirty |= so.noise_dirty;
-      last_noise_dirty = so.noise_dirty;
-      if (rio.reward) rio.reward[tn] = so.reward;
-      if (rio.dones) rio.dones[tn] = so.reset ? 1 : 0;
-      if (rio.terminated) rio.terminated[tn] = so.terminated ? 1 : 0;
-      if (rio.time_out) rio.time_out[tn] = so.time_out ? 1 : 0;
-    }
+    for (int t = 0; t < T; ++t)
+      rollout_one_step<kNoise, kDiff, kPhilox, kStats, true>(cfg, tr, st, rng, rio, gsink, coop_draws, t, i, li, active, e, eps0, lsum, a_next, c);
+  } else {
+#pragma unroll 1
+    for (int t = 0; t < T - 1; ++t)
+      rollout_one_step<kNoise, kDiff, kPhilox, kStats, false>(cfg, tr, st, rng, rio, gsink, coop_draws, t, i, li, active, e, eps0, lsum, a_next, c);
+    rollout_one_step<kNoise, kDiff, kPhilox, kStats, true>(cfg, tr, st, rng, rio, gsink, coop_draws, T - 1, i, li, active, e, eps0, lsum, a_next, c);
   }
   if (active) {      // what T single steps leave behind: cold planes rewritten if any step reset, the noise-dirty flag = the LAST step's
-    store_env<kNoise>(e, tile, any_reset, any_noise_dirty);
-    if (kNoise && any_noise_dirty && !last_noise_dirty)
+    store_env<kNoise>(e, tile, c.any_reset, c.any_noise_dirty);
+    if (kNoise && c.any_noise_dirty && !c.last_noise_dirty)
       st_plane(tile, PL_LINVEL, pack(e.v, __uint_as_float(eplen_word(e.eplen, e.aux != 0.0f, false, e.arate, e.metrics_zero))));
     if (kStats) { st_plane(tile, PL_EPSUM0, eps0); if (kDiff) st_plane(tile, PL_LOSSSUM, lsum); }
   }
@@ -424,23 +448,23 @@ extern "C" int gr_step_fwd(const GrConfig* cfg, const GrTrack* track, const GrSt
                             : dispatch_diff<false>(diff, philox, stats, cfg, track, st, rng, io, s);
 }
 
-template <bool kNoise, bool kDiff, bool kPhilox>
-static int launch_rollout(bool stats, const GrConfig* cfg, const GrTrack* tr, const GrState* st, const GrRandom* rng, const GrRolloutIO* io, cudaStream_t s) {
+template <bool kNoise, bool kDiff, bool kPhilox, bool kStats, bool kRecord>
+static int launch_rollout_k(const GrConfig* cfg, const GrTrack* tr, const GrState* st, const GrRandom* rng, const GrRolloutIO* io, cudaStream_t s) {
   const size_t bytes = track_smem_bytes(tr, st);
   const int kBlock = block_threads(st);
   const int grid = (st->num_envs + kBlock - 1) / kBlock;
-  if (stats) {
-    auto kernel = racing_rollout_fwd_kernel<kNoise, kDiff, kPhilox, true>;
-    int rc = prepare_smem(kernel, bytes);
-    if (rc != GR_OK) return rc;
-    kernel<<<grid, kBlock, bytes, s>>>(*cfg, *tr, *st, *rng, *io);
-  } else {
-    auto kernel = racing_rollout_fwd_kernel<kNoise, kDiff, kPhilox, false>;
-    int rc = prepare_smem(kernel, bytes);
-    if (rc != GR_OK) return rc;
-    kernel<<<grid, kBlock, bytes, s>>>(*cfg, *tr, *st, *rng, *io);
-  }
+  auto kernel = racing_rollout_fwd_kernel<kNoise, kDiff, kPhilox, kStats, kRecord>;
+  int rc = prepare_smem(kernel, bytes);
+  if (rc != GR_OK) return rc;
+  kernel<<<grid, kBlock, bytes, s>>>(*cfg, *tr, *st, *rng, *io);
   return (int)cudaGetLastError();
+}
+
+template <bool kNoise, bool kDiff, bool kPhilox>
+static int launch_rollout(bool stats, const GrConfig* cfg, const GrTrack* tr, const GrState* st, const GrRandom* rng, const GrRolloutIO* io, cudaStream_t s) {
+  const bool record = io->obs_seq != nullptr;
+  if (stats) return record ? launch_rollout_k<kNoise, kDiff, kPhilox, true, true>(cfg, tr, st, rng, io, s) : launch_rollout_k<kNoise, kDiff, kPhilox, true, false>(cfg, tr, st, rng, io, s);
+  return record ? launch_rollout_k<kNoise, kDiff, kPhilox, false, true>(cfg, tr, st, rng, io, s) : launch_rollout_k<kNoise, kDiff, kPhilox, false, false>(cfg, tr, st, rng, io, s);
 }
 
 extern "C" int gr_rollout_fwd(const GrConfig* cfg, const GrTrack* track, const GrState* st, const GrRandom* rng, const GrRolloutIO* io, void* stream) {

@@ -166,7 +166,9 @@ class RacingVecEnv:
         # read-mostly planes before the grid dependency: "1" = into registers with the stale-flag protocol, "l2" = into L2 only, "0" = off
         pf = {"0": 0, "1": B.GR_LAUNCH_PREFETCH, "l2": B.GR_LAUNCH_PREFETCH_L2}[os.environ.get("GRACING_PREFETCH", "1").lower()]
         flags = (B.GR_LAUNCH_PDL | pf) if (pdl and self.device.type == "cuda") else 0
-        if os.environ.get("GRACING_COOP_RESET", "0") == "1" and self.device.type == "cuda":
+        # warp-cooperative Philox draws for resetting envs: measured on the B200 -0.25 .. -0.4 us per 65,536-env step at a 4.5 % reset
+        # rate (gpurun r2g / r2h / r2i A/B pairs), -0.2 us per step in the window kernel; bit-identical draws (tests/test_philox_chain.py)
+        if os.environ.get("GRACING_COOP_RESET", "1") == "1" and self.device.type == "cuda":
             flags |= B.GR_LAUNCH_COOP_RESET
         if os.environ.get("GRACING_EARLY_STORE", "1") == "1":       # measured on the B200: -0.06 .. -0.15 us per 65,536-env step
             flags |= B.GR_LAUNCH_EARLY_STORE
@@ -451,6 +453,7 @@ class RacingVecEnv:
         io.log_accum = self._log_accum.data_ptr()
         if self._bptt is not None:
             self._bptt.bind_step(io)
+            w_reward, w_dones = self._bptt.bind_outputs(io)
             if self.export_aligned_states:
                 if "aligned" not in o:
                     o["aligned"], o["acc"] = torch.zeros(self.num_envs, 13, device=self.device), torch.zeros(self.num_envs, 3, device=self.device)
@@ -474,8 +477,10 @@ class RacingVecEnv:
                 ex["aligned_states"] = ex["nominal_states"] = o["aligned"]
                 ex["acc"] = o["acc"]
             # a differentiable-physics loop keeps what a step returns for the whole window (naive_train.py:170-172 appends dones and
-            # losses to lists): hand out tensors that the step after next does not overwrite
-            return self._grad_safe_obs(o["obs"], actions.requires_grad), o["reward"].clone(), o["dones"].clone(), ex
+            # losses to lists): the kernel wrote reward / dones into this step's rows of the window (BpttWindow.bind_outputs), which no
+            # later step of the window overwrites -- no copy launches on this path
+            self._last = dict(o, reward=w_reward, dones=w_dones)
+            return self._grad_safe_obs(o["obs"], actions.requires_grad), w_reward, w_dones, ex
         return o["obs"], o["reward"], o["dones"], ex
 
     def rollout(self, actions: torch.Tensor, rnd: Optional[torch.Tensor] = None, record_obs: bool = False) -> dict:

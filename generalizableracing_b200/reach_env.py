@@ -219,12 +219,14 @@ class ReachTargetVecEnv:
         io.action = act.data_ptr()
         io.reward_terms = o["reward_terms"].data_ptr() if self.export_reward_terms else None
         io.log_accum = self._log_accum.data_ptr()
+        reward, dones = o["reward"], o["dones"]
         if self._bptt is not None:
             self._bptt.bind_step(io)
+            reward, dones = self._bptt.bind_outputs(io)     # this step's rows of the window: valid until the window is detached
         rc = self._lib.gr_reach_step_fwd(C.byref(self._gcfg), C.byref(self._state), C.byref(self._rand(rnd)), C.byref(io), self._stream())
         if rc:
             B.check(rc, "gr_reach_step_fwd")
-        self._last = o
+        self._last = o if self._bptt is None else dict(o, reward=reward, dones=dones)
         ex = self.extras
         dict.pop(ex, "log", None)
         to, term = self._views[k]
@@ -233,7 +235,7 @@ class ReachTargetVecEnv:
         ex["terminated"] = term
         if self._bptt is not None:
             self._bptt.after_step(actions, ex)
-        return self._grad_safe_obs(o["obs"], actions.requires_grad), o["reward"], o["dones"], ex
+        return self._grad_safe_obs(o["obs"], actions.requires_grad), reward, dones, ex
 
     def rollout(self, actions: torch.Tensor, rnd: Optional[torch.Tensor] = None, record_obs: bool = False) -> dict:
         """``for t in range(T): env.step(actions[t])`` in ONE launch (gr_reach_rollout_fwd) for actions known in advance

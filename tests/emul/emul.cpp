@@ -37,7 +37,10 @@ int emul_step_fwd(const GrConfig* cfg, const GrTrack* tr, const GrState* st, con
 int emul_rollout_fwd(const GrConfig* cfg, const GrTrack* tr, const GrState* st, const GrRandom* rng, const GrRolloutIO* io) {
   const bool diff = io->loss || io->tape || io->loss_terms, stats = st->num_planes == GR_NUM_PLANES_WITH_STATS, philox = rng->rnd == nullptr,
              noise = cfg->add_cmd_noise != 0;
-#define GO(a, b, c, d) if (noise == a && diff == b && philox == c && stats == d) { run_grid(st->num_envs, [&] { racing_rollout_fwd_kernel<a, b, c, d>(*cfg, *tr, *st, *rng, *io); }); return 0; }
+#define GO(a, b, c, d) if (noise == a && diff == b && philox == c && stats == d) { \
+    if (io->obs_seq) run_grid(st->num_envs, [&] { racing_rollout_fwd_kernel<a, b, c, d, true>(*cfg, *tr, *st, *rng, *io); }); \
+    else run_grid(st->num_envs, [&] { racing_rollout_fwd_kernel<a, b, c, d, false>(*cfg, *tr, *st, *rng, *io); }); \
+    return 0; }
   GO(false, false, false, false) GO(false, false, false, true) GO(false, false, true, false) GO(false, false, true, true)
   GO(false, true, false, false) GO(false, true, false, true) GO(false, true, true, false) GO(false, true, true, true)
   GO(true, false, false, false) GO(true, false, false, true) GO(true, false, true, false) GO(true, false, true, true)
