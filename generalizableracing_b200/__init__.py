@@ -3,7 +3,7 @@ the reference's env, storage and runner interfaces.  See DESIGN.md."""
 from .config import RacingCfg, ReachTargetCfg
 from .tracks import GateTable, figure_eight_track, synthetic_track_table
 
-__all__ = ["RacingCfg", "GateTable", "figure_eight_track", "synthetic_track_table", "RacingVecEnv", "RolloutStorage", "make_env", "ReachTargetCfg", "ReachTargetVecEnv", "make_reach_env"]
+__all__ = ["RacingCfg", "GateTable", "figure_eight_track", "synthetic_track_table", "RacingVecEnv", "RolloutStorage", "make_env", "ReachTargetCfg", "ReachTargetVecEnv", "make_reach_env", "TerrainMesh", "get_uav_collision_num_ray"]
 
 
 def __getattr__(name):
@@ -19,4 +19,7 @@ def __getattr__(name):
     if name in ("ReachTargetVecEnv", "make_reach_env"):
         from . import reach_env
         return getattr(reach_env, name)
+    if name in ("TerrainMesh", "get_uav_collision_num_ray", "collision_penalty_custom", "LATTICE_TENSOR"):
+        from . import mesh
+        return getattr(mesh, name)
     raise AttributeError(name)

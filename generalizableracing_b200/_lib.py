@@ -165,6 +165,10 @@ class GrReachRolloutIO(C.Structure):
                 ("loss", c_p), ("loss_terms", c_p), ("tape", c_p), ("tape_stride", C.c_int64), ("log_accum", c_p), ("T", c_i)]
 
 
+class GrMesh(C.Structure):
+    _fields_ = [("nodes", c_p), ("tris", c_p), ("num_nodes", c_i), ("num_faces", c_i)]
+
+
 GR_REACH_LOG_NUM_RESET, GR_REACH_LOG_SUM_POS_ERR, GR_REACH_LOG_SUM_EPSUM, GR_REACH_LOG_NUM_TIMEOUT, GR_REACH_LOG_NUM_TERMINATED = 0, 1, 2, 12, 13
 GR_LOG_SHARDS = 256
 GR_PHILOX_CALL_ACTION = 16
@@ -213,6 +217,10 @@ PROTOTYPES = {
                                     C.POINTER(GrHostStep), c_p, C.POINTER(C.c_int64)]),
     "gr_host_pipe_wait": (C.c_int, [c_p, C.c_int64]),
     "gr_host_copy_probe": (C.c_int, [c_i, c_i, c_i, C.POINTER(C.c_double)]),
+    "gr_mesh_bvh_max_nodes": (C.c_int64, [c_i]),
+    "gr_mesh_build_bvh": (C.c_int, [c_p, c_p, c_i, c_i, c_p, C.c_int64, c_p, c_p, C.POINTER(c_i)]),
+    "gr_uav_collision_ray": (C.c_int, [C.POINTER(GrMesh), c_p, c_p, c_i, c_p, c_i, c_f, c_f, c_f, c_p, c_p]),
+    "gr_mesh_query_rays": (C.c_int, [C.POINTER(GrMesh), c_p, c_p, C.c_int64, c_f, c_p, c_p, c_p]),
 }
 
 

@@ -565,6 +565,35 @@ int gr_traj_unpad(const float* padded, const uint8_t* masks, int32_t T, int32_t 
 int gr_traj_hidden(const float* saved, int32_t T, int32_t L, int32_t N, int32_t H, const int32_t* traj_env, const int32_t* traj_start,
                    int32_t first, int32_t count, float* out, void* stream);
 
+/* ---- UAV-vs-terrain-mesh collision count: replaces the reference's only GPU kernel, the Warp kernel
+ * check_uav_collision_ray_kernel (L/utils/mesh_tools.py:128-233) and its launcher get_uav_collision_num_ray (:237-295), consumed by the
+ * STAGE-0 reward term collision_penalty_custom (QD/mdp/rewards.py:226-242).  The terrain is a triangle mesh (the inputs of wp.Mesh:
+ * points [V,3], indices [F,3]); gr_mesh_build_bvh turns it on the HOST into the BVH + face records the device kernels traverse. */
+typedef struct GrMesh {
+  const float* nodes;       /* device, [num_nodes][8]: (lo.xyz, int32 first face of a leaf | left child), (hi.xyz, int32 face count of a leaf | 0);
+                               16-byte aligned; the children of an internal node are adjacent (left, left + 1); node 0 is the root */
+  const float* tris;        /* device, [num_faces][12] in BVH order: (v0.xyz, 0), (v1 - v0, 0), (v2 - v0, 0); 16-byte aligned */
+  int32_t num_nodes;
+  int32_t num_faces;
+} GrMesh;
+/* upper bound of the nodes gr_mesh_build_bvh writes for `num_faces` faces */
+int64_t gr_mesh_bvh_max_nodes(int32_t num_faces);
+/* HOST function (no device work): points [V,3] fp32, indices [F,3] int32 -> nodes_out [max_nodes][8], tris_out [F][12], face_ids_out [F]
+ * (optional: original index of the face stored at each BVH position), *num_nodes_out.  Median split of the face centroids along the
+ * widest axis, <= 4 faces per leaf, boxes padded by a relative 1e-5. */
+int gr_mesh_build_bvh(const float* points, const int32_t* indices, int32_t num_points, int32_t num_faces, float* nodes_out, int64_t max_nodes,
+                      float* tris_out, int32_t* face_ids_out, int32_t* num_nodes_out);
+/* get_uav_collision_num_ray: uav_position [N,3], uav_quat_wxyz [N,4] (Isaac order; the reference re-orders to Warp's xyzw itself,
+ * mesh_tools.py:261), lattices [M,3] or NULL with num_lattices = 0 (centre point only) -> collision_num [N] int32 (zeroed here, as the
+ * launcher's torch.zeros).  Per lattice point six axis rays (+x -x +y -y +z -z) of length max_dist; the point counts when the closest hit
+ * of one of them is a back face. */
+int gr_uav_collision_ray(const GrMesh* mesh, const float* uav_position, const float* uav_quat_wxyz, int32_t num_uav, const float* lattices,
+                         int32_t num_lattices, float max_dist, float arm_length, float height, int32_t* collision_num, void* stream);
+/* wp.mesh_query_ray over arrays: origins / dirs [R,3] -> t_out [R] (max_t where nothing was hit), sign_out [R] (+1 front face, -1 back
+ * face, 0 no hit). */
+int gr_mesh_query_rays(const GrMesh* mesh, const float* origins, const float* dirs, int64_t num_rays, float max_t, float* t_out, float* sign_out,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

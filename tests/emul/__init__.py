@@ -21,7 +21,7 @@ def _stale():
         return True
     t = os.path.getmtime(_SO)
     deps = [os.path.join(_HERE, f) for f in ("emul.cpp", "cuda_shim.h")] + \
-           [os.path.join(_CSRC, f) for f in ("racing_step.cu", "racing_bwd.cu", "gr_math.cuh", "gr_common.cuh", "reach_step.cu", "reach_bwd.cu", "reach_core.cuh", "racing_step_core.cuh", "rollout.cu")] + \
+           [os.path.join(_CSRC, f) for f in ("racing_step.cu", "racing_bwd.cu", "gr_math.cuh", "gr_common.cuh", "reach_step.cu", "reach_bwd.cu", "reach_core.cuh", "racing_step_core.cuh", "rollout.cu", "mesh_collision.cu")] + \
            [os.path.join(_HERE, "..", "..", "include", "gracing.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -55,6 +55,8 @@ class EmulLib:
         self._l.emul_compute_returns.argtypes = [P(B.GrStorage), C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int32]
         self._l.emul_advantage_normalize.argtypes = [P(B.GrStorage), C.c_void_p]
         self._l.emul_storage_gather.argtypes = [P(B.GrStorage), C.c_void_p, C.c_int32, P(B.GrMiniBatch)]
+        self._l.emul_uav_collision_ray.argtypes = [P(B.GrMesh), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        self._l.emul_mesh_query_rays.argtypes = [P(B.GrMesh), C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]
 
     def gr_step_fwd(self, cfg, tr, st, rng, io, stream):
         return self._l.emul_step_fwd(cfg, tr, st, rng, io)
@@ -113,3 +115,9 @@ class EmulLib:
 
     def gr_storage_gather(self, s, idx, b, out, stream):
         return self._l.emul_storage_gather(s, idx, b, out)
+
+    def gr_uav_collision_ray(self, mesh, pos, quat, n, lattices, num_lattices, max_dist, arm, height, out, stream):
+        return self._l.emul_uav_collision_ray(mesh, pos, quat, n, lattices, num_lattices, max_dist, arm, height, out)
+
+    def gr_mesh_query_rays(self, mesh, origins, dirs, n, max_t, t_out, sign_out, stream):
+        return self._l.emul_mesh_query_rays(mesh, origins, dirs, n, max_t, t_out, sign_out)

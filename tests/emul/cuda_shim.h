@@ -45,6 +45,7 @@ static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
 static inline bool __any_sync(unsigned, bool p) { return p; }
 static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }
+static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
 using std::min;
 using std::max;
 typedef int cudaError_t;

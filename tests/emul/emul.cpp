@@ -10,6 +10,7 @@
 // there is no other lane, i.e. an empty triple, which merge() skips.  (Valid for this file's merge-style reductions only.)
 static inline double __shfl_down_sync(unsigned, double, int) { return 0.0; }
 #include "../../generalizableracing_b200/csrc/rollout.cu"
+#include "../../generalizableracing_b200/csrc/mesh_collision.cu"
 #include <vector>
 
 using namespace gr;
@@ -150,6 +151,18 @@ int emul_storage_gather(const GrStorage* s, const int64_t* indices, int32_t B, c
   const int64_t total = (int64_t)B * per_row;
   if (V == 4) run_grid(total, [&] { storage_gather_kernel<4>(*s, indices, B, *out); });
   else run_grid(total, [&] { storage_gather_kernel<1>(*s, indices, B, *out); });
+  return 0;
+}
+
+int emul_uav_collision_ray(const GrMesh* mesh, const float* pos, const float* quat, int32_t n, const float* lattices, int32_t num_lattices, float max_dist,
+                           float arm_length, float height, int32_t* out) {
+  std::memset(out, 0, sizeof(int32_t) * (size_t)n);
+  run_grid((int64_t)n * (num_lattices > 0 ? num_lattices : 1), [&] { uav_collision_ray_kernel(*mesh, pos, quat, lattices, num_lattices, n, max_dist, arm_length, height, out); });
+  return 0;
+}
+
+int emul_mesh_query_rays(const GrMesh* mesh, const float* origins, const float* dirs, int64_t num_rays, float max_t, float* t_out, float* sign_out) {
+  run_grid(num_rays, [&] { mesh_query_rays_kernel(*mesh, origins, dirs, num_rays, max_t, t_out, sign_out); });
   return 0;
 }
 }
