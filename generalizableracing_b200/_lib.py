@@ -106,7 +106,7 @@ class GrMlpGrad(C.Structure):
 
 
 class GrBackwardJob(C.Structure):
-    _fields_ = [("policy", GrPolicy), ("obs", c_p), ("grad_actions", c_p), ("scale", c_p), ("out", GrMlpGrad)]
+    _fields_ = [("policy", GrPolicy), ("obs", c_p), ("grad_actions", c_p), ("scale", c_p), ("out", GrMlpGrad), ("indices", c_p)]
 
 
 class GrAdamStep(C.Structure):
@@ -118,7 +118,7 @@ class GrAdamStep(C.Structure):
 class GrPpoBatch(C.Structure):
     _fields_ = [("mu", c_p), ("value", c_p), ("sigma", c_p), ("actions", c_p), ("old_log_prob", c_p), ("advantages", c_p), ("returns", c_p),
                 ("old_values", c_p), ("old_mu", c_p), ("old_sigma", c_p), ("clip_param", c_f), ("value_loss_coef", c_f), ("entropy_coef", c_f),
-                ("use_clipped_value_loss", c_i)]
+                ("use_clipped_value_loss", c_i), ("indices", c_p)]
 
 
 class GrHostStep(C.Structure):
@@ -198,6 +198,7 @@ PROTOTYPES = {
                                  C.POINTER(GrStorage), C.POINTER(GrCollectIO), c_p]),
     "gr_actor_backward": (C.c_int, [C.POINTER(GrPolicy), c_i, c_i, c_p, c_p, c_p, C.c_int64, C.POINTER(GrMlpGrad), c_p]),
     "gr_policy_forward": (C.c_int, [C.POINTER(GrPolicy), c_p, c_p, c_p, c_p, C.c_int64, c_p]),
+    "gr_policy_forward_gather": (C.c_int, [C.POINTER(GrPolicy), c_p, c_p, c_p, c_p, c_p, C.c_int64, c_p]),
     "gr_ppo_loss_grad": (C.c_int, [C.POINTER(GrPpoBatch), C.c_int64, c_p, c_p, c_p, c_p]),
     "gr_adam_clip_step": (C.c_int, [C.POINTER(GrAdamStep), c_p]),
     "gr_actor_backward_jobs": (C.c_int, [C.POINTER(GrBackwardJob), c_i, c_i, c_i, C.c_int64, c_p]),
@@ -253,7 +254,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.gr_abi_version() != 2:
+    if lib.gr_abi_version() != 3:
         raise ImportError("libgracing.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -116,8 +116,8 @@ class PPO:
         return loss, surrogate_loss, value_loss, mu_batch, sigma_batch
 
     def _kernel_step_factory(self, g, mbs, desc, lr, mb):
-        """The captured step of `kernel_update` (ppo.py:118-178 of the reference without autograd), nine launches:
-        gather -> pack -> sigma -> zero(flat) -> gr_policy_forward -> gr_ppo_loss_grad -> gr_actor_backward_jobs (actor + critic) -> [all-reduce] ->
+        """The captured step of `kernel_update` (ppo.py:118-178 of the reference without autograd), eight launches:
+        pack -> sigma -> zero(flat) -> gr_policy_forward_gather -> gr_ppo_loss_grad -> gr_actor_backward_jobs (actor + critic) -> [all-reduce] ->
         gr_adam_clip_step (2).  One flat fp32 buffer holds every gradient (the parameters' .grad are views of it) and, in its
         last 16 floats, the loss kernel's sums (losses, KL, d/d std, loss scales): a multi-GPU run all-reduces exactly that."""
         import ctypes as C
@@ -183,24 +183,27 @@ class PPO:
                            c3.bias.grad.data_ptr(), 1, 1)
         pol_both = B.GrPolicy(g["packed"].data_ptr(), g["sigma4"].data_ptr(), slope)
         pol_c = B.GrPolicy(g["packed"].data_ptr() + net_bytes, g["sigma4"].data_ptr(), slope)
-        batch = B.GrPpoBatch(g["mu_new"].data_ptr(), g["v_new"].data_ptr(), g["sigma4"].data_ptr(), g["actions"].data_ptr(), g["log_prob"].data_ptr(),
-                             g["advantages"].data_ptr(), g["returns"].data_ptr(), g["values"].data_ptr(), g["mu"].data_ptr(), g["sigma"].data_ptr(),
-                             float(self.clip_param), float(self.value_loss_coef), float(self.entropy_coef), int(self.use_clipped_value_loss))
+        # the mini-batch gather (rollout_storage.py:179-187) happens ON LOAD: every kernel reads the storage's own columns at row idx[r]
+        # (measured at 65,536 envs: the separate gather launch was 84 us of a 440 us step, and its output was read once)
+        idx_ptr = g["idx"].data_ptr()
+        s_obs, s_critic = desc.obs, desc.critic_obs or desc.obs
+        batch = B.GrPpoBatch(g["mu_new"].data_ptr(), g["v_new"].data_ptr(), g["sigma4"].data_ptr(), desc.actions, desc.log_prob, desc.advantages, desc.returns,
+                             desc.values, desc.mu, desc.sigma, float(self.clip_param), float(self.value_loss_coef), float(self.entropy_coef),
+                             int(self.use_clipped_value_loss), idx_ptr)
         p_max_mu, p_max_v = ksums.data_ptr() + 8 * 4, ksums.data_ptr() + 9 * 4
-        jobs = (B.GrBackwardJob * 2)(B.GrBackwardJob(pol_both, g["obs"].data_ptr(), g["grad_mu"].data_ptr(), p_max_mu, gr_a),
-                                     B.GrBackwardJob(pol_c, g["critic_obs"].data_ptr(), g["grad_v"].data_ptr(), p_max_v, gr_c))
+        jobs = (B.GrBackwardJob * 2)(B.GrBackwardJob(pol_both, s_obs, g["grad_mu"].data_ptr(), p_max_mu, gr_a, idx_ptr),
+                                     B.GrBackwardJob(pol_c, s_critic, g["grad_v"].data_ptr(), p_max_v, gr_c, idx_ptr))
         g["keep_k"] = (mlp_a, mlp_c, gr_a, gr_c, pol_both, pol_c, batch, adam, ptrs, seg_off, seg_n, jobs)
         g["kernel_sums"] = True                      # the running loss sums live in adam_state[5:7]
 
         def step():
             st = torch.cuda.current_stream(dev).cuda_stream
-            B.check(lib.gr_storage_gather(C.byref(desc), g["idx"].data_ptr(), mb, C.byref(mbs), st), "gr_storage_gather")
             B.check(lib.gr_policy_pack(C.byref(mlp_a), C.byref(mlp_c), g["packed"].data_ptr(), st), "gr_policy_pack")
             with torch.no_grad():
                 g["sigma4"].copy_(pol.std)
                 flat.zero_()
-            B.check(lib.gr_policy_forward(C.byref(pol_both), g["obs"].data_ptr(), g["critic_obs"].data_ptr(), g["mu_new"].data_ptr(), g["v_new"].data_ptr(), mb, st),
-                    "gr_policy_forward")
+            B.check(lib.gr_policy_forward_gather(C.byref(pol_both), s_obs, s_critic, idx_ptr, g["mu_new"].data_ptr(), g["v_new"].data_ptr(), mb, st),
+                    "gr_policy_forward_gather")
             B.check(lib.gr_ppo_loss_grad(C.byref(batch), mb, g["grad_mu"].data_ptr(), g["grad_v"].data_ptr(), ksums.data_ptr(), st), "gr_ppo_loss_grad")
             B.check(lib.gr_actor_backward_jobs(jobs, 2, 128, 128, mb, st), "gr_actor_backward_jobs")       # actor (d/d mu) and critic (d/d v) in one launch
             if world > 1:              # env-sharded data parallelism: ONE all-reduce per step carries the gradients and the loss / KL sums

@@ -17,6 +17,8 @@
 // accumulators stay in tensor memory across all tiles of the CTA (fp32) and are flushed once with atomics.
 // fp16 operands need a loss scale: the cotangent is multiplied by *scale (device scalar, caller picks ~1024 / max|G|) on
 // load and the accumulators are divided by it at the flush.
+#include <cstdlib>
+
 #include "mlp_tc.cuh"
 
 namespace gr {
@@ -67,154 +69,206 @@ constexpr uint32_t kMnA = 1u << 15, kMnB = 1u << 16;          // instruction-des
 __device__ __forceinline__ uint64_t desc_rows_k(uint32_t addr) { return make_smem_desc(addr, kChunkA, 128); }     // rows = M, columns = K
 __device__ __forceinline__ uint64_t desc_rows_mn(uint32_t addr) { return make_smem_desc(addr, 128, kChunkA); }    // columns = M|N, rows = K
 
-// blockIdx.y selects the job: the actor and the critic of a PPO step share one launch (same widths, same row count)
-template <class NL>
-__global__ void __launch_bounds__(kTileEnvs, 1) actor_backward_kernel(const GrBackwardJob job0, const GrBackwardJob job1, const int64_t R) {
+// blockIdx.y selects the job: the actor and the critic of a PPO step share one launch (same widths, same row count).
+//
+// Warp-specialised: kGroups producer groups of 128 threads (one thread per row of a 128-row tile: operand rows in, epilogues out) and
+// ONE issuing warp whose lane 0 issues every tcgen05.mma of the CTA in program order.  A stage of a group = [its 128 threads have
+// written the operands: `full[g]`, 128 arrivals] -> the issuer queues the stage's MMAs and commits them to `done[g]` -> the group reads
+// the accumulator and writes the next operands.  With two groups the issuer alternates between them, so the tensor pipe works on one
+// tile while the other group's threads run their epilogue (one group alone leaves the pipe idle during every epilogue: 23 % tensor-
+// pipe activity, 14 % issue-slot use).  The weight-gradient accumulators are shared by the groups -- a single thread issues all MMAs,
+// so the accumulations are ordered -- and each group owns 128 scratch columns.  TMEM: 16 -> 128 -> 128: 2 x 128 scratch + 128 (dW2) +
+// 32 (dW1|db1) + 16 (dW3) + 16 (db2) = 448 columns, two groups; 16 -> 256 -> 128: 128 + 256 + 64 + 32 = 480 columns, one group.
+template <class NL, int kGroups>
+__global__ void __launch_bounds__(kGroups * kTileEnvs + 32, 1) actor_backward_kernel(const GrBackwardJob job0, const GrBackwardJob job1, const int64_t R) {
   const GrBackwardJob& job = blockIdx.y == 0 ? job0 : job1;
   const GrPolicy pol = job.policy;
   const float* __restrict__ X = job.obs;
   const float* __restrict__ G = job.grad_actions;
   const float* __restrict__ scale_ptr = job.scale;
+  const int64_t* __restrict__ idx = job.indices;
   const GrMlpGrad out = job.out;
   constexpr int H1 = NL::kH1, H2 = NL::kH2, kHalves = H1 / 128;
   static_assert(H2 == 128 && (H1 == 128 || H1 == 256), "built for 16 -> 128|256 -> 128 -> 4");
-  // tensor memory: scratch accumulator | dW2 [H2 x H1] | dW1 (+ db1) [H1 x 32] as `kHalves` blocks | dW3^T [H2 x 16] | db2 [H2 x 16]
-  constexpr uint32_t kColD = 0, kColW2 = 128, kColW1 = kColW2 + H1, kColW3 = kColW1 + 32 * kHalves, kColB2 = kColW3 + 16, kColsUsed = kColB2 + 16;
+  // tensor memory: one scratch accumulator per group | dW2 [H2 x H1] | dW1 (+ db1) [H1 x 32] as `kHalves` blocks | dW3^T [H2 x 16] | db2 [H2 x 16]
+  constexpr uint32_t kColD = 0, kColW2 = 128 * kGroups, kColW1 = kColW2 + H1, kColW3 = kColW1 + 32 * kHalves, kColB2 = kColW3 + 16, kColsUsed = kColB2 + 16;
   static_assert(kColsUsed <= 512, "tensor memory budget");
+  constexpr int kStages = 2 * kHalves + 3;                  // forward L1 (per half), forward L2, dW3 | dH2, dW2 | db2 | dH1 (per half), dW1
+  constexpr int kGroupBytes = (4 + H1 / 8 + H2 / 8 + 2) * kChunkA;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* w_smem = smem;                                   // forward-packed actor
-  uint8_t* xs = w_smem + NL::kNetBytes;                     // [4][128][8]   obs | 1 1 0.. | 0
-  uint8_t* h1s = xs + 4 * kChunkA;                          // [H1/8][128][8]
-  uint8_t* h2s = h1s + (H1 / 8) * kChunkA;                  // [H2/8][128][8]
-  uint8_t* das = h2s + (H2 / 8) * kChunkA;                  // [2][128][8]   scaled cotangent (4 columns) | 0
-  uint8_t* ones = das + 2 * kChunkA;                        // [2][128][8]   column 0 = 1
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + 2 * kChunkA);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
+  uint8_t* w_smem = smem;                                   // forward-packed net
+  uint8_t* grp_smem = w_smem + NL::kNetBytes;               // per group: xs [4][128][8] | h1s [H1/8][128][8] | h2s [H2/8][128][8] | das [2][128][8]
+  uint8_t* ones = grp_smem + kGroups * kGroupBytes;         // [2][128][8]   column 0 = 1 (shared, read-only)
+  uint64_t* full = reinterpret_cast<uint64_t*>(ones + 2 * kChunkA);
+  uint64_t* done = full + kGroups;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + kGroups);
 
-  const int row = threadIdx.x;
+  const int tid = threadIdx.x;
+  const bool producer = tid < kGroups * kTileEnvs;
+  const int grp = producer ? tid / kTileEnvs : 0, row = tid % kTileEnvs;
   {
     const uint4* src = reinterpret_cast<const uint4*>(pol.packed);
     uint4* dst = reinterpret_cast<uint4*>(w_smem);
-    for (int k = row; k < NL::kNetBytes / 16; k += kTileEnvs) dst[k] = __ldg(src + k);
+    for (int k = tid; k < NL::kNetBytes / 16; k += kGroups * kTileEnvs + 32) dst[k] = __ldg(src + k);
   }
-  *reinterpret_cast<uint4*>(ones + row * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);            // half(1) in column 0
-  *reinterpret_cast<uint4*>(ones + kChunkA + row * 16) = make_uint4(0u, 0u, 0u, 0u);
-  *reinterpret_cast<uint4*>(das + kChunkA + row * 16) = make_uint4(0u, 0u, 0u, 0u);
-  if (row == 0) mbar_init(&bars[0], 1);
+  uint8_t* xs = grp_smem + grp * kGroupBytes;
+  uint8_t* h1s = xs + 4 * kChunkA;
+  uint8_t* h2s = h1s + (H1 / 8) * kChunkA;
+  uint8_t* das = h2s + (H2 / 8) * kChunkA;
+  if (tid < kTileEnvs) {
+    *reinterpret_cast<uint4*>(ones + row * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);            // half(1) in column 0
+    *reinterpret_cast<uint4*>(ones + kChunkA + row * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (producer) *reinterpret_cast<uint4*>(das + kChunkA + row * 16) = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) {
+    for (int g = 0; g < kGroups; ++g) { mbar_init(&full[g], kTileEnvs); mbar_init(&done[g], 1); }
+  }
   __syncwarp();
-  if (row < 32) tmem_alloc(tmem_slot, 512);
+  if (tid < 32) tmem_alloc(tmem_slot, 512);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
 
-  GroupCtx g = make_group_ctx(h1s, 0, bars, *tmem_slot, 0, 0, row, pol.negative_slope);       // (hbuf / hrow are not used through g here)
-  g.issuer = row == 0;
   const uint32_t tm = *tmem_slot;
-  const uint32_t lane_sel = (uint32_t)((row >> 5) * 32) << 16;
-  const uint32_t w_addr = smem_u32(w_smem), xs_a = smem_u32(xs), h1_a = smem_u32(h1s), h2_a = smem_u32(h2s), da_a = smem_u32(das), ones_a = smem_u32(ones);
-  const float scale = out.scale_is_maxabs ? 1024.0f / fmaxf(__ldg(scale_ptr), 1e-30f) : __ldg(scale_ptr);
-  float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);            // db3 = sum of the (unscaled) cotangent rows
   const int64_t tiles = (R + kTileEnvs - 1) / kTileEnvs;
-  bool first = true;
+  const int64_t stride = (int64_t)gridDim.x * kGroups;
+  const float scale = out.scale_is_maxabs ? 1024.0f / fmaxf(__ldg(scale_ptr), 1e-30f) : __ldg(scale_ptr);
 
-  // one barrier round = [operands written] -> sync -> thread 0 issues a batch -> commit -> everybody waits
-#define GR_STAGE_BEGIN() do { fence_proxy_async_smem(); tc_fence_before_sync(); bar_sync(g.bar_id, kTileEnvs); } while (0)
-#define GR_STAGE_END() do { if (g.issuer) tc_commit(g.bar); stage_wait(g); } while (0)
-
+  if (producer) {
+    const uint32_t lane_sel = (uint32_t)((row >> 5) * 32) << 16;
+    const uint32_t d_addr = tm + kColD + 128u * grp + lane_sel;
+    const __half2 slope = __float2half2_rn(pol.negative_slope);
+    float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);          // db3 = sum of the (unscaled) cotangent rows
+    uint32_t ph = 0u;
+    // one stage hand-over: operands written -> arrive; wait for the stage's MMAs
+#define GR_HANDOVER() do { fence_proxy_async_smem(); tc_fence_before_sync(); mbar_arrive(&full[grp]); mbar_wait(&done[grp], ph); ph ^= 1u; tc_fence_after_sync(); } while (0)
 #pragma unroll 1
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t r = tile * kTileEnvs + row;
-    // ---- operands of this tile: observation row (+ bias ones), scaled cotangent row
-    float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0, o2 = o0, o3 = o0, gr4 = o0;
-    if (r < R) {
-      const float4* xr = reinterpret_cast<const float4*>(X) + r * 4;
-      o0 = __ldcs(xr); o1 = __ldcs(xr + 1); o2 = __ldcs(xr + 2); o3 = __ldcs(xr + 3);
-      gr4 = __ldcs(reinterpret_cast<const float4*>(G) + r);
-    }
-    gsum.x += gr4.x; gsum.y += gr4.y; gsum.z += gr4.z; gsum.w += gr4.w;
-    // (the previous tile's last batch -- dW1 -- read xs and h1s: it was waited for at the end of that tile)
-    write_x_row(xs + row * 16, pack8(o0, o1), pack8(o2, o3));
-    *reinterpret_cast<uint4*>(das + row * 16) =
-        make_uint4(h2_bits(__floats2half2_rn(gr4.x * scale, gr4.y * scale)), h2_bits(__floats2half2_rn(gr4.z * scale, gr4.w * scale)), 0u, 0u);
-
-    // ---- forward layer 1 (128 units at a time) and layer 2: recompute the activations
-#pragma unroll 1
-    for (int h = 0; h < kHalves; ++h) {
-      GR_STAGE_BEGIN();
-      if (g.issuer) {
-        tc_fence_after_sync();
-#pragma unroll
-        for (int kk = 0; kk < kK1 / 16; ++kk)
-          mma_f16_ss(tm + kColD, desc_rows_k(xs_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW1Off + h * 128 * 16 + kk * 2 * (H1 * 16), H1 * 16, 128),
-                     make_idesc_f16(128, 128), kk > 0);
+    for (int64_t tile = (int64_t)blockIdx.x * kGroups + grp; tile < tiles; tile += stride) {
+      const int64_t r = tile * kTileEnvs + row;
+      // ---- operands of this tile: observation row (+ bias ones), scaled cotangent row
+      float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0, o2 = o0, o3 = o0, gr4 = o0;
+      if (r < R) {
+        const float4* xr = reinterpret_cast<const float4*>(X) + (idx ? __ldg(idx + r) : r) * 4;      // (mini-batch gather on load)
+        o0 = __ldcs(xr); o1 = __ldcs(xr + 1); o2 = __ldcs(xr + 2); o3 = __ldcs(xr + 3);
+        gr4 = __ldcs(reinterpret_cast<const float4*>(G) + r);
       }
-      GR_STAGE_END();
-      hidden_epilogue<false, 128>(tm + kColD + lane_sel, h1s + row * 16 + h * 16 * kChunkA, nullptr, g.slope);
-    }
-    GR_STAGE_BEGIN();
-    if (g.issuer) {
-      tc_fence_after_sync();
-#pragma unroll
-      for (int kk = 0; kk < H1 / 16; ++kk)
-        mma_f16_ss(tm + kColD, desc_rows_k(h1_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW2Off + kk * 2 * (H2 * 16), H2 * 16, 128),
-                   make_idesc_f16(128, H2), kk > 0);
-    }
-    GR_STAGE_END();
-    hidden_epilogue<true, H2>(tm + kColD + lane_sel, h2s + row * 16, reinterpret_cast<const uint4*>(w_smem + NL::kB2Off), g.slope);
-
-    // ---- dW3^T += H2^T . dA   (rows are K: both operands MN-major) ;  dH2 = dA . W3  (forward-packed W3 as MN-major B)
-    GR_STAGE_BEGIN();
-    if (g.issuer) {
-      tc_fence_after_sync();
-#pragma unroll
-      for (int kk = 0; kk < kTileEnvs / 16; ++kk)
-        mma_f16_ss(tm + kColW3, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(da_a + kk * 256), make_idesc_f16(H2, 16) | kMnA | kMnB, !first || kk > 0);
-      mma_f16_ss(tm + kColD, desc_rows_k(da_a), make_smem_desc(w_addr + NL::kW3Off, 128, kOutPad * 16), make_idesc_f16(128, H2) | kMnB, false);
-    }
-    GR_STAGE_END();
-    dact_epilogue(tm + kColD + lane_sel, h2s + row * 16, 0, g.slope);                    // h2s now holds dH2'
-
-    // ---- dW2 += dH2'^T . H1 ; db2 += dH2'^T . 1 ; dH1 = dH2' . W2 (forward-packed W2 as MN-major B), 128 units at a time
+      gsum.x += gr4.x; gsum.y += gr4.y; gsum.z += gr4.z; gsum.w += gr4.w;
+      // (the previous tile's last stage -- dW1 -- read xs and h1s: its hand-over waited for it)
+      write_x_row(xs + row * 16, pack8(o0, o1), pack8(o2, o3));
+      *reinterpret_cast<uint4*>(das + row * 16) =
+          make_uint4(h2_bits(__floats2half2_rn(gr4.x * scale, gr4.y * scale)), h2_bits(__floats2half2_rn(gr4.z * scale, gr4.w * scale)), 0u, 0u);
+      // ---- forward layer 1 (128 units at a time) and layer 2: recompute the activations
 #pragma unroll 1
-    for (int h = 0; h < kHalves; ++h) {
-      GR_STAGE_BEGIN();
-      if (g.issuer) {
-        tc_fence_after_sync();
-        if (h == 0) {
+      for (int h = 0; h < kHalves; ++h) {
+        GR_HANDOVER();
+        hidden_epilogue<false, 128>(d_addr, h1s + row * 16 + h * 16 * kChunkA, nullptr, slope);
+      }
+      GR_HANDOVER();
+      hidden_epilogue<true, H2>(d_addr, h2s + row * 16, reinterpret_cast<const uint4*>(w_smem + NL::kB2Off), slope);
+      // ---- dW3^T += H2^T . dA ;  dH2 = dA . W3
+      GR_HANDOVER();
+      dact_epilogue(d_addr, h2s + row * 16, 0, slope);                    // h2s now holds dH2'
+      // ---- dW2 += dH2'^T . H1 ; db2 += dH2'^T . 1 ; dH1 = dH2' . W2, 128 units at a time
+#pragma unroll 1
+      for (int h = 0; h < kHalves; ++h) {
+        GR_HANDOVER();
+        // (h == 0 with two halves: dW2 also read ALL of h1s -- it completed with this stage, so overwriting is safe)
+        dact_epilogue(d_addr, h1s + row * 16, h * 16, slope);             // h1s chunks [16h, 16h+16) now hold dH1'
+      }
+      // ---- dW1 | db1 += dH1'^T . [X | 1 1 0..]: nothing to read back, but xs / h1s stay in use until it completes
+      GR_HANDOVER();
+    }
+#undef GR_HANDOVER
 #pragma unroll
-          for (int kk = 0; kk < kTileEnvs / 16; ++kk) {
-            mma_f16_ss(tm + kColW2, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(h1_a + kk * 256), make_idesc_f16(H2, H1) | kMnA | kMnB, !first || kk > 0);
-            mma_f16_ss(tm + kColB2, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(ones_a + kk * 256), make_idesc_f16(H2, 16) | kMnA | kMnB, !first || kk > 0);
+    for (int o = 16; o > 0; o >>= 1) {
+      gsum.x += __shfl_xor_sync(0xffffffffu, gsum.x, o); gsum.y += __shfl_xor_sync(0xffffffffu, gsum.y, o);
+      gsum.z += __shfl_xor_sync(0xffffffffu, gsum.z, o); gsum.w += __shfl_xor_sync(0xffffffffu, gsum.w, o);
+    }
+    if ((row & 31) == 0) {
+      atomicAdd(out.b3 + 0, gsum.x);
+      if (out.out_dim > 1) atomicAdd(out.b3 + 1, gsum.y);
+      if (out.out_dim > 2) atomicAdd(out.b3 + 2, gsum.z);
+      if (out.out_dim > 3) atomicAdd(out.b3 + 3, gsum.w);
+    }
+  } else if (tid == kGroups * kTileEnvs) {
+    // ---- the issuing thread: every MMA of the CTA, in program order
+    const uint32_t w_addr = smem_u32(w_smem), ones_a = smem_u32(ones), grp0_a = smem_u32(grp_smem);
+    int64_t n_tiles[kGroups];
+    uint32_t ph[kGroups];
+    int64_t rounds = 0;
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+      const int64_t first_tile = (int64_t)blockIdx.x * kGroups + g;
+      n_tiles[g] = first_tile < tiles ? (tiles - first_tile + stride - 1) / stride : 0;
+      ph[g] = 0u;
+      rounds = n_tiles[g] > rounds ? n_tiles[g] : rounds;
+    }
+    bool acc_w3 = false, acc_w2 = false, acc_w1 = false;     // the shared accumulators have been written at least once
+#pragma unroll 1
+    for (int64_t j = 0; j < rounds; ++j) {
+#pragma unroll 1
+      for (int s = 0; s < kStages; ++s) {
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+          if (j >= n_tiles[g]) continue;
+          const uint32_t xs_a = grp0_a + g * kGroupBytes, h1_a = xs_a + 4 * kChunkA, h2_a = h1_a + (H1 / 8) * kChunkA, da_a = h2_a + (H2 / 8) * kChunkA;
+          const uint32_t d_tm = tm + kColD + 128u * g;
+          mbar_wait(&full[g], ph[g]);
+          ph[g] ^= 1u;
+          tc_fence_after_sync();
+          if (s < kHalves) {                                   // forward layer 1, units [128 s, 128 s + 128)
+#pragma unroll
+            for (int kk = 0; kk < kK1 / 16; ++kk)
+              mma_f16_ss(d_tm, desc_rows_k(xs_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW1Off + s * 128 * 16 + kk * 2 * (H1 * 16), H1 * 16, 128),
+                         make_idesc_f16(128, 128), kk > 0);
+          } else if (s == kHalves) {                           // forward layer 2
+#pragma unroll
+            for (int kk = 0; kk < H1 / 16; ++kk)
+              mma_f16_ss(d_tm, desc_rows_k(h1_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW2Off + kk * 2 * (H2 * 16), H2 * 16, 128),
+                         make_idesc_f16(128, H2), kk > 0);
+          } else if (s == kHalves + 1) {                       // dW3^T += H2^T . dA (rows are K: both operands MN-major) ; dH2 = dA . W3 (W3 as MN-major B)
+#pragma unroll
+            for (int kk = 0; kk < kTileEnvs / 16; ++kk)
+              mma_f16_ss(tm + kColW3, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(da_a + kk * 256), make_idesc_f16(H2, 16) | kMnA | kMnB, acc_w3 || kk > 0);
+            acc_w3 = true;
+            mma_f16_ss(d_tm, desc_rows_k(da_a), make_smem_desc(w_addr + NL::kW3Off, 128, kOutPad * 16), make_idesc_f16(128, H2) | kMnB, false);
+          } else if (s < 2 * kHalves + 2) {                    // dW2 | db2 (first half only) ; dH1 units [128 h, 128 h + 128) = dH2' . W2 (W2 as MN-major B)
+            const int h = s - (kHalves + 2);
+            if (h == 0) {
+#pragma unroll
+              for (int kk = 0; kk < kTileEnvs / 16; ++kk) {
+                mma_f16_ss(tm + kColW2, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(h1_a + kk * 256), make_idesc_f16(H2, H1) | kMnA | kMnB, acc_w2 || kk > 0);
+                mma_f16_ss(tm + kColB2, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(ones_a + kk * 256), make_idesc_f16(H2, 16) | kMnA | kMnB, acc_w2 || kk > 0);
+              }
+              acc_w2 = true;
+            }
+#pragma unroll
+            for (int kk = 0; kk < H2 / 16; ++kk)
+              mma_f16_ss(d_tm, desc_rows_k(h2_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW2Off + h * 16 * (H2 * 16) + kk * 256, 128, H2 * 16),
+                         make_idesc_f16(128, 128) | kMnB, kk > 0);
+          } else {                                             // dW1 | db1 += dH1'^T . [X | 1 1 0..]
+#pragma unroll
+            for (int h = 0; h < kHalves; ++h)
+#pragma unroll
+              for (int kk = 0; kk < kTileEnvs / 16; ++kk)
+                mma_f16_ss(tm + kColW1 + 32 * h, desc_rows_mn(h1_a + h * 16 * kChunkA + kk * 256), desc_rows_mn(xs_a + kk * 256), make_idesc_f16(128, 32) | kMnA | kMnB,
+                           acc_w1 || kk > 0);
+            acc_w1 = true;
           }
+          tc_commit(&done[g]);
         }
-#pragma unroll
-        for (int kk = 0; kk < H2 / 16; ++kk)
-          mma_f16_ss(tm + kColD, desc_rows_k(h2_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW2Off + h * 16 * (H2 * 16) + kk * 256, 128, H2 * 16),
-                     make_idesc_f16(128, 128) | kMnB, kk > 0);
       }
-      GR_STAGE_END();
-      // (h == 0 with two halves: dW2 above also read ALL of h1s -- it completed with this batch, so overwriting is safe)
-      dact_epilogue(tm + kColD + lane_sel, h1s + row * 16, h * 16, g.slope);              // h1s chunks [16h, 16h+16) now hold dH1'
     }
-
-    // ---- dW1 | db1 += dH1'^T . [X | 1 1 0..]
-    GR_STAGE_BEGIN();
-    if (g.issuer) {
-      tc_fence_after_sync();
-#pragma unroll
-      for (int h = 0; h < kHalves; ++h)
-#pragma unroll
-        for (int kk = 0; kk < kTileEnvs / 16; ++kk)
-          mma_f16_ss(tm + kColW1 + 32 * h, desc_rows_mn(h1_a + h * 16 * kChunkA + kk * 256), desc_rows_mn(xs_a + kk * 256), make_idesc_f16(128, 32) | kMnA | kMnB,
-                     !first || kk > 0);
-    }
-    GR_STAGE_END();
-    first = false;
   }
+  // every group waited for its own last stage; after this barrier every MMA of the CTA has completed
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
 
-  // ---- flush: accumulator row m = TMEM lane m = this thread; everything divided by the loss scale
-  if (!first) {
+  // ---- flush (group 0): accumulator row m = TMEM lane m = this thread; everything divided by the loss scale
+  if (tid < kTileEnvs && (int64_t)blockIdx.x * kGroups < tiles) {
+    const uint32_t lane_sel = (uint32_t)((row >> 5) * 32) << 16;
     const float inv = 1.0f / scale;
     const int j = row;                                       // unit of layer 2 (dW2, db2, dW3) / unit within a 128-block of layer 1 (dW1)
 #pragma unroll 1
@@ -248,42 +302,30 @@ __global__ void __launch_bounds__(kTileEnvs, 1) actor_backward_kernel(const GrBa
       for (int a = 0; a < GR_NUM_ACTIONS; ++a) if (a < out.out_dim) atomicAdd(out.w3 + (int64_t)a * H2 + j, __uint_as_float(v[a]) * inv);
       atomicAdd(out.b2 + j, __uint_as_float(w[0]) * inv);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      gsum.x += __shfl_xor_sync(0xffffffffu, gsum.x, o); gsum.y += __shfl_xor_sync(0xffffffffu, gsum.y, o);
-      gsum.z += __shfl_xor_sync(0xffffffffu, gsum.z, o); gsum.w += __shfl_xor_sync(0xffffffffu, gsum.w, o);
-    }
-    if ((row & 31) == 0) {
-      atomicAdd(out.b3 + 0, gsum.x);
-      if (out.out_dim > 1) atomicAdd(out.b3 + 1, gsum.y);
-      if (out.out_dim > 2) atomicAdd(out.b3 + 2, gsum.z);
-      if (out.out_dim > 3) atomicAdd(out.b3 + 3, gsum.w);
-    }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (row < 32) tmem_dealloc(tm, 512);
-#undef GR_STAGE_BEGIN
-#undef GR_STAGE_END
+  if (tid < 32) tmem_dealloc(tm, 512);
 }
 
 }  // namespace gr
 
 using namespace gr;
 
-template <class NL>
+template <class NL, int kGroups>
 static int launch_actor_backward(const GrBackwardJob* jobs, int n_jobs, int64_t R, cudaStream_t s) {
-  const size_t bytes = (size_t)NL::kNetBytes + (size_t)(4 + NL::kH1 / 8 + NL::kH2 / 8 + 2 + 2) * kChunkA + 128;
+  const size_t bytes = (size_t)NL::kNetBytes + (size_t)kGroups * (4 + NL::kH1 / 8 + NL::kH2 / 8 + 2) * kChunkA + 2 * kChunkA + 128;
   if (bytes > 227 * 1024) return GR_ERR_SMEM;
-  auto kernel = actor_backward_kernel<NL>;
+  auto kernel = actor_backward_kernel<NL, kGroups>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) return (int)e;
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t tiles = (R + kTileEnvs - 1) / kTileEnvs;
+  const int64_t units = (tiles + kGroups - 1) / kGroups;      // a CTA works on kGroups tiles at a time
   const int per_job = sms / n_jobs;
-  const int grid = (int)(tiles < per_job ? tiles : per_job);
-  kernel<<<dim3(grid, n_jobs), kTileEnvs, bytes, s>>>(jobs[0], jobs[n_jobs - 1], R);
+  const int grid = (int)(units < per_job ? units : per_job);
+  kernel<<<dim3(grid, n_jobs), kGroups * kTileEnvs + 32, bytes, s>>>(jobs[0], jobs[n_jobs - 1], R);
   return (int)cudaGetLastError();
 }
 
@@ -305,13 +347,21 @@ extern "C" int gr_actor_backward_jobs(const GrBackwardJob* jobs, int32_t n_jobs,
   if (!((hidden == 128 || hidden == 256) && hidden2 == 128)) return GR_ERR_SIZE;
   for (int k = 0; k < n_jobs; ++k) { const int rc = check_job(&jobs[k]); if (rc != GR_OK) return rc; }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  return hidden == 256 ? launch_actor_backward<NetLayout<256, 128>>(jobs, n_jobs, rows, s) : launch_actor_backward<NetLayout<128, 128>>(jobs, n_jobs, rows, s);
+  // two tiles in flight per CTA where tensor memory has room for two scratch accumulators (16 -> 128 -> 128); one otherwise.
+  // (a job with very few tiles keeps one group per CTA so that the tiles spread over more SMs)
+  if (hidden == 256) return launch_actor_backward<NetLayout<256, 128>, 1>(jobs, n_jobs, rows, s);
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t tiles = (rows + kTileEnvs - 1) / kTileEnvs;
+  bool two = tiles > sms / n_jobs;
+  if (const char* e = getenv("GRACING_ACTOR_BACKWARD_GROUPS")) two = e[0] == '2';      // (A/B tests: the two variants must agree to accumulation order)
+  return two ? launch_actor_backward<NetLayout<128, 128>, 2>(jobs, n_jobs, rows, s) : launch_actor_backward<NetLayout<128, 128>, 1>(jobs, n_jobs, rows, s);
 }
 
 extern "C" int gr_actor_backward(const GrPolicy* policy, int32_t hidden, int32_t hidden2, const float* obs, const float* grad_actions,
                                  const float* scale, int64_t rows, const GrMlpGrad* out, void* stream) {
   if (!policy || !out) return GR_ERR_NULL;
   GrBackwardJob job;
-  job.policy = *policy; job.obs = obs; job.grad_actions = grad_actions; job.scale = scale; job.out = *out;
+  job.policy = *policy; job.obs = obs; job.grad_actions = grad_actions; job.scale = scale; job.out = *out; job.indices = nullptr;
   return gr_actor_backward_jobs(&job, 1, hidden, hidden2, rows, stream);
 }

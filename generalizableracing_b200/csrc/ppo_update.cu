@@ -15,8 +15,8 @@ constexpr int kFwdGroups = 2;                // two 128-row tiles in flight per 
 
 // mu [rows,4], value [rows]: persistent over 128-row tiles, both nets resident in shared memory
 __global__ void __launch_bounds__(kFwdGroups * kTileEnvs, 1) policy_forward_kernel(const GrPolicy pol, const float* __restrict__ obs,
-                                                                                  const float* __restrict__ critic_obs, float* __restrict__ mu,
-                                                                                  float* __restrict__ value, const int64_t R) {
+                                                                                  const float* __restrict__ critic_obs, const int64_t* __restrict__ idx,
+                                                                                  float* __restrict__ mu, float* __restrict__ value, const int64_t R) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* w_smem = smem;
   uint8_t* h_smem = smem + 2 * NLp::kNetBytes;
@@ -46,8 +46,9 @@ __global__ void __launch_bounds__(kFwdGroups * kTileEnvs, 1) policy_forward_kern
     const bool live = tile < tiles && r < R;
     float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0, o2 = o0, o3 = o0, c0 = o0, c1 = o0, c2 = o0, c3 = o0;
     if (live) {
-      const float4* xo = reinterpret_cast<const float4*>(obs) + r * 4;
-      const float4* xc = reinterpret_cast<const float4*>(critic_obs) + r * 4;
+      const int64_t q = idx ? __ldg(idx + r) : r;              // mini-batch gather on load (rollout_storage.py:179-187)
+      const float4* xo = reinterpret_cast<const float4*>(obs) + q * 4;
+      const float4* xc = reinterpret_cast<const float4*>(critic_obs) + q * 4;
       o0 = __ldcs(xo); o1 = __ldcs(xo + 1); o2 = __ldcs(xo + 2); o3 = __ldcs(xo + 3);
       c0 = __ldcs(xc); c1 = __ldcs(xc + 1); c2 = __ldcs(xc + 2); c3 = __ldcs(xc + 3);
     }
@@ -84,9 +85,10 @@ __global__ void __launch_bounds__(256) ppo_loss_grad_kernel(const GrPpoBatch b, 
   float max_gm = 0.0f, max_gv = 0.0f;
   if (r < R) {
     const float inv_rows = 1.0f / (float)R;
-    const float4 mu = __ldg(reinterpret_cast<const float4*>(b.mu) + r), a = __ldg(reinterpret_cast<const float4*>(b.actions) + r);
+    const int64_t q = b.indices ? __ldg(b.indices + r) : r;    // row of the stored columns (gather on load)
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(b.mu) + r), a = __ldg(reinterpret_cast<const float4*>(b.actions) + q);
     const float4 sg = __ldg(reinterpret_cast<const float4*>(b.sigma));
-    const float4 omu = __ldg(reinterpret_cast<const float4*>(b.old_mu) + r), osg = __ldg(reinterpret_cast<const float4*>(b.old_sigma) + r);
+    const float4 omu = __ldg(reinterpret_cast<const float4*>(b.old_mu) + q), osg = __ldg(reinterpret_cast<const float4*>(b.old_sigma) + q);
     const float mus[4] = {mu.x, mu.y, mu.z, mu.w}, as[4] = {a.x, a.y, a.z, a.w}, sgs[4] = {sg.x, sg.y, sg.z, sg.w};
     const float omus[4] = {omu.x, omu.y, omu.z, omu.w}, osgs[4] = {osg.x, osg.y, osg.z, osg.w};
     // log-prob of the stored action under the current policy (Normal.log_prob summed over the action dims), KL(old || new) (ppo.py:126-129)
@@ -98,18 +100,18 @@ __global__ void __launch_bounds__(256) ppo_loss_grad_kernel(const GrPpoBatch b, 
       const float dm = omus[k] - mus[k];
       kl += logf(sgs[k] / osgs[k] + 1.0e-5f) + (osgs[k] * osgs[k] + dm * dm) / (2.0f * sgs[k] * sgs[k]) - 0.5f;
     }
-    const float adv = b.advantages[r];
-    const float ratio = expf(logp - b.old_log_prob[r]);
+    const float adv = b.advantages[q];
+    const float ratio = expf(logp - b.old_log_prob[q]);
     const float s1 = -adv * ratio;
     const float s2 = -adv * fminf(fmaxf(ratio, 1.0f - b.clip_param), 1.0f + b.clip_param);
     const float surrogate = fmaxf(s1, s2);
     // d max(s1, s2) / d logp: s1 carries -adv * ratio; s2 carries it only inside the clip range (where s1 == s2: the tie's two halves add up)
     const float g_logp = (s1 >= s2 ? -adv * ratio : 0.0f) * inv_rows;
     // value loss (ppo.py:153-160)
-    const float v = b.value[r], ret = b.returns[r];
+    const float v = b.value[r], ret = b.returns[q];
     float vloss, g_v;
     if (b.use_clipped_value_loss) {
-      const float ov = b.old_values[r];
+      const float ov = b.old_values[q];
       const float dv = v - ov;
       const bool inside = dv >= -b.clip_param && dv <= b.clip_param;     // torch.clamp passes the gradient at the bounds
       const float vc = ov + fminf(fmaxf(dv, -b.clip_param), b.clip_param);
@@ -239,7 +241,8 @@ __global__ void __launch_bounds__(256) adam_apply_kernel(const GrAdamStep a) {
 
 using namespace gr;
 
-extern "C" int gr_policy_forward(const GrPolicy* policy, const float* obs, const float* critic_obs, float* mu, float* value, int64_t rows, void* stream) {
+extern "C" int gr_policy_forward_gather(const GrPolicy* policy, const float* obs, const float* critic_obs, const int64_t* indices, float* mu, float* value,
+                                        int64_t rows, void* stream) {
   if (!policy || !policy->packed || !obs || !critic_obs || !mu || !value) return GR_ERR_NULL;
   if (rows <= 0) return GR_ERR_SIZE;
   if (policy->negative_slope < 0.0f || policy->negative_slope > 1.0f) return GR_ERR_CONFIG;
@@ -252,8 +255,12 @@ extern "C" int gr_policy_forward(const GrPolicy* policy, const float* obs, const
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t pairs = ((rows + kTileEnvs - 1) / kTileEnvs + kFwdGroups - 1) / kFwdGroups;
   const int grid = (int)(pairs < sms ? pairs : sms);
-  policy_forward_kernel<<<grid, kFwdGroups * kTileEnvs, bytes, reinterpret_cast<cudaStream_t>(stream)>>>(*policy, obs, critic_obs, mu, value, rows);
+  policy_forward_kernel<<<grid, kFwdGroups * kTileEnvs, bytes, reinterpret_cast<cudaStream_t>(stream)>>>(*policy, obs, critic_obs, indices, mu, value, rows);
   return (int)cudaGetLastError();
+}
+
+extern "C" int gr_policy_forward(const GrPolicy* policy, const float* obs, const float* critic_obs, float* mu, float* value, int64_t rows, void* stream) {
+  return gr_policy_forward_gather(policy, obs, critic_obs, nullptr, mu, value, rows, stream);
 }
 
 extern "C" int gr_adam_clip_step(const GrAdamStep* a, void* stream) {

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GR_ABI_VERSION 2
+#define GR_ABI_VERSION 3
 
 /* ---- layout constants (mirrored by generalizableracing_b200/layout.py) ---- */
 #define GR_OBS_DIM 16
@@ -374,7 +374,8 @@ typedef struct GrMlpGrad {           /* shapes as GrMlp, fp32; w3 [out_dim, hidd
 int gr_actor_backward(const GrPolicy* policy, int32_t hidden, int32_t hidden2, const float* obs /* [rows,16] */,
                       const float* grad_actions /* [rows,4] */, const float* scale, int64_t rows, const GrMlpGrad* out, void* stream);
 /* one launch for up to two nets of the same widths over the same number of rows (a PPO step's actor and critic) */
-typedef struct GrBackwardJob { GrPolicy policy; const float* obs; const float* grad_actions; const float* scale; GrMlpGrad out; } GrBackwardJob;
+/* indices (optional, [rows] int64): row r reads obs[indices[r]] -- the mini-batch gather of rollout_storage.py:179-187 done on load */
+typedef struct GrBackwardJob { GrPolicy policy; const float* obs; const float* grad_actions; const float* scale; GrMlpGrad out; const int64_t* indices; } GrBackwardJob;
 int gr_actor_backward_jobs(const GrBackwardJob* jobs, int32_t n_jobs, int32_t hidden, int32_t hidden2, int64_t rows, void* stream);
 
 /* ---- PPO update on the kernels (forward, loss gradients; the weight gradients come from gr_actor_backward) -----------------
@@ -386,6 +387,10 @@ int gr_actor_backward_jobs(const GrBackwardJob* jobs, int32_t n_jobs, int32_t hi
  * followed by two gr_actor_backward launches (actor with d/d(mu), critic with d/d(v)). */
 int gr_policy_forward(const GrPolicy* policy /* packed actor + critic, widths (128,128) */, const float* obs, const float* critic_obs,
                       float* mu /* [rows,4] */, float* value /* [rows] */, int64_t rows, void* stream);
+/* the same with the mini-batch gather on load: row r evaluates obs[indices[r]] / critic_obs[indices[r]] (indices [rows] int64 into the flattened
+ * [T*N] transitions of the rollout storage, as gr_storage_gather takes them); mu / value are dense [rows] */
+int gr_policy_forward_gather(const GrPolicy* policy, const float* obs, const float* critic_obs, const int64_t* indices, float* mu, float* value,
+                             int64_t rows, void* stream);
 typedef struct GrPpoBatch {
   const float* mu; const float* value;                 /* current policy outputs [rows,4], [rows] */
   const float* sigma;                                  /* device [4]: current action std */
@@ -393,6 +398,8 @@ typedef struct GrPpoBatch {
   const float* old_mu; const float* old_sigma;         /* [rows,4] each */
   float clip_param, value_loss_coef, entropy_coef;
   int32_t use_clipped_value_loss;
+  const int64_t* indices;                              /* optional [rows] int64: the STORED columns (actions .. old_sigma) are read at row indices[r]
+                                                          (the mini-batch gather done on load); mu / value and the gradients stay dense */
 } GrPpoBatch;
 int gr_ppo_loss_grad(const GrPpoBatch* batch, int64_t rows, float* grad_mu /* [rows,4] */, float* grad_value /* [rows,4] */,
                      float* sums /* [16] accumulated */, void* stream);

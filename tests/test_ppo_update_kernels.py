@@ -169,3 +169,52 @@ def test_adam_clip_step_matches_torch(cuda_lib):
         for p, q in zip(ref, mine):
             assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), (it, float((p - q).abs().max()))
     assert abs(float(state[5]) - 6 * 0.09) < 1e-5 and abs(float(state[6]) - 6 * 0.07) < 1e-5
+
+
+@pytest.mark.parametrize("rows,pool", [(1000, 5000), (24576 + 5, 98304), (128 * 149, 400000)])
+def test_gather_on_load_equals_gather_then_dense(cuda_lib, rows, pool):
+    """The mini-batch gather of rollout_storage.py:179-187 done on load (`indices` of gr_policy_forward_gather, GrPpoBatch, GrBackwardJob)
+    against the same kernels on rows gathered beforehand: identical arithmetic on identical values, so forward outputs and loss
+    gradients are bit-identical and the weight gradients agree to accumulation order."""
+    from generalizableracing_b200 import _lib as B
+    from generalizableracing_b200.modules import ActorCritic
+    lib = cuda_lib
+    torch.manual_seed(rows)
+    pol = ActorCritic(16, 16, 4).cuda()
+    la, lc = [m for m in pol.actor if isinstance(m, torch.nn.Linear)], [m for m in pol.critic if isinstance(m, torch.nn.Linear)]
+    mk = lambda l, out: B.GrMlp(l[0].weight.data_ptr(), l[0].bias.data_ptr(), l[1].weight.data_ptr(), l[1].bias.data_ptr(), l[2].weight.data_ptr(), l[2].bias.data_ptr(), 16, 128, 128, out)
+    packed = torch.zeros(int(lib.gr_policy_packed_bytes(128, 128, 2)), dtype=torch.uint8, device="cuda")
+    a, c = mk(la, 4), mk(lc, 1)
+    st = torch.cuda.current_stream().cuda_stream
+    B.check(lib.gr_policy_pack(C.byref(a), C.byref(c), packed.data_ptr(), st), "pack")
+    sigma = torch.full((4,), 0.8, device="cuda")
+    p = B.GrPolicy(packed.data_ptr(), sigma.data_ptr(), 0.01)
+    rn = lambda *s: torch.randn(*s, device="cuda")
+    S = dict(obs=rn(pool, 16) * 3, cobs=rn(pool, 16) * 3, actions=rn(pool, 4), logp=rn(pool), adv=rn(pool), ret=rn(pool), val=rn(pool), mu=rn(pool, 4),
+             sig=(0.5 + torch.rand(pool, 4, device="cuda")))
+    idx = torch.randperm(pool, device="cuda")[:rows].contiguous()
+    D = {k: v[idx].contiguous() for k, v in S.items()}
+    out = {}
+    for mode, T, ip in (("dense", D, None), ("gather", S, idx.data_ptr())):
+        mu, val = torch.zeros(rows, 4, device="cuda"), torch.zeros(rows, device="cuda")
+        B.check(lib.gr_policy_forward_gather(C.byref(p), T["obs"].data_ptr(), T["cobs"].data_ptr(), ip, mu.data_ptr(), val.data_ptr(), rows, st), "fwd")
+        gm, gv, sums = torch.zeros(rows, 4, device="cuda"), torch.zeros(rows, 4, device="cuda"), torch.zeros(16, device="cuda")
+        b = B.GrPpoBatch(mu.data_ptr(), val.data_ptr(), sigma.data_ptr(), T["actions"].data_ptr(), T["logp"].data_ptr(), T["adv"].data_ptr(), T["ret"].data_ptr(),
+                         T["val"].data_ptr(), T["mu"].data_ptr(), T["sig"].data_ptr(), 0.2, 1.0, 0.01, 1, ip)
+        B.check(lib.gr_ppo_loss_grad(C.byref(b), rows, gm.data_ptr(), gv.data_ptr(), sums.data_ptr(), st), "loss")
+        grads = [torch.zeros_like(t) for l in (la, lc) for m in l for t in (m.weight, m.bias)]
+        ga = B.GrMlpGrad(*(t.data_ptr() for t in grads[:6]), 4, 1)
+        gc = B.GrMlpGrad(*(t.data_ptr() for t in grads[6:]), 1, 1)
+        pc = B.GrPolicy(packed.data_ptr() + packed.numel() // 2, sigma.data_ptr(), 0.01)
+        jobs = (B.GrBackwardJob * 2)(B.GrBackwardJob(p, T["obs"].data_ptr(), gm.data_ptr(), sums.data_ptr() + 32, ga, ip),
+                                     B.GrBackwardJob(pc, T["cobs"].data_ptr(), gv.data_ptr(), sums.data_ptr() + 36, gc, ip))
+        B.check(lib.gr_actor_backward_jobs(jobs, 2, 128, 128, rows, st), "bwd")
+        torch.cuda.synchronize()
+        out[mode] = (mu, val, gm, gv, sums[:8].clone(), grads)
+    d, g = out["dense"], out["gather"]
+    for k in range(4):
+        assert torch.equal(d[k], g[k]), k
+    assert torch.allclose(d[4], g[4], rtol=1e-5, atol=1e-6)          # sums: atomics in any order
+    for x, y in zip(d[5], g[5]):
+        assert float((x - y).abs().max()) <= 2e-5 * float(x.abs().max()) + 1e-12
+        assert float(x.abs().max()) > 0
