@@ -52,7 +52,8 @@ class GrStepIO(C.Structure):
     _fields_ = [("action", c_p), ("obs", c_p), ("critic_obs", c_p), ("aux_obs", c_p), ("reward", c_p),
                 ("terminated", c_p), ("time_out", c_p), ("dones", c_p), ("reward_terms", c_p), ("gate_passed", c_p),
                 ("loss", c_p), ("loss_terms", c_p), ("tape", c_p), ("tape_stride", C.c_int64), ("phase_times", c_p), ("log_accum", c_p),
-                ("aligned_states", c_p), ("acc", c_p), ("dones_u8", c_p)]
+                ("aligned_states", c_p), ("acc", c_p), ("dones_u8", c_p),
+                ("pre_reset_pos", c_p), ("pre_reset_quat", c_p)]
 
 
 class GrBwdIO(C.Structure):

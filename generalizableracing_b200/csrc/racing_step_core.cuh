@@ -396,6 +396,12 @@ __device__ __forceinline__ bool racing_step_body(const GrConfig& cfg, const Trac
     if (io.acc) { io.acc[(int64_t)i * 3] = acc.x; io.acc[(int64_t)i * 3 + 1] = acc.y; io.acc[(int64_t)i * 3 + 2] = acc.z; }
   }
 
+  if (io.pre_reset_pos && active) {                  // pose the reward terms see (mesh collision term: a separate launch on this snapshot)
+    float* __restrict__ pp = io.pre_reset_pos + (int64_t)i * 3;
+    pp[0] = e.w.x; pp[1] = e.w.y; pp[2] = e.w.z;
+    if (io.pre_reset_quat) __stcs(reinterpret_cast<float4*>(io.pre_reset_quat) + i, pack(q1));
+  }
+
   // ---- 4./5. counters + terminations (QD/mdp/termination.py:15-33; Isaac Lab mdp.time_out) ----
   e.eplen += 1;
   const bool time_out = e.eplen >= cfg.max_episode_length;

@@ -197,6 +197,10 @@ class RacingVecEnv:
         # (manager_based_diff_rl_env.py:205-212; detached values -- nothing outside the reference's own LossManager consumes them)
         self.export_aligned_states = False
         self._loss_term_names = L.LOSS_TERM_NAMES
+        # opt-in: the STAGE-0 reward term collision_penalty_custom (QD/mdp/rewards.py:226-242, weight -50: QD/racing_ctbr_env.py:299-303)
+        # against a terrain mesh -- see set_terrain_mesh()
+        self._terrain_mesh = None
+        self._w_collision = 0.0
         # ---- BPTT window (cfg.is_differentiable_physics)
         self._bptt = None
         if cfg.is_differentiable_physics:
@@ -423,10 +427,24 @@ class RacingVecEnv:
             self._lib.gr_host_pipe_destroy(self._pipe)
             self._pipe = None
 
+    def set_terrain_mesh(self, mesh, weight: float = -50.0):
+        """Add the reference's mesh-collision reward term to ``step``: ``reward += weight * dt * (lattice points inside the mesh > 2)``
+        (QD/mdp/rewards.py:226-242; weight -50 in STAGE 0, QD/racing_ctbr_env.py:299-303), evaluated like every reward term on the
+        pose after the step's physics and BEFORE any reset (the step kernel exports that pose, ``GrStepIO.pre_reset_pos / _quat``;
+        the ray casts are one more launch, ``gr_uav_collision_ray``).  ``mesh``: a :class:`..mesh.TerrainMesh` in the world frame of
+        ``terrain_origins``; None switches the term off.  The term's value of the last step is ``extras["collision_penalty"]``; it is not
+        part of the in-kernel episode sums (``Episode_Reward/*``)."""
+        self._terrain_mesh, self._w_collision = mesh, float(weight)
+        self._ios = None
+        if mesh is not None and not hasattr(self, "_pre_pose"):
+            self._pre_pose = (torch.zeros(self.num_envs, 3, device=self.device), torch.zeros(self.num_envs, 4, device=self.device))
+
     def _make_io(self, o) -> B.GrStepIO:
         io = B.GrStepIO()
         io.obs, io.critic_obs, io.aux_obs = o["obs"].data_ptr(), o["critic"].data_ptr(), o["aux"].data_ptr()
         io.reward, io.terminated, io.time_out, io.dones = o["reward"].data_ptr(), o["terminated"].data_ptr(), o["time_out"].data_ptr(), o["dones"].data_ptr()
+        if self._terrain_mesh is not None:
+            io.pre_reset_pos, io.pre_reset_quat = self._pre_pose[0].data_ptr(), self._pre_pose[1].data_ptr()
         return io
 
     def step(self, actions: torch.Tensor, rnd: Optional[torch.Tensor] = None):
@@ -466,6 +484,11 @@ class RacingVecEnv:
             self._params_edited = False
         self._last = o
         ex = self.extras
+        if self._terrain_mesh is not None:
+            from .mesh import collision_penalty_custom
+            pen = collision_penalty_custom(self._terrain_mesh, self._pre_pose[0], self._pre_pose[1])
+            (w_reward if self._bptt is not None else o["reward"]).add_(pen, alpha=self._w_collision * self.step_dt)
+            ex["collision_penalty"] = pen
         dict.pop(ex, "log", None)
         to, term, obs_dict = self._views[k]
         ex["observations"] = obs_dict

@@ -166,6 +166,9 @@ typedef struct GrStepIO {
                                (L/envs/manager_based_diff_rl_env.py:205-212)                                  optional */
   float* acc;               /* [N,3] extras["acc"]: world linear acceleration of the step (droneDynamics.py:126) optional */
   uint8_t* dones_u8;        /* [N] terminated | time_out as one byte (RolloutStorage keeps dones as bytes)   optional */
+  float* pre_reset_pos;     /* [N,3] world position after this step's physics, BEFORE any reset: the state the reward terms see
+                               (input of collision_penalty_custom, QD/mdp/rewards.py:226-242 -> gr_uav_collision_ray)  optional */
+  float* pre_reset_quat;    /* [N,4] attitude (w,x,y,z) at the same instant                                           optional */
 } GrStepIO;
 
 #define GR_LOG_NUM_RESET 0          /* number of envs reset in this step                          */

@@ -129,7 +129,7 @@ def test_collision_counts_match_the_oracle(backend):
     pts, faces = _scene(0)
     mesh = M.TerrainMesh(pts, faces, device=device, _lib=lib)
     rng = np.random.default_rng(5)
-    n = 400
+    n = 240
     pos = np.stack([rng.uniform(-9, 9, n), rng.uniform(-9, 9, n), rng.uniform(-0.3, 3.5, n)], 1).astype(np.float32)
     quat = _rand_quat(rng, n)
     lat = M.LATTICE_TENSOR
@@ -229,3 +229,40 @@ def test_collision_at_c4_size_properties(cuda_lib):
     k = torch.arange(0, N, 331, device="cuda")
     want, margins = O.uav_collision_num_ray(pts, faces, pos[k].cpu().numpy(), quat[k].cpu().numpy(), 0.09, 0.05, 1e3, M.LATTICE_TENSOR.numpy())
     _assert_counts(num[k].cpu().numpy(), want, margins, "c4 sample")
+
+
+@pytest.mark.parametrize("backend", backend_params(), indirect=True)
+def test_env_step_adds_the_collision_term_on_the_pre_reset_pose(backend):
+    """RacingVecEnv.set_terrain_mesh: reward += -50 * dt * collision_penalty_custom(pose after the step's physics, before any reset)
+    (QD/racing_ctbr_env.py:299-303, QD/mdp/rewards.py:226-242); everything else of the step is untouched."""
+    from generalizableracing_b200.config import RacingCfg
+    from generalizableracing_b200.env import RacingVecEnv
+    from generalizableracing_b200.tracks import GateTable
+    device, lib = backend
+    full = synthetic_track_table()
+    table = GateTable(full.gate_pose[:2, :2].copy(), full.next_gate_id[:2, :2].copy(), full.terrain_origins[:2, :2].copy(), "2x2 tiles")
+    cfg, N = RacingCfg.for_stage(0), 48
+    pts, faces = M.track_table_mesh(table)                     # 4 tiles: the brute-force oracle stays fast
+    mesh = M.TerrainMesh(pts, faces, device=device, _lib=lib)
+    a, b = (RacingVecEnv(cfg, table, N, device=device, seed=11, _lib=lib) for _ in range(2))
+    b.set_terrain_mesh(mesh, -50.0)
+    a.reset(); b.reset()
+    g = torch.Generator().manual_seed(3)
+    hits = resets = 0
+    for t in range(48):
+        act = (torch.randn(N, 4, generator=g) * (0.5 if t % 3 else 2.5)).to(device)
+        oa, ra, da, _ = a.step(act)
+        ob, rb, db, ex = b.step(act)
+        pen = ex["collision_penalty"]
+        assert torch.equal(oa, ob) and torch.equal(da, db)
+        assert torch.equal(rb, ra + pen * (-50.0 * cfg.step_dt))
+        pos, quat = b._pre_pose
+        if t % 4 == 3:
+            want, margins = O.collision_penalty_custom(pts, faces, pos.cpu().numpy(), quat.cpu().numpy(), M.LATTICE_TENSOR.numpy())
+            assert (pen.cpu().numpy() != want).sum() <= 1
+        sv = b.state_dict_view()
+        keep = ~db.bool()                                       # envs that did not reset: the exported pose IS the stored state
+        assert torch.equal(sv["root_pos_w"][keep], pos[keep]) and torch.equal(sv["root_quat_w"][keep], quat[keep])
+        hits += int(pen.sum()); resets += int(db.sum())
+    assert hits > 0 and resets > 0
+    assert torch.equal(a.planes, b.planes)
