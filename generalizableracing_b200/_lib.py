@@ -122,6 +122,11 @@ class GrPpoBatch(C.Structure):
                 ("use_clipped_value_loss", c_i), ("indices", c_p)]
 
 
+class GrPpoStep(C.Structure):
+    _fields_ = [("policy", GrPolicy), ("obs", c_p), ("critic_obs", c_p), ("batch", GrPpoBatch), ("actor_grad", GrMlpGrad), ("critic_grad", GrMlpGrad),
+                ("sums", c_p), ("cotangent_scale", c_f)]
+
+
 class GrHostStep(C.Structure):
     _fields_ = [("action", c_p), ("obs", c_p), ("reward", c_p), ("dones", c_p), ("critic_obs", c_p), ("time_out", c_p), ("dones_u8", c_p)]
 
@@ -201,6 +206,7 @@ PROTOTYPES = {
     "gr_policy_forward": (C.c_int, [C.POINTER(GrPolicy), c_p, c_p, c_p, c_p, C.c_int64, c_p]),
     "gr_policy_forward_gather": (C.c_int, [C.POINTER(GrPolicy), c_p, c_p, c_p, c_p, c_p, C.c_int64, c_p]),
     "gr_ppo_loss_grad": (C.c_int, [C.POINTER(GrPpoBatch), C.c_int64, c_p, c_p, c_p, c_p]),
+    "gr_ppo_fused_step": (C.c_int, [C.POINTER(GrPpoStep), C.c_int64, c_p]),
     "gr_adam_clip_step": (C.c_int, [C.POINTER(GrAdamStep), c_p]),
     "gr_actor_backward_jobs": (C.c_int, [C.POINTER(GrBackwardJob), c_i, c_i, c_i, C.c_int64, c_p]),
     "gr_reach_reset": (C.c_int, [C.POINTER(GrReachConfig), C.POINTER(GrReachState), C.POINTER(GrRandom), c_p, c_p, c_p]),

@@ -20,6 +20,7 @@
 #include <cstdlib>
 
 #include "mlp_tc.cuh"
+#include "ppo_loss.cuh"
 
 namespace gr {
 
@@ -79,8 +80,18 @@ __device__ __forceinline__ uint64_t desc_rows_mn(uint32_t addr) { return make_sm
 // pipe activity, 14 % issue-slot use).  The weight-gradient accumulators are shared by the groups -- a single thread issues all MMAs,
 // so the accumulations are ordered -- and each group owns 128 scratch columns.  TMEM: 16 -> 128 -> 128: 2 x 128 scratch + 128 (dW2) +
 // 32 (dW1|db1) + 16 (dW3) + 16 (db2) = 448 columns, two groups; 16 -> 256 -> 128: 128 + 256 + 64 + 32 = 480 columns, one group.
-template <class NL, int kGroups>
-__global__ void __launch_bounds__(kGroups * kTileEnvs + 32, 1) actor_backward_kernel(const GrBackwardJob job0, const GrBackwardJob job1, const int64_t R) {
+//
+// kPpo (gr_ppo_fused_step): the same kernel with the PPO mini-batch step's forward head and loss inside.  One more stage per tile -- layer 3
+// (N = 16) on the recomputed H2 -- gives the row's mean (job 0: actor) or value (job 1: critic); the row's thread evaluates the loss of
+// ppo_loss.cuh on it and on the stored columns it fetched at the start of the tile, and writes the cotangent row itself.  The separate
+// gr_policy_forward / gr_ppo_loss_grad launches and their mu / value / gradient round trips through HBM disappear.  The cotangent goes to
+// fp16 with a STATIC scale (fz.cot_scale x the un-normalised per-row gradient, 1 / rows applied to the fp32 accumulators at the flush):
+// the batch maximum the stand-alone path scales by would need a grid-wide reduction between the loss and the weight gradients.
+struct PpoFusedArgs { GrPpoBatch b; float* sums; float cot_scale; };
+
+template <class NL, int kGroups, bool kPpo>
+__global__ void __launch_bounds__(kGroups * kTileEnvs + 32, 1) actor_backward_kernel(const GrBackwardJob job0, const GrBackwardJob job1, const int64_t R,
+                                                                                    const PpoFusedArgs fz) {
   const GrBackwardJob& job = blockIdx.y == 0 ? job0 : job1;
   const GrPolicy pol = job.policy;
   const float* __restrict__ X = job.obs;
@@ -93,7 +104,7 @@ __global__ void __launch_bounds__(kGroups * kTileEnvs + 32, 1) actor_backward_ke
   // tensor memory: one scratch accumulator per group | dW2 [H2 x H1] | dW1 (+ db1) [H1 x 32] as `kHalves` blocks | dW3^T [H2 x 16] | db2 [H2 x 16]
   constexpr uint32_t kColD = 0, kColW2 = 128 * kGroups, kColW1 = kColW2 + H1, kColW3 = kColW1 + 32 * kHalves, kColB2 = kColW3 + 16, kColsUsed = kColB2 + 16;
   static_assert(kColsUsed <= 512, "tensor memory budget");
-  constexpr int kStages = 2 * kHalves + 3;                  // forward L1 (per half), forward L2, dW3 | dH2, dW2 | db2 | dH1 (per half), dW1
+  constexpr int kStages = 2 * kHalves + 3 + (kPpo ? 1 : 0); // forward L1 (per half), forward L2, [forward L3], dW3 | dH2, dW2 | db2 | dH1 (per half), dW1
   constexpr int kGroupBytes = (4 + H1 / 8 + H2 / 8 + 2) * kChunkA;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* w_smem = smem;                                   // forward-packed net
@@ -133,31 +144,68 @@ __global__ void __launch_bounds__(kGroups * kTileEnvs + 32, 1) actor_backward_ke
   const uint32_t tm = *tmem_slot;
   const int64_t tiles = (R + kTileEnvs - 1) / kTileEnvs;
   const int64_t stride = (int64_t)gridDim.x * kGroups;
-  const float scale = out.scale_is_maxabs ? 1024.0f / fmaxf(__ldg(scale_ptr), 1e-30f) : __ldg(scale_ptr);
+  const float inv_rows = 1.0f / (float)R;
+  const float scale = kPpo ? fz.cot_scale : (out.scale_is_maxabs ? 1024.0f / fmaxf(__ldg(scale_ptr), 1e-30f) : __ldg(scale_ptr));
+  const bool critic_job = blockIdx.y != 0;
 
   if (producer) {
     const uint32_t lane_sel = (uint32_t)((row >> 5) * 32) << 16;
     const uint32_t d_addr = tm + kColD + 128u * grp + lane_sel;
     const __half2 slope = __float2half2_rn(pol.negative_slope);
     float4 gsum = make_float4(0.f, 0.f, 0.f, 0.f);          // db3 = sum of the (unscaled) cotangent rows
+    float lsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // kPpo: this thread's share of gr_ppo_loss_grad's sums
     uint32_t ph = 0u;
     // one stage hand-over: operands written -> arrive; wait for the stage's MMAs
 #define GR_HANDOVER() do { fence_proxy_async_smem(); tc_fence_before_sync(); mbar_arrive(&full[grp]); mbar_wait(&done[grp], ph); ph ^= 1u; tc_fence_after_sync(); } while (0)
+    // the rows of a tile: observation row, and either the cotangent row (plain backward) or the stored columns of the row (kPpo).  The rows of
+    // the NEXT tile are fetched while this one is processed: with the mini-batch gather on load every row is a scattered 64-byte read (plus
+    // five scattered scalars / 16-byte rows under kPpo), and one tile at a time per group leaves nothing else to hide that latency behind
+    // (ncu before this: long-scoreboard 11 of 16 stall cycles per issue)
+    struct TileRows {
+      float4 o0, o1, o2, o3, gr4, st_a, st_omu, st_osg;
+      float st_adv, st_logp, st_ret, st_ov;
+    };
+    auto fetch = [&](const int64_t tile, TileRows& t) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      t.o0 = t.o1 = t.o2 = t.o3 = t.gr4 = t.st_a = t.st_omu = z;
+      t.st_osg = make_float4(1.f, 1.f, 1.f, 1.f);
+      t.st_adv = t.st_logp = t.st_ret = t.st_ov = 0.f;
+      const int64_t r = tile * kTileEnvs + row;
+      if (r >= R) return;
+      const int64_t q = idx ? __ldg(idx + r) : r;                                  // (mini-batch gather on load)
+      const float4* xr = reinterpret_cast<const float4*>(X) + q * 4;
+      t.o0 = __ldcs(xr); t.o1 = __ldcs(xr + 1); t.o2 = __ldcs(xr + 2); t.o3 = __ldcs(xr + 3);
+      if (!kPpo) {
+        t.gr4 = __ldcs(reinterpret_cast<const float4*>(G) + r);
+      } else if (!critic_job) {
+        t.st_a = __ldg(reinterpret_cast<const float4*>(fz.b.actions) + q);
+        t.st_omu = __ldg(reinterpret_cast<const float4*>(fz.b.old_mu) + q);
+        t.st_osg = __ldg(reinterpret_cast<const float4*>(fz.b.old_sigma) + q);
+        t.st_adv = __ldg(fz.b.advantages + q);
+        t.st_logp = __ldg(fz.b.old_log_prob + q);
+      } else {
+        t.st_ret = __ldg(fz.b.returns + q);
+        if (fz.b.use_clipped_value_loss) t.st_ov = __ldg(fz.b.old_values + q);
+      }
+    };
+    TileRows cur = {}, nxt = {};
+    {
+      const int64_t first_tile = (int64_t)blockIdx.x * kGroups + grp;
+      if (first_tile < tiles) fetch(first_tile, cur);
+    }
 #pragma unroll 1
     for (int64_t tile = (int64_t)blockIdx.x * kGroups + grp; tile < tiles; tile += stride) {
       const int64_t r = tile * kTileEnvs + row;
-      // ---- operands of this tile: observation row (+ bias ones), scaled cotangent row
-      float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0, o2 = o0, o3 = o0, gr4 = o0;
-      if (r < R) {
-        const float4* xr = reinterpret_cast<const float4*>(X) + (idx ? __ldg(idx + r) : r) * 4;      // (mini-batch gather on load)
-        o0 = __ldcs(xr); o1 = __ldcs(xr + 1); o2 = __ldcs(xr + 2); o3 = __ldcs(xr + 3);
-        gr4 = __ldcs(reinterpret_cast<const float4*>(G) + r);
-      }
-      gsum.x += gr4.x; gsum.y += gr4.y; gsum.z += gr4.z; gsum.w += gr4.w;
+      if (tile + stride < tiles) fetch(tile + stride, nxt);
+      const float4 o0 = cur.o0, o1 = cur.o1, o2 = cur.o2, o3 = cur.o3, gr4 = cur.gr4, st_a = cur.st_a, st_omu = cur.st_omu, st_osg = cur.st_osg;
+      const float st_adv = cur.st_adv, st_logp = cur.st_logp, st_ret = cur.st_ret, st_ov = cur.st_ov;
       // (the previous tile's last stage -- dW1 -- read xs and h1s: its hand-over waited for it)
       write_x_row(xs + row * 16, pack8(o0, o1), pack8(o2, o3));
-      *reinterpret_cast<uint4*>(das + row * 16) =
-          make_uint4(h2_bits(__floats2half2_rn(gr4.x * scale, gr4.y * scale)), h2_bits(__floats2half2_rn(gr4.z * scale, gr4.w * scale)), 0u, 0u);
+      if (!kPpo) {
+        gsum.x += gr4.x; gsum.y += gr4.y; gsum.z += gr4.z; gsum.w += gr4.w;
+        *reinterpret_cast<uint4*>(das + row * 16) =
+            make_uint4(h2_bits(__floats2half2_rn(gr4.x * scale, gr4.y * scale)), h2_bits(__floats2half2_rn(gr4.z * scale, gr4.w * scale)), 0u, 0u);
+      }
       // ---- forward layer 1 (128 units at a time) and layer 2: recompute the activations
 #pragma unroll 1
       for (int h = 0; h < kHalves; ++h) {
@@ -166,6 +214,40 @@ __global__ void __launch_bounds__(kGroups * kTileEnvs + 32, 1) actor_backward_ke
       }
       GR_HANDOVER();
       hidden_epilogue<true, H2>(d_addr, h2s + row * 16, reinterpret_cast<const uint4*>(w_smem + NL::kB2Off), slope);
+      if (kPpo) {
+        // ---- forward layer 3 -> this row's mean / value -> its loss gradient = the cotangent row (ppo.py:118-171, ppo_loss.cuh)
+        GR_HANDOVER();
+        uint32_t hr[4];
+        tmem_ld_x4(d_addr, hr);
+        tmem_ld_wait();
+        const float4 b3 = *reinterpret_cast<const float4*>(w_smem + NL::kB3Off);
+        float4 cot = make_float4(0.f, 0.f, 0.f, 0.f);          // un-normalised d(loss)/d(head); 1 / rows goes to the accumulators at the flush
+        if (r < R) {
+          if (!critic_job) {
+            const float4 mu = make_float4(__uint_as_float(hr[0]) + b3.x, __uint_as_float(hr[1]) + b3.y, __uint_as_float(hr[2]) + b3.z, __uint_as_float(hr[3]) + b3.w);
+            const float4 sg = __ldg(reinterpret_cast<const float4*>(fz.b.sigma));
+            const PpoActorRow ar = ppo_actor_row(mu, sg, st_a, st_omu, st_osg, st_adv, st_logp, fz.b.clip_param);
+            const float g_logp = ar.g_logp * inv_rows;
+            float gs[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float d = ar.d[k], inv_s = ar.inv_s[k];
+              (&cot.x)[k] = ar.g_logp * d * inv_s * inv_s;
+              gs[k] = g_logp * (d * d * inv_s * inv_s * inv_s - inv_s) - fz.b.entropy_coef * inv_rows * inv_s;
+            }
+            lsum[0] += ar.surrogate; lsum[2] += ar.kl; lsum[3] += gs[0]; lsum[4] += gs[1]; lsum[5] += gs[2]; lsum[6] += gs[3]; lsum[7] += 1.0f;
+          } else {
+            const PpoCriticRow cr = ppo_critic_row(__uint_as_float(hr[0]) + b3.x, st_ret, st_ov, fz.b.use_clipped_value_loss != 0, fz.b.clip_param);
+            cot.x = cr.g_v * fz.b.value_loss_coef;
+            lsum[1] += cr.vloss;
+          }
+        }
+        gsum.x += cot.x * inv_rows; gsum.y += cot.y * inv_rows; gsum.z += cot.z * inv_rows; gsum.w += cot.w * inv_rows;
+        const float hi = 60000.0f;                             // (fp16 saturation guard; |cotangent * scale| this large does not occur in practice)
+        *reinterpret_cast<uint4*>(das + row * 16) =
+            make_uint4(h2_bits(__floats2half2_rn(fminf(fmaxf(cot.x * scale, -hi), hi), fminf(fmaxf(cot.y * scale, -hi), hi))),
+                       h2_bits(__floats2half2_rn(fminf(fmaxf(cot.z * scale, -hi), hi), fminf(fmaxf(cot.w * scale, -hi), hi))), 0u, 0u);
+      }
       // ---- dW3^T += H2^T . dA ;  dH2 = dA . W3
       GR_HANDOVER();
       dact_epilogue(d_addr, h2s + row * 16, 0, slope);                    // h2s now holds dH2'
@@ -178,6 +260,7 @@ __global__ void __launch_bounds__(kGroups * kTileEnvs + 32, 1) actor_backward_ke
       }
       // ---- dW1 | db1 += dH1'^T . [X | 1 1 0..]: nothing to read back, but xs / h1s stay in use until it completes
       GR_HANDOVER();
+      cur = nxt;
     }
 #undef GR_HANDOVER
 #pragma unroll
@@ -191,74 +274,97 @@ __global__ void __launch_bounds__(kGroups * kTileEnvs + 32, 1) actor_backward_ke
       if (out.out_dim > 2) atomicAdd(out.b3 + 2, gsum.z);
       if (out.out_dim > 3) atomicAdd(out.b3 + 3, gsum.w);
     }
+    if (kPpo) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float v = lsum[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((row & 31) == 0 && v != 0.0f) atomicAdd(fz.sums + k, v);
+      }
+    }
   } else if (tid == kGroups * kTileEnvs) {
     // ---- the issuing thread: every MMA of the CTA, in program order
     const uint32_t w_addr = smem_u32(w_smem), ones_a = smem_u32(ones), grp0_a = smem_u32(grp_smem);
-    int64_t n_tiles[kGroups];
+    // The issuer serves whichever group has its next stage ready (non-blocking test of `full[g]`), each group at its own stage: a group
+    // that waits for its rows from HBM at the start of a tile does not hold the other one back (strict alternation did: ncu showed both
+    // groups' threads in their mbarrier waits half of the time with the tensor pipe 15-30 % busy).
+    int64_t left[kGroups];
     uint32_t ph[kGroups];
-    int64_t rounds = 0;
+    int stage[kGroups];
+    int active = 0;
 #pragma unroll
     for (int g = 0; g < kGroups; ++g) {
       const int64_t first_tile = (int64_t)blockIdx.x * kGroups + g;
-      n_tiles[g] = first_tile < tiles ? (tiles - first_tile + stride - 1) / stride : 0;
+      left[g] = first_tile < tiles ? (tiles - first_tile + stride - 1) / stride : 0;
       ph[g] = 0u;
-      rounds = n_tiles[g] > rounds ? n_tiles[g] : rounds;
+      stage[g] = 0;
+      active += left[g] > 0 ? 1 : 0;
     }
     bool acc_w3 = false, acc_w2 = false, acc_w1 = false;     // the shared accumulators have been written at least once
-#pragma unroll 1
-    for (int64_t j = 0; j < rounds; ++j) {
-#pragma unroll 1
-      for (int s = 0; s < kStages; ++s) {
+    while (active > 0) {
+      bool served = false;
 #pragma unroll
-        for (int g = 0; g < kGroups; ++g) {
-          if (j >= n_tiles[g]) continue;
-          const uint32_t xs_a = grp0_a + g * kGroupBytes, h1_a = xs_a + 4 * kChunkA, h2_a = h1_a + (H1 / 8) * kChunkA, da_a = h2_a + (H2 / 8) * kChunkA;
-          const uint32_t d_tm = tm + kColD + 128u * g;
-          mbar_wait(&full[g], ph[g]);
-          ph[g] ^= 1u;
-          tc_fence_after_sync();
-          if (s < kHalves) {                                   // forward layer 1, units [128 s, 128 s + 128)
+      for (int g = 0; g < kGroups; ++g) {
+        if (left[g] <= 0 || !mbar_test(&full[g], ph[g])) continue;
+        served = true;
+        ph[g] ^= 1u;
+        tc_fence_after_sync();
+        const int s = stage[g];
+        const uint32_t xs_a = grp0_a + g * kGroupBytes, h1_a = xs_a + 4 * kChunkA, h2_a = h1_a + (H1 / 8) * kChunkA, da_a = h2_a + (H2 / 8) * kChunkA;
+        const uint32_t d_tm = tm + kColD + 128u * g;
+        const int s_bwd = (kPpo && s > kHalves + 1) ? s - 1 : s;      // stage index in the plain backward's numbering
+        if (kPpo && s == kHalves + 1) {                      // forward layer 3 (N = 16): the head of the net
 #pragma unroll
-            for (int kk = 0; kk < kK1 / 16; ++kk)
-              mma_f16_ss(d_tm, desc_rows_k(xs_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW1Off + s * 128 * 16 + kk * 2 * (H1 * 16), H1 * 16, 128),
-                         make_idesc_f16(128, 128), kk > 0);
-          } else if (s == kHalves) {                           // forward layer 2
+          for (int kk = 0; kk < H2 / 16; ++kk)
+            mma_f16_ss(d_tm, desc_rows_k(h2_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW3Off + kk * 2 * (kOutPad * 16), kOutPad * 16, 128),
+                       make_idesc_f16(128, kOutPad), kk > 0);
+        } else if (s < kHalves) {                            // forward layer 1, units [128 s, 128 s + 128)
 #pragma unroll
-            for (int kk = 0; kk < H1 / 16; ++kk)
-              mma_f16_ss(d_tm, desc_rows_k(h1_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW2Off + kk * 2 * (H2 * 16), H2 * 16, 128),
-                         make_idesc_f16(128, H2), kk > 0);
-          } else if (s == kHalves + 1) {                       // dW3^T += H2^T . dA (rows are K: both operands MN-major) ; dH2 = dA . W3 (W3 as MN-major B)
+          for (int kk = 0; kk < kK1 / 16; ++kk)
+            mma_f16_ss(d_tm, desc_rows_k(xs_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW1Off + s * 128 * 16 + kk * 2 * (H1 * 16), H1 * 16, 128),
+                       make_idesc_f16(128, 128), kk > 0);
+        } else if (s == kHalves) {                           // forward layer 2
+#pragma unroll
+          for (int kk = 0; kk < H1 / 16; ++kk)
+            mma_f16_ss(d_tm, desc_rows_k(h1_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW2Off + kk * 2 * (H2 * 16), H2 * 16, 128),
+                       make_idesc_f16(128, H2), kk > 0);
+        } else if (s_bwd == kHalves + 1) {                   // dW3^T += H2^T . dA (rows are K: both operands MN-major) ; dH2 = dA . W3 (W3 as MN-major B)
+#pragma unroll
+          for (int kk = 0; kk < kTileEnvs / 16; ++kk)
+            mma_f16_ss(tm + kColW3, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(da_a + kk * 256), make_idesc_f16(H2, 16) | kMnA | kMnB, acc_w3 || kk > 0);
+          acc_w3 = true;
+          mma_f16_ss(d_tm, desc_rows_k(da_a), make_smem_desc(w_addr + NL::kW3Off, 128, kOutPad * 16), make_idesc_f16(128, H2) | kMnB, false);
+        } else if (s_bwd < 2 * kHalves + 2) {                // dW2 | db2 (first half only) ; dH1 units [128 h, 128 h + 128) = dH2' . W2 (W2 as MN-major B)
+          const int h = s_bwd - (kHalves + 2);
+          if (h == 0) {
+#pragma unroll
+            for (int kk = 0; kk < kTileEnvs / 16; ++kk) {
+              mma_f16_ss(tm + kColW2, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(h1_a + kk * 256), make_idesc_f16(H2, H1) | kMnA | kMnB, acc_w2 || kk > 0);
+              mma_f16_ss(tm + kColB2, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(ones_a + kk * 256), make_idesc_f16(H2, 16) | kMnA | kMnB, acc_w2 || kk > 0);
+            }
+            acc_w2 = true;
+          }
+#pragma unroll
+          for (int kk = 0; kk < H2 / 16; ++kk)
+            mma_f16_ss(d_tm, desc_rows_k(h2_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW2Off + h * 16 * (H2 * 16) + kk * 256, 128, H2 * 16),
+                       make_idesc_f16(128, 128) | kMnB, kk > 0);
+        } else {                                             // dW1 | db1 += dH1'^T . [X | 1 1 0..]
+#pragma unroll
+          for (int h = 0; h < kHalves; ++h)
 #pragma unroll
             for (int kk = 0; kk < kTileEnvs / 16; ++kk)
-              mma_f16_ss(tm + kColW3, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(da_a + kk * 256), make_idesc_f16(H2, 16) | kMnA | kMnB, acc_w3 || kk > 0);
-            acc_w3 = true;
-            mma_f16_ss(d_tm, desc_rows_k(da_a), make_smem_desc(w_addr + NL::kW3Off, 128, kOutPad * 16), make_idesc_f16(128, H2) | kMnB, false);
-          } else if (s < 2 * kHalves + 2) {                    // dW2 | db2 (first half only) ; dH1 units [128 h, 128 h + 128) = dH2' . W2 (W2 as MN-major B)
-            const int h = s - (kHalves + 2);
-            if (h == 0) {
-#pragma unroll
-              for (int kk = 0; kk < kTileEnvs / 16; ++kk) {
-                mma_f16_ss(tm + kColW2, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(h1_a + kk * 256), make_idesc_f16(H2, H1) | kMnA | kMnB, acc_w2 || kk > 0);
-                mma_f16_ss(tm + kColB2, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(ones_a + kk * 256), make_idesc_f16(H2, 16) | kMnA | kMnB, acc_w2 || kk > 0);
-              }
-              acc_w2 = true;
-            }
-#pragma unroll
-            for (int kk = 0; kk < H2 / 16; ++kk)
-              mma_f16_ss(d_tm, desc_rows_k(h2_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW2Off + h * 16 * (H2 * 16) + kk * 256, 128, H2 * 16),
-                         make_idesc_f16(128, 128) | kMnB, kk > 0);
-          } else {                                             // dW1 | db1 += dH1'^T . [X | 1 1 0..]
-#pragma unroll
-            for (int h = 0; h < kHalves; ++h)
-#pragma unroll
-              for (int kk = 0; kk < kTileEnvs / 16; ++kk)
-                mma_f16_ss(tm + kColW1 + 32 * h, desc_rows_mn(h1_a + h * 16 * kChunkA + kk * 256), desc_rows_mn(xs_a + kk * 256), make_idesc_f16(128, 32) | kMnA | kMnB,
-                           acc_w1 || kk > 0);
-            acc_w1 = true;
-          }
-          tc_commit(&done[g]);
+              mma_f16_ss(tm + kColW1 + 32 * h, desc_rows_mn(h1_a + h * 16 * kChunkA + kk * 256), desc_rows_mn(xs_a + kk * 256), make_idesc_f16(128, 32) | kMnA | kMnB,
+                         acc_w1 || kk > 0);
+          acc_w1 = true;
+        }
+        tc_commit(&done[g]);
+        if (++stage[g] == kStages) {
+          stage[g] = 0;
+          if (--left[g] == 0) --active;
         }
       }
+      if (!served) __nanosleep(20);
     }
   }
   // every group waited for its own last stage; after this barrier every MMA of the CTA has completed
@@ -269,7 +375,7 @@ __global__ void __launch_bounds__(kGroups * kTileEnvs + 32, 1) actor_backward_ke
   // ---- flush (group 0): accumulator row m = TMEM lane m = this thread; everything divided by the loss scale
   if (tid < kTileEnvs && (int64_t)blockIdx.x * kGroups < tiles) {
     const uint32_t lane_sel = (uint32_t)((row >> 5) * 32) << 16;
-    const float inv = 1.0f / scale;
+    const float inv = kPpo ? inv_rows / scale : 1.0f / scale;
     const int j = row;                                       // unit of layer 2 (dW2, db2, dW3) / unit within a 128-block of layer 1 (dW1)
 #pragma unroll 1
     for (int c0 = 0; c0 < H1; c0 += 16) {
@@ -312,11 +418,11 @@ __global__ void __launch_bounds__(kGroups * kTileEnvs + 32, 1) actor_backward_ke
 
 using namespace gr;
 
-template <class NL, int kGroups>
-static int launch_actor_backward(const GrBackwardJob* jobs, int n_jobs, int64_t R, cudaStream_t s) {
+template <class NL, int kGroups, bool kPpo = false>
+static int launch_actor_backward(const GrBackwardJob* jobs, int n_jobs, int64_t R, cudaStream_t s, const PpoFusedArgs* fz = nullptr) {
   const size_t bytes = (size_t)NL::kNetBytes + (size_t)kGroups * (4 + NL::kH1 / 8 + NL::kH2 / 8 + 2) * kChunkA + 2 * kChunkA + 128;
   if (bytes > 227 * 1024) return GR_ERR_SMEM;
-  auto kernel = actor_backward_kernel<NL, kGroups>;
+  auto kernel = actor_backward_kernel<NL, kGroups, kPpo>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) return (int)e;
   int dev = 0, sms = 148;
@@ -325,7 +431,8 @@ static int launch_actor_backward(const GrBackwardJob* jobs, int n_jobs, int64_t 
   const int64_t units = (tiles + kGroups - 1) / kGroups;      // a CTA works on kGroups tiles at a time
   const int per_job = sms / n_jobs;
   const int grid = (int)(units < per_job ? units : per_job);
-  kernel<<<dim3(grid, n_jobs), kGroups * kTileEnvs + 32, bytes, s>>>(jobs[0], jobs[n_jobs - 1], R);
+  const PpoFusedArgs none = {};
+  kernel<<<dim3(grid, n_jobs), kGroups * kTileEnvs + 32, bytes, s>>>(jobs[0], jobs[n_jobs - 1], R, fz ? *fz : none);
   return (int)cudaGetLastError();
 }
 
@@ -364,4 +471,40 @@ extern "C" int gr_actor_backward(const GrPolicy* policy, int32_t hidden, int32_t
   GrBackwardJob job;
   job.policy = *policy; job.obs = obs; job.grad_actions = grad_actions; job.scale = scale; job.out = *out; job.indices = nullptr;
   return gr_actor_backward_jobs(&job, 1, hidden, hidden2, rows, stream);
+}
+
+extern "C" int gr_ppo_fused_step(const GrPpoStep* st, int64_t rows, void* stream) {
+  if (!st) return GR_ERR_NULL;
+  const GrPpoBatch& b = st->batch;
+  if (!st->policy.packed || !st->obs || !st->critic_obs || !st->sums || !b.sigma || !b.actions || !b.old_log_prob || !b.advantages || !b.returns || !b.old_mu ||
+      !b.old_sigma)
+    return GR_ERR_NULL;
+  if (b.use_clipped_value_loss && !b.old_values) return GR_ERR_NULL;
+  if (rows <= 0) return GR_ERR_SIZE;
+  if (st->cotangent_scale < 0.0f) return GR_ERR_CONFIG;
+  GrBackwardJob jobs[2];
+  const int net_bytes = NetLayout<128, 128>::kNetBytes;
+  for (int k = 0; k < 2; ++k) {
+    jobs[k].policy = st->policy;
+    if (k == 1) jobs[k].policy.packed = static_cast<const uint8_t*>(st->policy.packed) + net_bytes;
+    jobs[k].obs = k == 0 ? st->obs : st->critic_obs;
+    jobs[k].grad_actions = st->obs;                // (unused by the fused kernel; non-null for check_job)
+    jobs[k].scale = st->sums;                      // (unused)
+    jobs[k].out = k == 0 ? st->actor_grad : st->critic_grad;
+    jobs[k].indices = b.indices;
+    const int rc = check_job(&jobs[k]);
+    if (rc != GR_OK) return rc;
+  }
+  if ((reinterpret_cast<uintptr_t>(b.actions) | reinterpret_cast<uintptr_t>(b.old_mu) | reinterpret_cast<uintptr_t>(b.old_sigma) | reinterpret_cast<uintptr_t>(b.sigma)) & 15u)
+    return GR_ERR_ALIGN;
+  if (jobs[0].out.out_dim != 4 || jobs[1].out.out_dim != 1) return GR_ERR_SIZE;
+  PpoFusedArgs fz;
+  fz.b = b;
+  fz.sums = st->sums;
+  fz.cot_scale = st->cotangent_scale > 0.0f ? st->cotangent_scale : 1.0f / 64.0f;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t tiles = (rows + kTileEnvs - 1) / kTileEnvs;
+  return tiles > sms / 2 ? launch_actor_backward<NetLayout<128, 128>, 2, true>(jobs, 2, rows, s, &fz) : launch_actor_backward<NetLayout<128, 128>, 1, true>(jobs, 2, rows, s, &fz);
 }

@@ -7,6 +7,7 @@
 //   to the network outputs
 // The weight gradients then come from gr_actor_backward (actor with d/d mu, critic with d/d v); clipping and Adam stay torch.
 #include "mlp_tc.cuh"
+#include "ppo_loss.cuh"
 
 namespace gr {
 
@@ -89,46 +90,18 @@ __global__ void __launch_bounds__(256) ppo_loss_grad_kernel(const GrPpoBatch b, 
     const float4 mu = __ldg(reinterpret_cast<const float4*>(b.mu) + r), a = __ldg(reinterpret_cast<const float4*>(b.actions) + q);
     const float4 sg = __ldg(reinterpret_cast<const float4*>(b.sigma));
     const float4 omu = __ldg(reinterpret_cast<const float4*>(b.old_mu) + q), osg = __ldg(reinterpret_cast<const float4*>(b.old_sigma) + q);
-    const float mus[4] = {mu.x, mu.y, mu.z, mu.w}, as[4] = {a.x, a.y, a.z, a.w}, sgs[4] = {sg.x, sg.y, sg.z, sg.w};
-    const float omus[4] = {omu.x, omu.y, omu.z, omu.w}, osgs[4] = {osg.x, osg.y, osg.z, osg.w};
-    // log-prob of the stored action under the current policy (Normal.log_prob summed over the action dims), KL(old || new) (ppo.py:126-129)
-    float logp = 0.0f, kl = 0.0f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float d = as[k] - mus[k];
-      logp += -(d * d) / (2.0f * sgs[k] * sgs[k]) - logf(sgs[k]) - 0.91893853320467274178f;
-      const float dm = omus[k] - mus[k];
-      kl += logf(sgs[k] / osgs[k] + 1.0e-5f) + (osgs[k] * osgs[k] + dm * dm) / (2.0f * sgs[k] * sgs[k]) - 0.5f;
-    }
-    const float adv = b.advantages[q];
-    const float ratio = expf(logp - b.old_log_prob[q]);
-    const float s1 = -adv * ratio;
-    const float s2 = -adv * fminf(fmaxf(ratio, 1.0f - b.clip_param), 1.0f + b.clip_param);
-    const float surrogate = fmaxf(s1, s2);
-    // d max(s1, s2) / d logp: s1 carries -adv * ratio; s2 carries it only inside the clip range (where s1 == s2: the tie's two halves add up)
-    const float g_logp = (s1 >= s2 ? -adv * ratio : 0.0f) * inv_rows;
-    // value loss (ppo.py:153-160)
-    const float v = b.value[r], ret = b.returns[q];
-    float vloss, g_v;
-    if (b.use_clipped_value_loss) {
-      const float ov = b.old_values[q];
-      const float dv = v - ov;
-      const bool inside = dv >= -b.clip_param && dv <= b.clip_param;     // torch.clamp passes the gradient at the bounds
-      const float vc = ov + fminf(fmaxf(dv, -b.clip_param), b.clip_param);
-      const float l1 = (v - ret) * (v - ret), l2 = (vc - ret) * (vc - ret);
-      vloss = fmaxf(l1, l2);
-      g_v = l1 >= l2 ? 2.0f * (v - ret) : (inside ? 2.0f * (vc - ret) : 0.0f);
-      if (l1 == l2 && !inside) g_v *= 0.5f;                              // exact tie outside the range: only the l1 half has a gradient
-    } else {
-      vloss = (ret - v) * (ret - v);
-      g_v = 2.0f * (v - ret);
-    }
+    const PpoActorRow ar = ppo_actor_row(mu, sg, a, omu, osg, b.advantages[q], b.old_log_prob[q], b.clip_param);
+    const float kl = ar.kl, surrogate = ar.surrogate;
+    const float g_logp = ar.g_logp * inv_rows;
+    const PpoCriticRow cr = ppo_critic_row(b.value[r], b.returns[q], b.use_clipped_value_loss ? b.old_values[q] : 0.0f, b.use_clipped_value_loss != 0, b.clip_param);
+    const float vloss = cr.vloss;
+    float g_v = cr.g_v;
     g_v *= b.value_loss_coef * inv_rows;
     float4 gm;
     float gs[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float d = as[k] - mus[k], inv_s = 1.0f / sgs[k];
+      const float d = ar.d[k], inv_s = ar.inv_s[k];
       (&gm.x)[k] = g_logp * d * inv_s * inv_s;
       // d logp / d std = d^2 / std^3 - 1 / std ; entropy = sum(0.5 + 0.5 log 2pi + log std) enters with -entropy_coef * mean
       gs[k] = g_logp * (d * d * inv_s * inv_s * inv_s - inv_s) - b.entropy_coef * inv_rows * inv_s;

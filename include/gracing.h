@@ -406,6 +406,21 @@ typedef struct GrPpoBatch {
 } GrPpoBatch;
 int gr_ppo_loss_grad(const GrPpoBatch* batch, int64_t rows, float* grad_mu /* [rows,4] */, float* grad_value /* [rows,4] */,
                      float* sums /* [16] accumulated */, void* stream);
+/* The three launches above (gr_policy_forward_gather, gr_ppo_loss_grad, gr_actor_backward_jobs) as ONE: per 128-row tile and net the kernel
+ * recomputes the activations, takes the head (layer 3) on them, evaluates the row's loss gradient in registers and accumulates the weight
+ * gradients -- mu / value / d(loss)/d(mu) / d(loss)/d(v) never exist in memory.  batch.mu / batch.value are ignored; batch.indices (optional)
+ * gathers obs / critic_obs and the stored columns on load.  actor_grad / critic_grad accumulate (zero them first, out_dim 4 / 1,
+ * scale_is_maxabs ignored); sums[0..7] accumulate as gr_ppo_loss_grad's (sums[8..9] are not written).  The cotangent rows go to fp16 as
+ * cotangent_scale x the un-normalised per-row gradient (0 => 1/64; the accumulators are divided by rows * cotangent_scale at the flush). */
+typedef struct GrPpoStep {
+  GrPolicy policy;                     /* packed actor + critic, widths (128,128) */
+  const float* obs; const float* critic_obs;
+  GrPpoBatch batch;
+  GrMlpGrad actor_grad, critic_grad;
+  float* sums;                         /* device [16] */
+  float cotangent_scale;
+} GrPpoStep;
+int gr_ppo_fused_step(const GrPpoStep* step, int64_t rows, void* stream);
 
 /* Gradient clipping + Adam + the KL-adaptive learning rate of one optimiser step (nn.utils.clip_grad_norm_, torch.optim.Adam.step
  * and ppo.py:124-141), two launches over a flat view of the parameters: replaces ~40 element-wise torch launches of the

@@ -218,3 +218,65 @@ def test_gather_on_load_equals_gather_then_dense(cuda_lib, rows, pool):
     for x, y in zip(d[5], g[5]):
         assert float((x - y).abs().max()) <= 2e-5 * float(x.abs().max()) + 1e-12
         assert float(x.abs().max()) > 0
+
+
+@pytest.mark.parametrize("rows,pool,clipped,entropy_coef", [(1000, 5000, True, 0.0), (128 * 149 + 3, 400000, True, 0.01), (65536 * 6, 65536 * 24, False, 0.0)])
+def test_fused_step_equals_the_three_launches(cuda_lib, rows, pool, clipped, entropy_coef):
+    """gr_ppo_fused_step (forward head + loss + weight gradients in one kernel per net) against gr_policy_forward_gather -> gr_ppo_loss_grad ->
+    gr_actor_backward_jobs on the same mini-batch: the loss sums agree to summation order, the weight gradients to the fp16 rounding of the
+    cotangent rows (static scale vs batch-maximum scale: different bits of the same value)."""
+    from generalizableracing_b200 import _lib as B
+    from generalizableracing_b200.modules import ActorCritic
+    lib = cuda_lib
+    torch.manual_seed(rows)
+    pol = ActorCritic(16, 16, 4).cuda()
+    la, lc = [m for m in pol.actor if isinstance(m, torch.nn.Linear)], [m for m in pol.critic if isinstance(m, torch.nn.Linear)]
+    mk = lambda l, out: B.GrMlp(l[0].weight.data_ptr(), l[0].bias.data_ptr(), l[1].weight.data_ptr(), l[1].bias.data_ptr(), l[2].weight.data_ptr(), l[2].bias.data_ptr(), 16, 128, 128, out)
+    packed = torch.zeros(int(lib.gr_policy_packed_bytes(128, 128, 2)), dtype=torch.uint8, device="cuda")
+    a, c = mk(la, 4), mk(lc, 1)
+    st = torch.cuda.current_stream().cuda_stream
+    B.check(lib.gr_policy_pack(C.byref(a), C.byref(c), packed.data_ptr(), st), "pack")
+    sigma = torch.tensor([0.8, 0.6, 1.0, 0.7], device="cuda")
+    p = B.GrPolicy(packed.data_ptr(), sigma.data_ptr(), 0.01)
+    pc = B.GrPolicy(packed.data_ptr() + packed.numel() // 2, sigma.data_ptr(), 0.01)
+    rn = lambda *s: torch.randn(*s, device="cuda")
+    obs, cobs = rn(pool, 16) * 2, rn(pool, 16) * 2
+    with torch.no_grad():
+        old_mu = pol.actor(obs) + 0.1 * rn(pool, 4)
+        old_v = pol.critic(cobs)[:, 0] + 0.2 * rn(pool)
+    old_sig = (sigma * (1 + 0.05 * rn(4))).abs().expand(pool, 4).contiguous()
+    actions = old_mu + old_sig * rn(pool, 4)
+    logp = torch.distributions.Normal(old_mu, old_sig).log_prob(actions).sum(-1)
+    adv, ret = rn(pool), old_v + 0.5 * rn(pool)
+    idx = torch.randperm(pool, device="cuda")[:rows].contiguous()
+    ip = idx.data_ptr()
+
+    def grads():
+        gs = [torch.zeros_like(t) for l in (la, lc) for m in l for t in (m.weight, m.bias)]
+        return gs, B.GrMlpGrad(*(t.data_ptr() for t in gs[:6]), 4, 1), B.GrMlpGrad(*(t.data_ptr() for t in gs[6:]), 1, 1)
+
+    # --- three launches
+    mu, val = torch.zeros(rows, 4, device="cuda"), torch.zeros(rows, device="cuda")
+    gm, gv, sums = torch.zeros(rows, 4, device="cuda"), torch.zeros(rows, 4, device="cuda"), torch.zeros(16, device="cuda")
+    B.check(lib.gr_policy_forward_gather(C.byref(p), obs.data_ptr(), cobs.data_ptr(), ip, mu.data_ptr(), val.data_ptr(), rows, st), "fwd")
+    b = B.GrPpoBatch(mu.data_ptr(), val.data_ptr(), sigma.data_ptr(), actions.data_ptr(), logp.data_ptr(), adv.data_ptr(), ret.data_ptr(), old_v.data_ptr(),
+                     old_mu.data_ptr(), old_sig.data_ptr(), 0.2, 1.0, entropy_coef, int(clipped), ip)
+    B.check(lib.gr_ppo_loss_grad(C.byref(b), rows, gm.data_ptr(), gv.data_ptr(), sums.data_ptr(), st), "loss")
+    g3, ga, gc = grads()
+    jobs = (B.GrBackwardJob * 2)(B.GrBackwardJob(p, obs.data_ptr(), gm.data_ptr(), sums.data_ptr() + 32, ga, ip),
+                                 B.GrBackwardJob(pc, cobs.data_ptr(), gv.data_ptr(), sums.data_ptr() + 36, gc, ip))
+    B.check(lib.gr_actor_backward_jobs(jobs, 2, 128, 128, rows, st), "bwd")
+    # --- one launch
+    g1, ga1, gc1 = grads()
+    sums1 = torch.zeros(16, device="cuda")
+    b1 = B.GrPpoBatch(None, None, sigma.data_ptr(), actions.data_ptr(), logp.data_ptr(), adv.data_ptr(), ret.data_ptr(), old_v.data_ptr(),
+                      old_mu.data_ptr(), old_sig.data_ptr(), 0.2, 1.0, entropy_coef, int(clipped), ip)
+    step = B.GrPpoStep(p, obs.data_ptr(), cobs.data_ptr(), b1, ga1, gc1, sums1.data_ptr(), 0.0)
+    B.check(lib.gr_ppo_fused_step(C.byref(step), rows, st), "gr_ppo_fused_step")
+    torch.cuda.synchronize()
+    assert torch.allclose(sums1[:8], sums[:8], rtol=2e-4, atol=1e-4 * float(sums[:8].abs().max())), (sums1[:8], sums[:8])
+    assert int(sums1[7]) == rows
+    names = [f"{net}.{n}" for net in ("actor", "critic") for n in ("w1", "b1", "w2", "b2", "w3", "b3")]
+    for name, x, y in zip(names, g3, g1):
+        assert bool(torch.isfinite(y).all()) and float(x.abs().max()) > 0, name
+        assert float((x - y).abs().max()) <= 1e-2 * float(x.abs().max()), (name, float((x - y).abs().max() / x.abs().max()))
