@@ -867,7 +867,55 @@ def bench_extras(dev, cfg, table):
     out["reach_target"] = {"step_lv_65536": bench_step(ReachTargetCfg.lv(decimation=1, is_differentiable_physics=False), 65536),
                            "bptt_window_ctbr_16384x48": bench_window(ReachTargetCfg.ctbr()),
                            "bptt_window_lv_16384x48": bench_window(ReachTargetCfg.lv(decimation=1))}
+    out["mesh_collision"] = bench_mesh_collision(dev, cfg, table)
     return out
+
+
+def bench_mesh_collision(dev, cfg, table, N: int = NUM_ENVS):
+    """SURVEY 8f rank 4, last item: the terrain-mesh collision count (gr_uav_collision_ray = the reference's Warp kernel behind
+    get_uav_collision_num_ray) for 65,536 UAVs x 17 lattice points x up to 6 axis rays against a box model of the bench's gate table (200
+    tiles: ground slabs + four-bar gate frames), on the poses of a stepped env batch; and env.step with the term switched on."""
+    from generalizableracing_b200 import mesh as M
+    from generalizableracing_b200.env import RacingVecEnv
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pts, faces = M.track_table_mesh(table)
+    t0 = time.perf_counter()
+    tm = M.TerrainMesh(pts, faces, device=dev)
+    build_s = time.perf_counter() - t0
+    env = RacingVecEnv(cfg, table, N, device=dev, seed=77)
+    env.reset()
+    env.episode_length_buf = torch.randint(0, cfg.max_episode_length, (N,), device=dev, dtype=torch.int32)
+    acts = torch.randn(N, 4, device=dev) * 0.5
+    for _ in range(30):
+        env.step(acts)
+    sv = env.state_dict_view()
+    pos, quat = sv["root_pos_w"].contiguous(), sv["root_quat_w"].contiguous()
+    lat = M.LATTICE_TENSOR.to(dev)
+    num = M.get_uav_collision_num_ray(tm, pos, quat, 0.09, 0.05, 1e3, lat)
+    torch.cuda.synchronize(dev)
+    reps = 20
+    e0.record()
+    for _ in range(reps):
+        M.get_uav_collision_num_ray(tm, pos, quat, 0.09, 0.05, 1e3, lat)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    us = e0.elapsed_time(e1) * 1e3 / reps
+    env.set_terrain_mesh(tm, -50.0)
+    for _ in range(5):
+        env.step(acts)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(reps):
+        env.step(acts)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    us_step = e0.elapsed_time(e1) * 1e3 / reps
+    env.close()
+    return {"uavs": N, "faces": int(faces.shape[0]), "bvh_nodes": int(tm.num_nodes), "bvh_build_host_s": build_s, "us_per_call": us,
+            "uav_checks_per_s": N / (us * 1e-6), "lattice_points_inside_mean": float(num.float().mean()), "colliding_fraction": float((num > 2).float().mean()),
+            "env_step_with_term_us": us_step,
+            "what": "get_uav_collision_num_ray (17 lattice points x <= 6 axis rays per UAV, BVH traversal) on the poses of a stepped 65,536-env batch; "
+                    "env_step_with_term_us = RacingVecEnv.step with set_terrain_mesh (step kernel + ray casts + reward add, Python-driven)"}
 
 
 def bench_ppo_training(dev, cfg, table, N: int = 4096, T: int = 24):

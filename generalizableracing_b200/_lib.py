@@ -191,6 +191,7 @@ PROTOTYPES = {
     "gr_rollout_fwd": (C.c_int, [C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom), C.POINTER(GrRolloutIO), c_p]),
     "gr_fill_rand": (C.c_int, [c_p, c_i, c_i, C.c_uint64, C.c_uint32, c_p]),
     "gr_fill_startup_rand": (C.c_int, [c_p, c_i, c_i, C.c_uint64, c_p]),
+    "gr_selftest_sqrt_rn": (C.c_int, [c_p, c_p, C.c_int64, c_p]),
     "gr_storage_add": (C.c_int, [C.POINTER(GrStorage), C.POINTER(GrTransition), c_i, c_p]),
     "gr_gae_scratch_bytes": (C.c_int64, [c_i]),
     "gr_compute_returns": (C.c_int, [C.POINTER(GrStorage), c_p, c_f, c_f, c_p, c_p, c_i, c_p]),

@@ -350,6 +350,13 @@ __global__ void fill_rand_kernel(float4* __restrict__ out, const int num_envs, c
   }
 }
 
+// the square root of the gate predicate `|gate - pos| < update_threshold`, exposed for a test: it must stay correctly rounded whatever
+// the library-wide -prec-sqrt / -prec-div flags are (a 1-ulp error flips gate passes against the reference)
+__global__ void sqrt_rn_kernel(const float* __restrict__ x, float* __restrict__ y, const int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = sqrt_rn(x[i]);
+}
+
 __global__ void fill_startup_rand_kernel(float* __restrict__ out, const int num_envs, const int env_id_offset, const uint64_t seed) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= num_envs) return;
@@ -553,6 +560,13 @@ extern "C" int gr_fill_rand(float* rnd, int32_t num_envs, int32_t env_id_offset,
   if (misaligned16(rnd)) return GR_ERR_ALIGN;
   const int total = num_envs * (GR_RND_STRIDE / 4);
   fill_rand_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<float4*>(rnd), num_envs, env_id_offset, seed, step);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int gr_selftest_sqrt_rn(const float* x, float* y, int64_t n, void* stream) {
+  if (!x || !y) return GR_ERR_NULL;
+  if (n <= 0) return GR_ERR_SIZE;
+  sqrt_rn_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, n);
   return (int)cudaGetLastError();
 }
 

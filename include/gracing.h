@@ -256,6 +256,10 @@ int gr_rollout_fwd(const GrConfig* cfg, const GrTrack* track, const GrState* st,
 
 /* Dense random tensor exactly as the in-kernel Philox path would draw it (parity chain). */
 int gr_fill_rand(float* rnd, int32_t num_envs, int32_t env_id_offset, uint64_t seed, uint32_t step, void* stream);
+/* Self-test hook: y[i] = the device square root the gate predicate `|gate - pos| < update_threshold` (QD/mdp/commands.py:308-312) is
+ * evaluated with.  It must be correctly rounded (IEEE) whatever -prec-sqrt / -prec-div the library is built with; tests/test_misc.py compares
+ * it bit for bit with numpy. */
+int gr_selftest_sqrt_rn(const float* x, float* y, int64_t n, void* stream);
 int gr_fill_startup_rand(float* srnd, int32_t num_envs, int32_t env_id_offset, uint64_t seed, void* stream);
 
 /* ---- rollout storage (S/rsl_rl/ext/storage/rollout_storage.py) ---- */

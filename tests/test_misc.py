@@ -132,3 +132,26 @@ def test_episode_log_accumulators(backend, stage, diff):
     if cfg.noise_curriculum and cfg.add_cmd_noise:
         assert abs(float(log["Curriculum/command_noise_level"]) - float(orc.noise_level.mean())) < 1e-5
     assert float(log["Episode_Termination/time_out"]) + float(log["Episode_Termination/terminated"]) >= n_reset
+
+
+@pytest.mark.gpu
+def test_gate_predicate_square_root_is_correctly_rounded(cuda_lib):
+    """The library is built with -prec-sqrt=false -prec-div=false (fast paths for the smooth quantities); the square root behind the gate
+    predicate `|gate - pos| < 0.35` must not follow: a 1-ulp error there flips gate passes against the reference.  Bit-for-bit against numpy's
+    IEEE square root on a million values, dense around the threshold 0.35^2 and across the exponent range."""
+    import numpy as np
+    lib = cuda_lib
+    rng = np.random.default_rng(0)
+    thr2 = np.float32(0.35) * np.float32(0.35)
+    base = np.float32(thr2).view(np.uint32)
+    around = (np.arange(-200000, 200001, dtype=np.int64) + int(base)).astype(np.uint32).view(np.float32)          # 400,001 consecutive floats around 0.1225
+    wide = np.exp(rng.uniform(np.log(1e-12), np.log(1e12), 600000)).astype(np.float32)
+    x = np.concatenate([around, wide, np.array([0.0, 1.0, 4.0, 1e-38, 3e38], dtype=np.float32)])
+    xt = torch.from_numpy(x).cuda()
+    yt = torch.empty_like(xt)
+    assert lib.gr_selftest_sqrt_rn(xt.data_ptr(), yt.data_ptr(), xt.numel(), torch.cuda.current_stream().cuda_stream) == 0
+    got = yt.cpu().numpy()
+    want = np.sqrt(x.astype(np.float32))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), int((got.view(np.uint32) != want.view(np.uint32)).sum())
+    # and the decision itself on the consecutive floats around the threshold
+    assert np.array_equal(got[:around.size] < np.float32(0.35), want[:around.size] < np.float32(0.35))
