@@ -157,22 +157,26 @@ __global__ void __launch_bounds__(kGroups * kTileEnvs + 32, 1) actor_backward_ke
     uint32_t ph = 0u;
     // one stage hand-over: operands written -> arrive; wait for the stage's MMAs
 #define GR_HANDOVER() do { fence_proxy_async_smem(); tc_fence_before_sync(); mbar_arrive(&full[grp]); mbar_wait(&done[grp], ph); ph ^= 1u; tc_fence_after_sync(); } while (0)
-    // the rows of a tile: observation row, and either the cotangent row (plain backward) or the stored columns of the row (kPpo).  The rows of
-    // the NEXT tile are fetched while this one is processed: with the mini-batch gather on load every row is a scattered 64-byte read (plus
-    // five scattered scalars / 16-byte rows under kPpo), and one tile at a time per group leaves nothing else to hide that latency behind
-    // (ncu before this: long-scoreboard 11 of 16 stall cycles per issue)
+    // The rows of a tile: observation row, and either the cotangent row (plain backward) or the stored columns of the row (kPpo).  With the
+    // mini-batch gather on load every row is a scattered 64-byte read (plus five scattered scalars / 16-byte rows under kPpo) behind a
+    // scattered index read, and one tile at a time per group leaves nothing else to hide two DRAM latencies behind (ncu: long-scoreboard
+    // 11 of 16 stall cycles per issue).  So the loads run ahead of the tile they belong to: the INDEX of tile t + 2 and the ROWS of tile
+    // t + 1 are requested while tile t is processed -- when the rows are requested their address has been known for a whole tile.  The
+    // requests are unconditional (rows past the end are clamped to the last row and zeroed at their use): a divergent or skipped request
+    // would make the compiler wait for the outstanding loads where the paths meet.
     struct TileRows {
       float4 o0, o1, o2, o3, gr4, st_a, st_omu, st_osg;
       float st_adv, st_logp, st_ret, st_ov;
     };
-    auto fetch = [&](const int64_t tile, TileRows& t) {
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      t.o0 = t.o1 = t.o2 = t.o3 = t.gr4 = t.st_a = t.st_omu = z;
-      t.st_osg = make_float4(1.f, 1.f, 1.f, 1.f);
-      t.st_adv = t.st_logp = t.st_ret = t.st_ov = 0.f;
-      const int64_t r = tile * kTileEnvs + row;
-      if (r >= R) return;
-      const int64_t q = idx ? __ldg(idx + r) : r;                                  // (mini-batch gather on load)
+    const bool gather = idx != nullptr;
+    auto index_of = [&](const int64_t tile) -> int64_t {
+      int64_t r = tile * kTileEnvs + row;
+      r = r < R ? r : R - 1;
+      return gather ? __ldg(idx + r) : r;
+    };
+    auto fetch = [&](const int64_t tile, const int64_t q, TileRows& t) {
+      int64_t r = tile * kTileEnvs + row;
+      r = r < R ? r : R - 1;
       const float4* xr = reinterpret_cast<const float4*>(X) + q * 4;
       t.o0 = __ldcs(xr); t.o1 = __ldcs(xr + 1); t.o2 = __ldcs(xr + 2); t.o3 = __ldcs(xr + 3);
       if (!kPpo) {
@@ -185,19 +189,25 @@ __global__ void __launch_bounds__(kGroups * kTileEnvs + 32, 1) actor_backward_ke
         t.st_logp = __ldg(fz.b.old_log_prob + q);
       } else {
         t.st_ret = __ldg(fz.b.returns + q);
-        if (fz.b.use_clipped_value_loss) t.st_ov = __ldg(fz.b.old_values + q);
+        t.st_ov = fz.b.use_clipped_value_loss ? __ldg(fz.b.old_values + q) : 0.0f;
       }
     };
     TileRows cur = {}, nxt = {};
-    {
-      const int64_t first_tile = (int64_t)blockIdx.x * kGroups + grp;
-      if (first_tile < tiles) fetch(first_tile, cur);
+    const int64_t first_tile = (int64_t)blockIdx.x * kGroups + grp;
+    int64_t q_next = 0, q_next2 = 0;
+    if (first_tile < tiles) {
+      fetch(first_tile, index_of(first_tile), cur);
+      q_next = index_of(first_tile + stride);
     }
 #pragma unroll 1
-    for (int64_t tile = (int64_t)blockIdx.x * kGroups + grp; tile < tiles; tile += stride) {
+    for (int64_t tile = first_tile; tile < tiles; tile += stride) {
       const int64_t r = tile * kTileEnvs + row;
-      if (tile + stride < tiles) fetch(tile + stride, nxt);
-      const float4 o0 = cur.o0, o1 = cur.o1, o2 = cur.o2, o3 = cur.o3, gr4 = cur.gr4, st_a = cur.st_a, st_omu = cur.st_omu, st_osg = cur.st_osg;
+      q_next2 = index_of(tile + 2 * stride);
+      fetch(tile + stride, q_next, nxt);
+      const bool live = r < R;
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 o0 = live ? cur.o0 : z4, o1 = live ? cur.o1 : z4, o2 = live ? cur.o2 : z4, o3 = live ? cur.o3 : z4, gr4 = live ? cur.gr4 : z4;
+      const float4 st_a = cur.st_a, st_omu = cur.st_omu, st_osg = cur.st_osg;
       const float st_adv = cur.st_adv, st_logp = cur.st_logp, st_ret = cur.st_ret, st_ov = cur.st_ov;
       // (the previous tile's last stage -- dW1 -- read xs and h1s: its hand-over waited for it)
       write_x_row(xs + row * 16, pack8(o0, o1), pack8(o2, o3));
@@ -261,6 +271,7 @@ __global__ void __launch_bounds__(kGroups * kTileEnvs + 32, 1) actor_backward_ke
       // ---- dW1 | db1 += dH1'^T . [X | 1 1 0..]: nothing to read back, but xs / h1s stay in use until it completes
       GR_HANDOVER();
       cur = nxt;
+      q_next = q_next2;
     }
 #undef GR_HANDOVER
 #pragma unroll
