@@ -266,3 +266,4 @@ def test_env_step_adds_the_collision_term_on_the_pre_reset_pose(backend):
         hits += int(pen.sum()); resets += int(db.sum())
     assert hits > 0 and resets > 0
     assert torch.equal(a.planes, b.planes)
+
