@@ -207,6 +207,7 @@ PROTOTYPES = {
     "gr_policy_forward": (C.c_int, [C.POINTER(GrPolicy), c_p, c_p, c_p, c_p, C.c_int64, c_p]),
     "gr_policy_forward_gather": (C.c_int, [C.POINTER(GrPolicy), c_p, c_p, c_p, c_p, c_p, C.c_int64, c_p]),
     "gr_ppo_loss_grad": (C.c_int, [C.POINTER(GrPpoBatch), C.c_int64, c_p, c_p, c_p, c_p]),
+    "gr_policy_forward_loss": (C.c_int, [C.POINTER(GrPolicy), c_p, c_p, C.POINTER(GrPpoBatch), C.c_int64, c_p, c_p, c_p, c_p]),
     "gr_ppo_fused_step": (C.c_int, [C.POINTER(GrPpoStep), C.c_int64, c_p]),
     "gr_adam_clip_step": (C.c_int, [C.POINTER(GrAdamStep), c_p]),
     "gr_actor_backward_jobs": (C.c_int, [C.POINTER(GrBackwardJob), c_i, c_i, c_i, C.c_int64, c_p]),

@@ -192,16 +192,18 @@ class PPO:
         batch = B.GrPpoBatch(g["mu_new"].data_ptr(), g["v_new"].data_ptr(), g["sigma4"].data_ptr(), desc.actions, desc.log_prob, desc.advantages, desc.returns,
                              desc.values, desc.mu, desc.sigma, float(self.clip_param), float(self.value_loss_coef), float(self.entropy_coef),
                              int(self.use_clipped_value_loss), idx_ptr)
+        batch_fl = B.GrPpoBatch(None, None, g["sigma4"].data_ptr(), desc.actions, desc.log_prob, desc.advantages, desc.returns, desc.values, desc.mu, desc.sigma,
+                                float(self.clip_param), float(self.value_loss_coef), float(self.entropy_coef), int(self.use_clipped_value_loss), idx_ptr)
         p_max_mu, p_max_v = ksums.data_ptr() + 8 * 4, ksums.data_ptr() + 9 * 4
         jobs = (B.GrBackwardJob * 2)(B.GrBackwardJob(pol_both, s_obs, g["grad_mu"].data_ptr(), p_max_mu, gr_a, idx_ptr),
                                      B.GrBackwardJob(pol_c, s_critic, g["grad_v"].data_ptr(), p_max_v, gr_c, idx_ptr))
-        # forward + loss + weight gradients of both nets as ONE launch (gr_ppo_fused_step) for small mini-batches, three launches
-        # (gr_policy_forward_gather -> gr_ppo_loss_grad -> gr_actor_backward_jobs) for large ones.  Measured on the B200 (gpurun r2v):
+        # forward + loss + weight gradients of both nets as ONE launch (gr_ppo_fused_step) for small mini-batches, two launches
+        # (gr_policy_forward_loss -> gr_actor_backward_jobs) for large ones.  Measured on the B200 (gpurun r2v):
         # 24,576 rows (4,096 envs): 1.21 vs 1.27 ms of update per iteration; 393,216 rows (65,536 envs): 7.3 vs 6.4 ms -- at that size the
         # one-launch kernel's tiles wait for their scattered rows with nothing left to overlap.  GRACING_PPO_FUSED_STEP=0|1 forces.
         fused = {"0": False, "1": True}.get(os.environ.get("GRACING_PPO_FUSED_STEP", ""), mb <= 131072)
         fstep = B.GrPpoStep(pol_both, s_obs, s_critic, batch, gr_a, gr_c, ksums.data_ptr(), 0.0)
-        g["keep_k"] = (mlp_a, mlp_c, gr_a, gr_c, pol_both, pol_c, batch, adam, ptrs, seg_off, seg_n, jobs, fstep)
+        g["keep_k"] = (mlp_a, mlp_c, gr_a, gr_c, pol_both, pol_c, batch, batch_fl, adam, ptrs, seg_off, seg_n, jobs, fstep)
         g["kernel_sums"] = True                      # the running loss sums live in adam_state[5:7]
 
         def step():
@@ -213,10 +215,11 @@ class PPO:
             if fused:
                 B.check(lib.gr_ppo_fused_step(C.byref(fstep), mb, st), "gr_ppo_fused_step")
             else:
-                B.check(lib.gr_policy_forward_gather(C.byref(pol_both), s_obs, s_critic, idx_ptr, g["mu_new"].data_ptr(), g["v_new"].data_ptr(), mb, st),
-                        "gr_policy_forward_gather")
-                B.check(lib.gr_ppo_loss_grad(C.byref(batch), mb, g["grad_mu"].data_ptr(), g["grad_v"].data_ptr(), ksums.data_ptr(), st), "gr_ppo_loss_grad")
-                B.check(lib.gr_actor_backward_jobs(jobs, 2, 128, 128, mb, st), "gr_actor_backward_jobs")       # actor (d/d mu) and critic (d/d v) in one launch
+                # forward + loss in one launch (the thread holding a row's mean / value evaluates its loss), then the weight gradients of
+                # actor (d/d mu) and critic (d/d v) in one launch
+                B.check(lib.gr_policy_forward_loss(C.byref(pol_both), s_obs, s_critic, C.byref(batch_fl), mb, g["grad_mu"].data_ptr(), g["grad_v"].data_ptr(),
+                                                   ksums.data_ptr(), st), "gr_policy_forward_loss")
+                B.check(lib.gr_actor_backward_jobs(jobs, 2, 128, 128, mb, st), "gr_actor_backward_jobs")
             if world > 1:              # env-sharded data parallelism: ONE all-reduce per step carries the gradients and the loss / KL sums
                 torch.distributed.all_reduce(flat)
             B.check(lib.gr_adam_clip_step(C.byref(adam), st), "gr_adam_clip_step")

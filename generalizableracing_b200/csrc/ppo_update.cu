@@ -14,10 +14,25 @@ namespace gr {
 using NLp = NetLayout<128, 128>;
 constexpr int kFwdGroups = 2;                // two 128-row tiles in flight per CTA (one covers the other's MMA latency)
 
-// mu [rows,4], value [rows]: persistent over 128-row tiles, both nets resident in shared memory
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// what the forward kernel needs to evaluate the loss of a row itself (kLoss): the stored columns, the outputs, the sums
+struct FwdLossArgs { GrPpoBatch b; float* grad_mu; float* grad_value; float* sums; };
+
+// mu [rows,4], value [rows]: persistent over 128-row tiles, both nets resident in shared memory.  The rows of a tile (gathered on load:
+// scattered 64-byte reads behind a scattered index read) are requested one tile ahead, their indices two tiles ahead, unconditionally
+// (rows past the end are clamped and never stored) -- see actor_backward.cu.
+// kLoss: the thread that holds a row's mean and value also evaluates the row's loss (ppo_loss.cuh) on the stored columns it fetched with
+// the row, and writes d(loss)/d(mu), d(loss)/d(v) and its share of the sums: gr_ppo_loss_grad's launch and the mu / value round trip go.
+template <bool kLoss>
 __global__ void __launch_bounds__(kFwdGroups * kTileEnvs, 1) policy_forward_kernel(const GrPolicy pol, const float* __restrict__ obs,
                                                                                   const float* __restrict__ critic_obs, const int64_t* __restrict__ idx,
-                                                                                  float* __restrict__ mu, float* __restrict__ value, const int64_t R) {
+                                                                                  float* __restrict__ mu, float* __restrict__ value, const int64_t R,
+                                                                                  const FwdLossArgs la) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* w_smem = smem;
   uint8_t* h_smem = smem + 2 * NLp::kNetBytes;
@@ -39,29 +54,92 @@ __global__ void __launch_bounds__(kFwdGroups * kTileEnvs, 1) policy_forward_kern
   GroupCtx g = make_group_ctx(h_smem, NLp::kHBytes, bars, *tmem_slot, NLp::kCols, grp, row, pol.negative_slope);
   const uint32_t w_addr = smem_u32(w_smem);
   const int64_t tiles = (R + kTileEnvs - 1) / kTileEnvs;
-  // both groups of a CTA run the same number of rounds (the named barriers are per group, the tile loop is not)
+  const int64_t stride = (int64_t)gridDim.x * kFwdGroups;
+  const bool gather = idx != nullptr;
+  struct Rows { float4 o0, o1, o2, o3, c0, c1, c2, c3, a, omu, osg; float adv, logp, ret, ov; };
+  auto index_of = [&](const int64_t tile) -> int64_t {
+    int64_t r = tile * kTileEnvs + row;
+    r = r < R ? r : R - 1;
+    return gather ? __ldg(idx + r) : r;
+  };
+  auto fetch = [&](const int64_t q, Rows& t) {
+    const float4* xo = reinterpret_cast<const float4*>(obs) + q * 4;
+    const float4* xc = reinterpret_cast<const float4*>(critic_obs) + q * 4;
+    t.o0 = __ldcs(xo); t.o1 = __ldcs(xo + 1); t.o2 = __ldcs(xo + 2); t.o3 = __ldcs(xo + 3);
+    t.c0 = __ldcs(xc); t.c1 = __ldcs(xc + 1); t.c2 = __ldcs(xc + 2); t.c3 = __ldcs(xc + 3);
+    if (kLoss) {
+      t.a = __ldg(reinterpret_cast<const float4*>(la.b.actions) + q);
+      t.omu = __ldg(reinterpret_cast<const float4*>(la.b.old_mu) + q);
+      t.osg = __ldg(reinterpret_cast<const float4*>(la.b.old_sigma) + q);
+      t.adv = __ldg(la.b.advantages + q);
+      t.logp = __ldg(la.b.old_log_prob + q);
+      t.ret = __ldg(la.b.returns + q);
+      t.ov = la.b.use_clipped_value_loss ? __ldg(la.b.old_values + q) : 0.0f;
+    }
+  };
+  Rows cur = {}, nxt = {};
+  const int64_t first = (int64_t)blockIdx.x * kFwdGroups + grp;
+  int64_t q_next = 0, q_next2 = 0;
+  // (every thread of the CTA runs the same number of rounds -- the named barriers are per group, the tile loop is not -- so the requests
+  //  are issued whether or not this group's tile exists)
+  fetch(index_of(first), cur);
+  q_next = index_of(first + stride);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float max_gm = 0.0f, max_gv = 0.0f;
+  const float inv_rows = 1.0f / (float)R;
 #pragma unroll 1
-  for (int64_t base = (int64_t)blockIdx.x * kFwdGroups; base < tiles; base += (int64_t)gridDim.x * kFwdGroups) {
+  for (int64_t base = (int64_t)blockIdx.x * kFwdGroups; base < tiles; base += stride) {
     const int64_t tile = base + grp;
     const int64_t r = tile * kTileEnvs + row;
     const bool live = tile < tiles && r < R;
-    float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0, o2 = o0, o3 = o0, c0 = o0, c1 = o0, c2 = o0, c3 = o0;
-    if (live) {
-      const int64_t q = idx ? __ldg(idx + r) : r;              // mini-batch gather on load (rollout_storage.py:179-187)
-      const float4* xo = reinterpret_cast<const float4*>(obs) + q * 4;
-      const float4* xc = reinterpret_cast<const float4*>(critic_obs) + q * 4;
-      o0 = __ldcs(xo); o1 = __ldcs(xo + 1); o2 = __ldcs(xo + 2); o3 = __ldcs(xo + 3);
-      c0 = __ldcs(xc); c1 = __ldcs(xc + 1); c2 = __ldcs(xc + 2); c3 = __ldcs(xc + 3);
-    }
-    write_x_row(g.hrow, pack8(o0, o1), pack8(o2, o3));
+    q_next2 = index_of(tile + 2 * stride);
+    fetch(q_next, nxt);
+    write_x_row(g.hrow, pack8(cur.o0, cur.o1), pack8(cur.o2, cur.o3));
     const float4 m = run_net<NLp>(g, w_smem, w_addr);
     tc_fence_before_sync();
-    write_x_row(g.hrow, pack8(c0, c1), pack8(c2, c3));
+    write_x_row(g.hrow, pack8(cur.c0, cur.c1), pack8(cur.c2, cur.c3));
     const float4 v = run_net<NLp>(g, w_smem + NLp::kNetBytes, w_addr + NLp::kNetBytes);
     tc_fence_before_sync();
     if (live) {
-      __stcs(reinterpret_cast<float4*>(mu) + r, m);
-      value[r] = v.x;
+      if (mu) __stcs(reinterpret_cast<float4*>(mu) + r, m);
+      if (value) value[r] = v.x;
+      if (kLoss) {       // exactly ppo_loss_grad_kernel's arithmetic on this row
+        const float4 sg = __ldg(reinterpret_cast<const float4*>(la.b.sigma));
+        const PpoActorRow ar = ppo_actor_row(m, sg, cur.a, cur.omu, cur.osg, cur.adv, cur.logp, la.b.clip_param);
+        const float g_logp = ar.g_logp * inv_rows;
+        const PpoCriticRow cr = ppo_critic_row(v.x, cur.ret, cur.ov, la.b.use_clipped_value_loss != 0, la.b.clip_param);
+        float g_v = cr.g_v;
+        g_v *= la.b.value_loss_coef * inv_rows;
+        float4 gm;
+        float gs[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float d = ar.d[k], inv_s = ar.inv_s[k];
+          (&gm.x)[k] = g_logp * d * inv_s * inv_s;
+          gs[k] = g_logp * (d * d * inv_s * inv_s * inv_s - inv_s) - la.b.entropy_coef * inv_rows * inv_s;
+        }
+        __stcs(reinterpret_cast<float4*>(la.grad_mu) + r, gm);
+        __stcs(reinterpret_cast<float4*>(la.grad_value) + r, make_float4(g_v, 0.f, 0.f, 0.f));
+        max_gm = fmaxf(max_gm, fmaxf(fmaxf(fabsf(gm.x), fabsf(gm.y)), fmaxf(fabsf(gm.z), fabsf(gm.w))));
+        max_gv = fmaxf(max_gv, fabsf(g_v));
+        acc[0] += ar.surrogate; acc[1] += cr.vloss; acc[2] += ar.kl; acc[3] += gs[0]; acc[4] += gs[1]; acc[5] += gs[2]; acc[6] += gs[3]; acc[7] += 1.0f;
+      }
+    }
+    cur = nxt;
+    q_next = q_next2;
+  }
+  if (kLoss) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float sacc = warp_sum_f(acc[k]);
+      if (lane == 0 && sacc != 0.0f) atomicAdd(la.sums + k, sacc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { max_gm = fmaxf(max_gm, __shfl_xor_sync(0xffffffffu, max_gm, o)); max_gv = fmaxf(max_gv, __shfl_xor_sync(0xffffffffu, max_gv, o)); }
+    if (lane == 0) {       // non-negative floats order like their bit patterns
+      atomicMax(reinterpret_cast<unsigned int*>(la.sums) + 8, __float_as_uint(max_gm));
+      atomicMax(reinterpret_cast<unsigned int*>(la.sums) + 9, __float_as_uint(max_gv));
     }
   }
   tc_fence_before_sync();
@@ -73,12 +151,6 @@ __global__ void __launch_bounds__(kFwdGroups * kTileEnvs, 1) policy_forward_kern
 // loss gradients of one mini-batch (ppo.py:118-171), one thread per row
 //   sums[0] += sum surrogate, [1] += sum value loss, [2] += sum KL, [3..6] += d loss / d std, [7] += rows
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float warp_sum_f(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
 __global__ void __launch_bounds__(256) ppo_loss_grad_kernel(const GrPpoBatch b, const int64_t R, float* __restrict__ grad_mu, float* __restrict__ grad_value,
                                                            float* __restrict__ sums) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -214,6 +286,21 @@ __global__ void __launch_bounds__(256) adam_apply_kernel(const GrAdamStep a) {
 
 using namespace gr;
 
+template <bool kLoss>
+static int launch_policy_forward(const GrPolicy* policy, const float* obs, const float* critic_obs, const int64_t* indices, float* mu, float* value, int64_t rows,
+                                 const FwdLossArgs& la, cudaStream_t s) {
+  const size_t bytes = 2 * (size_t)NLp::kNetBytes + (size_t)kFwdGroups * NLp::kHBytes + 128;
+  auto kernel = policy_forward_kernel<kLoss>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return (int)e;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t pairs = ((rows + kTileEnvs - 1) / kTileEnvs + kFwdGroups - 1) / kFwdGroups;
+  const int grid = (int)(pairs < sms ? pairs : sms);
+  kernel<<<grid, kFwdGroups * kTileEnvs, bytes, s>>>(*policy, obs, critic_obs, indices, mu, value, rows, la);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int gr_policy_forward_gather(const GrPolicy* policy, const float* obs, const float* critic_obs, const int64_t* indices, float* mu, float* value,
                                         int64_t rows, void* stream) {
   if (!policy || !policy->packed || !obs || !critic_obs || !mu || !value) return GR_ERR_NULL;
@@ -221,15 +308,25 @@ extern "C" int gr_policy_forward_gather(const GrPolicy* policy, const float* obs
   if (policy->negative_slope < 0.0f || policy->negative_slope > 1.0f) return GR_ERR_CONFIG;
   if ((reinterpret_cast<uintptr_t>(policy->packed) | reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(critic_obs) | reinterpret_cast<uintptr_t>(mu)) & 15u)
     return GR_ERR_ALIGN;
-  const size_t bytes = 2 * (size_t)NLp::kNetBytes + (size_t)kFwdGroups * NLp::kHBytes + 128;
-  cudaError_t e = cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  if (e != cudaSuccess) return (int)e;
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t pairs = ((rows + kTileEnvs - 1) / kTileEnvs + kFwdGroups - 1) / kFwdGroups;
-  const int grid = (int)(pairs < sms ? pairs : sms);
-  policy_forward_kernel<<<grid, kFwdGroups * kTileEnvs, bytes, reinterpret_cast<cudaStream_t>(stream)>>>(*policy, obs, critic_obs, indices, mu, value, rows);
-  return (int)cudaGetLastError();
+  const FwdLossArgs none = {};
+  return launch_policy_forward<false>(policy, obs, critic_obs, indices, mu, value, rows, none, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gr_policy_forward_loss(const GrPolicy* policy, const float* obs, const float* critic_obs, const GrPpoBatch* b, int64_t rows, float* grad_mu,
+                                      float* grad_value, float* sums, void* stream) {
+  if (!policy || !policy->packed || !obs || !critic_obs || !b || !grad_mu || !grad_value || !sums) return GR_ERR_NULL;
+  if (!b->sigma || !b->actions || !b->old_log_prob || !b->advantages || !b->returns || !b->old_mu || !b->old_sigma) return GR_ERR_NULL;
+  if (b->use_clipped_value_loss && !b->old_values) return GR_ERR_NULL;
+  if (rows <= 0) return GR_ERR_SIZE;
+  if (policy->negative_slope < 0.0f || policy->negative_slope > 1.0f) return GR_ERR_CONFIG;
+  if ((reinterpret_cast<uintptr_t>(policy->packed) | reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(critic_obs) | reinterpret_cast<uintptr_t>(b->actions) |
+       reinterpret_cast<uintptr_t>(b->old_mu) | reinterpret_cast<uintptr_t>(b->old_sigma) | reinterpret_cast<uintptr_t>(b->sigma) | reinterpret_cast<uintptr_t>(grad_mu) |
+       reinterpret_cast<uintptr_t>(grad_value) | (b->mu ? reinterpret_cast<uintptr_t>(b->mu) : 0)) & 15u)
+    return GR_ERR_ALIGN;
+  FwdLossArgs la;
+  la.b = *b; la.grad_mu = grad_mu; la.grad_value = grad_value; la.sums = sums;
+  return launch_policy_forward<true>(policy, obs, critic_obs, b->indices, const_cast<float*>(b->mu), const_cast<float*>(b->value), rows, la,
+                                     reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int gr_policy_forward(const GrPolicy* policy, const float* obs, const float* critic_obs, float* mu, float* value, int64_t rows, void* stream) {

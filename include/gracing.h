@@ -410,6 +410,11 @@ typedef struct GrPpoBatch {
 } GrPpoBatch;
 int gr_ppo_loss_grad(const GrPpoBatch* batch, int64_t rows, float* grad_mu /* [rows,4] */, float* grad_value /* [rows,4] */,
                      float* sums /* [16] accumulated */, void* stream);
+/* gr_policy_forward_gather + gr_ppo_loss_grad as ONE launch: the thread that holds a row's mean and value evaluates the row's loss on the stored
+ * columns it fetched with the row (batch->indices gathers on load).  batch->mu / batch->value: optional OUTPUTS here (dense [rows,4] / [rows]; NULL:
+ * the policy outputs are never written); grad_mu / grad_value / sums exactly as gr_ppo_loss_grad writes them (bit-identical gradients). */
+int gr_policy_forward_loss(const GrPolicy* policy, const float* obs, const float* critic_obs, const GrPpoBatch* batch, int64_t rows,
+                           float* grad_mu /* [rows,4] */, float* grad_value /* [rows,4] */, float* sums /* [16] accumulated */, void* stream);
 /* The three launches above (gr_policy_forward_gather, gr_ppo_loss_grad, gr_actor_backward_jobs) as ONE: per 128-row tile and net the kernel
  * recomputes the activations, takes the head (layer 3) on them, evaluates the row's loss gradient in registers and accumulates the weight
  * gradients -- mu / value / d(loss)/d(mu) / d(loss)/d(v) never exist in memory.  batch.mu / batch.value are ignored; batch.indices (optional)

@@ -280,3 +280,54 @@ def test_fused_step_equals_the_three_launches(cuda_lib, rows, pool, clipped, ent
     for name, x, y in zip(names, g3, g1):
         assert bool(torch.isfinite(y).all()) and float(x.abs().max()) > 0, name
         assert float((x - y).abs().max()) <= 1e-2 * float(x.abs().max()), (name, float((x - y).abs().max() / x.abs().max()))
+
+
+@pytest.mark.parametrize("rows,pool,clipped", [(1000, 5000, True), (128 * 149 + 3, 400000, False), (65536 * 6, 65536 * 24, True)])
+def test_forward_with_loss_equals_forward_then_loss(cuda_lib, rows, pool, clipped):
+    """gr_policy_forward_loss (the thread holding a row's mean / value evaluates the row's loss) against gr_policy_forward_gather followed by
+    gr_ppo_loss_grad: same arithmetic per row -> bit-identical policy outputs and gradients; the sums agree to summation order."""
+    from generalizableracing_b200 import _lib as B
+    from generalizableracing_b200.modules import ActorCritic
+    lib = cuda_lib
+    torch.manual_seed(rows + 1)
+    pol = ActorCritic(16, 16, 4).cuda()
+    la, lc = [m for m in pol.actor if isinstance(m, torch.nn.Linear)], [m for m in pol.critic if isinstance(m, torch.nn.Linear)]
+    mk = lambda l, out: B.GrMlp(l[0].weight.data_ptr(), l[0].bias.data_ptr(), l[1].weight.data_ptr(), l[1].bias.data_ptr(), l[2].weight.data_ptr(), l[2].bias.data_ptr(), 16, 128, 128, out)
+    packed = torch.zeros(int(lib.gr_policy_packed_bytes(128, 128, 2)), dtype=torch.uint8, device="cuda")
+    a, c = mk(la, 4), mk(lc, 1)
+    st = torch.cuda.current_stream().cuda_stream
+    B.check(lib.gr_policy_pack(C.byref(a), C.byref(c), packed.data_ptr(), st), "pack")
+    sigma = torch.tensor([0.8, 0.6, 1.0, 0.7], device="cuda")
+    p = B.GrPolicy(packed.data_ptr(), sigma.data_ptr(), 0.01)
+    rn = lambda *s: torch.randn(*s, device="cuda")
+    obs, cobs = rn(pool, 16) * 2, rn(pool, 16) * 2
+    old_mu, old_v = rn(pool, 4) * 0.5, rn(pool)
+    old_sig = (sigma * (1 + 0.05 * rn(4))).abs().expand(pool, 4).contiguous()
+    actions = old_mu + old_sig * rn(pool, 4)
+    logp = torch.distributions.Normal(old_mu, old_sig).log_prob(actions).sum(-1)
+    adv, ret = rn(pool), old_v + 0.5 * rn(pool)
+    idx = torch.randperm(pool, device="cuda")[:rows].contiguous()
+    ip = idx.data_ptr()
+    # two launches
+    mu, val = torch.zeros(rows, 4, device="cuda"), torch.zeros(rows, device="cuda")
+    gm, gv, sums = torch.zeros(rows, 4, device="cuda"), torch.zeros(rows, 4, device="cuda"), torch.zeros(16, device="cuda")
+    B.check(lib.gr_policy_forward_gather(C.byref(p), obs.data_ptr(), cobs.data_ptr(), ip, mu.data_ptr(), val.data_ptr(), rows, st), "fwd")
+    b = B.GrPpoBatch(mu.data_ptr(), val.data_ptr(), sigma.data_ptr(), actions.data_ptr(), logp.data_ptr(), adv.data_ptr(), ret.data_ptr(), old_v.data_ptr(),
+                     old_mu.data_ptr(), old_sig.data_ptr(), 0.2, 1.0, 0.003, int(clipped), ip)
+    B.check(lib.gr_ppo_loss_grad(C.byref(b), rows, gm.data_ptr(), gv.data_ptr(), sums.data_ptr(), st), "loss")
+    # one launch (with and without the optional policy outputs)
+    mu1, val1 = torch.zeros(rows, 4, device="cuda"), torch.zeros(rows, device="cuda")
+    gm1, gv1, sums1 = torch.zeros(rows, 4, device="cuda"), torch.zeros(rows, 4, device="cuda"), torch.zeros(16, device="cuda")
+    b1 = B.GrPpoBatch(mu1.data_ptr(), val1.data_ptr(), sigma.data_ptr(), actions.data_ptr(), logp.data_ptr(), adv.data_ptr(), ret.data_ptr(), old_v.data_ptr(),
+                      old_mu.data_ptr(), old_sig.data_ptr(), 0.2, 1.0, 0.003, int(clipped), ip)
+    B.check(lib.gr_policy_forward_loss(C.byref(p), obs.data_ptr(), cobs.data_ptr(), C.byref(b1), rows, gm1.data_ptr(), gv1.data_ptr(), sums1.data_ptr(), st), "fwd+loss")
+    gm2, gv2, sums2 = torch.zeros(rows, 4, device="cuda"), torch.zeros(rows, 4, device="cuda"), torch.zeros(16, device="cuda")
+    b2 = B.GrPpoBatch(None, None, sigma.data_ptr(), actions.data_ptr(), logp.data_ptr(), adv.data_ptr(), ret.data_ptr(), old_v.data_ptr(),
+                      old_mu.data_ptr(), old_sig.data_ptr(), 0.2, 1.0, 0.003, int(clipped), ip)
+    B.check(lib.gr_policy_forward_loss(C.byref(p), obs.data_ptr(), cobs.data_ptr(), C.byref(b2), rows, gm2.data_ptr(), gv2.data_ptr(), sums2.data_ptr(), st), "fwd+loss")
+    torch.cuda.synchronize()
+    assert torch.equal(mu, mu1) and torch.equal(val, val1)
+    assert torch.equal(gm, gm1) and torch.equal(gv, gv1) and torch.equal(gm, gm2) and torch.equal(gv, gv2)
+    assert torch.equal(sums[8:10], sums1[8:10]) and torch.equal(sums[8:10], sums2[8:10])          # maxima: exact
+    assert torch.allclose(sums[:8], sums1[:8], rtol=2e-5, atol=1e-5 * float(sums[:8].abs().max()))
+    assert torch.allclose(sums[:8], sums2[:8], rtol=2e-5, atol=1e-5 * float(sums[:8].abs().max()))
