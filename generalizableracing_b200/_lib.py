@@ -107,7 +107,7 @@ class GrMlpGrad(C.Structure):
 
 
 class GrBackwardJob(C.Structure):
-    _fields_ = [("policy", GrPolicy), ("obs", c_p), ("grad_actions", c_p), ("scale", c_p), ("out", GrMlpGrad), ("indices", c_p)]
+    _fields_ = [("policy", GrPolicy), ("obs", c_p), ("grad_actions", c_p), ("scale", c_p), ("out", GrMlpGrad), ("indices", c_p), ("obs_stride", c_i)]
 
 
 class GrAdamStep(C.Structure):
@@ -119,7 +119,7 @@ class GrAdamStep(C.Structure):
 class GrPpoBatch(C.Structure):
     _fields_ = [("mu", c_p), ("value", c_p), ("sigma", c_p), ("actions", c_p), ("old_log_prob", c_p), ("advantages", c_p), ("returns", c_p),
                 ("old_values", c_p), ("old_mu", c_p), ("old_sigma", c_p), ("clip_param", c_f), ("value_loss_coef", c_f), ("entropy_coef", c_f),
-                ("use_clipped_value_loss", c_i), ("indices", c_p)]
+                ("use_clipped_value_loss", c_i), ("indices", c_p), ("records", c_p)]
 
 
 class GrPpoStep(C.Structure):
@@ -177,6 +177,7 @@ class GrMesh(C.Structure):
 
 GR_REACH_LOG_NUM_RESET, GR_REACH_LOG_SUM_POS_ERR, GR_REACH_LOG_SUM_EPSUM, GR_REACH_LOG_NUM_TIMEOUT, GR_REACH_LOG_NUM_TERMINATED = 0, 1, 2, 12, 13
 GR_LOG_SHARDS = 256
+GR_RECORD_FLOATS = 48
 GR_PHILOX_CALL_ACTION = 16
 STATUS = {0: "GR_OK", -1: "GR_ERR_NULL", -2: "GR_ERR_SIZE", -3: "GR_ERR_ALIGN", -4: "GR_ERR_CONFIG", -5: "GR_ERR_SMEM"}
 
@@ -196,6 +197,7 @@ PROTOTYPES = {
     "gr_gae_scratch_bytes": (C.c_int64, [c_i]),
     "gr_compute_returns": (C.c_int, [C.POINTER(GrStorage), c_p, c_f, c_f, c_p, c_p, c_i, c_p]),
     "gr_advantage_normalize": (C.c_int, [C.POINTER(GrStorage), c_p, c_p]),
+    "gr_storage_pack_records": (C.c_int, [C.POINTER(GrStorage), c_p, c_p]),
     "gr_storage_gather": (C.c_int, [C.POINTER(GrStorage), c_p, c_i, C.POINTER(GrMiniBatch), c_p]),
     "gr_policy_packed_bytes": (C.c_int64, [c_i, c_i, c_i]),
     "gr_bptt_collect": (C.c_int, [C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom), C.POINTER(GrPolicy), c_i, c_i,

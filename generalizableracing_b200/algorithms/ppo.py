@@ -192,17 +192,26 @@ class PPO:
         batch = B.GrPpoBatch(g["mu_new"].data_ptr(), g["v_new"].data_ptr(), g["sigma4"].data_ptr(), desc.actions, desc.log_prob, desc.advantages, desc.returns,
                              desc.values, desc.mu, desc.sigma, float(self.clip_param), float(self.value_loss_coef), float(self.entropy_coef),
                              int(self.use_clipped_value_loss), idx_ptr)
+        # transition records (storage.pack_records, once per iteration): one scattered 192-byte record per sampled row instead of nine scattered
+        # columns (measured at 393,216 rows: the scattered 4 / 16-byte column reads were what the fused kernels waited for)
+        fused = {"0": False, "1": True}.get(os.environ.get("GRACING_PPO_FUSED_STEP", ""), mb <= 131072)
+        use_rec = os.environ.get("GRACING_PPO_RECORDS", "1") != "0" and sto.obs_shape[0] == 16 and (sto.privileged_obs_shape[0] or 16) == 16
+        rec_ptr = sto.pack_records().data_ptr() if use_rec else None
+        g["records"] = use_rec
         batch_fl = B.GrPpoBatch(None, None, g["sigma4"].data_ptr(), desc.actions, desc.log_prob, desc.advantages, desc.returns, desc.values, desc.mu, desc.sigma,
-                                float(self.clip_param), float(self.value_loss_coef), float(self.entropy_coef), int(self.use_clipped_value_loss), idx_ptr)
+                                float(self.clip_param), float(self.value_loss_coef), float(self.entropy_coef), int(self.use_clipped_value_loss), idx_ptr, rec_ptr)
         p_max_mu, p_max_v = ksums.data_ptr() + 8 * 4, ksums.data_ptr() + 9 * 4
-        jobs = (B.GrBackwardJob * 2)(B.GrBackwardJob(pol_both, s_obs, g["grad_mu"].data_ptr(), p_max_mu, gr_a, idx_ptr),
-                                     B.GrBackwardJob(pol_c, s_critic, g["grad_v"].data_ptr(), p_max_v, gr_c, idx_ptr))
+        if use_rec:
+            jobs = (B.GrBackwardJob * 2)(B.GrBackwardJob(pol_both, rec_ptr, g["grad_mu"].data_ptr(), p_max_mu, gr_a, idx_ptr, B.GR_RECORD_FLOATS),
+                                         B.GrBackwardJob(pol_c, rec_ptr + 16 * 4, g["grad_v"].data_ptr(), p_max_v, gr_c, idx_ptr, B.GR_RECORD_FLOATS))
+        else:
+            jobs = (B.GrBackwardJob * 2)(B.GrBackwardJob(pol_both, s_obs, g["grad_mu"].data_ptr(), p_max_mu, gr_a, idx_ptr, 0),
+                                         B.GrBackwardJob(pol_c, s_critic, g["grad_v"].data_ptr(), p_max_v, gr_c, idx_ptr, 0))
         # forward + loss + weight gradients of both nets as ONE launch (gr_ppo_fused_step) for small mini-batches, two launches
         # (gr_policy_forward_loss -> gr_actor_backward_jobs) for large ones.  Measured on the B200 (gpurun r2v):
         # 24,576 rows (4,096 envs): 1.21 vs 1.27 ms of update per iteration; 393,216 rows (65,536 envs): 7.3 vs 6.4 ms -- at that size the
         # one-launch kernel's tiles wait for their scattered rows with nothing left to overlap.  GRACING_PPO_FUSED_STEP=0|1 forces.
-        fused = {"0": False, "1": True}.get(os.environ.get("GRACING_PPO_FUSED_STEP", ""), mb <= 131072)
-        fstep = B.GrPpoStep(pol_both, s_obs, s_critic, batch, gr_a, gr_c, ksums.data_ptr(), 0.0)
+        fstep = B.GrPpoStep(pol_both, s_obs, s_critic, batch_fl if use_rec else batch, gr_a, gr_c, ksums.data_ptr(), 0.0)
         g["keep_k"] = (mlp_a, mlp_c, gr_a, gr_c, pol_both, pol_c, batch, batch_fl, adam, ptrs, seg_off, seg_n, jobs, fstep)
         g["kernel_sums"] = True                      # the running loss sums live in adam_state[5:7]
 
@@ -321,6 +330,8 @@ class PPO:
         if g.get("kernel_sums"):
             g["adam_state"][5:7].zero_()
         indices = torch.randperm(self.num_mini_batches * mb, requires_grad=False, device=self.device)
+        if g.get("records"):
+            sto.pack_records()                       # this iteration's transitions -> the static record buffer the captured step reads
         for _ in range(self.num_learning_epochs):
             for i in range(self.num_mini_batches):
                 g["idx"].copy_(indices[i * mb:(i + 1) * mb])

@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(kGroups * kTileEnvs + 32, 1) actor_backward_ke
   const float* __restrict__ G = job.grad_actions;
   const float* __restrict__ scale_ptr = job.scale;
   const int64_t* __restrict__ idx = job.indices;
+  const int64_t x_stride = job.obs_stride > 0 ? job.obs_stride : kObsDim;      // floats per observation row (transition records: 48)
   const GrMlpGrad out = job.out;
   constexpr int H1 = NL::kH1, H2 = NL::kH2, kHalves = H1 / 128;
   static_assert(H2 == 128 && (H1 == 128 || H1 == 256), "built for 16 -> 128|256 -> 128 -> 4");
@@ -177,10 +178,15 @@ __global__ void __launch_bounds__(kGroups * kTileEnvs + 32, 1) actor_backward_ke
     auto fetch = [&](const int64_t tile, const int64_t q, TileRows& t) {
       int64_t r = tile * kTileEnvs + row;
       r = r < R ? r : R - 1;
-      const float4* xr = reinterpret_cast<const float4*>(X) + q * 4;
+      const float4* xr = reinterpret_cast<const float4*>(X + q * x_stride);
       t.o0 = __ldcs(xr); t.o1 = __ldcs(xr + 1); t.o2 = __ldcs(xr + 2); t.o3 = __ldcs(xr + 3);
       if (!kPpo) {
         t.gr4 = __ldcs(reinterpret_cast<const float4*>(G) + r);
+      } else if (fz.b.records) {                   // transition records: the stored columns sit behind the observations of the same record
+        const float4* p = reinterpret_cast<const float4*>(fz.b.records) + q * (GR_RECORD_FLOATS / 4);
+        const float4 sc = __ldcs(p + 11);
+        if (!critic_job) { t.st_a = __ldcs(p + 8); t.st_omu = __ldcs(p + 9); t.st_osg = __ldcs(p + 10); t.st_logp = sc.x; t.st_adv = sc.y; }
+        else { t.st_ret = sc.z; t.st_ov = sc.w; }
       } else if (!critic_job) {
         t.st_a = __ldg(reinterpret_cast<const float4*>(fz.b.actions) + q);
         t.st_omu = __ldg(reinterpret_cast<const float4*>(fz.b.old_mu) + q);
@@ -453,6 +459,7 @@ static int check_job(const GrBackwardJob* j) {
   if (!out->w1 || !out->b1 || !out->w2 || !out->b2 || !out->w3 || !out->b3) return GR_ERR_NULL;
   if (out->out_dim < 1 || out->out_dim > 4) return GR_ERR_SIZE;
   if (j->policy.negative_slope < 0.0f || j->policy.negative_slope > 1.0f) return GR_ERR_CONFIG;
+  if (j->obs_stride < 0 || (j->obs_stride & 3) || (j->obs_stride > 0 && j->obs_stride < kObsDim)) return GR_ERR_SIZE;
   if ((reinterpret_cast<uintptr_t>(j->policy.packed) | reinterpret_cast<uintptr_t>(j->obs) | reinterpret_cast<uintptr_t>(j->grad_actions) |
        reinterpret_cast<uintptr_t>(out->w1) | reinterpret_cast<uintptr_t>(out->w2)) & 15u)
     return GR_ERR_ALIGN;
@@ -480,17 +487,18 @@ extern "C" int gr_actor_backward(const GrPolicy* policy, int32_t hidden, int32_t
                                  const float* scale, int64_t rows, const GrMlpGrad* out, void* stream) {
   if (!policy || !out) return GR_ERR_NULL;
   GrBackwardJob job;
-  job.policy = *policy; job.obs = obs; job.grad_actions = grad_actions; job.scale = scale; job.out = *out; job.indices = nullptr;
+  job.policy = *policy; job.obs = obs; job.grad_actions = grad_actions; job.scale = scale; job.out = *out; job.indices = nullptr; job.obs_stride = 0;
   return gr_actor_backward_jobs(&job, 1, hidden, hidden2, rows, stream);
 }
 
 extern "C" int gr_ppo_fused_step(const GrPpoStep* st, int64_t rows, void* stream) {
   if (!st) return GR_ERR_NULL;
   const GrPpoBatch& b = st->batch;
-  if (!st->policy.packed || !st->obs || !st->critic_obs || !st->sums || !b.sigma || !b.actions || !b.old_log_prob || !b.advantages || !b.returns || !b.old_mu ||
-      !b.old_sigma)
-    return GR_ERR_NULL;
-  if (b.use_clipped_value_loss && !b.old_values) return GR_ERR_NULL;
+  if (!st->policy.packed || !st->sums || !b.sigma) return GR_ERR_NULL;
+  const bool rec = b.records != nullptr;
+  if (!rec && (!st->obs || !st->critic_obs || !b.actions || !b.old_log_prob || !b.advantages || !b.returns || !b.old_mu || !b.old_sigma)) return GR_ERR_NULL;
+  if (!rec && b.use_clipped_value_loss && !b.old_values) return GR_ERR_NULL;
+  if (rec && (reinterpret_cast<uintptr_t>(b.records) & 15u)) return GR_ERR_ALIGN;
   if (rows <= 0) return GR_ERR_SIZE;
   if (st->cotangent_scale < 0.0f) return GR_ERR_CONFIG;
   GrBackwardJob jobs[2];
@@ -498,16 +506,17 @@ extern "C" int gr_ppo_fused_step(const GrPpoStep* st, int64_t rows, void* stream
   for (int k = 0; k < 2; ++k) {
     jobs[k].policy = st->policy;
     if (k == 1) jobs[k].policy.packed = static_cast<const uint8_t*>(st->policy.packed) + net_bytes;
-    jobs[k].obs = k == 0 ? st->obs : st->critic_obs;
-    jobs[k].grad_actions = st->obs;                // (unused by the fused kernel; non-null for check_job)
+    jobs[k].obs = rec ? b.records + 16 * k : (k == 0 ? st->obs : st->critic_obs);
+    jobs[k].grad_actions = jobs[k].obs;            // (unused by the fused kernel; non-null for check_job)
     jobs[k].scale = st->sums;                      // (unused)
     jobs[k].out = k == 0 ? st->actor_grad : st->critic_grad;
     jobs[k].indices = b.indices;
+    jobs[k].obs_stride = rec ? GR_RECORD_FLOATS : 0;
     const int rc = check_job(&jobs[k]);
     if (rc != GR_OK) return rc;
   }
-  if ((reinterpret_cast<uintptr_t>(b.actions) | reinterpret_cast<uintptr_t>(b.old_mu) | reinterpret_cast<uintptr_t>(b.old_sigma) | reinterpret_cast<uintptr_t>(b.sigma)) & 15u)
-    return GR_ERR_ALIGN;
+  if (reinterpret_cast<uintptr_t>(b.sigma) & 15u) return GR_ERR_ALIGN;
+  if (!rec && ((reinterpret_cast<uintptr_t>(b.actions) | reinterpret_cast<uintptr_t>(b.old_mu) | reinterpret_cast<uintptr_t>(b.old_sigma)) & 15u)) return GR_ERR_ALIGN;
   if (jobs[0].out.out_dim != 4 || jobs[1].out.out_dim != 1) return GR_ERR_SIZE;
   PpoFusedArgs fz;
   fz.b = b;

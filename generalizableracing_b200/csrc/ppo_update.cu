@@ -62,7 +62,17 @@ __global__ void __launch_bounds__(kFwdGroups * kTileEnvs, 1) policy_forward_kern
     r = r < R ? r : R - 1;
     return gather ? __ldg(idx + r) : r;
   };
+  const float4* __restrict__ rec = kLoss ? reinterpret_cast<const float4*>(la.b.records) : nullptr;
   auto fetch = [&](const int64_t q, Rows& t) {
+    if (kLoss && rec) {                            // one 192-byte transition record (gr_storage_pack_records): 12 contiguous 16-byte loads
+      const float4* p = rec + q * (GR_RECORD_FLOATS / 4);
+      t.o0 = __ldcs(p); t.o1 = __ldcs(p + 1); t.o2 = __ldcs(p + 2); t.o3 = __ldcs(p + 3);
+      t.c0 = __ldcs(p + 4); t.c1 = __ldcs(p + 5); t.c2 = __ldcs(p + 6); t.c3 = __ldcs(p + 7);
+      t.a = __ldcs(p + 8); t.omu = __ldcs(p + 9); t.osg = __ldcs(p + 10);
+      const float4 sc = __ldcs(p + 11);
+      t.logp = sc.x; t.adv = sc.y; t.ret = sc.z; t.ov = sc.w;
+      return;
+    }
     const float4* xo = reinterpret_cast<const float4*>(obs) + q * 4;
     const float4* xc = reinterpret_cast<const float4*>(critic_obs) + q * 4;
     t.o0 = __ldcs(xo); t.o1 = __ldcs(xo + 1); t.o2 = __ldcs(xo + 2); t.o3 = __ldcs(xo + 3);
@@ -314,15 +324,20 @@ extern "C" int gr_policy_forward_gather(const GrPolicy* policy, const float* obs
 
 extern "C" int gr_policy_forward_loss(const GrPolicy* policy, const float* obs, const float* critic_obs, const GrPpoBatch* b, int64_t rows, float* grad_mu,
                                       float* grad_value, float* sums, void* stream) {
-  if (!policy || !policy->packed || !obs || !critic_obs || !b || !grad_mu || !grad_value || !sums) return GR_ERR_NULL;
-  if (!b->sigma || !b->actions || !b->old_log_prob || !b->advantages || !b->returns || !b->old_mu || !b->old_sigma) return GR_ERR_NULL;
-  if (b->use_clipped_value_loss && !b->old_values) return GR_ERR_NULL;
+  if (!policy || !policy->packed || !b || !grad_mu || !grad_value || !sums || !b->sigma) return GR_ERR_NULL;
   if (rows <= 0) return GR_ERR_SIZE;
   if (policy->negative_slope < 0.0f || policy->negative_slope > 1.0f) return GR_ERR_CONFIG;
-  if ((reinterpret_cast<uintptr_t>(policy->packed) | reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(critic_obs) | reinterpret_cast<uintptr_t>(b->actions) |
-       reinterpret_cast<uintptr_t>(b->old_mu) | reinterpret_cast<uintptr_t>(b->old_sigma) | reinterpret_cast<uintptr_t>(b->sigma) | reinterpret_cast<uintptr_t>(grad_mu) |
-       reinterpret_cast<uintptr_t>(grad_value) | (b->mu ? reinterpret_cast<uintptr_t>(b->mu) : 0)) & 15u)
-    return GR_ERR_ALIGN;
+  uintptr_t align = reinterpret_cast<uintptr_t>(policy->packed) | reinterpret_cast<uintptr_t>(b->sigma) | reinterpret_cast<uintptr_t>(grad_mu) |
+                    reinterpret_cast<uintptr_t>(grad_value) | (b->mu ? reinterpret_cast<uintptr_t>(b->mu) : 0);
+  if (b->records) {                                // everything a row needs comes from its transition record
+    align |= reinterpret_cast<uintptr_t>(b->records);
+  } else {
+    if (!obs || !critic_obs || !b->actions || !b->old_log_prob || !b->advantages || !b->returns || !b->old_mu || !b->old_sigma) return GR_ERR_NULL;
+    if (b->use_clipped_value_loss && !b->old_values) return GR_ERR_NULL;
+    align |= reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(critic_obs) | reinterpret_cast<uintptr_t>(b->actions) |
+             reinterpret_cast<uintptr_t>(b->old_mu) | reinterpret_cast<uintptr_t>(b->old_sigma);
+  }
+  if (align & 15u) return GR_ERR_ALIGN;
   FwdLossArgs la;
   la.b = *b; la.grad_mu = grad_mu; la.grad_value = grad_value; la.sums = sums;
   return launch_policy_forward<true>(policy, obs, critic_obs, b->indices, const_cast<float*>(b->mu), const_cast<float*>(b->value), rows, la,

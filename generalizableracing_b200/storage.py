@@ -78,6 +78,14 @@ class RolloutStorage:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
 
+    def pack_records(self) -> torch.Tensor:
+        """Transition records [T*N, 48]: the columns one PPO mini-batch row needs, side by side (include/gracing.h, GR_RECORD_FLOATS): packed
+        once per iteration after compute_returns so that the update kernels read one scattered 192-byte record per sampled row."""
+        if getattr(self, "_records", None) is None:
+            self._records = torch.empty(self.num_transitions_per_env * self.num_envs, B.GR_RECORD_FLOATS, device=self.device)
+        B.check(self._lib.gr_storage_pack_records(C.byref(self._desc()), self._records.data_ptr(), self._stream()), "gr_storage_pack_records")
+        return self._records
+
     def _desc(self) -> B.GrStorage:
         """Argument struct of the buffers (built once: the class never re-binds its tensors; do not re-bind them either)."""
         if self._desc_cache is not None:

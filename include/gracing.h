@@ -382,7 +382,10 @@ int gr_actor_backward(const GrPolicy* policy, int32_t hidden, int32_t hidden2, c
                       const float* grad_actions /* [rows,4] */, const float* scale, int64_t rows, const GrMlpGrad* out, void* stream);
 /* one launch for up to two nets of the same widths over the same number of rows (a PPO step's actor and critic) */
 /* indices (optional, [rows] int64): row r reads obs[indices[r]] -- the mini-batch gather of rollout_storage.py:179-187 done on load */
-typedef struct GrBackwardJob { GrPolicy policy; const float* obs; const float* grad_actions; const float* scale; GrMlpGrad out; const int64_t* indices; } GrBackwardJob;
+typedef struct GrBackwardJob { GrPolicy policy; const float* obs; const float* grad_actions; const float* scale; GrMlpGrad out; const int64_t* indices;
+                               int32_t obs_stride;   /* floats between consecutive observation rows: 0 = 16 (dense [rows,16]); GR_RECORD_FLOATS when `obs`
+                                                        points into transition records (+16 floats for the critic's observation) */
+} GrBackwardJob;
 int gr_actor_backward_jobs(const GrBackwardJob* jobs, int32_t n_jobs, int32_t hidden, int32_t hidden2, int64_t rows, void* stream);
 
 /* ---- PPO update on the kernels (forward, loss gradients; the weight gradients come from gr_actor_backward) -----------------
@@ -407,6 +410,8 @@ typedef struct GrPpoBatch {
   int32_t use_clipped_value_loss;
   const int64_t* indices;                              /* optional [rows] int64: the STORED columns (actions .. old_sigma) are read at row indices[r]
                                                           (the mini-batch gather done on load); mu / value and the gradients stay dense */
+  const float* records;                                /* optional (gr_policy_forward_loss, gr_ppo_fused_step): transition records (gr_storage_pack_records); when set,
+                                                          obs / critic_obs and the stored columns of row r all come from record indices[r] */
 } GrPpoBatch;
 int gr_ppo_loss_grad(const GrPpoBatch* batch, int64_t rows, float* grad_mu /* [rows,4] */, float* grad_value /* [rows,4] */,
                      float* sums /* [16] accumulated */, void* stream);
@@ -421,6 +426,12 @@ int gr_policy_forward_loss(const GrPolicy* policy, const float* obs, const float
  * gathers obs / critic_obs and the stored columns on load.  actor_grad / critic_grad accumulate (zero them first, out_dim 4 / 1,
  * scale_is_maxabs ignored); sums[0..7] accumulate as gr_ppo_loss_grad's (sums[8..9] are not written).  The cotangent rows go to fp16 as
  * cotangent_scale x the un-normalised per-row gradient (0 => 1/64; the accumulators are divided by rows * cotangent_scale at the flush). */
+/* Transition records: the columns one PPO mini-batch row needs, side by side, GR_RECORD_FLOATS floats per transition of the [T*N] storage:
+ * [0,16) policy obs | [16,32) critic obs | [32,36) action | [36,40) old mean | [40,44) old std | 44 old log-prob | 45 advantage | 46 return |
+ * 47 old value.  Packed once per PPO iteration (after gr_compute_returns); with GrPpoBatch.records / GrBackwardJob.obs_stride set the update
+ * kernels read ONE scattered 192-byte record per sampled row instead of nine scattered columns.  Needs obs_dim = critic_dim = 16, act_dim = 4. */
+#define GR_RECORD_FLOATS 48
+int gr_storage_pack_records(const GrStorage* s, float* records /* [T*N][GR_RECORD_FLOATS], 16-byte aligned */, void* stream);
 typedef struct GrPpoStep {
   GrPolicy policy;                     /* packed actor + critic, widths (128,128) */
   const float* obs; const float* critic_obs;

@@ -273,7 +273,17 @@ def test_fused_step_equals_the_three_launches(cuda_lib, rows, pool, clipped, ent
                       old_mu.data_ptr(), old_sig.data_ptr(), 0.2, 1.0, entropy_coef, int(clipped), ip)
     step = B.GrPpoStep(p, obs.data_ptr(), cobs.data_ptr(), b1, ga1, gc1, sums1.data_ptr(), 0.0)
     B.check(lib.gr_ppo_fused_step(C.byref(step), rows, st), "gr_ppo_fused_step")
+    # ... and with the rows coming from transition records
+    rec = torch.cat([obs, cobs, actions, old_mu, old_sig, logp[:, None], adv[:, None], ret[:, None], old_v[:, None]], dim=1).contiguous()
+    g2, ga2, gc2 = grads()
+    sums2 = torch.zeros(16, device="cuda")
+    b2 = B.GrPpoBatch(None, None, sigma.data_ptr(), None, None, None, None, None, None, None, 0.2, 1.0, entropy_coef, int(clipped), ip, rec.data_ptr())
+    step2 = B.GrPpoStep(p, None, None, b2, ga2, gc2, sums2.data_ptr(), 0.0)
+    B.check(lib.gr_ppo_fused_step(C.byref(step2), rows, st), "gr_ppo_fused_step (records)")
     torch.cuda.synchronize()
+    assert torch.allclose(sums2[:8], sums1[:8], rtol=2e-5, atol=1e-5 * float(sums1[:8].abs().max()))
+    for x, y in zip(g1, g2):
+        assert float((x - y).abs().max()) <= 2e-5 * float(x.abs().max()) + 1e-12
     assert torch.allclose(sums1[:8], sums[:8], rtol=2e-4, atol=1e-4 * float(sums[:8].abs().max())), (sums1[:8], sums[:8])
     assert int(sums1[7]) == rows
     names = [f"{net}.{n}" for net in ("actor", "critic") for n in ("w1", "b1", "w2", "b2", "w3", "b3")]
@@ -325,9 +335,46 @@ def test_forward_with_loss_equals_forward_then_loss(cuda_lib, rows, pool, clippe
     b2 = B.GrPpoBatch(None, None, sigma.data_ptr(), actions.data_ptr(), logp.data_ptr(), adv.data_ptr(), ret.data_ptr(), old_v.data_ptr(),
                       old_mu.data_ptr(), old_sig.data_ptr(), 0.2, 1.0, 0.003, int(clipped), ip)
     B.check(lib.gr_policy_forward_loss(C.byref(p), obs.data_ptr(), cobs.data_ptr(), C.byref(b2), rows, gm2.data_ptr(), gv2.data_ptr(), sums2.data_ptr(), st), "fwd+loss")
+    # transition records: the same columns side by side, one 192-byte record per transition
+    rec = torch.cat([obs, cobs, actions, old_mu, old_sig, logp[:, None], adv[:, None], ret[:, None], old_v[:, None]], dim=1).contiguous()
+    assert rec.shape == (pool, B.GR_RECORD_FLOATS)
+    gm3, gv3, sums3 = torch.zeros(rows, 4, device="cuda"), torch.zeros(rows, 4, device="cuda"), torch.zeros(16, device="cuda")
+    b3 = B.GrPpoBatch(None, None, sigma.data_ptr(), None, None, None, None, None, None, None, 0.2, 1.0, 0.003, int(clipped), ip, rec.data_ptr())
+    B.check(lib.gr_policy_forward_loss(C.byref(p), None, None, C.byref(b3), rows, gm3.data_ptr(), gv3.data_ptr(), sums3.data_ptr(), st), "fwd+loss (records)")
+    # weight gradients reading the observation rows out of the records (obs_stride) against dense gathered rows
+    def bwd(obs_ptr, cobs_ptr, stride, index_ptr):
+        gs = [torch.zeros_like(t) for l in (la, lc) for m in l for t in (m.weight, m.bias)]
+        ga, gc = B.GrMlpGrad(*(t.data_ptr() for t in gs[:6]), 4, 1), B.GrMlpGrad(*(t.data_ptr() for t in gs[6:]), 1, 1)
+        pc = B.GrPolicy(packed.data_ptr() + packed.numel() // 2, sigma.data_ptr(), 0.01)
+        jobs = (B.GrBackwardJob * 2)(B.GrBackwardJob(p, obs_ptr, gm.data_ptr(), sums.data_ptr() + 32, ga, index_ptr, stride),
+                                     B.GrBackwardJob(pc, cobs_ptr, gv.data_ptr(), sums.data_ptr() + 36, gc, index_ptr, stride))
+        B.check(lib.gr_actor_backward_jobs(jobs, 2, 128, 128, rows, st), "bwd")
+        return gs
+    g_dense = bwd(obs.data_ptr(), cobs.data_ptr(), 0, ip)
+    g_rec = bwd(rec.data_ptr(), rec.data_ptr() + 64, B.GR_RECORD_FLOATS, ip)
     torch.cuda.synchronize()
+    assert torch.equal(gm, gm3) and torch.equal(gv, gv3) and torch.equal(sums[8:10], sums3[8:10])
+    assert torch.allclose(sums[:8], sums3[:8], rtol=2e-5, atol=1e-5 * float(sums[:8].abs().max()))
+    for x, y in zip(g_dense, g_rec):
+        assert float(x.abs().max()) > 0 and float((x - y).abs().max()) <= 2e-5 * float(x.abs().max()) + 1e-12
     assert torch.equal(mu, mu1) and torch.equal(val, val1)
     assert torch.equal(gm, gm1) and torch.equal(gv, gv1) and torch.equal(gm, gm2) and torch.equal(gv, gv2)
     assert torch.equal(sums[8:10], sums1[8:10]) and torch.equal(sums[8:10], sums2[8:10])          # maxima: exact
     assert torch.allclose(sums[:8], sums1[:8], rtol=2e-5, atol=1e-5 * float(sums[:8].abs().max()))
     assert torch.allclose(sums[:8], sums2[:8], rtol=2e-5, atol=1e-5 * float(sums[:8].abs().max()))
+
+
+def test_storage_pack_records(cuda_lib):
+    """gr_storage_pack_records against torch.cat of the storage's own columns."""
+    from generalizableracing_b200 import _lib as B
+    from generalizableracing_b200.storage import RolloutStorage
+    T, N = 5, 333
+    sto = RolloutStorage("rl", N, T, [16], [16], [4], device="cuda:0")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for t in (sto.observations, sto.privileged_observations, sto.actions, sto.mu, sto.sigma, sto.actions_log_prob, sto.advantages, sto.returns, sto.values):
+        t.copy_(torch.randn(t.shape, device="cuda", generator=g))
+    rec = sto.pack_records()
+    f = lambda t: t.reshape(T * N, -1)
+    want = torch.cat([f(sto.observations), f(sto.privileged_observations), f(sto.actions), f(sto.mu), f(sto.sigma), f(sto.actions_log_prob), f(sto.advantages),
+                      f(sto.returns), f(sto.values)], dim=1)
+    assert rec.shape == (T * N, B.GR_RECORD_FLOATS) and torch.equal(rec, want)
