@@ -445,10 +445,10 @@ def run_ours(args):
     # so the copies of step t overlap the kernel of step t+1 (the consumer reads step t's results while t+1 runs).
     env = envs[0]
     depth = 3
-    h_act = [(torch.randn(N, 4) * 0.5).pin_memory() for _ in range(depth)]
-    h_obs = [torch.empty(N, 16).pin_memory() for _ in range(depth)]
-    h_rew = [torch.empty(N).pin_memory() for _ in range(depth)]
-    h_done = [torch.empty(N, dtype=torch.int64).pin_memory() for _ in range(depth)]
+    hb = env.host_buffers(depth)                     # pinned; obs | reward | dones of a set contiguous: one device->host copy per step
+    for b in hb:
+        b["actions"].copy_(torch.randn(N, 4) * 0.5)
+    h_act, h_obs, h_rew, h_done = [b["actions"] for b in hb], [b["obs"] for b in hb], [b["reward"] for b in hb], [b["dones"] for b in hb]
     torch.cuda.synchronize(dev)
 
     def e2e_loop(n, d):
@@ -483,15 +483,19 @@ def run_ours(args):
     e2e_ms = med(e2e_v)
     e2e_value = world * N * Ke / (e2e_ms * 1e-3)
     e2e_sync_ms = med(timed_e2e(Ke, 1, max(5, e2e_reps // 4)))          # one step in flight: H2D -> kernel -> D2H strictly in sequence
-    assert torch.isfinite(h_obs[0]).all() and h_done[0].min() >= 0
-    h_done_int64 = h_done
+    assert torch.isfinite(h_obs[0]).all() and h_done[0].min() >= 0 and h_done[0].max() <= 1 and float(h_rew[0].abs().max()) < 1e3
+    packed_sets = (h_obs, h_rew, h_done)
+    h_obs, h_rew = [torch.empty(N, 16).pin_memory() for _ in range(depth)], [torch.empty(N).pin_memory() for _ in range(depth)]
+    h_done = [torch.empty(N, dtype=torch.int64).pin_memory() for _ in range(depth)]              # three separate buffers: three copies per step
+    e2e_sep_ms = med(timed_e2e(Ke, depth, max(5, e2e_reps // 3)))
     h_done = [torch.empty(N, dtype=torch.uint8).pin_memory() for _ in range(depth)]           # the same call with one-byte dones
     e2e_u8_ms = med(timed_e2e(Ke, depth, max(5, e2e_reps // 3)))
     assert int(h_done[0].max()) <= 1
-    h_done = h_done_int64
+    h_obs, h_rew, h_done = packed_sets
     h2d = N * 4 * 4
     d2h = N * 16 * 4 + N * 4 + N * 8
-    probe = copy_only_probe(dev, world, lib, N, h2d, d2h, Ke)
+    probe = copy_only_probe(dev, world, lib, N, h2d, d2h, Ke, packed=1)
+    probe["separate_buffers"] = copy_only_probe(dev, world, lib, N, h2d, d2h, Ke, packed=0)
 
     # ---- C5: the one collective of the path (NCCL policy-gradient all-reduce) and a whole PPO iteration with it inside the captured
     # update graph, 65,536 envs per GPU (on_policy_runner.py:135-183)
@@ -544,8 +548,11 @@ def run_ours(args):
             "timing": timing,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                     "ms_per_step": e2e_ms / Ke, "repeats": e2e_reps, "rep_ms_min": float(e2e_v.min()), "rep_ms_max": float(e2e_v.max()),
-                    "api": f"RacingVecEnv.step_host -> gr_host_pipe_step/wait (C ABI, pinned HOST buffers: actions in; obs, reward, int64 dones out "
-                           f"every step; {depth} steps in flight, results of step t read while step t+1 runs)",
+                    "api": f"RacingVecEnv.step_host -> gr_host_pipe_step/wait (C ABI, pinned HOST buffers from env.host_buffers(): actions in; obs, reward, "
+                           f"int64 dones out every step -- contiguous in host memory, so they cross PCIe as one copy; {depth} steps in flight, results of "
+                           f"step t read while step t+1 runs)",
+                    "separate_buffers": {"value": world * N * Ke / (e2e_sep_ms * 1e-3), "ms_per_step": e2e_sep_ms / Ke,
+                                         "note": "same call with three separately allocated pinned output tensors (three device->host copies per step)"},
                     "sync_per_step": {"value": world * N * Ke / (e2e_sync_ms * 1e-3), "ms_per_step": e2e_sync_ms / Ke,
                                       "note": "same call, one step in flight (H2D -> kernel -> D2H in sequence)"},
                     "byte_dones": {"value": world * N * Ke / (e2e_u8_ms * 1e-3), "ms_per_step": e2e_u8_ms / Ke, "d2h_bytes_per_step": N * 16 * 4 + N * 4 + N,
@@ -575,10 +582,11 @@ def run_ours(args):
         print(json.dumps(line))
 
 
-def copy_only_probe(dev, world, lib, N, h2d, d2h, steps):
-    """The platform's ceiling for the e2e loop: the SAME transfers per step (actions in; obs, reward, int64 dones out), one cudaMemcpyAsync
-    per buffer from pinned memory, H2D on one stream and D2H on another, all ranks concurrently, NO kernel and no dependencies
-    (gr_host_copy_probe: a C loop, so that Python's per-call cost is not what gets measured)."""
+def copy_only_probe(dev, world, lib, N, h2d, d2h, steps, packed=1):
+    """The platform's ceiling for the e2e loop: the SAME transfers per step (actions in; obs, reward, int64 dones out) from pinned memory --
+    obs | reward | dones as ONE copy (packed, what the pipe issues for env.host_buffers()) or one cudaMemcpyAsync per buffer -- H2D on one
+    stream and D2H on another, all ranks concurrently, NO kernel and no dependencies (gr_host_copy_probe2: a C loop, so that Python's
+    per-call cost is not what gets measured)."""
     import ctypes as C
     n = max(50, min(steps, 500))
     out = []
@@ -586,14 +594,15 @@ def copy_only_probe(dev, world, lib, N, h2d, d2h, steps):
         barrier(world)
         torch.cuda.synchronize(dev)
         sec = C.c_double()
-        rc = lib.gr_host_copy_probe(N, n, 8, C.byref(sec))
+        rc = lib.gr_host_copy_probe2(N, n, 8, int(packed), C.byref(sec))
         if rc:
             return {"error": int(rc)}
         out.append(sec.value * 1e3)
     ms = med(reduce_vector(out, world, dev, "max"))
     return {"us_per_step": ms * 1e3 / n, "aggregate_GBps": world * (h2d + d2h) * n / (ms * 1e-3) / 1e9, "per_gpu_GBps": (h2d + d2h) * n / (ms * 1e-3) / 1e9,
             "env_steps_per_s_ceiling": world * N * n / (ms * 1e-3),
-            "what": f"copies only (pinned buffers, {h2d} B H2D + {d2h} B D2H per step, two streams, C loop, {world} rank(s) concurrently): the platform limit of the e2e loop"}
+            "what": f"copies only (pinned buffers, {h2d} B H2D + {d2h} B D2H per step as {'one copy' if packed else 'three copies'}, two streams, C loop, "
+                    f"{world} rank(s) concurrently): the platform limit of the e2e loop"}
 
 
 def bench_collective(dev, cfg, table, N, rank, world, T: int = 24):

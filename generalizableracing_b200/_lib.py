@@ -128,7 +128,8 @@ class GrPpoStep(C.Structure):
 
 
 class GrHostStep(C.Structure):
-    _fields_ = [("action", c_p), ("obs", c_p), ("reward", c_p), ("dones", c_p), ("critic_obs", c_p), ("time_out", c_p), ("dones_u8", c_p)]
+    _fields_ = [("action", c_p), ("obs", c_p), ("reward", c_p), ("dones", c_p), ("critic_obs", c_p), ("time_out", c_p), ("dones_u8", c_p),
+                ("outputs_contiguous", c_i)]
 
 
 GR_HOST_PIPE_MAX_DEPTH = 4
@@ -229,6 +230,7 @@ PROTOTYPES = {
                                     C.POINTER(GrHostStep), c_p, C.POINTER(C.c_int64)]),
     "gr_host_pipe_wait": (C.c_int, [c_p, C.c_int64]),
     "gr_host_copy_probe": (C.c_int, [c_i, c_i, c_i, C.POINTER(C.c_double)]),
+    "gr_host_copy_probe2": (C.c_int, [c_i, c_i, c_i, c_i, C.POINTER(C.c_double)]),
     "gr_mesh_bvh_max_nodes": (C.c_int64, [c_i]),
     "gr_mesh_build_bvh": (C.c_int, [c_p, c_p, c_i, c_i, c_p, C.c_int64, c_p, c_p, C.POINTER(c_i)]),
     "gr_uav_collision_ray": (C.c_int, [C.POINTER(GrMesh), c_p, c_p, c_i, c_p, c_i, c_f, c_f, c_f, c_p, c_p]),

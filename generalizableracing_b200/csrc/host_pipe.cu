@@ -44,7 +44,10 @@ extern "C" int gr_host_pipe_create(int32_t num_envs, int32_t depth, void* comput
   p->num_envs = num_envs; p->depth = depth; p->issued = 0; p->arena = nullptr;
   p->compute = reinterpret_cast<cudaStream_t>(compute_stream);
   const size_t N = (size_t)num_envs;
-  const size_t per_slot = align256(N * 16) + 2 * align256(N * 64) + align256(N * 4) + 3 * align256(N) + align256(N * 8);
+  // obs | reward | int64 dones sit back to back (no padding in between: 68 N is a multiple of 8 for even N), so that a caller whose three
+  // host buffers are laid out the same way gets ONE device->host copy per step (measured with tools/pcie_probe.cu on the B200 box:
+  // 108.9 -> 101.1 us per 65,536-env step for the same bytes; the copy alone, without the concurrent action upload, takes 90.2 us)
+  const size_t per_slot = align256(N * 16) + align256(N * 64 + N * 4 + N * 8 + 8) + align256(N * 64) + 3 * align256(N);
   cudaError_t e = cudaMalloc(&p->arena, per_slot * depth);
   if (e != cudaSuccess) { delete p; return (int)e; }
   e = cudaStreamCreateWithFlags(&p->h2d, cudaStreamNonBlocking);
@@ -55,13 +58,14 @@ extern "C" int gr_host_pipe_create(int32_t num_envs, int32_t depth, void* comput
     GrHostPipe::Slot& sl = p->slot[s];
     char* q = base + per_slot * s;
     sl.action = reinterpret_cast<float*>(q); q += align256(N * 16);
-    sl.obs = reinterpret_cast<float*>(q); q += align256(N * 64);
+    sl.obs = reinterpret_cast<float*>(q);
+    sl.reward = reinterpret_cast<float*>(q + N * 64);
+    sl.dones = reinterpret_cast<int64_t*>(q + ((N * 68 + 7) & ~(size_t)7));
+    q += align256(N * 64 + N * 4 + N * 8 + 8);
     sl.critic = reinterpret_cast<float*>(q); q += align256(N * 64);
-    sl.reward = reinterpret_cast<float*>(q); q += align256(N * 4);
     sl.terminated = reinterpret_cast<uint8_t*>(q); q += align256(N);
     sl.time_out = reinterpret_cast<uint8_t*>(q); q += align256(N);
-    sl.dones_u8 = reinterpret_cast<uint8_t*>(q); q += align256(N);
-    sl.dones = reinterpret_cast<int64_t*>(q);
+    sl.dones_u8 = reinterpret_cast<uint8_t*>(q);
     sl.busy = false;
     cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&sl.kernel_done, cudaEventDisableTiming);
@@ -115,9 +119,17 @@ extern "C" int gr_host_pipe_step(GrHostPipe* p, const GrConfig* cfg, const GrTra
   cudaEventRecord(sl.kernel_done, p->compute);
   // stage 3: results device -> host
   cudaStreamWaitEvent(p->d2h, sl.kernel_done, 0);
-  e = cudaMemcpyAsync(host->obs, sl.obs, N * 64, cudaMemcpyDeviceToHost, p->d2h);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(host->reward, sl.reward, N * 4, cudaMemcpyDeviceToHost, p->d2h);
-  if (e == cudaSuccess && host->dones) e = cudaMemcpyAsync(host->dones, sl.dones, N * 8, cudaMemcpyDeviceToHost, p->d2h);
+  const char* h_obs = reinterpret_cast<const char*>(host->obs);
+  // the caller's buffers mirror the slot AND are one allocation (its promise: a copy may not span separately pinned allocations): one copy
+  const bool packed = host->outputs_contiguous != 0 && (N & 1) == 0 && host->dones && reinterpret_cast<const char*>(host->reward) == h_obs + N * 64 &&
+                      reinterpret_cast<const char*>(host->dones) == h_obs + N * 68;
+  if (packed) {
+    e = cudaMemcpyAsync(host->obs, sl.obs, N * 76, cudaMemcpyDeviceToHost, p->d2h);
+  } else {
+    e = cudaMemcpyAsync(host->obs, sl.obs, N * 64, cudaMemcpyDeviceToHost, p->d2h);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host->reward, sl.reward, N * 4, cudaMemcpyDeviceToHost, p->d2h);
+    if (e == cudaSuccess && host->dones) e = cudaMemcpyAsync(host->dones, sl.dones, N * 8, cudaMemcpyDeviceToHost, p->d2h);
+  }
   if (e == cudaSuccess && host->dones_u8) e = cudaMemcpyAsync(host->dones_u8, sl.dones_u8, N, cudaMemcpyDeviceToHost, p->d2h);
   if (e == cudaSuccess && host->critic_obs) e = cudaMemcpyAsync(host->critic_obs, sl.critic, N * 64, cudaMemcpyDeviceToHost, p->d2h);
   if (e == cudaSuccess && host->time_out) e = cudaMemcpyAsync(host->time_out, sl.time_out, N, cudaMemcpyDeviceToHost, p->d2h);
@@ -140,7 +152,12 @@ extern "C" int gr_host_pipe_wait(GrHostPipe* p, int64_t ticket) {
 // obs / reward / dones device->host on another -- from pinned buffers, no kernel, no dependencies.  Returns the seconds the loop took
 // (host clock between two device synchronisations).  Several ranks call it concurrently to find the aggregate limit of a node.
 #include <chrono>
+extern "C" int gr_host_copy_probe2(int32_t num_envs, int32_t steps, int32_t dones_bytes, int32_t packed, double* seconds_out);
 extern "C" int gr_host_copy_probe(int32_t num_envs, int32_t steps, int32_t dones_bytes, double* seconds_out) {
+  return gr_host_copy_probe2(num_envs, steps, dones_bytes, 0, seconds_out);
+}
+// packed != 0: obs | reward | dones as ONE device->host copy per step (what gr_host_pipe_step does for a caller whose buffers are contiguous)
+extern "C" int gr_host_copy_probe2(int32_t num_envs, int32_t steps, int32_t dones_bytes, int32_t packed, double* seconds_out) {
   if (!seconds_out) return GR_ERR_NULL;
   if (num_envs <= 0 || steps <= 0 || dones_bytes < 0 || dones_bytes > 8) return GR_ERR_SIZE;
   const size_t N = (size_t)num_envs, in_b = N * 16, out_b[3] = {N * 64, N * 4, N * (size_t)dones_bytes};
@@ -157,6 +174,10 @@ extern "C" int gr_host_copy_probe(int32_t num_envs, int32_t steps, int32_t dones
     auto loop = [&](int n) {
       for (int t = 0; t < n; ++t) {
         cudaMemcpyAsync(d_in, h_in, in_b, cudaMemcpyHostToDevice, s_in);
+        if (packed) {
+          cudaMemcpyAsync(h_out, d_out, out_b[0] + out_b[1] + out_b[2], cudaMemcpyDeviceToHost, s_out);
+          continue;
+        }
         size_t off = 0;
         for (int k = 0; k < 3; ++k) {
           if (out_b[k]) cudaMemcpyAsync(static_cast<char*>(h_out) + off, static_cast<char*>(d_out) + off, out_b[k], cudaMemcpyDeviceToHost, s_out);

@@ -42,3 +42,37 @@ def test_step_host_rejects_device_or_misshaped_tensors(cuda_lib):
         env.step_host(torch.zeros(64, 4, device="cuda"), torch.empty(64, 16), torch.empty(64))
     with pytest.raises(ValueError):
         env.step_host(torch.zeros(64, 4), torch.empty(64, 8), torch.empty(64))
+
+
+@pytest.mark.parametrize("N", [4096, 1002, 65536])
+def test_contiguous_host_buffers_take_the_single_copy_path(cuda_lib, N):
+    """env.host_buffers(): obs | reward | int64 dones of a set back to back in one pinned block -> gr_host_pipe_step ships them as ONE
+    device->host copy; same bits as the device-tensor step, and nothing outside the three views is written (guard bytes survive)."""
+    from generalizableracing_b200.env import RacingVecEnv
+    cfg, table = RacingCfg.for_stage(1), synthetic_track_table()
+    ref, env = RacingVecEnv(cfg, table, N, seed=8), RacingVecEnv(cfg, table, N, seed=8)
+    ref.reset(); env.reset()
+    sets = env.host_buffers(3)
+    for b in sets:
+        assert b["reward"].data_ptr() == b["obs"].data_ptr() + N * 64 and b["dones"].data_ptr() == b["obs"].data_ptr() + N * 68
+        b["_block"][N * 76:] = 0x5A
+    g = torch.Generator().manual_seed(4)
+    tickets, acts = [], []
+    for t in range(9):
+        b = sets[t % 3]
+        if t >= 3:
+            env.wait_host(tickets[t - 3])
+            obs, rew, dones, _ = ref.step(acts[t - 3].cuda())
+            assert torch.equal(b["obs"], obs.cpu()) and torch.equal(b["reward"], rew.cpu()) and torch.equal(b["dones"], dones.cpu()), t
+        a = torch.randn(N, 4, generator=g) * 0.5
+        acts.append(a)
+        b["actions"].copy_(a)
+        tickets.append(env.step_host(b["actions"], b["obs"], b["reward"], b["dones"], depth=3))
+    for t in range(6, 9):
+        env.wait_host(tickets[t])
+        obs, rew, dones, _ = ref.step(acts[t].cuda())
+        b = sets[t % 3]
+        assert torch.equal(b["obs"], obs.cpu()) and torch.equal(b["reward"], rew.cpu()) and torch.equal(b["dones"], dones.cpu()), t
+    assert all(bool((b["_block"][N * 76:] == 0x5A).all()) for b in sets)
+    assert torch.equal(env.planes, ref.planes)
+    env.close()
