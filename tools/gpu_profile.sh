@@ -2,7 +2,7 @@
 # round-2 check-up + profile: suite, smoke, bench as the driver runs it, then (plain run first, same command) the ncu launch list and
 # ONE --set full capture of the step kernel and of the window / sweep kernels from the same bench command
 set -u
-out=gpurun_out; mkdir -p "$out"; tag=${1:-r2k}
+out=gpurun_out; mkdir -p "$out"; tag=${1:-prof}
 timeout 1200 python -m pytest tests -m gpu -q -x --durations=8 > "$out/${tag}_pytest_gpu.log" 2>&1
 echo "pytest -m gpu: exit $?" | tee "$out/${tag}_status.txt"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > "$out/${tag}_smoke.log" 2>&1
