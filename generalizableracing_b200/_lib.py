@@ -93,7 +93,7 @@ class GrPolicy(C.Structure):
 
 class GrCollectIO(C.Structure):
     _fields_ = [("obs0", c_p), ("critic_obs0", c_p), ("obs_out", c_p), ("critic_obs_out", c_p), ("aux_out", c_p), ("last_values", c_p),
-                ("episode_acc", c_p), ("log_accum", c_p), ("episode_log", c_p), ("gamma", c_f), ("groups_per_cta", c_i)]
+                ("episode_acc", c_p), ("log_accum", c_p), ("episode_log", c_p), ("gamma", c_f), ("groups_per_cta", c_i), ("coop_reset_columns", c_i)]
 
 
 class GrBpttCollectIO(C.Structure):
@@ -199,6 +199,7 @@ PROTOTYPES = {
     "gr_compute_returns": (C.c_int, [C.POINTER(GrStorage), c_p, c_f, c_f, c_p, c_p, c_i, c_p]),
     "gr_advantage_normalize": (C.c_int, [C.POINTER(GrStorage), c_p, c_p]),
     "gr_storage_pack_records": (C.c_int, [C.POINTER(GrStorage), c_p, c_p]),
+    "gr_storage_pack_records_permuted": (C.c_int, [C.POINTER(GrStorage), c_p, C.c_int64, c_p, c_p]),
     "gr_storage_gather": (C.c_int, [C.POINTER(GrStorage), c_p, c_i, C.POINTER(GrMiniBatch), c_p]),
     "gr_policy_packed_bytes": (C.c_int64, [c_i, c_i, c_i]),
     "gr_bptt_collect": (C.c_int, [C.POINTER(GrConfig), C.POINTER(GrTrack), C.POINTER(GrState), C.POINTER(GrRandom), C.POINTER(GrPolicy), c_i, c_i,
@@ -267,7 +268,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.gr_abi_version() != 3:
+    if lib.gr_abi_version() != 4:
         raise ImportError("libgracing.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -198,24 +198,36 @@ class PPO:
         use_rec = os.environ.get("GRACING_PPO_RECORDS", "1") != "0" and sto.obs_shape[0] == 16 and (sto.privileged_obs_shape[0] or 16) == 16
         rec_ptr = sto.pack_records().data_ptr() if use_rec else None
         g["records"] = use_rec
-        batch_fl = B.GrPpoBatch(None, None, g["sigma4"].data_ptr(), desc.actions, desc.log_prob, desc.advantages, desc.returns, desc.values, desc.mu, desc.sigma,
-                                float(self.clip_param), float(self.value_loss_coef), float(self.entropy_coef), int(self.use_clipped_value_loss), idx_ptr, rec_ptr)
+        # dense records (default with records): the iteration's permutation is applied ONCE, while packing (storage.pack_records(indices)), so
+        # mini-batch i of every epoch is the contiguous record slice [i*mb, (i+1)*mb) -- the update kernels stream their rows (indices = NULL)
+        # instead of gathering one scattered record per row behind a scattered index read; one captured step per mini-batch slot.
+        dense = use_rec and os.environ.get("GRACING_PPO_DENSE_RECORDS", "1") != "0"
+        g["dense_records"] = dense
         p_max_mu, p_max_v = ksums.data_ptr() + 8 * 4, ksums.data_ptr() + 9 * 4
-        if use_rec:
-            jobs = (B.GrBackwardJob * 2)(B.GrBackwardJob(pol_both, rec_ptr, g["grad_mu"].data_ptr(), p_max_mu, gr_a, idx_ptr, B.GR_RECORD_FLOATS),
-                                         B.GrBackwardJob(pol_c, rec_ptr + 16 * 4, g["grad_v"].data_ptr(), p_max_v, gr_c, idx_ptr, B.GR_RECORD_FLOATS))
-        else:
-            jobs = (B.GrBackwardJob * 2)(B.GrBackwardJob(pol_both, s_obs, g["grad_mu"].data_ptr(), p_max_mu, gr_a, idx_ptr, 0),
-                                         B.GrBackwardJob(pol_c, s_critic, g["grad_v"].data_ptr(), p_max_v, gr_c, idx_ptr, 0))
-        # forward + loss + weight gradients of both nets as ONE launch (gr_ppo_fused_step) for small mini-batches, two launches
-        # (gr_policy_forward_loss -> gr_actor_backward_jobs) for large ones.  Measured on the B200 (gpurun r2v):
-        # 24,576 rows (4,096 envs): 1.21 vs 1.27 ms of update per iteration; 393,216 rows (65,536 envs): 7.3 vs 6.4 ms -- at that size the
-        # one-launch kernel's tiles wait for their scattered rows with nothing left to overlap.  GRACING_PPO_FUSED_STEP=0|1 forces.
-        fstep = B.GrPpoStep(pol_both, s_obs, s_critic, batch_fl if use_rec else batch, gr_a, gr_c, ksums.data_ptr(), 0.0)
-        g["keep_k"] = (mlp_a, mlp_c, gr_a, gr_c, pol_both, pol_c, batch, batch_fl, adam, ptrs, seg_off, seg_n, jobs, fstep)
+
+        def slot_args(i):
+            ip = None if dense else idx_ptr
+            rp = rec_ptr + i * mb * B.GR_RECORD_FLOATS * 4 if dense else rec_ptr
+            batch_fl = B.GrPpoBatch(None, None, g["sigma4"].data_ptr(), desc.actions, desc.log_prob, desc.advantages, desc.returns, desc.values, desc.mu, desc.sigma,
+                                    float(self.clip_param), float(self.value_loss_coef), float(self.entropy_coef), int(self.use_clipped_value_loss), ip, rp)
+            if use_rec:
+                jobs = (B.GrBackwardJob * 2)(B.GrBackwardJob(pol_both, rp, g["grad_mu"].data_ptr(), p_max_mu, gr_a, ip, B.GR_RECORD_FLOATS),
+                                             B.GrBackwardJob(pol_c, rp + 16 * 4, g["grad_v"].data_ptr(), p_max_v, gr_c, ip, B.GR_RECORD_FLOATS))
+            else:
+                jobs = (B.GrBackwardJob * 2)(B.GrBackwardJob(pol_both, s_obs, g["grad_mu"].data_ptr(), p_max_mu, gr_a, idx_ptr, 0),
+                                             B.GrBackwardJob(pol_c, s_critic, g["grad_v"].data_ptr(), p_max_v, gr_c, idx_ptr, 0))
+            # forward + loss + weight gradients of both nets as ONE launch (gr_ppo_fused_step) for small mini-batches, two launches
+            # (gr_policy_forward_loss -> gr_actor_backward_jobs) for large ones.  Measured on the B200 (gpurun r2v):
+            # 24,576 rows (4,096 envs): 1.21 vs 1.27 ms of update per iteration; 393,216 rows (65,536 envs): 7.3 vs 6.4 ms -- at that size the
+            # one-launch kernel's tiles wait for their scattered rows with nothing left to overlap.  GRACING_PPO_FUSED_STEP=0|1 forces.
+            fstep = B.GrPpoStep(pol_both, s_obs, s_critic, batch_fl if use_rec else batch, gr_a, gr_c, ksums.data_ptr(), 0.0)
+            return batch_fl, jobs, fstep
+        slots = [slot_args(i) for i in range(self.num_mini_batches if dense else 1)]
+        g["keep_k"] = (mlp_a, mlp_c, gr_a, gr_c, pol_both, pol_c, batch, adam, ptrs, seg_off, seg_n, slots)
         g["kernel_sums"] = True                      # the running loss sums live in adam_state[5:7]
 
-        def step():
+        def step(slot=0):
+            batch_fl, jobs, fstep = slots[slot]
             st = torch.cuda.current_stream(dev).cuda_stream
             B.check(lib.gr_policy_pack(C.byref(mlp_a), C.byref(mlp_c), g["packed"].data_ptr(), st), "gr_policy_pack")
             with torch.no_grad():
@@ -304,6 +316,13 @@ class PPO:
         with torch.cuda.graph(graph, stream=side):
             step()
         g["graph"] = graph
+        if g.get("dense_records"):             # one captured step per mini-batch slot: the same launches on the slot's contiguous record slice
+            g["graphs"] = [graph]
+            for i in range(1, self.num_mini_batches):
+                gi = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gi, stream=side, pool=graph.pool()):
+                    step(i)
+                g["graphs"].append(gi)
         return g
 
     def _update_graphed(self):
@@ -330,12 +349,21 @@ class PPO:
         if g.get("kernel_sums"):
             g["adam_state"][5:7].zero_()
         indices = torch.randperm(self.num_mini_batches * mb, requires_grad=False, device=self.device)
-        if g.get("records"):
-            sto.pack_records()                       # this iteration's transitions -> the static record buffer the captured step reads
-        for _ in range(self.num_learning_epochs):
-            for i in range(self.num_mini_batches):
-                g["idx"].copy_(indices[i * mb:(i + 1) * mb])
-                g["graph"].replay()
+        if g.get("dense_records"):
+            # this iteration's transitions -> the static record buffer, IN MINI-BATCH ORDER: record r = transition indices[r] (the reference draws
+            # one permutation per update and reuses it in every epoch, rollout_storage.py:165-178), so slot i's captured step streams records
+            # [i*mb, (i+1)*mb) -- no index copy, no gather
+            sto.pack_records(indices)
+            for _ in range(self.num_learning_epochs):
+                for i in range(self.num_mini_batches):
+                    g["graphs"][i].replay()
+        else:
+            if g.get("records"):
+                sto.pack_records()                   # this iteration's transitions -> the static record buffer the captured step reads
+            for _ in range(self.num_learning_epochs):
+                for i in range(self.num_mini_batches):
+                    g["idx"].copy_(indices[i * mb:(i + 1) * mb])
+                    g["graph"].replay()
         num_updates = self.num_learning_epochs * self.num_mini_batches
         sums = g["adam_state"][5:7] if g.get("kernel_sums") else g["sums"]
         out = torch.cat([sums / num_updates, g["lr"].reshape(1)]).tolist()          # the iteration's only host read
@@ -348,6 +376,7 @@ class PPO:
         if self._graph is not None:
             torch.cuda.synchronize(self.device)
             self._graph.pop("graph", None)
+            self._graph.pop("graphs", None)
             self._graph = None
             import gc
             gc.collect()

@@ -10,6 +10,7 @@ torch modules; the PPO ratio is formed against the log-probs stored here).  Work
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -66,6 +67,7 @@ class FusedCollector:
         self.episode_log = torch.zeros(B.GR_LOG_SHARDS, 4, device=dev)
         self.gamma = float(gamma)
         self.groups_per_cta = int(groups_per_cta)
+        self.coop_reset_columns = int(os.environ.get("GRACING_COLLECT_COOP_COLUMNS", "0"))      # 0 = as many as fit (<= 4), -1 = off (A/B switch)
         self._pol = B.GrPolicy(self.packed.data_ptr(), self.sigma.data_ptr(), self.slope)
 
     def _mlp(self, l1, l2, l3, out) -> B.GrMlp:
@@ -95,7 +97,8 @@ class FusedCollector:
             dst = env._outs[k]
         env._flip = k ^ 1
         io = B.GrCollectIO(src["obs"].data_ptr(), src["critic"].data_ptr(), dst["obs"].data_ptr(), dst["critic"].data_ptr(), dst["aux"].data_ptr(),
-                           self.last_values.data_ptr(), self.episode_acc.data_ptr(), env._log_accum.data_ptr(), self.episode_log.data_ptr(), self.gamma, self.groups_per_cta)
+                           self.last_values.data_ptr(), self.episode_acc.data_ptr(), env._log_accum.data_ptr(), self.episode_log.data_ptr(), self.gamma, self.groups_per_cta,
+                           self.coop_reset_columns)
         rng = env._rng
         rng.rnd = None
         rng.step = env._step_count & 0xFFFFFFFF

@@ -35,7 +35,8 @@ struct BpttObsSink {
 
 template <class NL, int G, bool kNoise, bool kStats>
 __global__ void __launch_bounds__(G * kTileEnvs, 1) bptt_collect_kernel(const GrConfig cfg, const GrTrack track, const GrState st, const GrRandom rng,
-                                                                       const GrPolicy pol, const GrBpttCollectIO cio, const int track_in_smem) {
+                                                                       const GrPolicy pol, const GrBpttCollectIO cio, const int track_in_smem,
+                                                                       const int coop_off, const int coop_k) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* w_smem = smem;                                        // actor
   uint8_t* h_smem = smem + NL::kNetBytes;                        // G activation tiles
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) bptt_collect_kernel(const Gr
     io.tape_stride = cio.tape_stride;
     io.loss = cio.loss + (int64_t)t * N;
     io.loss_terms = cio.loss_terms ? cio.loss_terms + (int64_t)t * N * 3 : nullptr;
-    const Draws<true> draws{rs, nullptr};
+    const CompactDraws draws{rs, coop_k > 0 ? track_rows + coop_off + (tid >> 5) * (7 * coop_k) : nullptr, coop_k};      // (ppo_collect.cu)
     const bool last = t == T - 1;
     BpttObsSink sink;
     sink.obs_row = (last ? reinterpret_cast<float4*>(cio.obs_out) : reinterpret_cast<float4*>(cio.obs_seq) + (int64_t)(t + 1) * N * 4) + (int64_t)i * 4;
@@ -171,13 +172,16 @@ static int launch_bptt(const GrConfig* cfg, const GrTrack* tr, const GrState* st
   const size_t fixed = (size_t)NL::kNetBytes + (size_t)G * NL::kHBytes + 128;
   const int track_in_smem = fixed + track_bytes <= 227 * 1024;
   if (!track_in_smem) track_bytes = 0;
-  const size_t bytes = fixed + track_bytes;
-  if (bytes > 227 * 1024) return GR_ERR_SMEM;
+  if (fixed + track_bytes > 227 * 1024) return GR_ERR_SMEM;
+  const size_t per_k = (size_t)(G * kTileEnvs / 32) * 7 * sizeof(float4);      // staging columns of the cooperative reset draws (gr_common.cuh)
+  int coop_k = (int)((227 * 1024 - fixed - track_bytes) / per_k);
+  coop_k = coop_k > 4 ? 4 : coop_k;
+  const size_t bytes = fixed + track_bytes + (size_t)coop_k * per_k;
   auto kernel = bptt_collect_kernel<NL, G, kNoise, kStats>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) return (int)e;
   const int grid = (st->num_envs + G * kTileEnvs - 1) / (G * kTileEnvs);
-  kernel<<<grid, G * kTileEnvs, bytes, s>>>(*cfg, *tr, *st, *rng, *pol, *io, track_in_smem);
+  kernel<<<grid, G * kTileEnvs, bytes, s>>>(*cfg, *tr, *st, *rng, *pol, *io, track_in_smem, (int)(track_bytes / sizeof(float4)), coop_k);
   return (int)cudaGetLastError();
 }
 

@@ -131,6 +131,9 @@ struct Draws {
   }
   // slot 6 (thr_est_error normal, consumed by a reset only)
   __device__ __forceinline__ float thr_normal(float from_normals8) const { return have_normals ? from_normals8 : rs.normal6(); }
+  // called by the step body with the warp converged once `reset` is known: stages the reset draws (if a staging area was given) and returns
+  // the source the reset tail reads from
+  __device__ __forceinline__ Draws staged(bool reset, bool with_noise) const;
 };
 
 // Warp-cooperative generation of the reset draws (Philox mode): call with all 32 lanes converged; `reset` = this lane's env resets in
@@ -155,6 +158,52 @@ __device__ __forceinline__ void stage_reset_draws(const RandSrc<true>& rs, float
 #endif
 }
 __device__ __forceinline__ void stage_reset_draws(const RandSrc<false>&, float4*, bool, uint32_t, bool) {}
+template <bool kPhilox>
+__device__ __forceinline__ Draws<kPhilox> Draws<kPhilox>::staged(bool reset, bool with_noise) const {
+  if (kPhilox && spec) stage_reset_draws(rs, const_cast<float4*>(spec), reset, rs.ph_env(), with_noise);
+  return *this;
+}
+
+// The same hand-over for kernels whose shared memory is nearly full (the fused collection kernels: weights + activation tiles): each WARP
+// owns a compact staging area of [7 calls][K columns] float4 (112 * K bytes), enough for the first K resetting lanes of a step; a lane
+// beyond them (P(>= 3 resets in a warp) = 15 % at a 4.2 % reset rate, 1.2 % for >= 5) draws for itself as before.  Same counters, same bits.
+struct CompactDraws {
+  const RandSrc<true>& rs;
+  float4* spec;             // shared: this warp's [7][K] columns, or nullptr (every lane draws for itself)
+  int K;
+  int col = -1;             // this lane's column after staged(), -1: not staged
+  bool have_normals = true;
+  __device__ __forceinline__ float4 get4(int call) const {
+    if (col >= 0 && call < 10) return spec[spec_slot(call) * K + col];
+    return rs.get4(call);
+  }
+  __device__ __forceinline__ float thr_normal(float from_normals8) const { return have_normals ? from_normals8 : rs.normal6(); }
+  __device__ __forceinline__ CompactDraws staged(bool reset, bool with_noise) const {
+    CompactDraws d = *this;
+#ifndef GR_CPU_EMUL
+    if (!spec) return d;
+    unsigned m = __ballot_sync(0xffffffffu, reset);
+    if (m == 0u) return d;
+    const int lane = threadIdx.x & 31;
+    const int rank = __popc(m & ((1u << lane) - 1u));               // this lane's place among the resetting lanes
+    if (reset && rank < K) d.col = rank;
+    const int calls = with_noise ? 7 : 5;
+    __syncwarp();                                                   // (the columns may still be read by a straggler of the previous step)
+    for (int s = 0; s < K && m; ++s) {
+      const int r = __ffs(m) - 1;
+      m &= m - 1;
+      Philox ph = rs.ph;
+      ph.c0 = __shfl_sync(0xffffffffu, rs.ph.c0, r);
+      if (lane < calls) {
+        const uint4 x = ph((uint32_t)(2 + lane));
+        spec[lane * K + s] = make_float4(u01(x.x), u01(x.y), u01(x.z), u01(x.w));
+      }
+    }
+    __syncwarp();
+#endif
+    return d;
+  }
+};
 
 // Gate table slice staged in shared memory: rows of types [type_lo, type_lo + ntypes).
 struct TrackSmem {

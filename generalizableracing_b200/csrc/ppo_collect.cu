@@ -61,7 +61,7 @@ struct FusedObsSink {
 template <int G, bool kNoise, bool kStats>
 __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrConfig cfg, const GrTrack track, const GrState st, const GrRandom rng,
                                                                       const GrPolicy pol, const GrStorage sto, const GrCollectIO cio,
-                                                                      const int track_in_smem) {
+                                                                      const int track_in_smem, const int coop_off, const int coop_k) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* w_smem = smem;                                        // actor net | critic net
   uint8_t* h_smem = smem + 2 * kNetBytes;                        // G activation tiles
@@ -176,7 +176,9 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
 
     // ---- env.step (same body as gr_step_fwd) while the critic's layer 2 runs; its observations are the next step's
     //      operands (kept packed in registers until the activation tile is free) and storage rows
-    const Draws<true> draws{rs, nullptr};
+    // reset draws: the warp generates the seven Philox calls of its first coop_k resetting lanes together (CompactDraws, gr_common.cuh) --
+    // left to the resetting lane alone they are ~770 issue slots of the warp in a kernel that is bound by issue slots
+    const CompactDraws draws{rs, coop_k > 0 ? track_rows + coop_off + (tid >> 5) * (7 * coop_k) : nullptr, coop_k};
     const bool last = t == T - 1;
     FusedObsSink sink;
     sink.obs_row = (last ? reinterpret_cast<float4*>(cio.obs_out) : reinterpret_cast<float4*>(sto.obs) + (int64_t)(t + 1) * N * 4) + (int64_t)i * 4;
@@ -280,12 +282,18 @@ static int launch_collect(const GrConfig* cfg, const GrTrack* tr, const GrState*
   const size_t fixed = 2 * (size_t)kNetBytes + (size_t)G * kHBytes + 128;
   const int track_in_smem = fixed + track_bytes <= 227 * 1024;
   if (!track_in_smem) track_bytes = 0;
-  const size_t bytes = fixed + track_bytes;
+  // what is left goes to the warps' staging columns of the cooperative reset draws: 7 calls x K columns x 16 B per warp, K <= 4
+  const size_t per_k = (size_t)(G * kTileEnvs / 32) * 7 * sizeof(float4);
+  int coop_k = (int)((227 * 1024 - fixed - track_bytes) / per_k);
+  coop_k = coop_k > 4 ? 4 : coop_k;
+  if (io->coop_reset_columns < 0) coop_k = 0;
+  else if (io->coop_reset_columns > 0 && io->coop_reset_columns < coop_k) coop_k = io->coop_reset_columns;
+  const size_t bytes = fixed + track_bytes + (size_t)coop_k * per_k;
   auto kernel = ppo_collect_kernel<G, kNoise, kStats>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) return (int)e;
   const int grid = (st->num_envs + G * kTileEnvs - 1) / (G * kTileEnvs);
-  kernel<<<grid, G * kTileEnvs, bytes, s>>>(*cfg, *tr, *st, *rng, *pol, *sto, *io, track_in_smem);
+  kernel<<<grid, G * kTileEnvs, bytes, s>>>(*cfg, *tr, *st, *rng, *pol, *sto, *io, track_in_smem, (int)(track_bytes / sizeof(float4)), coop_k);
   return (int)cudaGetLastError();
 }
 

@@ -129,8 +129,8 @@ __device__ __forceinline__ void write_observations(const GrConfig& cfg, const En
 
 // _reset_idx for one env (L/envs/manager_based_diff_rl_env.py:362-410): curricula, root-state sampler,
 // controller/dynamics/command reset.  Mutates e; returns the new origin.
-template <bool kNoise, bool kPhilox>
-__device__ __forceinline__ V3 reset_env(const GrConfig& cfg, const TrackSmem& tr, EnvRegs& e, const Draws<kPhilox>& rs, float thr_normal) {
+template <bool kNoise, bool kPhilox, class DrawsT>
+__device__ __forceinline__ V3 reset_env(const GrConfig& cfg, const TrackSmem& tr, EnvRegs& e, const DrawsT& rs, float thr_normal) {
   const int type = (int)pk_type(e.pk);
   int level = (int)pk_level(e.pk);
   const int acc = (int)pk_acc(e.pk);
@@ -303,9 +303,9 @@ __device__ __forceinline__ bool GlobalObsSink::state_final(EnvRegs& e, float4& e
 // eps0 / e.es4 / e.es5 = episode sums of the reward terms (kStats): logged + zeroed here on reset, the non-reset accumulation
 // is left to the caller (add_episode_sums with out.terms), who knows when its copy of the sums has arrived; lsum = LossManager
 // episode sums (kDiff && kStats, PL_LOSSSUM).  Returns false for a lane past the last env.
-template <bool kNoise, bool kDiff, bool kPhilox, bool kStats, class ObsSink>
+template <bool kNoise, bool kDiff, bool kPhilox, bool kStats, class ObsSink, class DrawsT>
 __device__ __forceinline__ bool racing_step_body(const GrConfig& cfg, const TrackSmem& tr, EnvRegs& e, const float4 a_t, const float4 n01,
-                                                 const float4 n23, const Draws<kPhilox>& draws, float4& eps0, float4& lsum, const GrStepIO& io,
+                                                 const float4 n23, const DrawsT& draws_in, float4& eps0, float4& lsum, const GrStepIO& io,
                                                  const int i, const bool active, const ObsSink& sink, StepOut& out) {
   const int type = (int)pk_type(e.pk);
   int level = (int)pk_level(e.pk);
@@ -448,7 +448,7 @@ __device__ __forceinline__ bool racing_step_body(const GrConfig& cfg, const Trac
 
   // ---- 7. reset (L/envs/manager_based_diff_rl_env.py:232-247,362-410) ----
   const bool reset = terminated || time_out;
-  if (kPhilox && draws.spec) stage_reset_draws(draws.rs, const_cast<float4*>(draws.spec), reset && active, draws.rs.ph_env(), kNoise);
+  const DrawsT draws = draws_in.staged(reset && active, kNoise);       // (warp-cooperative reset draws, when the caller gave a staging area)
   bool noise_dirty = false;
   bool passed = pass_pre;                                 // 8. on an env that did not reset this is the same test
   if (reset) {

@@ -262,14 +262,18 @@ __global__ void storage_gather_kernel(const GrStorage s, const int64_t* __restri
 // transition records: the columns one PPO mini-batch row needs, side by side (GR_RECORD_FLOATS = 48 floats = 192 B per transition):
 //   [0,16) policy obs | [16,32) critic obs | [32,36) action | [36,40) old mean | [40,44) old std | 44 old log-prob | 45 advantage |
 //   46 return | 47 old value
-// Packed once per PPO iteration (after compute_returns); the update kernels then read ONE scattered 192-byte record per sampled row
-// instead of nine scattered columns.  One thread per (transition, 16-byte chunk).
+// Packed once per PPO iteration (after compute_returns); the update kernels then read ONE 192-byte record per sampled row
+// instead of nine scattered columns.  One thread per (record, 16-byte chunk).
+// perm (optional, [rows] int64): record r holds transition perm[r] -- the mini-batch permutation of rollout_storage.py:165 applied ONCE per
+// iteration (the reference reuses one permutation for every epoch), so that mini-batch i of every epoch is the CONTIGUOUS record range
+// [i * mb, (i + 1) * mb): the update kernels stream their rows instead of gathering them.
 // ---------------------------------------------------------------------------------------------
-__global__ void storage_pack_records_kernel(const GrStorage s, float4* __restrict__ rec, const int64_t rows) {
+__global__ void storage_pack_records_kernel(const GrStorage s, const int64_t* __restrict__ perm, float4* __restrict__ rec, const int64_t rows) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t r = tid / 12;
-  if (r >= rows) return;
-  const int c = (int)(tid - r * 12);
+  const int64_t d = tid / 12;
+  if (d >= rows) return;
+  const int c = (int)(tid - d * 12);
+  const int64_t r = perm ? __ldg(perm + d) : d;
   float4 v;
   if (c < 4) v = __ldg(reinterpret_cast<const float4*>(s.obs) + r * 4 + c);
   else if (c < 8) v = __ldg(reinterpret_cast<const float4*>(s.critic_obs ? s.critic_obs : s.obs) + r * 4 + (c - 4));
@@ -277,7 +281,7 @@ __global__ void storage_pack_records_kernel(const GrStorage s, float4* __restric
   else if (c == 9) v = __ldg(reinterpret_cast<const float4*>(s.mu) + r);
   else if (c == 10) v = __ldg(reinterpret_cast<const float4*>(s.sigma) + r);
   else v = make_float4(__ldg(s.log_prob + r), __ldg(s.advantages + r), __ldg(s.returns + r), __ldg(s.values + r));
-  rec[r * 12 + c] = v;
+  rec[d * 12 + c] = v;
 }
 
 }  // namespace gr
@@ -361,15 +365,23 @@ extern "C" int gr_compute_returns(const GrStorage* s, const float* last_values, 
   return GR_OK;
 }
 
-extern "C" int gr_storage_pack_records(const GrStorage* s, float* records, void* stream) {
+static int pack_records_impl(const GrStorage* s, const int64_t* perm, int64_t num, float* records, void* stream) {
   int rc = check_storage(s);
   if (rc != GR_OK) return rc;
   if (!records || !s->values || !s->advantages || !s->returns || !s->log_prob || !s->mu || !s->sigma) return GR_ERR_NULL;
   if (s->obs_dim != 16 || s->act_dim != 4 || (s->critic_obs && s->critic_dim != 16)) return GR_ERR_SIZE;
   if (mis16(records)) return GR_ERR_ALIGN;
-  const int64_t rows = (int64_t)s->T * s->N;
-  storage_pack_records_kernel<<<(unsigned)((rows * 12 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*s, reinterpret_cast<float4*>(records), rows);
+  const int64_t rows = perm ? num : (int64_t)s->T * s->N;
+  if (rows < 1 || rows > (int64_t)s->T * s->N) return GR_ERR_SIZE;
+  storage_pack_records_kernel<<<(unsigned)((rows * 12 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*s, perm, reinterpret_cast<float4*>(records), rows);
   return (int)cudaGetLastError();
+}
+
+extern "C" int gr_storage_pack_records(const GrStorage* s, float* records, void* stream) { return pack_records_impl(s, nullptr, 0, records, stream); }
+
+extern "C" int gr_storage_pack_records_permuted(const GrStorage* s, const int64_t* perm, int64_t num, float* records, void* stream) {
+  if (!perm) return GR_ERR_NULL;
+  return pack_records_impl(s, perm, num, records, stream);
 }
 
 extern "C" int gr_storage_gather(const GrStorage* s, const int64_t* indices, int32_t B, const GrMiniBatch* out, void* stream) {

@@ -78,12 +78,20 @@ class RolloutStorage:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
 
-    def pack_records(self) -> torch.Tensor:
+    def pack_records(self, indices: torch.Tensor = None) -> torch.Tensor:
         """Transition records [T*N, 48]: the columns one PPO mini-batch row needs, side by side (include/gracing.h, GR_RECORD_FLOATS): packed
-        once per iteration after compute_returns so that the update kernels read one scattered 192-byte record per sampled row."""
+        once per iteration after compute_returns so that the update kernels read one 192-byte record per sampled row.  ``indices`` (the
+        iteration's ``torch.randperm`` over [T*N], rollout_storage.py:165): record r holds transition ``indices[r]``, i.e. mini-batch i of every
+        epoch is the contiguous slice ``records[i*mb:(i+1)*mb]``."""
         if getattr(self, "_records", None) is None:
             self._records = torch.empty(self.num_transitions_per_env * self.num_envs, B.GR_RECORD_FLOATS, device=self.device)
-        B.check(self._lib.gr_storage_pack_records(C.byref(self._desc()), self._records.data_ptr(), self._stream()), "gr_storage_pack_records")
+        if indices is None:
+            B.check(self._lib.gr_storage_pack_records(C.byref(self._desc()), self._records.data_ptr(), self._stream()), "gr_storage_pack_records")
+        else:
+            if indices.dtype != torch.int64 or indices.numel() > self._records.shape[0] or not indices.is_contiguous() or indices.device != self._records.device:
+                raise ValueError("pack_records: indices must be a contiguous int64 tensor of <= T*N transition ids on the storage's device")
+            B.check(self._lib.gr_storage_pack_records_permuted(C.byref(self._desc()), indices.data_ptr(), indices.numel(), self._records.data_ptr(), self._stream()),
+                    "gr_storage_pack_records_permuted")
         return self._records
 
     def _desc(self) -> B.GrStorage:

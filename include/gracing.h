@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GR_ABI_VERSION 3
+#define GR_ABI_VERSION 4
 
 /* ---- layout constants (mirrored by generalizableracing_b200/layout.py) ---- */
 #define GR_OBS_DIM 16
@@ -329,6 +329,9 @@ typedef struct GrCollectIO {
                                         -- the runner's rewbuffer / lenbuffer book keeping (on_policy_runner.py:160-173) */
   float gamma;                       /* time-out bootstrap r += gamma * V(s_t) * time_out */
   int32_t groups_per_cta;            /* 128-env tiles per thread block: 1, 2, 4 or 0 = pick (fewest that fit one wave) */
+  int32_t coop_reset_columns;        /* warp-cooperative Philox draws for resetting envs: staging columns per warp (112 B each); 0 = as many as
+                                        the shared memory left by weights / activation tiles / gate table holds (<= 4), -1 = off (each
+                                        resetting lane draws for itself), k > 0 = at most k.  Same counters, same bits either way. */
 } GrCollectIO;
 /* packed size of `nets` (1 = actor only, 2 = actor + critic) MLPs of widths 16 -> hidden -> hidden2; < 0: unsupported widths */
 int64_t gr_policy_packed_bytes(int32_t hidden, int32_t hidden2, int32_t nets);
@@ -432,6 +435,11 @@ int gr_policy_forward_loss(const GrPolicy* policy, const float* obs, const float
  * kernels read ONE scattered 192-byte record per sampled row instead of nine scattered columns.  Needs obs_dim = critic_dim = 16, act_dim = 4. */
 #define GR_RECORD_FLOATS 48
 int gr_storage_pack_records(const GrStorage* s, float* records /* [T*N][GR_RECORD_FLOATS], 16-byte aligned */, void* stream);
+/* The same with the iteration's mini-batch permutation applied while packing: record r < num holds transition perm[r] (perm [num <= T*N] int64, the
+ * torch.randperm of rollout_storage.py:165 -- ONE permutation per update, reused by every epoch), so mini-batch i of every epoch is the
+ * contiguous record range [i*mb, (i+1)*mb): pass records + i*mb*GR_RECORD_FLOATS with indices = NULL to the update kernels, which then
+ * stream their rows instead of gathering them (same rows in the same order: bit-identical results). */
+int gr_storage_pack_records_permuted(const GrStorage* s, const int64_t* perm, int64_t num, float* records, void* stream);
 typedef struct GrPpoStep {
   GrPolicy policy;                     /* packed actor + critic, widths (128,128) */
   const float* obs; const float* critic_obs;

@@ -177,3 +177,40 @@ def test_collector_refuses_what_it_cannot_run(cuda_lib):
         FusedCollector(env, ActorCritic(16, 16, 4, activation="elu").cuda(), sto, 0.99)
     with pytest.raises(ValueError):
         FusedCollector(env, ActorCritic(16, 16, 4, actor_hidden_dims=(256, 128)).cuda(), sto, 0.99)
+
+
+@pytest.mark.parametrize("groups,max_len", [(4, 200), (4, 6), (1, 6), (2, 12)])
+def test_cooperative_reset_draws_in_the_collection_kernel_are_the_same_bits(cuda_lib, groups, max_len):
+    """Reset draws generated by the warp (CompactDraws: up to K staging columns per warp, lanes beyond them draw for themselves) against
+    every resetting lane drawing for itself: identical storage and state.  Short episodes put many resetting lanes into one warp, so
+    the overflow path and the column hand-over are both exercised."""
+    import dataclasses
+    from generalizableracing_b200.collect import FusedCollector
+    from generalizableracing_b200.env import RacingVecEnv
+    from generalizableracing_b200.modules import ActorCritic
+    from generalizableracing_b200.storage import RolloutStorage
+    N, T = 1000, 16
+    cfg = RacingCfg.for_stage(1)
+    cfg = dataclasses.replace(cfg, episode_length_s=max_len * cfg.step_dt - 1e-6)
+    assert cfg.max_episode_length == max_len
+    torch.manual_seed(5)
+    pol = ActorCritic(16, 16, 4).cuda()
+    runs = []
+    for cols in (-1, 0, 1, 2):
+        env = RacingVecEnv(cfg, synthetic_track_table(), N, seed=9)
+        env.reset()
+        env.episode_length_buf = torch.randint(0, max_len, (N,), generator=torch.Generator().manual_seed(3), dtype=torch.int32)
+        sto = RolloutStorage("rl", N, T, [16], [16], [4], device="cuda:0")
+        col = FusedCollector(env, pol, sto, gamma=0.99, groups_per_cta=groups)
+        col.coop_reset_columns = cols
+        col.pack()
+        col.collect()
+        torch.cuda.synchronize()
+        runs.append((env, sto, col))
+    env0, sto0, col0 = runs[0]
+    assert int(sto0.dones.sum()) > (N * T // max_len) // 2           # resets did happen (time-outs alone give N*T/max_len)
+    for env, sto, col in runs[1:]:
+        for name in ("observations", "privileged_observations", "actions", "rewards", "dones", "values", "actions_log_prob", "mu"):
+            assert torch.equal(getattr(sto, name), getattr(sto0, name)), (name, col.coop_reset_columns)
+        assert torch.equal(env.planes, env0.planes)
+        assert torch.equal(env._log_accum.sum(0), env0._log_accum.sum(0))

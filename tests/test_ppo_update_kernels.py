@@ -378,3 +378,82 @@ def test_storage_pack_records(cuda_lib):
     want = torch.cat([f(sto.observations), f(sto.privileged_observations), f(sto.actions), f(sto.mu), f(sto.sigma), f(sto.actions_log_prob), f(sto.advantages),
                       f(sto.returns), f(sto.values)], dim=1)
     assert rec.shape == (T * N, B.GR_RECORD_FLOATS) and torch.equal(rec, want)
+
+
+def test_storage_pack_records_permuted(cuda_lib):
+    """gr_storage_pack_records_permuted: record r = transition perm[r]; a prefix of a permutation packs only that many records."""
+    from generalizableracing_b200 import _lib as B
+    from generalizableracing_b200.storage import RolloutStorage
+    T, N = 5, 333
+    sto = RolloutStorage("rl", N, T, [16], [16], [4], device="cuda:0")
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for t in (sto.observations, sto.privileged_observations, sto.actions, sto.mu, sto.sigma, sto.actions_log_prob, sto.advantages, sto.returns, sto.values):
+        t.copy_(torch.randn(t.shape, device="cuda", generator=g))
+    want = sto.pack_records().clone()
+    perm = torch.randperm(T * N, device="cuda", generator=g)
+    rec = sto.pack_records(perm)
+    assert torch.equal(rec, want[perm])
+    sto._records.fill_(-7.0)
+    k = 4 * ((T * N) // 4)
+    rec = sto.pack_records(perm[:k].contiguous())
+    assert torch.equal(rec[:k], want[perm[:k]]) and bool((rec[k:] == -7.0).all())
+    with pytest.raises(ValueError):
+        sto.pack_records(perm.to(torch.int32))
+
+
+@pytest.mark.parametrize("rows,pool", [(1000, 5000), (40000, 98304)])
+def test_dense_records_are_the_gathered_rows(cuda_lib, rows, pool):
+    """Records packed in mini-batch order and read densely (indices = NULL, records + slot offset) against the same records gathered through
+    the index buffer: per-row outputs bit for bit, sums and weight gradients up to the order of the flush atomics."""
+    import ctypes as C
+    from generalizableracing_b200 import _lib as B
+    from generalizableracing_b200.modules import ActorCritic
+    lib = cuda_lib
+    torch.manual_seed(rows + 5)
+    pol = ActorCritic(16, 16, 4).cuda()
+    la, lc = [m for m in pol.actor if isinstance(m, torch.nn.Linear)], [m for m in pol.critic if isinstance(m, torch.nn.Linear)]
+    mk = lambda l, out: B.GrMlp(l[0].weight.data_ptr(), l[0].bias.data_ptr(), l[1].weight.data_ptr(), l[1].bias.data_ptr(), l[2].weight.data_ptr(), l[2].bias.data_ptr(), 16, 128, 128, out)
+    packed = torch.zeros(int(lib.gr_policy_packed_bytes(128, 128, 2)), dtype=torch.uint8, device="cuda")
+    a, c = mk(la, 4), mk(lc, 1)
+    st = torch.cuda.current_stream().cuda_stream
+    B.check(lib.gr_policy_pack(C.byref(a), C.byref(c), packed.data_ptr(), st), "pack")
+    sigma = torch.tensor([0.8, 0.6, 1.0, 0.7], device="cuda")
+    p = B.GrPolicy(packed.data_ptr(), sigma.data_ptr(), 0.01)
+    pc = B.GrPolicy(packed.data_ptr() + packed.numel() // 2, sigma.data_ptr(), 0.01)
+    rn = lambda *s: torch.randn(*s, device="cuda")
+    old_mu, old_v = rn(pool, 4) * 0.5, rn(pool)
+    old_sig = (sigma * (1 + 0.05 * rn(4))).abs().expand(pool, 4).contiguous()
+    actions = old_mu + old_sig * rn(pool, 4)
+    logp = torch.distributions.Normal(old_mu, old_sig).log_prob(actions).sum(-1)
+    rec = torch.cat([rn(pool, 16) * 2, rn(pool, 16) * 2, actions, old_mu, old_sig, logp[:, None], rn(pool, 1), old_v[:, None] + 0.5 * rn(pool, 1), old_v[:, None]], dim=1).contiguous()
+    perm = torch.randperm(pool, device="cuda")
+    slot = 1                                                         # the second mini-batch slot: rows [rows, 2*rows) of the permutation
+    idx = perm[slot * rows:(slot + 1) * rows].contiguous()
+    rec_perm = rec[perm].contiguous()
+    dense_ptr = rec_perm.data_ptr() + slot * rows * B.GR_RECORD_FLOATS * 4
+
+    def run(rec_ptr, index_ptr):
+        gm, gv, sums = torch.zeros(rows, 4, device="cuda"), torch.zeros(rows, 4, device="cuda"), torch.zeros(16, device="cuda")
+        b = B.GrPpoBatch(None, None, sigma.data_ptr(), None, None, None, None, None, None, None, 0.2, 1.0, 0.003, 1, index_ptr, rec_ptr)
+        B.check(lib.gr_policy_forward_loss(C.byref(p), None, None, C.byref(b), rows, gm.data_ptr(), gv.data_ptr(), sums.data_ptr(), st), "fwd+loss")
+        gs = [torch.zeros_like(t) for l in (la, lc) for m in l for t in (m.weight, m.bias)]
+        ga, gc = B.GrMlpGrad(*(t.data_ptr() for t in gs[:6]), 4, 1), B.GrMlpGrad(*(t.data_ptr() for t in gs[6:]), 1, 1)
+        jobs = (B.GrBackwardJob * 2)(B.GrBackwardJob(p, rec_ptr, gm.data_ptr(), sums.data_ptr() + 32, ga, index_ptr, B.GR_RECORD_FLOATS),
+                                     B.GrBackwardJob(pc, rec_ptr + 64, gv.data_ptr(), sums.data_ptr() + 36, gc, index_ptr, B.GR_RECORD_FLOATS))
+        B.check(lib.gr_actor_backward_jobs(jobs, 2, 128, 128, rows, st), "bwd")
+        # the one-launch step on the same rows
+        gs1 = [torch.zeros_like(t) for t in gs]
+        ga1, gc1 = B.GrMlpGrad(*(t.data_ptr() for t in gs1[:6]), 4, 1), B.GrMlpGrad(*(t.data_ptr() for t in gs1[6:]), 1, 1)
+        sums1 = torch.zeros(16, device="cuda")
+        fs = B.GrPpoStep(p, None, None, b, ga1, gc1, sums1.data_ptr(), 0.0)
+        B.check(lib.gr_ppo_fused_step(C.byref(fs), rows, st), "fused step")
+        torch.cuda.synchronize()
+        return gm, gv, sums, gs, sums1, gs1
+    gm, gv, sums, gs, sums1, gs1 = run(rec.data_ptr(), idx.data_ptr())
+    dm, dv, dsums, ds, dsums1, ds1 = run(dense_ptr, None)
+    assert torch.equal(gm, dm) and torch.equal(gv, dv) and torch.equal(sums[8:10], dsums[8:10])
+    assert float(gm.abs().max()) > 0 and float(gv.abs().max()) > 0
+    for x, y in ((sums[:8], dsums[:8]), (sums1[:8], dsums1[:8])):
+        assert torch.allclose(x, y, rtol=2e-5, atol=1e-5 * float(x.abs().max()))
+    for x, y in list(zip(gs, ds)) + list(zip(gs1, ds1)):
+        assert float(x.abs().max()) > 0 and float((x - y).abs().max()) <= 2e-5 * float(x.abs().max()) + 1e-12

@@ -51,8 +51,14 @@ def main():
                 alg.storage.clear()
                 col.collect()
 
-            ms = timeit(fused, 20)
+            reps = int(os.environ.get("REPS", "1"))
+            ms = sorted(timeit(fused, 20 if reps == 1 else 100) for _ in range(reps))[reps // 2]          # REPS > 1: median of REPS x 100 rollouts
             row[f"fused_G{G}"] = {"ms_per_rollout": ms, "us_per_step": ms * 1e3 / T, "env_steps_per_s": N * T / (ms * 1e-3)}
+
+        if os.environ.get("SKIP_EAGER"):
+            out[str(N)] = row
+            env.close()
+            continue
 
         def unfused():
             alg.storage.clear()

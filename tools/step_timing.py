@@ -17,12 +17,17 @@ from generalizableracing_b200.env import RacingVecEnv  # noqa: E402
 from generalizableracing_b200.tracks import synthetic_track_table  # noqa: E402
 
 
-def make_io(e, a):
+def make_io(e, a, dones="i64"):
     o = e._outs[0]
     io = B.GrStepIO()
     io.action = a.data_ptr()
     io.obs, io.critic_obs, io.aux_obs = o["obs"].data_ptr(), o["critic"].data_ptr(), o["aux"].data_ptr()
-    io.reward, io.terminated, io.time_out, io.dones = o["reward"].data_ptr(), o["terminated"].data_ptr(), o["time_out"].data_ptr(), o["dones"].data_ptr()
+    io.reward, io.terminated, io.time_out = o["reward"].data_ptr(), o["terminated"].data_ptr(), o["time_out"].data_ptr()
+    if dones == "i64":
+        io.dones = o["dones"].data_ptr()
+    elif dones == "u8":                      # one byte per env (the int64 view of the wrapper's `.long()` only on request)
+        e._dones_u8 = torch.zeros(e.num_envs, dtype=torch.uint8, device=a.device)
+        io.dones_u8 = e._dones_u8.data_ptr()
     io.log_accum = e._log_accum.data_ptr()
     return io
 
@@ -35,6 +40,8 @@ def main():
     ap.add_argument("--blocks", default="32,64,128,256")
     ap.add_argument("--no-stats", action="store_true")
     ap.add_argument("--pdl", type=int, default=1)
+    ap.add_argument("--dones", default="i64", choices=["i64", "u8", "none"], help="what the kernel writes besides terminated / time_out")
+    ap.add_argument("--complex", type=int, default=0, help="1: the bench's 20 x 10 x 8 gate table instead of the synthetic one")
     ap.add_argument("--hover", type=int, default=0, help="1: near-hover actions (time-out resets only, ~0.5%/step)")
     args = ap.parse_args()
     BLD.build()
@@ -42,6 +49,9 @@ def main():
     dev = torch.device("cuda:0")
     cfg = RacingCfg.for_stage(args.stage)
     table = synthetic_track_table()
+    if args.complex:
+        from generalizableracing_b200.track_gen import generate_track_table, racing_complex_cfg
+        table = generate_track_table(racing_complex_cfg())
     N = args.envs
     flush = torch.empty(int(512e6) // 4, device=dev)
     res = []
@@ -53,7 +63,7 @@ def main():
         for e in envs:
             e.reset()
             e.episode_length_buf = torch.randint(0, cfg.max_episode_length, (N,), device=dev, dtype=torch.int32)
-        ios = [make_io(e, a) for e, a in zip(envs, acts)]
+        ios = [make_io(e, a, args.dones) for e, a in zip(envs, acts)]
         step = [0]
 
         def launch(k):
@@ -124,7 +134,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         eager = e0.elapsed_time(e1) * 1e3 / (10 * len(envs))
-        r = {"hover": args.hover, "reset_rate": float(torch.stack([e._log_accum.sum(0) for e in envs]).sum(0)[0]) / (step[0] * N), "pdl": args.pdl, "block": blk, "cold_single_us_median": cold[len(cold) // 2], "cold_single_us_min": cold[0], "graph_rot_us": out, "l2_resident_us": hot, "eager_rot_us": eager}
+        r = {"dones": args.dones, "hover": args.hover, "reset_rate": float(torch.stack([e._log_accum.sum(0) for e in envs]).sum(0)[0]) / (step[0] * N), "pdl": args.pdl, "block": blk, "cold_single_us_median": cold[len(cold) // 2], "cold_single_us_min": cold[0], "graph_rot_us": out, "l2_resident_us": hot, "eager_rot_us": eager}
         print(json.dumps(r), flush=True)
         res.append(r)
         del envs, ios, acts
