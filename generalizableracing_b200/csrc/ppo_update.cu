@@ -6,6 +6,7 @@
 //   KL for the adaptive learning rate, loss.backward() up      loss and KL sums)
 //   to the network outputs
 // The weight gradients then come from gr_actor_backward (actor with d/d mu, critic with d/d v); clipping and Adam stay torch.
+#include <cstdlib>
 #include "mlp_tc.cuh"
 #include "ppo_loss.cuh"
 
@@ -28,31 +29,42 @@ struct FwdLossArgs { GrPpoBatch b; float* grad_mu; float* grad_value; float* sum
 // (rows past the end are clamped and never stored) -- see actor_backward.cu.
 // kLoss: the thread that holds a row's mean and value also evaluates the row's loss (ppo_loss.cuh) on the stored columns it fetched with
 // the row, and writes d(loss)/d(mu), d(loss)/d(v) and its share of the sums: gr_ppo_loss_grad's launch and the mu / value round trip go.
-template <bool kLoss>
+template <bool kLoss, bool kInter>
 __global__ void __launch_bounds__(kFwdGroups * kTileEnvs, 1) policy_forward_kernel(const GrPolicy pol, const float* __restrict__ obs,
                                                                                   const float* __restrict__ critic_obs, const int64_t* __restrict__ idx,
                                                                                   float* __restrict__ mu, float* __restrict__ value, const int64_t R,
                                                                                   const FwdLossArgs la) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* w_smem = smem;
-  uint8_t* h_smem = smem + 2 * NLp::kNetBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(h_smem + kFwdGroups * NLp::kHBytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kFwdGroups);
+  uint8_t* h_smem = smem + 2 * NLp::kNetBytes;                     // activation tiles: [actor | critic][group]
+  constexpr int kCtx = kInter ? 2 * kFwdGroups : kFwdGroups;      // (activation tile, accumulator, mbarrier) sets of the CTA
+  uint64_t* bars = reinterpret_cast<uint64_t*>(h_smem + kCtx * NLp::kHBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kCtx);
   const int tid = threadIdx.x, grp = tid / kTileEnvs, row = tid % kTileEnvs;
   {
     const uint4* src = reinterpret_cast<const uint4*>(pol.packed);
     uint4* dst = reinterpret_cast<uint4*>(w_smem);
     for (int k = tid; k < 2 * NLp::kNetBytes / 16; k += kFwdGroups * kTileEnvs) dst[k] = __ldg(src + k);
   }
-  if (tid < kFwdGroups) mbar_init(&bars[tid], 1);
+  if (tid < kCtx) mbar_init(&bars[tid], 1);
   __syncwarp();
-  if (tid < 32) tmem_alloc(tmem_slot, kFwdGroups * NLp::kCols);
+  if (tid < 32) tmem_alloc(tmem_slot, kCtx * NLp::kCols);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  // The two nets of a tile are independent chains (actor on the policy observation, critic on the critic's): each group runs them
+  // INTERLEAVED on two activation tiles / accumulators / mbarriers of its own, so that the epilogue of one net's layer runs while the
+  // other net's MMAs are in flight -- four of the six MMA waits of a tile disappear behind epilogue work (they were 26 % of the stall
+  // samples, profiles/r2_ncu_ppo_update_kernels_summary.md).  The 128 threads of a group pass the same named barriers in program order,
+  // so both contexts share the group's two barrier ids; the issuing thread queues actor and critic MMAs in that order.
   GroupCtx g = make_group_ctx(h_smem, NLp::kHBytes, bars, *tmem_slot, NLp::kCols, grp, row, pol.negative_slope);
+  GroupCtx gc = make_group_ctx(h_smem, NLp::kHBytes, bars, *tmem_slot, NLp::kCols, kInter ? kFwdGroups + grp : grp, row, pol.negative_slope);
+  gc.bar_id = g.bar_id;
+  gc.issuer = g.issuer;
   const uint32_t w_addr = smem_u32(w_smem);
+  const uint8_t* wc_smem = w_smem + NLp::kNetBytes;
+  const uint32_t wc_addr = w_addr + NLp::kNetBytes;
   const int64_t tiles = (R + kTileEnvs - 1) / kTileEnvs;
   const int64_t stride = (int64_t)gridDim.x * kFwdGroups;
   const bool gather = idx != nullptr;
@@ -104,11 +116,27 @@ __global__ void __launch_bounds__(kFwdGroups * kTileEnvs, 1) policy_forward_kern
     const bool live = tile < tiles && r < R;
     q_next2 = index_of(tile + 2 * stride);
     fetch(q_next, nxt);
-    write_x_row(g.hrow, pack8(cur.o0, cur.o1), pack8(cur.o2, cur.o3));
-    const float4 m = run_net<NLp>(g, w_smem, w_addr);
-    tc_fence_before_sync();
-    write_x_row(g.hrow, pack8(cur.c0, cur.c1), pack8(cur.c2, cur.c3));
-    const float4 v = run_net<NLp>(g, w_smem + NLp::kNetBytes, w_addr + NLp::kNetBytes);
+    float4 m, v;
+    if (kInter) {
+      write_x_row(g.hrow, pack8(cur.o0, cur.o1), pack8(cur.o2, cur.o3));
+      stage_issue<NLp>(g, w_addr, kL1);
+      write_x_row(gc.hrow, pack8(cur.c0, cur.c1), pack8(cur.c2, cur.c3));
+      stage_issue<NLp>(gc, wc_addr, kL1);
+      stage_wait(g);  epilogue1<NLp>(g);            stage_issue<NLp>(g, w_addr, kL2);
+      stage_wait(gc); epilogue1<NLp>(gc);           stage_issue<NLp>(gc, wc_addr, kL2);
+      stage_wait(g);  epilogue2<NLp>(g, w_smem);    stage_issue<NLp>(g, w_addr, kL3);
+      stage_wait(gc); epilogue2<NLp>(gc, wc_smem);  stage_issue<NLp>(gc, wc_addr, kL3);
+      stage_wait(g);
+      m = read_head<NLp>(g, w_smem);
+      stage_wait(gc);
+      v = read_head<NLp>(gc, wc_smem);
+    } else {
+      write_x_row(g.hrow, pack8(cur.o0, cur.o1), pack8(cur.o2, cur.o3));
+      m = run_net<NLp>(g, w_smem, w_addr);
+      tc_fence_before_sync();
+      write_x_row(g.hrow, pack8(cur.c0, cur.c1), pack8(cur.c2, cur.c3));
+      v = run_net<NLp>(g, wc_smem, wc_addr);
+    }
     tc_fence_before_sync();
     if (live) {
       if (mu) __stcs(reinterpret_cast<float4*>(mu) + r, m);
@@ -154,7 +182,7 @@ __global__ void __launch_bounds__(kFwdGroups * kTileEnvs, 1) policy_forward_kern
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (tid < 32) tmem_dealloc(*tmem_slot, kFwdGroups * NLp::kCols);
+  if (tid < 32) tmem_dealloc(*tmem_slot, kCtx * NLp::kCols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -299,15 +327,24 @@ using namespace gr;
 template <bool kLoss>
 static int launch_policy_forward(const GrPolicy* policy, const float* obs, const float* critic_obs, const int64_t* indices, float* mu, float* value, int64_t rows,
                                  const FwdLossArgs& la, cudaStream_t s) {
-  const size_t bytes = 2 * (size_t)NLp::kNetBytes + (size_t)kFwdGroups * NLp::kHBytes + 128;
-  auto kernel = policy_forward_kernel<kLoss>;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  if (e != cudaSuccess) return (int)e;
+  // GRACING_FWD_INTERLEAVE=1: the two nets of a tile as interleaved chains (two activation tiles / accumulators per group); measured, see DESIGN 4d
+  static const bool inter = [] { const char* e = getenv("GRACING_FWD_INTERLEAVE"); return e && e[0] == '1'; }();
+  const size_t bytes = 2 * (size_t)NLp::kNetBytes + (inter ? 2 : 1) * (size_t)kFwdGroups * NLp::kHBytes + 128;      // weights | activation tiles
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t pairs = ((rows + kTileEnvs - 1) / kTileEnvs + kFwdGroups - 1) / kFwdGroups;
   const int grid = (int)(pairs < sms ? pairs : sms);
-  kernel<<<grid, kFwdGroups * kTileEnvs, bytes, s>>>(*policy, obs, critic_obs, indices, mu, value, rows, la);
+  if (inter) {
+    auto kernel = policy_forward_kernel<kLoss, true>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    kernel<<<grid, kFwdGroups * kTileEnvs, bytes, s>>>(*policy, obs, critic_obs, indices, mu, value, rows, la);
+  } else {
+    auto kernel = policy_forward_kernel<kLoss, false>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    kernel<<<grid, kFwdGroups * kTileEnvs, bytes, s>>>(*policy, obs, critic_obs, indices, mu, value, rows, la);
+  }
   return (int)cudaGetLastError();
 }
 
