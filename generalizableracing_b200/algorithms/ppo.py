@@ -194,7 +194,6 @@ class PPO:
                              int(self.use_clipped_value_loss), idx_ptr)
         # transition records (storage.pack_records, once per iteration): one scattered 192-byte record per sampled row instead of nine scattered
         # columns (measured at 393,216 rows: the scattered 4 / 16-byte column reads were what the fused kernels waited for)
-        fused = {"0": False, "1": True}.get(os.environ.get("GRACING_PPO_FUSED_STEP", ""), mb <= 131072)
         use_rec = os.environ.get("GRACING_PPO_RECORDS", "1") != "0" and sto.obs_shape[0] == 16 and (sto.privileged_obs_shape[0] or 16) == 16
         rec_ptr = sto.pack_records().data_ptr() if use_rec else None
         g["records"] = use_rec
@@ -203,6 +202,12 @@ class PPO:
         # instead of gathering one scattered record per row behind a scattered index read; one captured step per mini-batch slot.
         dense = use_rec and os.environ.get("GRACING_PPO_DENSE_RECORDS", "1") != "0"
         g["dense_records"] = dense
+        # forward + loss + weight gradients of both nets as ONE launch (gr_ppo_fused_step) or as two (gr_policy_forward_loss ->
+        # gr_actor_backward_jobs).  With gathered rows the one launch lost above ~131 k rows (393,216 rows: 7.3 vs 6.4 ms of update -- its tiles
+        # waited for their scattered rows with nothing left to overlap); with dense records it streams them and wins at every
+        # size measured (gpurun r4j, update per iteration: 16,384 envs 2.0 vs 2.2 ms, 32,768 envs 3.3 vs 3.5 ms, 65,536 envs 5.6 vs 5.7 ms).
+        # GRACING_PPO_FUSED_STEP=0|1 forces.
+        fused = {"0": False, "1": True}.get(os.environ.get("GRACING_PPO_FUSED_STEP", ""), dense or mb <= 131072)
         p_max_mu, p_max_v = ksums.data_ptr() + 8 * 4, ksums.data_ptr() + 9 * 4
 
         def slot_args(i):
@@ -216,10 +221,6 @@ class PPO:
             else:
                 jobs = (B.GrBackwardJob * 2)(B.GrBackwardJob(pol_both, s_obs, g["grad_mu"].data_ptr(), p_max_mu, gr_a, idx_ptr, 0),
                                              B.GrBackwardJob(pol_c, s_critic, g["grad_v"].data_ptr(), p_max_v, gr_c, idx_ptr, 0))
-            # forward + loss + weight gradients of both nets as ONE launch (gr_ppo_fused_step) for small mini-batches, two launches
-            # (gr_policy_forward_loss -> gr_actor_backward_jobs) for large ones.  Measured on the B200 (gpurun r2v):
-            # 24,576 rows (4,096 envs): 1.21 vs 1.27 ms of update per iteration; 393,216 rows (65,536 envs): 7.3 vs 6.4 ms -- at that size the
-            # one-launch kernel's tiles wait for their scattered rows with nothing left to overlap.  GRACING_PPO_FUSED_STEP=0|1 forces.
             fstep = B.GrPpoStep(pol_both, s_obs, s_critic, batch_fl if use_rec else batch, gr_a, gr_c, ksums.data_ptr(), 0.0)
             return batch_fl, jobs, fstep
         slots = [slot_args(i) for i in range(self.num_mini_batches if dense else 1)]
