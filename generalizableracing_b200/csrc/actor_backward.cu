@@ -300,8 +300,8 @@ __global__ void __launch_bounds__(kGroups * kTileEnvs + 32, 1) actor_backward_ke
         if ((row & 31) == 0 && v != 0.0f) atomicAdd(fz.sums + k, v);
       }
     }
-  } else if (tid == kGroups * kTileEnvs) {
-    // ---- the issuing thread: every MMA of the CTA, in program order
+  } else {
+    // ---- the issuing warp (all 32 lanes run this code converged, one elected lane issues): every MMA of the CTA, in program order
     const uint32_t w_addr = smem_u32(w_smem), ones_a = smem_u32(ones), grp0_a = smem_u32(grp_smem);
     // The issuer serves whichever group has its next stage ready (non-blocking test of `full[g]`), each group at its own stage: a group
     // that waits for its rows from HBM at the start of a tile does not hold the other one back (strict alternation did: ncu showed both
@@ -334,53 +334,54 @@ __global__ void __launch_bounds__(kGroups * kTileEnvs + 32, 1) actor_backward_ke
         if (kPpo && s == kHalves + 1) {                      // forward layer 3 (N = 16): the head of the net
 #pragma unroll
           for (int kk = 0; kk < H2 / 16; ++kk)
-            mma_f16_ss(d_tm, desc_rows_k(h2_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW3Off + kk * 2 * (kOutPad * 16), kOutPad * 16, 128),
+            mma_f16_ss_warp(d_tm, desc_rows_k(h2_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW3Off + kk * 2 * (kOutPad * 16), kOutPad * 16, 128),
                        make_idesc_f16(128, kOutPad), kk > 0);
         } else if (s < kHalves) {                            // forward layer 1, units [128 s, 128 s + 128)
 #pragma unroll
           for (int kk = 0; kk < kK1 / 16; ++kk)
-            mma_f16_ss(d_tm, desc_rows_k(xs_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW1Off + s * 128 * 16 + kk * 2 * (H1 * 16), H1 * 16, 128),
+            mma_f16_ss_warp(d_tm, desc_rows_k(xs_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW1Off + s * 128 * 16 + kk * 2 * (H1 * 16), H1 * 16, 128),
                        make_idesc_f16(128, 128), kk > 0);
         } else if (s == kHalves) {                           // forward layer 2
 #pragma unroll
           for (int kk = 0; kk < H1 / 16; ++kk)
-            mma_f16_ss(d_tm, desc_rows_k(h1_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW2Off + kk * 2 * (H2 * 16), H2 * 16, 128),
+            mma_f16_ss_warp(d_tm, desc_rows_k(h1_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW2Off + kk * 2 * (H2 * 16), H2 * 16, 128),
                        make_idesc_f16(128, H2), kk > 0);
         } else if (s_bwd == kHalves + 1) {                   // dW3^T += H2^T . dA (rows are K: both operands MN-major) ; dH2 = dA . W3 (W3 as MN-major B)
 #pragma unroll
           for (int kk = 0; kk < kTileEnvs / 16; ++kk)
-            mma_f16_ss(tm + kColW3, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(da_a + kk * 256), make_idesc_f16(H2, 16) | kMnA | kMnB, acc_w3 || kk > 0);
+            mma_f16_ss_warp(tm + kColW3, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(da_a + kk * 256), make_idesc_f16(H2, 16) | kMnA | kMnB, acc_w3 || kk > 0);
           acc_w3 = true;
-          mma_f16_ss(d_tm, desc_rows_k(da_a), make_smem_desc(w_addr + NL::kW3Off, 128, kOutPad * 16), make_idesc_f16(128, H2) | kMnB, false);
+          mma_f16_ss_warp(d_tm, desc_rows_k(da_a), make_smem_desc(w_addr + NL::kW3Off, 128, kOutPad * 16), make_idesc_f16(128, H2) | kMnB, false);
         } else if (s_bwd < 2 * kHalves + 2) {                // dW2 | db2 (first half only) ; dH1 units [128 h, 128 h + 128) = dH2' . W2 (W2 as MN-major B)
           const int h = s_bwd - (kHalves + 2);
           if (h == 0) {
 #pragma unroll
             for (int kk = 0; kk < kTileEnvs / 16; ++kk) {
-              mma_f16_ss(tm + kColW2, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(h1_a + kk * 256), make_idesc_f16(H2, H1) | kMnA | kMnB, acc_w2 || kk > 0);
-              mma_f16_ss(tm + kColB2, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(ones_a + kk * 256), make_idesc_f16(H2, 16) | kMnA | kMnB, acc_w2 || kk > 0);
+              mma_f16_ss_warp(tm + kColW2, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(h1_a + kk * 256), make_idesc_f16(H2, H1) | kMnA | kMnB, acc_w2 || kk > 0);
+              mma_f16_ss_warp(tm + kColB2, desc_rows_mn(h2_a + kk * 256), desc_rows_mn(ones_a + kk * 256), make_idesc_f16(H2, 16) | kMnA | kMnB, acc_w2 || kk > 0);
             }
             acc_w2 = true;
           }
 #pragma unroll
           for (int kk = 0; kk < H2 / 16; ++kk)
-            mma_f16_ss(d_tm, desc_rows_k(h2_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW2Off + h * 16 * (H2 * 16) + kk * 256, 128, H2 * 16),
+            mma_f16_ss_warp(d_tm, desc_rows_k(h2_a + kk * 2 * kChunkA), make_smem_desc(w_addr + NL::kW2Off + h * 16 * (H2 * 16) + kk * 256, 128, H2 * 16),
                        make_idesc_f16(128, 128) | kMnB, kk > 0);
         } else {                                             // dW1 | db1 += dH1'^T . [X | 1 1 0..]
 #pragma unroll
           for (int h = 0; h < kHalves; ++h)
 #pragma unroll
             for (int kk = 0; kk < kTileEnvs / 16; ++kk)
-              mma_f16_ss(tm + kColW1 + 32 * h, desc_rows_mn(h1_a + h * 16 * kChunkA + kk * 256), desc_rows_mn(xs_a + kk * 256), make_idesc_f16(128, 32) | kMnA | kMnB,
+              mma_f16_ss_warp(tm + kColW1 + 32 * h, desc_rows_mn(h1_a + h * 16 * kChunkA + kk * 256), desc_rows_mn(xs_a + kk * 256), make_idesc_f16(128, 32) | kMnA | kMnB,
                          acc_w1 || kk > 0);
           acc_w1 = true;
         }
-        tc_commit(&done[g]);
+        tc_commit_warp(&done[g]);
         if (++stage[g] == kStages) {
           stage[g] = 0;
           if (--left[g] == 0) --active;
         }
       }
+      __syncwarp();
       if (!served) __nanosleep(20);
     }
   }

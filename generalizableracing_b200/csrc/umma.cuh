@@ -107,6 +107,26 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
 }
+// The same, called by ALL 32 lanes of a converged warp: one elected lane (elect.sync: the same lane for the same member mask every time)
+// issues.  With the whole warp in the issuing code the descriptors are warp-uniform values and stay in uniform registers; issued from one
+// lane of a diverged warp every UTCHMMA costs ~16 instructions of R2UR / ELECT / BRA.U.ANY hand-over (cuobjdump).
+__device__ __forceinline__ void mma_f16_ss_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_warp(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar)) : "memory");
+}
 // arrive on `bar` when every tcgen05.mma issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
