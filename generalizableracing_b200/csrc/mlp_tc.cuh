@@ -117,15 +117,21 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t taddr, uint8_t* hrow, c
   }
 }
 
-// one thread: D[tmem] = A[smem: KSTEPS x 16 K-columns] . B[smem]^T, then arrive on `bar` when done.  The descriptors of
-// successive K steps differ only in the start-address field (bytes >> 4), so they are formed by integer adds.
-template <int KSTEPS, int LBO_B>
+// one WARP, converged (one elected lane issues, umma.cuh): D[tmem] = A[smem: KSTEPS x 16 K-columns] . B[smem]^T, then arrive on `bar` when
+// done.  The descriptors of successive K steps differ only in the start-address field (bytes >> 4), so they are formed by integer adds.
+// kWarp = false: ONE thread issues (the issuing lane of a diverged warp: ~16 instructions of R2UR / ELECT / BRA.U.ANY hand-over per UTCHMMA,
+// but no extra live registers -- what ppo_collect_kernel<G = 4> at its 128-register cap needs: the converged form spills 152 B there and
+// measured 14.5-14.9 instead of 13.4 us per step).
+template <int KSTEPS, int LBO_B, bool kWarp>
 __device__ __forceinline__ void issue_layer(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint64_t* bar) {
   tc_fence_after_sync();
 #pragma unroll
-  for (int kk = 0; kk < KSTEPS; ++kk)
-    mma_f16_ss(d_tmem, a_desc + (uint64_t)(kk * ((2 * kChunkA) >> 4)), b_desc + (uint64_t)(kk * ((2 * LBO_B) >> 4)), idesc, kk > 0);
-  tc_commit(bar);
+  for (int kk = 0; kk < KSTEPS; ++kk) {
+    if (kWarp) mma_f16_ss_warp(d_tmem, a_desc + (uint64_t)(kk * ((2 * kChunkA) >> 4)), b_desc + (uint64_t)(kk * ((2 * LBO_B) >> 4)), idesc, kk > 0);
+    else mma_f16_ss(d_tmem, a_desc + (uint64_t)(kk * ((2 * kChunkA) >> 4)), b_desc + (uint64_t)(kk * ((2 * LBO_B) >> 4)), idesc, kk > 0);
+  }
+  if (kWarp) tc_commit_warp(bar);
+  else tc_commit(bar);
 }
 
 // what one group needs to run a net
@@ -138,24 +144,26 @@ struct GroupCtx {
   uint64_t* bar;
   uint32_t phase;
   int bar_id;           // named barrier of the group (bar_id + 8: its release barrier)
-  bool issuer;
+  bool issuer;          // the lane that polls the mbarrier
+  bool issuer_warp;     // its warp: issues the group's MMAs
   __half2 slope;
 };
 
 // A layer = [every thread of the group has written its operand row] -> group barrier -> one thread issues the MMAs ->
 // ... independent work ... -> stage_wait -> the accumulator is readable.
 enum Layer : int { kL1 = 0, kL2 = 1, kL3 = 2 };
-template <class NL>
+template <class NL, bool kWarp = true>
 __device__ __forceinline__ void stage_issue(const GroupCtx& g, uint32_t net_addr, const int layer) {
   constexpr int H1 = NL::kH1, H2 = NL::kH2;
   fence_proxy_async_smem();                 // this thread's st.shared operand rows -> async proxy
   tc_fence_before_sync();                   // this thread's tcgen05.ld of the columns about to be overwritten
   bar_sync(g.bar_id, kTileEnvs);
-  if (g.issuer) {
+  if (kWarp ? g.issuer_warp : g.issuer) {   // kWarp: warp-uniform -- all 32 lanes run the issue code, one elected lane issues
+    if (kWarp) __syncwarp();
     const uint64_t a_desc = make_smem_desc(g.hbuf_addr, kChunkA, 128);
-    if (layer == kL1) issue_layer<kK1 / 16, H1 * 16>(g.d_tmem, a_desc, make_smem_desc(net_addr + NL::kW1Off, H1 * 16, 128), make_idesc_f16(kTileEnvs, H1), g.bar);
-    else if (layer == kL2) issue_layer<H1 / 16, H2 * 16>(g.d_tmem, a_desc, make_smem_desc(net_addr + NL::kW2Off, H2 * 16, 128), make_idesc_f16(kTileEnvs, H2), g.bar);
-    else issue_layer<H2 / 16, kOutPad * 16>(g.d_tmem, a_desc, make_smem_desc(net_addr + NL::kW3Off, kOutPad * 16, 128), make_idesc_f16(kTileEnvs, kOutPad), g.bar);
+    if (layer == kL1) issue_layer<kK1 / 16, H1 * 16, kWarp>(g.d_tmem, a_desc, make_smem_desc(net_addr + NL::kW1Off, H1 * 16, 128), make_idesc_f16(kTileEnvs, H1), g.bar);
+    else if (layer == kL2) issue_layer<H1 / 16, H2 * 16, kWarp>(g.d_tmem, a_desc, make_smem_desc(net_addr + NL::kW2Off, H2 * 16, 128), make_idesc_f16(kTileEnvs, H2), g.bar);
+    else issue_layer<H2 / 16, kOutPad * 16, kWarp>(g.d_tmem, a_desc, make_smem_desc(net_addr + NL::kW3Off, kOutPad * 16, 128), make_idesc_f16(kTileEnvs, kOutPad), g.bar);
   }
 }
 // Only the issuing thread polls the mbarrier; everybody else blocks in hardware on the group's second named barrier.
@@ -185,13 +193,13 @@ __device__ __forceinline__ void epilogue2(const GroupCtx& g, const uint8_t* net_
   hidden_epilogue<true, NL::kH2>(g.taddr, g.hrow, reinterpret_cast<const uint4*>(net_smem + NL::kB2Off), g.slope);
 }
 // a whole net with nothing overlapped
-template <class NL>
+template <class NL, bool kWarp = true>
 __device__ __forceinline__ float4 run_net(GroupCtx& g, const uint8_t* net_smem, uint32_t net_addr) {
-  stage_issue<NL>(g, net_addr, kL1); stage_wait(g);
+  stage_issue<NL, kWarp>(g, net_addr, kL1); stage_wait(g);
   epilogue1<NL>(g);
-  stage_issue<NL>(g, net_addr, kL2); stage_wait(g);
+  stage_issue<NL, kWarp>(g, net_addr, kL2); stage_wait(g);
   epilogue2<NL>(g, net_smem);
-  stage_issue<NL>(g, net_addr, kL3); stage_wait(g);
+  stage_issue<NL, kWarp>(g, net_addr, kL3); stage_wait(g);
   return read_head<NL>(g, net_smem);
 }
 
@@ -208,6 +216,7 @@ __device__ __forceinline__ GroupCtx make_group_ctx(uint8_t* h_smem, int h_bytes,
   g.phase = 0u;
   g.bar_id = 1 + grp;
   g.issuer = row == 32 * (grp & 3);            // lane 0 of a different warp per group: the issuers sit on different SM sub-partitions
+  g.issuer_warp = (row >> 5) == (grp & 3);
   g.slope = __float2half2_rn(negative_slope);
   return g;
 }

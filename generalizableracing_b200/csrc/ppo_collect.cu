@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + G);
   float4* track_rows = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + 128);
 
+  constexpr bool kWarpIssue = G < 4;        // (mlp_tc.cuh issue_layer: the converged issue form needs registers the 128-register build does not have)
   const int tid = threadIdx.x, grp = tid / kTileEnvs, row = tid % kTileEnvs;
   const int i = blockIdx.x * (G * kTileEnvs) + tid;
   const bool active = i < st.num_envs;
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
   for (int t = 0; t < T; ++t) {
     const int64_t tn = (int64_t)t * N + i;
     // ---- PPO.act: actor mean, sample, log-prob (ppo.py:71-83; Normal(mean, std).sample() / .log_prob().sum(-1))
-    stage_issue<NL>(g, w_addr, kL1);
+    stage_issue<NL, kWarpIssue>(g, w_addr, kL1);
     GrRandom rt = rng;
     rt.step = rng.step + (uint32_t)t;
     const RandSrc<true> rs(rt, li, st.env_id_offset + li);
@@ -150,14 +151,14 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
     }
     stage_wait(g);
     epilogue1<NL>(g);
-    stage_issue<NL>(g, w_addr, kL2); stage_wait(g);
+    stage_issue<NL, kWarpIssue>(g, w_addr, kL2); stage_wait(g);
     epilogue2<NL>(g, w_smem);
-    stage_issue<NL>(g, w_addr, kL3); stage_wait(g);
+    stage_issue<NL, kWarpIssue>(g, w_addr, kL3); stage_wait(g);
     const float4 mu = read_head<NL>(g, w_smem);
     const float4 a_t = make_float4(mu.x + sigma.x * an0.x, mu.y + sigma.y * an0.y, mu.z + sigma.z * an1.x, mu.w + sigma.w * an1.y);
     // ---- critic value of the same state
     write_x_row(g.hrow, critic_pk[0], critic_pk[1]);
-    stage_issue<NL>(g, critic_addr, kL1);
+    stage_issue<NL, kWarpIssue>(g, critic_addr, kL1);
     {
       const float dx = a_t.x - mu.x, dy = a_t.y - mu.y, dz = a_t.z - mu.z, dw = a_t.w - mu.w;
       const float kLogSqrt2Pi = 0.91893853320467274178f;
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
     }
     stage_wait(g);
     epilogue1<NL>(g);
-    stage_issue<NL>(g, critic_addr, kL2);
+    stage_issue<NL, kWarpIssue>(g, critic_addr, kL2);
 
     // ---- env.step (same body as gr_step_fwd) while the critic's layer 2 runs; its observations are the next step's
     //      operands (kept packed in registers until the activation tile is free) and storage rows
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
 
     stage_wait(g);
     epilogue2<NL>(g, critic_smem);
-    stage_issue<NL>(g, critic_addr, kL3);
+    stage_issue<NL, kWarpIssue>(g, critic_addr, kL3);
     if (alive) {
       if (kStats && !so.reset) add_episode_sums(eps0, e, so.terms, cfg.dt);
       any_reset |= so.reset;
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(G * kTileEnvs, 1) ppo_collect_kernel(const GrC
 
   // ---- V(observation after the last step) for the GAE bootstrap (ppo.py:99-100)
   write_x_row(g.hrow, critic_pk[0], critic_pk[1]);
-  const float last_value = run_net<NL>(g, critic_smem, critic_addr).x;
+  const float last_value = run_net<NL, kWarpIssue>(g, critic_smem, critic_addr).x;
   if (active) {
     cio.last_values[i] = last_value;
     // ---- env state -> HBM (once per rollout).  Every env that reset at ANY step rewrote its read-mostly planes: the

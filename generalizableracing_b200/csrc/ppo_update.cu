@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(kFwdGroups * kTileEnvs, 1) policy_forward_kern
   GroupCtx gc = make_group_ctx(h_smem, NLp::kHBytes, bars, *tmem_slot, NLp::kCols, kInter ? kFwdGroups + grp : grp, row, pol.negative_slope);
   gc.bar_id = g.bar_id;
   gc.issuer = g.issuer;
+  gc.issuer_warp = g.issuer_warp;
   const uint32_t w_addr = smem_u32(w_smem);
   const uint8_t* wc_smem = w_smem + NLp::kNetBytes;
   const uint32_t wc_addr = w_addr + NLp::kNetBytes;
