@@ -153,3 +153,47 @@ def test_c3_window_gradient_at_full_size(backend):
     rs = [PC.draw_rnd(N, g2) for _ in range(H)]
     env2.rollout(torch.stack(a2).to(device), torch.stack(rs).to(device))
     assert torch.equal(env2._bptt.backward_window().cpu(), got)
+
+
+@pytest.mark.gpu
+def test_fused_collection_at_c4_size_equals_the_single_steps(cuda_lib):
+    """BASELINE C4 / C5 size through the fused collection kernel (G = 4: 128 CTAs of 512 envs, gate-table slice + cooperative-draw columns in
+    what shared memory is left) on the bench's table: replaying the stored actions through gr_step_fwd reproduces every stored observation,
+    reward and done bit for bit, with the cooperative reset draws on (default) and off."""
+    from generalizableracing_b200.collect import FusedCollector
+    from generalizableracing_b200.modules import ActorCritic
+    from generalizableracing_b200.storage import RolloutStorage
+    N, T = 65536, 6
+    cfg, table = RacingCfg.for_stage(1), complex_table()
+    torch.manual_seed(2)
+    pol = ActorCritic(16, 16, 4).cuda()
+    stored = []
+    for cols in (0, -1):
+        env = RacingVecEnv(cfg, table, N, seed=42)
+        env.reset()
+        env.episode_length_buf = torch.randint(0, cfg.max_episode_length, (N,), generator=torch.Generator().manual_seed(7), dtype=torch.int32)
+        sto = RolloutStorage("rl", N, T, [16], [16], [4], device="cuda:0")
+        col = FusedCollector(env, pol, sto, gamma=0.99)
+        col.coop_reset_columns = cols
+        col.pack()
+        obs_last, critic_last, _ = col.collect()
+        torch.cuda.synchronize()
+        stored.append((env, sto, obs_last.clone(), critic_last.clone()))
+    (env_a, sto_a, obs_a, critic_a), (env_b, sto_b, obs_b, critic_b) = stored
+    for name in ("observations", "privileged_observations", "actions", "rewards", "dones", "values", "actions_log_prob"):
+        assert torch.equal(getattr(sto_a, name), getattr(sto_b, name)), name
+    assert torch.equal(env_a.planes, env_b.planes) and torch.equal(obs_a, obs_b) and torch.equal(critic_a, critic_b)
+    assert int(sto_a.dones.sum()) > N * T // 400                                    # resets happened (time-outs alone: N * T / 200)
+    # the single-step kernel on the same actions
+    ref = RacingVecEnv(cfg, table, N, seed=42)
+    ref.reset()
+    ref.episode_length_buf = torch.randint(0, cfg.max_episode_length, (N,), generator=torch.Generator().manual_seed(7), dtype=torch.int32)
+    obs, ex = ref.get_observations()
+    for t in range(T):
+        assert torch.equal(sto_a.observations[t], obs), t
+        assert torch.equal(sto_a.privileged_observations[t], ex["observations"]["critic"]), t
+        obs, rew, dones, ex = ref.step(sto_a.actions[t])
+        assert torch.equal(sto_a.dones[t].view(-1).to(dones.dtype), dones), t
+        boot = rew + 0.99 * sto_a.values[t].view(-1) * ex["time_outs"].float()
+        assert torch.allclose(sto_a.rewards[t].view(-1), boot, rtol=1e-6, atol=1e-7), t          # (the kernel may contract r + gamma * V into one fma)
+    assert torch.equal(obs_a, obs) and torch.equal(env_a.planes, ref.planes)
