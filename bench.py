@@ -635,9 +635,35 @@ def bench_collective(dev, cfg, table, N, rank, world, T: int = 24):
         per_it.append(e0.elapsed_time(e1) / iters)
     ms = med(reduce_vector(per_it, world, dev, "max"))
     flat = runner.alg._graph["flat_grad"]
+    peer = runner.alg._graph.get("peer_allreduce")
     out["ppo_iteration"] = {"ms_per_iteration": ms, "env_steps_per_s": world * N * T / (ms * 1e-3), "allreduces_per_iteration": 20 if world > 1 else 0,
-                            "what": "gr_ppo_collect (24 steps, tcgen05 policy) + GAE + 20 captured mini-batch steps (gather, forward, loss grads, tcgen05 weight grads, "
-                                    "[NCCL all-reduce of the flat gradient buffer], clip + Adam), max over ranks, median of 3 x 10 iterations"}
+                            "gradient_sum": "none (one rank)" if world == 1 else ("gr_peer_allreduce (own kernel over NVLink peer memory)" if peer is not None else "NCCL all_reduce"),
+                            "what": "gr_ppo_collect (24 steps, tcgen05 policy) + GAE + transition records packed in mini-batch order + 20 captured mini-batch steps "
+                                    "(forward head + loss + tcgen05 weight gradients in one launch, [sum of the flat gradient buffer over the ranks], clip + Adam), "
+                                    "max over ranks, median of 3 x 10 iterations"}
+    if peer is not None:                 # the exchange kernel alone, as the NCCL one below: 20 per graph replay
+        gr = torch.cuda.CUDAGraph()
+        n_in = 20
+        for _ in range(3):
+            peer.launch()
+        torch.cuda.synchronize(dev)
+        with torch.cuda.graph(gr):
+            for _ in range(n_in):
+                peer.launch()
+        gr.replay()
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(30):
+            e0.record()
+            gr.replay()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1) * 1e3 / n_in)
+        us = reduce_vector(ts, world, dev, "max")
+        out["peer_allreduce"] = {"us": med(us), "us_min": float(us.min()), "us_max": float(us.max()), "floats": int(peer.n), "failed": bool(peer.failed()),
+                                 "what": "gr_peer_allreduce (csrc/peer_reduce.cu): every rank reads the other ranks' gradient buffers over NVLink between two flag "
+                                         "barriers, rank-order sum; 20 per CUDA-graph replay, device-timed, max over ranks, median of 30 replays"}
+        del gr
     if world > 1:
         import torch.distributed as dist
         buf = torch.zeros_like(flat)

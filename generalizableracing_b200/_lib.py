@@ -127,6 +127,14 @@ class GrPpoStep(C.Structure):
                 ("sums", c_p), ("cotangent_scale", c_f)]
 
 
+class GrPeerReduce(C.Structure):
+    _fields_ = [("peer_bufs", c_p), ("peer_flags", c_p), ("world", c_i), ("rank", c_i), ("n", c_i), ("reserved", c_i), ("max_spins", C.c_int64),
+                ("epoch", c_p), ("counter", c_p), ("error", c_p)]
+
+
+GR_PEER_MAX_WORLD = 16
+
+
 class GrHostStep(C.Structure):
     _fields_ = [("action", c_p), ("obs", c_p), ("reward", c_p), ("dones", c_p), ("critic_obs", c_p), ("time_out", c_p), ("dones_u8", c_p),
                 ("outputs_contiguous", c_i)]
@@ -214,6 +222,7 @@ PROTOTYPES = {
     "gr_policy_forward_loss": (C.c_int, [C.POINTER(GrPolicy), c_p, c_p, C.POINTER(GrPpoBatch), C.c_int64, c_p, c_p, c_p, c_p]),
     "gr_ppo_fused_step": (C.c_int, [C.POINTER(GrPpoStep), C.c_int64, c_p]),
     "gr_adam_clip_step": (C.c_int, [C.POINTER(GrAdamStep), c_p]),
+    "gr_peer_allreduce": (C.c_int, [C.POINTER(GrPeerReduce), c_p, c_p]),
     "gr_actor_backward_jobs": (C.c_int, [C.POINTER(GrBackwardJob), c_i, c_i, c_i, C.c_int64, c_p]),
     "gr_reach_reset": (C.c_int, [C.POINTER(GrReachConfig), C.POINTER(GrReachState), C.POINTER(GrRandom), c_p, c_p, c_p]),
     "gr_reach_observe": (C.c_int, [C.POINTER(GrReachConfig), C.POINTER(GrReachState), c_p, c_p]),

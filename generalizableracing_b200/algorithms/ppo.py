@@ -150,6 +150,26 @@ class PPO:
         tail = off                                   # 16 floats: gr_ppo_loss_grad's sums
         n_flat = tail + 16
         flat, flat_m, flat_v = (torch.zeros(n_flat, device=dev) for _ in range(3))
+        # env-sharded runs: the sum of `flat` over the ranks, once per step.  Default: our own kernel over NVLink peer memory
+        # (peer.py / csrc/peer_reduce.cu: `flat` lives in symmetric memory, every rank reads the others' buffers between two flag barriers
+        # and writes the sum to a local buffer the optimiser kernels read); GRACING_PEER_ALLREDUCE=0, or no symmetric memory: NCCL's all-reduce in place.
+        peer = None
+        if world > 1 and os.environ.get("GRACING_PEER_ALLREDUCE", "1") != "0":
+            ok = torch.ones(1, device=dev)
+            try:
+                from ..peer import PeerAllReduce
+                peer = PeerAllReduce(n_flat, dev)
+            except Exception as exc:           # no symmetric memory on this platform (no NVLink / no fabric handles): NCCL carries the sum
+                ok.zero_()
+                if D.world()[0] == 0:
+                    print(f"[gracing] peer all-reduce unavailable ({type(exc).__name__}: {exc}); using NCCL", flush=True)
+            torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)          # every rank takes the same path
+            if float(ok) < 1.0:
+                peer = None
+        if peer is not None:
+            flat = peer.buf[:n_flat]
+        g["peer_allreduce"] = peer
+        reduced = peer.out[:n_flat] if peer is not None else flat            # what the optimiser kernels read
         ksums = flat[tail:tail + 16]
         segs = [(p, o, p.numel()) for p, o in zip(params, offs)] + [(pol.std, tail + 3, 4)]
         old_state = self.optimizer.state
@@ -173,8 +193,8 @@ class PPO:
         ptrs, seg_off, seg_n = ptrs[order].contiguous(), seg_off[order].contiguous(), seg_n[order].contiguous()
         b1, b2 = self.optimizer.param_groups[0]["betas"]
         adaptive = self.desired_kl is not None and self.schedule == "adaptive"
-        adam = B.GrAdamStep(ptrs.data_ptr(), seg_off.data_ptr(), seg_n.data_ptr(), len(segs), n_flat, flat.data_ptr(), flat_m.data_ptr(), flat_v.data_ptr(),
-                            state.data_ptr(), ksums.data_ptr() if adaptive else None, 1.0 / world, float(b1), float(b2), float(self.optimizer.param_groups[0]["eps"]),
+        adam = B.GrAdamStep(ptrs.data_ptr(), seg_off.data_ptr(), seg_n.data_ptr(), len(segs), n_flat, reduced.data_ptr(), flat_m.data_ptr(), flat_v.data_ptr(),
+                            state.data_ptr(), reduced[tail:tail + 16].data_ptr() if adaptive else None, 1.0 / world, float(b1), float(b2), float(self.optimizer.param_groups[0]["eps"]),
                             float(self.max_grad_norm), float(self.desired_kl or 0.0), 1e-5, 1e-2)
         mk = lambda l1, l2, l3, out: B.GrMlp(l1.weight.data_ptr(), l1.bias.data_ptr(), l2.weight.data_ptr(), l2.bias.data_ptr(), l3.weight.data_ptr(),
                                              l3.bias.data_ptr(), 16, 128, 128, out)
@@ -242,7 +262,9 @@ class PPO:
                 B.check(lib.gr_policy_forward_loss(C.byref(pol_both), s_obs, s_critic, C.byref(batch_fl), mb, g["grad_mu"].data_ptr(), g["grad_v"].data_ptr(),
                                                    ksums.data_ptr(), st), "gr_policy_forward_loss")
                 B.check(lib.gr_actor_backward_jobs(jobs, 2, 128, 128, mb, st), "gr_actor_backward_jobs")
-            if world > 1:              # env-sharded data parallelism: ONE all-reduce per step carries the gradients and the loss / KL sums
+            if peer is not None:       # env-sharded data parallelism: ONE sum per step carries the gradients and the loss / KL sums
+                peer.launch()
+            elif world > 1:
                 torch.distributed.all_reduce(flat)
             B.check(lib.gr_adam_clip_step(C.byref(adam), st), "gr_adam_clip_step")
         return step
@@ -369,6 +391,8 @@ class PPO:
         sums = g["adam_state"][5:7] if g.get("kernel_sums") else g["sums"]
         out = torch.cat([sums / num_updates, g["lr"].reshape(1)]).tolist()          # the iteration's only host read
         self.learning_rate = out[2]
+        if g.get("peer_allreduce") is not None and g["peer_allreduce"].failed():
+            raise RuntimeError("gr_peer_allreduce: a rank did not reach the gradient exchange (flag wait gave up); the update of this iteration is invalid")
         self.storage.clear()
         return {"value_function": out[0], "surrogate": out[1]}
 

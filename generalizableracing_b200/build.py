@@ -13,7 +13,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libgracing.so")
-SOURCES = ["racing_step.cu", "racing_bwd.cu", "rollout.cu", "host_pipe.cu", "ppo_collect.cu", "bptt_collect.cu", "actor_backward.cu", "ppo_update.cu", "reach_step.cu", "reach_bwd.cu", "traj.cu", "mesh_collision.cu"]
+SOURCES = ["racing_step.cu", "racing_bwd.cu", "rollout.cu", "host_pipe.cu", "ppo_collect.cu", "bptt_collect.cu", "actor_backward.cu", "ppo_update.cu", "reach_step.cu", "reach_bwd.cu", "traj.cu", "mesh_collision.cu", "peer_reduce.cu"]
 HEADERS = ["gr_math.cuh", "gr_common.cuh", "racing_step_core.cuh", "reach_core.cuh", "umma.cuh", "mlp_tc.cuh", os.path.join("..", "..", "include", "gracing.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -468,6 +468,27 @@ typedef struct GrAdamStep {
 } GrAdamStep;
 int gr_adam_clip_step(const GrAdamStep* a, void* stream);
 
+/* ---- the policy-gradient all-reduce as one kernel over NVLink peer memory (csrc/peer_reduce.cu) ---------------------------------------
+ * BASELINE config C5's exchange step (env-sharded training: one sum of the flat gradient buffer per optimiser step).  Every rank's buffer
+ * lives in symmetric memory (mapped into every rank of the node); out[i] = sum over ranks 0..world-1, in that order on every rank (the
+ * replicas get the same bits), of peer_bufs[r][i].  Two flag barriers bracket the reads (all gradients complete / all ranks have read), so
+ * when the kernel ends this rank's buffer may be overwritten.  Call it on every rank of the group, once per step, in stream order after the
+ * kernels that wrote the gradients; it can be captured in a CUDA graph.  Waits are bounded: after max_spins polls *error = 1 and the
+ * kernel returns (results undefined) instead of hanging. */
+#define GR_PEER_MAX_WORLD 16
+typedef struct GrPeerReduce {
+  const void* peer_bufs;             /* device [world] uint64: address, in THIS process, of rank r's gradient buffer [n] fp32 (16-byte aligned) */
+  const void* peer_flags;            /* device [world] uint64: address of rank r's flag pad, uint32 [2][GR_PEER_MAX_WORLD], zero-initialised once */
+  int32_t world, rank;
+  int32_t n;                         /* floats, multiple of 4 */
+  int32_t reserved;
+  int64_t max_spins;                 /* polls (32 ns apart) before a wait gives up */
+  uint32_t* epoch;                   /* device, local: launch counter (zero-initialised once, same on every rank) */
+  uint32_t* counter;                 /* device, local: block counter (zero-initialised once) */
+  int32_t* error;                    /* device, local: set to 1 when a wait gave up */
+} GrPeerReduce;
+int gr_peer_allreduce(const GrPeerReduce* a, float* out /* device, local [n], 16-byte aligned */, void* stream);
+
 /* ---- env.step() with HOST buffers (the e2e boundary) -------------------------------------------------------------
  * Same call as gr_step_fwd for a caller whose actions / observations live in host memory: replaces
  * `env.step(torch.as_tensor(a).to(device))` + `.cpu()` of obs / reward / dones around ManagerBasedDiffRLEnv.step

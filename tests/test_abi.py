@@ -52,7 +52,7 @@ def _c_struct_fields(name):
     return fields
 
 
-@pytest.mark.parametrize("name", ["GrConfig", "GrTrack", "GrState", "GrRandom", "GrStepIO", "GrBwdIO", "GrTransition", "GrStorage", "GrMiniBatch", "GrHostStep", "GrMlp", "GrPolicy", "GrCollectIO", "GrBpttCollectIO", "GrMlpGrad", "GrPpoBatch", "GrAdamStep", "GrBackwardJob", "GrReachConfig", "GrReachState", "GrReachStepIO"])
+@pytest.mark.parametrize("name", ["GrConfig", "GrTrack", "GrState", "GrRandom", "GrStepIO", "GrBwdIO", "GrTransition", "GrStorage", "GrMiniBatch", "GrHostStep", "GrMlp", "GrPolicy", "GrCollectIO", "GrBpttCollectIO", "GrMlpGrad", "GrPpoBatch", "GrAdamStep", "GrBackwardJob", "GrPeerReduce", "GrReachConfig", "GrReachState", "GrReachStepIO"])
 def test_ctypes_structs_follow_the_header(name):
     assert [f for f, _ in getattr(B, name)._fields_] == _c_struct_fields(name)
 
