@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # the one-launch PPO step with dense records at 65,536 envs: plain run, ncu launch list, one --set full capture with source
 set -u
-out=gpurun_out; mkdir -p "$out"; tag=${1:-r4k}
+out=gpurun_out; mkdir -p "$out"; tag=${1:-fusedprof}
 ppo="python tools/train.py ppo --num_envs 65536 --iters 4 --fused --kernel_update"
 if timeout 300 $ppo > "$out/${tag}_plain.log" 2>&1; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:actor_backward|adam_|policy_|ppo_|storage_|gae" -c 400 --csv --log-file "$out/${tag}_launches.csv" $ppo > "$out/${tag}_ncu_list.log" 2>&1

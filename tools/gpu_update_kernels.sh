@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # update kernels after a change: tests, whole-iteration timing (twice), ncu launch list
 set -u
-out=gpurun_out; mkdir -p "$out"; tag=${1:-r4i}
+out=gpurun_out; mkdir -p "$out"; tag=${1:-upd}
 timeout 900 python -m pytest tests/test_ppo_update_kernels.py tests/test_ppo_graphed_update.py tests/test_actor_backward.py tests/test_bptt_collect.py tests/test_runners_gpu.py -m gpu -q -x > "$out/${tag}_pytest.log" 2>&1
 echo "pytest: exit $?" | tee "$out/${tag}_status.txt"
 tail -n 3 "$out/${tag}_pytest.log"
