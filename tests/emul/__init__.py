@@ -55,6 +55,7 @@ class EmulLib:
         self._l.emul_compute_returns.argtypes = [P(B.GrStorage), C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int32]
         self._l.emul_advantage_normalize.argtypes = [P(B.GrStorage), C.c_void_p]
         self._l.emul_storage_gather.argtypes = [P(B.GrStorage), C.c_void_p, C.c_int32, P(B.GrMiniBatch)]
+        self._l.emul_storage_pack_records.argtypes = [P(B.GrStorage), C.c_void_p, C.c_int64, C.c_void_p]
         self._l.emul_uav_collision_ray.argtypes = [P(B.GrMesh), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p]
         self._l.emul_mesh_query_rays.argtypes = [P(B.GrMesh), C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]
 
@@ -115,6 +116,12 @@ class EmulLib:
 
     def gr_storage_gather(self, s, idx, b, out, stream):
         return self._l.emul_storage_gather(s, idx, b, out)
+
+    def gr_storage_pack_records(self, s, records, stream):
+        return self._l.emul_storage_pack_records(s, None, 0, records)
+
+    def gr_storage_pack_records_permuted(self, s, perm, num, records, stream):
+        return self._l.emul_storage_pack_records(s, perm, num, records)
 
     def gr_uav_collision_ray(self, mesh, pos, quat, n, lattices, num_lattices, max_dist, arm, height, out, stream):
         return self._l.emul_uav_collision_ray(mesh, pos, quat, n, lattices, num_lattices, max_dist, arm, height, out)

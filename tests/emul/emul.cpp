@@ -154,6 +154,13 @@ int emul_storage_gather(const GrStorage* s, const int64_t* indices, int32_t B, c
   return 0;
 }
 
+int emul_storage_pack_records(const GrStorage* s, const int64_t* perm, int64_t num, float* records) {
+  const int64_t rows = perm ? num : (int64_t)s->T * s->N;
+  if (rows < 1 || rows > (int64_t)s->T * s->N) return GR_ERR_SIZE;
+  run_grid(rows * 12, [&] { storage_pack_records_kernel(*s, perm, reinterpret_cast<float4*>(records), rows); });
+  return 0;
+}
+
 int emul_uav_collision_ray(const GrMesh* mesh, const float* pos, const float* quat, int32_t n, const float* lattices, int32_t num_lattices, float max_dist,
                            float arm_length, float height, int32_t* out) {
   std::memset(out, 0, sizeof(int32_t) * (size_t)n);

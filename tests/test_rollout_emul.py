@@ -81,3 +81,32 @@ def test_gather_rows_are_the_indexed_rows(emul_lib):
         rows = idx[i * 100:(i + 1) * 100]
         for k, name in enumerate(flat):
             assert torch.equal(batch[k], flat[name][rows]), name
+
+
+def test_transition_records_plain_and_in_mini_batch_order(emul_lib):
+    """gr_storage_pack_records / _permuted (csrc/rollout.cu, emulated): record r = the nine columns of transition r (or perm[r]) side by
+    side, so that mini-batch i of every epoch of rollout_storage.py:165-178 is the contiguous record slice [i*mb, (i+1)*mb) -- the rows the
+    reference's generator yields for that mini-batch, in its order."""
+    from generalizableracing_b200 import _lib as B
+    T, N, nmb = 6, 50, 3
+    sto = _run(emul_lib, T, N, 16, 16, seed=11, use_reference=False)
+    cols = [getattr(sto, k).flatten(0, 1) for k in ("observations", "privileged_observations", "actions", "mu", "sigma", "actions_log_prob", "advantages",
+                                                    "returns", "values")]
+    want = torch.cat([c.reshape(T * N, -1) for c in cols], dim=1)
+    rec = sto.pack_records().clone()
+    assert rec.shape == (T * N, B.GR_RECORD_FLOATS) and torch.equal(rec, want)
+    perm = torch.randperm(T * N, generator=torch.Generator().manual_seed(2))
+    rec_p = sto.pack_records(perm).clone()
+    assert torch.equal(rec_p, want[perm])
+    mb = T * N // nmb
+    for i, batch in enumerate(sto.mini_batch_generator(nmb, 1, indices=perm)):          # (obs, critic, actions, values, advantages, returns, logp, mu, sigma, ...)
+        sl = rec_p[i * mb:(i + 1) * mb]
+        assert torch.equal(sl[:, 0:16], batch[0]) and torch.equal(sl[:, 16:32], batch[1]) and torch.equal(sl[:, 32:36], batch[2])
+        assert torch.equal(sl[:, 36:40], batch[7]) and torch.equal(sl[:, 40:44], batch[8])
+        assert torch.equal(sl[:, 44:45], batch[6].reshape(-1, 1)) and torch.equal(sl[:, 45:46], batch[4].reshape(-1, 1))
+        assert torch.equal(sl[:, 46:47], batch[5].reshape(-1, 1)) and torch.equal(sl[:, 47:48], batch[3].reshape(-1, 1))
+    # a prefix of the permutation packs only that many records
+    sto._records.fill_(-7.0)
+    k = 100
+    rec_k = sto.pack_records(perm[:k].contiguous())
+    assert torch.equal(rec_k[:k], want[perm[:k]]) and bool((rec_k[k:] == -7.0).all())
